@@ -1,0 +1,315 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under binius_b200/ may import this module.
+
+B128 vectors are numpy uint64 arrays of shape (n, 2): [:, 0] = low 64 bits, [:, 1] = high 64 bits
+(the little-endian u128 layout of BinaryField128b, reference crates/field/src/binary_field.rs:115-133).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+INPUT_VALIDATION = 1
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        super().__init__(f"oracle error code {code}")
+        self.code = code
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+    return _LIB
+
+
+# ------------------------------------------------------------------------------------------------
+# conversions
+def to_arr(vals) -> np.ndarray:
+    """list of python ints (< 2^128) -> (n,2) uint64"""
+    a = np.empty((len(vals), 2), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        a[i, 0] = v & 0xFFFFFFFFFFFFFFFF
+        a[i, 1] = v >> 64
+    return a
+
+
+def to_ints(arr) -> list:
+    arr = np.asarray(arr, dtype=np.uint64).reshape(-1, 2)
+    return [int(lo) | (int(hi) << 64) for lo, hi in arr]
+
+
+def one(v: int) -> np.ndarray:
+    return to_arr([v])
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.ndim == 2 and a.shape[1] == 2
+    return a
+
+
+def _check(rc):
+    if rc != 0:
+        raise OracleError(rc)
+
+
+class ExprStep(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("l", C.c_uint32), ("r", C.c_uint64), ("c_lo", C.c_uint64), ("c_hi", C.c_uint64)]
+
+
+def encode_expr(steps):
+    """steps: list of ('add',l,r) | ('mul',l,r) | ('pow',l,e) | ('const',c) | ('var',i)"""
+    arr = (ExprStep * max(len(steps), 1))()
+    for i, st in enumerate(steps):
+        k = st[0]
+        if k == "add":
+            arr[i] = ExprStep(0, st[1], st[2], 0, 0)
+        elif k == "mul":
+            arr[i] = ExprStep(1, st[1], st[2], 0, 0)
+        elif k == "pow":
+            arr[i] = ExprStep(2, st[1], st[2], 0, 0)
+        elif k == "const":
+            arr[i] = ExprStep(3, 0, 0, st[1] & 0xFFFFFFFFFFFFFFFF, st[1] >> 64)
+        elif k == "var":
+            arr[i] = ExprStep(4, st[1], 0, 0, 0)
+        else:
+            raise ValueError(k)
+    return arr
+
+
+def expr_n_vars(steps):
+    return 1 + max([st[1] for st in steps if st[0] == "var"], default=-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# scalar field ops (python ints)
+def _scalar2(fn, a, b, k):
+    out = one(0)
+    getattr(lib(), fn)(_p(one(a)), _p(one(b)), C.c_uint32(k), _p(out))
+    return to_ints(out)[0]
+
+
+def _scalar1(fn, a, k):
+    out = one(0)
+    getattr(lib(), fn)(_p(one(a)), C.c_uint32(k), _p(out))
+    return to_ints(out)[0]
+
+
+def mul(a, b, k=7):
+    return _scalar2("orc_mul", a, b, k)
+
+
+def mul_slow(a, b, k=7):
+    return _scalar2("orc_mul_slow", a, b, k)
+
+
+def mul_subfield(a, s, k):
+    return _scalar2("orc_mul_subfield", a, s, k)
+
+
+def square(a, k=7):
+    return _scalar1("orc_square", a, k)
+
+
+def invert(a, k=7):
+    return _scalar1("orc_invert", a, k)
+
+
+def mul_alpha(a, k=7):
+    return _scalar1("orc_mul_alpha", a, k)
+
+
+def pow_(a, e, k=7):
+    r = 1
+    while e:
+        if e & 1:
+            r = mul(r, a, k)
+        a = mul(a, a, k)
+        e >>= 1
+    return r
+
+
+def mul_vec(a, b):
+    a, b = _c(a), _c(b)
+    out = np.empty_like(a)
+    lib().orc_mul_vec(_p(a), _p(b), _p(out), C.c_uint64(len(a)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# ComputeLayer ops
+def extrapolate_line(e0, e1, z: int):
+    e0 = _c(e0).copy()
+    e1 = _c(e1)
+    if len(e0) != len(e1):
+        raise OracleError(INPUT_VALIDATION)
+    _check(lib().orc_extrapolate_line(_p(e0), _p(e1), C.c_uint64(len(e0)), _p(one(z))))
+    return e0
+
+
+def tensor_expand(data, log_n: int, coords):
+    data = _c(data).copy()
+    cs = to_arr(list(coords)) if len(coords) else np.zeros((1, 2), np.uint64)
+    _check(lib().orc_tensor_expand(_p(data), C.c_uint64(len(data)), C.c_uint32(log_n), _p(cs), C.c_uint32(len(coords))))
+    return data
+
+
+def inner_product(a, lvl: int, b) -> int:
+    a, b = _c(a), _c(b)
+    out = one(0)
+    _check(lib().orc_inner_product(_p(a), C.c_uint64(len(a)), C.c_uint32(lvl), _p(b), C.c_uint64(len(b)), _p(out)))
+    return to_ints(out)[0]
+
+
+def _fold(fn, mat, lvl, vec, n_out):
+    mat, vec = _c(mat), _c(vec)
+    out = np.zeros((n_out, 2), np.uint64)
+    _check(getattr(lib(), fn)(_p(mat), C.c_uint64(len(mat)), C.c_uint32(lvl), _p(vec), C.c_uint64(len(vec)), _p(out), C.c_uint64(n_out)))
+    return out
+
+
+def fold_left(mat, lvl, vec, n_out):
+    return _fold("orc_fold_left", mat, lvl, vec, n_out)
+
+
+def fold_right(mat, lvl, vec, n_out):
+    return _fold("orc_fold_right", mat, lvl, vec, n_out)
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def compute_composite(inputs, steps, n_out=None):
+    inputs = [_c(a) for a in inputs]
+    row_len = len(inputs[0]) if inputs else 0
+    n_out = row_len if n_out is None else n_out
+    out = np.zeros((n_out, 2), np.uint64)
+    enc = encode_expr(steps)
+    _check(lib().orc_compute_composite(_ptr_array(inputs), C.c_uint32(len(inputs)), C.c_uint64(row_len), _p(out),
+                                       C.c_uint64(n_out), enc, C.c_uint32(len(steps)), C.c_uint32(expr_n_vars(steps))))
+    return out
+
+
+def sum_composition_evals(inputs, steps, batch_coeff: int, acc: int) -> int:
+    inputs = [_c(a) for a in inputs]
+    accv = one(acc)
+    enc = encode_expr(steps)
+    _check(lib().orc_sum_composition_evals(_ptr_array(inputs), C.c_uint32(len(inputs)), C.c_uint64(len(inputs[0])), enc,
+                                           C.c_uint32(len(steps)), _p(one(batch_coeff)), _p(accv)))
+    return to_ints(accv)[0]
+
+
+def pairwise_product_reduce(inp, out_lens=None):
+    inp = _c(inp)
+    n = len(inp)
+    if out_lens is None:
+        out_lens = [n >> (r + 1) for r in range(max(n.bit_length() - 1, 0))]
+    outs = [np.zeros((max(l, 1), 2), np.uint64)[:l] for l in out_lens]
+    bufs = [np.ascontiguousarray(o) if len(o) else np.zeros((1, 2), np.uint64) for o in outs]
+    lens = (C.c_uint64 * max(len(out_lens), 1))(*out_lens)
+    _check(lib().orc_pairwise_product_reduce(_p(inp), C.c_uint64(n), _ptr_array(bufs) if bufs else None, lens, C.c_uint32(len(out_lens))))
+    return [b[:l] for b, l in zip(bufs, out_lens)]
+
+
+def bivariate_round_evals(multilins, n_vars, pairs, batch_coeff: int):
+    multilins = [_c(m) for m in multilins]
+    ia = (C.c_uint32 * len(pairs))(*[p[0] for p in pairs])
+    ib = (C.c_uint32 * len(pairs))(*[p[1] for p in pairs])
+    out = np.zeros((2, 2), np.uint64)
+    _check(lib().orc_bivariate_round_evals(_ptr_array(multilins), C.c_uint32(len(multilins)), C.c_uint32(n_vars), ia, ib,
+                                           C.c_uint32(len(pairs)), _p(one(batch_coeff)), _p(out)))
+    return to_ints(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# additive NTT
+_NP_DT = {3: np.uint8, 4: np.uint16, 5: np.uint32, 6: np.uint64}
+
+
+class NTT:
+    """AdditiveNTT over T_kt with the standard subspace <1,2,4,...> of dimension d
+    (reference: SingleThreadedNTT::new(log_domain_size), ntt/src/single_threaded.rs:27-45)."""
+
+    def __init__(self, kt: int, d: int):
+        self.kt, self.d = kt, d
+        self.s = np.zeros((max(d * max(d - 1, 1), 1), 2), np.uint64)
+        _check(lib().orc_ntt_s_evals(C.c_uint32(kt), C.c_uint32(d), _p(self.s)))
+
+    def s_evals(self):
+        """list of rows (python ints)"""
+        W = self.d - 1
+        flat = to_ints(self.s)
+        return [flat[r * W: r * W + (self.d - 1 - r)] for r in range(self.d)]
+
+    def get_subspace_eval(self, i: int, j: int) -> int:
+        out = one(0)
+        _check(lib().orc_ntt_get_subspace_eval(_p(self.s), C.c_uint32(self.d), C.c_uint32(i), C.c_uint64(j), _p(out)))
+        return to_ints(out)[0]
+
+    def _tr(self, inverse, data, kd, log_x, log_y, log_z, coset, coset_bits, skip_rounds):
+        data = np.ascontiguousarray(data).copy()
+        n_elems = data.shape[0]
+        _check(lib().orc_ntt_transform(C.c_int(inverse), _p(self.s), C.c_uint32(self.kt), C.c_uint32(self.d), _p(data),
+                                       C.c_uint32(kd), C.c_uint64(n_elems), C.c_uint32(log_x), C.c_uint32(log_y),
+                                       C.c_uint32(log_z), C.c_uint64(coset), C.c_uint32(coset_bits), C.c_uint32(skip_rounds)))
+        return data
+
+    def forward(self, data, kd, log_x=0, log_y=None, log_z=0, coset=0, coset_bits=0, skip_rounds=0):
+        if log_y is None:
+            log_y = (data.shape[0]).bit_length() - 1 - log_x - log_z
+        return self._tr(0, data, kd, log_x, log_y, log_z, coset, coset_bits, skip_rounds)
+
+    def inverse(self, data, kd, log_x=0, log_y=None, log_z=0, coset=0, coset_bits=0, skip_rounds=0):
+        if log_y is None:
+            log_y = (data.shape[0]).bit_length() - 1 - log_x - log_z
+        return self._tr(1, data, kd, log_x, log_y, log_z, coset, coset_bits, skip_rounds)
+
+    def fri_fold(self, log_len, log_batch, challenges, data_in, n_out):
+        data_in = _c(data_in)
+        ch = to_arr(list(challenges)) if len(challenges) else np.zeros((1, 2), np.uint64)
+        out = np.zeros((max(n_out, 1), 2), np.uint64)
+        _check(lib().orc_fri_fold(_p(self.s), C.c_uint32(self.kt), C.c_uint32(self.d), C.c_uint32(log_len),
+                                  C.c_uint32(log_batch), _p(ch), C.c_uint32(len(challenges)), _p(data_in),
+                                  C.c_uint64(len(data_in)), _p(out), C.c_uint64(n_out)))
+        return out[:n_out]
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic inputs: SplitMix64 (documented generator of SURVEY.md 8d; the reference's rand 0.9
+# ChaCha12 StdRng is not available outside Rust and the reference stores no golden op outputs)
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        out[:] = z ^ (z >> np.uint64(31))
+    return out
+
+
+def rand_b128(seed: int, n: int) -> np.ndarray:
+    return splitmix64(seed, 2 * n).reshape(n, 2)
