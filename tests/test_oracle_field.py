@@ -184,3 +184,9 @@ def test_polyval_kats_pin_b128_mul(oracle, kat):
     # the POLYVAL KAT itself, pulled back to the tower: tower(a)*tower(b) == tower(c)
     ta, tb, tc = (_lin(p2b, new(x)) for x in (a, b, c))
     assert oracle.mul(ta, tb, 7) == tc
+
+
+def test_generator_maps_to_polyval_generator(oracle, kat):
+    # binary_field.rs:747 and polyval.rs:496 are related by the basis change (polyval.rs:516-648)
+    b2p = [int(x, 16) for x in kat["binary_to_polyval"]]
+    assert _lin(b2p, kat["generators"]["128"]) == int(kat["polyval_generator"], 16)
