@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py -- headline measurement of the hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-coeffs 24]
+
+A "step" = one fold-high (sumcheck fold / extrapolate_line) over one multilinear
+of 2^24 GF(2^128) input coefficients per GPU (256 MiB read, 128 MiB written: larger than the 126 MB
+L2, so no flush is needed between steps).  `value` = coefficients/s over all ranks with inputs resident
+in HBM; `e2e` = the same metric through the plugin API with HOST buffers (copy_h2d + fold + copy_d2h
+inside the timed region).  The additive-NTT numbers (BASELINE config #2) ride along under "ntt".
+N > 1: one process per GPU (torchrun), independent multilinears per rank (weak scaling, no data-path
+collective); the only collective is the timing max-reduce.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sumcheck_fold_high_gf2_128_coeffs_per_s"
+UNIT = "coeffs/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[1]))
+                mx = float(p[2])
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class Ev:
+    """CUDA events on the library's own stream (torch.cuda.Event would only see torch's stream)."""
+
+    def __init__(self, hal):
+        self.hal = hal
+        self.a, self.b = C.c_void_p(), C.c_void_p()
+        hal._check(hal._lib.b200_event_create(hal._ctx, C.byref(self.a)))
+        hal._check(hal._lib.b200_event_create(hal._ctx, C.byref(self.b)))
+
+    def start(self):
+        self.hal._check(self.hal._lib.b200_event_record(self.hal._ctx, self.a))
+
+    def stop_ms(self):
+        self.hal._check(self.hal._lib.b200_event_record(self.hal._ctx, self.b))
+        ms = C.c_float()
+        self.hal._check(self.hal._lib.b200_event_elapsed_ms(self.hal._ctx, self.a, self.b, C.byref(ms)))
+        return float(ms.value)
+
+
+def cpu_fold_baseline(log_coeffs, budget_s=12.0):
+    """CPU arm: the oracle's restatement of the reference fold loop (fold_left_lerp_inplace /
+    extrapolate_line), timed on the host cores of this box on a bounded sample."""
+    from oracle import binding as orc
+
+    orc.lib()
+    cores = os.cpu_count() or 1
+    if hasattr(orc, "cpu_fold_parallel"):
+        return orc.cpu_fold_parallel(log_coeffs, budget_s)
+    log_s = min(log_coeffs, 18)
+    n = 1 << (log_s - 1)
+    e0, e1 = orc.rand_b128(0, n), orc.rand_b128(1, n)
+    z = 0x2E895399AF449ACE499596F6E5FCCAFA
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        orc.extrapolate_line(e0, e1, z)
+        reps += 1
+        if time.perf_counter() - t0 > min(budget_s, 3.0):
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (2 * n) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"2^{log_s} coefficients x {reps} reps, scalar oracle (host has {cores} cores)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    ms = []
+    base = None
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        base = cpu_fold_baseline(args.log_coeffs, budget_s=8.0)
+        if s >= args.warmup:
+            ms.append((time.perf_counter() - t0) * 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u128 (GF(2^128) tower)", "data": "synthetic",
+            "config": {"workload": f"fold-high over BinaryField128b, 2^{args.log_coeffs} coefficients (bounded CPU sample)"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--log-coeffs", type=int, default=24)
+    ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import binius_b200
+    from binius_b200 import NTTShape
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hal = binius_b200.B200Layer(local_rank)
+    peak, peak_src = peaks()
+
+    # ---- synthetic multilinear: 2^log_coeffs B128 coefficients (SplitMix64, seed = rank) ----------
+    n_in = 1 << args.log_coeffs
+    half = n_in // 2
+    rng = np.random.default_rng(rank)
+    host = rng.integers(0, 1 << 63, size=(n_in, 2), dtype=np.int64).astype(np.uint64)
+    ph = C.c_void_p()
+    hal._check(hal._lib.b200_host_alloc(hal._ctx, n_in * 16, C.byref(ph)))
+    pinned = np.ctypeslib.as_array((C.c_uint64 * (2 * n_in)).from_address(ph.value)).reshape(n_in, 2)
+    pinned[:] = host
+    dev = hal.dev_alloc(n_in)
+    hal._check(hal._lib.b200_copy_h2d(hal._ctx, ph.value, dev.ptr, n_in))
+    lo, hi = dev.split_half_mut()
+    z = 0x2E895399AF449ACE499596F6E5FCCAFA
+    zs = (C.c_uint64 * 2)(z & (2**64 - 1), z >> 64)
+
+    def fold_step():
+        hal._check(hal._lib.b200_extrapolate_line(hal._ctx, lo.ptr, half, hi.ptr, half, zs))
+
+    def barrier():
+        hal.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    ev = Ev(hal)
+    for _ in range(args.warmup):
+        fold_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    l0 = hal.launch_count()
+    t0 = time.time()
+    ev.start()
+    for _ in range(args.steps):
+        fold_step()
+    ms_total = ev.stop_ms()
+    barrier()
+    t1 = time.time()
+    launches = hal.launch_count() - l0
+
+    # per-launch duration of the dominant kernel (k_lerp_lut), CUDA events around single launches
+    kern_ms = []
+    for _ in range(min(args.steps, 10)):
+        hal._check(hal._lib.b200_sync(hal._ctx))
+        ev.start()
+        fold_step()
+        kern_ms.append(ev.stop_ms())
+    kern_ms_avg = float(np.mean(kern_ms))
+
+    # ---- e2e: host buffers through the plugin API (copy_h2d + fold + copy_d2h of the folded half) --
+    out_host = np.empty((half, 2), dtype=np.uint64)
+    po = C.c_void_p()
+    hal._check(hal._lib.b200_host_alloc(hal._ctx, half * 16, C.byref(po)))
+    e2e_steps = max(3, min(args.steps, 5))
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hal._check(hal._lib.b200_copy_h2d(hal._ctx, ph.value, dev.ptr, n_in))
+        fold_step()
+        hal._check(hal._lib.b200_copy_d2h(hal._ctx, lo.ptr, po.value, half))
+    barrier()
+    e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
+    clocks = sampler.stop(t0, t1)
+
+    # ---- NTT (BASELINE config #2): B32, 2^24 coefficients, S1/S2/S3 shapes ------------------------
+    ntt_res = None
+    if not args.no_ntt:
+        ntt = binius_b200.B200AdditiveNTT(hal, 5, 24)
+        n32 = 1 << 24
+        ntt_res = {}
+        for name, (lx, ly, lz, skip) in {"S1_rs_encode": (6, 18, 0, 1), "S2_single": (0, 24, 0, 0), "S3_batch": (0, 16, 8, 0)}.items():
+            S = NTTShape(lx, ly, lz)
+            for _ in range(2):
+                ntt.forward_device(dev.ptr, 5, n32, S, 0, 0, skip)
+            hal.sync()
+            c0 = hal.launch_count()
+            ev.start()
+            reps = 5
+            for _ in range(reps):
+                ntt.forward_device(dev.ptr, 5, n32, S, 0, 0, skip)
+            fwd_ms = ev.stop_ms() / reps
+            passes = (hal.launch_count() - c0) // reps
+            ev.start()
+            for _ in range(reps):
+                ntt.inverse_device(dev.ptr, 5, n32, S, 0, 0, skip)
+            inv_ms = ev.stop_ms() / reps
+            ntt_res[name] = {"fwd_ms": fwd_ms, "inv_ms": inv_ms, "coeffs_per_s": n32 / (fwd_ms * 1e-3), "passes": passes,
+                             "roofline_frac": (8 * n32 / (fwd_ms * 1e-3)) / (peak * 1e9)}
+
+    # ---- reduce over ranks: max time ----------------------------------------------------------------
+    ms_step = ms_total / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms, kern_ms_avg], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms, kern_ms_avg = [float(x) for x in t.tolist()]
+    if rank == 0:
+        value = world * n_in / (ms_step * 1e-3)
+        achieved = 24.0 * n_in / (kern_ms_avg * 1e-3) / 1e9  # algorithmic bytes: 16 B read + 8 B written per coefficient
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u128 (GF(2^128) tower, integer/bitwise)", "data": "synthetic",
+            "config": {"workload": f"fold-high (extrapolate_line) over BinaryField128b, 2^{args.log_coeffs} coefficients per GPU",
+                       "l2_policy": "inputs (256 MiB) larger than L2; no flush", "parallelism": f"independent multilinears x{world}"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": world * n_in / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_in * 16, "d2h_bytes_per_step": half * 16,
+                    "ms_per_step": e2e_ms},
+            "roofline": {"bound": "hbm", "kernel": "k_lerp_lut", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "kernel_ms": kern_ms_avg},
+        }
+        if ntt_res:
+            line["ntt"] = ntt_res
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_fold_baseline(args.log_coeffs)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    hal.close()
+
+
+if __name__ == "__main__":
+    main()

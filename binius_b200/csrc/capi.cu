@@ -1,0 +1,756 @@
+// capi.cu -- C ABI (include/binius_b200.h): validation + kernel launches.  No CPU fallback: every
+// compute entry point launches sm_100a kernels on the context's stream or fails.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+#include "context.hpp"
+#include "host_field.hpp"
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+using namespace b200;
+
+struct b200_expr {
+	std::vector<b200_expr_step> steps;
+	b200_expr_step *d_steps = nullptr;
+	uint32_t n_vars = 0;
+};
+
+struct b200_ntt {
+	uint32_t kt = 5, d = 0;
+	std::vector<std::vector<uint64_t>> s_evals;  // rows (host), values < 2^(2^kt)
+	uint32_t *d_s_evals = nullptr;               // device [32][32]
+};
+
+namespace b200 {
+
+int32_t stage_args(b200_ctx *ctx, const void *host, uint64_t bytes, void **dev_out) {
+	uint64_t need = (bytes + 255) & ~255ull;
+	if (need > ARGS_BYTES) return fail(ctx, B200_ERR_ALLOC, "argument block of %llu bytes too large", (unsigned long long)bytes);
+	if (ctx->args_off + need > ARGS_BYTES) {
+		B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		ctx->args_off = 0;
+	}
+	memcpy(ctx->h_args + ctx->args_off, host, bytes);
+	B200_CUDA(ctx, cudaMemcpyAsync(ctx->d_args + ctx->args_off, ctx->h_args + ctx->args_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	*dev_out = ctx->d_args + ctx->args_off;
+	ctx->args_off += need;
+	return B200_OK;
+}
+
+int32_t ensure_scratch(b200_ctx *ctx, uint64_t bytes) {
+	if (bytes <= ctx->scratch_bytes) return B200_OK;
+	if (ctx->d_scratch) {
+		B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_scratch);
+		ctx->d_scratch = nullptr;
+		ctx->scratch_bytes = 0;
+	}
+	if (cudaMalloc(&ctx->d_scratch, bytes) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(ctx, B200_ERR_ALLOC, "out of device memory (scratch %llu bytes)", (unsigned long long)bytes);
+	}
+	ctx->scratch_bytes = bytes;
+	return B200_OK;
+}
+
+static uint32_t grid_for(const b200_ctx *ctx, uint64_t n, uint32_t threads, uint32_t per_sm) {
+	uint64_t blocks = (n + threads - 1) / threads;
+	uint64_t cap = (uint64_t)ctx->n_sms * per_sm;
+	return (uint32_t)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+static int32_t new_slot(b200_ctx *ctx, uint32_t *slot) {
+	if (ctx->n_results >= MAX_RESULTS) return fail(ctx, B200_ERR_ALLOC, "out of result slots");
+	*slot = ctx->n_results++;
+	return B200_OK;
+}
+
+template <typename K>
+static int32_t set_smem(b200_ctx *ctx, K kernel, uint32_t bytes) {
+	B200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	return B200_OK;
+}
+
+}  // namespace b200
+
+// =================================================================================================
+extern "C" {
+
+int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
+	if (!out) return B200_ERR_INPUT_VALIDATION;
+	*out = nullptr;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+		cudaGetLastError();
+		return B200_ERR_DEVICE;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B200_ERR_DEVICE;
+	if (prop.major != 10) return B200_ERR_DEVICE;  // sm_100a only: there is no other code path
+	std::unique_ptr<b200_ctx> ctx(new b200_ctx);
+	ctx->device = device;
+	ctx->n_sms = prop.multiProcessorCount;
+	if (cudaSetDevice(device) != cudaSuccess) return B200_ERR_DEVICE;
+	if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return B200_ERR_DEVICE;
+	ctx->stream = ctx->own_stream;
+	bool ok = cudaMalloc(&ctx->d_tables, FIELD_TABLE_BYTES) == cudaSuccess &&
+			  cudaMalloc(&ctx->d_basis, sizeof(uint4) * 128 * MAX_LINMAPS) == cudaSuccess &&
+			  cudaMalloc(&ctx->d_results, sizeof(uint4) * MAX_RESULTS) == cudaSuccess &&
+			  cudaMalloc(&ctx->d_args, ARGS_BYTES) == cudaSuccess && cudaMallocHost(&ctx->h_args, ARGS_BYTES) == cudaSuccess;
+	if (!ok) return B200_ERR_ALLOC;
+	// 8-bit tables from the bit-level tower recursion (host_field.hpp)
+	std::vector<uint8_t> tables(FIELD_TABLE_BYTES);
+	for (int a = 0; a < 256; a++) {
+		for (int b = a; b < 256; b++) {
+			uint8_t p = (uint8_t)hostf::Tw<3>::mul((hostf::u128)a, (hostf::u128)b);
+			tables[(a << 8) | b] = p;
+			tables[(b << 8) | a] = p;
+		}
+		tables[65536 + a] = (uint8_t)hostf::Tw<3>::mul_alpha((hostf::u128)a);
+	}
+	if (cudaMemcpy(ctx->d_tables, tables.data(), FIELD_TABLE_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) return B200_ERR_DEVICE;
+	if (cudaMemset(ctx->d_results, 0, sizeof(uint4) * MAX_RESULTS) != cudaSuccess) return B200_ERR_DEVICE;
+	b200_ctx *c = ctx.get();
+	// opt in to large dynamic shared memory once
+	int32_t rc = B200_OK;
+#define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
+	SET(k_basis_products, FIELD_TABLE_BYTES);
+	SET(k_lerp_lut, LUT_BYTES + 2048);
+	SET(k_expand_lut, LUT_BYTES + 2048);
+	SET(k_expand_small, FIELD_TABLE_BYTES + 16 * 2048);
+	SET(k_inner_product, FIELD_TABLE_BYTES);
+	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
+	SET(k_fold_mat<true>, FIELD_TABLE_BYTES);
+	SET(k_compute_composite, FIELD_TABLE_BYTES);
+	SET(k_sum_composition, FIELD_TABLE_BYTES);
+	SET(k_pairwise_product, FIELD_TABLE_BYTES);
+	SET(k_bivariate_round_evals, FIELD_TABLE_BYTES);
+	SET(k_eq_ind_round_evals, FIELD_TABLE_BYTES);
+	SET(k_fri_fold, FIELD_TABLE_BYTES);
+	SET(k_ntt_pass<uint32_t>, FIELD_TABLE_BYTES + 4 * 8192 + 4 * 8192);
+	SET(k_ntt_pass<uint16_t>, FIELD_TABLE_BYTES + 4 * 8192 + 2 * 8192);
+	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
+#undef SET
+	if (rc != B200_OK) return rc;
+	*out = ctx.release();
+	return B200_OK;
+}
+
+void b200_ctx_destroy(b200_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->d_tables);
+	cudaFree(ctx->d_basis);
+	cudaFree(ctx->d_results);
+	cudaFree(ctx->d_args);
+	cudaFreeHost(ctx->h_args);
+	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+	cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+}
+
+const char *b200_last_error(b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *b200_ctx_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t b200_ctx_launch_count(b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t b200_ctx_set_stream(b200_ctx *ctx, void *s) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+	return B200_OK;
+}
+int32_t b200_event_create(b200_ctx *ctx, void **out) {
+	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
+	cudaEvent_t e;
+	B200_CUDA(ctx, cudaEventCreate(&e));
+	*out = e;
+	return B200_OK;
+}
+int32_t b200_event_record(b200_ctx *ctx, void *e) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaEventRecord((cudaEvent_t)e, ctx->stream));
+	return B200_OK;
+}
+int32_t b200_event_elapsed_ms(b200_ctx *ctx, void *a, void *b, float *ms) {
+	if (!ctx || !ms) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)b));
+	B200_CUDA(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+	return B200_OK;
+}
+void b200_event_destroy(void *e) {
+	if (e) cudaEventDestroy((cudaEvent_t)e);
+}
+
+int32_t b200_dev_alloc(b200_ctx *ctx, uint64_t n_elems, b200_dev_ptr *out) {
+	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
+	cudaSetDevice(ctx->device);
+	void *p = nullptr;
+	if (cudaMalloc(&p, std::max<uint64_t>(n_elems, 1) * 16) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(ctx, B200_ERR_ALLOC, "out of device memory allocating %llu elements", (unsigned long long)n_elems);
+	}
+	*out = p;
+	return B200_OK;
+}
+int32_t b200_dev_free(b200_ctx *ctx, b200_dev_ptr p) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	B200_CUDA(ctx, cudaFree(p));
+	return B200_OK;
+}
+int32_t b200_host_alloc(b200_ctx *ctx, uint64_t n_bytes, void **out) {
+	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
+	if (cudaMallocHost(out, std::max<uint64_t>(n_bytes, 1)) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(ctx, B200_ERR_ALLOC, "out of pinned host memory");
+	}
+	return B200_OK;
+}
+int32_t b200_host_free(b200_ctx *ctx, void *p) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaFreeHost(p));
+	return B200_OK;
+}
+
+int32_t b200_copy_h2d(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t n) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n == 0) return B200_OK;
+	B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+	// pageable sources are staged synchronously by the runtime; pinned ones stay async
+	return B200_OK;
+}
+int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *dst, uint64_t n) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n) B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return B200_OK;
+}
+int32_t b200_copy_d2d(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n) B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+	return B200_OK;
+}
+int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n, const uint64_t value[2]) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n == 0) return B200_OK;
+	k_fill<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((uint4 *)dst, n, to_u4(value));
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+int32_t b200_sync(b200_ctx *ctx) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return B200_OK;
+}
+
+int32_t b200_results_reset(b200_ctx *ctx) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (ctx->n_results) B200_CUDA(ctx, cudaMemsetAsync(ctx->d_results, 0, sizeof(uint4) * ctx->n_results, ctx->stream));
+	ctx->n_results = 0;
+	return B200_OK;
+}
+int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uint64_t *host_out) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n == 0) {
+		B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return B200_OK;
+	}
+	uint32_t hi = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		if (slots[i] >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "result slot %u out of range", slots[i]);
+		hi = std::max(hi, slots[i]);
+	}
+	std::vector<uint64_t> tmp(2 * (size_t)(hi + 1));
+	B200_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->d_results, 16 * (size_t)(hi + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (uint32_t i = 0; i < n; i++) {
+		host_out[2 * i] = tmp[2 * slots[i]];
+		host_out[2 * i + 1] = tmp[2 * slots[i] + 1];
+	}
+	return B200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+static int32_t launch_basis(b200_ctx *ctx, const uint64_t *zs, uint32_t n_maps) {
+	if (n_maps > MAX_LINMAPS) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many linear maps in one call (%u)", n_maps);
+	std::vector<uint4> h(n_maps);
+	for (uint32_t i = 0; i < n_maps; i++) h[i] = to_u4(zs + 2 * i);
+	void *dz;
+	int32_t rc = stage_args(ctx, h.data(), sizeof(uint4) * n_maps, &dz);
+	if (rc) return rc;
+	k_basis_products<<<n_maps, 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)dz, ctx->d_basis);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint64_t z[2]) {
+	uint64_t tiles = 0;
+	std::vector<LerpSeg> live;
+	for (auto &s : segs) {
+		if (s.upper == 0) continue;
+		s.tile_start = tiles;
+		tiles += (s.upper + FOLD_TILE - 1) / FOLD_TILE;
+		live.push_back(s);
+	}
+	if (live.empty()) return B200_OK;
+	int32_t rc = launch_basis(ctx, z, 1);
+	if (rc) return rc;
+	void *dsegs;
+	rc = stage_args(ctx, live.data(), sizeof(LerpSeg) * live.size(), &dsegs);
+	if (rc) return rc;
+	uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * 3);
+	k_lerp_lut<<<grid, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const LerpSeg *)dsegs, (uint32_t)live.size(), tiles, ctx->d_basis);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_dev_ptr e1, uint64_t n1, const uint64_t z[2]) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n0 != n1) return fail(ctx, B200_ERR_INPUT_VALIDATION, "evals_0 and evals_1 must be the same length");
+	std::vector<LerpSeg> segs(1);
+	segs[0] = LerpSeg{(uint4 *)e0, (const uint4 *)e1, n0, n0, make_uint4(0, 0, 0, 0), 0};
+	return launch_lerp(ctx, segs, z);
+}
+
+int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars,
+										   const uint64_t *prefix, const uint64_t *suffix, const uint64_t z[2], uint64_t *new_lens) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
+	uint64_t half = 1ull << (n_vars - 1);
+	std::vector<LerpSeg> segs(m);
+	for (uint32_t t = 0; t < m; t++) {
+		uint64_t p = prefix[t];
+		if (p > 2 * half) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: prefix %llu exceeds 2^n_vars", t, (unsigned long long)p);
+		uint64_t pivot = p > half ? p - half : 0;
+		uint64_t upper = std::min(p, half);
+		uint4 *e0 = (uint4 *)mls[t];
+		segs[t] = LerpSeg{e0, e0 + half, pivot, upper, to_u4(suffix + 2 * t), 0};
+		if (new_lens) new_lens[t] = upper;
+	}
+	return launch_lerp(ctx, segs, z);
+}
+
+int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, uint32_t log_n, const uint64_t *coords, uint32_t k) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (log_n + k > 60 || data_len != (1ull << (log_n + k))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data length: %llu", (unsigned long long)data_len);
+	if (k == 0) return B200_OK;
+	// rounds that fit one CTA's shared memory
+	uint32_t k_small = 0;
+	if (log_n <= 11) k_small = std::min(k, 11 - log_n);
+	if (k_small) {
+		std::vector<uint4> h(k_small);
+		for (uint32_t i = 0; i < k_small; i++) h[i] = to_u4(coords + 2 * i);
+		void *dc;
+		int32_t rc = stage_args(ctx, h.data(), sizeof(uint4) * k_small, &dc);
+		if (rc) return rc;
+		k_expand_small<<<1, 256, FIELD_TABLE_BYTES + (16u << (log_n + k_small)), ctx->stream>>>(ctx->d_tables, (uint4 *)data, log_n, (const uint4 *)dc, k_small);
+		B200_LAUNCH_CHECK(ctx);
+	}
+	for (uint32_t r0 = k_small; r0 < k; r0 += MAX_LINMAPS) {
+		uint32_t cnt = std::min(MAX_LINMAPS, k - r0);
+		int32_t rc = launch_basis(ctx, coords + 2 * r0, cnt);
+		if (rc) return rc;
+		for (uint32_t r = r0; r < r0 + cnt; r++) {
+			uint64_t half = 1ull << (log_n + r);
+			uint64_t tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
+			uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * 3);
+			k_expand_lut<<<grid, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((uint4 *)data, half, ctx->d_basis + 128 * (r - r0));
+			B200_LAUNCH_CHECK(ctx);
+		}
+	}
+	return B200_OK;
+}
+
+int32_t b200_tensor_product_full_query(b200_ctx *ctx, const uint64_t *query, uint32_t k, b200_dev_ptr out, uint64_t n_out) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (k > 60 || n_out != (1ull << k)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output must hold 2^%u elements", k);
+	const uint64_t one[2] = {1, 0};
+	int32_t rc = b200_fill(ctx, out, 1, one);
+	if (rc) return rc;
+	return b200_tensor_expand(ctx, out, n_out, 0, query, k);
+}
+
+static bool valid_level(uint32_t lvl) { return lvl == 0 || (lvl >= 3 && lvl <= 7); }
+
+int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t lvl, b200_dev_ptr b, uint64_t n_b, uint32_t *slot) {
+	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
+	if (lvl > 7 || (n_a << (7 - lvl)) != n_b) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid input: a_edeg=%u |a|=%llu |b|=%llu", lvl, (unsigned long long)n_a, (unsigned long long)n_b);
+	if (!valid_level(lvl)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "unsupported tower level %u", lvl);
+	int32_t rc = new_slot(ctx, slot);
+	if (rc) return rc;
+	if (n_b == 0) return B200_OK;
+	k_inner_product<<<grid_for(ctx, n_b, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)a, lvl, (const uint4 *)b, n_b, ctx->d_results + *slot);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (lvl > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid evals: tower_level=%u > 7", lvl);
+	if (!valid_level(lvl)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "unsupported tower level %u", lvl);
+	if (!is_pow2(n_mat)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "the length of `mat` must be a power of 2");
+	if (!is_pow2(n_vec)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "the length of `vec` must be a power of 2");
+	uint32_t log_evals = ilog2(n_mat) + 7 - lvl, log_q = ilog2(n_vec);
+	if (log_q > log_evals) return fail(ctx, B200_ERR_INPUT_VALIDATION, "query larger than evals");
+	uint64_t expect_out = 1ull << (log_evals - log_q);
+	if (n_out != expect_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output has %llu elements, expected %llu", (unsigned long long)n_out, (unsigned long long)expect_out);
+	uint32_t grid = grid_for(ctx, n_out, 256, 2);
+	if (right) k_fold_mat<true><<<grid, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)mat, lvl, (const uint4 *)vec, log_q, (uint4 *)out, n_out);
+	else k_fold_mat<false><<<grid, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)mat, lvl, (const uint4 *)vec, log_q, (uint4 *)out, n_out);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
+	return fold_mat(ctx, false, mat, n_mat, lvl, vec, n_vec, out, n_out);
+}
+int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
+	return fold_mat(ctx, true, mat, n_mat, lvl, vec, n_vec, out, n_out);
+}
+
+// ---- expressions --------------------------------------------------------------------------------
+int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n_steps, b200_expr **out) {
+	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
+	if (n_steps > MAX_EXPR_STEPS) return fail(ctx, B200_ERR_INPUT_VALIDATION, "expression has %u steps (max %u)", n_steps, MAX_EXPR_STEPS);
+	uint32_t n_vars = 0;
+	for (uint32_t s = 0; s < n_steps; s++) {
+		const b200_expr_step &st = steps[s];
+		switch (st.op) {
+		case 0:
+		case 1:
+			if (st.l >= s || st.r >= s) return fail(ctx, B200_ERR_INPUT_VALIDATION, "step %u references a later step", s);
+			break;
+		case 2:
+			if (st.l >= s) return fail(ctx, B200_ERR_INPUT_VALIDATION, "step %u references a later step", s);
+			break;
+		case 3: break;
+		case 4: n_vars = std::max(n_vars, st.l + 1); break;
+		default: return fail(ctx, B200_ERR_INPUT_VALIDATION, "step %u: unknown op %u", s, st.op);
+		}
+	}
+	std::unique_ptr<b200_expr> e(new b200_expr);
+	e->steps.assign(steps, steps + n_steps);
+	e->n_vars = n_vars;
+	if (cudaMalloc(&e->d_steps, sizeof(b200_expr_step) * std::max(n_steps, 1u)) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(ctx, B200_ERR_ALLOC, "out of device memory");
+	}
+	if (n_steps) B200_CUDA(ctx, cudaMemcpy(e->d_steps, steps, sizeof(b200_expr_step) * n_steps, cudaMemcpyHostToDevice));
+	*out = e.release();
+	return B200_OK;
+}
+void b200_expr_free(b200_expr *e) {
+	if (!e) return;
+	cudaFree(e->d_steps);
+	delete e;
+}
+uint32_t b200_expr_n_vars(const b200_expr *e) { return e ? e->n_vars : 0; }
+
+static DevExpr dev_expr(const b200_expr *e) { return DevExpr{e->d_steps, (uint32_t)e->steps.size(), e->n_vars}; }
+
+int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, b200_dev_ptr out, uint64_t n_out, const b200_expr *expr) {
+	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
+	if (row_len != n_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "inputs and output must be the same length");
+	if (expr->n_vars > n_inputs) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition not match with input");
+	if (n_out == 0) return B200_OK;
+	void *dptrs = nullptr;
+	if (n_inputs) {
+		int32_t rc = stage_args(ctx, inputs, sizeof(void *) * n_inputs, &dptrs);
+		if (rc) return rc;
+	}
+	k_compute_composite<<<grid_for(ctx, n_out, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, PtrList{(const uint4 *const *)dptrs, n_inputs}, dev_expr(expr), (uint4 *)out, n_out);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t n_in, const b200_dev_ptr *outs, const uint64_t *lens, uint32_t n_rounds) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (!is_pow2(n_in)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "input length must be a power of 2: %llu", (unsigned long long)n_in);
+	if (n_in < 2) return fail(ctx, B200_ERR_INPUT_VALIDATION, "input length must be greater than or equal to 2 in order to perform at least one reduction: %llu", (unsigned long long)n_in);
+	uint32_t log_n = ilog2(n_in);
+	if (n_rounds != log_n) return fail(ctx, B200_ERR_INPUT_VALIDATION, "round_outputs.len() does not match the expected length: %u != %u", n_rounds, log_n);
+	for (uint32_t r = 0; r < n_rounds; r++)
+		if (lens[r] != (1ull << (log_n - r - 1))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "round_outputs[%u].len() = %llu, expected %llu", r, (unsigned long long)lens[r], 1ull << (log_n - r - 1));
+	const uint4 *src = (const uint4 *)input;
+	for (uint32_t r = 0; r < n_rounds; r++) {
+		k_pairwise_product<<<grid_for(ctx, lens[r], 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, src, (uint4 *)outs[r], lens[r]);
+		B200_LAUNCH_CHECK(ctx);
+		src = (const uint4 *)outs[r];
+	}
+	return B200_OK;
+}
+
+// ---- KernelExecutor ------------------------------------------------------------------------------
+int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *slot) {
+	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
+	int32_t rc = new_slot(ctx, slot);
+	if (rc) return rc;
+	if (init[0] | init[1]) {
+		k_set_slot<<<1, 1, 0, ctx->stream>>>(ctx->d_results + *slot, to_u4(init));
+		B200_LAUNCH_CHECK(ctx);
+	}
+	return B200_OK;
+}
+int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
+	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
+	if (slot >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "value slot %u not declared", slot);
+	if (expr->n_vars > n_inputs) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition not match with input");
+	if (row_len == 0) return B200_OK;
+	void *dptrs = nullptr;
+	if (n_inputs) {
+		int32_t rc = stage_args(ctx, inputs, sizeof(void *) * n_inputs, &dptrs);
+		if (rc) return rc;
+	}
+	k_sum_composition<<<grid_for(ctx, row_len, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, PtrList{(const uint4 *const *)dptrs, n_inputs}, dev_expr(expr), row_len, to_u4(coeff), ctx->d_results + slot);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr a, b200_dev_ptr b, b200_dev_ptr dst) {
+	if (!ctx || log_len > 60) return B200_ERR_INPUT_VALIDATION;
+	uint64_t n = 1ull << log_len;
+	k_add<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)dst, n);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+int32_t b200_kernel_add_assign(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr src, b200_dev_ptr dst) {
+	return b200_kernel_add(ctx, log_len, dst, src, dst);
+}
+
+int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, const uint32_t *ia, const uint32_t *ib, uint32_t n_comp, const uint64_t coeff[2], uint32_t *slot_y1, uint32_t *slot_yinf) {
+	if (!ctx || !slot_y1 || !slot_yinf) return B200_ERR_INPUT_VALIDATION;
+	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
+	for (uint32_t c = 0; c < n_comp; c++)
+		if (ia[c] >= m || ib[c] >= m) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition %u indexes a missing multilinear", c);
+	int32_t rc = new_slot(ctx, slot_y1);
+	if (rc) return rc;
+	rc = new_slot(ctx, slot_yinf);
+	if (rc) return rc;
+	if (n_comp == 0) return B200_OK;
+	if (n_comp > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many compositions");
+	uint64_t half = 1ull << (n_vars - 1);
+	// batch coefficient powers alpha^c (host; n_comp scalar products)
+	std::vector<uint4> pows(n_comp);
+	hostf::u128 a = hostf::from_words(coeff), pw = 1;
+	for (uint32_t c = 0; c < n_comp; c++) {
+		uint64_t w[2] = {(uint64_t)pw, (uint64_t)(pw >> 64)};
+		pows[c] = to_u4(w);
+		pw = hostf::mul128(pw, a);
+	}
+	void *dm, *dia, *dib, *dp;
+	if ((rc = stage_args(ctx, mls, sizeof(void *) * m, &dm))) return rc;
+	if ((rc = stage_args(ctx, ia, 4 * n_comp, &dia))) return rc;
+	if ((rc = stage_args(ctx, ib, 4 * n_comp, &dib))) return rc;
+	if ((rc = stage_args(ctx, pows.data(), 16 * n_comp, &dp))) return rc;
+	uint32_t gx = grid_for(ctx, half, 256, 2);
+	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::max(1u, std::min(n_comp, (uint32_t)ctx->n_sms * 4)) + 1)));
+	k_bivariate_round_evals<<<dim3(gx, n_comp), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *const *)dm, half, (const uint32_t *)dia, (const uint32_t *)dib, (const uint4 *)dp, ctx->d_results + *slot_y1, ctx->d_results + *slot_yinf);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
+	if (!ctx || !first_slot) return B200_ERR_INPUT_VALIDATION;
+	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
+	if ((uint64_t)n_comp * n_points > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many (composition, point) pairs");
+	for (uint32_t c = 0; c < n_comp; c++)
+		if (!comps[c] || !leads[c] || comps[c]->n_vars > m || leads[c]->n_vars > m) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition %u does not match the multilinears", c);
+	for (uint32_t p = 0; p < n_points; p++)
+		if (codes[p] == 0) return fail(ctx, B200_ERR_INPUT_VALIDATION, "evaluation point code 0 (evaluate at 0) is never computed by the prover");
+	uint32_t total = n_comp * n_points;
+	if (ctx->n_results + total > MAX_RESULTS) return fail(ctx, B200_ERR_ALLOC, "out of result slots");
+	*first_slot = ctx->n_results;
+	ctx->n_results += total;
+	if (total == 0) return B200_OK;
+	std::vector<DevExpr> hc(n_comp), hl(n_comp);
+	for (uint32_t c = 0; c < n_comp; c++) {
+		hc[c] = dev_expr(comps[c]);
+		hl[c] = dev_expr(leads[c]);
+	}
+	std::vector<uint4> hp(n_points);
+	for (uint32_t p = 0; p < n_points; p++) hp[p] = to_u4(points + 2 * p);
+	EqIndArgs A;
+	int32_t rc;
+	void *d;
+	if ((rc = stage_args(ctx, mls, sizeof(void *) * std::max(m, 1u), &d))) return rc;
+	A.mls = (const uint4 *const *)d;
+	A.n_mls = m;
+	A.half = 1ull << (n_vars - 1);
+	A.eq_ind = (const uint4 *)eq_ind;
+	if ((rc = stage_args(ctx, hc.data(), sizeof(DevExpr) * n_comp, &d))) return rc;
+	A.comps = (const DevExpr *)d;
+	if ((rc = stage_args(ctx, hl.data(), sizeof(DevExpr) * n_comp, &d))) return rc;
+	A.comps_lead = (const DevExpr *)d;
+	if ((rc = stage_args(ctx, codes, 4 * n_points, &d))) return rc;
+	A.codes = (const uint32_t *)d;
+	if ((rc = stage_args(ctx, hp.data(), 16 * n_points, &d))) return rc;
+	A.points = (const uint4 *)d;
+	A.n_points = n_points;
+	A.slots = ctx->d_results + *first_slot;
+	uint32_t gx = grid_for(ctx, A.half, 256, 2);
+	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::min(total, (uint32_t)ctx->n_sms * 4) + 1)));
+	k_eq_ind_round_evals<<<dim3(gx, total), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+// ---- NTT -----------------------------------------------------------------------------------------
+int32_t b200_ntt_create(b200_ctx *ctx, uint32_t kt, uint32_t d, b200_ntt **out) {
+	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
+	if (kt < 3 || kt > 5) return fail(ctx, B200_ERR_INPUT_VALIDATION, "twiddle field must be B8, B16 or B32");
+	if (d == 0) return fail(ctx, B200_ERR_NTT_DOMAIN, "domain size is less than 2**1");
+	if (d > (1u << kt)) return fail(ctx, B200_ERR_NTT_FIELD, "field order must be at least 2**%u", d);
+	std::unique_ptr<b200_ntt> n(new b200_ntt);
+	n->kt = kt;
+	n->d = d;
+	// precompute_subspace_evals (crates/ntt/src/twiddle.rs:244-313) over the basis beta_j = 1 << j
+	using hostf::u128;
+	std::vector<std::vector<u128>> s(d);
+	std::vector<u128> norm(d);
+	norm[0] = 1;
+	for (uint32_t j = 1; j < d; j++) s[0].push_back((u128)1 << j);
+	for (uint32_t r = 1; r < d; r++) {
+		u128 np = norm[r - 1];
+		auto phi = [&](u128 e) { return hostf::mul(e, e, kt) ^ hostf::mul(np, e, kt); };
+		norm[r] = phi(s[r - 1][0]);
+		for (size_t j = 1; j < s[r - 1].size(); j++) s[r].push_back(phi(s[r - 1][j]));
+	}
+	std::vector<uint32_t> flat(32 * 32, 0);
+	n->s_evals.resize(d);
+	for (uint32_t r = 0; r < d; r++) {
+		u128 inv = hostf::invert(norm[r], kt);
+		for (size_t j = 0; j < s[r].size(); j++) {
+			u128 v = hostf::mul(s[r][j], inv, kt);
+			n->s_evals[r].push_back((uint64_t)v);
+			flat[r * 32 + j] = (uint32_t)v;
+		}
+	}
+	if (cudaMalloc(&n->d_s_evals, sizeof(uint32_t) * 32 * 32) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(ctx, B200_ERR_ALLOC, "out of device memory");
+	}
+	B200_CUDA(ctx, cudaMemcpy(n->d_s_evals, flat.data(), sizeof(uint32_t) * 32 * 32, cudaMemcpyHostToDevice));
+	*out = n.release();
+	return B200_OK;
+}
+void b200_ntt_destroy(b200_ntt *ntt) {
+	if (!ntt) return;
+	cudaFree(ntt->d_s_evals);
+	delete ntt;
+}
+uint32_t b200_ntt_log_domain_size(const b200_ntt *ntt) { return ntt ? ntt->d : 0; }
+
+int32_t b200_ntt_get_subspace_eval(const b200_ntt *ntt, uint32_t i, uint64_t j, uint64_t out[2]) {
+	if (!ntt || !out || i == 0 || i > ntt->d) return B200_ERR_INPUT_VALIDATION;
+	const auto &row = ntt->s_evals[ntt->d - i];
+	uint64_t t = 0;
+	for (size_t b = 0; b < row.size(); b++)
+		if ((j >> b) & 1) t ^= row[b];
+	out[0] = t;
+	out[1] = 0;
+	return B200_OK;
+}
+
+static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev_ptr data, uint32_t kd, uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z, uint64_t coset, uint32_t coset_bits, uint32_t skip_rounds) {
+	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
+	if (kd < ntt->kt || kd > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "element width 2^%u bits is not an extension of the twiddle field", kd);
+	// check_batch_transform_inputs_and_params (crates/ntt/src/single_threaded.rs:364-406), WIDTH = 1
+	if (!is_pow2(n_elems)) return fail(ctx, B200_ERR_NTT_POWER_OF_TWO, "the input length must be a power of two");
+	if (skip_rounds > log_y) return fail(ctx, B200_ERR_NTT_SKIP_ROUNDS, "the skip_rounds parameter exceeds the total number of NTT rounds");
+	if (log_x + log_y + log_z > 62) return fail(ctx, B200_ERR_NTT_BATCH, "the batch size is greater than the number of elements");
+	uint64_t full_y = n_elems >> (log_x + log_z);
+	if (((1ull << log_y) != full_y && n_elems > 2) || (1ull << log_y) > full_y) return fail(ctx, B200_ERR_NTT_BATCH, "the batch size is greater than the number of elements");
+	if (coset_bits > 62 || coset >= (1ull << coset_bits)) return fail(ctx, B200_ERR_NTT_COSET, "coset index must be less than 2**%u, got %llu", coset_bits, (unsigned long long)coset);
+	if (log_y + coset_bits > ntt->d) return fail(ctx, B200_ERR_NTT_DOMAIN, "domain size is less than 2**%u", log_y + coset_bits);
+	uint32_t n_layers = log_y - skip_rounds;
+	if (n_layers == 0) return B200_OK;
+	uint32_t lx = log_x + (kd - ntt->kt);  // *_transform_ext: extension limbs become extra batch columns
+	// pass plan, bottom-up: [i_lo, i_lo + R)
+	struct Pass { uint32_t i_lo, R, log_c; };
+	std::vector<Pass> plan;
+	const uint32_t MAX_LOG_TILE = 13;
+	for (uint32_t i_lo = 0; i_lo < n_layers;) {
+		uint32_t log_inner = lx + i_lo;
+		uint32_t log_c = std::min(5u, log_inner);
+		uint32_t R = std::min(n_layers - i_lo, MAX_LOG_TILE - log_c);
+		if (log_c == 5) R = std::min(R, 8u);
+		plan.push_back(Pass{i_lo, R, log_c});
+		i_lo += R;
+	}
+	uint32_t n_z = 1u << log_z;
+	if (n_z > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "log_z too large");
+	for (size_t pi = 0; pi < plan.size(); pi++) {
+		const Pass &P = inverse ? plan[pi] : plan[plan.size() - 1 - pi];
+		NttPassArgs A;
+		A.data = data;
+		A.log_x = lx;
+		A.log_y = log_y;
+		A.i_lo = P.i_lo;
+		A.R = P.R;
+		A.log_c = P.log_c;
+		A.row0 = ntt->d - (log_y + coset_bits);
+		A.d = ntt->d;
+		A.coset = coset;
+		A.inverse = inverse;
+		A.s_evals = ntt->d_s_evals;
+		uint64_t n_blocks = 1ull << (log_y - (P.i_lo + P.R) + (lx + P.i_lo - P.log_c));
+		if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
+		uint32_t esz = 1u << (ntt->kt - 3);
+		uint32_t smem = FIELD_TABLE_BYTES + (4u << P.R) + (esz << (P.R + P.log_c));
+		dim3 grid((uint32_t)n_blocks, n_z);
+		if (ntt->kt == 5) k_ntt_pass<uint32_t><<<grid, 256, smem, ctx->stream>>>(ctx->d_tables, A);
+		else if (ntt->kt == 4) k_ntt_pass<uint16_t><<<grid, 256, smem, ctx->stream>>>(ctx->d_tables, A);
+		else k_ntt_pass<uint8_t><<<grid, 256, smem, ctx->stream>>>(ctx->d_tables, A);
+		B200_LAUNCH_CHECK(ctx);
+	}
+	return B200_OK;
+}
+
+int32_t b200_ntt_forward(b200_ctx *ctx, const b200_ntt *ntt, b200_dev_ptr data, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	return ntt_run(ctx, ntt, 0, data, kd, n, lx, ly, lz, coset, cb, skip);
+}
+int32_t b200_ntt_inverse(b200_ctx *ctx, const b200_ntt *ntt, b200_dev_ptr data, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	return ntt_run(ctx, ntt, 1, data, kd, n, lx, ly, lz, coset, cb, skip);
+}
+
+static int32_t ntt_host(b200_ctx *ctx, const b200_ntt *ntt, int inverse, void *host, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
+	if (kd < 3 || kd > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "bad element width");
+	uint64_t bytes = n << (kd - 3);
+	int32_t rc = ensure_scratch(ctx, std::max<uint64_t>(bytes, 16));
+	if (rc) return rc;
+	B200_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	rc = ntt_run(ctx, ntt, inverse, ctx->d_scratch, kd, n, lx, ly, lz, coset, cb, skip);
+	if (rc) return rc;
+	B200_CUDA(ctx, cudaMemcpyAsync(host, ctx->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return B200_OK;
+}
+int32_t b200_ntt_forward_host(b200_ctx *ctx, const b200_ntt *ntt, void *host, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	return ntt_host(ctx, ntt, 0, host, kd, n, lx, ly, lz, coset, cb, skip);
+}
+int32_t b200_ntt_inverse_host(b200_ctx *ctx, const b200_ntt *ntt, void *host, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	return ntt_host(ctx, ntt, 1, host, kd, n, lx, ly, lz, coset, cb, skip);
+}
+
+int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint32_t log_batch, const uint64_t *challenges, uint32_t n_ch, b200_dev_ptr in, uint64_t n_in, b200_dev_ptr out, uint64_t n_out) {
+	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
+	if (log_len + log_batch > 60 || n_in != (1ull << (log_len + log_batch))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data_in length: %llu", (unsigned long long)n_in);
+	if (n_ch < log_batch) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid challenges length: %u", n_ch);
+	if (n_ch > log_batch + log_len) return fail(ctx, B200_ERR_INPUT_VALIDATION, "challenges length too big: %u", n_ch);
+	uint32_t eta = n_ch - log_batch;
+	if (n_out != (1ull << (log_len - eta))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data_out length: %llu", (unsigned long long)n_out);
+	if (eta > 0 && log_len > ntt->d) return fail(ctx, B200_ERR_NTT_DOMAIN, "domain size is less than 2**%u", log_len);
+	if (n_ch > FRI_MAX_LOG_CHUNK) return fail(ctx, B200_ERR_INPUT_VALIDATION, "fri_fold: more than %u challenges per call not supported", FRI_MAX_LOG_CHUNK);
+	std::vector<uint4> hc(std::max(n_ch, 1u));
+	for (uint32_t i = 0; i < n_ch; i++) hc[i] = to_u4(challenges + 2 * i);
+	void *dc;
+	int32_t rc = stage_args(ctx, hc.data(), 16 * hc.size(), &dc);
+	if (rc) return rc;
+	FriArgs A{(const uint4 *)in, (uint4 *)out, n_out, log_len, log_batch, n_ch, (const uint4 *)dc, ntt->d_s_evals, ntt->d, ntt->kt};
+	k_fri_fold<<<grid_for(ctx, n_out, 128, 2), 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+}  // extern "C"

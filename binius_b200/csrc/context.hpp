@@ -1,0 +1,84 @@
+// context.hpp -- the per-device context behind the C ABI (include/binius_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/binius_b200.h"
+
+struct b200_ctx {
+	int device = 0;
+	int n_sms = 148;
+	cudaStream_t stream = nullptr;
+	cudaStream_t own_stream = nullptr;
+	std::string err;
+	uint64_t launches = 0;
+
+	// field tables (64 KiB B8 product table + 256 B times-X_2 table), device global memory
+	uint8_t *d_tables = nullptr;
+	// basis images for the LUT engine: up to MAX_LINMAPS x 128 uint4
+	uint4 *d_basis = nullptr;
+	// deferred scalar results (OpValue slots)
+	uint4 *d_results = nullptr;
+	uint32_t n_results = 0;
+	// small device scratch for argument arrays (pointer lists etc.), ring-allocated
+	uint8_t *d_args = nullptr;
+	uint64_t args_off = 0;
+	// pinned host mirror used for staging small argument arrays
+	uint8_t *h_args = nullptr;
+	// general device scratch (grown on demand)
+	uint8_t *d_scratch = nullptr;
+	uint64_t scratch_bytes = 0;
+};
+
+namespace b200 {
+
+constexpr uint32_t MAX_RESULTS = 1u << 16;
+constexpr uint32_t MAX_LINMAPS = 64;
+constexpr uint64_t ARGS_BYTES = 4u << 20;
+
+inline int32_t fail(b200_ctx *ctx, int32_t code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (ctx) ctx->err = buf;
+	return code;
+}
+
+#define B200_CUDA(ctx, call)                                                                         \
+	do {                                                                                             \
+		cudaError_t e__ = (call);                                                                    \
+		if (e__ != cudaSuccess)                                                                      \
+			return b200::fail(ctx, B200_ERR_DEVICE, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+	} while (0)
+
+#define B200_LAUNCH_CHECK(ctx)                                                                 \
+	do {                                                                                       \
+		(ctx)->launches++;                                                                     \
+		cudaError_t e__ = cudaGetLastError();                                                  \
+		if (e__ != cudaSuccess)                                                                \
+			return b200::fail(ctx, B200_ERR_DEVICE, "kernel launch failed at %s:%d: %s", __FILE__, \
+							  __LINE__, cudaGetErrorString(e__));                              \
+	} while (0)
+
+// copy a small host array into the device argument ring; returns device pointer (stream-ordered)
+int32_t stage_args(b200_ctx *ctx, const void *host, uint64_t bytes, void **dev_out);
+int32_t ensure_scratch(b200_ctx *ctx, uint64_t bytes);
+
+inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+inline uint32_t ilog2(uint64_t x) {
+	uint32_t r = 0;
+	while (x >>= 1) r++;
+	return r;
+}
+inline uint4 to_u4(const uint64_t v[2]) {
+	return make_uint4((uint32_t)v[0], (uint32_t)(v[0] >> 32), (uint32_t)v[1], (uint32_t)(v[1] >> 32));
+}
+
+}  // namespace b200

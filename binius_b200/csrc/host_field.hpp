@@ -1,0 +1,79 @@
+// host_field.hpp -- host-side binary tower field arithmetic used by the product library for
+// one-off scalar work (twiddle generation, 8-bit table generation, batch-coefficient powers).
+// Independent of oracle/ (the oracle is test infrastructure and is never linked here).
+//
+// Field definition: reference crates/field/src/binary_field.rs:33-40, 503-527 and
+// crates/field/src/arch/portable/pairwise_recursive_arithmetic.rs:12-81:
+//   T_0 = GF(2),  T_{k+1} = T_k[X_k] / (X_k^2 + X_k * X_{k-1} + 1),  X_{-1} = 1,
+//   element of T_k = integer of 2^k bits = lo + hi * X_{k-1}.
+#pragma once
+#include <cstdint>
+
+namespace b200 {
+namespace hostf {
+
+typedef unsigned __int128 u128;
+
+template <int K>
+struct Tw {
+	static constexpr int H = 1 << (K - 1);
+	static inline u128 lo(u128 a) { return a & ((((u128)1) << H) - 1); }
+	static inline u128 hi(u128 a) { return (a >> H) & ((((u128)1) << H) - 1); }
+	// multiply by X_{K-1}
+	static u128 mul_alpha(u128 a) {
+		u128 a0 = lo(a), a1 = hi(a);
+		return a1 | ((a0 ^ Tw<K - 1>::mul_alpha(a1)) << H);
+	}
+	static u128 mul(u128 a, u128 b) {
+		u128 a0 = lo(a), a1 = hi(a), b0 = lo(b), b1 = hi(b);
+		u128 p0 = Tw<K - 1>::mul(a0, b0);
+		u128 p2 = Tw<K - 1>::mul(a1, b1);
+		u128 pm = Tw<K - 1>::mul(a0 ^ a1, b0 ^ b1);
+		return (p0 ^ p2) | ((pm ^ p0 ^ p2 ^ Tw<K - 1>::mul_alpha(p2)) << H);
+	}
+	static u128 square(u128 a) { return mul(a, a); }
+	static u128 invert(u128 a) {
+		u128 a0 = lo(a), a1 = hi(a);
+		u128 t = a0 ^ Tw<K - 1>::mul_alpha(a1);
+		u128 delta = Tw<K - 1>::mul(a0, t) ^ Tw<K - 1>::square(a1);
+		u128 di = Tw<K - 1>::invert(delta);
+		return Tw<K - 1>::mul(di, t) | (Tw<K - 1>::mul(di, a1) << H);
+	}
+};
+template <>
+struct Tw<0> {
+	static u128 mul_alpha(u128 a) { return a & 1; }
+	static u128 mul(u128 a, u128 b) { return a & b & 1; }
+	static u128 square(u128 a) { return a & 1; }
+	static u128 invert(u128 a) { return a & 1; }
+};
+
+inline u128 mul(u128 a, u128 b, int k) {
+	switch (k) {
+	case 0: return Tw<0>::mul(a, b);
+	case 1: return Tw<1>::mul(a, b);
+	case 2: return Tw<2>::mul(a, b);
+	case 3: return Tw<3>::mul(a, b);
+	case 4: return Tw<4>::mul(a, b);
+	case 5: return Tw<5>::mul(a, b);
+	case 6: return Tw<6>::mul(a, b);
+	default: return Tw<7>::mul(a, b);
+	}
+}
+inline u128 invert(u128 a, int k) {
+	switch (k) {
+	case 0: return Tw<0>::invert(a);
+	case 1: return Tw<1>::invert(a);
+	case 2: return Tw<2>::invert(a);
+	case 3: return Tw<3>::invert(a);
+	case 4: return Tw<4>::invert(a);
+	case 5: return Tw<5>::invert(a);
+	case 6: return Tw<6>::invert(a);
+	default: return Tw<7>::invert(a);
+	}
+}
+inline u128 mul128(u128 a, u128 b) { return Tw<7>::mul(a, b); }
+inline u128 from_words(const uint64_t w[2]) { return ((u128)w[1] << 64) | w[0]; }
+
+}  // namespace hostf
+}  // namespace b200

@@ -1,0 +1,390 @@
+// kernels.cuh -- CUDA kernels (sm_100a) for the ComputeLayer / ComputationBackend hot path.
+// Host-side launch wrappers + validation live in capi.cu.  Reference citations are next to each
+// kernel; semantics are restated for the checker in oracle/ops.c.
+#pragma once
+#include "field.cuh"
+#include "linmap.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// basis images for the LUT engine: W[m*128 + i] = beta_i * z[m]   (beta_i = 1 << i)
+// grid = n_maps, block = 128, dyn smem = FIELD_TABLE_BYTES
+__global__ void __launch_bounds__(128) k_basis_products(const uint8_t *__restrict__ g_tables, const uint4 *__restrict__ zs,
+														 uint4 *__restrict__ W) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint32_t i = threadIdx.x, m = blockIdx.x;
+	uint32_t w[4] = {0, 0, 0, 0};
+	w[i >> 5] = 1u << (i & 31);
+	W[m * 128 + i] = f_mul128(T, make_uint4(w[0], w[1], w[2], w[3]), zs[m]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fold-high / extrapolate_line over a list of segments sharing ONE challenge z:
+//     e0[i] ^= (e1[i] ^ e0[i]) * z            i <  pivot
+//     e0[i] ^= (suffix ^ e0[i]) * z           pivot <= i < upper
+// reference: compute/src/cpu/layer.rs:393-408 (extrapolate_line) and math/src/fold.rs:648-696
+// (fold_left_lerp_inplace with const-suffix; packed width 1).
+struct LerpSeg {
+	uint4 *e0;
+	const uint4 *e1;
+	uint64_t pivot;
+	uint64_t upper;
+	uint4 suffix;
+	uint64_t tile_start;  // first global tile of this segment (prefix sum), filled by the host
+};
+
+constexpr uint32_t FOLD_THREADS = 512;
+constexpr uint32_t FOLD_UNROLL = 2;
+constexpr uint32_t FOLD_TILE = FOLD_THREADS * FOLD_UNROLL;
+
+__global__ void __launch_bounds__(FOLD_THREADS) k_lerp_lut(const LerpSeg *__restrict__ segs, uint32_t n_segs, uint64_t n_tiles,
+															const uint4 *__restrict__ W) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *tbl = smem;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
+	lut_build(tbl, stage, W);
+	const LutLane L = lut_lane_init();
+
+	uint32_t seg = 0;
+	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		while (seg + 1 < n_segs && segs[seg + 1].tile_start <= tile) seg++;
+		const LerpSeg S = segs[seg];
+		uint64_t base = (tile - S.tile_start) * FOLD_TILE + threadIdx.x;
+		uint4 a[FOLD_UNROLL], b[FOLD_UNROLL];
+#pragma unroll
+		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
+			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
+			if (i < S.upper) {
+				a[u] = S.e0[i];
+				b[u] = i < S.pivot ? __ldg(S.e1 + i) : S.suffix;
+			}
+		}
+#pragma unroll
+		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
+			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
+			if (i < S.upper) S.e0[i] = a[u] ^ lut_apply(tbl, L, a[u] ^ b[u]);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// one tensor-expansion round:  p = x * r ; lo[j] = x ^ p ; hi[j] = p        j < half
+// reference: compute/src/layer.rs:269-296 (definition), math/src/tensor_prod_eq_ind.rs:35-77
+__global__ void __launch_bounds__(FOLD_THREADS) k_expand_lut(uint4 *__restrict__ data, uint64_t half, const uint4 *__restrict__ W) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *tbl = smem;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
+	lut_build(tbl, stage, W);
+	const LutLane L = lut_lane_init();
+	uint64_t n_tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
+	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		uint64_t base = tile * FOLD_TILE + threadIdx.x;
+		uint4 x[FOLD_UNROLL];
+#pragma unroll
+		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
+			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
+			if (i < half) x[u] = data[i];
+		}
+#pragma unroll
+		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
+			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
+			if (i < half) {
+				uint4 p = lut_apply(tbl, L, x[u]);
+				data[i] = x[u] ^ p;
+				data[half + i] = p;
+			}
+		}
+	}
+}
+
+// small tensor expansion: rounds [0, k) entirely inside one CTA's shared memory (2^(log_n+k) <= 2048)
+// dyn smem = FIELD_TABLE_BYTES + 16 * 2^(log_n+k)
+__global__ void __launch_bounds__(256) k_expand_small(const uint8_t *__restrict__ g_tables, uint4 *__restrict__ data, uint32_t log_n,
+													  const uint4 *__restrict__ coords, uint32_t k) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint4 *buf = reinterpret_cast<uint4 *>(smem + FIELD_TABLE_BYTES);
+	uint32_t n0 = 1u << log_n;
+	for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) buf[i] = data[i];
+	__syncthreads();
+	for (uint32_t r = 0; r < k; r++) {
+		uint32_t half = 1u << (log_n + r);
+		uint4 c = coords[r];
+		for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+			uint4 x = buf[i];
+			uint4 p = f_mul128(T, x, c);
+			buf[i] = x ^ p;
+			buf[half + i] = p;
+		}
+		__syncthreads();
+	}
+	uint32_t n = 1u << (log_n + k);
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) data[i] = buf[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill(uint4 *__restrict__ dst, uint64_t n, uint4 v) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+// KernelExecutor::add / add_assign (compute/src/cpu/layer.rs:516-548)
+__global__ void k_add(const uint4 *__restrict__ a, const uint4 *__restrict__ b, uint4 *__restrict__ dst, uint64_t n) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = a[i] ^ b[i];
+}
+__global__ void k_set_slot(uint4 *slot, uint4 v) { *slot = v; }
+
+// ------------------------------------------------------------------------------------------------
+// inner_product(SubfieldSlice{a, lvl}, b) = sum_i sum_j b[i*L + j] * limb_j(a[i])
+// reference: compute/src/cpu/layer.rs:205-236
+__global__ void __launch_bounds__(256) k_inner_product(const uint8_t *__restrict__ g_tables, const uint4 *__restrict__ a,
+													   uint32_t lvl, const uint4 *__restrict__ b, uint64_t n_b, uint4 *__restrict__ slot) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	__shared__ uint4 red[32];
+	uint32_t logL = 7 - lvl;
+	uint4 acc = u4_zero();
+	for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_b; e += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 av = __ldg(a + (e >> logL));
+		uint4 s = f_limb(av, lvl, (uint32_t)(e & ((1u << logL) - 1)));
+		acc ^= f_mul128_sub(T, __ldg(b + e), s, lvl);
+	}
+	acc = block_xor(acc, red);
+	if (threadIdx.x == 0) atomic_xor_u4(slot, acc);
+}
+
+// fold_left : out[i] = sum_j vec[j] * evals[j*rows + i]      (cpu/layer.rs:574-621)
+// fold_right: out[i] = sum_j vec[j] * evals[i*cols + j]      (cpu/layer.rs:628-675)
+// evals = limbs of `mat` at tower level lvl, flattened low limb first.
+template <bool RIGHT>
+__global__ void __launch_bounds__(256) k_fold_mat(const uint8_t *__restrict__ g_tables, const uint4 *__restrict__ mat, uint32_t lvl,
+												  const uint4 *__restrict__ vec, uint32_t log_q, uint4 *__restrict__ out, uint64_t n_out) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint32_t logL = 7 - lvl;
+	uint64_t nq = 1ull << log_q;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 acc = u4_zero();
+		for (uint64_t j = 0; j < nq; j++) {
+			uint64_t e = RIGHT ? (i * nq + j) : (j * n_out + i);
+			uint4 m = __ldg(mat + (e >> logL));
+			uint4 s = f_limb(m, lvl, (uint32_t)(e & ((1u << logL) - 1)));
+			acc ^= f_mul128_sub(T, __ldg(vec + j), s, lvl);
+		}
+		out[i] = acc;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// ArithCircuit interpreter (math/src/arith_expr.rs:367-383)
+constexpr uint32_t MAX_EXPR_STEPS = 64;
+struct DevExpr {
+	const b200_expr_step *steps;
+	uint32_t n_steps;
+	uint32_t n_vars;
+};
+struct PtrList {
+	const uint4 *const *ptrs;  // device array of row pointers
+	uint32_t n;
+};
+
+__device__ __forceinline__ uint4 f_pow128(const FieldTables &T, uint4 x, uint64_t e) {
+	uint4 r = u4_one();
+	while (e) {
+		if (e & 1) r = f_mul128(T, r, x);
+		e >>= 1;
+		if (e) x = f_mul128(T, x, x);
+	}
+	return r;
+}
+
+__device__ __forceinline__ uint4 expr_eval(const FieldTables &T, const DevExpr &E, const uint4 *const *rows, uint64_t i) {
+	uint4 tmp[MAX_EXPR_STEPS];
+	for (uint32_t s = 0; s < E.n_steps; s++) {
+		const b200_expr_step st = E.steps[s];
+		uint4 v;
+		switch (st.op) {
+		case 0: v = tmp[st.l] ^ tmp[st.r]; break;
+		case 1: v = f_mul128(T, tmp[st.l], tmp[st.r]); break;
+		case 2: v = f_pow128(T, tmp[st.l], st.r); break;
+		case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
+		default: v = __ldg(rows[st.l] + i); break;
+		}
+		tmp[s] = v;
+	}
+	return E.n_steps ? tmp[E.n_steps - 1] : u4_zero();
+}
+
+// compute_composite (cpu/layer.rs:410-435): out[i] = expr(inputs[.][i])
+__global__ void __launch_bounds__(256) k_compute_composite(const uint8_t *__restrict__ g_tables, PtrList in, DevExpr E,
+														   uint4 *__restrict__ out, uint64_t n) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = expr_eval(T, E, in.ptrs, i);
+}
+
+// KernelExecutor::sum_composition_evals (cpu/layer.rs:499-514): slot += coeff * sum_i expr(rows[.][i])
+__global__ void __launch_bounds__(256) k_sum_composition(const uint8_t *__restrict__ g_tables, PtrList in, DevExpr E, uint64_t n,
+														 uint4 coeff, uint4 *__restrict__ slot) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	__shared__ uint4 red[32];
+	uint4 acc = u4_zero();
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		acc ^= expr_eval(T, E, in.ptrs, i);
+	acc = block_xor(acc, red);
+	if (threadIdx.x == 0 && !is_zero(acc)) atomic_xor_u4(slot, f_mul128(T, acc, coeff));
+}
+
+// pairwise_product_reduce, one round (cpu/layer.rs:437-484): out[i] = in[2i] * in[2i+1]
+__global__ void __launch_bounds__(256) k_pairwise_product(const uint8_t *__restrict__ g_tables, const uint4 *__restrict__ in,
+														  uint4 *__restrict__ out, uint64_t n_out) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = f_mul128(T, __ldg(in + 2 * i), __ldg(in + 2 * i + 1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// v3::calculate_round_evals (core/src/protocols/sumcheck/v3/bivariate_product.rs:303-408), fused:
+// blockIdx.y = composition c; slots[0] ^= alpha^c * sum_i hi_a*hi_b ; slots[1] ^= alpha^c * sum_i
+// (lo_a+hi_a)*(lo_b+hi_b).  `pows[c]` = alpha^c.
+__global__ void __launch_bounds__(256) k_bivariate_round_evals(const uint8_t *__restrict__ g_tables, const uint4 *const *__restrict__ mls,
+															   uint64_t half, const uint32_t *__restrict__ ia, const uint32_t *__restrict__ ib,
+															   const uint4 *__restrict__ pows, uint4 *__restrict__ slot_y1,
+															   uint4 *__restrict__ slot_yinf) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	__shared__ uint4 red[32];
+	uint32_t c = blockIdx.y;
+	const uint4 *a = mls[ia[c]], *b = mls[ib[c]];
+	uint4 s1 = u4_zero(), sinf = u4_zero();
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < half; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 alo = __ldg(a + i), ahi = __ldg(a + half + i), blo = __ldg(b + i), bhi = __ldg(b + half + i);
+		s1 ^= f_mul128(T, ahi, bhi);
+		sinf ^= f_mul128(T, alo ^ ahi, blo ^ bhi);
+	}
+	s1 = block_xor(s1, red);
+	sinf = block_xor(sinf, red);
+	if (threadIdx.x == 0) {
+		uint4 p = pows[c];
+		if (!is_zero(s1)) atomic_xor_u4(slot_y1, f_mul128(T, s1, p));
+		if (!is_zero(sinf)) atomic_xor_u4(slot_yinf, f_mul128(T, sinf, p));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// eq-ind (zerocheck) round evaluations, HighToLow: R[c][p] = sum_i E[i] * C_c^{(p)}(P(i))
+// reference: hal/src/sumcheck_round_calculation.rs:222-297, core/.../prove/eq_ind.rs:670-702.
+// point code 1: P = hi ; 2: P = hi - lo evaluated on leading_term(C) ; >=3: P = lo + (hi-lo)*z_p.
+// blockIdx.y = c * n_points + p
+struct EqIndArgs {
+	const uint4 *const *mls;
+	uint32_t n_mls;
+	uint64_t half;
+	const uint4 *eq_ind;
+	const DevExpr *comps;       // [n_comp]
+	const DevExpr *comps_lead;  // [n_comp]
+	const uint32_t *codes;      // [n_points]
+	const uint4 *points;        // [n_points]
+	uint32_t n_points;
+	uint4 *slots;  // [n_comp * n_points]
+};
+constexpr uint32_t MAX_EQIND_MLS = 24;  // per-thread operand staging for the general-point path
+
+__global__ void __launch_bounds__(256) k_eq_ind_round_evals(const uint8_t *__restrict__ g_tables, EqIndArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	__shared__ uint4 red[32];
+	uint32_t c = blockIdx.y / A.n_points, p = blockIdx.y % A.n_points;
+	uint32_t code = A.codes[p];
+	const DevExpr E = code == 2 ? A.comps_lead[c] : A.comps[c];
+	uint4 z = A.points[p];
+	uint4 acc = u4_zero();
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.half; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 tmp[MAX_EXPR_STEPS];
+		for (uint32_t s = 0; s < E.n_steps; s++) {
+			const b200_expr_step st = E.steps[s];
+			uint4 v;
+			switch (st.op) {
+			case 0: v = tmp[st.l] ^ tmp[st.r]; break;
+			case 1: v = f_mul128(T, tmp[st.l], tmp[st.r]); break;
+			case 2: v = f_pow128(T, tmp[st.l], st.r); break;
+			case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
+			default: {
+				const uint4 *m = A.mls[st.l];
+				uint4 hi = __ldg(m + A.half + i);
+				if (code == 1) v = hi;
+				else {
+					uint4 lo = __ldg(m + i);
+					uint4 d = hi ^ lo;
+					v = code == 2 ? d : (lo ^ f_mul128(T, d, z));
+				}
+			}
+			}
+			tmp[s] = v;
+		}
+		uint4 val = E.n_steps ? tmp[E.n_steps - 1] : u4_zero();
+		acc ^= f_mul128(T, val, __ldg(A.eq_ind + i));
+	}
+	acc = block_xor(acc, red);
+	if (threadIdx.x == 0) atomic_xor_u4(A.slots + blockIdx.y, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fri_fold (compute/src/cpu/layer.rs:304-391).  One thread per output element, chunk of
+// 2^n_ch <= 2^FRI_MAX_LOG_CHUNK values kept in local memory.  Twiddles (field T_kt, kt <= 5) are
+// produced on the fly from the s_evals rows: t = XOR_b bit_b(idx) * s[row][b]  (twiddle.rs:163-168).
+constexpr uint32_t FRI_MAX_LOG_CHUNK = 8;
+struct FriArgs {
+	const uint4 *in;
+	uint4 *out;
+	uint64_t n_out;
+	uint32_t log_len, log_batch, n_ch;
+	const uint4 *challenges;  // device [n_ch]
+	const uint32_t *s_evals;  // device [d][32] rows (padded), twiddle field elements (<= 32 bit)
+	uint32_t d;               // log domain size
+	uint32_t kt;              // twiddle field level
+};
+
+__device__ __forceinline__ uint32_t twiddle_on_the_fly(const uint32_t *s_row, uint32_t n_bits, uint64_t idx) {
+	uint32_t t = 0;
+	for (uint32_t b = 0; b < n_bits; b++)
+		if ((idx >> b) & 1) t ^= s_row[b];
+	return t;
+}
+
+__global__ void __launch_bounds__(128) k_fri_fold(const uint8_t *__restrict__ g_tables, FriArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint32_t eta = A.n_ch - A.log_batch;
+	uint32_t chunk = 1u << A.n_ch;
+	for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < A.n_out; c += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 v[1u << FRI_MAX_LOG_CHUNK];
+		for (uint32_t i = 0; i < chunk; i++) v[i] = __ldg(A.in + c * chunk + i);
+		uint32_t cur = chunk;
+		for (uint32_t r = 0; r < A.log_batch; r++) {
+			cur >>= 1;
+			uint4 z = A.challenges[r];
+			for (uint32_t o = 0; o < cur; o++) v[o] = v[2 * o] ^ f_mul128(T, v[2 * o] ^ v[2 * o + 1], z);
+		}
+		uint32_t L = A.log_len, sz = eta;
+		for (uint32_t r = 0; r < eta; r++) {
+			uint4 z = A.challenges[A.log_batch + r];
+			uint32_t row = A.d - L;
+			for (uint32_t o = 0; o < (1u << (sz - 1)); o++) {
+				uint32_t t = twiddle_on_the_fly(A.s_evals + row * 32, A.d - 1 - row, (c << (sz - 1)) | o);
+				uint4 u = v[2 * o], w = v[2 * o + 1];
+				w ^= u;
+				u ^= f_mul128_sub(T, w, make_uint4(t, 0, 0, 0), A.kt);
+				v[o] = u ^ f_mul128(T, u ^ w, z);
+			}
+			L--;
+			sz--;
+		}
+		A.out[c] = v[0];
+	}
+}
+
+}  // namespace b200

@@ -1,0 +1,203 @@
+/*
+ * binius_b200.h -- C ABI of the B200-native (sm_100a) implementation of the Binius prover hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what a thin Rust `cc`/bindgen shim
+ * implementing the reference's own traits would bind:
+ *
+ *   binius_compute::ComputeLayer / ComputeLayerExecutor / KernelExecutor
+ *        (reference crates/compute/src/layer.rs:22-88, 100-510, 518-590)
+ *   binius_ntt::AdditiveNTT                       (crates/ntt/src/additive_ntt.rs:58-166)
+ *   binius_hal::ComputationBackend                (crates/hal/src/backend.rs:35-83)
+ *
+ * Conventions
+ *   - A field element F = BinaryField128b is a little-endian u128, passed as 2 x uint64 {lo, hi}
+ *     (crates/field/src/binary_field.rs:115-133).  Element i of a slice lives at byte offset 16*i.
+ *   - `b200_dev_ptr` values are DEVICE pointers (element-aligned, 16 B); an FSlice/FSliceMut of the
+ *     reference maps to (b200_dev_ptr, n_elems).  ComputeMemory::ALIGNMENT is 1: any element
+ *     offset is a valid slice start (crates/compute/src/memory.rs:69-235).
+ *   - Scalars, challenge vectors and index arrays are HOST pointers.
+ *   - Every call returns a status; B200_OK = 0.  Statuses map onto compute::Error
+ *     (crates/compute/src/layer.rs:706-716) and ntt::Error (crates/ntt/src/error.rs:3-29).
+ *   - All work of one context is issued on one CUDA stream in call order, so the store-to-load
+ *     ordering contract of ComputeLayerExecutor (layer.rs:90-99) holds.  Calls are asynchronous
+ *     unless stated; scalar results are deferred "OpValue" slots read back by b200_results_fetch.
+ *   - A context is not thread-safe; use one context per host thread (or serialise externally).
+ *   - There is no CPU fallback: every entry point fails with B200_ERR_DEVICE when no sm_100 device
+ *     is usable.
+ */
+#ifndef BINIUS_B200_H
+#define BINIUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+typedef void *b200_dev_ptr;
+
+enum {
+	B200_OK = 0,
+	B200_ERR_INPUT_VALIDATION = 1, /* compute::Error::InputValidation */
+	B200_ERR_ALLOC = 2,            /* compute::Error::Alloc(OutOfMemory) */
+	B200_ERR_DEVICE = 3,           /* compute::Error::DeviceError */
+	/* ntt::Error classes (crates/ntt/src/error.rs) */
+	B200_ERR_NTT_POWER_OF_TWO = 11,  /* PowerOfTwoLengthRequired */
+	B200_ERR_NTT_SKIP_ROUNDS = 12,   /* SkipRoundsTooLarge */
+	B200_ERR_NTT_BATCH = 13,         /* BatchTooLarge */
+	B200_ERR_NTT_COSET = 14,         /* CosetIndexOutOfBounds */
+	B200_ERR_NTT_DOMAIN = 15,        /* DomainTooSmall */
+	B200_ERR_NTT_FIELD = 16          /* FieldTooSmall */
+};
+
+/* ---- context / memory (ComputeHolder + ComputeLayer::copy_*, layer.rs:36-55, 732-776) ---------- */
+int32_t b200_ctx_create(int32_t device, b200_ctx **out);
+void b200_ctx_destroy(b200_ctx *ctx);
+const char *b200_last_error(b200_ctx *ctx);
+/* the CUDA stream of the context (cudaStream_t as void*) so callers can record events on it */
+void *b200_ctx_stream(b200_ctx *ctx);
+/* adopt an external stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own one */
+int32_t b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
+/* CUDA-event timing on the context's stream (bench.py): record two events, read elapsed ms */
+int32_t b200_event_create(b200_ctx *ctx, void **event_out);
+int32_t b200_event_record(b200_ctx *ctx, void *event);
+int32_t b200_event_elapsed_ms(b200_ctx *ctx, void *start, void *stop, float *ms_out); /* syncs on stop */
+void b200_event_destroy(void *event);
+/* number of kernels this library has launched on the context so far (bench `gpu_launches`) */
+uint64_t b200_ctx_launch_count(b200_ctx *ctx);
+
+/* device arena handed to the reference's BumpAllocator (alloc.rs:31-105): n_elems B128 elements */
+int32_t b200_dev_alloc(b200_ctx *ctx, uint64_t n_elems, b200_dev_ptr *out);
+int32_t b200_dev_free(b200_ctx *ctx, b200_dev_ptr p);
+/* pinned host staging memory (optional; pageable host pointers are accepted everywhere) */
+int32_t b200_host_alloc(b200_ctx *ctx, uint64_t n_bytes, void **out);
+int32_t b200_host_free(b200_ctx *ctx, void *p);
+
+int32_t b200_copy_h2d(b200_ctx *ctx, const void *host_src, b200_dev_ptr dst, uint64_t n_elems);
+int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *host_dst, uint64_t n_elems); /* synchronous */
+int32_t b200_copy_d2d(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n_elems);
+/* ComputeLayer::fill (layer.rs:74-87) */
+int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n_elems, const uint64_t value[2]);
+int32_t b200_sync(b200_ctx *ctx);
+
+/* ---- deferred scalar results (ComputeLayerExecutor::OpValue; ComputeLayer::execute returns them,
+ *      layer.rs:62-72).  Slots are valid until b200_results_reset. ------------------------------ */
+int32_t b200_results_reset(b200_ctx *ctx);
+int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uint64_t *host_out /* 2*n */);
+
+/* ---- ComputeLayerExecutor ops ------------------------------------------------------------------ */
+/* extrapolate_line (layer.rs:402-426; cpu/layer.rs:393-408): e0[i] += (e1[i]-e0[i])*z */
+int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr evals_0, uint64_t n0, b200_dev_ptr evals_1,
+							  uint64_t n1, const uint64_t z[2]);
+/* tensor_expand (layer.rs:269-296; cpu/layer.rs:282-302) */
+int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, uint32_t log_n,
+						   const uint64_t *coordinates /* 2*k */, uint32_t k);
+/* inner_product (layer.rs:247-267; cpu/layer.rs:205-236): a = SubfieldSlice{a, tower_level} */
+int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t tower_level,
+						   b200_dev_ptr b, uint64_t n_b, uint32_t *result_slot);
+/* fold_left / fold_right (layer.rs:298-356; cpu/layer.rs:238-280, 574-675) */
+int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t tower_level,
+					   b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out);
+int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t tower_level,
+						b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out);
+
+/* Arithmetic circuit (crates/math/src/arith_expr.rs:200-206); ComputeLayer::compile_expr */
+typedef struct {
+	uint32_t op; /* 0 Add(l,r)  1 Mul(l,r)  2 Pow(l, r = exponent)  3 Const(c)  4 Var(l) */
+	uint32_t l;
+	uint64_t r;
+	uint64_t c_lo, c_hi;
+} b200_expr_step;
+typedef struct b200_expr b200_expr;
+int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n_steps, b200_expr **out);
+void b200_expr_free(b200_expr *e);
+uint32_t b200_expr_n_vars(const b200_expr *e);
+
+/* compute_composite (layer.rs:428-464; cpu/layer.rs:410-435) */
+int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs,
+							   uint64_t row_len, b200_dev_ptr out, uint64_t n_out, const b200_expr *expr);
+/* pairwise_product_reduce (layer.rs:466-509; cpu/layer.rs:437-484) */
+int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t n_in,
+									 const b200_dev_ptr *round_outputs, const uint64_t *round_output_lens,
+									 uint32_t n_rounds);
+
+/* ---- KernelExecutor ops (layer.rs:518-590), issued with log_chunks = 0 (whole buffers) --------- */
+/* decl_value */
+int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *value_slot);
+/* sum_composition_evals: slot += batch_coeff * sum_i expr(inputs[.][i]) */
+int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs,
+										  uint64_t row_len, const b200_expr *expr,
+										  const uint64_t batch_coeff[2], uint32_t value_slot);
+int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr src1, b200_dev_ptr src2, b200_dev_ptr dst);
+int32_t b200_kernel_add_assign(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr src, b200_dev_ptr dst);
+
+/* Fused form of v3::calculate_round_evals (core/src/protocols/sumcheck/v3/bivariate_product.rs:
+ * 303-408): the traced accumulate_kernels program {sum(hi_a*hi_b), add(lo,hi), sum(inf_a*inf_b)}
+ * over m multilinears of 2^n_vars elements; writes y_1 and y_inf to two result slots. */
+int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *multilins, uint32_t n_multilins,
+								   uint32_t n_vars, const uint32_t *idx_a, const uint32_t *idx_b,
+								   uint32_t n_compositions, const uint64_t batch_coeff[2],
+								   uint32_t *slot_y1, uint32_t *slot_yinf);
+
+/* ---- additive NTT (binius_ntt::AdditiveNTT<F>, additive_ntt.rs:58-166) ------------------------- */
+typedef struct b200_ntt b200_ntt;
+/* SingleThreadedNTT::new(log_domain_size) over BinaryField{8,16,32}b: field_log_bits = 3,4,5
+ * (single_threaded.rs:27-45; twiddles per twiddle.rs:244-313) */
+int32_t b200_ntt_create(b200_ctx *ctx, uint32_t field_log_bits, uint32_t log_domain_size, b200_ntt **out);
+void b200_ntt_destroy(b200_ntt *ntt);
+uint32_t b200_ntt_log_domain_size(const b200_ntt *ntt);
+/* get_subspace_eval(i, j) (single_threaded.rs:91-93), host-side */
+int32_t b200_ntt_get_subspace_eval(const b200_ntt *ntt, uint32_t i, uint64_t j, uint64_t out[2]);
+/* forward/inverse_transform on DEVICE data of n_elems scalars of 2^elem_log_bits bits each
+ * (elem_log_bits >= field_log_bits; 7 = packed B128 i.e. *_transform_ext, additive_ntt.rs:137-165).
+ * Scalar index = x | y << log_x | z << (log_x+log_y)  (additive_ntt.rs:8-27). */
+int32_t b200_ntt_forward(b200_ctx *ctx, const b200_ntt *ntt, b200_dev_ptr data, uint32_t elem_log_bits,
+						 uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z, uint64_t coset,
+						 uint32_t coset_bits, uint32_t skip_rounds);
+int32_t b200_ntt_inverse(b200_ctx *ctx, const b200_ntt *ntt, b200_dev_ptr data, uint32_t elem_log_bits,
+						 uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z, uint64_t coset,
+						 uint32_t coset_bits, uint32_t skip_rounds);
+/* The trait-shaped variants: data is a HOST `&mut [P]`; staged H2D, transformed, D2H (synchronous). */
+int32_t b200_ntt_forward_host(b200_ctx *ctx, const b200_ntt *ntt, void *host_data, uint32_t elem_log_bits,
+							  uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z,
+							  uint64_t coset, uint32_t coset_bits, uint32_t skip_rounds);
+int32_t b200_ntt_inverse_host(b200_ctx *ctx, const b200_ntt *ntt, void *host_data, uint32_t elem_log_bits,
+							  uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z,
+							  uint64_t coset, uint32_t coset_bits, uint32_t skip_rounds);
+
+/* fri_fold (layer.rs:358-400; cpu/layer.rs:304-391) */
+int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint32_t log_batch_size,
+					  const uint64_t *challenges /* 2*n_challenges */, uint32_t n_challenges,
+					  b200_dev_ptr data_in, uint64_t n_in, b200_dev_ptr data_out, uint64_t n_out);
+
+/* ---- ComputationBackend (old HAL, crates/hal/src/backend.rs:35-83) on device-resident data ---- */
+/* tensor_product_full_query(query) (backend.rs:42-45 -> math/src/tensor_prod_eq_ind.rs:94-101):
+ * out[0..2^k) = eq-indicator expansion of `query`; out must hold 2^k elements. */
+int32_t b200_tensor_product_full_query(b200_ctx *ctx, const uint64_t *query /* 2*k */, uint32_t k,
+									   b200_dev_ptr out, uint64_t n_out);
+/* sumcheck_fold_multilinears, HighToLow, Folded branch (backend.rs:65-75 ->
+ * hal/src/sumcheck_folding.rs:149-241 -> math/src/fold.rs:648-696 fold_left_lerp_inplace):
+ * each multilinear of 2^n_vars evals with `non_const_prefix[t]` stored elements followed by an
+ * implicit constant suffix `suffix_eval[t]`; folds in place and reports the new stored length. */
+int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *multilins,
+										   uint32_t n_multilins, uint32_t n_vars,
+										   const uint64_t *non_const_prefix, const uint64_t *suffix_evals /* 2*m */,
+										   const uint64_t challenge[2], uint64_t *new_lens);
+/* sumcheck_compute_round_evals for eq-ind (zerocheck) provers, HighToLow (backend.rs:48-62 ->
+ * hal/src/sumcheck_round_calculation.rs:126-349; evaluator core/.../prove/eq_ind.rs:646-731):
+ * for each composition c and each requested evaluation point, R = sum_i E[i] * C_z(P(i)).
+ * eval point codes: 1 = evaluate at 1, 2 = Karatsuba infinity point (leading term on hi-lo),
+ * k >= 3 = finite domain point given in `domain_points`.  Results: n_compositions * n_points slots. */
+int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *multilins, uint32_t n_multilins,
+								uint32_t n_vars, b200_dev_ptr eq_ind /* 2^(n_vars-1) */,
+								const b200_expr *const *compositions,
+								const b200_expr *const *compositions_leading, uint32_t n_compositions,
+								const uint32_t *point_codes, const uint64_t *domain_points /* 2*n_points */,
+								uint32_t n_points, uint32_t *first_slot);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BINIUS_B200_H */

@@ -1,0 +1,326 @@
+"""GPU parity tests of the ComputeLayer ops: CUDA path (through the C ABI) vs the CPU oracle on the
+same seeded inputs.  Mirrors crates/compute_test_utils/src/layer.rs (instantiated for CpuLayer in
+crates/compute/tests/layer.rs:12-165).  Bit-exact (integer GF(2^k) arithmetic)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hal():
+    import binius_b200
+
+    layer = binius_b200.B200Layer(0)
+    yield layer
+    layer.close()
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.uint64).reshape(-1, 2), np.asarray(b, dtype=np.uint64).reshape(-1, 2))
+
+
+def test_copy_fill_roundtrip(hal, oracle):
+    x = oracle.rand_b128(1, 1000)
+    d = hal.to_device(x)
+    assert _same(hal.to_host(d), x)
+    d2 = hal.dev_alloc(1000)
+    hal.copy_d2d(d, d2)
+    assert _same(hal.to_host(d2), x)
+    v = 0x0123456789ABCDEF_FEDCBA9876543210
+    hal.fill(d2.slice(10, 500), v)
+    got = oracle.to_ints(hal.to_host(d2))
+    exp = oracle.to_ints(x)
+    exp[10:500] = [v] * 490
+    assert got == exp
+    import binius_b200
+
+    with pytest.raises(binius_b200.InputValidation):
+        hal.copy_d2d(d, d2.slice(0, 999))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 32, 1000, 1 << 15, (1 << 17) + 13])
+def test_extrapolate_line(hal, oracle, n):
+    # cfg#1 of BASELINE.json is n = 2^15 (2^16 input coefficients); compute_test_utils layer.rs:370-420
+    e0, e1 = oracle.rand_b128(10 + n, n), oracle.rand_b128(20 + n, n)
+    z = oracle.to_ints(oracle.rand_b128(30 + n, 1))[0]
+    d0, d1 = hal.to_device(e0), hal.to_device(e1)
+    hal.execute(lambda ex: (ex.extrapolate_line(d0, d1, z), [])[1])
+    assert _same(hal.to_host(d0), oracle.extrapolate_line(e0, e1, z))
+    assert _same(hal.to_host(d1), e1)
+
+
+def test_extrapolate_line_edge_values(hal, oracle, kat):
+    import binius_b200
+
+    g = kat["generators"]["128"]
+    special = [0, 1, (1 << 128) - 1, 0xFF, 0xFFFF, 0xFFFFFFFF, (1 << 64) - 1, g, 1 << 127, 1 << 64]
+    e0 = oracle.to_arr(special * 4)
+    e1 = oracle.to_arr((special[3:] + special[:3]) * 4)
+    for z in [0, 1, g, (1 << 128) - 1, 1 << 127, 0x2]:
+        d0, d1 = hal.to_device(e0), hal.to_device(e1)
+        hal.execute(lambda ex: (ex.extrapolate_line(d0, d1, z), [])[1])
+        assert _same(hal.to_host(d0), oracle.extrapolate_line(e0, e1, z))
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.extrapolate_line(d0, d1.slice(0, 5), 3), [])[1])
+
+
+def test_extrapolate_line_unaligned_subslices(hal, oracle):
+    # ALIGNMENT = 1: split_half below any packing width (memory.rs:165-195)
+    x = oracle.rand_b128(77, 64)
+    d = hal.to_device(x)
+    z = 0xDEADBEEF00000000CAFEBABE12345678
+    cur = d.slice(3, 3 + 32)
+    ref = x[3:35].copy()
+    while cur.len() > 1:
+        lo, hi = cur.split_half_mut()
+        hal.execute(lambda ex: (ex.extrapolate_line(lo, hi, z), [])[1])
+        h = len(ref) // 2
+        ref = oracle.extrapolate_line(ref[:h], ref[h:], z)
+        cur = lo
+        assert _same(hal.to_host(cur), ref)
+
+
+@pytest.mark.parametrize("log_n,k", [(0, 0), (0, 1), (0, 5), (2, 3), (0, 11), (3, 10), (0, 14), (12, 2), (5, 12)])
+def test_tensor_expand(hal, oracle, log_n, k):
+    # compute_test_utils layer.rs:30-71 (zero-filled tail, compare with tensor_prod_eq_ind)
+    import random
+
+    rng = random.Random(log_n * 100 + k)
+    coords = [rng.getrandbits(128) for _ in range(k)]
+    data = np.zeros((1 << (log_n + k), 2), np.uint64)
+    data[: 1 << log_n] = oracle.rand_b128(5, 1 << log_n)
+    d = hal.to_device(data)
+    hal.execute(lambda ex: (ex.tensor_expand(log_n, coords, d), [])[1])
+    assert _same(hal.to_host(d), oracle.tensor_expand(data, log_n, coords))
+
+
+def test_tensor_expand_overwrites_and_validates(hal, oracle):
+    # the upper part is an OUTPUT (layer.rs:269-296 definition; tensor_prod_eq_ind.rs:70-72 assigns)
+    import binius_b200
+
+    coords = [3, 0x1234 << 64, 7, 9, 11, 13, 15, 17, 19, 21, 23, 25, 27]
+    for k in (3, 13):
+        data = oracle.rand_b128(9, 1 << k)  # garbage beyond element 0
+        clean = np.zeros_like(data)
+        clean[0] = data[0]
+        d = hal.to_device(data)
+        hal.execute(lambda ex: (ex.tensor_expand(0, coords[:k], d), [])[1])
+        assert _same(hal.to_host(d), oracle.tensor_expand(clean, 0, coords[:k]))
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.tensor_expand(1, coords[:3], d), [])[1])
+
+
+def test_eq_ind_partial_eval(hal, oracle):
+    # compute/src/ops.rs:26-50
+    import binius_b200
+
+    holder_mem = hal.dev_alloc(1 << 10)
+    alloc = binius_b200.BumpAllocator(holder_mem)
+    point = [5, 1 << 100, 0xABCDEF, 77]
+    out = binius_b200.eq_ind_partial_eval(hal, alloc, point)
+    exp = oracle.tensor_expand(oracle.to_arr([1] + [0] * 15), 0, point)
+    assert _same(hal.to_host(out), exp)
+    assert alloc.remaining() == (1 << 10) - 16
+
+
+@pytest.mark.parametrize("lvl", [0, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("log_b", [7, 10, 14])
+def test_inner_product(hal, oracle, lvl, log_b):
+    # compute_test_utils layer.rs:73-120
+    import binius_b200
+
+    n_b = 1 << log_b
+    n_a = n_b >> (7 - lvl)
+    a, b = oracle.rand_b128(40 + lvl, n_a), oracle.rand_b128(50 + log_b, n_b)
+    da, db = hal.to_device(a), hal.to_device(b)
+    (got,) = hal.execute(lambda ex: [ex.inner_product(binius_b200.SubfieldSlice(da, lvl), db)])
+    assert got == oracle.inner_product(a, lvl, b)
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: [ex.inner_product(binius_b200.SubfieldSlice(da, lvl), db.slice(0, n_b - 1))])
+
+
+@pytest.mark.parametrize("lvl", [0, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("log_q", [0, 2, 5])
+def test_fold_left_right(hal, oracle, lvl, log_q):
+    # compute_test_utils layer.rs:122-260
+    import binius_b200
+
+    n_mat = 1 << 6
+    log_evals = 6 + 7 - lvl
+    mat, vec = oracle.rand_b128(60 + lvl, n_mat), oracle.rand_b128(70 + log_q, 1 << log_q)
+    n_out = 1 << (log_evals - log_q)
+    dm, dv = hal.to_device(mat), hal.to_device(vec)
+    dl, dr = hal.dev_alloc(n_out), hal.dev_alloc(n_out)
+    hal.execute(lambda ex: (ex.fold_left(binius_b200.SubfieldSlice(dm, lvl), dv, dl), ex.fold_right(binius_b200.SubfieldSlice(dm, lvl), dv, dr), [])[2])
+    assert _same(hal.to_host(dl), oracle.fold_left(mat, lvl, vec, n_out))
+    assert _same(hal.to_host(dr), oracle.fold_right(mat, lvl, vec, n_out))
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.fold_left(binius_b200.SubfieldSlice(dm, lvl), dv, dl.slice(0, n_out - 1)), [])[1])
+    hal.dev_free(dl)
+    hal.dev_free(dr)
+
+
+def _expr_cases():
+    c = 0x1234567890ABCDEF1122334455667788
+    return [
+        ([("var", 0), ("var", 1), ("mul", 0, 1)], 2),  # BivariateProduct
+        ([("const", 1), ("var", 0), ("mul", 0, 1), ("var", 1), ("mul", 2, 3)], 2),  # IndexComposition<BivariateProduct>
+        ([("var", 0), ("var", 1), ("mul", 0, 1), ("const", c), ("add", 2, 3), ("pow", 4, 3), ("var", 2), ("add", 5, 6)], 3),
+        ([("var", 0), ("pow", 0, 0)], 1),
+        ([("var", 2), ("var", 0), ("add", 0, 1), ("pow", 2, 5)], 3),
+    ]
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_compute_composite_and_kernel_sum(hal, oracle, case):
+    # compute_test_utils layer.rs:422-520 (compute_composite), :262-330 (kernel add / sum)
+    import binius_b200
+
+    steps, n_vars = _expr_cases()[case]
+    n = 1 << 9
+    ins = [oracle.rand_b128(80 + j, n) for j in range(n_vars)]
+    dins = [hal.to_device(a) for a in ins]
+    dout = hal.dev_alloc(n)
+    ev = hal.compile_expr(binius_b200.ArithCircuit(steps))
+    hal.execute(lambda ex: (ex.compute_composite(binius_b200.SlicesBatch(dins, n), dout, ev), [])[1])
+    assert _same(hal.to_host(dout), oracle.compute_composite(ins, steps))
+    coeff, init = 0xABCDEF0123456789 << 50, 0x77
+
+    def kern(kex, log_chunks, bufs):
+        acc = kex.decl_value(init)
+        kex.sum_composition_evals(binius_b200.SlicesBatch([b.to_ref() for b in bufs], n), ev, coeff, acc)
+        return [acc]
+
+    (got,) = hal.execute(lambda ex: ex.accumulate_kernels(kern, [binius_b200.KernelMemMap.Chunked(d, 3) for d in dins]))
+    assert got == oracle.sum_composition_evals(ins, steps, coeff, init)
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.compute_composite(binius_b200.SlicesBatch(dins, n), dout.slice(0, n - 1), ev), [])[1])
+
+
+def test_kernel_add_and_map_kernels(hal, oracle):
+    # compute_test_utils layer.rs:262-330: map_kernels with Chunked, ChunkedMut and Local buffers
+    import binius_b200
+
+    n, log_n = 1 << 10, 10
+    a, b = oracle.rand_b128(90, n), oracle.rand_b128(91, n)
+    da, db, dc = hal.to_device(a), hal.to_device(b), hal.dev_alloc(n)
+
+    def kern(kex, log_chunks, bufs):
+        la = log_n - log_chunks
+        kex.add(la, bufs[0].to_ref(), bufs[1].to_ref(), bufs[3].data)  # local = a + b
+        kex.add_assign(la, bufs[0].to_ref(), bufs[3].data)  # local += a  -> b
+        kex.add(la, bufs[3].to_ref(), bufs[0].to_ref(), bufs[2].data)  # c = b + a
+        return None
+
+    M = binius_b200.KernelMemMap
+    hal.execute(lambda ex: (ex.map_kernels(kern, [M.Chunked(da, 0), M.Chunked(db, 0), M.ChunkedMut(dc, 0), M.Local(log_n)]), [])[1])
+    assert _same(hal.to_host(dc), a ^ b)
+    assert M.log_chunks_range([M.Chunked(da, 3), M.Local(6)]) == (0, 6)
+    assert M.log_chunks_range([M.Chunked(da, 3), M.Local(9)]) == (0, 7)
+
+
+@pytest.mark.parametrize("log_n", [1, 4, 11])
+def test_pairwise_product_reduce(hal, oracle, log_n):
+    # compute_test_utils layer.rs:522-600
+    import binius_b200
+
+    x = oracle.rand_b128(100 + log_n, 1 << log_n)
+    dx = hal.to_device(x)
+    outs = [hal.dev_alloc(1 << (log_n - r - 1)) for r in range(log_n)]
+    hal.execute(lambda ex: (ex.pairwise_product_reduce(dx, outs), [])[1])
+    for got, exp in zip(outs, oracle.pairwise_product_reduce(x)):
+        assert _same(hal.to_host(got), exp)
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.pairwise_product_reduce(dx, outs[:-1] if log_n > 1 else outs + outs), [])[1])
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.pairwise_product_reduce(dx.slice(0, 1), []), [])[1])
+
+
+@pytest.mark.parametrize("n_vars,m", [(1, 2), (6, 4), (12, 8)])
+def test_bivariate_round_evals_fused_and_traced(hal, oracle, n_vars, m):
+    # core/src/protocols/sumcheck/v3/bivariate_product.rs:303-408, both as the fused entry point and
+    # as the literal accumulate_kernels program the reference prover issues
+    import random
+
+    import binius_b200
+
+    rng = random.Random(n_vars)
+    mls = [oracle.rand_b128(110 + t, 1 << n_vars) for t in range(m)]
+    dmls = [hal.to_device(x) for x in mls]
+    pairs = [(rng.randrange(m), rng.randrange(m)) for _ in range(m)]
+    alpha = rng.getrandbits(128)
+    exp = oracle.bivariate_round_evals(mls, n_vars, pairs, alpha)
+    got = hal.execute(lambda ex: list(ex.bivariate_round_evals(dmls, n_vars, pairs, alpha)))
+    assert got == exp
+
+    half_log = n_vars - 1
+    M, SB = binius_b200.KernelMemMap, binius_b200.SlicesBatch
+    ev = hal.compile_expr(binius_b200.ArithCircuit([("var", 0), ("var", 1), ("mul", 0, 1)]))
+    pows = [1]
+    for _ in pairs:
+        pows.append(oracle.mul(pows[-1], alpha))
+
+    def kern(kex, log_chunks, bufs):
+        sz = half_log - log_chunks
+        lo = [bufs[3 * t] for t in range(m)]
+        hi = [bufs[3 * t + 1] for t in range(m)]
+        inf = [bufs[3 * t + 2] for t in range(m)]
+        y1 = kex.decl_value(0)
+        for c, (ia, ib) in enumerate(pairs):
+            kex.sum_composition_evals(SB([hi[ia].to_ref(), hi[ib].to_ref()], 1 << sz), ev, pows[c], y1)
+        for t in range(m):
+            kex.add(sz, lo[t].to_ref(), hi[t].to_ref(), inf[t].data)
+        yinf = kex.decl_value(0)
+        for c, (ia, ib) in enumerate(pairs):
+            kex.sum_composition_evals(SB([inf[ia].to_ref(), inf[ib].to_ref()], 1 << sz), ev, pows[c], yinf)
+        return [y1, yinf]
+
+    maps = []
+    for d in dmls:
+        lo, hi = d.split_half()
+        maps += [M.Chunked(lo, 0), M.Chunked(hi, 0), M.Local(half_log)]
+    got2 = hal.execute(lambda ex: ex.accumulate_kernels(kern, maps))
+    assert got2 == exp
+
+
+def test_fri_fold(hal, oracle):
+    # compute_test_utils layer.rs:332-368 ; cpu/layer.rs:304-391
+    import random
+
+    import binius_b200
+
+    ntt = binius_b200.B200AdditiveNTT(hal, 5, 12)
+    ontt = oracle.NTT(5, 12)
+    rng = random.Random(5)
+    for log_len, log_batch, n_ch in [(6, 2, 2), (6, 0, 3), (5, 2, 5), (4, 3, 3), (3, 0, 0), (10, 4, 4), (12, 0, 4)]:
+        ch = [rng.getrandbits(128) for _ in range(n_ch)]
+        data = oracle.rand_b128(log_len * 10 + n_ch, 1 << (log_len + log_batch))
+        n_out = 1 << (log_len - (n_ch - log_batch))
+        din, dout = hal.to_device(data), hal.dev_alloc(n_out)
+        hal.execute(lambda ex: (ex.fri_fold(ntt, log_len, log_batch, ch, din, dout), [])[1])
+        assert _same(hal.to_host(dout), ontt.fri_fold(log_len, log_batch, ch, data, n_out))
+    with pytest.raises(binius_b200.InputValidation):
+        hal.execute(lambda ex: (ex.fri_fold(ntt, 4, 2, [1], din.slice(0, 64), dout.slice(0, 16)), [])[1])
+    for i in range(1, 13):
+        for j in (0, 1, 5, 100):
+            assert ntt.get_subspace_eval(i, j) == ontt.get_subspace_eval(i, j)
+
+
+def test_holder_and_bump_allocator(oracle):
+    # ComputeHolder::to_data + BumpAllocator OutOfMemory (alloc.rs:110-114)
+    import binius_b200
+
+    holder = binius_b200.B200LayerHolder.new(1 << 8, 1 << 12)
+    data = holder.to_data()
+    a = data.dev_alloc.alloc(1 << 11)
+    b = data.dev_alloc.alloc(1 << 11)
+    assert a.ptr + 16 * (1 << 11) == b.ptr
+    with pytest.raises(binius_b200.AllocError):
+        data.dev_alloc.alloc(1)
+    h = data.host_alloc.alloc(16)
+    h[:] = oracle.rand_b128(3, 16)
+    data.hal.copy_h2d(h, a.slice(0, 16))
+    assert _same(data.hal.to_host(a.slice(0, 16)), h)
+    assert _same(data.hal.to_host(a.slice(16, 32)), np.zeros((16, 2), np.uint64))
+    holder.layer.close()
