@@ -117,7 +117,6 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	int32_t rc = B200_OK;
 #define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
 	SET(k_basis_products, FIELD_TABLE_BYTES);
-	SET(k_lerp_lut, LUT_BYTES + 2048);
 	SET(k_expand_lut, LUT_BYTES + 2048);
 	SET(k_expand_small, FIELD_TABLE_BYTES + 16 * 2048);
 	SET(k_inner_product, FIELD_TABLE_BYTES);
@@ -285,25 +284,52 @@ static int32_t launch_basis(b200_ctx *ctx, const uint64_t *zs, uint32_t n_maps) 
 	return B200_OK;
 }
 
-static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint64_t z[2]) {
-	uint64_t tiles = 0;
-	std::vector<LerpSeg> live;
-	for (auto &s : segs) {
-		if (s.upper == 0) continue;
-		s.tile_start = tiles;
-		tiles += (s.upper + FOLD_TILE - 1) / FOLD_TILE;
-		live.push_back(s);
+}  // extern "C"
+template <uint32_t THREADS, uint32_t UNR, int MINB>
+static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
+	constexpr uint32_t TILE = THREADS * UNR;
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(ctx, cudaFuncSetAttribute(k_lerp_lut<THREADS, UNR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LUT_BYTES + 2048)));
+		attr_set = true;
 	}
-	if (live.empty()) return B200_OK;
-	int32_t rc = launch_basis(ctx, z, 1);
-	if (rc) return rc;
-	void *dsegs;
-	rc = stage_args(ctx, live.data(), sizeof(LerpSeg) * live.size(), &dsegs);
-	if (rc) return rc;
-	uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * 3);
-	k_lerp_lut<<<grid, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const LerpSeg *)dsegs, (uint32_t)live.size(), tiles, ctx->d_basis);
-	B200_LAUNCH_CHECK(ctx);
+	// segments travel by value in the kernel parameters: no staging copy, one launch per <= 48 segments
+	for (size_t s0 = 0; s0 < live.size(); s0 += LERP_MAX_SEGS) {
+		LerpArgs A;
+		A.n_segs = (uint32_t)std::min<size_t>(LERP_MAX_SEGS, live.size() - s0);
+		uint64_t tiles = 0;
+		for (uint32_t i = 0; i < A.n_segs; i++) {
+			A.segs[i] = live[s0 + i];
+			A.segs[i].tile_start = tiles;
+			tiles += (A.segs[i].upper + TILE - 1) / TILE;
+		}
+		A.n_tiles = tiles;
+		A.z = to_u4(z);
+		uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * MINB);
+		k_lerp_lut<THREADS, UNR, MINB><<<grid, THREADS, LUT_BYTES + 2048, ctx->stream>>>(A);
+		B200_LAUNCH_CHECK(ctx);
+	}
 	return B200_OK;
+}
+
+extern "C" {
+static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint64_t z[2]) {
+	std::vector<LerpSeg> live;
+	for (auto &s : segs)
+		if (s.upper) {
+			live.push_back(s);
+		}
+	if (live.empty()) return B200_OK;
+	static int variant = getenv("B200_FOLD_VARIANT") ? atoi(getenv("B200_FOLD_VARIANT")) : 0;
+	switch (variant) {
+	case 1: return launch_lerp_variant<512, 4, 2>(ctx, live, z);
+	case 2: return launch_lerp_variant<256, 2, 4>(ctx, live, z);
+	case 3: return launch_lerp_variant<256, 4, 3>(ctx, live, z);
+	case 4: return launch_lerp_variant<1024, 2, 1>(ctx, live, z);
+	case 5: return launch_lerp_variant<512, 3, 2>(ctx, live, z);
+	case 6: return launch_lerp_variant<384, 2, 3>(ctx, live, z);
+	default: return launch_lerp_variant<512, 2, 2>(ctx, live, z);
+	}
 }
 
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_dev_ptr e1, uint64_t n1, const uint64_t z[2]) {
@@ -348,17 +374,12 @@ int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, 
 		k_expand_small<<<1, 256, FIELD_TABLE_BYTES + (16u << (log_n + k_small)), ctx->stream>>>(ctx->d_tables, (uint4 *)data, log_n, (const uint4 *)dc, k_small);
 		B200_LAUNCH_CHECK(ctx);
 	}
-	for (uint32_t r0 = k_small; r0 < k; r0 += MAX_LINMAPS) {
-		uint32_t cnt = std::min(MAX_LINMAPS, k - r0);
-		int32_t rc = launch_basis(ctx, coords + 2 * r0, cnt);
-		if (rc) return rc;
-		for (uint32_t r = r0; r < r0 + cnt; r++) {
-			uint64_t half = 1ull << (log_n + r);
-			uint64_t tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
-			uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * 3);
-			k_expand_lut<<<grid, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((uint4 *)data, half, ctx->d_basis + 128 * (r - r0));
-			B200_LAUNCH_CHECK(ctx);
-		}
+	for (uint32_t r = k_small; r < k; r++) {
+		uint64_t half = 1ull << (log_n + r);
+		uint64_t tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
+		uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * 3);
+		k_expand_lut<<<grid, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((uint4 *)data, half, to_u4(coords + 2 * r));
+		B200_LAUNCH_CHECK(ctx);
 	}
 	return B200_OK;
 }

@@ -34,37 +34,49 @@ struct LerpSeg {
 	uint4 suffix;
 	uint64_t tile_start;  // first global tile of this segment (prefix sum), filled by the host
 };
+constexpr uint32_t LERP_MAX_SEGS = 48;  // segments passed by value in the kernel parameters
+struct LerpArgs {
+	LerpSeg segs[LERP_MAX_SEGS];
+	uint32_t n_segs;
+	uint64_t n_tiles;
+	uint4 z;
+};
 
 constexpr uint32_t FOLD_THREADS = 512;
 constexpr uint32_t FOLD_UNROLL = 2;
 constexpr uint32_t FOLD_TILE = FOLD_THREADS * FOLD_UNROLL;
 
-__global__ void __launch_bounds__(FOLD_THREADS) k_lerp_lut(const LerpSeg *__restrict__ segs, uint32_t n_segs, uint64_t n_tiles,
-															const uint4 *__restrict__ W) {
+// THREADS x UNR elements per tile; host must compute tile_start with the same tile size
+template <uint32_t THREADS, uint32_t UNR, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_lerp_lut(const __grid_constant__ LerpArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *tbl = smem;
 	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
-	lut_build(tbl, stage, W);
+	lut_build_mul(tbl, stage, A.z);
 	const LutLane L = lut_lane_init();
+	constexpr uint32_t TILE = THREADS * UNR;
 
 	uint32_t seg = 0;
-	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		while (seg + 1 < n_segs && segs[seg + 1].tile_start <= tile) seg++;
-		const LerpSeg S = segs[seg];
-		uint64_t base = (tile - S.tile_start) * FOLD_TILE + threadIdx.x;
-		uint4 a[FOLD_UNROLL], b[FOLD_UNROLL];
+	for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+		while (seg + 1 < A.n_segs && A.segs[seg + 1].tile_start <= tile) seg++;
+		const LerpSeg &S = A.segs[seg];
+		uint64_t base = (tile - S.tile_start) * TILE + threadIdx.x;
+		const uint64_t upper = S.upper, pivot = S.pivot;
+		uint4 *e0 = S.e0;
+		const uint4 *e1 = S.e1;
+		uint4 a[UNR], b[UNR];
 #pragma unroll
-		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
-			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
-			if (i < S.upper) {
-				a[u] = S.e0[i];
-				b[u] = i < S.pivot ? __ldg(S.e1 + i) : S.suffix;
+		for (uint32_t u = 0; u < UNR; u++) {
+			uint64_t i = base + (uint64_t)u * THREADS;
+			if (i < upper) {
+				a[u] = e0[i];
+				b[u] = i < pivot ? __ldg(e1 + i) : S.suffix;
 			}
 		}
 #pragma unroll
-		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
-			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
-			if (i < S.upper) S.e0[i] = a[u] ^ lut_apply(tbl, L, a[u] ^ b[u]);
+		for (uint32_t u = 0; u < UNR; u++) {
+			uint64_t i = base + (uint64_t)u * THREADS;
+			if (i < upper) e0[i] = a[u] ^ lut_apply(tbl, L, a[u] ^ b[u]);
 		}
 	}
 }
@@ -72,11 +84,11 @@ __global__ void __launch_bounds__(FOLD_THREADS) k_lerp_lut(const LerpSeg *__rest
 // ------------------------------------------------------------------------------------------------
 // one tensor-expansion round:  p = x * r ; lo[j] = x ^ p ; hi[j] = p        j < half
 // reference: compute/src/layer.rs:269-296 (definition), math/src/tensor_prod_eq_ind.rs:35-77
-__global__ void __launch_bounds__(FOLD_THREADS) k_expand_lut(uint4 *__restrict__ data, uint64_t half, const uint4 *__restrict__ W) {
+__global__ void __launch_bounds__(FOLD_THREADS, 3) k_expand_lut(uint4 *__restrict__ data, uint64_t half, uint4 r) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *tbl = smem;
 	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
-	lut_build(tbl, stage, W);
+	lut_build_mul(tbl, stage, r);
 	const LutLane L = lut_lane_init();
 	uint64_t n_tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
 	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

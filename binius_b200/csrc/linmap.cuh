@@ -38,23 +38,65 @@ __device__ __forceinline__ LutLane lut_lane_init() {
 	return L;
 }
 
-// Build the 64 KiB table from the 128 basis images W[i] = L(beta_i) (global memory).
-// `stage` = 2 KiB of shared memory used to stage W.  All threads of the CTA must call.
-__device__ __forceinline__ void lut_build(uint8_t *tbl, uint4 *stage, const uint4 *__restrict__ W) {
-	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) stage[i] = __ldg(W + i);
-	__syncthreads();
+// ---- multiplication by the tower generators, limb-wise (no tables) -------------------------------
+// alpha_w<K>(w): multiply every 2^K-bit limb of the word w by X_{K-1}  (K <= 5), i.e. mul_alpha at
+// level K (reference pairwise_recursive_arithmetic.rs:48-62): (a0, a1) -> (a1, a0 + alpha_{K-1}(a1)).
+template <int K> __device__ __forceinline__ uint32_t alpha_w(uint32_t w) {
+	constexpr uint32_t M = K == 1 ? 0x55555555u : K == 2 ? 0x33333333u : K == 3 ? 0x0F0F0F0Fu : K == 4 ? 0x00FF00FFu : 0x0000FFFFu;
+	constexpr int H = 1 << (K - 1);
+	uint32_t hi = (w >> H) & M, lo = w & M;
+	return hi | ((lo ^ alpha_w<K - 1>(hi)) << H);
+}
+template <> __device__ __forceinline__ uint32_t alpha_w<0>(uint32_t w) { return w; }
+
+// multiply a B128 element by X_k = beta_{2^k} (k = 0..6)
+__device__ __forceinline__ uint4 mul_tower_gen(uint4 v, uint32_t k) {
+	switch (k) {
+	case 0: return make_uint4(alpha_w<1>(v.x), alpha_w<1>(v.y), alpha_w<1>(v.z), alpha_w<1>(v.w));
+	case 1: return make_uint4(alpha_w<2>(v.x), alpha_w<2>(v.y), alpha_w<2>(v.z), alpha_w<2>(v.w));
+	case 2: return make_uint4(alpha_w<3>(v.x), alpha_w<3>(v.y), alpha_w<3>(v.z), alpha_w<3>(v.w));
+	case 3: return make_uint4(alpha_w<4>(v.x), alpha_w<4>(v.y), alpha_w<4>(v.z), alpha_w<4>(v.w));
+	case 4: return make_uint4(alpha_w<5>(v.x), alpha_w<5>(v.y), alpha_w<5>(v.z), alpha_w<5>(v.w));
+	case 5: return make_uint4(v.y, v.x ^ alpha_w<5>(v.y), v.w, v.z ^ alpha_w<5>(v.w));
+	default: return make_uint4(v.z, v.w, v.x ^ v.w, v.y ^ v.z ^ alpha_w<5>(v.w));  // (lo,hi)->(hi, lo + alpha_6(hi))
+	}
+}
+
+// beta_i * z for the tower basis beta_i = 1 << i = prod_{k : bit k of i} X_k
+__device__ __forceinline__ uint4 basis_image(uint4 z, uint32_t i) {
+#pragma unroll
+	for (uint32_t k = 0; k < 7; k++)
+		if ((i >> k) & 1u) z = mul_tower_gen(z, k);
+	return z;
+}
+
+// Build the 64 KiB table of the map x -> x * z.  `stage` = 2 KiB of shared memory holding the basis
+// images transposed (stage[bit * 16 + k] = beta_{8k+bit} * z) so that the 8 lanes of a quarter-warp
+// read and write 8 different bank-quads (conflict-free build).  All threads of the CTA must call.
+__device__ __forceinline__ void lut_build_images(uint8_t *tbl, const uint4 *stage) {
 	for (uint32_t e = threadIdx.x; e < 4096; e += blockDim.x) {
 		uint32_t k = e & 15, b = e >> 4;
 		uint4 acc = u4_zero();
 #pragma unroll
 		for (uint32_t i = 0; i < 8; i++) {
 			uint32_t m = 0u - ((b >> i) & 1u);
-			uint4 w = stage[8 * k + i];
+			uint4 w = stage[i * 16 + k];
 			acc.x ^= w.x & m; acc.y ^= w.y & m; acc.z ^= w.z & m; acc.w ^= w.w & m;
 		}
 		*reinterpret_cast<uint4 *>(tbl + (k >> 3) * 32768 + b * 128 + (k & 7) * 16) = acc;
 	}
 	__syncthreads();
+}
+__device__ __forceinline__ void lut_build_mul(uint8_t *tbl, uint4 *stage, uint4 z) {
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) stage[(i & 7) * 16 + (i >> 3)] = basis_image(z, i);
+	__syncthreads();
+	lut_build_images(tbl, stage);
+}
+// general linear map given by 128 basis images in global memory (W[i] = L(beta_i))
+__device__ __forceinline__ void lut_build(uint8_t *tbl, uint4 *stage, const uint4 *__restrict__ W) {
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) stage[(i & 7) * 16 + (i >> 3)] = __ldg(W + i);
+	__syncthreads();
+	lut_build_images(tbl, stage);
 }
 
 __device__ __forceinline__ uint4 lut_ld(const uint8_t *tbl, uint32_t w, uint32_t bytepos, uint32_t blk, uint32_t off) {
