@@ -8,6 +8,7 @@
 #include "host_field.hpp"
 #include "kernels.cuh"
 #include "ntt.cuh"
+#include "ntt_bs.cuh"
 
 using namespace b200;
 
@@ -131,6 +132,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint32_t>, FIELD_TABLE_BYTES + 4 * 8192 + 4 * 8192);
 	SET(k_ntt_pass<uint16_t>, FIELD_TABLE_BYTES + 4 * 8192 + 2 * 8192);
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
+	SET(k_ntt_bs_pass, 4 * 1024 + 128 * 1024);
+	SET(k_ntt_bs_low, 152 * 1024 + 640);
 #undef SET
 	if (rc != B200_OK) return rc;
 	*out = ctx.release();
@@ -686,30 +689,102 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 	uint32_t n_layers = log_y - skip_rounds;
 	if (n_layers == 0) return B200_OK;
 	uint32_t lx = log_x + (kd - ntt->kt);  // *_transform_ext: extension limbs become extra batch columns
-	// pass plan, bottom-up: [i_lo, i_lo + R)
-	struct Pass { uint32_t i_lo, R, log_c; };
+	// pass plan, bottom-up.  kind 0 = table-driven scalar pass (ntt.cuh), kind 1 = bit-sliced pass
+	// (ntt_bs.cuh; needs >= 32 contiguous positions sharing every twiddle: lx + i_lo >= 5, B32 only).
+	struct Pass { uint32_t kind, i_lo, R, R_exec, log_c; };
 	std::vector<Pass> plan;
 	const uint32_t MAX_LOG_TILE = 13;
-	for (uint32_t i_lo = 0; i_lo < n_layers;) {
-		uint32_t log_inner = lx + i_lo;
-		uint32_t log_c = std::min(5u, log_inner);
-		uint32_t R = std::min(n_layers - i_lo, MAX_LOG_TILE - log_c);
-		if (log_c == 5) R = std::min(R, 8u);
-		plan.push_back(Pass{i_lo, R, log_c});
-		i_lo += R;
+	static int force_scalar = getenv("B200_NTT_SCALAR") ? atoi(getenv("B200_NTT_SCALAR")) : 0;
+	if (ntt->kt == 5 && !force_scalar) {
+		uint32_t i_lo = 0;
+		if (lx < 5 && lx + log_y >= 5) {
+			// kind 2: lowest pass on units of 32 consecutive scalars (intra-unit layers + up to Rt inter-unit)
+			uint32_t L0 = 5 - lx;
+			uint32_t Rt = std::min(10u, lx + log_y - 5);
+			uint32_t n_intra = std::min(n_layers, L0);
+			uint32_t n_inter = std::min(n_layers - n_intra, Rt);
+			uint32_t rest = n_layers - n_intra - n_inter;
+			if (rest > 0 && rest < 4 && n_inter + rest >= 8) n_inter = n_inter + rest - 4;  // avoid a tiny upper pass
+			plan.push_back(Pass{2, 0, Rt, n_intra, n_inter});
+			i_lo = n_intra + n_inter;
+		} else if (lx < 5) {
+			plan.push_back(Pass{0, 0, log_y, n_layers, lx});  // transform smaller than one unit
+			i_lo = n_layers;
+		}
+		// tiles of 2^(R + log_cu) = 1024 units (128 KiB of shared memory): 512 butterfly-units per layer,
+		// two per thread, so no thread idles between the per-layer barriers
+		while (i_lo < n_layers) {
+			uint32_t log_cu = std::min(lx + i_lo - 5, 2u);
+			uint32_t R = std::min(n_layers - i_lo, 10 - log_cu);
+			if (n_layers - i_lo - R > 0 && n_layers - i_lo - R < 4) R = (n_layers - i_lo + 1) / 2;  // avoid a tiny last pass
+			log_cu = std::min(lx + i_lo - 5, 10 - R);  // short passes take wider tiles: always ~1024 units
+			plan.push_back(Pass{1, i_lo, R, R, log_cu});
+			i_lo += R;
+		}
+	} else {
+		for (uint32_t i_lo = 0; i_lo < n_layers;) {
+			uint32_t log_inner = lx + i_lo;
+			uint32_t log_c = std::min(5u, log_inner);
+			uint32_t R = std::min(n_layers - i_lo, MAX_LOG_TILE - log_c);
+			if (log_c == 5) R = std::min(R, 8u);
+			plan.push_back(Pass{0, i_lo, R, R, log_c});
+			i_lo += R;
+		}
 	}
 	uint32_t n_z = 1u << log_z;
 	if (n_z > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "log_z too large");
 	for (size_t pi = 0; pi < plan.size(); pi++) {
 		const Pass &P = inverse ? plan[pi] : plan[plan.size() - 1 - pi];
+		uint32_t row0 = ntt->d - (log_y + coset_bits);
+		if (P.kind == 2) {
+			NttBsLowArgs L;
+			L.data = (uint32_t *)data;
+			L.log_x = lx;
+			L.log_y = log_y;
+			L.Rt = P.R;
+			L.n_intra = P.R_exec;
+			L.n_inter = P.log_c;
+			L.row0 = row0;
+			L.d = ntt->d;
+			L.coset = coset;
+			L.inverse = inverse;
+			L.s_evals = ntt->d_s_evals;
+			uint64_t n_blocks = 1ull << (lx + log_y - 5 - P.R);
+			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
+			uint32_t smem = (152u << P.R) + 640;
+			k_ntt_bs_low<<<dim3((uint32_t)n_blocks, n_z), NTT_BS_THREADS, smem, ctx->stream>>>(L);
+			B200_LAUNCH_CHECK(ctx);
+			continue;
+		}
+		if (P.kind == 1) {
+			NttBsArgs B;
+			B.data = (uint32_t *)data;
+			B.log_x = lx;
+			B.log_y = log_y;
+			B.i_lo = P.i_lo;
+			B.R = P.R;
+			B.log_cu = P.log_c;
+			B.row0 = row0;
+			B.d = ntt->d;
+			B.coset = coset;
+			B.inverse = inverse;
+			B.s_evals = ntt->d_s_evals;
+			uint64_t n_blocks = 1ull << (log_y - (P.i_lo + P.R) + (lx + P.i_lo - 5 - P.log_c));
+			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
+			uint32_t smem = (4u << P.R) + (128u << (P.R + P.log_c));
+			k_ntt_bs_pass<<<dim3((uint32_t)n_blocks, n_z), NTT_BS_THREADS, smem, ctx->stream>>>(B);
+			B200_LAUNCH_CHECK(ctx);
+			continue;
+		}
 		NttPassArgs A;
 		A.data = data;
 		A.log_x = lx;
 		A.log_y = log_y;
 		A.i_lo = P.i_lo;
 		A.R = P.R;
+		A.R_exec = P.R_exec;
 		A.log_c = P.log_c;
-		A.row0 = ntt->d - (log_y + coset_bits);
+		A.row0 = row0;
 		A.d = ntt->d;
 		A.coset = coset;
 		A.inverse = inverse;

@@ -29,7 +29,8 @@ template <> struct NttField<uint8_t> {
 struct NttPassArgs {
 	void *data;
 	uint32_t log_x, log_y;   // log_x already includes the extension-degree shift
-	uint32_t i_lo, R;        // layers [i_lo, i_lo + R)
+	uint32_t i_lo, R;        // tile spans layers [i_lo, i_lo + R) ...
+	uint32_t R_exec;         // ... of which only [i_lo, i_lo + R_exec) are executed (R_exec <= R)
 	uint32_t log_c;          // tile width along the inner (contiguous) axis
 	uint32_t row0;           // s_evals row of layer 0 = d - (log_y + coset_bits)
 	uint32_t d;              // log domain size
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const uint8_t *__restrict__ g_
 	}
 	__syncthreads();
 	const uint32_t n_bf = n_tile >> 1;
-	for (uint32_t step = 0; step < R; step++) {
-		uint32_t li = A.inverse ? step : (R - 1 - step);
+	for (uint32_t step = 0; step < A.R_exec; step++) {
+		uint32_t li = A.inverse ? step : (A.R_exec - 1 - step);
 		for (uint32_t bfi = threadIdx.x; bfi < n_bf; bfi += blockDim.x) {
 			uint32_t c = bfi & cmask, q = bfi >> log_c;
 			uint32_t kk = q & ((1u << li) - 1), jr = q >> li;
