@@ -96,7 +96,7 @@ def load() -> C.CDLL:
         "b200_fri_fold": (i32, [vp, vp, u32, u32, P(u64), u32, vp, u64, vp, u64]),
         "b200_tensor_product_full_query": (i32, [vp, P(u64), u32, vp, u64]),
         "b200_fold_multilinears_high_to_low": (i32, [vp, P(vp), u32, u32, P(u64), P(u64), P(u64), P(u64)]),
-        "b200_eq_ind_round_evals": (i32, [vp, P(vp), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(u32)]),
+        "b200_eq_ind_round_evals": (i32, [vp, P(vp), P(u64), P(u64), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(u32)]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the build is stale: fail loudly

@@ -573,7 +573,7 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 	return B200_OK;
 }
 
-int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
+int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint64_t *lens, const uint64_t *suffix_evals, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
 	if (!ctx || !first_slot) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
 	if ((uint64_t)n_comp * n_points > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many (composition, point) pairs");
@@ -598,6 +598,19 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t
 	void *d;
 	if ((rc = stage_args(ctx, mls, sizeof(void *) * std::max(m, 1u), &d))) return rc;
 	A.mls = (const uint4 *const *)d;
+	{
+		std::vector<uint64_t> hl(std::max(m, 1u));
+		std::vector<uint4> hs(std::max(m, 1u));
+		for (uint32_t t = 0; t < m; t++) {
+			hl[t] = lens ? lens[t] : (1ull << n_vars);
+			if (hl[t] > (1ull << n_vars)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: stored length exceeds 2^n_vars", t);
+			hs[t] = suffix_evals ? to_u4(suffix_evals + 2 * t) : make_uint4(0, 0, 0, 0);
+		}
+		if ((rc = stage_args(ctx, hl.data(), 8 * hl.size(), &d))) return rc;
+		A.lens = (const uint64_t *)d;
+		if ((rc = stage_args(ctx, hs.data(), 16 * hs.size(), &d))) return rc;
+		A.suffix = (const uint4 *)d;
+	}
 	A.n_mls = m;
 	A.half = 1ull << (n_vars - 1);
 	A.eq_ind = (const uint4 *)eq_ind;

@@ -293,6 +293,8 @@ __global__ void __launch_bounds__(256) k_bivariate_round_evals(const uint8_t *__
 // blockIdx.y = c * n_points + p
 struct EqIndArgs {
 	const uint4 *const *mls;
+	const uint64_t *lens;   // [n_mls] stored prefix length of each multilinear (<= 2*half)
+	const uint4 *suffix;    // [n_mls] implicit constant value beyond the stored prefix
 	uint32_t n_mls;
 	uint64_t half;
 	const uint4 *eq_ind;
@@ -326,10 +328,11 @@ __global__ void __launch_bounds__(256) k_eq_ind_round_evals(const uint8_t *__res
 			case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
 			default: {
 				const uint4 *m = A.mls[st.l];
-				uint4 hi = __ldg(m + A.half + i);
+				const uint64_t len = A.lens[st.l];
+				uint4 hi = A.half + i < len ? __ldg(m + A.half + i) : A.suffix[st.l];
 				if (code == 1) v = hi;
 				else {
-					uint4 lo = __ldg(m + i);
+					uint4 lo = i < len ? __ldg(m + i) : A.suffix[st.l];
 					uint4 d = hi ^ lo;
 					v = code == 2 ? d : (lo ^ f_mul128(T, d, z));
 				}

@@ -189,8 +189,13 @@ int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *mu
  * hal/src/sumcheck_round_calculation.rs:126-349; evaluator core/.../prove/eq_ind.rs:646-731):
  * for each composition c and each requested evaluation point, R = sum_i E[i] * C_z(P(i)).
  * eval point codes: 1 = evaluate at 1, 2 = Karatsuba infinity point (leading term on hi-lo),
- * k >= 3 = finite domain point given in `domain_points`.  Results: n_compositions * n_points slots. */
-int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *multilins, uint32_t n_multilins,
+ * k >= 3 = finite domain point given in `domain_points`.  Results: n_compositions * n_points slots.
+ * Folded multilinears may be truncated: element i >= stored_lens[t] reads as suffix_evals[t]
+ * (sumcheck_round_calculation.rs:573-600); the reference's const-suffix shortcut (eq_ind.rs:704-721)
+ * is an analytic form of the same sum. */
+int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *multilins,
+								const uint64_t *stored_lens /* NULL = all 2^n_vars */,
+								const uint64_t *suffix_evals /* 2*m, NULL = zeros */, uint32_t n_multilins,
 								uint32_t n_vars, b200_dev_ptr eq_ind /* 2^(n_vars-1) */,
 								const b200_expr *const *compositions,
 								const b200_expr *const *compositions_leading, uint32_t n_compositions,

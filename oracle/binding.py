@@ -245,6 +245,41 @@ def bivariate_round_evals(multilins, n_vars, pairs, batch_coeff: int):
 
 
 # ------------------------------------------------------------------------------------------------
+# old HAL (ComputationBackend) restatements, oracle/hal.c
+def fold_left_lerp_inplace(evals, prefix: int, suffix: int, log_n: int, z: int):
+    """returns the folded (truncated) vector"""
+    buf = _c(evals).copy()
+    lib().orc_fold_left_lerp_inplace.restype = C.c_uint64
+    n = lib().orc_fold_left_lerp_inplace(_p(buf), C.c_uint64(prefix), _p(one(suffix)), C.c_uint32(log_n), _p(one(z)))
+    return buf[:n]
+
+
+def eq_ind_round_evals(mls, lens, suffixes, n_vars, eq_ind, comps, leads, codes, points):
+    """comps / leads: lists of step lists; returns [[value per code] per composition]"""
+    mls = [_c(m) if len(m) else np.zeros((1, 2), np.uint64) for m in mls]
+    m = len(mls)
+    enc_c = [encode_expr(s) for s in comps]
+    enc_l = [encode_expr(s) for s in leads]
+    pc = (C.c_void_p * len(comps))(*[C.addressof(e) for e in enc_c])
+    pl = (C.c_void_p * len(comps))(*[C.addressof(e) for e in enc_l])
+    nc = (C.c_uint32 * len(comps))(*[len(s) for s in comps])
+    nl = (C.c_uint32 * len(comps))(*[len(s) for s in leads])
+    out = np.zeros((max(len(comps) * len(codes), 1), 2), np.uint64)
+    lib().orc_eq_ind_round_evals(_ptr_array(mls), (C.c_uint64 * max(m, 1))(*lens), _p(to_arr(list(suffixes)) if m else np.zeros((1, 2), np.uint64)),
+                                 C.c_uint32(m), C.c_uint32(n_vars), _p(_c(eq_ind)), pc, nc, pl, nl, C.c_uint32(len(comps)),
+                                 (C.c_uint32 * max(len(codes), 1))(*codes), _p(to_arr(list(points)) if len(points) else np.zeros((1, 2), np.uint64)),
+                                 C.c_uint32(len(codes)), _p(out))
+    vals = to_ints(out)
+    return [vals[c * len(codes):(c + 1) * len(codes)] for c in range(len(comps))]
+
+
+def fold_partial_eq_ind(e):
+    buf = _c(e).copy()
+    lib().orc_fold_partial_eq_ind(_p(buf), C.c_uint64(len(buf)))
+    return buf[: len(buf) // 2]
+
+
+# ------------------------------------------------------------------------------------------------
 # additive NTT
 _NP_DT = {3: np.uint8, 4: np.uint16, 5: np.uint32, 6: np.uint64}
 

@@ -1,0 +1,135 @@
+"""GPU parity tests of the old-HAL (ComputationBackend) hot path: eq-ind round evaluations, fold of
+Folded multilinears with constant suffixes, eq-ind expansion -- CUDA path vs oracle, round by round.
+Workload shape = BASELINE config #3 scaled down (u32_add constraints, m3/src/gadgets/add.rs:71-76)."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hal():
+    import binius_b200
+
+    layer = binius_b200.B200Layer(0)
+    yield layer
+    layer.close()
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.uint64).reshape(-1, 2), np.asarray(b, dtype=np.uint64).reshape(-1, 2))
+
+
+def u32_add_compositions():
+    from binius_b200 import ArithCircuit as A
+
+    x, y, cin, cout, z = (A.var(i) for i in range(5))
+    c1 = (x + cin) * (y + cin) + cin - cout  # degree 2
+    c2 = x + y + cin - z  # degree 1
+    return [c1, c2]
+
+
+def test_tensor_product_full_query(hal, oracle):
+    from binius_b200.hal import B200Backend
+
+    be = B200Backend(hal)
+    rng = random.Random(1)
+    for k in (0, 1, 4, 11, 13):
+        q = [rng.getrandbits(128) for _ in range(k)]
+        out = be.tensor_product_full_query(q)
+        exp = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << k) - 1)), 0, q)
+        assert _same(hal.to_host(out), exp)
+
+
+@pytest.mark.parametrize("n_vars", [1, 5, 11])
+def test_zerocheck_rounds_match_oracle(hal, oracle, n_vars):
+    """All rounds of an eq-ind sumcheck: round evals (at 1 and infinity, plus an extra finite domain
+    point for the degree-3 variant), fold of every multilinear, halving of the eq-ind table."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
+
+    be = B200Backend(hal)
+    rng = random.Random(n_vars)
+    comps = u32_add_compositions() + [A.var(0) * A.var(1) * A.var(4) + A.var(2)]  # a degree-3 one -> finite point
+    mls_h = [oracle.rand_b128(200 + t, 1 << n_vars) for t in range(5)]
+    eq_pt = [rng.getrandbits(128) for _ in range(n_vars - 1)]
+    eq_h = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << (n_vars - 1)) - 1)), 0, eq_pt)
+    mls = [FoldedMultilinear(hal.to_device(m), 0) for m in mls_h]
+    eq_d = be.tensor_product_full_query(eq_pt)
+    assert _same(hal.to_host(eq_d), eq_h)
+    finite = [oracle.mul(0x2, 0x2)]  # domain point index 3
+    for rnd in range(n_vars):
+        nv = n_vars - rnd
+        evs = [EqIndEvaluator(c, have_first_round_eval_1s=(rnd == 0 and i == 0)) for i, c in enumerate(comps)]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, eq_d, finite)
+        codes = [1, 2, 3]
+        exp_all = oracle.eq_ind_round_evals(mls_h, [len(m) for m in mls_h], [0] * 5, nv, eq_h,
+                                            [c.steps for c in comps], [c.leading_term().steps for c in comps], codes, [0, 0, finite[0]])
+        for ev, g, e in zip(evs, got, exp_all):
+            assert g == [e[k - 1] for k in ev.eval_point_indices()]
+        assert len(got[1]) == 1 and len(got[2]) == 3 and len(got[0]) == (1 if rnd == 0 else 2)
+        ch = rng.getrandbits(128)
+        be.sumcheck_fold_multilinears(nv, mls, ch)
+        mls_h = [oracle.fold_left_lerp_inplace(m, len(m), 0, nv, ch) for m in mls_h]
+        for d, h in zip(mls, mls_h):
+            assert d.evals.len() == len(h) and _same(hal.to_host(d.evals), h)
+        if nv > 1:
+            eq_d = be.fold_partial_eq_ind(nv - 1, eq_d)
+            eq_h = oracle.fold_partial_eq_ind(eq_h)
+            assert _same(hal.to_host(eq_d), eq_h)
+    assert all(m.evals.len() == 1 for m in mls)
+
+
+def test_truncated_multilinears_with_const_suffix(hal, oracle):
+    """Folded multilinears store only a non-constant prefix (fold.rs:648-696, round calc :573-600)."""
+    from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
+
+    be = B200Backend(hal)
+    n_vars = 8
+    rng = random.Random(9)
+    prefixes = [256, 200, 129, 128, 77]
+    suffixes = [0, rng.getrandbits(128), 1, rng.getrandbits(128), rng.getrandbits(128)]
+    mls_h = [oracle.rand_b128(300 + t, p) for t, p in enumerate(prefixes)]
+    mls = [FoldedMultilinear(hal.to_device(m), s) for m, s in zip(mls_h, suffixes)]
+    comps = u32_add_compositions()
+    eq_pt = [rng.getrandbits(128) for _ in range(n_vars - 1)]
+    eq_d = be.tensor_product_full_query(eq_pt)
+    eq_h = hal.to_host(eq_d)
+    for rnd in range(4):
+        nv = n_vars - rnd
+        evs = [EqIndEvaluator(c) for c in comps]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, eq_d, [])
+        exp = oracle.eq_ind_round_evals(mls_h, [len(m) for m in mls_h], suffixes, nv, eq_h, [c.steps for c in comps],
+                                        [c.leading_term().steps for c in comps], [1, 2], [0, 0])
+        assert got[0] == exp[0] and got[1] == exp[1][:1]
+        ch = rng.getrandbits(128)
+        be.sumcheck_fold_multilinears(nv, mls, ch)
+        mls_h = [oracle.fold_left_lerp_inplace(m, len(m), s, nv, ch) for m, s in zip(mls_h, suffixes)]
+        for d, h in zip(mls, mls_h):
+            assert d.evals.len() == len(h) and _same(hal.to_host(d.evals), h)
+        eq_d = be.fold_partial_eq_ind(nv - 1, eq_d)
+        eq_h = oracle.fold_partial_eq_ind(eq_h)
+    import binius_b200
+
+    with pytest.raises(binius_b200.InputValidation):
+        be.sumcheck_compute_round_evals(4, mls, [EqIndEvaluator(comps[0])], eq_d, [1, 2])
+
+
+def test_evaluate_partial_high(hal, oracle):
+    from binius_b200.hal import B200Backend
+
+    be = B200Backend(hal)
+    n, k = 10, 3
+    ml = oracle.rand_b128(400, 1 << n)
+    q = [5, 1 << 90, 0xABCDEF]
+    qe = be.tensor_product_full_query(q)
+    out = be.evaluate_partial_high(hal.to_device(ml), qe)
+    exp = oracle.fold_left(ml, 7, hal.to_host(qe), 1 << (n - k))
+    assert _same(hal.to_host(out), exp)
+    # successive single-variable folds with the same challenges (reversed order: highest first) agree
+    cur = ml
+    for i, c in enumerate(reversed(q)):
+        cur = oracle.fold_left_lerp_inplace(cur, len(cur), 0, n - i, c)
+    assert _same(cur, exp)

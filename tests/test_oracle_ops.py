@@ -309,3 +309,40 @@ def test_fri_fold_matches_definition(oracle):
             assert got[c] == v[0]
     with pytest.raises(o.OracleError):
         ntt.fri_fold(4, 2, [1], o.rand_b128(0, 64), 16)
+
+
+def test_hal_restatements_match_definitions(oracle):
+    # fold_left_lerp_inplace with const suffix (fold.rs:648-696) and eq-ind round evals (A.8)
+    o = oracle
+    rng = random.Random(21)
+    n = 5
+    full = o.rand_b128(500, 1 << n)
+    z = rng.getrandbits(128)
+    for prefix, suffix in [(32, 0), (20, rng.getrandbits(128)), (16, 7), (9, rng.getrandbits(128)), (0, 3)]:
+        padded = ints(o, full)[:prefix] + [suffix] * (32 - prefix)
+        got = ints(o, o.fold_left_lerp_inplace(full[:prefix], prefix, suffix, n, z))
+        exp = [padded[i] ^ o.mul(padded[i] ^ padded[16 + i], z) for i in range(16)]
+        assert got == exp[: min(prefix, 16)]
+        # the dropped tail is again the constant suffix
+        assert all(e == suffix for e in exp[min(prefix, 16):])
+    # eq-ind round evals vs python loops: sum_i E[i] * C(P_z(i))
+    m, nv = 3, 4
+    mls = [o.rand_b128(510 + t, 1 << nv) for t in range(m)]
+    E = o.rand_b128(520, 1 << (nv - 1))
+    comp = [("var", 0), ("var", 1), ("mul", 0, 1), ("var", 2), ("add", 2, 3)]  # x0*x1 + x2
+    lead = [("var", 0), ("var", 1), ("mul", 0, 1)]
+    pt = rng.getrandbits(128)
+    got = o.eq_ind_round_evals(mls, [16] * m, [0] * m, nv, E, [comp], [lead], [1, 2, 3], [0, 0, pt])[0]
+    v = [ints(o, x) for x in mls]
+    e = ints(o, E)
+    r1 = rinf = r3 = 0
+    for i in range(8):
+        lo = [v[t][i] for t in range(m)]
+        hi = [v[t][8 + i] for t in range(m)]
+        r1 ^= o.mul(e[i], o.mul(hi[0], hi[1]) ^ hi[2])
+        rinf ^= o.mul(e[i], o.mul(hi[0] ^ lo[0], hi[1] ^ lo[1]))
+        p = [lo[t] ^ o.mul(lo[t] ^ hi[t], pt) for t in range(m)]
+        r3 ^= o.mul(e[i], o.mul(p[0], p[1]) ^ p[2])
+    assert got == [r1, rinf, r3]
+    h = ints(o, o.fold_partial_eq_ind(E))
+    assert h == [e[i] ^ e[4 + i] for i in range(4)]
