@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200_event_create", "b200_event_record", "b200_event_elapsed_ms", "b200_event_destroy",
     "b200_ctx_launch_count", "b200_dev_alloc", "b200_dev_free", "b200_host_alloc", "b200_host_free",
     "b200_copy_h2d", "b200_copy_d2h", "b200_copy_d2d", "b200_fill", "b200_sync", "b200_results_reset",
-    "b200_results_fetch", "b200_extrapolate_line", "b200_tensor_expand", "b200_inner_product", "b200_fold_left",
+    "b200_results_fetch", "b200_extrapolate_line", "b200_extrapolate_line_host", "b200_tensor_expand", "b200_inner_product", "b200_fold_left",
     "b200_fold_right", "b200_expr_compile", "b200_expr_free", "b200_expr_n_vars", "b200_compute_composite",
     "b200_pairwise_product_reduce", "b200_kernel_decl_value", "b200_kernel_sum_composition_evals",
     "b200_kernel_add", "b200_kernel_add_assign", "b200_bivariate_round_evals", "b200_ntt_create",
@@ -71,6 +71,7 @@ def load() -> C.CDLL:
         "b200_results_reset": (i32, [vp]),
         "b200_results_fetch": (i32, [vp, P(u32), u32, P(u64)]),
         "b200_extrapolate_line": (i32, [vp, vp, u64, vp, u64, P(u64)]),
+        "b200_extrapolate_line_host": (i32, [vp, vp, vp, u64, P(u64)]),
         "b200_tensor_expand": (i32, [vp, vp, u64, u32, P(u64), u32]),
         "b200_inner_product": (i32, [vp, vp, u64, u32, vp, u64, P(u32)]),
         "b200_fold_left": (i32, [vp, vp, u64, u32, vp, u64, vp, u64]),

@@ -150,6 +150,15 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	cudaFree(ctx->d_args);
 	cudaFreeHost(ctx->h_args);
 	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+	if (ctx->s_h2d) {
+		cudaStreamDestroy(ctx->s_h2d);
+		cudaStreamDestroy(ctx->s_d2h);
+		for (int i = 0; i < 3; i++) {
+			cudaEventDestroy(ctx->ev_in[i]);
+			cudaEventDestroy(ctx->ev_k[i]);
+			cudaEventDestroy(ctx->ev_out[i]);
+		}
+	}
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -341,6 +350,51 @@ int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_
 	std::vector<LerpSeg> segs(1);
 	segs[0] = LerpSeg{(uint4 *)e0, (const uint4 *)e1, n0, n0, make_uint4(0, 0, 0, 0), 0};
 	return launch_lerp(ctx, segs, z);
+}
+
+// Host-buffer form of the fold (what a ComputationBackend whose Vec<P> lives in host memory calls,
+// hal/src/backend.rs:19-31, 65-75): chunked 3-slot pipeline  H2D(e0,e1) -> k_lerp_lut -> D2H(e0)  on
+// three streams so that both PCIe directions and the kernel overlap.  Synchronous.
+int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *host_e1, uint64_t n, const uint64_t z[2]) {
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n == 0) return B200_OK;
+	const uint64_t CH = 1ull << 20;  // elements per chunk (16 MiB per operand)
+	const uint32_t NS = 3;
+	int32_t rc = ensure_scratch(ctx, NS * 2 * CH * 16);
+	if (rc) return rc;
+	if (!ctx->s_h2d) {
+		B200_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+		B200_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+		for (uint32_t i = 0; i < NS; i++) {
+			B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+			B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+			B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+		}
+	}
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	uint8_t *h0 = (uint8_t *)host_e0;
+	const uint8_t *h1 = (const uint8_t *)host_e1;
+	uint64_t n_chunks = (n + CH - 1) / CH;
+	for (uint64_t c = 0; c < n_chunks; c++) {
+		uint32_t s = (uint32_t)(c % NS);
+		uint64_t off = c * CH, cnt = std::min(CH, n - off);
+		uint8_t *d0 = ctx->d_scratch + (uint64_t)s * 2 * CH * 16, *d1 = d0 + CH * 16;
+		if (c >= NS) B200_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_out[s], 0));  // slot drained
+		B200_CUDA(ctx, cudaMemcpyAsync(d0, h0 + off * 16, cnt * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+		B200_CUDA(ctx, cudaMemcpyAsync(d1, h1 + off * 16, cnt * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+		B200_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_h2d));
+		B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+		std::vector<LerpSeg> segs(1);
+		segs[0] = LerpSeg{(uint4 *)d0, (const uint4 *)d1, cnt, cnt, make_uint4(0, 0, 0, 0), 0};
+		if ((rc = launch_lerp(ctx, segs, z))) return rc;
+		B200_CUDA(ctx, cudaEventRecord(ctx->ev_k[s], ctx->stream));
+		B200_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[s], 0));
+		B200_CUDA(ctx, cudaMemcpyAsync(h0 + off * 16, d0, cnt * 16, cudaMemcpyDeviceToHost, ctx->s_d2h));
+		B200_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_d2h));
+	}
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return B200_OK;
 }
 
 int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars,

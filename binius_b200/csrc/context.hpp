@@ -15,6 +15,9 @@ struct b200_ctx {
 	int n_sms = 148;
 	cudaStream_t stream = nullptr;
 	cudaStream_t own_stream = nullptr;
+	// copy streams + events of the host-buffer pipeline (b200_extrapolate_line_host), created lazily
+	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+	cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_k[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
 	std::string err;
 	uint64_t launches = 0;
 

@@ -609,6 +609,20 @@ class B200Layer:
     def fill(self, slice: DevSlice, value: int):
         self._check(self._lib.b200_fill(self._ctx, slice.ptr, slice.len(), _u64x2(value)))
 
+    def extrapolate_line_host(self, evals_0: np.ndarray, evals_1: np.ndarray, z: int):
+        """fold-high on HOST arrays (in place on evals_0): the old-HAL-shaped call
+        (`Backend::Vec<P>` is host memory, hal/src/backend.rs:19-31); pipelined H2D/kernel/D2H."""
+        if evals_0.shape != evals_1.shape:
+            raise InputValidation("evals_0 and evals_1 must be the same length")
+        assert evals_0.dtype == np.uint64 and evals_0.flags["C_CONTIGUOUS"] and evals_1.flags["C_CONTIGUOUS"]
+        self._check(self._lib.b200_extrapolate_line_host(self._ctx, evals_0.ctypes.data, evals_1.ctypes.data, evals_0.size // 2, _u64x2(z)))
+
+    def host_alloc(self, n_elems: int) -> np.ndarray:
+        """pinned host buffer of n_elems B128 elements as an (n,2) uint64 array (never freed before close)"""
+        p = C.c_void_p()
+        self._check(self._lib.b200_host_alloc(self._ctx, n_elems * 16, C.byref(p)))
+        return np.ctypeslib.as_array((C.c_uint64 * (2 * n_elems)).from_address(p.value)).reshape(n_elems, 2)
+
     # -- helpers for tests / bench
     def sync(self):
         self._check(self._lib.b200_sync(self._ctx))

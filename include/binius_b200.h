@@ -91,6 +91,11 @@ int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uin
 /* extrapolate_line (layer.rs:402-426; cpu/layer.rs:393-408): e0[i] += (e1[i]-e0[i])*z */
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr evals_0, uint64_t n0, b200_dev_ptr evals_1,
 							  uint64_t n1, const uint64_t z[2]);
+/* The same fold on HOST buffers (a ComputationBackend whose Vec<P> is host-dereferenceable,
+ * hal/src/backend.rs:19-31, 65-75): chunked H2D -> kernel -> D2H pipeline over both PCIe directions.
+ * Synchronous; host_e0 is updated in place.  Pinned buffers (b200_host_alloc) give full overlap. */
+int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *host_e1, uint64_t n,
+								   const uint64_t z[2]);
 /* tensor_expand (layer.rs:269-296; cpu/layer.rs:282-302) */
 int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, uint32_t log_n,
 						   const uint64_t *coordinates /* 2*k */, uint32_t k);

@@ -245,6 +245,32 @@ def bivariate_round_evals(multilins, n_vars, pairs, batch_coeff: int):
 
 
 # ------------------------------------------------------------------------------------------------
+# timed CPU arm (oracle/cpu_baseline.c): C restatement of the reference's GFNI/AVX-512 fold path
+def cpu_fold(e0, e1, z: int, n_threads: int = 1, use_gfni: bool = True):
+    a = _c(e0).copy()
+    used = lib().cpu_fold(_p(a), _p(_c(e1)), C.c_uint64(len(a)), _p(one(z)), C.c_int(n_threads), C.c_int(int(use_gfni)))
+    return a, bool(used)
+
+
+def cpu_fold_parallel(log_coeffs: int, budget_s: float = 10.0, n_threads: int = 0):
+    """Times fold-high over a bounded sample on this host; returns the bench.py cpu_baseline object."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    log_s = min(log_coeffs, 24)
+    fn = lib().cpu_fold_bench
+    fn.restype = C.c_double
+    used = C.c_int()
+    t1 = fn(C.c_uint32(log_s), C.c_int(1), C.c_int(n_threads), C.c_int(1), C.byref(used))
+    reps = max(1, min(200, int(budget_s / max(t1, 1e-4))))
+    t = fn(C.c_uint32(log_s), C.c_int(reps), C.c_int(n_threads), C.c_int(1), C.byref(used))
+    how = "AVX-512+GFNI" if used.value else "scalar (host CPU lacks AVX-512/GFNI)"
+    return {"value": reps * (1 << log_s) / t, "unit": "coeffs/s", "cores": n_threads, "kind": "port",
+            "sample": f"2^{log_s} coefficients x {reps} reps, {n_threads} threads, {how}; C restatement of the reference "
+                      f"GFNI fold path (fold_left_lerp_inplace), not the Rust binary"}
+
+
+# ------------------------------------------------------------------------------------------------
 # old HAL (ComputationBackend) restatements, oracle/hal.c
 def fold_left_lerp_inplace(evals, prefix: int, suffix: int, log_n: int, z: int):
     """returns the folded (truncated) vector"""

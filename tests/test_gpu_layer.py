@@ -324,3 +324,25 @@ def test_holder_and_bump_allocator(oracle):
     assert _same(data.hal.to_host(a.slice(0, 16)), h)
     assert _same(data.hal.to_host(a.slice(16, 32)), np.zeros((16, 2), np.uint64))
     holder.layer.close()
+
+
+@pytest.mark.parametrize("n", [1, 1000, (1 << 20) + 5, 3 << 20])
+def test_extrapolate_line_host_pipeline(hal, oracle, n):
+    # host-buffer form (old-HAL shaped): chunked H2D/kernel/D2H pipeline, pageable and pinned memory
+    e0, e1 = oracle.rand_b128(700 + n % 97, n), oracle.rand_b128(701 + n % 97, n)
+    z = 0x0123456789ABCDEF_0FEDCBA987654321
+    sample = slice(0, min(n, 1 << 12))
+    exp_head = oracle.extrapolate_line(e0[sample], e1[sample], z)
+    exp_tail = oracle.extrapolate_line(e0[-257:], e1[-257:], z)
+    a = e0.copy()
+    hal.extrapolate_line_host(a, e1, z)
+    assert _same(a[sample], exp_head) and _same(a[-257:], exp_tail)
+    p0, p1 = hal.host_alloc(n), hal.host_alloc(n)
+    p0[:], p1[:] = e0, e1
+    hal.extrapolate_line_host(p0, p1, z)
+    assert np.array_equal(p0, a)
+    d0, d1 = hal.to_device(e0), hal.to_device(e1)
+    hal.execute(lambda ex: (ex.extrapolate_line(d0, d1, z), [])[1])
+    assert _same(hal.to_host(d0), a)
+    hal.dev_free(d0)
+    hal.dev_free(d1)

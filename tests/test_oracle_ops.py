@@ -346,3 +346,15 @@ def test_hal_restatements_match_definitions(oracle):
     assert got == [r1, rinf, r3]
     h = ints(o, o.fold_partial_eq_ind(E))
     assert h == [e[i] ^ e[4 + i] for i in range(4)]
+
+
+def test_cpu_baseline_matches_oracle(oracle):
+    # the timed CPU arm (AVX-512+GFNI restatement, threaded) is bit-identical to the scalar oracle
+    o = oracle
+    n = (1 << 10) + 3
+    e0, e1 = o.rand_b128(600, n), o.rand_b128(601, n)
+    for z in [0, 1, (1 << 128) - 1, 0x2E895399AF449ACE499596F6E5FCCAFA, o.to_ints(o.rand_b128(602, 1))[0]]:
+        exp = o.extrapolate_line(e0, e1, z)
+        for threads, gfni in [(1, True), (3, True), (2, False)]:
+            got, _ = o.cpu_fold(e0, e1, z, threads, gfni)
+            assert np.array_equal(got, exp)
