@@ -1,0 +1,133 @@
+"""Multi-GPU sharding of the sumcheck hot path: one process per GPU, every round local.
+
+HighToLow folding pairs index i with i + 2^(n-1), so partitioning every multilinear by its LOW
+log2(W) index bits (rank g holds the compact array of elements with index = g mod W) keeps every
+fold and every round-evaluation pass local to a GPU for the first n - log2(W) rounds.  Per round each
+rank produces partial sums (<= 3 B128 per composition); GF(2^k) addition is XOR, which NCCL cannot
+reduce, so the partials are all-gathered (48 B per rank) and XOR-ed locally -- they are needed on the
+host for Fiat-Shamir anyway.  When a single element per rank is left, one all-gather brings the W
+survivors together and the last log2(W) rounds run on those W elements (replicated, on the host).
+
+The compute object is any ComputeLayer-shaped layer (`B200Layer` in production; the CPU tests drive the
+same orchestration over gloo with an oracle-backed stand-in).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import hostfield
+
+
+def shard_low_vars(host: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """elements with index = rank (mod world): the rank's sub-multilinear over the high variables"""
+    assert world & (world - 1) == 0 and host.shape[0] % world == 0
+    return np.ascontiguousarray(host[rank::world])
+
+
+def unshard_low_vars(shards: Sequence[np.ndarray]) -> np.ndarray:
+    world = len(shards)
+    out = np.empty((shards[0].shape[0] * world,) + shards[0].shape[1:], dtype=shards[0].dtype)
+    for g, s in enumerate(shards):
+        out[g::world] = s
+    return out
+
+
+def xor_all_gather(values: Sequence[int], dist=None, device="cpu") -> List[int]:
+    """XOR-combine a short vector of B128 scalars over all ranks (all_gather + local XOR)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(values)
+    import torch
+
+    t = torch.tensor([[v & 0x7FFFFFFFFFFFFFFF, (v >> 63) & 0x7FFFFFFFFFFFFFFF, v >> 126] for v in values], dtype=torch.int64, device=device)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    acc = [0] * len(values)
+    for o in outs:
+        for i, row in enumerate(o.tolist()):
+            acc[i] ^= row[0] | (row[1] << 63) | (row[2] << 126)
+    return acc
+
+
+def gather_elements(local: np.ndarray, dist=None, device="cpu") -> np.ndarray:
+    """all-gather the per-rank survivor elements ((k,2) uint64 each) in rank order -> (W, k, 2)"""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local[None]
+    import torch
+
+    t = torch.from_numpy(local.view(np.int64).copy()).to(device)
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return np.stack([o.cpu().numpy().view(np.uint64) for o in outs])
+
+
+class ShardedBivariateSumcheck:
+    """The prover-side data plane of v3::BivariateSumcheckProver
+    (reference core/src/protocols/sumcheck/v3/bivariate_product.rs:57-252) sharded over W ranks:
+    `round_evals` = calculate_round_evals (:303-408), `fold` = receive_challenge/fold (:168-232)."""
+
+    def __init__(self, layer, host_multilinears: Sequence[np.ndarray], n_vars: int, pairs: Sequence[Tuple[int, int]],
+                 world: int = 1, rank: int = 0, dist=None, comm_device="cpu"):
+        self.layer, self.n_vars, self.pairs = layer, n_vars, list(pairs)
+        self.world, self.rank, self.dist, self.comm_device = world, rank, dist, comm_device
+        self.log_w = world.bit_length() - 1
+        assert 1 << self.log_w == world and self.log_w <= n_vars
+        self.local_vars = n_vars - self.log_w
+        self.dev = [layer.to_device(shard_low_vars(m, world, rank)) for m in host_multilinears]
+        self.tail = None  # (m, W) python ints once the local variables are exhausted
+
+    def round_evals(self, batch_coeff: int) -> Tuple[int, int]:
+        """(y_1, y_inf) of the current round, combined over all ranks"""
+        if self.local_vars > 0:
+            nv = self.local_vars
+            got = self.layer.execute(lambda ex: list(ex.bivariate_round_evals(self.dev, nv, self.pairs, batch_coeff)))
+            y1, yinf = xor_all_gather(got, self.dist, self.comm_device)
+            return y1, yinf
+        # replicated tail on the W gathered survivors (host scalars)
+        half = len(self.tail[0]) // 2
+        y1 = yinf = 0
+        pw = 1
+        for a, b in self.pairs:
+            s1 = sinf = 0
+            for i in range(half):
+                s1 ^= hostfield.mul(self.tail[a][half + i], self.tail[b][half + i])
+                sinf ^= hostfield.mul(self.tail[a][i] ^ self.tail[a][half + i], self.tail[b][i] ^ self.tail[b][half + i])
+            y1 ^= hostfield.mul(s1, pw)
+            yinf ^= hostfield.mul(sinf, pw)
+            pw = hostfield.mul(pw, batch_coeff)
+        return y1, yinf
+
+    def fold(self, challenge: int):
+        if self.local_vars > 0:
+            def op(ex):
+                for i, d in enumerate(self.dev):
+                    lo, hi = d.split_half_mut()
+                    ex.extrapolate_line(lo, hi, challenge)
+                    self.dev[i] = lo
+                return []
+
+            self.layer.execute(op)
+            self.local_vars -= 1
+            if self.local_vars == 0:
+                local = np.concatenate([self.layer.to_host(d) for d in self.dev])  # (m, 2)
+                allv = gather_elements(local, self.dist, self.comm_device)  # (W, m, 2)
+                self.tail = [[int(allv[g, t, 0]) | (int(allv[g, t, 1]) << 64) for g in range(self.world)] for t in range(len(self.dev))]
+        else:
+            new = []
+            for vals in self.tail:
+                half = len(vals) // 2
+                new.append([vals[i] ^ hostfield.mul(vals[i] ^ vals[half + i], challenge) for i in range(half)])
+            self.tail = new
+
+    def finish(self) -> List[int]:
+        """the fully folded value of every multilinear (bivariate_product.rs:245-252)"""
+        assert self.tail is not None and all(len(v) == 1 for v in self.tail)
+        return [v[0] for v in self.tail]
+
+
+def shard_units(n_units: int, world: int, rank: int) -> range:
+    """contiguous block partition of independent units (NTT batch columns, sumcheck instances)"""
+    per, rem = divmod(n_units, world)
+    start = rank * per + min(rank, rem)
+    return range(start, start + per + (1 if rank < rem else 0))
