@@ -245,6 +245,39 @@ def main():
             ntt_res[name] = {"fwd_ms": fwd_ms, "inv_ms": inv_ms, "coeffs_per_s": n32 / (fwd_ms * 1e-3), "passes": passes,
                              "roofline_frac": (8 * n32 / (fwd_ms * 1e-3)) / (peak * 1e9)}
 
+    # ---- sumcheck round (BASELINE config #3 shape, v3 bivariate variant): m = 8 multilinears, n = 20,
+    #      8 compositions: round evaluations + fold of every multilinear; and one tensor expansion ------
+    extras = None
+    if not args.no_ntt:
+        import random as _r
+
+        rr = _r.Random(7)
+        nv, m = 20, 8
+        sub = [dev.slice(t << nv, (t + 1) << nv) for t in range(m)]  # 8 x 2^20 elements of the resident buffer
+        pairs = [(rr.randrange(m), rr.randrange(m)) for _ in range(m)]
+        alpha = rr.getrandbits(128)
+        for _ in range(2):
+            hal.execute(lambda ex: list(ex.bivariate_round_evals(sub, nv, pairs, alpha)))
+        ev.start()
+        reps = 5
+        for _ in range(reps):
+            hal.execute(lambda ex: list(ex.bivariate_round_evals(sub, nv, pairs, alpha)))
+        re_ms = ev.stop_ms() / reps
+        k = 22
+        coords = [rr.getrandbits(128) for _ in range(k)]
+        te = dev.slice(0, 1 << k)
+        hal.fill(te.slice(0, 1), 1)
+        for _ in range(2):
+            hal.execute(lambda ex: (ex.tensor_expand(0, coords, te), [])[1])
+        ev.start()
+        for _ in range(reps):
+            hal.execute(lambda ex: (ex.tensor_expand(0, coords, te), [])[1])
+        te_ms = ev.stop_ms() / reps
+        extras = {"bivariate_round_evals_m8_n20": {"ms": re_ms, "products_per_s": 2 * len(pairs) * (1 << (nv - 1)) / (re_ms * 1e-3),
+                                                   "hbm_frac": (16 * m * (1 << nv) / (re_ms * 1e-3)) / (peak * 1e9)},
+                  "tensor_expand_k22": {"ms": te_ms, "elems_per_s": (1 << k) / (te_ms * 1e-3),
+                                        "hbm_frac": (16 * (1 << k) / (te_ms * 1e-3)) / (peak * 1e9)}}
+
     # ---- reduce over ranks: max time ----------------------------------------------------------------
     ms_step = ms_total / args.steps
     if world > 1:
@@ -268,6 +301,8 @@ def main():
         }
         if ntt_res:
             line["ntt"] = ntt_res
+        if extras:
+            line["sumcheck_round"] = extras
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_fold_baseline(args.log_coeffs)
         print(json.dumps(line))
