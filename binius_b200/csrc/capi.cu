@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "ntt.cuh"
 #include "ntt_bs.cuh"
+#include "roundevals_tc.cuh"
 
 using namespace b200;
 
@@ -55,6 +56,23 @@ int32_t ensure_scratch(b200_ctx *ctx, uint64_t bytes) {
 	ctx->scratch_bytes = bytes;
 	return B200_OK;
 }
+
+// several small host arrays -> ONE staged H2D copy
+struct ArgPack {
+	std::vector<uint8_t> buf;
+	size_t add(const void *p, size_t bytes) {
+		size_t off = (buf.size() + 15) & ~(size_t)15;
+		buf.resize(off + bytes);
+		if (bytes) memcpy(buf.data() + off, p, bytes);
+		return off;
+	}
+	int32_t commit(b200_ctx *ctx, uint8_t **base) {
+		void *d;
+		int32_t rc = stage_args(ctx, buf.data(), buf.size(), &d);
+		*base = (uint8_t *)d;
+		return rc;
+	}
+};
 
 static uint32_t grid_for(const b200_ctx *ctx, uint64_t n, uint32_t threads, uint32_t per_sm) {
 	uint64_t blocks = (n + threads - 1) / threads;
@@ -134,6 +152,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
 	SET(k_ntt_bs_pass, 4 * 1024 + 128 * 1024);
 	SET(k_ntt_bs_low, 152 * 1024 + 640);
+	SET(tc::k_bivariate_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
+	SET(tc::k_bivariate_tc_combine, FIELD_TABLE_BYTES);
 #undef SET
 	if (rc != B200_OK) return rc;
 	*out = ctx.release();
@@ -615,11 +635,33 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 		pows[c] = to_u4(w);
 		pw = hostf::mul128(pw, a);
 	}
-	void *dm, *dia, *dib, *dp;
-	if ((rc = stage_args(ctx, mls, sizeof(void *) * m, &dm))) return rc;
-	if ((rc = stage_args(ctx, ia, 4 * n_comp, &dia))) return rc;
-	if ((rc = stage_args(ctx, ib, 4 * n_comp, &dib))) return rc;
-	if ((rc = stage_args(ctx, pows.data(), 16 * n_comp, &dp))) return rc;
+	ArgPack pack;
+	size_t o_m = pack.add(mls, sizeof(void *) * m), o_a = pack.add(ia, 4 * n_comp), o_b = pack.add(ib, 4 * n_comp), o_p = pack.add(pows.data(), 16 * n_comp);
+	uint8_t *dbase;
+	if ((rc = pack.commit(ctx, &dbase))) return rc;
+	void *dm = dbase + o_m, *dia = dbase + o_a, *dib = dbase + o_b, *dp = dbase + o_p;
+	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
+	if (tc_mode && half >= 4096 && half % tc::CHUNK == 0) {
+		// tensor-core path (roundevals_tc.cuh): bit-GEMM with tcgen05.mma.kind::i8, parity epilogue
+		uint64_t gbytes = (uint64_t)n_comp * 2 * 512 * 4;
+		if ((rc = ensure_scratch(ctx, gbytes))) return rc;
+		B200_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, gbytes, ctx->stream));
+		tc::TcArgs T;
+		T.mls = (const uint4 *const *)dm;
+		T.ia = (const uint32_t *)dia;
+		T.ib = (const uint32_t *)dib;
+		T.half = half;
+		T.debug = getenv("B200_TC_DEBUG") ? (uint32_t)atoi(getenv("B200_TC_DEBUG")) : 0;
+		T.gmat = (uint32_t *)ctx->d_scratch;
+		uint64_t n_chunks = (half + tc::CHUNK - 1) / tc::CHUNK;
+		// exactly one wave: 2 CTAs per SM are resident (256 TMEM columns each); a partial second wave would double the time
+		uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, (uint64_t)(2 * ctx->n_sms) / n_comp));
+		tc::k_bivariate_tc<<<dim3(gx, n_comp), tc::THREADS, tc::NSTAGE * tc::STAGE_BYTES + 1024, ctx->stream>>>(T);
+		B200_LAUNCH_CHECK(ctx);
+		tc::k_bivariate_tc_combine<<<n_comp, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint32_t *)ctx->d_scratch, (const uint4 *)dp, ctx->d_results + *slot_y1, ctx->d_results + *slot_yinf);
+		B200_LAUNCH_CHECK(ctx);
+		return B200_OK;
+	}
 	uint32_t gx = grid_for(ctx, half, 256, 2);
 	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::max(1u, std::min(n_comp, (uint32_t)ctx->n_sms * 4)) + 1)));
 	k_bivariate_round_evals<<<dim3(gx, n_comp), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *const *)dm, half, (const uint32_t *)dia, (const uint32_t *)dib, (const uint4 *)dp, ctx->d_results + *slot_y1, ctx->d_results + *slot_yinf);
@@ -649,33 +691,29 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const ui
 	for (uint32_t p = 0; p < n_points; p++) hp[p] = to_u4(points + 2 * p);
 	EqIndArgs A;
 	int32_t rc;
-	void *d;
-	if ((rc = stage_args(ctx, mls, sizeof(void *) * std::max(m, 1u), &d))) return rc;
-	A.mls = (const uint4 *const *)d;
-	{
-		std::vector<uint64_t> hl(std::max(m, 1u));
-		std::vector<uint4> hs(std::max(m, 1u));
-		for (uint32_t t = 0; t < m; t++) {
-			hl[t] = lens ? lens[t] : (1ull << n_vars);
-			if (hl[t] > (1ull << n_vars)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: stored length exceeds 2^n_vars", t);
-			hs[t] = suffix_evals ? to_u4(suffix_evals + 2 * t) : make_uint4(0, 0, 0, 0);
-		}
-		if ((rc = stage_args(ctx, hl.data(), 8 * hl.size(), &d))) return rc;
-		A.lens = (const uint64_t *)d;
-		if ((rc = stage_args(ctx, hs.data(), 16 * hs.size(), &d))) return rc;
-		A.suffix = (const uint4 *)d;
+	std::vector<uint64_t> hlen(std::max(m, 1u));
+	std::vector<uint4> hs(std::max(m, 1u));
+	for (uint32_t t = 0; t < m; t++) {
+		hlen[t] = lens ? lens[t] : (1ull << n_vars);
+		if (hlen[t] > (1ull << n_vars)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: stored length exceeds 2^n_vars", t);
+		hs[t] = suffix_evals ? to_u4(suffix_evals + 2 * t) : make_uint4(0, 0, 0, 0);
 	}
+	ArgPack pack;
+	size_t o_m = pack.add(mls, sizeof(void *) * m), o_l = pack.add(hlen.data(), 8 * hlen.size()), o_s = pack.add(hs.data(), 16 * hs.size());
+	size_t o_c = pack.add(hc.data(), sizeof(DevExpr) * n_comp), o_ld = pack.add(hl.data(), sizeof(DevExpr) * n_comp);
+	size_t o_k = pack.add(codes, 4 * n_points), o_p = pack.add(hp.data(), 16 * n_points);
+	uint8_t *dbase;
+	if ((rc = pack.commit(ctx, &dbase))) return rc;
+	A.mls = (const uint4 *const *)(dbase + o_m);
+	A.lens = (const uint64_t *)(dbase + o_l);
+	A.suffix = (const uint4 *)(dbase + o_s);
 	A.n_mls = m;
 	A.half = 1ull << (n_vars - 1);
 	A.eq_ind = (const uint4 *)eq_ind;
-	if ((rc = stage_args(ctx, hc.data(), sizeof(DevExpr) * n_comp, &d))) return rc;
-	A.comps = (const DevExpr *)d;
-	if ((rc = stage_args(ctx, hl.data(), sizeof(DevExpr) * n_comp, &d))) return rc;
-	A.comps_lead = (const DevExpr *)d;
-	if ((rc = stage_args(ctx, codes, 4 * n_points, &d))) return rc;
-	A.codes = (const uint32_t *)d;
-	if ((rc = stage_args(ctx, hp.data(), 16 * n_points, &d))) return rc;
-	A.points = (const uint4 *)d;
+	A.comps = (const DevExpr *)(dbase + o_c);
+	A.comps_lead = (const DevExpr *)(dbase + o_ld);
+	A.codes = (const uint32_t *)(dbase + o_k);
+	A.points = (const uint4 *)(dbase + o_p);
 	A.n_points = n_points;
 	A.slots = ctx->d_results + *first_slot;
 	uint32_t gx = grid_for(ctx, A.half, 256, 2);

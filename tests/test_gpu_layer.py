@@ -237,7 +237,7 @@ def test_pairwise_product_reduce(hal, oracle, log_n):
         hal.execute(lambda ex: (ex.pairwise_product_reduce(dx.slice(0, 1), []), [])[1])
 
 
-@pytest.mark.parametrize("n_vars,m", [(1, 2), (6, 4), (12, 8)])
+@pytest.mark.parametrize("n_vars,m", [(1, 2), (6, 4), (12, 8), (13, 3), (15, 5)])
 def test_bivariate_round_evals_fused_and_traced(hal, oracle, n_vars, m):
     # core/src/protocols/sumcheck/v3/bivariate_product.rs:303-408, both as the fused entry point and
     # as the literal accumulate_kernels program the reference prover issues
