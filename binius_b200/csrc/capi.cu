@@ -651,7 +651,6 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 		T.ia = (const uint32_t *)dia;
 		T.ib = (const uint32_t *)dib;
 		T.half = half;
-		T.debug = getenv("B200_TC_DEBUG") ? (uint32_t)atoi(getenv("B200_TC_DEBUG")) : 0;
 		T.gmat = (uint32_t *)ctx->d_scratch;
 		uint64_t n_chunks = (half + tc::CHUNK - 1) / tc::CHUNK;
 		// exactly one wave: 2 CTAs per SM are resident (256 TMEM columns each); a partial second wave would double the time

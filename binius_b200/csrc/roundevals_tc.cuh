@@ -98,7 +98,6 @@ struct TcArgs {
 	const uint4 *const *mls;
 	const uint32_t *ia, *ib;
 	uint64_t half;
-	uint32_t debug;  // experiment switch (0 in production): 1 = no MMA, 2 = no unpack/stores, 3 = no global loads
 	uint32_t *gmat;  // [n_comp][2][128][4] words, zero-initialised: XOR of the parity matrices of all CTAs
 };
 
@@ -142,22 +141,21 @@ __global__ void __launch_bounds__(THREADS) k_bivariate_tc(const TcArgs A) {
 		// half is a multiple of CHUNK (checked by the host), so every chunk is full: loads are
 		// unconditional and land directly in their ring slot (no select / move on the loaded value,
 		// which would stall on the load right after issuing it)
+		// Loads are UNCONDITIONAL and land directly in their ring slot: a predicated load makes ptxas
+		// load into temporaries and move them right away, which stalls every iteration for a full
+		// memory latency.  Iterations past the end re-read the last valid chunk (clamped pointer).
+		const uint4 *p_last = ((op & 1) ? b : a) + (n_chunks - 1) * CHUNK + pt;
 		auto load = [&](uint4 &xh, uint4 &xl) {
-			xh = __ldg(p_lo + half);
-			if (need_lo) xl = __ldg(p_lo);
+			const uint4 *p = p_lo < p_last ? p_lo : p_last;
+			xh = __ldg(p + half);
+			xl = __ldg(need_lo ? p : p + half);  // operands 0/1 read the same line twice (L1 hit) and cancel below
 			p_lo += step;
 		};
 		// register ring of raw loads, one slot per pipeline stage (slot u <-> stage u): the HBM latency
 		// spans several stages, and stage / ring indices stay compile-time constants
 		uint4 rh[NSTAGE], rl[NSTAGE];
 #pragma unroll
-		for (uint32_t u = 0; u < NSTAGE; u++) {
-			rh[u] = make_uint4(0, 0, 0, 0);
-			rl[u] = rh[u];
-		}
-#pragma unroll
-		for (uint32_t u = 0; u < NSTAGE; u++)
-			if (u < my_chunks) load(rh[u], rl[u]);
+		for (uint32_t u = 0; u < NSTAGE; u++) load(rh[u], rl[u]);
 		uint8_t *row = smem + op * (CHUNK * 128) + pt * 128;
 		const uint32_t sw16 = (pt & 7) << 4;
 		uint32_t phase = 1;  // parity of the previous completion of empty[]; first round needs no wait
@@ -166,11 +164,11 @@ __global__ void __launch_bounds__(THREADS) k_bivariate_tc(const TcArgs A) {
 			for (uint32_t u = 0; u < NSTAGE; u++) {
 				const uint32_t it = it0 + u;
 				if (it < my_chunks) {
-					const uint4 x = rh[u] ^ rl[u];
-					if (it + NSTAGE < my_chunks) load(rh[u], rl[u]);
-					if (it0 > 0 && A.debug != 5) mbar_wait(&empty[u], phase);  // MMAs that read this stage are done
-					if (A.debug != 2) unpack_store(row + u * STAGE_BYTES, sw16, x);
-					if (A.debug != 4) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					const uint4 x = need_lo ? (rh[u] ^ rl[u]) : rh[u];
+					load(rh[u], rl[u]);
+					if (it0 > 0) mbar_wait(&empty[u], phase);  // MMAs that read this stage are done
+					unpack_store(row + u * STAGE_BYTES, sw16, x);
+					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 					__syncwarp();
 					if (lane == 0) mbar_arrive(&full[u]);
 				}
@@ -186,10 +184,6 @@ __global__ void __launch_bounds__(THREADS) k_bivariate_tc(const TcArgs A) {
 				const uint32_t it = it0 + u;
 				if (it < my_chunks) {
 					mbar_wait(&full[u], phase);
-					if (A.debug == 1) {
-						mbar_arrive(&empty[u]);
-						continue;
-					}
 					asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
 					for (uint32_t ks = 0; ks < CHUNK / 32; ks++) {
