@@ -115,7 +115,6 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return B200_ERR_DEVICE;
 	ctx->stream = ctx->own_stream;
 	bool ok = cudaMalloc(&ctx->d_tables, FIELD_TABLE_BYTES) == cudaSuccess &&
-			  cudaMalloc(&ctx->d_basis, sizeof(uint4) * 128 * MAX_LINMAPS) == cudaSuccess &&
 			  cudaMalloc(&ctx->d_results, sizeof(uint4) * MAX_RESULTS) == cudaSuccess &&
 			  cudaMalloc(&ctx->d_args, ARGS_BYTES) == cudaSuccess && cudaMallocHost(&ctx->h_args, ARGS_BYTES) == cudaSuccess;
 	if (!ok) return B200_ERR_ALLOC;
@@ -135,7 +134,6 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	// opt in to large dynamic shared memory once
 	int32_t rc = B200_OK;
 #define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
-	SET(k_basis_products, FIELD_TABLE_BYTES);
 	SET(k_expand_lut, LUT_BYTES + 2048);
 	SET(k_expand_small, FIELD_TABLE_BYTES + 16 * 2048);
 	SET(k_inner_product, FIELD_TABLE_BYTES);
@@ -165,7 +163,6 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_tables);
-	cudaFree(ctx->d_basis);
 	cudaFree(ctx->d_results);
 	cudaFree(ctx->d_args);
 	cudaFreeHost(ctx->h_args);
@@ -304,18 +301,6 @@ int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uin
 }
 
 // -------------------------------------------------------------------------------------------------
-static int32_t launch_basis(b200_ctx *ctx, const uint64_t *zs, uint32_t n_maps) {
-	if (n_maps > MAX_LINMAPS) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many linear maps in one call (%u)", n_maps);
-	std::vector<uint4> h(n_maps);
-	for (uint32_t i = 0; i < n_maps; i++) h[i] = to_u4(zs + 2 * i);
-	void *dz;
-	int32_t rc = stage_args(ctx, h.data(), sizeof(uint4) * n_maps, &dz);
-	if (rc) return rc;
-	k_basis_products<<<n_maps, 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)dz, ctx->d_basis);
-	B200_LAUNCH_CHECK(ctx);
-	return B200_OK;
-}
-
 }  // extern "C"
 template <uint32_t THREADS, uint32_t UNR, int MINB>
 static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
@@ -352,16 +337,8 @@ static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint
 			live.push_back(s);
 		}
 	if (live.empty()) return B200_OK;
-	static int variant = getenv("B200_FOLD_VARIANT") ? atoi(getenv("B200_FOLD_VARIANT")) : 0;
-	switch (variant) {
-	case 1: return launch_lerp_variant<512, 4, 2>(ctx, live, z);
-	case 2: return launch_lerp_variant<256, 2, 4>(ctx, live, z);
-	case 3: return launch_lerp_variant<256, 4, 3>(ctx, live, z);
-	case 4: return launch_lerp_variant<1024, 2, 1>(ctx, live, z);
-	case 5: return launch_lerp_variant<512, 3, 2>(ctx, live, z);
-	case 6: return launch_lerp_variant<384, 2, 3>(ctx, live, z);
-	default: return launch_lerp_variant<512, 2, 2>(ctx, live, z);
-	}
+	// 512 threads x 2 elements in flight, 2 CTAs per SM (64 registers): best of the measured variants
+	return launch_lerp_variant<512, 2, 2>(ctx, live, z);
 }
 
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_dev_ptr e1, uint64_t n1, const uint64_t z[2]) {

@@ -23,8 +23,6 @@ struct b200_ctx {
 
 	// field tables (64 KiB B8 product table + 256 B times-X_2 table), device global memory
 	uint8_t *d_tables = nullptr;
-	// basis images for the LUT engine: up to MAX_LINMAPS x 128 uint4
-	uint4 *d_basis = nullptr;
 	// deferred scalar results (OpValue slots)
 	uint4 *d_results = nullptr;
 	uint32_t n_results = 0;
@@ -41,7 +39,6 @@ struct b200_ctx {
 namespace b200 {
 
 constexpr uint32_t MAX_RESULTS = 1u << 16;
-constexpr uint32_t MAX_LINMAPS = 64;
 constexpr uint64_t ARGS_BYTES = 4u << 20;
 
 inline int32_t fail(b200_ctx *ctx, int32_t code, const char *fmt, ...) {

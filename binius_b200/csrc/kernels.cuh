@@ -8,19 +8,6 @@
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------------
-// basis images for the LUT engine: W[m*128 + i] = beta_i * z[m]   (beta_i = 1 << i)
-// grid = n_maps, block = 128, dyn smem = FIELD_TABLE_BYTES
-__global__ void __launch_bounds__(128) k_basis_products(const uint8_t *__restrict__ g_tables, const uint4 *__restrict__ zs,
-														 uint4 *__restrict__ W) {
-	extern __shared__ __align__(128) uint8_t smem[];
-	FieldTables T = load_field_tables(smem, g_tables);
-	uint32_t i = threadIdx.x, m = blockIdx.x;
-	uint32_t w[4] = {0, 0, 0, 0};
-	w[i >> 5] = 1u << (i & 31);
-	W[m * 128 + i] = f_mul128(T, make_uint4(w[0], w[1], w[2], w[3]), zs[m]);
-}
-
-// ------------------------------------------------------------------------------------------------
 // fold-high / extrapolate_line over a list of segments sharing ONE challenge z:
 //     e0[i] ^= (e1[i] ^ e0[i]) * z            i <  pivot
 //     e0[i] ^= (suffix ^ e0[i]) * z           pivot <= i < upper
