@@ -94,6 +94,15 @@ static int32_t set_smem(b200_ctx *ctx, K kernel, uint32_t bytes) {
 
 }  // namespace b200
 
+static int32_t flush_pending(b200_ctx *ctx);
+#define B200_FLUSH(ctx)                                   \
+	do {                                                  \
+		if ((ctx) && !(ctx)->pending.empty()) {           \
+			int32_t rc__ = flush_pending(ctx);            \
+			if (rc__) return rc__;                        \
+		}                                                 \
+	} while (0)
+
 // =================================================================================================
 extern "C" {
 
@@ -161,6 +170,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 void b200_ctx_destroy(b200_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (!ctx->pending.empty()) flush_pending(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_tables);
 	cudaFree(ctx->d_results);
@@ -184,6 +194,7 @@ const char *b200_last_error(b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "nu
 void *b200_ctx_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t b200_ctx_launch_count(b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int32_t b200_ctx_set_stream(b200_ctx *ctx, void *s) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
@@ -197,11 +208,13 @@ int32_t b200_event_create(b200_ctx *ctx, void **out) {
 	return B200_OK;
 }
 int32_t b200_event_record(b200_ctx *ctx, void *e) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaEventRecord((cudaEvent_t)e, ctx->stream));
 	return B200_OK;
 }
 int32_t b200_event_elapsed_ms(b200_ctx *ctx, void *a, void *b, float *ms) {
+	B200_FLUSH(ctx);
 	if (!ctx || !ms) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)b));
 	B200_CUDA(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
@@ -223,6 +236,7 @@ int32_t b200_dev_alloc(b200_ctx *ctx, uint64_t n_elems, b200_dev_ptr *out) {
 	return B200_OK;
 }
 int32_t b200_dev_free(b200_ctx *ctx, b200_dev_ptr p) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	B200_CUDA(ctx, cudaFree(p));
@@ -243,6 +257,7 @@ int32_t b200_host_free(b200_ctx *ctx, void *p) {
 }
 
 int32_t b200_copy_h2d(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t n) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) return B200_OK;
 	B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyHostToDevice, ctx->stream));
@@ -250,17 +265,20 @@ int32_t b200_copy_h2d(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t
 	return B200_OK;
 }
 int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *dst, uint64_t n) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n) B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return B200_OK;
 }
 int32_t b200_copy_d2d(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n) B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
 	return B200_OK;
 }
 int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n, const uint64_t value[2]) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) return B200_OK;
 	k_fill<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((uint4 *)dst, n, to_u4(value));
@@ -268,18 +286,21 @@ int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n, const uint64_t va
 	return B200_OK;
 }
 int32_t b200_sync(b200_ctx *ctx) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return B200_OK;
 }
 
 int32_t b200_results_reset(b200_ctx *ctx) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (ctx->n_results) B200_CUDA(ctx, cudaMemsetAsync(ctx->d_results, 0, sizeof(uint4) * ctx->n_results, ctx->stream));
 	ctx->n_results = 0;
 	return B200_OK;
 }
 int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uint64_t *host_out) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) {
 		B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -344,15 +365,44 @@ static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_dev_ptr e1, uint64_t n1, const uint64_t z[2]) {
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n0 != n1) return fail(ctx, B200_ERR_INPUT_VALIDATION, "evals_0 and evals_1 must be the same length");
-	std::vector<LerpSeg> segs(1);
-	segs[0] = LerpSeg{(uint4 *)e0, (const uint4 *)e1, n0, n0, make_uint4(0, 0, 0, 0), 0};
-	return launch_lerp(ctx, segs, z);
+	if (n0 == 0) return B200_OK;
+	// deferred: queue the segment; everything queued with the same challenge goes out as one launch
+	// when any other entry point (or a conflicting fold) arrives
+	uint8_t *w0 = (uint8_t *)e0;
+	const uint8_t *r0 = (const uint8_t *)e1;
+	const uint64_t bytes = n0 * 16;
+	bool conflict = !ctx->pending.empty() && (ctx->pending_z[0] != z[0] || ctx->pending_z[1] != z[1] || ctx->pending.size() >= 4096);
+	auto overlap = [](const uint8_t *a, uint64_t an, const uint8_t *b, uint64_t bn) { return a < b + bn && b < a + an; };
+	for (size_t i = 0; i < ctx->pending.size() && !conflict; i++) {
+		const b200_pending_lerp &p = ctx->pending[i];
+		const uint64_t pb = p.n * 16;
+		// RAW / WAW on a pending output, or WAR on a pending input
+		conflict = overlap(w0, bytes, p.e0, pb) || overlap(r0, bytes, p.e0, pb) || overlap(w0, bytes, p.e1, pb);
+	}
+	if (conflict) B200_FLUSH(ctx);
+	ctx->pending_z[0] = z[0];
+	ctx->pending_z[1] = z[1];
+	ctx->pending.push_back(b200_pending_lerp{w0, r0, n0});
+	return B200_OK;
 }
+
+}  // extern "C"
+static int32_t flush_pending(b200_ctx *ctx) {
+	std::vector<LerpSeg> segs(ctx->pending.size());
+	for (size_t i = 0; i < segs.size(); i++) {
+		const b200_pending_lerp &p = ctx->pending[i];
+		segs[i] = LerpSeg{(uint4 *)p.e0, (const uint4 *)p.e1, p.n, p.n, make_uint4(0, 0, 0, 0), 0};
+	}
+	ctx->pending.clear();
+	return launch_lerp(ctx, segs, ctx->pending_z);
+}
+extern "C" {
 
 // Host-buffer form of the fold (what a ComputationBackend whose Vec<P> lives in host memory calls,
 // hal/src/backend.rs:19-31, 65-75): chunked 3-slot pipeline  H2D(e0,e1) -> k_lerp_lut -> D2H(e0)  on
 // three streams so that both PCIe directions and the kernel overlap.  Synchronous.
 int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *host_e1, uint64_t n, const uint64_t z[2]) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) return B200_OK;
 	const uint64_t CH = 1ull << 20;  // elements per chunk (16 MiB per operand)
@@ -396,6 +446,7 @@ int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *hos
 
 int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars,
 										   const uint64_t *prefix, const uint64_t *suffix, const uint64_t z[2], uint64_t *new_lens) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
 	uint64_t half = 1ull << (n_vars - 1);
@@ -413,6 +464,7 @@ int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *ml
 }
 
 int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, uint32_t log_n, const uint64_t *coords, uint32_t k) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (log_n + k > 60 || data_len != (1ull << (log_n + k))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data length: %llu", (unsigned long long)data_len);
 	if (k == 0) return B200_OK;
@@ -450,6 +502,7 @@ int32_t b200_tensor_product_full_query(b200_ctx *ctx, const uint64_t *query, uin
 static bool valid_level(uint32_t lvl) { return lvl == 0 || (lvl >= 3 && lvl <= 7); }
 
 int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t lvl, b200_dev_ptr b, uint64_t n_b, uint32_t *slot) {
+	B200_FLUSH(ctx);
 	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
 	if (lvl > 7 || (n_a << (7 - lvl)) != n_b) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid input: a_edeg=%u |a|=%llu |b|=%llu", lvl, (unsigned long long)n_a, (unsigned long long)n_b);
 	if (!valid_level(lvl)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "unsupported tower level %u", lvl);
@@ -462,6 +515,7 @@ int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t
 }
 
 static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (lvl > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid evals: tower_level=%u > 7", lvl);
 	if (!valid_level(lvl)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "unsupported tower level %u", lvl);
@@ -525,6 +579,7 @@ uint32_t b200_expr_n_vars(const b200_expr *e) { return e ? e->n_vars : 0; }
 static DevExpr dev_expr(const b200_expr *e) { return DevExpr{e->d_steps, (uint32_t)e->steps.size(), e->n_vars}; }
 
 int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, b200_dev_ptr out, uint64_t n_out, const b200_expr *expr) {
+	B200_FLUSH(ctx);
 	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
 	if (row_len != n_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "inputs and output must be the same length");
 	if (expr->n_vars > n_inputs) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition not match with input");
@@ -540,6 +595,7 @@ int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32
 }
 
 int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t n_in, const b200_dev_ptr *outs, const uint64_t *lens, uint32_t n_rounds) {
+	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (!is_pow2(n_in)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "input length must be a power of 2: %llu", (unsigned long long)n_in);
 	if (n_in < 2) return fail(ctx, B200_ERR_INPUT_VALIDATION, "input length must be greater than or equal to 2 in order to perform at least one reduction: %llu", (unsigned long long)n_in);
@@ -558,6 +614,7 @@ int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t
 
 // ---- KernelExecutor ------------------------------------------------------------------------------
 int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *slot) {
+	B200_FLUSH(ctx);
 	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
 	int32_t rc = new_slot(ctx, slot);
 	if (rc) return rc;
@@ -568,6 +625,7 @@ int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *
 	return B200_OK;
 }
 int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
+	B200_FLUSH(ctx);
 	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
 	if (slot >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "value slot %u not declared", slot);
 	if (expr->n_vars > n_inputs) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition not match with input");
@@ -582,6 +640,7 @@ int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inp
 	return B200_OK;
 }
 int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr a, b200_dev_ptr b, b200_dev_ptr dst) {
+	B200_FLUSH(ctx);
 	if (!ctx || log_len > 60) return B200_ERR_INPUT_VALIDATION;
 	uint64_t n = 1ull << log_len;
 	k_add<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)dst, n);
@@ -593,6 +652,7 @@ int32_t b200_kernel_add_assign(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr src
 }
 
 int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, const uint32_t *ia, const uint32_t *ib, uint32_t n_comp, const uint64_t coeff[2], uint32_t *slot_y1, uint32_t *slot_yinf) {
+	B200_FLUSH(ctx);
 	if (!ctx || !slot_y1 || !slot_yinf) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
 	for (uint32_t c = 0; c < n_comp; c++)
@@ -646,6 +706,7 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 }
 
 int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint64_t *lens, const uint64_t *suffix_evals, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
+	B200_FLUSH(ctx);
 	if (!ctx || !first_slot) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
 	if ((uint64_t)n_comp * n_points > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many (composition, point) pairs");
@@ -757,6 +818,7 @@ int32_t b200_ntt_get_subspace_eval(const b200_ntt *ntt, uint32_t i, uint64_t j, 
 }
 
 static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev_ptr data, uint32_t kd, uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z, uint64_t coset, uint32_t coset_bits, uint32_t skip_rounds) {
+	B200_FLUSH(ctx);
 	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
 	if (kd < ntt->kt || kd > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "element width 2^%u bits is not an extension of the twiddle field", kd);
 	// check_batch_transform_inputs_and_params (crates/ntt/src/single_threaded.rs:364-406), WIDTH = 1
@@ -891,6 +953,7 @@ int32_t b200_ntt_inverse(b200_ctx *ctx, const b200_ntt *ntt, b200_dev_ptr data, 
 }
 
 static int32_t ntt_host(b200_ctx *ctx, const b200_ntt *ntt, int inverse, void *host, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	B200_FLUSH(ctx);
 	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
 	if (kd < 3 || kd > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "bad element width");
 	uint64_t bytes = n << (kd - 3);
@@ -911,6 +974,7 @@ int32_t b200_ntt_inverse_host(b200_ctx *ctx, const b200_ntt *ntt, void *host, ui
 }
 
 int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint32_t log_batch, const uint64_t *challenges, uint32_t n_ch, b200_dev_ptr in, uint64_t n_in, b200_dev_ptr out, uint64_t n_out) {
+	B200_FLUSH(ctx);
 	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
 	if (log_len + log_batch > 60 || n_in != (1ull << (log_len + log_batch))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data_in length: %llu", (unsigned long long)n_in);
 	if (n_ch < log_batch) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid challenges length: %u", n_ch);

@@ -10,6 +10,15 @@
 
 #include "../../include/binius_b200.h"
 
+// one deferred extrapolate_line (see b200_extrapolate_line): consecutive folds with the same challenge
+// on disjoint slices are batched into ONE multi-segment launch (the executor contract allows deferral
+// as long as store-to-load order is kept, compute/src/layer.rs:90-99)
+struct b200_pending_lerp {
+	uint8_t *e0;
+	const uint8_t *e1;
+	uint64_t n;
+};
+
 struct b200_ctx {
 	int device = 0;
 	int n_sms = 148;
@@ -20,6 +29,8 @@ struct b200_ctx {
 	cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_k[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
 	std::string err;
 	uint64_t launches = 0;
+	std::vector<b200_pending_lerp> pending;
+	uint64_t pending_z[2] = {0, 0};
 
 	// field tables (64 KiB B8 product table + 256 B times-X_2 table), device global memory
 	uint8_t *d_tables = nullptr;

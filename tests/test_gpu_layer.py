@@ -346,3 +346,47 @@ def test_extrapolate_line_host_pipeline(hal, oracle, n):
     assert _same(hal.to_host(d0), a)
     hal.dev_free(d0)
     hal.dev_free(d1)
+
+
+def test_deferred_fold_batching(hal, oracle):
+    """consecutive extrapolate_line calls with one challenge are deferred and launched as ONE
+    multi-segment kernel; dependent folds, a different challenge or any other op flush the queue
+    (store-to-load order of compute/src/layer.rs:90-99 must be preserved)"""
+    m, n = 60, 1 << 9
+    z1, z2 = 0x1111111122222222_3333333344444444, 0x5555555566666666_7777777788888889
+    hosts = [oracle.rand_b128(800 + t, n) for t in range(m)]
+    devs = [hal.to_device(h) for h in hosts]
+    l0 = hal.launch_count()
+
+    def op(ex):
+        for d in devs:
+            lo, hi = d.split_half_mut()
+            ex.extrapolate_line(lo, hi, z1)
+        return []
+
+    hal.execute(op)
+    assert hal.launch_count() - l0 <= 2  # 60 folds -> two launches of <= 48 segments
+    exp = [oracle.extrapolate_line(h[: n // 2], h[n // 2:], z1) for h in hosts]
+    for d, e in zip(devs, exp):
+        assert _same(hal.to_host(d.slice(0, n // 2)), e)
+
+    # dependent chain + challenge switch + interleaved copy inside one execute
+    d, h = devs[0], exp[0]
+    scratch = hal.dev_alloc(n // 4)
+
+    def op2(ex):
+        a, b = d.slice(0, n // 4), d.slice(n // 4, n // 2)
+        ex.extrapolate_line(a, b, z1)  # queued
+        a2, b2 = d.slice(0, n // 8), d.slice(n // 8, n // 4)
+        ex.extrapolate_line(a2, b2, z1)  # reads the pending output -> flush first
+        ex.extrapolate_line(d.slice(n // 4, n // 4 + 8), d.slice(n // 2, n // 2 + 8), z2)  # new challenge -> flush
+        hal.copy_d2d(d.slice(0, n // 4), scratch)  # any other op -> flush
+        return []
+
+    hal.execute(op2)
+    r1 = oracle.extrapolate_line(h[: n // 4], h[n // 4: n // 2], z1)
+    r2 = oracle.extrapolate_line(r1[: n // 8], r1[n // 8: n // 4], z1)
+    r3 = oracle.extrapolate_line(h[n // 4: n // 4 + 8], hosts[0][n // 2: n // 2 + 8], z2)
+    got = hal.to_host(d.slice(0, n // 2))
+    assert _same(got[: n // 8], r2) and _same(got[n // 8: n // 4], r1[n // 8:]) and _same(got[n // 4: n // 4 + 8], r3)
+    assert _same(hal.to_host(scratch)[: n // 8], r2)
