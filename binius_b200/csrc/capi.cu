@@ -147,6 +147,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_expand_small, FIELD_TABLE_BYTES + 16 * 2048);
 	SET(k_inner_product, FIELD_TABLE_BYTES);
 	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
+	SET(k_fold_right_lut, LUT_BYTES + 2048);
 	SET(k_fold_mat<true>, FIELD_TABLE_BYTES);
 	SET(k_compute_composite, FIELD_TABLE_BYTES);
 	SET(k_sum_composition, FIELD_TABLE_BYTES);
@@ -154,6 +155,11 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_bivariate_round_evals, FIELD_TABLE_BYTES);
 	SET(k_eq_ind_round_evals, FIELD_TABLE_BYTES);
 	SET(k_fri_fold, FIELD_TABLE_BYTES);
+	SET(k_fri_fold_lut<1>, FIELD_TABLE_BYTES + 1 * NLUT_BYTES);
+	SET(k_fri_fold_lut<2>, FIELD_TABLE_BYTES + 2 * NLUT_BYTES);
+	SET(k_fri_fold_lut<3>, FIELD_TABLE_BYTES + 3 * NLUT_BYTES);
+	SET(k_fri_fold_lut<4>, FIELD_TABLE_BYTES + 4 * NLUT_BYTES);
+	SET(k_fri_fold_lut<5>, FIELD_TABLE_BYTES + 5 * NLUT_BYTES);
 	SET(k_ntt_pass<uint32_t>, FIELD_TABLE_BYTES + 4 * 8192 + 4 * 8192);
 	SET(k_ntt_pass<uint16_t>, FIELD_TABLE_BYTES + 4 * 8192 + 2 * 8192);
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
@@ -525,6 +531,11 @@ static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_
 	if (log_q > log_evals) return fail(ctx, B200_ERR_INPUT_VALIDATION, "query larger than evals");
 	uint64_t expect_out = 1ull << (log_evals - log_q);
 	if (n_out != expect_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output has %llu elements, expected %llu", (unsigned long long)n_out, (unsigned long long)expect_out);
+	if (right && (n_vec << lvl) == 128 && n_out >= 1024) {
+		k_fold_right_lut<<<grid_for(ctx, n_out, FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const uint4 *)mat, lvl, (const uint4 *)vec, (uint4 *)out, n_out);
+		B200_LAUNCH_CHECK(ctx);
+		return B200_OK;
+	}
 	uint32_t grid = grid_for(ctx, n_out, 256, 2);
 	if (right) k_fold_mat<true><<<grid, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)mat, lvl, (const uint4 *)vec, log_q, (uint4 *)out, n_out);
 	else k_fold_mat<false><<<grid, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)mat, lvl, (const uint4 *)vec, log_q, (uint4 *)out, n_out);
@@ -989,7 +1000,16 @@ int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint
 	int32_t rc = stage_args(ctx, hc.data(), 16 * hc.size(), &dc);
 	if (rc) return rc;
 	FriArgs A{(const uint4 *)in, (uint4 *)out, n_out, log_len, log_batch, n_ch, (const uint4 *)dc, ntt->d_s_evals, ntt->d, ntt->kt};
-	k_fri_fold<<<grid_for(ctx, n_out, 128, 2), 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	// arities 1..5: register-resident chunk + nibble-LUT lerps (one 8 KiB table per challenge)
+	uint32_t grid = grid_for(ctx, n_out, 256, 1);
+	switch (n_ch) {
+	case 1: k_fri_fold_lut<1><<<grid, 256, FIELD_TABLE_BYTES + 1 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
+	case 2: k_fri_fold_lut<2><<<grid, 256, FIELD_TABLE_BYTES + 2 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
+	case 3: k_fri_fold_lut<3><<<grid, 256, FIELD_TABLE_BYTES + 3 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
+	case 4: k_fri_fold_lut<4><<<grid, 256, FIELD_TABLE_BYTES + 4 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
+	case 5: k_fri_fold_lut<5><<<grid, 256, FIELD_TABLE_BYTES + 5 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
+	default: k_fri_fold<<<grid_for(ctx, n_out, 128, 2), 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
+	}
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
 }

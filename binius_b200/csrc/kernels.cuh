@@ -174,6 +174,23 @@ __global__ void __launch_bounds__(256) k_fold_mat(const uint8_t *__restrict__ g_
 	}
 }
 
+// fold_right fast path (the ring-switch shape, core/src/ring_switch/eq_ind.rs:140-146): when
+// vec.len() * 2^lvl == 128 every output is a GF(2)-linear image of ONE input element,
+//   out[i] = sum_j vec[j] * limb_j(mat[i]) = L(mat[i]),   L(beta_{j*2^lvl + s}) = vec[j] * beta_s,
+// so the byte-LUT engine applies: 16 conflict-free LDS.128 per output instead of 128/2^lvl multiplies.
+__global__ void __launch_bounds__(FOLD_THREADS, 2) k_fold_right_lut(const uint4 *__restrict__ mat, uint32_t lvl, const uint4 *__restrict__ vec,
+																   uint4 *__restrict__ out, uint64_t n_out) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *tbl = smem;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) stage[(i & 7) * 16 + (i >> 3)] = basis_image(__ldg(vec + (i >> lvl)), i & ((1u << lvl) - 1));
+	__syncthreads();
+	lut_build_images(tbl, stage);
+	const LutLane L = lut_lane_init();
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = lut_apply(tbl, L, __ldg(mat + i));
+}
+
 // ------------------------------------------------------------------------------------------------
 // ArithCircuit interpreter (math/src/arith_expr.rs:367-383)
 constexpr uint32_t MAX_EXPR_STEPS = 64;
@@ -384,6 +401,47 @@ __global__ void __launch_bounds__(128) k_fri_fold(const uint8_t *__restrict__ g_
 			}
 			L--;
 			sz--;
+		}
+		A.out[c] = v[0];
+	}
+}
+
+// Fast path for n_ch = NCH <= 5 challenges (the prover's arities): the chunk lives in registers and
+// every lerp `u + (v-u)*challenge` is a multiplication by one of NCH broadcast constants, served by
+// the nibble-LUT engine (8 KiB of shared memory per challenge) instead of the general multiply.
+// dyn smem = FIELD_TABLE_BYTES + NCH * NLUT_BYTES
+template <uint32_t NCH>
+__global__ void __launch_bounds__(256) k_fri_fold_lut(const uint8_t *__restrict__ g_tables, FriArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint8_t *luts = smem + FIELD_TABLE_BYTES;
+	for (uint32_t r = 0; r < NCH; r++) nlut_build_mul(luts + r * NLUT_BYTES, A.challenges[r]);
+	const NLutLane L = nlut_lane_init();
+	constexpr uint32_t CHUNK = 1u << NCH;
+	const uint32_t log_batch = A.log_batch;
+	for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < A.n_out; c += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 v[CHUNK];
+#pragma unroll
+		for (uint32_t i = 0; i < CHUNK; i++) v[i] = __ldg(A.in + c * CHUNK + i);
+#pragma unroll
+		for (uint32_t r = 0; r < NCH; r++) {
+			const uint8_t *lut = luts + r * NLUT_BYTES;
+			if (r < log_batch) {
+#pragma unroll
+				for (uint32_t o = 0; o < (CHUNK >> (r + 1)); o++) v[o] = v[2 * o] ^ nlut_apply(lut, L, v[2 * o] ^ v[2 * o + 1]);
+			} else {
+				const uint32_t k = r - log_batch;             // fold round index
+				const uint32_t Llen = A.log_len - k, sz = (NCH - log_batch) - k;
+				const uint32_t row = A.d - Llen;
+#pragma unroll
+				for (uint32_t o = 0; o < (CHUNK >> (r + 1)); o++) {
+					uint32_t t = twiddle_on_the_fly(A.s_evals + row * 32, A.d - 1 - row, (c << (sz - 1)) | o);
+					uint4 u = v[2 * o], w = v[2 * o + 1];
+					w ^= u;
+					u ^= f_mul128_sub(T, w, make_uint4(t, 0, 0, 0), A.kt);
+					v[o] = u ^ nlut_apply(lut, L, u ^ w);
+				}
+			}
 		}
 		A.out[c] = v[0];
 	}

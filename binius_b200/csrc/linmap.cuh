@@ -123,4 +123,61 @@ __device__ __forceinline__ uint4 lut_apply(const uint8_t *tbl, const LutLane &L,
 	return (a0 ^ a1) ^ (a2 ^ a3);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Nibble variant: 32 tables of 16 entries = 8 KiB per constant instead of 64 KiB, 32 gathers per
+// product instead of 16.  For ops that multiply by SEVERAL constants in one kernel (fri_fold: one
+// table per folding challenge).  Entry (p, e) of nibble position p lives at
+//       (p >> 3) * 2048 + e * 128 + (p & 7) * 16
+// and lane j (= lane & 7) visits the positions in the order p = s ^ j: same conflict-free argument
+// as above.  The per-lane pre-permutation is a PRMT (bytes, bits 1-2 of j) plus a nibble swap (bit 0).
+constexpr uint32_t NLUT_BYTES = 8192;
+
+struct NLutLane {
+	uint32_t sel;     // PRMT selector: byte index XOR ((j >> 1) & 3)
+	uint32_t nswap;   // nonzero: swap the nibbles of every byte (j & 1)
+	uint32_t off[8];  // ((s & 7) ^ j) << 4
+};
+__device__ __forceinline__ NLutLane nlut_lane_init() {
+	NLutLane L;
+	uint32_t j = threadIdx.x & 7;
+	L.sel = 0x3210u ^ (((j >> 1) & 3u) * 0x1111u);
+	L.nswap = j & 1u;
+#pragma unroll
+	for (uint32_t s = 0; s < 8; s++) L.off[s] = ((s ^ j) << 4);
+	return L;
+}
+// build the table of x -> x * z; all threads of the CTA must call (ends with __syncthreads)
+__device__ __forceinline__ void nlut_build_mul(uint8_t *tbl, uint4 z) {
+	for (uint32_t e = threadIdx.x; e < 512; e += blockDim.x) {
+		uint32_t p = e & 31, v = e >> 5;  // consecutive lanes -> consecutive positions -> distinct bank-quads
+		uint4 acc = u4_zero();
+#pragma unroll
+		for (uint32_t i = 0; i < 4; i++)
+			if ((v >> i) & 1u) acc ^= basis_image(z, 4 * p + i);
+		*reinterpret_cast<uint4 *>(tbl + (p >> 3) * 2048 + v * 128 + (p & 7) * 16) = acc;
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ uint4 nlut_ld(const uint8_t *tbl, uint32_t w, uint32_t n, uint32_t blk, uint32_t off) {
+	// ((w >> 4n) & 15) * 128
+	uint32_t r = n >= 2 ? ((w >> (4 * n - 7)) & 0x780u) : ((w << (7 - 4 * n)) & 0x780u);
+	return *reinterpret_cast<const uint4 *>(tbl + blk * 2048u + r + off);
+}
+__device__ __forceinline__ uint4 nlut_apply(const uint8_t *tbl, const NLutLane &L, uint4 x) {
+	uint32_t w[4] = {x.x, x.y, x.z, x.w};
+	uint4 a0 = u4_zero(), a1 = u4_zero();
+#pragma unroll
+	for (uint32_t k = 0; k < 4; k++) {
+		uint32_t v = __byte_perm(w[k], 0u, L.sel);
+		uint32_t sw = ((v & 0x0F0F0F0Fu) << 4) | ((v >> 4) & 0x0F0F0F0Fu);
+		v = L.nswap ? sw : v;
+#pragma unroll
+		for (uint32_t n = 0; n < 8; n += 2) {
+			a0 ^= nlut_ld(tbl, v, n, k, L.off[n]);
+			a1 ^= nlut_ld(tbl, v, n + 1, k, L.off[n + 1]);
+		}
+	}
+	return a0 ^ a1;
+}
+
 }  // namespace b200

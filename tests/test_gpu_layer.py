@@ -390,3 +390,15 @@ def test_deferred_fold_batching(hal, oracle):
     got = hal.to_host(d.slice(0, n // 2))
     assert _same(got[: n // 8], r2) and _same(got[n // 8: n // 4], r1[n // 8:]) and _same(got[n // 4: n // 4 + 8], r3)
     assert _same(hal.to_host(scratch)[: n // 8], r2)
+
+
+@pytest.mark.parametrize("lvl", [0, 3, 4, 5, 6, 7])
+def test_fold_right_ring_switch_shape(hal, oracle, lvl):
+    # ring-switch shape (core/src/ring_switch/eq_ind.rs:140-146): vec.len() * 2^lvl == 128 -> LUT fast path
+    import binius_b200
+
+    n = 1 << 12
+    mat, vec = oracle.rand_b128(910 + lvl, n), oracle.rand_b128(920 + lvl, 128 >> lvl)
+    dm, dv, do = hal.to_device(mat), hal.to_device(vec), hal.dev_alloc(n)
+    hal.execute(lambda ex: (ex.fold_right(binius_b200.SubfieldSlice(dm, lvl), dv, do), [])[1])
+    assert _same(hal.to_host(do), oracle.fold_right(mat, lvl, vec, n))
