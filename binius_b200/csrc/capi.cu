@@ -4,7 +4,12 @@
 #include <cstring>
 #include <memory>
 
+#include <map>
+#include <set>
+#include <tuple>
+
 #include "context.hpp"
+#include "eqind_plan.hpp"
 #include "host_field.hpp"
 #include "kernels.cuh"
 #include "ntt.cuh"
@@ -17,6 +22,8 @@ struct b200_expr {
 	std::vector<b200_expr_step> steps;
 	b200_expr_step *d_steps = nullptr;
 	uint32_t n_vars = 0;
+	plan::Poly poly;       // monomial expansion (eqind_plan.hpp), valid when poly_ok
+	bool poly_ok = false;  // degree <= 2 and few terms
 };
 
 struct b200_ntt {
@@ -49,11 +56,18 @@ int32_t ensure_scratch(b200_ctx *ctx, uint64_t bytes) {
 		ctx->d_scratch = nullptr;
 		ctx->scratch_bytes = 0;
 	}
-	if (cudaMalloc(&ctx->d_scratch, bytes) != cudaSuccess) {
+	// grow with 25% headroom in 32 MiB steps: successive rounds need slightly different sizes and a
+	// reallocation costs a stream sync + cudaFree + cudaMalloc (~10 ms)
+	uint64_t want = ((bytes + bytes / 4) + (32ull << 20) - 1) & ~((32ull << 20) - 1);
+	if (cudaMalloc(&ctx->d_scratch, want) != cudaSuccess) {
 		cudaGetLastError();
-		return fail(ctx, B200_ERR_ALLOC, "out of device memory (scratch %llu bytes)", (unsigned long long)bytes);
+		want = bytes;
+		if (cudaMalloc(&ctx->d_scratch, want) != cudaSuccess) {
+			cudaGetLastError();
+			return fail(ctx, B200_ERR_ALLOC, "out of device memory (scratch %llu bytes)", (unsigned long long)bytes);
+		}
 	}
-	ctx->scratch_bytes = bytes;
+	ctx->scratch_bytes = want;
 	return B200_OK;
 }
 
@@ -94,8 +108,141 @@ static int32_t set_smem(b200_ctx *ctx, K kernel, uint32_t bytes) {
 
 }  // namespace b200
 
+// Inner-product jobs on the tensor cores: gmat scratch, k_pair_tc over job pairs, combine into result slots.
+static int32_t launch_tc_pairs(b200_ctx *ctx, std::vector<tc::TcJob> &jobs, uint64_t len, const std::vector<tc::TcTarget> &targets,
+							   uint64_t scratch_offset = 0) {
+	if (jobs.empty() || targets.empty()) return B200_OK;
+	if (jobs.size() & 1) jobs.push_back(jobs.back());  // pad to a pair; the duplicate's result is ignored
+	const uint32_t n_pairs = (uint32_t)(jobs.size() / 2);
+	if (n_pairs > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many inner-product jobs");
+	const uint64_t gbytes = (uint64_t)jobs.size() * 512 * 4;
+	int32_t rc = ensure_scratch(ctx, scratch_offset + gbytes);
+	if (rc) return rc;
+	uint32_t *gmat = (uint32_t *)(ctx->d_scratch + scratch_offset);
+	B200_CUDA(ctx, cudaMemsetAsync(gmat, 0, gbytes, ctx->stream));
+	ArgPack pack;
+	size_t o_j = pack.add(jobs.data(), sizeof(tc::TcJob) * jobs.size()), o_t = pack.add(targets.data(), sizeof(tc::TcTarget) * targets.size());
+	uint8_t *dbase;
+	if ((rc = pack.commit(ctx, &dbase))) return rc;
+	tc::TcArgs T;
+	T.jobs = (const tc::TcJob *)(dbase + o_j);
+	T.len = len;
+	T.gmat = gmat;
+	const uint64_t n_chunks = len / tc::CHUNK;
+	// whole waves only: 2 CTAs per SM are resident (256 TMEM columns each); a partial extra wave costs a full one
+	const uint32_t resident = 2 * ctx->n_sms;
+	uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, resident / std::min(n_pairs, resident)));
+	tc::k_pair_tc<<<dim3(gx, n_pairs), tc::THREADS, tc::NSTAGE * tc::STAGE_BYTES + 1024, ctx->stream>>>(T);
+	B200_LAUNCH_CHECK(ctx);
+	tc::k_pair_tc_combine<<<(uint32_t)targets.size(), 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, gmat, (const tc::TcTarget *)(dbase + o_t), ctx->d_results);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+// Monomial plan for eq-ind round evaluations at the points 1 and infinity (eqind_plan.hpp): every
+// (composition, point) sum is a coefficient-weighted combination of inner products shared between the
+// compositions; a degree-2 monomial x*y costs one elementwise product w = E . P_x per covering variable.
+static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint64_t half, b200_dev_ptr eq_ind, const b200_expr *const *comps,
+									const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, uint32_t n_points, uint32_t first_slot) {
+	struct AJob {
+		uint32_t code;
+		int32_t scaled;  // -1: the eq-indicator itself, else index of the scaled vector
+		int32_t y;       // -1: the all-ones vector (constant term), else the multilinear
+	};
+	struct AScale {
+		uint32_t code, x;
+	};
+	std::vector<AJob> ajobs;
+	std::vector<AScale> scales;
+	std::vector<tc::TcTarget> targets;
+	std::map<std::tuple<uint32_t, int32_t, int32_t>, uint32_t> job_ix;
+	bool need_ones = false;
+	for (uint32_t code = 1; code <= 2; code++) {
+		std::vector<uint32_t> pts;
+		for (uint32_t p = 0; p < n_points; p++)
+			if (codes[p] == code) pts.push_back(p);
+		if (pts.empty()) continue;
+		auto poly = [&](uint32_t c) -> const plan::Poly & { return code == 1 ? comps[c]->poly : leads[c]->poly; };
+		// greedy vertex cover of the degree-2 monomial graph; covering variables get scaled by E
+		std::set<std::pair<uint32_t, uint32_t>> left;
+		for (uint32_t c = 0; c < n_comp; c++)
+			for (auto &t : poly(c))
+				if (t.first.size() == 2) left.insert({t.first[0], t.first[1]});
+		std::map<uint32_t, int32_t> cover;
+		while (!left.empty()) {
+			std::map<uint32_t, uint32_t> cnt;
+			for (auto &e : left) {
+				cnt[e.first]++;
+				if (e.second != e.first) cnt[e.second]++;
+			}
+			uint32_t best = cnt.begin()->first;
+			for (auto &kv : cnt)
+				if (kv.second > cnt[best]) best = kv.first;
+			cover[best] = (int32_t)scales.size();
+			scales.push_back(AScale{code, best});
+			for (auto it = left.begin(); it != left.end();)
+				it = (it->first == best || it->second == best) ? left.erase(it) : std::next(it);
+		}
+		auto job = [&](int32_t scaled, int32_t y) {
+			auto key = std::make_tuple(code, scaled, y);
+			auto it = job_ix.find(key);
+			if (it != job_ix.end()) return it->second;
+			uint32_t j = (uint32_t)ajobs.size();
+			ajobs.push_back(AJob{code, scaled, y});
+			job_ix[key] = j;
+			return j;
+		};
+		for (uint32_t c = 0; c < n_comp; c++)
+			for (auto &t : poly(c)) {
+				uint32_t j;
+				if (t.first.empty()) {
+					need_ones = true;
+					j = job(-1, -1);
+				} else if (t.first.size() == 1) {
+					j = job(-1, (int32_t)t.first[0]);
+				} else {
+					auto cx = cover.find(t.first[0]);
+					j = cx != cover.end() ? job(cx->second, (int32_t)t.first[1]) : job(cover.at(t.first[1]), (int32_t)t.first[0]);
+				}
+				uint64_t w[2] = {(uint64_t)t.second, (uint64_t)(t.second >> 64)};
+				for (uint32_t p : pts) targets.push_back(tc::TcTarget{j, first_slot + c * n_points + p, to_u4(w)});
+			}
+	}
+	if (targets.empty()) return B200_OK;  // all compositions vanish identically: slots stay zero
+	const uint64_t n_scale = scales.size();
+	const uint64_t off_ones = n_scale * half * 16, off_g = off_ones + (need_ones ? half * 16 : 0);
+	int32_t rc = ensure_scratch(ctx, off_g + (uint64_t)(ajobs.size() + 1) * 512 * 4);
+	if (rc) return rc;
+	uint4 *base = (uint4 *)ctx->d_scratch, *ones = (uint4 *)(ctx->d_scratch + off_ones);
+	if (n_scale) {
+		std::vector<EqScaleOp> ops(n_scale);
+		for (uint64_t s = 0; s < n_scale; s++) {
+			const uint4 *x = (const uint4 *)mls[scales[s].x];
+			ops[s] = EqScaleOp{x + half, scales[s].code == 2 ? x : nullptr, base + s * half};
+		}
+		void *d_ops;
+		if ((rc = stage_args(ctx, ops.data(), sizeof(EqScaleOp) * n_scale, &d_ops))) return rc;
+		uint32_t gx = grid_for(ctx, half, 256, 3);
+		gx = std::max<uint32_t>(1, std::min<uint64_t>(gx, (uint64_t)ctx->n_sms * 6 / std::min<uint64_t>(n_scale, ctx->n_sms * 6) + 1));
+		k_eq_scale<<<dim3(gx, (uint32_t)n_scale), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)eq_ind, (const EqScaleOp *)d_ops, half);
+		B200_LAUNCH_CHECK(ctx);
+	}
+	if (need_ones) {
+		k_fill<<<grid_for(ctx, half, 256, 8), 256, 0, ctx->stream>>>(ones, half, make_uint4(1, 0, 0, 0));
+		B200_LAUNCH_CHECK(ctx);
+	}
+	std::vector<tc::TcJob> jobs(ajobs.size());
+	for (size_t j = 0; j < ajobs.size(); j++) {
+		const AJob &a = ajobs[j];
+		const uint4 *y = a.y < 0 ? nullptr : (const uint4 *)mls[a.y];
+		jobs[j] = tc::TcJob{a.scaled < 0 ? (const uint4 *)eq_ind : base + (uint64_t)a.scaled * half, nullptr, y ? y + half : ones,
+							(y && a.code == 2) ? y : nullptr};
+	}
+	return launch_tc_pairs(ctx, jobs, half, targets, off_g);
+}
+
 static int32_t flush_pending(b200_ctx *ctx);
-#define B200_FLUSH(ctx)                                   \
+#define B200_FLUSH(ctx)                                  \
 	do {                                                  \
 		if ((ctx) && !(ctx)->pending.empty()) {           \
 			int32_t rc__ = flush_pending(ctx);            \
@@ -154,6 +301,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_pairwise_product, FIELD_TABLE_BYTES);
 	SET(k_bivariate_round_evals, FIELD_TABLE_BYTES);
 	SET(k_eq_ind_round_evals, FIELD_TABLE_BYTES);
+	SET(k_eq_ind_vals, FIELD_TABLE_BYTES);
+	SET(k_eq_scale, FIELD_TABLE_BYTES);
 	SET(k_fri_fold, FIELD_TABLE_BYTES);
 	SET(k_fri_fold_lut<1>, FIELD_TABLE_BYTES + 1 * NLUT_BYTES);
 	SET(k_fri_fold_lut<2>, FIELD_TABLE_BYTES + 2 * NLUT_BYTES);
@@ -165,8 +314,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
 	SET(k_ntt_bs_pass, 4 * 1024 + 128 * 1024);
 	SET(k_ntt_bs_low, 152 * 1024 + 640);
-	SET(tc::k_bivariate_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
-	SET(tc::k_bivariate_tc_combine, FIELD_TABLE_BYTES);
+	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
+	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
 #undef SET
 	if (rc != B200_OK) return rc;
 	*out = ctx.release();
@@ -572,6 +721,7 @@ int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n
 	std::unique_ptr<b200_expr> e(new b200_expr);
 	e->steps.assign(steps, steps + n_steps);
 	e->n_vars = n_vars;
+	e->poly_ok = plan::expand(steps, n_steps, 2, 64, e->poly);
 	if (cudaMalloc(&e->d_steps, sizeof(b200_expr_step) * std::max(n_steps, 1u)) != cudaSuccess) {
 		cudaGetLastError();
 		return fail(ctx, B200_ERR_ALLOC, "out of device memory");
@@ -683,32 +833,25 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 		pows[c] = to_u4(w);
 		pw = hostf::mul128(pw, a);
 	}
+	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
+	if (tc_mode && half >= 4096 && half % tc::CHUNK == 0) {
+		// tensor-core path (roundevals_tc.cuh): two inner-product jobs per composition
+		std::vector<tc::TcJob> jobs(2 * (size_t)n_comp);
+		std::vector<tc::TcTarget> targets(jobs.size());
+		for (uint32_t c = 0; c < n_comp; c++) {
+			const uint4 *a = (const uint4 *)mls[ia[c]], *b = (const uint4 *)mls[ib[c]];
+			jobs[2 * c] = tc::TcJob{a + half, nullptr, b + half, nullptr};
+			jobs[2 * c + 1] = tc::TcJob{a + half, a, b + half, b};
+			targets[2 * c] = tc::TcTarget{2 * c, *slot_y1, pows[c]};
+			targets[2 * c + 1] = tc::TcTarget{2 * c + 1, *slot_yinf, pows[c]};
+		}
+		return launch_tc_pairs(ctx, jobs, half, targets);
+	}
 	ArgPack pack;
 	size_t o_m = pack.add(mls, sizeof(void *) * m), o_a = pack.add(ia, 4 * n_comp), o_b = pack.add(ib, 4 * n_comp), o_p = pack.add(pows.data(), 16 * n_comp);
 	uint8_t *dbase;
 	if ((rc = pack.commit(ctx, &dbase))) return rc;
 	void *dm = dbase + o_m, *dia = dbase + o_a, *dib = dbase + o_b, *dp = dbase + o_p;
-	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
-	if (tc_mode && half >= 4096 && half % tc::CHUNK == 0) {
-		// tensor-core path (roundevals_tc.cuh): bit-GEMM with tcgen05.mma.kind::i8, parity epilogue
-		uint64_t gbytes = (uint64_t)n_comp * 2 * 512 * 4;
-		if ((rc = ensure_scratch(ctx, gbytes))) return rc;
-		B200_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, gbytes, ctx->stream));
-		tc::TcArgs T;
-		T.mls = (const uint4 *const *)dm;
-		T.ia = (const uint32_t *)dia;
-		T.ib = (const uint32_t *)dib;
-		T.half = half;
-		T.gmat = (uint32_t *)ctx->d_scratch;
-		uint64_t n_chunks = (half + tc::CHUNK - 1) / tc::CHUNK;
-		// exactly one wave: 2 CTAs per SM are resident (256 TMEM columns each); a partial second wave would double the time
-		uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, (uint64_t)(2 * ctx->n_sms) / n_comp));
-		tc::k_bivariate_tc<<<dim3(gx, n_comp), tc::THREADS, tc::NSTAGE * tc::STAGE_BYTES + 1024, ctx->stream>>>(T);
-		B200_LAUNCH_CHECK(ctx);
-		tc::k_bivariate_tc_combine<<<n_comp, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint32_t *)ctx->d_scratch, (const uint4 *)dp, ctx->d_results + *slot_y1, ctx->d_results + *slot_yinf);
-		B200_LAUNCH_CHECK(ctx);
-		return B200_OK;
-	}
 	uint32_t gx = grid_for(ctx, half, 256, 2);
 	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::max(1u, std::min(n_comp, (uint32_t)ctx->n_sms * 4)) + 1)));
 	k_bivariate_round_evals<<<dim3(gx, n_comp), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *const *)dm, half, (const uint32_t *)dia, (const uint32_t *)dib, (const uint4 *)dp, ctx->d_results + *slot_y1, ctx->d_results + *slot_yinf);
@@ -746,6 +889,18 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const ui
 		if (hlen[t] > (1ull << n_vars)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: stored length exceeds 2^n_vars", t);
 		hs[t] = suffix_evals ? to_u4(suffix_evals + 2 * t) : make_uint4(0, 0, 0, 0);
 	}
+	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
+	const uint64_t half = 1ull << (n_vars - 1);
+	if (tc_mode >= 1 && tc_mode != 2 && half >= 4096 && half % tc::CHUNK == 0) {
+		// points 1 / infinity only, full-length multilinears, degree <= 2: monomial plan, no interpreter
+		bool ok = true;
+		for (uint32_t t = 0; t < m && ok; t++) ok = hlen[t] == 2 * half;
+		for (uint32_t p = 0; p < n_points && ok; p++) {
+			ok = codes[p] == 1 || codes[p] == 2;
+			for (uint32_t c = 0; c < n_comp && ok; c++) ok = codes[p] == 1 ? comps[c]->poly_ok : leads[c]->poly_ok;
+		}
+		if (ok) return eq_ind_monomial_plan(ctx, mls, half, eq_ind, comps, leads, n_comp, codes, n_points, *first_slot);
+	}
 	ArgPack pack;
 	size_t o_m = pack.add(mls, sizeof(void *) * m), o_l = pack.add(hlen.data(), 8 * hlen.size()), o_s = pack.add(hs.data(), 16 * hs.size());
 	size_t o_c = pack.add(hc.data(), sizeof(DevExpr) * n_comp), o_ld = pack.add(hl.data(), sizeof(DevExpr) * n_comp);
@@ -766,6 +921,22 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const ui
 	A.slots = ctx->d_results + *first_slot;
 	uint32_t gx = grid_for(ctx, A.half, 256, 2);
 	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::min(total, (uint32_t)ctx->n_sms * 4) + 1)));
+	const uint64_t vals_bytes = (uint64_t)total * A.half * 16;
+	if (tc_mode && A.half >= 4096 && A.half % tc::CHUNK == 0 && vals_bytes <= (48ull << 30)) {
+		// materialise C(P(i)), then sum_i E[i] * val[i] as tensor-core inner-product jobs
+		const uint64_t gmat_bytes = (uint64_t)(total + 1) * 512 * 4;
+		if ((rc = ensure_scratch(ctx, vals_bytes + gmat_bytes))) return rc;
+		uint4 *vals = (uint4 *)ctx->d_scratch;
+		k_eq_ind_vals<<<dim3(gx, total), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A, vals);
+		B200_LAUNCH_CHECK(ctx);
+		std::vector<tc::TcJob> jobs(total);
+		std::vector<tc::TcTarget> targets(total);
+		for (uint32_t j = 0; j < total; j++) {
+			jobs[j] = tc::TcJob{(const uint4 *)eq_ind, nullptr, vals + (uint64_t)j * A.half, nullptr};
+			targets[j] = tc::TcTarget{j, *first_slot + j, make_uint4(1, 0, 0, 0)};
+		}
+		return launch_tc_pairs(ctx, jobs, A.half, targets, vals_bytes);
+	}
 	k_eq_ind_round_evals<<<dim3(gx, total), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;

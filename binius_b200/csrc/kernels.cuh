@@ -311,6 +311,34 @@ struct EqIndArgs {
 };
 constexpr uint32_t MAX_EQIND_MLS = 24;  // per-thread operand staging for the general-point path
 
+// C^{(p)}(P(i)) for one composition / evaluation point / hypercube index
+__device__ __forceinline__ uint4 eq_ind_eval_point(const FieldTables &T, const EqIndArgs &A, const DevExpr &E, uint32_t code, uint4 z, uint64_t i) {
+	uint4 tmp[MAX_EXPR_STEPS];
+	for (uint32_t s = 0; s < E.n_steps; s++) {
+		const b200_expr_step st = E.steps[s];
+		uint4 v;
+		switch (st.op) {
+		case 0: v = tmp[st.l] ^ tmp[st.r]; break;
+		case 1: v = f_mul128(T, tmp[st.l], tmp[st.r]); break;
+		case 2: v = f_pow128(T, tmp[st.l], st.r); break;
+		case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
+		default: {
+			const uint4 *m = A.mls[st.l];
+			const uint64_t len = A.lens[st.l];
+			uint4 hi = A.half + i < len ? __ldg(m + A.half + i) : A.suffix[st.l];
+			if (code == 1) v = hi;
+			else {
+				uint4 lo = i < len ? __ldg(m + i) : A.suffix[st.l];
+				uint4 d = hi ^ lo;
+				v = code == 2 ? d : (lo ^ f_mul128(T, d, z));
+			}
+		}
+		}
+		tmp[s] = v;
+	}
+	return E.n_steps ? tmp[E.n_steps - 1] : u4_zero();
+}
+
 __global__ void __launch_bounds__(256) k_eq_ind_round_evals(const uint8_t *__restrict__ g_tables, EqIndArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	FieldTables T = load_field_tables(smem, g_tables);
@@ -320,35 +348,43 @@ __global__ void __launch_bounds__(256) k_eq_ind_round_evals(const uint8_t *__res
 	const DevExpr E = code == 2 ? A.comps_lead[c] : A.comps[c];
 	uint4 z = A.points[p];
 	uint4 acc = u4_zero();
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.half; i += (uint64_t)gridDim.x * blockDim.x) {
-		uint4 tmp[MAX_EXPR_STEPS];
-		for (uint32_t s = 0; s < E.n_steps; s++) {
-			const b200_expr_step st = E.steps[s];
-			uint4 v;
-			switch (st.op) {
-			case 0: v = tmp[st.l] ^ tmp[st.r]; break;
-			case 1: v = f_mul128(T, tmp[st.l], tmp[st.r]); break;
-			case 2: v = f_pow128(T, tmp[st.l], st.r); break;
-			case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
-			default: {
-				const uint4 *m = A.mls[st.l];
-				const uint64_t len = A.lens[st.l];
-				uint4 hi = A.half + i < len ? __ldg(m + A.half + i) : A.suffix[st.l];
-				if (code == 1) v = hi;
-				else {
-					uint4 lo = i < len ? __ldg(m + i) : A.suffix[st.l];
-					uint4 d = hi ^ lo;
-					v = code == 2 ? d : (lo ^ f_mul128(T, d, z));
-				}
-			}
-			}
-			tmp[s] = v;
-		}
-		uint4 val = E.n_steps ? tmp[E.n_steps - 1] : u4_zero();
-		acc ^= f_mul128(T, val, __ldg(A.eq_ind + i));
-	}
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.half; i += (uint64_t)gridDim.x * blockDim.x)
+		acc ^= f_mul128(T, eq_ind_eval_point(T, A, E, code, z, i), __ldg(A.eq_ind + i));
 	acc = block_xor(acc, red);
 	if (threadIdx.x == 0) atomic_xor_u4(A.slots + blockIdx.y, acc);
+}
+
+// Large rounds: the composition values are materialised (vals[(c*n_points + p) * half + i]) and the
+// weighted sums sum_i E[i] * val[i] run as inner-product jobs on the tensor cores (roundevals_tc.cuh),
+// which removes the per-point multiplication by the eq-indicator from the ALU path.
+__global__ void __launch_bounds__(256) k_eq_ind_vals(const uint8_t *__restrict__ g_tables, EqIndArgs A, uint4 *__restrict__ vals) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint32_t c = blockIdx.y / A.n_points, p = blockIdx.y % A.n_points;
+	uint32_t code = A.codes[p];
+	const DevExpr E = code == 2 ? A.comps_lead[c] : A.comps[c];
+	uint4 z = A.points[p];
+	uint4 *out = vals + (uint64_t)blockIdx.y * A.half;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.half; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = eq_ind_eval_point(T, A, E, code, z, i);
+}
+
+// Degree-2 monomials of the monomial plan (eqind_plan.hpp): w[i] = E[i] * (x0[i] ^ x1[i]) (x1 may be
+// null).  blockIdx.y = scaled vector.
+struct EqScaleOp {
+	const uint4 *x0, *x1;
+	uint4 *w;
+};
+__global__ void __launch_bounds__(256) k_eq_scale(const uint8_t *__restrict__ g_tables, const uint4 *__restrict__ eq_ind,
+												  const EqScaleOp *__restrict__ ops, uint64_t len) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	const EqScaleOp op = ops[blockIdx.y];
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 x = __ldg(op.x0 + i);
+		if (op.x1) x = x ^ __ldg(op.x1 + i);
+		op.w[i] = f_mul128(T, x, __ldg(eq_ind + i));
+	}
 }
 
 // ------------------------------------------------------------------------------------------------

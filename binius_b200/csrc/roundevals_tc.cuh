@@ -1,4 +1,4 @@
-// roundevals_tc.cuh -- bivariate-product sumcheck round evaluations on the 5th-gen tensor cores.
+// roundevals_tc.cuh -- sumcheck round evaluations (inner products over GF(2^128)) on the 5th-gen tensor cores.
 //
 //   y = sum_i a_i * b_i  over GF(2^128)  is bilinear over GF(2):
 //       sum_i a_i*b_i = sum_{p,q} parity(G[p][q]) * beta_p*beta_q ,   G[p][q] = sum_i bit_p(a_i) & bit_q(b_i)
@@ -94,23 +94,27 @@ __device__ __forceinline__ void unpack_store(uint8_t *row, uint32_t sw16, uint4 
 	}
 }
 
+// One inner-product job:  S = sum_{i < len} (a0[i] ^ a1[i]) * (b0[i] ^ b1[i])   (a1 / b1 may be null).
+//   bivariate round evals: y_1 job = (a+half, -, b+half, -),  y_inf job = (a+half, a, b+half, b)
+//   eq-ind round evals   : (E, -, val_{c,p}, -)
+struct TcJob {
+	const uint4 *a0, *a1, *b0, *b1;
+};
 struct TcArgs {
-	const uint4 *const *mls;
-	const uint32_t *ia, *ib;
-	uint64_t half;
-	uint32_t *gmat;  // [n_comp][2][128][4] words, zero-initialised: XOR of the parity matrices of all CTAs
+	const TcJob *jobs;  // 2 * gridDim.y jobs (padded with a copy of the last job when the count is odd)
+	uint64_t len;       // points per job, a multiple of CHUNK
+	uint32_t *gmat;     // [2 * gridDim.y][128][4] words, zero-initialised: XOR of the parity matrices of all CTAs
 };
 
-// grid = (ctas_per_composition, n_comp), block = 288 (8 producer warps + 1 MMA warp), dyn smem = NSTAGE * STAGE_BYTES
-__global__ void __launch_bounds__(THREADS) k_bivariate_tc(const TcArgs A) {
+// grid = (ctas_per_job_pair, n_job_pairs), block = 288 (8 producer warps + 1 MMA warp), dyn smem = NSTAGE * STAGE_BYTES + 1024
+__global__ void __launch_bounds__(THREADS) k_pair_tc(const TcArgs A) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms are 1 KiB aligned
 	__shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE], done_bar;
 	__shared__ uint32_t tmem_base_s;
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t c = blockIdx.y;
-	const uint4 *a = A.mls[A.ia[c]], *b = A.mls[A.ib[c]];
-	const uint64_t half = A.half;
+	const uint32_t c = blockIdx.y;  // job pair
+	const uint64_t half = A.len;
 
 	if (warp == 0) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
@@ -132,24 +136,24 @@ __global__ void __launch_bounds__(THREADS) k_bivariate_tc(const TcArgs A) {
 	const uint64_t n_chunks = (half + CHUNK - 1) / CHUNK;
 	const uint32_t my_chunks = blockIdx.x < n_chunks ? (uint32_t)((n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 	if (warp < PRODUCERS / 32) {
-		// ---- producers: thread -> (operand, point): 0 = a_hi, 1 = b_hi, 2 = a_inf = a_lo + a_hi, 3 = b_inf
+		// ---- producers: thread -> (operand tile, point): tiles 0/1 = A/B of job 2c, tiles 2/3 = A/B of job 2c+1
 		const uint32_t op = tid >> 6, pt = tid & 63;
-		const bool need_lo = op >= 2;
-		// pointers walk the multilinear by gridDim.x chunks per iteration; the tail chunk is zero-padded
-		const uint4 *p_lo = ((op & 1) ? b : a) + (uint64_t)blockIdx.x * CHUNK + pt;
-		const uint64_t step = (uint64_t)gridDim.x * CHUNK;
-		// half is a multiple of CHUNK (checked by the host), so every chunk is full: loads are
-		// unconditional and land directly in their ring slot (no select / move on the loaded value,
-		// which would stall on the load right after issuing it)
+		// operand of this thread: job 2c + (op >> 1), side A (op even) or B (op odd)
+		const TcJob J = A.jobs[2 * c + (op >> 1)];
+		const uint4 *q0 = (op & 1) ? J.b0 : J.a0, *q1 = (op & 1) ? J.b1 : J.a1;
+		const bool need_lo = q1 != nullptr;
+		if (!need_lo) q1 = q0;  // read the same line twice (L1 hit); selected away below
 		// Loads are UNCONDITIONAL and land directly in their ring slot: a predicated load makes ptxas
 		// load into temporaries and move them right away, which stalls every iteration for a full
-		// memory latency.  Iterations past the end re-read the last valid chunk (clamped pointer).
-		const uint4 *p_last = ((op & 1) ? b : a) + (n_chunks - 1) * CHUNK + pt;
+		// memory latency.  len is a multiple of CHUNK (checked by the host); iterations past the end
+		// re-read the last valid chunk (clamped offset).
+		uint64_t off = (uint64_t)blockIdx.x * CHUNK + pt;
+		const uint64_t off_last = (n_chunks - 1) * CHUNK + pt, step = (uint64_t)gridDim.x * CHUNK;
 		auto load = [&](uint4 &xh, uint4 &xl) {
-			const uint4 *p = p_lo < p_last ? p_lo : p_last;
-			xh = __ldg(p + half);
-			xl = __ldg(need_lo ? p : p + half);  // operands 0/1 read the same line twice (L1 hit) and cancel below
-			p_lo += step;
+			const uint64_t o = off < off_last ? off : off_last;
+			xh = __ldg(q0 + o);
+			xl = __ldg(q1 + o);
+			off += step;
 		};
 		// register ring of raw loads, one slot per pipeline stage (slot u <-> stage u): the HBM latency
 		// spans several stages, and stage / ring indices stay compile-time constants
@@ -236,16 +240,22 @@ __global__ void __launch_bounds__(THREADS) k_bivariate_tc(const TcArgs A) {
 	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
-// G (position-permuted parity matrices) -> field: slot_y1 ^= sum_c alpha^c S_c(acc 0), slot_yinf likewise.
-// grid = n_comp, block = 256 (threads 0..127: acc 0, 128..255: acc 1), dyn smem = FIELD_TABLE_BYTES
-__global__ void __launch_bounds__(256) k_bivariate_tc_combine(const uint8_t *__restrict__ g_tables, const uint32_t *__restrict__ gmat,
-																const uint4 *__restrict__ pows, uint4 *__restrict__ slot_y1,
-																uint4 *__restrict__ slot_yinf) {
+// G (position-permuted parity matrices) -> field.  One block per TARGET t = (job, slot, coef):
+//   slots[slot_t] ^= coef_t * S_{job_t},   S_j = sum_m beta_{rho(m)} * (row m of G_j read as a field element)
+// (a job may feed several targets: a shared inner product used by several compositions).
+// grid = n_targets, block = 128, dyn smem = FIELD_TABLE_BYTES
+struct TcTarget {
+	uint32_t job, slot;
+	uint4 coef;
+};
+__global__ void __launch_bounds__(128) k_pair_tc_combine(const uint8_t *__restrict__ g_tables, const uint32_t *__restrict__ gmat,
+														   const TcTarget *__restrict__ targets, uint4 *__restrict__ slots) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	FieldTables T = load_field_tables(smem, g_tables);
 	__shared__ uint4 red[32];
-	const uint32_t c = blockIdx.x, acc = threadIdx.x >> 7, m = threadIdx.x & 127;
-	const uint32_t *row = gmat + ((size_t)c * 2 + acc) * 512 + m * 4;
+	const TcTarget tg = targets[blockIdx.x];
+	const uint32_t j = tg.job, m = threadIdx.x;
+	const uint32_t *row = gmat + (size_t)j * 512 + m * 4;
 	// row value: bit rho(pb) set iff G'[m][pb]
 	uint32_t v[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -259,14 +269,11 @@ __global__ void __launch_bounds__(256) k_bivariate_tc_combine(const uint8_t *__r
 		}
 	}
 	uint4 term = basis_image(make_uint4(v[0], v[1], v[2], v[3]), rho(m));  // beta_{rho(m)} * row
-	// reduce the two halves of the block separately
-	uint4 t0 = acc == 0 ? term : u4_zero(), t1 = acc == 1 ? term : u4_zero();
-	t0 = block_xor(t0, red);
-	t1 = block_xor(t1, red);
-	if (threadIdx.x == 0) {
-		uint4 p = pows[c];
-		if (!is_zero(t0)) atomic_xor_u4(slot_y1, f_mul128(T, t0, p));
-		if (!is_zero(t1)) atomic_xor_u4(slot_yinf, f_mul128(T, t1, p));
+	term = block_xor(term, red);
+	if (threadIdx.x == 0 && !is_zero(term)) {
+		uint4 cf = tg.coef;
+		bool one = cf.x == 1 && (cf.y | cf.z | cf.w) == 0;
+		atomic_xor_u4(slots + tg.slot, one ? term : f_mul128(T, term, cf));
 	}
 }
 

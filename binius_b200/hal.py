@@ -37,6 +37,10 @@ class EqIndEvaluator:
     have_first_round_eval_1s: bool = False
 
     def degree(self) -> int:
+        cached = getattr(self.composition, "_degree", None)
+        if cached is not None:
+            return cached
+
         def deg(c, step):
             st = c.steps[step]
             if st[0] == "const":
@@ -49,7 +53,9 @@ class EqIndEvaluator:
                 return deg(c, st[1]) + deg(c, st[2])
             return deg(c, st[1]) * st[2]
 
-        return deg(self.composition, len(self.composition.steps) - 1)
+        d = deg(self.composition, len(self.composition.steps) - 1)
+        self.composition._degree = d
+        return d
 
     def eval_point_indices(self) -> range:
         # eq_ind.rs:667-671: skip r(1) in the first round when known; never evaluate at 0
@@ -64,9 +70,13 @@ class B200Backend:
         self._exprs = {}
 
     def _compiled(self, circuit: ArithCircuit) -> ExprEval:
+        hit = getattr(circuit, "_b200_compiled", None)
+        if hit is not None and hit[0] is self:
+            return hit[1]
         key = tuple(circuit.steps)
         if key not in self._exprs:
             self._exprs[key] = (self._l.compile_expr(circuit), self._l.compile_expr(circuit.leading_term()))
+        circuit._b200_compiled = (self, self._exprs[key])
         return self._exprs[key]
 
     # -- backend.rs:42-45

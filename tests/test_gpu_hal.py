@@ -43,7 +43,7 @@ def test_tensor_product_full_query(hal, oracle):
         assert _same(hal.to_host(out), exp)
 
 
-@pytest.mark.parametrize("n_vars", [1, 5, 11])
+@pytest.mark.parametrize("n_vars", [1, 5, 11, 14])
 def test_zerocheck_rounds_match_oracle(hal, oracle, n_vars):
     """All rounds of an eq-ind sumcheck: round evals (at 1 and infinity, plus an extra finite domain
     point for the degree-3 variant), fold of every multilinear, halving of the eq-ind table."""
@@ -80,6 +80,42 @@ def test_zerocheck_rounds_match_oracle(hal, oracle, n_vars):
             eq_h = oracle.fold_partial_eq_ind(eq_h)
             assert _same(hal.to_host(eq_d), eq_h)
     assert all(m.evals.len() == 1 for m in mls)
+
+
+def test_zerocheck_degree2_monomial_plan(hal, oracle):
+    """Degree <= 2 compositions at the points 1 / infinity on large rounds take the monomial plan
+    (shared tensor-core inner products, eqind_plan.hpp); smaller rounds fall back to the interpreter.
+    Covers shared variables, a square, a constant term, a scaled monomial and an identically-zero
+    composition (x*y + y*x); shape = keccak chi constraints (m3/src/gadgets/hash/keccak/stacked.rs)."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
+
+    be = B200Backend(hal)
+    n_vars, m = 14, 9
+    rng = random.Random(77)
+    v = [A.var(i) for i in range(m)]
+    comps = [v[c] - (v[4 + c % 5] + (v[4 + (c + 1) % 5] - A.one()) * v[4 + (c + 2) % 5]) for c in range(4)]
+    comps += u32_add_compositions()
+    comps += [v[3] * v[3] + A.constant(rng.getrandbits(128)) * v[2] * v[8] + A.constant(rng.getrandbits(128)),
+              v[0] * v[1] + v[1] * v[0], v[5].pow(2) + v[6]]
+    mls_h = [oracle.rand_b128(500 + t, 1 << n_vars) for t in range(m)]
+    eq_pt = [rng.getrandbits(128) for _ in range(n_vars - 1)]
+    eq_d = be.tensor_product_full_query(eq_pt)
+    eq_h = hal.to_host(eq_d)
+    mls = [FoldedMultilinear(hal.to_device(x), 0) for x in mls_h]
+    for rnd in range(4):
+        nv = n_vars - rnd
+        evs = [EqIndEvaluator(c, have_first_round_eval_1s=(rnd == 0)) for c in comps]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, eq_d, [])
+        exp = oracle.eq_ind_round_evals(mls_h, [len(x) for x in mls_h], [0] * m, nv, eq_h, [c.steps for c in comps],
+                                        [c.leading_term().steps for c in comps], [1, 2], [0, 0])
+        for ev, g, e in zip(evs, got, exp):
+            assert g == [e[k - 1] for k in ev.eval_point_indices()]
+        ch = rng.getrandbits(128)
+        be.sumcheck_fold_multilinears(nv, mls, ch)
+        mls_h = [oracle.fold_left_lerp_inplace(x, len(x), 0, nv, ch) for x in mls_h]
+        eq_d = be.fold_partial_eq_ind(nv - 1, eq_d)
+        eq_h = oracle.fold_partial_eq_ind(eq_h)
 
 
 def test_truncated_multilinears_with_const_suffix(hal, oracle):
