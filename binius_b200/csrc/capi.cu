@@ -12,6 +12,7 @@
 #include "eqind_plan.hpp"
 #include "host_field.hpp"
 #include "kernels.cuh"
+#include "fold_tma.cuh"
 #include "ntt.cuh"
 #include "ntt_bs.cuh"
 #include "roundevals_tc.cuh"
@@ -478,12 +479,13 @@ int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uin
 
 // -------------------------------------------------------------------------------------------------
 }  // extern "C"
-template <uint32_t THREADS, uint32_t UNR, int MINB>
+template <uint32_t THREADS, uint32_t UNR, int MINB, bool PAIRS = false, bool K64 = true>
 static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
 	constexpr uint32_t TILE = THREADS * UNR;
 	static bool attr_set = false;
+	auto kernel = PAIRS ? k_lerp_pairs_lut<THREADS, UNR, MINB, K64> : k_lerp_lut<THREADS, UNR, MINB, K64>;
 	if (!attr_set) {
-		B200_CUDA(ctx, cudaFuncSetAttribute(k_lerp_lut<THREADS, UNR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LUT_BYTES + 2048)));
+		B200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LUT_BYTES + 2048)));
 		attr_set = true;
 	}
 	// segments travel by value in the kernel parameters: no staging copy, one launch per <= 48 segments
@@ -499,10 +501,44 @@ static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &li
 		A.n_tiles = tiles;
 		A.z = to_u4(z);
 		uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * MINB);
-		k_lerp_lut<THREADS, UNR, MINB><<<grid, THREADS, LUT_BYTES + 2048, ctx->stream>>>(A);
+		kernel<<<grid, THREADS, LUT_BYTES + 2048, ctx->stream>>>(A);
 		B200_LAUNCH_CHECK(ctx);
 	}
 	return B200_OK;
+}
+
+// TMA-staged persistent kernel (fold_tma.cuh): tiles of FT_TILE outputs, one CTA per SM
+template <bool PAIRS>
+static int32_t launch_lerp_tma(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
+	static bool attr_set = false;
+	if (!attr_set) {
+		B200_CUDA(ctx, cudaFuncSetAttribute(k_lerp_tma<PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+		attr_set = true;
+	}
+	for (size_t s0 = 0; s0 < live.size(); s0 += LERP_MAX_SEGS) {
+		LerpArgs A;
+		A.n_segs = (uint32_t)std::min<size_t>(LERP_MAX_SEGS, live.size() - s0);
+		uint64_t tiles = 0;
+		for (uint32_t i = 0; i < A.n_segs; i++) {
+			A.segs[i] = live[s0 + i];
+			A.segs[i].tile_start = tiles;
+			tiles += (A.segs[i].upper + FT_TILE - 1) / FT_TILE;
+		}
+		A.n_tiles = tiles;
+		A.z = to_u4(z);
+		uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + FT_WARPS - 1) / FT_WARPS, (uint64_t)ctx->n_sms);
+		k_lerp_tma<PAIRS><<<grid, FT_THREADS, FT_SMEM, ctx->stream>>>(A);
+		B200_LAUNCH_CHECK(ctx);
+	}
+	return B200_OK;
+}
+static int fold_engine() {
+	// B200_FOLD_ENGINE = tma (default) | k64 | lut128 : A/B runs of the three fold kernels
+	static const int engine = [] {
+		const char *e = getenv("B200_FOLD_ENGINE");
+		return !e ? 2 : !strcmp(e, "lut128") ? 0 : !strcmp(e, "k64") ? 1 : 2;
+	}();
+	return engine;
 }
 
 extern "C" {
@@ -513,8 +549,12 @@ static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint
 			live.push_back(s);
 		}
 	if (live.empty()) return B200_OK;
-	// 512 threads x 2 elements in flight, 2 CTAs per SM (64 registers): best of the measured variants
-	return launch_lerp_variant<512, 2, 2>(ctx, live, z);
+	// 512 threads x 2 elements in flight, 2 CTAs per SM (64 registers): best of the measured variants.
+	// B200_FOLD_ENGINE=lut128 selects the 16 x LDS.128 engine instead of the Karatsuba-64 one (A/B runs).
+	const int engine = fold_engine();
+	if (engine == 0) return launch_lerp_variant<512, 2, 2, false, false>(ctx, live, z);
+	if (engine == 1) return launch_lerp_variant<512, 2, 2, false, true>(ctx, live, z);
+	return launch_lerp_tma<false>(ctx, live, z);
 }
 
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_dev_ptr e1, uint64_t n1, const uint64_t z[2]) {
@@ -616,6 +656,27 @@ int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *ml
 		if (new_lens) new_lens[t] = upper;
 	}
 	return launch_lerp(ctx, segs, z);
+}
+
+int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *mls, const b200_dev_ptr *outs, uint32_t m, uint32_t n_vars,
+										   const uint64_t *prefix, const uint64_t *suffix, const uint64_t z[2], uint64_t *new_lens) {
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
+	std::vector<LerpSeg> live;
+	for (uint32_t t = 0; t < m; t++) {
+		uint64_t p = prefix[t];
+		if (p > (1ull << n_vars)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: prefix %llu exceeds 2^n_vars", t, (unsigned long long)p);
+		uint64_t upper = (p + 1) / 2;
+		const uint8_t *in = (const uint8_t *)mls[t], *out = (const uint8_t *)outs[t];
+		// fold_right_lerp is out of place (sumcheck_folding.rs:121-143); an overlap would race
+		if (upper && in < out + upper * 16 && out < in + p * 16) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: output overlaps the input", t);
+		if (new_lens) new_lens[t] = upper;
+		if (upper) live.push_back(LerpSeg{(uint4 *)outs[t], (const uint4 *)mls[t], p / 2, upper, to_u4(suffix + 2 * t), 0});
+	}
+	if (live.empty()) return B200_OK;
+	if (fold_engine() != 2) return launch_lerp_variant<512, 2, 2, true>(ctx, live, z);
+	return launch_lerp_tma<true>(ctx, live, z);
 }
 
 int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, uint32_t log_n, const uint64_t *coords, uint32_t k) {
@@ -860,9 +921,15 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 }
 
 int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint64_t *lens, const uint64_t *suffix_evals, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
+	if (ctx && !eq_ind) return fail(ctx, B200_ERR_INPUT_VALIDATION, "eq_ind_partial_evals is required by the eq-ind evaluator");
+	return b200_sumcheck_round_evals(ctx, B200_HIGH_TO_LOW, mls, lens, suffix_evals, m, n_vars, eq_ind, comps, leads, n_comp, codes, points, n_points, first_slot);
+}
+
+int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_ptr *mls, const uint64_t *lens, const uint64_t *suffix_evals, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
 	B200_FLUSH(ctx);
 	if (!ctx || !first_slot) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
+	if (order != B200_LOW_TO_HIGH && order != B200_HIGH_TO_LOW) return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown evaluation order %u", order);
 	if ((uint64_t)n_comp * n_points > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many (composition, point) pairs");
 	for (uint32_t c = 0; c < n_comp; c++)
 		if (!comps[c] || !leads[c] || comps[c]->n_vars > m || leads[c]->n_vars > m) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition %u does not match the multilinears", c);
@@ -891,7 +958,7 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const ui
 	}
 	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
 	const uint64_t half = 1ull << (n_vars - 1);
-	if (tc_mode >= 1 && tc_mode != 2 && half >= 4096 && half % tc::CHUNK == 0) {
+	if (tc_mode >= 1 && tc_mode != 2 && half >= 4096 && half % tc::CHUNK == 0 && eq_ind && order == B200_HIGH_TO_LOW) {
 		// points 1 / infinity only, full-length multilinears, degree <= 2: monomial plan, no interpreter
 		bool ok = true;
 		for (uint32_t t = 0; t < m && ok; t++) ok = hlen[t] == 2 * half;
@@ -919,10 +986,11 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const ui
 	A.points = (const uint4 *)(dbase + o_p);
 	A.n_points = n_points;
 	A.slots = ctx->d_results + *first_slot;
+	A.low_to_high = order == B200_LOW_TO_HIGH;
 	uint32_t gx = grid_for(ctx, A.half, 256, 2);
 	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::min(total, (uint32_t)ctx->n_sms * 4) + 1)));
 	const uint64_t vals_bytes = (uint64_t)total * A.half * 16;
-	if (tc_mode && A.half >= 4096 && A.half % tc::CHUNK == 0 && vals_bytes <= (48ull << 30)) {
+	if (tc_mode && eq_ind && A.half >= 4096 && A.half % tc::CHUNK == 0 && vals_bytes <= (48ull << 30)) {
 		// materialise C(P(i)), then sum_i E[i] * val[i] as tensor-core inner-product jobs
 		const uint64_t gmat_bytes = (uint64_t)(total + 1) * 512 * 4;
 		if ((rc = ensure_scratch(ctx, vals_bytes + gmat_bytes))) return rc;

@@ -33,14 +33,32 @@ constexpr uint32_t FOLD_THREADS = 512;
 constexpr uint32_t FOLD_UNROLL = 2;
 constexpr uint32_t FOLD_TILE = FOLD_THREADS * FOLD_UNROLL;
 
+// The two constant-multiplication engines of linmap.cuh behind one interface
+template <bool K64> struct MulEngine;
+template <> struct MulEngine<false> {
+	LutLane L;
+	const uint8_t *tbl;
+	__device__ __forceinline__ MulEngine(uint8_t *smem, uint4 z) : tbl(smem) {
+		lut_build_mul(smem, reinterpret_cast<uint4 *>(smem + LUT_BYTES), z);
+		L = lut_lane_init();
+	}
+	__device__ __forceinline__ uint4 mul(uint4 x) const { return lut_apply(tbl, L, x); }
+};
+template <> struct MulEngine<true> {
+	K64Lane L;
+	const uint8_t *tbl;
+	__device__ __forceinline__ MulEngine(uint8_t *smem, uint4 z) : tbl(smem) {
+		k64_build_mul(smem, reinterpret_cast<uint2 *>(smem + LUT_BYTES), z);
+		L = k64_lane_init(smem);
+	}
+	__device__ __forceinline__ uint4 mul(uint4 x) const { return k64_apply(L, x); }
+};
+
 // THREADS x UNR elements per tile; host must compute tile_start with the same tile size
-template <uint32_t THREADS, uint32_t UNR, int MINB>
+template <uint32_t THREADS, uint32_t UNR, int MINB, bool K64>
 __global__ void __launch_bounds__(THREADS, MINB) k_lerp_lut(const __grid_constant__ LerpArgs A) {
-	extern __shared__ __align__(128) uint8_t smem[];
-	uint8_t *tbl = smem;
-	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
-	lut_build_mul(tbl, stage, A.z);
-	const LutLane L = lut_lane_init();
+	extern __shared__ __align__(256) uint8_t smem[];
+	const MulEngine<K64> E(smem, A.z);
 	constexpr uint32_t TILE = THREADS * UNR;
 
 	uint32_t seg = 0;
@@ -63,7 +81,41 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lerp_lut(const __grid_constan
 #pragma unroll
 		for (uint32_t u = 0; u < UNR; u++) {
 			uint64_t i = base + (uint64_t)u * THREADS;
-			if (i < upper) e0[i] = a[u] ^ lut_apply(tbl, L, a[u] ^ b[u]);
+			if (i < upper) e0[i] = a[u] ^ E.mul(a[u] ^ b[u]);
+		}
+	}
+}
+
+// LowToHigh fold (fold_right_lerp, math/src/fold.rs:528-575, as driven by hal/src/sumcheck_folding.rs:
+// 117-143): out[i] = in[2i] + (in[2i+1] - in[2i]) * z for i < pivot (= prefix / 2); the odd tail
+// element pairs with the constant suffix.  Same LerpArgs: e0 = out, e1 = in, upper = ceil(prefix / 2).
+template <uint32_t THREADS, uint32_t UNR, int MINB, bool K64>
+__global__ void __launch_bounds__(THREADS, MINB) k_lerp_pairs_lut(const __grid_constant__ LerpArgs A) {
+	extern __shared__ __align__(256) uint8_t smem[];
+	const MulEngine<K64> E(smem, A.z);
+	constexpr uint32_t TILE = THREADS * UNR;
+
+	uint32_t seg = 0;
+	for (uint64_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+		while (seg + 1 < A.n_segs && A.segs[seg + 1].tile_start <= tile) seg++;
+		const LerpSeg &S = A.segs[seg];
+		uint64_t base = (tile - S.tile_start) * TILE + threadIdx.x;
+		const uint64_t upper = S.upper, pivot = S.pivot;
+		uint4 *out = S.e0;
+		const uint4 *in = S.e1;
+		uint4 a[UNR], b[UNR];
+#pragma unroll
+		for (uint32_t u = 0; u < UNR; u++) {
+			uint64_t i = base + (uint64_t)u * THREADS;
+			if (i < upper) {
+				a[u] = __ldg(in + 2 * i);
+				b[u] = i < pivot ? __ldg(in + 2 * i + 1) : S.suffix;
+			}
+		}
+#pragma unroll
+		for (uint32_t u = 0; u < UNR; u++) {
+			uint64_t i = base + (uint64_t)u * THREADS;
+			if (i < upper) out[i] = a[u] ^ E.mul(a[u] ^ b[u]);
 		}
 	}
 }
@@ -308,6 +360,7 @@ struct EqIndArgs {
 	const uint4 *points;        // [n_points]
 	uint32_t n_points;
 	uint4 *slots;  // [n_comp * n_points]
+	uint32_t low_to_high;  // 0: HighToLow pairs (i, half + i); 1: LowToHigh pairs (2i, 2i + 1)
 };
 constexpr uint32_t MAX_EQIND_MLS = 24;  // per-thread operand staging for the general-point path
 
@@ -325,10 +378,12 @@ __device__ __forceinline__ uint4 eq_ind_eval_point(const FieldTables &T, const E
 		default: {
 			const uint4 *m = A.mls[st.l];
 			const uint64_t len = A.lens[st.l];
-			uint4 hi = A.half + i < len ? __ldg(m + A.half + i) : A.suffix[st.l];
+			// HighToLowAccess / LowToHighAccess (sumcheck_round_calculation.rs:408-604)
+			const uint64_t i_lo = A.low_to_high ? 2 * i : i, i_hi = A.low_to_high ? 2 * i + 1 : A.half + i;
+			uint4 hi = i_hi < len ? __ldg(m + i_hi) : A.suffix[st.l];
 			if (code == 1) v = hi;
 			else {
-				uint4 lo = i < len ? __ldg(m + i) : A.suffix[st.l];
+				uint4 lo = i_lo < len ? __ldg(m + i_lo) : A.suffix[st.l];
 				uint4 d = hi ^ lo;
 				v = code == 2 ? d : (lo ^ f_mul128(T, d, z));
 			}
@@ -348,8 +403,11 @@ __global__ void __launch_bounds__(256) k_eq_ind_round_evals(const uint8_t *__res
 	const DevExpr E = code == 2 ? A.comps_lead[c] : A.comps[c];
 	uint4 z = A.points[p];
 	uint4 acc = u4_zero();
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.half; i += (uint64_t)gridDim.x * blockDim.x)
-		acc ^= f_mul128(T, eq_ind_eval_point(T, A, E, code, z, i), __ldg(A.eq_ind + i));
+	// eq_ind == nullptr: the regular (unweighted) evaluator, prove/regular_sumcheck.rs:233-277
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.half; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 v = eq_ind_eval_point(T, A, E, code, z, i);
+		acc ^= A.eq_ind ? f_mul128(T, v, __ldg(A.eq_ind + i)) : v;
+	}
 	acc = block_xor(acc, red);
 	if (threadIdx.x == 0) atomic_xor_u4(A.slots + blockIdx.y, acc);
 }

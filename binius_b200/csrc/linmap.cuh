@@ -180,4 +180,115 @@ __device__ __forceinline__ uint4 nlut_apply(const uint8_t *tbl, const NLutLane &
 	return a0 ^ a1;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Karatsuba-over-GF(2^64) variant of the byte-LUT engine ("K64").  With x = x0 + x1*X_6 and
+// z = z0 + z1*X_6  (X_6^2 = X_6*X_5 + 1, pairwise_recursive_arithmetic.rs:12-30)
+//     x*z = (z0 x0 + z1 x1) + (z1 x0 + (z0 + X_5 z1) x1) * X_6
+// is a symmetric 2x2 matrix [[c0, c1], [c1, c2]] over GF(2^64) applied to (x0, x1), which needs only
+// three products BY CONSTANTS and no post-multiplication:
+//     P = c1 (x0 + x1),   lo = (c0 + c1) x0 + P,   hi = (c1 + c2) x1 + P.
+// 3 x 8 byte-lookups of 8 bytes = 192 bytes of shared-memory reads per product instead of 16 x 16 = 256.
+//
+// Table layout (64 KiB): row b (256 B) = [ A_0..7[b] | B_0..7[b] | M_0..7[b] | M_0..7[b] ] with 8-byte
+// entries; A = (.)*(c0+c1) on the bytes of x0, B = (.)*(c1+c2) on the bytes of x1, M = (.)*c1 on x0+x1.
+// An LDS.64 is served per half-warp (16 lanes x 8 B = all 32 banks).  Lane (g, j) = ((lane>>3)&1,
+// lane&7) walks byte positions k = s ^ j; lanes with g = 0 read A then B then M(copy 0), lanes with
+// g = 1 read B then A then M(copy 1), so the 16 lanes of a half-warp always hit 16 distinct 8-byte
+// bank pairs: conflict-free by construction.  Byte extraction and address formation are ONE PRMT:
+// address = (byte << 8) | lane_offset with the offsets of four steps packed in a register.
+struct K64Lane {
+	uint32_t selP;      // PRMT selector: own operand's word (g) with bytes XOR-permuted by (j & 3)
+	uint32_t selQ;      // same for the other operand
+	uint32_t swap;      // swap the two words of each 64-bit half (j >> 2)
+	uint32_t g;         // 0: own half is x0, 1: own half is x1
+	uint32_t offP[2];   // byte s&3 of offP[s>>2] = g*64 + (s^j)*8       (own table set)
+	uint32_t offQ[2];   //                         (1-g)*64 + (s^j)*8   (the other table set)
+	uint32_t sbase;     // shared-window address of the table
+};
+__device__ __forceinline__ K64Lane k64_lane_init(const uint8_t *tbl) {
+	K64Lane L;
+	const uint32_t j = threadIdx.x & 7;
+	L.g = (threadIdx.x >> 3) & 1u;
+	const uint32_t perm = (j & 3u) * 0x1111u;
+	L.selP = (L.g ? 0x7654u : 0x3210u) ^ perm;
+	L.selQ = (L.g ? 0x3210u : 0x7654u) ^ perm;
+	L.swap = (j >> 2) & 1u;
+#pragma unroll
+	for (uint32_t h = 0; h < 2; h++) {
+		uint32_t p = 0, q = 0;
+#pragma unroll
+		for (uint32_t t = 0; t < 4; t++) {
+			const uint32_t k = (4 * h + t) ^ j;
+			p |= (L.g * 64u + k * 8u) << (8 * t);
+			q |= ((1u - L.g) * 64u + k * 8u) << (8 * t);
+		}
+		L.offP[h] = p;
+		L.offQ[h] = q;
+	}
+	L.sbase = (uint32_t)__cvta_generic_to_shared(tbl);
+	return L;
+}
+
+// Build the table of x -> x*z.  stage: 3 * 64 uint2 (1.5 KiB).  All threads of the CTA must call.
+__device__ __forceinline__ void k64_build_mul(uint8_t *tbl, uint2 *stage, uint4 z) {
+	for (uint32_t e = threadIdx.x; e < 192; e += blockDim.x) {
+		const uint32_t set = e >> 6, i = e & 63;
+		// c0 = z0, c1 = z1, c2 = z0 + X_5*z1;  A: c0+c1, B: c1+c2 = z0 + z1 + X_5*z1, M: c1
+		const uint4 z1 = make_uint4(z.z, z.w, 0, 0);
+		const uint4 az1 = mul_tower_gen(z1, 5);
+		uint4 c = set == 0 ? make_uint4(z.x ^ z.z, z.y ^ z.w, 0, 0) : set == 1 ? make_uint4(z.x ^ z.z ^ az1.x, z.y ^ z.w ^ az1.y, 0, 0) : z1;
+		uint4 im = basis_image(c, i);  // i < 64: stays inside the low GF(2^64) half
+		stage[e] = make_uint2(im.x, im.y);
+	}
+	__syncthreads();
+	for (uint32_t e = threadIdx.x; e < 3 * 2048; e += blockDim.x) {
+		const uint32_t k = e & 7, set = (e >> 3) % 3, b = e / 24;
+		uint2 acc = make_uint2(0, 0);
+#pragma unroll
+		for (uint32_t i = 0; i < 8; i++) {
+			const uint32_t m = 0u - ((b >> i) & 1u);
+			const uint2 w = stage[set * 64 + 8 * k + i];
+			acc.x ^= w.x & m;
+			acc.y ^= w.y & m;
+		}
+		uint2 *row = reinterpret_cast<uint2 *>(tbl + b * 256u);
+		row[set * 8 + k] = acc;
+		if (set == 2) row[24 + k] = acc;
+	}
+	__syncthreads();
+}
+
+template <uint32_t S, uint32_t IMM> __device__ __forceinline__ uint2 k64_ld(uint32_t sbase, uint32_t w, uint32_t off) {
+	constexpr uint32_t t = S & 3u;
+	constexpr uint32_t sel = ((0xCu + t) << 12) | ((0xCu + t) << 8) | (t << 4) | (4u + t);
+	// (byte t of w) << 8 | (byte t of off); bytes 2-3 = replicated msb of the offset byte (< 128) = 0.
+	// Inline PTX: __byte_perm masks the selector to 3 bits per nibble and drops the msb-replicate flag.
+	uint32_t addr;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(addr) : "r"(w), "r"(off), "n"(sel));
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr + sbase), "n"(IMM));
+	return v;
+}
+// 8 lookups of one 64-bit operand (w0, w1 already lane-permuted)
+template <uint32_t IMM> __device__ __forceinline__ uint2 k64_set(uint32_t sbase, uint32_t w0, uint32_t w1, const uint32_t (&off)[2]) {
+	uint2 a = k64_ld<0, IMM>(sbase, w0, off[0]), b = k64_ld<1, IMM>(sbase, w0, off[0]);
+	uint2 c = k64_ld<2, IMM>(sbase, w0, off[0]), d = k64_ld<3, IMM>(sbase, w0, off[0]);
+	uint2 e = k64_ld<4, IMM>(sbase, w1, off[1]), f = k64_ld<5, IMM>(sbase, w1, off[1]);
+	uint2 g = k64_ld<6, IMM>(sbase, w1, off[1]), h = k64_ld<7, IMM>(sbase, w1, off[1]);
+	return make_uint2((a.x ^ b.x ^ c.x) ^ (d.x ^ e.x ^ f.x) ^ (g.x ^ h.x), (a.y ^ b.y ^ c.y) ^ (d.y ^ e.y ^ f.y) ^ (g.y ^ h.y));
+}
+// y = x * z
+__device__ __forceinline__ uint4 k64_apply(const K64Lane &L, uint4 x) {
+	// word order by the lane's swap bit, then ONE PRMT per word picks own/other operand and permutes bytes
+	const uint32_t u0 = L.swap ? x.y : x.x, u1 = L.swap ? x.x : x.y, v0 = L.swap ? x.w : x.z, v1 = L.swap ? x.z : x.w;
+	const uint32_t a0 = __byte_perm(u0, v0, L.selP), a1 = __byte_perm(u1, v1, L.selP);
+	const uint32_t b0 = __byte_perm(u0, v0, L.selQ), b1 = __byte_perm(u1, v1, L.selQ);
+	const uint2 accP = k64_set<0>(L.sbase, a0, a1, L.offP);
+	const uint2 accQ = k64_set<0>(L.sbase, b0, b1, L.offQ);
+	const uint2 accM = k64_set<128>(L.sbase, a0 ^ b0, a1 ^ b1, L.offP);
+	const uint2 lo = L.g ? accQ : accP, hi = L.g ? accP : accQ;  // A(x0), B(x1)
+	return make_uint4(lo.x ^ accM.x, lo.y ^ accM.y, hi.x ^ accM.x, hi.y ^ accM.y);
+}
+
 }  // namespace b200

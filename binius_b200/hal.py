@@ -7,16 +7,23 @@ crates/hal/src/backend.rs:35-83) for device-resident multilinears, over the C AB
     evaluate_partial_high         backend.rs:78-82  -> math/src/multilinear_extension.rs:253-300
 
 The reference's trait is generic over packed fields, multilinear trait objects and evaluator trait
-objects; this backend covers what the prover's hot loop instantiates it with after the switchover:
-`SumcheckMultilinear::Folded` B128 multilinears (hal/src/sumcheck_multilinear.rs:8-40), `ArithCircuit`
-compositions, HighToLow evaluation order, and the eq-ind evaluator of
-core/src/protocols/sumcheck/prove/eq_ind.rs:646-731.
+objects; this backend covers what the prover instantiates it with: both `SumcheckMultilinear` variants
+(hal/src/sumcheck_multilinear.rs:8-40; `Transparent` = packed sub-field multilinear folded into B128 at
+its switchover round, `Folded` = B128 prefix + constant suffix), `ArithCircuit` compositions, both
+evaluation orders, the eq-ind evaluator of core/src/protocols/sumcheck/prove/eq_ind.rs:646-731 and the
+regular evaluator of prove/regular_sumcheck.rs:233-277.
+
+Transparent multilinears before their switchover round: the reference evaluates
+`subcube_partial_{high,low}_evals(tensor_query)` tile by tile on the fly to save host memory; here the
+same partial evaluation (fold_left / fold_right of the packed sub-field matrix by the query expansion)
+is written to device scratch for the round -- identical values, HBM is not the scarce resource.
 """
 from __future__ import annotations
 
 import ctypes as C
+import enum
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List, Optional, Sequence, Tuple, Union
 
 from .layer import (ArithCircuit, B200Layer, DevSlice, ExprEval, InputValidation, _u64_list, _u64x2)
 
@@ -30,6 +37,59 @@ class FoldedMultilinear:
 
 
 @dataclass
+class TransparentMultilinear:
+    """SumcheckMultilinear::Transparent { multilinear, switchover_round, const_suffix }: `evals` holds the
+    2^n_vars sub-field scalars (tower level `tower_level`, 2^(7-level) per B128 word, low limb first --
+    the MLEEmbeddingAdapter / SubfieldSlice layout, compute/src/memory.rs:257-281)."""
+    evals: DevSlice
+    tower_level: int
+    n_vars: int
+    switchover_round: int = 0
+    const_suffix: Tuple[int, int] = (0, 0)  # (suffix_eval, suffix_len) hint
+
+
+class EvaluationOrder(enum.IntEnum):
+    """binius_math::EvaluationOrder"""
+    LowToHigh = 0
+    HighToLow = 1
+
+
+def _degree(composition: ArithCircuit) -> int:
+    cached = getattr(composition, "_degree", None)
+    if cached is not None:
+        return cached
+
+    def deg(c, step):
+        st = c.steps[step]
+        if st[0] == "const":
+            return 0
+        if st[0] == "var":
+            return 1
+        if st[0] == "add":
+            return max(deg(c, st[1]), deg(c, st[2]))
+        if st[0] == "mul":
+            return deg(c, st[1]) + deg(c, st[2])
+        return deg(c, st[1]) * st[2]
+
+    d = deg(composition, len(composition.steps) - 1)
+    composition._degree = d
+    return d
+
+
+@dataclass
+class RegularSumcheckEvaluator:
+    """prove/regular_sumcheck.rs:221-277: plain sums of the composition, points 1..=degree
+    (r(0) is derived from the claimed sum); no eq-indicator weighting."""
+    composition: ArithCircuit
+
+    def degree(self) -> int:
+        return _degree(self.composition)
+
+    def eval_point_indices(self) -> range:
+        return range(1, self.degree() + 1)
+
+
+@dataclass
 class EqIndEvaluator:
     """The data of the eq-ind `Evaluator` (eq_ind.rs:646-662) that reaches the backend: the
     composition, and whether r(1) is already known (`have_first_round_eval_1s`)."""
@@ -37,25 +97,7 @@ class EqIndEvaluator:
     have_first_round_eval_1s: bool = False
 
     def degree(self) -> int:
-        cached = getattr(self.composition, "_degree", None)
-        if cached is not None:
-            return cached
-
-        def deg(c, step):
-            st = c.steps[step]
-            if st[0] == "const":
-                return 0
-            if st[0] == "var":
-                return 1
-            if st[0] == "add":
-                return max(deg(c, st[1]), deg(c, st[2]))
-            if st[0] == "mul":
-                return deg(c, st[1]) + deg(c, st[2])
-            return deg(c, st[1]) * st[2]
-
-        d = deg(self.composition, len(self.composition.steps) - 1)
-        self.composition._degree = d
-        return d
+        return _degree(self.composition)
 
     def eval_point_indices(self) -> range:
         # eq_ind.rs:667-671: skip r(1) in the first round when known; never evaluate at 0
@@ -68,6 +110,7 @@ class B200Backend:
     def __init__(self, layer: B200Layer):
         self._l = layer
         self._exprs = {}
+        self._unit = None
 
     def _compiled(self, circuit: ArithCircuit) -> ExprEval:
         hit = getattr(circuit, "_b200_compiled", None)
@@ -85,28 +128,67 @@ class B200Backend:
         self._l._check(self._l._lib.b200_tensor_product_full_query(self._l._ctx, _u64_list(query), len(query), out.ptr, out.len()))
         return out
 
+    def _one(self) -> DevSlice:
+        """the empty tensor query's expansion: a single 1 (MultilinearQuery::with_capacity(0))"""
+        if self._unit is None:
+            self._unit = self._l.dev_alloc(1)
+            self._l.fill(self._unit, 1)
+        return self._unit
+
+    def _partial_eval(self, order: EvaluationOrder, ml: TransparentMultilinear, tensor_query: Optional[DevSlice]) -> DevSlice:
+        """evaluate_partial_high / evaluate_partial_low of a packed sub-field multilinear by an expanded
+        tensor query (math/src/multilinear_extension.rs:253-341 -> fold_left / fold_right, fold.rs:88-179)."""
+        q = tensor_query if tensor_query is not None else self._one()
+        n_scalars = 1 << ml.n_vars
+        if q.len() == 0 or n_scalars % q.len():
+            raise InputValidation("tensor query does not divide the multilinear")
+        out = self._l.dev_alloc(n_scalars // q.len())
+        fn = self._l._lib.b200_fold_left if order == EvaluationOrder.HighToLow else self._l._lib.b200_fold_right
+        self._l._check(fn(self._l._ctx, ml.evals.ptr, ml.evals.len(), ml.tower_level, q.ptr, q.len(), out.ptr, out.len()))
+        return out
+
     # -- backend.rs:48-62
-    def sumcheck_compute_round_evals(self, n_vars: int, multilinears: Sequence[FoldedMultilinear],
-                                     evaluators: Sequence[EqIndEvaluator], eq_ind_partial_evals: DevSlice,
-                                     finite_evaluation_points: Sequence[int]) -> List[List[int]]:
+    def sumcheck_compute_round_evals(self, n_vars: int, multilinears: Sequence[Union[FoldedMultilinear, TransparentMultilinear]],
+                                     evaluators: Sequence[Union[EqIndEvaluator, RegularSumcheckEvaluator]],
+                                     eq_ind_partial_evals: Optional[DevSlice] = None,
+                                     finite_evaluation_points: Sequence[int] = (), *,
+                                     evaluation_order: EvaluationOrder = EvaluationOrder.HighToLow,
+                                     tensor_query: Optional[DevSlice] = None) -> List[List[int]]:
         """Returns RoundEvals per evaluator: the values at eval_point_indices() (1 = at 1, 2 = infinity,
-        k >= 3 = finite_evaluation_points[k-3]); sumcheck_round_calculation.rs:156-163 length check."""
+        k >= 3 = finite_evaluation_points[k-3]); sumcheck_round_calculation.rs:156-163 length check.
+        `eq_ind_partial_evals` is what Evaluator::eq_ind_partial_eval() returns (None for the regular
+        evaluator); `tensor_query` is the expansion of the challenges received so far, needed while any
+        multilinear is still Transparent."""
         if n_vars == 0:
             raise InputValidation("Computing round evaluations requires at least a single variable.")
         hi = max([ev.eval_point_indices().stop for ev in evaluators], default=0)
         if len(finite_evaluation_points) != max(hi - 3, 0):
             raise InputValidation("IncorrectNontrivialEvalPointsLength")
-        if eq_ind_partial_evals.len() != 1 << (n_vars - 1):
+        weighted = any(isinstance(ev, EqIndEvaluator) for ev in evaluators)
+        if weighted and not all(isinstance(ev, EqIndEvaluator) for ev in evaluators):
+            raise InputValidation("evaluators of one call must be of one kind")
+        if weighted and (eq_ind_partial_evals is None or eq_ind_partial_evals.len() != 1 << (n_vars - 1)):
             raise InputValidation("eq_ind_partial_evals must have 2^(n_vars-1) elements")
         lo = min([ev.eval_point_indices().start for ev in evaluators], default=1)
         codes = list(range(lo, hi))
         if not codes or not evaluators:
             return [[] for _ in evaluators]
         pts = [0 if c < 3 else finite_evaluation_points[c - 3] for c in codes]
-        m = len(multilinears)
-        ptrs = (C.c_void_p * max(m, 1))(*[ml.evals.ptr for ml in multilinears])
-        lens = (C.c_uint64 * max(m, 1))(*[ml.evals.len() for ml in multilinears])
-        sfx = _u64_list([ml.suffix_eval for ml in multilinears])
+        temps = []
+        views = []
+        for ml in multilinears:
+            if isinstance(ml, TransparentMultilinear):
+                d = self._partial_eval(evaluation_order, ml, tensor_query)
+                if d.len() != 1 << n_vars:
+                    raise InputValidation("transparent multilinear does not match n_vars and the tensor query")
+                temps.append(d)
+                views.append((d, ml.const_suffix[0] if ml.const_suffix[1] else 0))
+            else:
+                views.append((ml.evals, ml.suffix_eval))
+        m = len(views)
+        ptrs = (C.c_void_p * max(m, 1))(*[v[0].ptr for v in views])
+        lens = (C.c_uint64 * max(m, 1))(*[min(v[0].len(), 1 << n_vars) for v in views])
+        sfx = _u64_list([v[1] for v in views])
         compiled = [self._compiled(ev.composition) for ev in evaluators]
         comps = (C.c_void_p * len(evaluators))(*[c[0].handle.value for c in compiled])
         leads = (C.c_void_p * len(evaluators))(*[c[1].handle.value for c in compiled])
@@ -114,12 +196,15 @@ class B200Backend:
         first = C.c_uint32()
         L = self._l
         L._check(L._lib.b200_results_reset(L._ctx))
-        L._check(L._lib.b200_eq_ind_round_evals(L._ctx, ptrs, lens, sfx, m, n_vars, eq_ind_partial_evals.ptr, comps, leads,
-                                                len(evaluators), ccodes, _u64_list(pts), len(codes), C.byref(first)))
+        L._check(L._lib.b200_sumcheck_round_evals(L._ctx, int(evaluation_order), ptrs, lens, sfx, m, n_vars,
+                                                  eq_ind_partial_evals.ptr if weighted else None, comps, leads,
+                                                  len(evaluators), ccodes, _u64_list(pts), len(codes), C.byref(first)))
         total = len(evaluators) * len(codes)
         slots = (C.c_uint32 * total)(*range(first.value, first.value + total))
         out = (C.c_uint64 * (2 * total))()
-        L._check(L._lib.b200_results_fetch(L._ctx, slots, total, out))
+        L._check(L._lib.b200_results_fetch(L._ctx, slots, total, out))  # synchronises: temps may go
+        for d in temps:
+            L.dev_free(d)
         vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(total)]
         res = []
         for e, ev in enumerate(evaluators):
@@ -127,25 +212,59 @@ class B200Backend:
             res.append([vals[e * len(codes) + (k - lo)] for k in rng])
         return res
 
-    # -- backend.rs:65-75 (HighToLow, Folded branch): folds in place, truncates the handles
-    def sumcheck_fold_multilinears(self, n_vars: int, multilinears: List[FoldedMultilinear], challenge: int) -> bool:
-        m = len(multilinears)
-        if m == 0:
-            return False
-        ptrs = (C.c_void_p * m)(*[ml.evals.ptr for ml in multilinears])
-        prefix = (C.c_uint64 * m)(*[min(ml.evals.len(), 1 << n_vars) for ml in multilinears])
-        new_lens = (C.c_uint64 * m)()
+    # -- backend.rs:65-75: folds every multilinear by `challenge`; Folded ones by a single-variable lerp
+    #    (in place for HighToLow, into a fresh buffer for LowToHigh), Transparent ones are materialised by
+    #    `tensor_query` (which already includes `challenge`, prover_state.rs fold()) at their switchover
+    #    round.  Entries of `multilinears` are replaced/truncated; returns any_transparent_left.
+    def sumcheck_fold_multilinears(self, n_vars: int, multilinears: List[Union[FoldedMultilinear, TransparentMultilinear]],
+                                   challenge: int, tensor_query: Optional[DevSlice] = None, *,
+                                   evaluation_order: EvaluationOrder = EvaluationOrder.HighToLow) -> bool:
         L = self._l
-        L._check(L._lib.b200_fold_multilinears_high_to_low(L._ctx, ptrs, m, n_vars, prefix,
-                                                           _u64_list([ml.suffix_eval for ml in multilinears]), _u64x2(challenge), new_lens))
-        for ml, n in zip(multilinears, new_lens):
-            ml.evals = ml.evals.slice(0, int(n))
-        return False  # no transparent multilinears left (sumcheck_folding.rs:245-262)
+        any_transparent_left = False
+        folded_ix = []
+        for t, ml in enumerate(multilinears):
+            if isinstance(ml, TransparentMultilinear):
+                if ml.switchover_round == 0:
+                    if tensor_query is None:
+                        raise InputValidation("tensor_query is required while a multilinear is transparent")
+                    d = self._partial_eval(evaluation_order, ml, tensor_query)
+                    multilinears[t] = FoldedMultilinear(d, ml.const_suffix[0] if ml.const_suffix[1] else 0)
+                else:
+                    ml.switchover_round -= 1
+                    any_transparent_left = True
+            else:
+                folded_ix.append(t)
+        m = len(folded_ix)
+        if m == 0:
+            return any_transparent_left
+        mls = [multilinears[t] for t in folded_ix]
+        ptrs = (C.c_void_p * m)(*[ml.evals.ptr for ml in mls])
+        prefix = (C.c_uint64 * m)(*[min(ml.evals.len(), 1 << n_vars) for ml in mls])
+        new_lens = (C.c_uint64 * m)()
+        sfx = _u64_list([ml.suffix_eval for ml in mls])
+        if evaluation_order == EvaluationOrder.HighToLow:
+            L._check(L._lib.b200_fold_multilinears_high_to_low(L._ctx, ptrs, m, n_vars, prefix, sfx, _u64x2(challenge), new_lens))
+            for ml, n in zip(mls, new_lens):
+                ml.evals = ml.evals.slice(0, int(n))
+        else:
+            outs = [L.dev_alloc(max((int(p) + 1) // 2, 1)) for p in prefix]
+            optrs = (C.c_void_p * m)(*[o.ptr for o in outs])
+            L._check(L._lib.b200_fold_multilinears_low_to_high(L._ctx, ptrs, optrs, m, n_vars, prefix, sfx, _u64x2(challenge), new_lens))
+            for ml, o, n in zip(mls, outs, new_lens):
+                ml.evals = o.slice(0, int(n))
+        return any_transparent_left
 
     # -- prove/common.rs:13-73 fold_partial_eq_ind, HighToLow: E'[i] = E[i] + E[half + i]
-    def fold_partial_eq_ind(self, n_vars: int, eq_ind: DevSlice) -> DevSlice:
+    def fold_partial_eq_ind(self, n_vars: int, eq_ind: DevSlice, evaluation_order: EvaluationOrder = EvaluationOrder.HighToLow) -> DevSlice:
         if n_vars == 0:
             return eq_ind
+        if evaluation_order == EvaluationOrder.LowToHigh:
+            # E'[i] = E[2i] + E[2i+1] (common.rs:50-58) = fold_right of E by the all-ones pair
+            ones = self._l.dev_alloc(2)
+            self._l.fill(ones, 1)
+            out = self._l.dev_alloc(1 << (n_vars - 1))
+            self._l._check(self._l._lib.b200_fold_right(self._l._ctx, eq_ind.ptr, eq_ind.len(), 7, ones.ptr, 2, out.ptr, out.len()))
+            return out
         lo, hi = eq_ind.split_half()
         self._l._check(self._l._lib.b200_kernel_add(self._l._ctx, n_vars - 1, lo.ptr, hi.ptr, lo.ptr))
         return lo

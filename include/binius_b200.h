@@ -207,6 +207,30 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *multilins,
 								const uint32_t *point_codes, const uint64_t *domain_points /* 2*n_points */,
 								uint32_t n_points, uint32_t *first_slot);
 
+/* EvaluationOrder (crates/math/src/multilinear_query.rs / hal/src/sumcheck_folding.rs:16-35) */
+enum { B200_LOW_TO_HIGH = 0, B200_HIGH_TO_LOW = 1 };
+
+/* sumcheck_compute_round_evals in either evaluation order and for both evaluator kinds
+ * (hal/src/sumcheck_round_calculation.rs:126-349; LowToHighAccess :408-504 pairs (2i, 2i+1),
+ * HighToLowAccess :507-604 pairs (i, i + 2^(n-1))).  eq_ind != NULL: the eq-ind evaluator
+ * (core/.../prove/eq_ind.rs:646-731, sums weighted by eq_ind[i]); eq_ind == NULL: the regular evaluator
+ * (core/.../prove/regular_sumcheck.rs:233-277, plain sums).  Other arguments as b200_eq_ind_round_evals. */
+int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t evaluation_order, const b200_dev_ptr *multilins,
+								  const uint64_t *stored_lens, const uint64_t *suffix_evals, uint32_t n_multilins,
+								  uint32_t n_vars, b200_dev_ptr eq_ind /* 2^(n_vars-1) or NULL */,
+								  const b200_expr *const *compositions,
+								  const b200_expr *const *compositions_leading, uint32_t n_compositions,
+								  const uint32_t *point_codes, const uint64_t *domain_points, uint32_t n_points,
+								  uint32_t *first_slot);
+/* sumcheck_fold_multilinears, LowToHigh, Folded branch (hal/src/sumcheck_folding.rs:37-147 ->
+ * math/src/fold.rs:528-575 fold_right_lerp): out[i] = in[2i] + (in[2i+1] - in[2i]) * challenge over the
+ * stored prefix (an odd tail pairs with suffix_eval); out-of-place like the reference (outputs must
+ * not overlap inputs); new_lens[t] = ceil(prefix[t] / 2). */
+int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *multilins, const b200_dev_ptr *outputs,
+										   uint32_t n_multilins, uint32_t n_vars, const uint64_t *non_const_prefix,
+										   const uint64_t *suffix_evals /* 2*m */, const uint64_t challenge[2],
+										   uint64_t *new_lens);
+
 #ifdef __cplusplus
 }
 #endif

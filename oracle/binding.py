@@ -299,6 +299,43 @@ def eq_ind_round_evals(mls, lens, suffixes, n_vars, eq_ind, comps, leads, codes,
     return [vals[c * len(codes):(c + 1) * len(codes)] for c in range(len(comps))]
 
 
+def sumcheck_round_evals(order: int, mls, lens, suffixes, n_vars, eq_ind, comps, leads, codes, points):
+    """order 0 = LowToHigh, 1 = HighToLow; eq_ind None = regular (unweighted) evaluator."""
+    mls = [_c(m) if len(m) else np.zeros((1, 2), np.uint64) for m in mls]
+    m = len(mls)
+    enc_c = [encode_expr(s) for s in comps]
+    enc_l = [encode_expr(s) for s in leads]
+    pc = (C.c_void_p * len(comps))(*[C.addressof(e) for e in enc_c])
+    pl = (C.c_void_p * len(comps))(*[C.addressof(e) for e in enc_l])
+    nc = (C.c_uint32 * len(comps))(*[len(s) for s in comps])
+    nl = (C.c_uint32 * len(comps))(*[len(s) for s in leads])
+    out = np.zeros((max(len(comps) * len(codes), 1), 2), np.uint64)
+    eq = _p(_c(eq_ind)) if eq_ind is not None else C.c_void_p(None)
+    lib().orc_sumcheck_round_evals(C.c_uint32(order), _ptr_array(mls), (C.c_uint64 * max(m, 1))(*lens),
+                                   _p(to_arr(list(suffixes)) if m else np.zeros((1, 2), np.uint64)),
+                                   C.c_uint32(m), C.c_uint32(n_vars), eq, pc, nc, pl, nl, C.c_uint32(len(comps)),
+                                   (C.c_uint32 * max(len(codes), 1))(*codes), _p(to_arr(list(points)) if len(points) else np.zeros((1, 2), np.uint64)),
+                                   C.c_uint32(len(codes)), _p(out))
+    vals = to_ints(out)
+    return [vals[c * len(codes):(c + 1) * len(codes)] for c in range(len(comps))]
+
+
+def fold_right_lerp(evals, suffix: int, z: int):
+    """fold_right_lerp over the stored prefix `evals`; returns the ceil(len/2) folded elements"""
+    buf = _c(evals) if len(evals) else np.zeros((1, 2), np.uint64)
+    out = np.zeros(((len(evals) + 1) // 2 + 1, 2), np.uint64)
+    lib().orc_fold_right_lerp.restype = C.c_uint64
+    n = lib().orc_fold_right_lerp(_p(buf), C.c_uint64(len(evals)), _p(one(suffix)), _p(one(z)), _p(out))
+    return out[:n]
+
+
+def fold_partial_eq_ind_low_to_high(e):
+    buf = _c(e)
+    out = np.zeros((max(len(buf) // 2, 1), 2), np.uint64)
+    lib().orc_fold_partial_eq_ind_low_to_high(_p(buf), C.c_uint64(len(buf)), _p(out))
+    return out[: len(buf) // 2]
+
+
 def fold_partial_eq_ind(e):
     buf = _c(e).copy()
     lib().orc_fold_partial_eq_ind(_p(buf), C.c_uint64(len(buf)))

@@ -101,3 +101,60 @@ int orc_eq_ind_round_evals(const u128u *const *mls, const uint64_t *lens, const 
 void orc_fold_partial_eq_ind(u128u *e, uint64_t n) {
 	for (uint64_t i = 0; i < n / 2; i++) e[i] ^= e[n / 2 + i];
 }
+
+/*
+ * Both evaluation orders and both evaluator kinds of hal/src/sumcheck_round_calculation.rs:126-349:
+ *   order 1 = HighToLowAccess (:507-604): (lo, hi) = (M[i], M[half + i])
+ *   order 0 = LowToHighAccess (:408-504): (lo, hi) = (M[2i], M[2i + 1])   (interleaved, then unzipped)
+ *   eq_ind != NULL: eq-ind evaluator (core/.../prove/eq_ind.rs:646-731), sums weighted by eq_ind[i]
+ *   eq_ind == NULL: regular evaluator (core/.../prove/regular_sumcheck.rs:233-277), plain sums
+ */
+int orc_sumcheck_round_evals(uint32_t order, const u128u *const *mls, const uint64_t *lens, const u128u *suffix, uint32_t m,
+							 uint32_t n_vars, const u128u *eq_ind, const orc_expr_step *const *comps,
+							 const uint32_t *comp_steps, const orc_expr_step *const *leads,
+							 const uint32_t *lead_steps, uint32_t n_comp, const uint32_t *codes,
+							 const u128u *points, uint32_t n_points, u128u *out) {
+	tower_init();
+	uint64_t half = (uint64_t)1 << (n_vars - 1);
+	u128 *q = malloc(sizeof(u128) * (m + 1)), *tmp = malloc(sizeof(u128) * 256);
+	for (uint32_t c = 0; c < n_comp; c++)
+		for (uint32_t p = 0; p < n_points; p++) {
+			u128 acc = 0;
+			for (uint64_t i = 0; i < half; i++) {
+				uint64_t i_lo = order ? i : 2 * i, i_hi = order ? half + i : 2 * i + 1;
+				for (uint32_t t = 0; t < m; t++) {
+					u128 lo = i_lo < lens[t] ? mls[t][i_lo] : suffix[t];
+					u128 hi = i_hi < lens[t] ? mls[t][i_hi] : suffix[t];
+					if (codes[p] == 1) q[t] = hi;
+					else if (codes[p] == 2) q[t] = hi ^ lo;
+					else q[t] = lo ^ b128_mul(hi ^ lo, points[p]);
+				}
+				u128 v = codes[p] == 2 ? eval_expr(leads[c], lead_steps[c], q, tmp) : eval_expr(comps[c], comp_steps[c], q, tmp);
+				acc ^= eq_ind ? b128_mul(v, eq_ind[i]) : v;
+			}
+			out[c * n_points + p] = acc;
+		}
+	free(q);
+	free(tmp);
+	return 0;
+}
+
+/*
+ * math/src/fold.rs:528-575 fold_right_lerp (P::WIDTH = PE::WIDTH = 1) as driven by the Folded branch of
+ * fold_multilinears_low_to_high (hal/src/sumcheck_folding.rs:117-143):
+ *   out[i] = in[2i] + (in[2i+1] - in[2i]) * z        i < evals_size / 2
+ *   odd evals_size: out[evals_size/2] = in[last] + (suffix - in[last]) * z
+ * Returns the number of output elements, ceil(evals_size / 2).
+ */
+uint64_t orc_fold_right_lerp(const u128u *evals, uint64_t evals_size, const u128u *suffix, const u128u *z, u128u *out) {
+	tower_init();
+	uint64_t folded = evals_size >> 1;
+	for (uint64_t i = 0; i < folded; i++) out[i] = evals[2 * i] ^ b128_mul(evals[2 * i + 1] ^ evals[2 * i], *z);
+	if (evals_size & 1) out[folded] = evals[2 * folded] ^ b128_mul(*suffix ^ evals[2 * folded], *z);
+	return (evals_size + 1) >> 1;
+}
+
+/* core/src/protocols/sumcheck/prove/common.rs:37-57 fold_partial_eq_ind (low-to-high): E'[i] = E[2i] + E[2i+1] */
+void orc_fold_partial_eq_ind_low_to_high(const u128u *e, uint64_t n, u128u *out) {
+	for (uint64_t i = 0; i < n / 2; i++) out[i] = e[2 * i] ^ e[2 * i + 1];
+}

@@ -169,3 +169,121 @@ def test_evaluate_partial_high(hal, oracle):
     for i, c in enumerate(reversed(q)):
         cur = oracle.fold_left_lerp_inplace(cur, len(cur), 0, n - i, c)
     assert _same(cur, exp)
+
+
+@pytest.mark.parametrize("n_vars", [1, 6, 13])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_low_to_high_rounds_match_oracle(hal, oracle, n_vars, weighted):
+    """EvaluationOrder::LowToHigh (LowToHighAccess, fold_right_lerp, fold_partial_eq_ind low-to-high) with
+    the eq-ind evaluator and with the regular (unweighted) evaluator, all rounds, truncated inputs."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import (B200Backend, EqIndEvaluator, EvaluationOrder, FoldedMultilinear,
+                                 RegularSumcheckEvaluator)
+
+    be = B200Backend(hal)
+    rng = random.Random(100 + n_vars)
+    comps = u32_add_compositions() + [A.var(0) * A.var(1) * A.var(4) + A.var(2)]
+    full = 1 << n_vars
+    prefixes = [full, full, max(full - 3, 1), max(full // 2 + 1, 1), max(full // 3, 1)]
+    suffixes = [0, 0, rng.getrandbits(128), 1, rng.getrandbits(128)]
+    mls_h = [oracle.rand_b128(900 + t, p) for t, p in enumerate(prefixes)]
+    mls = [FoldedMultilinear(hal.to_device(m), s) for m, s in zip(mls_h, suffixes)]
+    eq_pt = [rng.getrandbits(128) for _ in range(n_vars - 1)]
+    eq_d = be.tensor_product_full_query(eq_pt) if weighted else None
+    eq_h = hal.to_host(eq_d) if weighted else None
+    finite = [oracle.mul(0x2, 0x2)]
+    Ev = EqIndEvaluator if weighted else RegularSumcheckEvaluator
+    for rnd in range(n_vars):
+        nv = n_vars - rnd
+        evs = [Ev(c) for c in comps]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, eq_d, finite, evaluation_order=EvaluationOrder.LowToHigh)
+        exp = oracle.sumcheck_round_evals(0, mls_h, [len(m) for m in mls_h], suffixes, nv, eq_h, [c.steps for c in comps],
+                                          [c.leading_term().steps for c in comps], [1, 2, 3], [0, 0, finite[0]])
+        for ev, g, e in zip(evs, got, exp):
+            assert g == [e[k - 1] for k in ev.eval_point_indices()]
+        ch = rng.getrandbits(128)
+        assert be.sumcheck_fold_multilinears(nv, mls, ch, evaluation_order=EvaluationOrder.LowToHigh) is False
+        mls_h = [oracle.fold_right_lerp(m, s, ch) for m, s in zip(mls_h, suffixes)]
+        for d, h in zip(mls, mls_h):
+            assert d.evals.len() == len(h) and _same(hal.to_host(d.evals), h)
+        if weighted and nv > 1:
+            eq_d = be.fold_partial_eq_ind(nv - 1, eq_d, EvaluationOrder.LowToHigh)
+            eq_h = oracle.fold_partial_eq_ind_low_to_high(eq_h)
+            assert _same(hal.to_host(eq_d), eq_h)
+    assert all(m.evals.len() == 1 for m in mls)
+
+
+def test_low_to_high_fold_rejects_overlap(hal, oracle):
+    import ctypes as C
+
+    import binius_b200
+
+    d = hal.to_device(oracle.rand_b128(1, 64))
+    ptrs = (C.c_void_p * 1)(d.ptr)
+    lens = (C.c_uint64 * 1)(64)
+    z = (C.c_uint64 * 2)(5, 0)
+    sfx = (C.c_uint64 * 2)(0, 0)
+    with pytest.raises(binius_b200.InputValidation):
+        hal._check(hal._lib.b200_fold_multilinears_low_to_high(hal._ctx, ptrs, ptrs, 1, 6, lens, sfx, z, None))
+
+
+def _pack_subfield(oracle, scalars, lvl):
+    """2^(7-lvl) sub-field scalars of 2^lvl bits per B128 word, low limb first (memory.rs:257-281)."""
+    per = 1 << (7 - lvl)
+    words = []
+    for w in range(len(scalars) // per):
+        v = 0
+        for j in range(per):
+            v |= scalars[w * per + j] << (j << lvl)
+        words.append(v)
+    return oracle.to_arr(words)
+
+
+@pytest.mark.parametrize("order_name", ["HighToLow", "LowToHigh"])
+@pytest.mark.parametrize("lvl", [0, 3, 5])
+def test_transparent_multilinears_switchover(hal, oracle, order_name, lvl):
+    """SumcheckMultilinear::Transparent (sub-field multilinears, switchover rounds 0/1/2) next to a Folded
+    one: every round's evaluations and the post-switchover folded values equal those of the same
+    sumcheck run on the B128 embeddings (sumcheck_folding.rs:37-241, prover_state.rs:138-188)."""
+    from binius_b200.hal import (B200Backend, EvaluationOrder, FoldedMultilinear, RegularSumcheckEvaluator,
+                                 TransparentMultilinear)
+
+    order = EvaluationOrder[order_name]
+    be = B200Backend(hal)
+    n_vars = 9
+    rng = random.Random(lvl * 10 + int(order))
+    bits = 1 << lvl
+    scal = [[rng.getrandbits(bits) for _ in range(1 << n_vars)] for _ in range(3)]
+    emb_h = [oracle.to_arr(s) for s in scal] + [oracle.rand_b128(33, 1 << n_vars)]
+    mls = [TransparentMultilinear(hal.to_device(_pack_subfield(oracle, s, lvl)), lvl, n_vars, switchover_round=t)
+           for t, s in enumerate(scal)] + [FoldedMultilinear(hal.to_device(emb_h[3]), 0)]
+    from binius_b200 import ArithCircuit as A
+
+    comps = [A.var(0) * A.var(1) + A.var(2) * A.var(3), A.var(0) * A.var(3) * A.var(2) + A.var(1)]
+    finite = [oracle.mul(0x2, 0x2)]
+    challenges = []
+    for rnd in range(5):
+        nv = n_vars - rnd
+        # tensor query = expansion of the challenges so far (HighToLow: newest first, prover_state.rs:161-171)
+        coords = challenges if order == EvaluationOrder.LowToHigh else list(reversed(challenges))
+        tq = be.tensor_product_full_query(coords) if any(isinstance(x, TransparentMultilinear) for x in mls) else None
+        evs = [RegularSumcheckEvaluator(c) for c in comps]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, None, finite, evaluation_order=order, tensor_query=tq)
+        exp = oracle.sumcheck_round_evals(int(order), emb_h, [len(x) for x in emb_h], [0] * 4, nv, None, [c.steps for c in comps],
+                                          [c.leading_term().steps for c in comps], [1, 2, 3], [0, 0, finite[0]])
+        for ev, g, e in zip(evs, got, exp):
+            assert g == [e[k - 1] for k in ev.eval_point_indices()]
+        ch = rng.getrandbits(128)
+        challenges.append(ch)
+        coords = challenges if order == EvaluationOrder.LowToHigh else list(reversed(challenges))
+        tq = be.tensor_product_full_query(coords)
+        left = be.sumcheck_fold_multilinears(nv, mls, ch, tq, evaluation_order=order)
+        assert left == (rnd < 2)
+        if order == EvaluationOrder.HighToLow:
+            emb_h = [oracle.fold_left_lerp_inplace(x, len(x), 0, nv, ch) for x in emb_h]
+        else:
+            emb_h = [oracle.fold_right_lerp(x, 0, ch) for x in emb_h]
+        for t, (d, h) in enumerate(zip(mls, emb_h)):
+            assert isinstance(d, FoldedMultilinear) == (t <= rnd or t == 3)
+            if isinstance(d, FoldedMultilinear):
+                assert _same(hal.to_host(d.evals), h)

@@ -358,3 +358,51 @@ def test_cpu_baseline_matches_oracle(oracle):
         for threads, gfni in [(1, True), (3, True), (2, False)]:
             got, _ = o.cpu_fold(e0, e1, z, threads, gfni)
             assert np.array_equal(got, exp)
+
+
+def _bitrev(i, n):
+    return int(format(i, f"0{n}b")[::-1], 2) if n else 0
+
+
+def test_low_to_high_restatements(oracle):
+    """LowToHigh order (sumcheck_round_calculation.rs:408-504, fold.rs:528-575, common.rs:37-57) against
+    definitions: (a) round evals equal the HighToLow ones of the bit-reversed multilinears, (b) the
+    regular evaluator satisfies r(0) + r(1) = sum over the hypercube, (c) fold_right_lerp is the
+    element-wise lerp of adjacent pairs with the constant suffix, (d) a full LowToHigh sumcheck ends in
+    the multilinear evaluation at the challenge point."""
+    o = oracle
+    rng = random.Random(5)
+    n, m = 6, 3
+    mls = [o.rand_b128(700 + t, 1 << n) for t in range(m)]
+    comp = [("var", 0), ("var", 1), ("mul", 0, 1), ("var", 2), ("add", 2, 3)]  # x*y + w
+    lead = [("var", 0), ("var", 1), ("mul", 0, 1)]
+    eq = o.rand_b128(710, 1 << (n - 1))
+    z3 = rng.getrandbits(128)
+    codes, pts = [1, 2, 3], [0, 0, z3]
+    lens, sfx = [1 << n] * m, [0] * m
+    lo2hi = o.sumcheck_round_evals(0, mls, lens, sfx, n, eq, [comp], [lead], codes, pts)
+    # (a) bit-reversed inputs in the other order; eq-ind indices follow the remaining n-1 variables
+    rev = [np.stack([x[_bitrev(i, n)] for i in range(1 << n)]) for x in mls]
+    eq_rev = np.stack([eq[_bitrev(i, n - 1)] for i in range(1 << (n - 1))])
+    assert o.sumcheck_round_evals(1, rev, lens, sfx, n, eq_rev, [comp], [lead], codes, pts) == lo2hi
+    assert o.sumcheck_round_evals(1, mls, lens, sfx, n, eq, [comp], [lead], codes, pts) == o.eq_ind_round_evals(mls, lens, sfx, n, eq, [comp], [lead], codes, pts)
+    # (b) regular evaluator: r(0) (finite point 0) + r(1) = sum_x C(M(x))
+    for order in (0, 1):
+        r = o.sumcheck_round_evals(order, mls, lens, sfx, n, None, [comp], [lead], [1, 3], [0, 0])[0]
+        total = o.sum_composition_evals(mls, comp, 1, 0)
+        assert r[0] ^ r[1] == total
+    # (c) fold_right_lerp with an odd stored prefix and a constant suffix
+    z = rng.getrandbits(128)
+    for plen, s in ((64, 0), (37, rng.getrandbits(128)), (1, 7), (0, 9)):
+        x = mls[0][:plen]
+        got = ints(o, o.fold_right_lerp(x, s, z))
+        xi = ints(o, x) + [s]
+        assert got == [xi[2 * i] ^ o.mul(xi[2 * i] ^ xi[2 * i + 1], z) for i in range((plen + 1) // 2)]
+    assert ints(o, o.fold_partial_eq_ind_low_to_high(eq)) == [a ^ b for a, b in zip(ints(o, eq)[0::2], ints(o, eq)[1::2])]
+    # (d) fold all variables low-to-high: the result is the multilinear evaluated at the challenges
+    ch = [rng.getrandbits(128) for _ in range(n)]
+    cur = mls[1]
+    for c in ch:
+        cur = o.fold_right_lerp(cur, 0, c)
+    basis = o.tensor_expand(o.to_arr([1] + [0] * ((1 << n) - 1)), 0, ch)
+    assert ints(o, cur) == [o.inner_product(mls[1], 7, basis)]
