@@ -37,6 +37,23 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def profiled_traffic(kernel="k_lerp_tma"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` summary of this same command (profiles/); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", f"r1_fold_{kernel}_ncu_full.csv")
+    try:
+        rd = wr = None
+        for line in open(path):
+            p = line.strip().split(",")
+            if len(p) >= 3 and p[0] == "dram__bytes_read.sum" and rd is None:
+                rd = float(p[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[p[1]]
+            if len(p) >= 3 and p[0] == "dram__bytes_write.sum" and wr is None:
+                wr = float(p[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[p[1]]
+        return None if rd is None or wr is None else {"bytes": rd + wr, "source": os.path.relpath(path, ROOT)}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -197,7 +214,7 @@ def main():
     t1 = time.time()
     launches = hal.launch_count() - l0
 
-    # per-launch duration of the dominant kernel (k_lerp_lut), CUDA events around single launches
+    # per-launch duration of the dominant kernel (k_lerp_tma), CUDA events around single launches
     kern_ms = []
     for _ in range(min(args.steps, 10)):
         hal._check(hal._lib.b200_sync(hal._ctx))
@@ -287,6 +304,7 @@ def main():
     if rank == 0:
         value = world * n_in / (ms_step * 1e-3)
         achieved = 24.0 * n_in / (kern_ms_avg * 1e-3) / 1e9  # algorithmic bytes: 16 B read + 8 B written per coefficient
+        traffic = profiled_traffic() if args.log_coeffs == 24 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -296,8 +314,9 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * n_in / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_in * 16, "d2h_bytes_per_step": half * 16,
                     "ms_per_step": e2e_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_lerp_lut", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel_ms": kern_ms_avg},
+            "roofline": {"bound": "hbm", "kernel": "k_lerp_tma", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
+                         "algorithmic_bytes": 24.0 * n_in, "kernel_ms": kern_ms_avg},
         }
         if ntt_res:
             line["ntt"] = ntt_res

@@ -291,8 +291,10 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	// opt in to large dynamic shared memory once
 	int32_t rc = B200_OK;
 #define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
-	SET(k_expand_lut, LUT_BYTES + 2048);
-	SET(k_expand_small, FIELD_TABLE_BYTES + 16 * 2048);
+	SET(k_expand_k64<1>, 1 * LUT_BYTES + 6144);
+	SET(k_expand_k64<2>, 2 * LUT_BYTES + 6144);
+	SET(k_expand_k64<3>, 3 * LUT_BYTES + 6144);
+	SET(k_expand_small, EXP_SMALL_LOG * (NLUT_BYTES + 2048) + (16u << EXP_SMALL_LOG));
 	SET(k_inner_product, FIELD_TABLE_BYTES);
 	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
 	SET(k_fold_right_lut, LUT_BYTES + 2048);
@@ -554,6 +556,8 @@ static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint
 	const int engine = fold_engine();
 	if (engine == 0) return launch_lerp_variant<512, 2, 2, false, false>(ctx, live, z);
 	if (engine == 1) return launch_lerp_variant<512, 2, 2, false, true>(ctx, live, z);
+	for (auto &sg : live)
+		if (sg.upper >> 32) return launch_lerp_variant<512, 2, 2, false, true>(ctx, live, z);  // 32-bit tile arithmetic in the TMA kernel
 	return launch_lerp_tma<false>(ctx, live, z);
 }
 
@@ -675,7 +679,9 @@ int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *ml
 		if (upper) live.push_back(LerpSeg{(uint4 *)outs[t], (const uint4 *)mls[t], p / 2, upper, to_u4(suffix + 2 * t), 0});
 	}
 	if (live.empty()) return B200_OK;
-	if (fold_engine() != 2) return launch_lerp_variant<512, 2, 2, true>(ctx, live, z);
+	bool small = fold_engine() == 2;
+	for (auto &sg : live) small = small && !(sg.upper >> 31);  // 32-bit tile arithmetic in the TMA kernel
+	if (!small) return launch_lerp_variant<512, 2, 2, true>(ctx, live, z);
 	return launch_lerp_tma<true>(ctx, live, z);
 }
 
@@ -686,22 +692,30 @@ int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, 
 	if (k == 0) return B200_OK;
 	// rounds that fit one CTA's shared memory
 	uint32_t k_small = 0;
-	if (log_n <= 11) k_small = std::min(k, 11 - log_n);
+	if (log_n <= EXP_SMALL_LOG) k_small = std::min(k, EXP_SMALL_LOG - log_n);
 	if (k_small) {
 		std::vector<uint4> h(k_small);
 		for (uint32_t i = 0; i < k_small; i++) h[i] = to_u4(coords + 2 * i);
 		void *dc;
 		int32_t rc = stage_args(ctx, h.data(), sizeof(uint4) * k_small, &dc);
 		if (rc) return rc;
-		k_expand_small<<<1, 256, FIELD_TABLE_BYTES + (16u << (log_n + k_small)), ctx->stream>>>(ctx->d_tables, (uint4 *)data, log_n, (const uint4 *)dc, k_small);
+		k_expand_small<<<1, 1024, k_small * (NLUT_BYTES + 2048) + (16u << (log_n + k_small)), ctx->stream>>>((uint4 *)data, log_n, (const uint4 *)dc, k_small);
 		B200_LAUNCH_CHECK(ctx);
 	}
-	for (uint32_t r = k_small; r < k; r++) {
-		uint64_t half = 1ull << (log_n + r);
-		uint64_t tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
-		uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sms * 3);
-		k_expand_lut<<<grid, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((uint4 *)data, half, to_u4(coords + 2 * r));
+	// the rest: up to three rounds per launch
+	for (uint32_t r = k_small; r < k;) {
+		// the short launch goes first: the last (largest) launches fuse three rounds
+		const uint32_t R = (k - r) % 3 ? (k - r) % 3 : 3;
+		ExpandArgs A;
+		A.data = (uint4 *)data;
+		A.n0 = 1ull << (log_n + r);
+		for (uint32_t t = 0; t < 3; t++) A.r[t] = t < R ? to_u4(coords + 2 * (r + t)) : make_uint4(0, 0, 0, 0);
+		uint32_t grid = (uint32_t)std::min<uint64_t>((A.n0 + EXP_THREADS - 1) / EXP_THREADS, (uint64_t)ctx->n_sms);
+		if (R == 3) k_expand_k64<3><<<grid, EXP_THREADS, 3 * LUT_BYTES + 6144, ctx->stream>>>(A);
+		else if (R == 2) k_expand_k64<2><<<grid, EXP_THREADS, 2 * LUT_BYTES + 6144, ctx->stream>>>(A);
+		else k_expand_k64<1><<<grid, EXP_THREADS, 1 * LUT_BYTES + 6144, ctx->stream>>>(A);
 		B200_LAUNCH_CHECK(ctx);
+		r += R;
 	}
 	return B200_OK;
 }

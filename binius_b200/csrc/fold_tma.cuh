@@ -48,21 +48,18 @@ __device__ __forceinline__ void ft_bulk_g2s(void *dst, const void *src, uint32_t
 				 : "memory");
 }
 
-// what one tile covers
-struct FtTile {
-	uint64_t base;  // first output index inside the segment
-	uint32_t cnt;   // outputs in this tile
+// what one warp-tile covers; computed once per tile, NSTAGE iterations before it is consumed.
+// All sizes are 32-bit: the host only launches this kernel for segments below 2^32 elements.
+struct FtDesc {
+	uint32_t seg;   // segment index
+	uint32_t base;  // first output index inside the segment
+	uint32_t cnt;   // outputs in this tile (0: past the end)
 	uint32_t cntb;  // outputs whose second operand is stored (the rest pair with the suffix)
 };
-__device__ __forceinline__ FtTile ft_tile(const LerpSeg &S, uint64_t tile) {
-	FtTile t;
-	t.base = (tile - S.tile_start) * FT_TILE;
-	const uint64_t left = S.upper - t.base;
-	t.cnt = left < FT_TILE ? (uint32_t)left : FT_TILE;
-	const uint64_t lb = S.pivot > t.base ? S.pivot - t.base : 0;
-	t.cntb = lb < t.cnt ? (uint32_t)lb : t.cnt;
-	return t;
-}
+// cursor over the segment list for an increasing tile sequence
+struct FtCursor {
+	uint32_t seg, seg_start, seg_end;
+};
 
 template <bool PAIRS>
 __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constant__ LerpArgs A) {
@@ -70,64 +67,77 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint8_t *ring = smem + LUT_BYTES + 2048 + warp * (FT_NSTAGE * FT_STAGE_BYTES);
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + LUT_BYTES + 2048 + FT_WARPS * FT_NSTAGE * FT_STAGE_BYTES) + warp * FT_NSTAGE;
-	const uint64_t tile0 = (uint64_t)blockIdx.x * FT_WARPS + warp, tile_step = (uint64_t)gridDim.x * FT_WARPS;
+	const uint32_t n_tiles = (uint32_t)A.n_tiles, tile_step = gridDim.x * FT_WARPS;
+	uint32_t next_tile = blockIdx.x * FT_WARPS + warp;  // tile of the next descriptor to build
 
-	// producer state (lane 0 of every warp): next tile to request and its segment cursor
-	uint64_t p_tile = tile0;
-	uint32_t p_seg = 0, p_k = 0;
-	auto issue = [&]() {
-		if (p_tile >= A.n_tiles) return;
-		while (p_seg + 1 < A.n_segs && A.segs[p_seg + 1].tile_start <= p_tile) p_seg++;
-		const LerpSeg &S = A.segs[p_seg];
-		const FtTile t = ft_tile(S, p_tile);
-		const uint32_t s = p_k % FT_NSTAGE;
-		uint8_t *dst = ring + s * FT_STAGE_BYTES;
-		ft_mbar_expect_tx(&full[s], (t.cnt + t.cntb) * 16);
-		if (PAIRS) {
-			ft_bulk_g2s(dst, S.e1 + 2 * t.base, (t.cnt + t.cntb) * 16, &full[s]);  // interleaved (2i, 2i+1)
-		} else {
-			ft_bulk_g2s(dst, S.e0 + t.base, t.cnt * 16, &full[s]);
-			if (t.cntb) ft_bulk_g2s(dst + FT_TILE * 16, S.e1 + t.base, t.cntb * 16, &full[s]);
+	FtCursor C{0, 0, A.n_segs > 1 ? (uint32_t)A.segs[1].tile_start : n_tiles};
+	// build the descriptor of `next_tile` (warp-uniform), have lane 0 request it into stage `s`, advance
+	auto request = [&](uint32_t s) -> FtDesc {
+		FtDesc d{0, 0, 0, 0};
+		if (next_tile < n_tiles) {
+			while (next_tile >= C.seg_end) {
+				C.seg++;
+				C.seg_start = C.seg_end;
+				C.seg_end = C.seg + 1 < A.n_segs ? (uint32_t)A.segs[C.seg + 1].tile_start : n_tiles;
+			}
+			const LerpSeg &S = A.segs[C.seg];
+			d.seg = C.seg;
+			d.base = (next_tile - C.seg_start) * FT_TILE;
+			d.cnt = min(FT_TILE, (uint32_t)S.upper - d.base);
+			const uint32_t pivot = (uint32_t)S.pivot;
+			d.cntb = min(d.cnt, max(pivot, d.base) - d.base);
+			if (lane == 0) {
+				uint8_t *dst = ring + s * FT_STAGE_BYTES;
+				ft_mbar_expect_tx(&full[s], (d.cnt + d.cntb) * 16);
+				if (PAIRS) {
+					ft_bulk_g2s(dst, S.e1 + 2 * (uint64_t)d.base, (d.cnt + d.cntb) * 16, &full[s]);  // interleaved (2i, 2i+1)
+				} else {
+					ft_bulk_g2s(dst, S.e0 + d.base, d.cnt * 16, &full[s]);
+					if (d.cntb) ft_bulk_g2s(dst + FT_TILE * 16, S.e1 + d.base, d.cntb * 16, &full[s]);
+				}
+			}
+			next_tile += tile_step;
 		}
-		p_tile += tile_step;
-		p_k++;
+		return d;
 	};
 	if (lane == 0) {
 		for (uint32_t s = 0; s < FT_NSTAGE; s++) ft_mbar_init(&full[s], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		for (uint32_t s = 0; s < FT_NSTAGE; s++) issue();  // loads fly while the table is built
 	}
-	const MulEngine<true> E(smem, A.z);  // ends with __syncthreads
+	__syncwarp();
+	static_assert(FT_NSTAGE == 2, "the descriptor ring below is written for two stages");
+	FtDesc d0 = request(0), d1 = request(1);  // loads fly while the table is built
+	const MulEngine<true> E(smem, A.z);       // ends with __syncthreads
 
-	uint32_t seg = 0, k = 0;
-	for (uint64_t tile = tile0; tile < A.n_tiles; tile += tile_step, k++) {
-		while (seg + 1 < A.n_segs && A.segs[seg + 1].tile_start <= tile) seg++;
-		const LerpSeg &S = A.segs[seg];
-		const FtTile t = ft_tile(S, tile);
-		const uint32_t s = k % FT_NSTAGE;
+	for (uint32_t k = 0; d0.cnt; k++) {
+		const uint32_t s = k & 1u;
+		const LerpSeg &S = A.segs[d0.seg];
 		const uint4 *st = reinterpret_cast<const uint4 *>(ring + s * FT_STAGE_BYTES);
-		ft_mbar_wait(&full[s], (k / FT_NSTAGE) & 1u);
+		ft_mbar_wait(&full[s], (k >> 1) & 1u);
 		uint4 a[FT_UNR], x[FT_UNR];
 #pragma unroll
 		for (uint32_t u = 0; u < FT_UNR; u++) {
 			const uint32_t i = lane + 32 * u;
-			a[u] = make_uint4(0, 0, 0, 0);
-			x[u] = a[u];
-			if (i < t.cnt) {
-				a[u] = PAIRS ? st[2 * i] : st[i];
-				const uint4 b = i < t.cntb ? (PAIRS ? st[2 * i + 1] : st[FT_TILE + i]) : S.suffix;
-				x[u] = a[u] ^ b;
-			}
+			// lanes past the end read stale (finite) shared memory; their result is never stored
+			a[u] = PAIRS ? st[2 * i] : st[i];
+			uint4 b = PAIRS ? st[2 * i + 1] : st[FT_TILE + i];
+			if (i >= d0.cntb) b = S.suffix;
+			x[u] = a[u] ^ b;
 		}
 		// the XORs consumed the shared-memory loads: once the whole warp is here the stage may be refilled
 		__syncwarp();
-		if (lane == 0) issue();
+		const FtDesc d2 = request(s);
+		uint4 *out = S.e0 + d0.base;
+#pragma unroll
+		for (uint32_t u = 0; u < FT_UNR; u++) x[u] = E.mul(x[u]);
 #pragma unroll
 		for (uint32_t u = 0; u < FT_UNR; u++) {
 			const uint32_t i = lane + 32 * u;
-			if (i < t.cnt) S.e0[t.base + i] = a[u] ^ E.mul(x[u]);
+			if (i < d0.cnt) out[i] = a[u] ^ x[u];
 		}
+		d0 = d1;
+		d1 = d2;
 	}
 }
 

@@ -121,57 +121,72 @@ __global__ void __launch_bounds__(THREADS, MINB) k_lerp_pairs_lut(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-// one tensor-expansion round:  p = x * r ; lo[j] = x ^ p ; hi[j] = p        j < half
+// Tensor expansion, R <= 3 rounds fused per launch:  round t:  p = x * r_t ; lo = x ^ p ; hi = p.
+// Each thread takes one input x[i] (i < n0), keeps its 2^R descendants in registers and stores them at
+// i + e * n0 (in place: a thread only touches its own column), so the intermediate rounds never travel
+// to HBM.  One Karatsuba-64 table per coordinate (linmap.cuh), R x 64 KiB of shared memory.
 // reference: compute/src/layer.rs:269-296 (definition), math/src/tensor_prod_eq_ind.rs:35-77
-__global__ void __launch_bounds__(FOLD_THREADS, 3) k_expand_lut(uint4 *__restrict__ data, uint64_t half, uint4 r) {
-	extern __shared__ __align__(128) uint8_t smem[];
-	uint8_t *tbl = smem;
-	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
-	lut_build_mul(tbl, stage, r);
-	const LutLane L = lut_lane_init();
-	uint64_t n_tiles = (half + FOLD_TILE - 1) / FOLD_TILE;
-	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		uint64_t base = tile * FOLD_TILE + threadIdx.x;
-		uint4 x[FOLD_UNROLL];
+constexpr uint32_t EXP_THREADS = 512;
+struct ExpandArgs {
+	uint4 *data;
+	uint64_t n0;
+	uint4 r[3];
+};
+template <uint32_t R>
+__global__ void __launch_bounds__(EXP_THREADS, 1) k_expand_k64(const __grid_constant__ ExpandArgs A) {
+	extern __shared__ __align__(256) uint8_t smem[];
+	uint2 *stage = reinterpret_cast<uint2 *>(smem + R * LUT_BYTES);
+	uint4 zs[R];
 #pragma unroll
-		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
-			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
-			if (i < half) x[u] = data[i];
-		}
+	for (uint32_t t = 0; t < R; t++) zs[t] = A.r[t];
+	k64_build_multi<R>(smem, stage, zs);
+	K64Lane L = k64_lane_init(smem);
+	const uint32_t sbase = L.sbase;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < A.n0; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 y[1u << R];
+		y[0] = A.data[i];
 #pragma unroll
-		for (uint32_t u = 0; u < FOLD_UNROLL; u++) {
-			uint64_t i = base + (uint64_t)u * FOLD_THREADS;
-			if (i < half) {
-				uint4 p = lut_apply(tbl, L, x[u]);
-				data[i] = x[u] ^ p;
-				data[half + i] = p;
+		for (uint32_t t = 0; t < R; t++) {
+			L.sbase = sbase + t * LUT_BYTES;
+#pragma unroll
+			for (uint32_t e = 0; e < (1u << t); e++) {
+				const uint4 p = k64_apply(L, y[e]);
+				y[e] ^= p;
+				y[e + (1u << t)] = p;
 			}
 		}
+#pragma unroll
+		for (uint32_t e = 0; e < (1u << R); e++) A.data[i + e * A.n0] = y[e];
 	}
 }
 
-// small tensor expansion: rounds [0, k) entirely inside one CTA's shared memory (2^(log_n+k) <= 2048)
-// dyn smem = FIELD_TABLE_BYTES + 16 * 2^(log_n+k)
-__global__ void __launch_bounds__(256) k_expand_small(const uint8_t *__restrict__ g_tables, uint4 *__restrict__ data, uint32_t log_n,
-													  const uint4 *__restrict__ coords, uint32_t k) {
+// small tensor expansion: rounds [0, k) entirely inside one CTA's shared memory (2^(log_n+k) <= 4096).
+// One nibble-LUT (8 KiB) per coordinate, all built up front in parallel; then k rounds of in-smem
+// doubling.  dyn smem = k * (NLUT_BYTES + 2048) + 16 * 2^(log_n+k)
+constexpr uint32_t EXP_SMALL_LOG = 12;
+__global__ void __launch_bounds__(1024) k_expand_small(uint4 *__restrict__ data, uint32_t log_n, const uint4 *__restrict__ coords, uint32_t k) {
 	extern __shared__ __align__(128) uint8_t smem[];
-	FieldTables T = load_field_tables(smem, g_tables);
-	uint4 *buf = reinterpret_cast<uint4 *>(smem + FIELD_TABLE_BYTES);
-	uint32_t n0 = 1u << log_n;
+	uint4 *buf = reinterpret_cast<uint4 *>(smem + k * NLUT_BYTES);
+	uint4 *img = buf + (1u << (log_n + k));  // [k][128] basis images beta_i * r_t, 2 KiB per coordinate
+	for (uint32_t e = threadIdx.x; e < k * 128; e += blockDim.x) img[e] = basis_image(coords[e >> 7], e & 127);
+	__syncthreads();
+	for (uint32_t e = threadIdx.x; e < k * 512; e += blockDim.x) nlut_fill_from_images(smem + (e >> 9) * NLUT_BYTES, img + (e >> 9) * 128, e & 511);
+	const uint32_t n0 = 1u << log_n;
 	for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) buf[i] = data[i];
 	__syncthreads();
+	const NLutLane L = nlut_lane_init();
 	for (uint32_t r = 0; r < k; r++) {
-		uint32_t half = 1u << (log_n + r);
-		uint4 c = coords[r];
+		const uint32_t half = 1u << (log_n + r);
+		const uint8_t *lut = smem + r * NLUT_BYTES;
 		for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
-			uint4 x = buf[i];
-			uint4 p = f_mul128(T, x, c);
+			const uint4 x = buf[i];
+			const uint4 p = nlut_apply(lut, L, x);
 			buf[i] = x ^ p;
 			buf[half + i] = p;
 		}
 		__syncthreads();
 	}
-	uint32_t n = 1u << (log_n + k);
+	const uint32_t n = 1u << (log_n + k);
 	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) data[i] = buf[i];
 }
 

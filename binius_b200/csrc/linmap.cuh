@@ -158,6 +158,18 @@ __device__ __forceinline__ void nlut_build_mul(uint8_t *tbl, uint4 z) {
 	}
 	__syncthreads();
 }
+// the same from 128 basis images already in shared memory (img[i] = beta_i * z); no barrier inside
+__device__ __forceinline__ void nlut_fill_from_images(uint8_t *tbl, const uint4 *img, uint32_t e) {
+	const uint32_t p = e & 31, v = e >> 5;
+	uint4 acc = u4_zero();
+#pragma unroll
+	for (uint32_t i = 0; i < 4; i++) {
+		const uint32_t m = 0u - ((v >> i) & 1u);
+		const uint4 w = img[4 * p + i];
+		acc.x ^= w.x & m; acc.y ^= w.y & m; acc.z ^= w.z & m; acc.w ^= w.w & m;
+	}
+	*reinterpret_cast<uint4 *>(tbl + (p >> 3) * 2048 + v * 128 + (p & 7) * 16) = acc;
+}
 __device__ __forceinline__ uint4 nlut_ld(const uint8_t *tbl, uint32_t w, uint32_t n, uint32_t blk, uint32_t off) {
 	// ((w >> 4n) & 15) * 128
 	uint32_t r = n >= 2 ? ((w >> (4 * n - 7)) & 0x780u) : ((w << (7 - 4 * n)) & 0x780u);
@@ -230,33 +242,41 @@ __device__ __forceinline__ K64Lane k64_lane_init(const uint8_t *tbl) {
 	return L;
 }
 
-// Build the table of x -> x*z.  stage: 3 * 64 uint2 (1.5 KiB).  All threads of the CTA must call.
-__device__ __forceinline__ void k64_build_mul(uint8_t *tbl, uint2 *stage, uint4 z) {
-	for (uint32_t e = threadIdx.x; e < 192; e += blockDim.x) {
-		const uint32_t set = e >> 6, i = e & 63;
+// Build the tables of x -> x*z[t], t < R, side by side (tbl + t * LUT_BYTES).  stage: R * 192 uint2
+// (1.5 KiB per table), laid out [bit i][set*8 + k] so that the entry loop reads and writes consecutive
+// 8-byte words from consecutive lanes (conflict-free).  All threads of the CTA must call.
+template <uint32_t R> __device__ __forceinline__ void k64_build_multi(uint8_t *tbl, uint2 *stage, const uint4 (&zs)[R]) {
+	for (uint32_t e = threadIdx.x; e < R * 192; e += blockDim.x) {
+		const uint32_t t = e / 192, r = e - t * 192, set = r >> 6, idx = r & 63;
+		const uint4 z = zs[t];
 		// c0 = z0, c1 = z1, c2 = z0 + X_5*z1;  A: c0+c1, B: c1+c2 = z0 + z1 + X_5*z1, M: c1
 		const uint4 z1 = make_uint4(z.z, z.w, 0, 0);
 		const uint4 az1 = mul_tower_gen(z1, 5);
 		uint4 c = set == 0 ? make_uint4(z.x ^ z.z, z.y ^ z.w, 0, 0) : set == 1 ? make_uint4(z.x ^ z.z ^ az1.x, z.y ^ z.w ^ az1.y, 0, 0) : z1;
-		uint4 im = basis_image(c, i);  // i < 64: stays inside the low GF(2^64) half
-		stage[e] = make_uint2(im.x, im.y);
+		uint4 im = basis_image(c, idx);  // idx < 64: stays inside the low GF(2^64) half
+		stage[t * 192 + (idx & 7) * 24 + set * 8 + (idx >> 3)] = make_uint2(im.x, im.y);
 	}
 	__syncthreads();
-	for (uint32_t e = threadIdx.x; e < 3 * 2048; e += blockDim.x) {
-		const uint32_t k = e & 7, set = (e >> 3) % 3, b = e / 24;
+	for (uint32_t e = threadIdx.x; e < R * 24 * 256; e += blockDim.x) {
+		const uint32_t t = e / (24 * 256), r = e - t * (24 * 256);
+		const uint32_t b = r / 24, col = r - b * 24;  // col = set*8 + k
 		uint2 acc = make_uint2(0, 0);
 #pragma unroll
 		for (uint32_t i = 0; i < 8; i++) {
 			const uint32_t m = 0u - ((b >> i) & 1u);
-			const uint2 w = stage[set * 64 + 8 * k + i];
+			const uint2 w = stage[t * 192 + i * 24 + col];
 			acc.x ^= w.x & m;
 			acc.y ^= w.y & m;
 		}
-		uint2 *row = reinterpret_cast<uint2 *>(tbl + b * 256u);
-		row[set * 8 + k] = acc;
-		if (set == 2) row[24 + k] = acc;
+		uint2 *row = reinterpret_cast<uint2 *>(tbl + t * LUT_BYTES + b * 256u);
+		row[col] = acc;
+		if (col >= 16) row[col + 8] = acc;
 	}
 	__syncthreads();
+}
+__device__ __forceinline__ void k64_build_mul(uint8_t *tbl, uint2 *stage, uint4 z) {
+	const uint4 zs[1] = {z};
+	k64_build_multi<1>(tbl, stage, zs);
 }
 
 template <uint32_t S, uint32_t IMM> __device__ __forceinline__ uint2 k64_ld(uint32_t sbase, uint32_t w, uint32_t off) {
