@@ -237,6 +237,42 @@ def main():
     e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
     clocks = sampler.stop(t0, t1)
 
+    # ---- sumcheck chain: what the prover does with one multilinear over a whole sumcheck -- upload once,
+    #      fold-high log_coeffs times (2^24, 2^23, ..., 2 coefficients, a fresh challenge per round), read the
+    #      final evaluation back.  Same ops through the same plugin calls; the PCIe copy is paid once.
+    def chain_device():
+        n = n_in
+        r = 0
+        while n >= 2:
+            h = n // 2
+            zr = (C.c_uint64 * 2)((z + r) & (2**64 - 1), z >> 64)
+            hal._check(hal._lib.b200_extrapolate_line(hal._ctx, dev.ptr, h, dev.ptr + 16 * h, h, zr))
+            n, r = h, r + 1
+
+    chain_coeffs = 2 * n_in - 2
+    for _ in range(2):
+        chain_device()
+    hal.sync()
+    lc0 = hal.launch_count()
+    ev.start()
+    chain_reps = 5
+    for _ in range(chain_reps):
+        chain_device()
+    chain_ms = ev.stop_ms() / chain_reps
+    chain_launches = (hal.launch_count() - lc0) // chain_reps
+    out1 = np.zeros((1, 2), np.uint64)
+    barrier()
+    tc0 = time.perf_counter()
+    for _ in range(3):
+        hal._check(hal._lib.b200_copy_h2d(hal._ctx, ph.value, dev.ptr, n_in))
+        chain_device()
+        hal._check(hal._lib.b200_copy_d2h(hal._ctx, dev.ptr, out1.ctypes.data, 1))
+    barrier()
+    chain_e2e_ms = (time.perf_counter() - tc0) * 1e3 / 3
+    chain = {"coeffs_per_chain": chain_coeffs, "rounds": args.log_coeffs, "launches": int(chain_launches), "device_ms": chain_ms,
+             "device_coeffs_per_s": chain_coeffs / (chain_ms * 1e-3), "e2e_ms": chain_e2e_ms,
+             "e2e_coeffs_per_s": chain_coeffs / (chain_e2e_ms * 1e-3), "h2d_bytes": n_in * 16, "d2h_bytes": 16}
+
     # ---- NTT (BASELINE config #2): B32, 2^24 coefficients, S1/S2/S3 shapes ------------------------
     ntt_res = None
     if not args.no_ntt:
@@ -322,8 +358,12 @@ def main():
             line["ntt"] = ntt_res
         if extras:
             line["sumcheck_round"] = extras
+        line["sumcheck_chain"] = chain
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_fold_baseline(args.log_coeffs)
+            from oracle import binding as orc
+
+            line["sumcheck_chain"]["cpu_baseline"] = orc.cpu_fold_chain_parallel(args.log_coeffs, 5.0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

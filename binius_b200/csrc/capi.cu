@@ -1142,6 +1142,10 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 	if (n_z > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "log_z too large");
 	for (size_t pi = 0; pi < plan.size(); pi++) {
 		const Pass &P = inverse ? plan[pi] : plan[plan.size() - 1 - pi];
+		// neighbours in execution order: bit-sliced passes hand the data over bit-sliced
+		auto kind_at = [&](size_t q) { return (inverse ? plan[q] : plan[plan.size() - 1 - q]).kind; };
+		const uint32_t in_sliced = pi > 0 && P.kind != 0 && kind_at(pi - 1) != 0;
+		const uint32_t out_sliced = pi + 1 < plan.size() && P.kind != 0 && kind_at(pi + 1) != 0;
 		uint32_t row0 = ntt->d - (log_y + coset_bits);
 		if (P.kind == 2) {
 			NttBsLowArgs L;
@@ -1156,6 +1160,8 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			L.coset = coset;
 			L.inverse = inverse;
 			L.s_evals = ntt->d_s_evals;
+			L.in_sliced = in_sliced;
+			L.out_sliced = out_sliced;
 			uint64_t n_blocks = 1ull << (lx + log_y - 5 - P.R);
 			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
 			uint32_t smem = (152u << P.R) + 640;
@@ -1176,6 +1182,8 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			B.coset = coset;
 			B.inverse = inverse;
 			B.s_evals = ntt->d_s_evals;
+			B.in_sliced = in_sliced;
+			B.out_sliced = out_sliced;
 			uint64_t n_blocks = 1ull << (log_y - (P.i_lo + P.R) + (lx + P.i_lo - 5 - P.log_c));
 			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
 			uint32_t smem = (4u << P.R) + (128u << (P.R + P.log_c));

@@ -16,9 +16,24 @@ namespace b200 {
 
 // ---- 32x32 bit-matrix transpose held in registers (a[i] = row i) ---------------------------------
 __device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+	// stages 16 and 8 move whole half-words / bytes: one PRMT per output word
 #pragma unroll
-	for (int j = 16; j >= 1; j >>= 1) {
-		const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+	for (int k = 0; k < 16; k++) {
+		const uint32_t lo = a[k], hi = a[k + 16];
+		a[k] = __byte_perm(lo, hi, 0x5410);
+		a[k + 16] = __byte_perm(lo, hi, 0x7632);
+	}
+#pragma unroll
+	for (int k = 0; k < 32; k++) {
+		if ((k & 8) == 0) {
+			const uint32_t lo = a[k], hi = a[k + 8];
+			a[k] = __byte_perm(lo, hi, 0x6240);
+			a[k + 8] = __byte_perm(lo, hi, 0x7351);
+		}
+	}
+#pragma unroll
+	for (int j = 4; j >= 1; j >>= 1) {
+		const uint32_t m = j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
 #pragma unroll
 		for (int k = 0; k < 32; k++) {
 			if ((k & j) == 0) {
@@ -124,6 +139,9 @@ struct NttBsArgs {
 	uint64_t coset;
 	int inverse;
 	const uint32_t *s_evals;
+	// between two bit-sliced passes the data stays bit-sliced in HBM (every 128-byte unit holds its 32
+	// bit-planes instead of its 32 scalars): only the first pass transposes in and the last one out
+	uint32_t in_sliced, out_sliced;
 };
 
 constexpr uint32_t NTT_BS_THREADS = 256;
@@ -166,7 +184,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_pass(const NttBsAr
 			uint4 w = src[q];
 			a[4 * q] = w.x; a[4 * q + 1] = w.y; a[4 * q + 2] = w.z; a[4 * q + 3] = w.w;
 		}
-		transpose32(a);
+		if (!A.in_sliced) transpose32(a);
 #pragma unroll
 		for (int p = 0; p < 32; p++) tile[p * NU + uid] = a[p];
 	}
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_pass(const NttBsAr
 		uint32_t a[32];
 #pragma unroll
 		for (int p = 0; p < 32; p++) a[p] = tile[p * NU + uid];
-		transpose32(a);
+		if (!A.out_sliced) transpose32(a);
 #pragma unroll
 		for (int q = 0; q < 8; q++) dst[q] = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
 	}
@@ -234,6 +252,7 @@ struct NttBsLowArgs {
 	uint64_t coset;
 	int inverse;
 	const uint32_t *s_evals;
+	uint32_t in_sliced, out_sliced;  // as in NttBsArgs
 };
 
 __device__ __forceinline__ uint32_t ntt_subset_sum(const uint32_t *srow, uint32_t nb, uint64_t idx) {
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_low(const NttBsLow
 			uint4 w = src[q];
 			a[4 * q] = w.x; a[4 * q + 1] = w.y; a[4 * q + 2] = w.z; a[4 * q + 3] = w.w;
 		}
-		transpose32(a);
+		if (!A.in_sliced) transpose32(a);
 #pragma unroll
 		for (int p = 0; p < 32; p++) tile[p * NU + uid] = a[p];
 	}
@@ -394,7 +413,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_low(const NttBsLow
 		uint32_t a[32];
 #pragma unroll
 		for (int p = 0; p < 32; p++) a[p] = tile[p * NU + uid];
-		transpose32(a);
+		if (!A.out_sliced) transpose32(a);
 #pragma unroll
 		for (int q = 0; q < 8; q++) dst[q] = make_uint4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
 	}

@@ -270,6 +270,22 @@ def cpu_fold_parallel(log_coeffs: int, budget_s: float = 10.0, n_threads: int = 
                       f"GFNI fold path (fold_left_lerp_inplace), not the Rust binary"}
 
 
+def cpu_fold_chain_parallel(log_coeffs: int, budget_s: float = 6.0, n_threads: int = 0):
+    """Times the complete fold chain (log_coeffs rounds of fold-high, 2^(log_coeffs+1) - 2 coefficients in
+    total) of one multilinear on this host; returns {"value": coeffs/s, ...}."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    fn = lib().cpu_fold_chain_bench
+    fn.restype = C.c_double
+    t1 = fn(C.c_uint32(log_coeffs), C.c_int(1), C.c_int(n_threads), C.c_int(1))
+    reps = max(1, min(50, int(budget_s / max(t1, 1e-4))))
+    t = fn(C.c_uint32(log_coeffs), C.c_int(reps), C.c_int(n_threads), C.c_int(1))
+    total = (2 << log_coeffs) - 2
+    return {"value": reps * total / t, "unit": "coeffs/s", "ms_per_chain": t / reps * 1e3, "cores": n_threads, "kind": "port",
+            "sample": f"{reps} x full fold chain of a 2^{log_coeffs}-coefficient multilinear, {n_threads} threads"}
+
+
 # ------------------------------------------------------------------------------------------------
 # old HAL (ComputationBackend) restatements, oracle/hal.c
 def fold_left_lerp_inplace(evals, prefix: int, suffix: int, log_n: int, z: int):

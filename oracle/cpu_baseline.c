@@ -176,3 +176,34 @@ double cpu_fold_bench(uint32_t log_n, int reps, int n_threads, int use_gfni, int
 	free(buf);
 	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* timed loop for bench.py "sumcheck_chain": folds a 2^log_n-coefficient multilinear all the way down
+ * (log_n rounds of fold-high, sizes 2^log_n, 2^(log_n-1), ..., 2; the reference prover's per-multilinear
+ * work over one sumcheck, sumcheck_folding.rs:223-237), `reps` times; returns seconds.  Rounds below
+ * 2^14 coefficients run on one thread (thread start-up would dominate). */
+double cpu_fold_chain_bench(uint32_t log_n, int reps, int n_threads, int use_gfni) {
+	uint64_t n = (uint64_t)1 << log_n;
+	u128u *src = aligned_alloc(64, sizeof(u128) * n), *buf = aligned_alloc(64, sizeof(u128) * n);
+	uint64_t s = 0x1234567;
+	for (uint64_t i = 0; i < n; i++) {
+		s = s * 6364136223846793005ull + 1442695040888963407ull;
+		src[i] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+	}
+	u128 z = ((u128)0x2E895399AF449ACEull << 64) | 0x499596F6E5FCCAFAull;
+	double total = 0;
+	for (int r = -1; r < reps; r++) { /* r = -1: warm-up */
+		memcpy(buf, src, sizeof(u128) * n);
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		for (uint32_t v = log_n; v >= 1; v--) {
+			uint64_t half = (uint64_t)1 << (v - 1);
+			cpu_fold(buf, buf + half, half, (const u128u *)&z, half >= (1u << 13) ? n_threads : 1, use_gfni);
+			z = z * 3 + 1; /* a different challenge every round */
+		}
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (r >= 0) total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+	}
+	free(src);
+	free(buf);
+	return total;
+}
