@@ -307,6 +307,10 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_eq_ind_vals, FIELD_TABLE_BYTES);
 	SET(k_eq_scale, FIELD_TABLE_BYTES);
 	SET(k_fri_fold, FIELD_TABLE_BYTES);
+	SET(k_fri_lerp_k64<1>, 1 * LUT_BYTES + 6144 + NLUT_BYTES);
+	SET(k_fri_lerp_k64<2>, 2 * LUT_BYTES + 6144 + NLUT_BYTES);
+	SET(k_fri_lerp_k64<3>, 3 * LUT_BYTES + 6144 + NLUT_BYTES);
+	SET(k_fri_lerp_k64<4>, 3 * LUT_BYTES + 6144 + NLUT_BYTES);
 	SET(k_fri_fold_lut<1>, FIELD_TABLE_BYTES + 1 * NLUT_BYTES);
 	SET(k_fri_fold_lut<2>, FIELD_TABLE_BYTES + 2 * NLUT_BYTES);
 	SET(k_fri_fold_lut<3>, FIELD_TABLE_BYTES + 3 * NLUT_BYTES);
@@ -1261,8 +1265,21 @@ int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint
 	int32_t rc = stage_args(ctx, hc.data(), 16 * hc.size(), &dc);
 	if (rc) return rc;
 	FriArgs A{(const uint4 *)in, (uint4 *)out, n_out, log_len, log_batch, n_ch, (const uint4 *)dc, ntt->d_s_evals, ntt->d, ntt->kt};
+	if (eta == 0 && n_ch >= 1 && n_ch <= 4 && n_out >= 4096) {
+		// pure tensor-lerp fold (first FRI fold of the interleaved codeword): K64 tables per challenge
+		const uint32_t nk = std::min(n_ch, 3u), smem = nk * LUT_BYTES + 6144 + NLUT_BYTES;
+		uint32_t g = grid_for(ctx, n_out, FRI_K64_THREADS, 1);
+		switch (n_ch) {
+		case 1: k_fri_lerp_k64<1><<<g, FRI_K64_THREADS, smem, ctx->stream>>>(A); break;
+		case 2: k_fri_lerp_k64<2><<<g, FRI_K64_THREADS, smem, ctx->stream>>>(A); break;
+		case 3: k_fri_lerp_k64<3><<<g, FRI_K64_THREADS, smem, ctx->stream>>>(A); break;
+		default: k_fri_lerp_k64<4><<<g, FRI_K64_THREADS, smem, ctx->stream>>>(A); break;
+		}
+		B200_LAUNCH_CHECK(ctx);
+		return B200_OK;
+	}
 	// arities 1..5: register-resident chunk + nibble-LUT lerps (one 8 KiB table per challenge)
-	uint32_t grid = grid_for(ctx, n_out, 256, 1);
+	uint32_t grid = grid_for(ctx, n_out, 256, 2);
 	switch (n_ch) {
 	case 1: k_fri_fold_lut<1><<<grid, 256, FIELD_TABLE_BYTES + 1 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;
 	case 2: k_fri_fold_lut<2><<<grid, 256, FIELD_TABLE_BYTES + 2 * NLUT_BYTES, ctx->stream>>>(ctx->d_tables, A); break;

@@ -556,4 +556,41 @@ __global__ void __launch_bounds__(256) k_fri_fold_lut(const uint8_t *__restrict_
 	}
 }
 
+// fri_fold with eta = 0 (all NCH challenges are tensor-lerp rounds: the first fold of the interleaved
+// codeword, fri/prove.rs:343-386 with log_batch = arity): per output a binary lerp tree over 2^NCH
+// consecutive inputs.  Rounds 0..2 (8 + 4 + 2 of the 15 products at NCH = 4) use one Karatsuba-64 table
+// each (linmap.cuh), a fourth round the 8 KiB nibble table.  dyn smem = min(NCH,3)*LUT_BYTES + 6144 + NLUT_BYTES
+constexpr uint32_t FRI_K64_THREADS = 512;
+template <uint32_t NCH>
+__global__ void __launch_bounds__(FRI_K64_THREADS, 1) k_fri_lerp_k64(FriArgs A) {
+	extern __shared__ __align__(256) uint8_t smem[];
+	constexpr uint32_t NK = NCH < 3 ? NCH : 3;
+	uint2 *stage = reinterpret_cast<uint2 *>(smem + NK * LUT_BYTES);
+	uint8_t *nl = smem + NK * LUT_BYTES + 6144;
+	uint4 zs[NK];
+#pragma unroll
+	for (uint32_t t = 0; t < NK; t++) zs[t] = A.challenges[t];
+	k64_build_multi<NK>(smem, stage, zs);
+	if (NCH > 3) nlut_build_mul(nl, A.challenges[3]);
+	K64Lane L = k64_lane_init(smem);
+	const uint32_t sbase = L.sbase;
+	const NLutLane NL = nlut_lane_init();
+	constexpr uint32_t CHUNK = 1u << NCH;
+	for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < A.n_out; c += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 v[CHUNK];
+#pragma unroll
+		for (uint32_t i = 0; i < CHUNK; i++) v[i] = __ldg(A.in + c * CHUNK + i);
+#pragma unroll
+		for (uint32_t r = 0; r < NCH; r++) {
+			if (r < NK) L.sbase = sbase + r * LUT_BYTES;
+#pragma unroll
+			for (uint32_t o = 0; o < (CHUNK >> (r + 1)); o++) {
+				const uint4 x = v[2 * o] ^ v[2 * o + 1];
+				v[o] = v[2 * o] ^ (r < NK ? k64_apply(L, x) : nlut_apply(nl, NL, x));
+			}
+		}
+		A.out[c] = v[0];
+	}
+}
+
 }  // namespace b200

@@ -293,7 +293,8 @@ def test_fri_fold(hal, oracle):
     ntt = binius_b200.B200AdditiveNTT(hal, 5, 12)
     ontt = oracle.NTT(5, 12)
     rng = random.Random(5)
-    for log_len, log_batch, n_ch in [(6, 2, 2), (6, 0, 3), (5, 2, 5), (4, 3, 3), (3, 0, 0), (10, 4, 4), (12, 0, 4)]:
+    for log_len, log_batch, n_ch in [(6, 2, 2), (6, 0, 3), (5, 2, 5), (4, 3, 3), (3, 0, 0), (10, 4, 4), (12, 0, 4),
+                                     (12, 1, 1), (12, 2, 2), (13, 3, 3), (12, 4, 4)]:  # last four: K64 tensor-lerp kernel
         ch = [rng.getrandbits(128) for _ in range(n_ch)]
         data = oracle.rand_b128(log_len * 10 + n_ch, 1 << (log_len + log_batch))
         n_out = 1 << (log_len - (n_ch - log_batch))
@@ -402,3 +403,73 @@ def test_fold_right_ring_switch_shape(hal, oracle, lvl):
     dm, dv, do = hal.to_device(mat), hal.to_device(vec), hal.dev_alloc(n)
     hal.execute(lambda ex: (ex.fold_right(binius_b200.SubfieldSlice(dm, lvl), dv, do), [])[1])
     assert _same(hal.to_host(do), oracle.fold_right(mat, lvl, vec, n))
+
+
+def _xor_sum(arr) -> int:
+    a = np.asarray(arr, dtype=np.uint64).reshape(-1, 2)
+    lo, hi = np.bitwise_xor.reduce(a[:, 0]), np.bitwise_xor.reduce(a[:, 1])
+    return int(lo) | (int(hi) << 64)
+
+
+def test_fold_high_full_size_properties(hal, oracle):
+    """BASELINE metric size (2^24 input coefficients) through size-independent properties: slabs against
+    the oracle, and the XOR checksum  sum(out) = sum(e0) + z * (sum(e0) + sum(e1))  (multiplication by the
+    challenge is GF(2)-linear), plus the degenerate challenges 0 and 1."""
+    n = 1 << 23
+    rng = np.random.default_rng(2024)
+    e0 = rng.integers(0, 1 << 63, size=(n, 2), dtype=np.int64).astype(np.uint64) * np.uint64(2) + np.uint64(1)
+    e1 = rng.integers(0, 1 << 63, size=(n, 2), dtype=np.int64).astype(np.uint64) * np.uint64(3)
+    z = 0x2E895399AF449ACE499596F6E5FCCAFA
+    d0, d1 = hal.to_device(e0), hal.to_device(e1)
+    hal.execute(lambda ex: (ex.extrapolate_line(d0, d1, z), [])[1])
+    out = hal.to_host(d0)
+    for off in (0, 4096 * 777 + 3, n - 5000):
+        sl = slice(off, off + 4321)
+        assert _same(out[sl], oracle.extrapolate_line(e0[sl], e1[sl], z))
+    s0, s1 = _xor_sum(e0), _xor_sum(e1)
+    assert _xor_sum(out) == s0 ^ oracle.mul(s0 ^ s1, z)
+    assert _same(hal.to_host(d1), e1)
+    # z = 1 selects e1, z = 0 keeps e0
+    hal.execute(lambda ex: (ex.extrapolate_line(d0, d1, 1), [])[1])
+    assert _same(hal.to_host(d0), e1)
+    hal.copy_h2d(e0, d0)
+    hal.execute(lambda ex: (ex.extrapolate_line(d0, d1, 0), [])[1])
+    assert _same(hal.to_host(d0), e0)
+
+
+def test_fold_multilinears_large_truncated_both_orders(hal, oracle):
+    """2^20-variable-count-scale multilinears with ragged stored prefixes and constant suffixes through
+    the TMA fold kernels (tiles that end mid-warp, pivot inside a tile, empty second operand), both
+    evaluation orders, whole result against the oracle."""
+    import ctypes as C
+
+    n_vars = 18
+    full = 1 << n_vars
+    prefixes = [full, full - 1, full // 2 + 77, full // 2, full // 2 - 1, 64 * 1000 + 33, 65, 1]
+    suffixes = [0, 5, 1 << 100, 7, 0x1234, (1 << 128) - 1, 3, 9]
+    z = 0x0F1E2D3C4B5A69788796A5B4C3D2E1F1
+    host = [oracle.rand_b128(4000 + t, p) for t, p in enumerate(prefixes)]
+    m = len(host)
+    zs = (C.c_uint64 * 2)(z & (2**64 - 1), z >> 64)
+    sfx = (C.c_uint64 * (2 * m))(*[w for s in suffixes for w in (s & (2**64 - 1), s >> 64)])
+    lens = (C.c_uint64 * m)(*prefixes)
+    new_lens = (C.c_uint64 * m)()
+    # HighToLow, in place
+    dev = [hal.to_device(h) for h in host]
+    ptrs = (C.c_void_p * m)(*[d.ptr for d in dev])
+    hal._check(hal._lib.b200_fold_multilinears_high_to_low(hal._ctx, ptrs, m, n_vars, lens, sfx, zs, new_lens))
+    for t in range(m):
+        exp = oracle.fold_left_lerp_inplace(host[t], prefixes[t], suffixes[t], n_vars, z)
+        assert int(new_lens[t]) == len(exp)
+        assert _same(hal.to_host(dev[t].slice(0, len(exp))), exp), t
+    # LowToHigh, out of place
+    dev = [hal.to_device(h) for h in host]
+    outs = [hal.dev_alloc((p + 1) // 2) for p in prefixes]
+    ptrs = (C.c_void_p * m)(*[d.ptr for d in dev])
+    optrs = (C.c_void_p * m)(*[o.ptr for o in outs])
+    hal._check(hal._lib.b200_fold_multilinears_low_to_high(hal._ctx, ptrs, optrs, m, n_vars, lens, sfx, zs, new_lens))
+    for t in range(m):
+        exp = oracle.fold_right_lerp(host[t], suffixes[t], z)
+        assert int(new_lens[t]) == len(exp)
+        assert _same(hal.to_host(outs[t].slice(0, len(exp))), exp), t
+        assert _same(hal.to_host(dev[t]), host[t])  # inputs untouched

@@ -104,6 +104,8 @@ def main():
                     eq = be.fold_partial_eq_ind(v - 1, eq)
             t_fold += t.ms
             launches += t.launches
+            if os.environ.get("REPLAY_VERBOSE"):
+                print(f"zerocheck round n_vars={v}: fold {t.ms:.3f} ms, {t.launches} launches", file=sys.stderr)
         res["phases"]["zerocheck_rounds"] = {"round_evals_ms": t_ev, "fold_ms": t_fold, "ms": t_ev + t_fold, "launches": launches,
                                              "multilinears": m, "compositions": 75, "n_vars": nv}
 
@@ -122,6 +124,8 @@ def main():
                 hal.execute(lambda ex: list(ex.bivariate_round_evals(dml, v, pairs, alpha)))
             t_ev += t.ms
             launches += t.launches
+            if os.environ.get("REPLAY_VERBOSE"):
+                print(f"piop round n_vars={v}: evals {t.ms:.3f} ms, {t.launches} launches", file=sys.stderr)
             # the prover issues one extrapolate_line per multilinear inside one execute (v3/bivariate_product.rs:
             # 196-232); the library batches them into multi-segment launches.  One C-ABI call here keeps the
             # python call overhead (which a Rust host would not have) out of the device timing.
