@@ -331,6 +331,44 @@ def main():
                   "tensor_expand_k22": {"ms": te_ms, "elems_per_s": (1 << k) / (te_ms * 1e-3),
                                         "hbm_frac": (16 * (1 << k) / (te_ms * 1e-3)) / (peak * 1e9)}}
 
+    # ---- the remaining ComputeLayer ops of SURVEY.md 8a (rows a6, a7, a9, a10) at 2^22 B128 elements:
+    #      device time, algorithmic GB/s and fraction of the HBM peak
+    ops = None
+    if not args.no_ntt:
+        from binius_b200 import ArithCircuit as A, SlicesBatch, SubfieldSlice
+
+        n22 = 1 << 22
+        va, vb, vc = dev.slice(0, n22), dev.slice(n22, 2 * n22), dev.slice(2 * n22, 3 * n22)
+        small = dev.slice(3 * n22, 3 * n22 + 128)
+        ntt12 = binius_b200.B200AdditiveNTT(hal, 5, 24)
+        expr = hal.compile_expr(A.var(0) * A.var(1) + A.var(2))
+        obuf = hal.dev_alloc(2 * n22)  # outputs
+        red_outs = []
+        off = 0
+        for r in range(22):
+            red_outs.append(obuf.slice(off, off + (n22 >> (r + 1))))
+            off += n22 >> (r + 1)
+        chs = [rr.getrandbits(128) for _ in range(4)]
+
+        def timed(fn, alg_bytes, reps=5):
+            for _ in range(2):
+                hal.execute(fn)
+            ev.start()
+            for _ in range(reps):
+                hal.execute(fn)
+            ms = ev.stop_ms() / reps
+            return {"ms": ms, "gbs": alg_bytes / (ms * 1e-3) / 1e9, "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak}
+
+        ops = {
+            "inner_product_b128_2^22": timed(lambda ex: [ex.inner_product(SubfieldSlice(va, 7), vb)], 32 * n22),
+            "inner_product_b1_2^22": timed(lambda ex: [ex.inner_product(SubfieldSlice(dev.slice(0, n22 >> 7), 0), vb)], 16 * n22 + n22 // 8),
+            "fold_left_b1_q128_out2^22": timed(lambda ex: (ex.fold_left(SubfieldSlice(dev.slice(0, n22), 0), small, obuf.slice(0, n22)), [])[1], 16 * n22 + 16 * n22),
+            "fold_right_b1_q128_out2^22": timed(lambda ex: (ex.fold_right(SubfieldSlice(va, 0), small, obuf.slice(0, n22)), [])[1], 32 * n22),
+            "compute_composite_xy+z_2^22": timed(lambda ex: (ex.compute_composite(SlicesBatch([va, vb, vc], n22), obuf.slice(0, n22), expr), [])[1], 64 * n22),
+            "pairwise_product_reduce_2^22": timed(lambda ex: (ex.pairwise_product_reduce(va, red_outs), [])[1], 32 * n22),
+            "fri_fold_first_2^24_in_batch4": timed(lambda ex: (ex.fri_fold(ntt12, 20, 4, chs, dev.slice(0, 1 << 24), obuf.slice(0, 1 << 20)), [])[1], 16 * (1 << 24) + 16 * (1 << 20)),
+        }
+
     # ---- reduce over ranks: max time ----------------------------------------------------------------
     ms_step = ms_total / args.steps
     if world > 1:
@@ -358,6 +396,8 @@ def main():
             line["ntt"] = ntt_res
         if extras:
             line["sumcheck_round"] = extras
+        if ops:
+            line["ops"] = ops
         line["sumcheck_chain"] = chain
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_fold_baseline(args.log_coeffs)

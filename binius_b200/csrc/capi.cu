@@ -298,6 +298,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_inner_product, FIELD_TABLE_BYTES);
 	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
 	SET(k_fold_right_lut, LUT_BYTES + 2048);
+	SET(k_fold_left_b1_lut, LUT_BYTES + 2048);
 	SET(k_fold_mat<true>, FIELD_TABLE_BYTES);
 	SET(k_compute_composite, FIELD_TABLE_BYTES);
 	SET(k_sum_composition, FIELD_TABLE_BYTES);
@@ -743,6 +744,19 @@ int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t
 	int32_t rc = new_slot(ctx, slot);
 	if (rc) return rc;
 	if (n_b == 0) return B200_OK;
+	if (lvl == 7 && n_b >= 4096 && n_b % tc::CHUNK == 0) {
+		// B128 x B128: one inner-product job on the tensor cores (roundevals_tc.cuh)
+		// (the kernel works on job pairs: the two halves of the range form the pair when they stay chunk-aligned)
+		const bool split = (n_b / 2) % tc::CHUNK == 0;
+		const uint64_t len = split ? n_b / 2 : n_b;
+		std::vector<tc::TcJob> jobs(1, tc::TcJob{(const uint4 *)a, nullptr, (const uint4 *)b, nullptr});
+		std::vector<tc::TcTarget> targets(1, tc::TcTarget{0, *slot, make_uint4(1, 0, 0, 0)});
+		if (split) {
+			jobs.push_back(tc::TcJob{(const uint4 *)a + len, nullptr, (const uint4 *)b + len, nullptr});
+			targets.push_back(tc::TcTarget{1, *slot, make_uint4(1, 0, 0, 0)});
+		}
+		return launch_tc_pairs(ctx, jobs, len, targets);
+	}
 	k_inner_product<<<grid_for(ctx, n_b, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const uint4 *)a, lvl, (const uint4 *)b, n_b, ctx->d_results + *slot);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
@@ -761,6 +775,14 @@ static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_
 	if (n_out != expect_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output has %llu elements, expected %llu", (unsigned long long)n_out, (unsigned long long)expect_out);
 	if (right && (n_vec << lvl) == 128 && n_out >= 1024) {
 		k_fold_right_lut<<<grid_for(ctx, n_out, FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const uint4 *)mat, lvl, (const uint4 *)vec, (uint4 *)out, n_out);
+		B200_LAUNCH_CHECK(ctx);
+		return B200_OK;
+	}
+	if (!right && lvl == 0 && n_vec <= 128 && n_out >= 4096 && n_out % 128 == 0) {
+		// bit-packed matrix, short query: warp-transposed bit blocks + byte-LUT linear map
+		const uint64_t n_warps = n_out / 128;
+		uint32_t g = (uint32_t)std::min<uint64_t>((n_warps * 32 + FOLD_THREADS - 1) / FOLD_THREADS, (uint64_t)ctx->n_sms * 2);
+		k_fold_left_b1_lut<<<g, FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const uint4 *)mat, (const uint4 *)vec, (uint32_t)n_vec, (uint4 *)out, n_out);
 		B200_LAUNCH_CHECK(ctx);
 		return B200_OK;
 	}

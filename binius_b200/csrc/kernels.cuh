@@ -258,6 +258,54 @@ __global__ void __launch_bounds__(FOLD_THREADS, 2) k_fold_right_lut(const uint4 
 		out[i] = lut_apply(tbl, L, __ldg(mat + i));
 }
 
+// fold_left fast path for B1 matrices (the switchover / evaluate_partial_high of bit-packed columns,
+// math/src/fold.rs:358-516 are the reference's own B1 fast paths): with nq = vec.len() <= 128 and
+// n_out a multiple of 128,
+//     out[i] = sum_j vec[j] * bit(j * n_out + i)  =  L(c_i),   c_i = (bit(j * n_out + i))_j in {0,1}^128,
+// L the GF(2)-linear map with basis images vec[j].  A warp takes 128 consecutive outputs: lane l loads
+// the 128-bit words of rows j = l, l+32, l+64, l+96 (coalesced per row), the 128 x 128 bit block is
+// transposed across the warp (sixteen 32x32 shuffle-butterfly transposes), after which every lane
+// holds the vectors c_i of its 4 outputs and applies L with the byte-LUT engine (16 LDS.128 each)
+// instead of 128 predicated accumulations.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+	for (uint32_t s = 16; s >= 1; s >>= 1) {
+		const uint32_t m = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+		const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+		x = (lane & s) ? (((y >> s) & m) | (x & ~m)) : ((x & m) | ((y & m) << s));
+	}
+	return x;
+}
+__global__ void __launch_bounds__(FOLD_THREADS, 2) k_fold_left_b1_lut(const uint4 *__restrict__ mat, const uint4 *__restrict__ vec, uint32_t nq,
+																	  uint4 *__restrict__ out, uint64_t n_out) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *tbl = smem;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) stage[(i & 7) * 16 + (i >> 3)] = i < nq ? __ldg(vec + i) : u4_zero();
+	__syncthreads();
+	lut_build_images(tbl, stage);
+	const LutLane L = lut_lane_init();
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t words_per_row = n_out >> 7;  // 128-bit words per matrix row j
+	const uint64_t n_blocks = words_per_row, warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	for (uint64_t blk = (((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; blk < n_blocks; blk += warps) {
+		uint32_t w[4][4];  // [row block r][word c]
+#pragma unroll
+		for (uint32_t r = 0; r < 4; r++) {
+			const uint32_t j = 32 * r + lane;
+			uint4 v = j < nq ? __ldg(mat + j * words_per_row + blk) : u4_zero();
+			w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
+		}
+#pragma unroll
+		for (uint32_t r = 0; r < 4; r++)
+#pragma unroll
+			for (uint32_t c = 0; c < 4; c++) w[r][c] = warp_transpose32(w[r][c], lane);
+#pragma unroll
+		for (uint32_t c = 0; c < 4; c++)
+			out[blk * 128 + 32 * c + lane] = lut_apply(tbl, L, make_uint4(w[0][c], w[1][c], w[2][c], w[3][c]));
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // ArithCircuit interpreter (math/src/arith_expr.rs:367-383)
 constexpr uint32_t MAX_EXPR_STEPS = 64;

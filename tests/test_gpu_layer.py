@@ -473,3 +473,28 @@ def test_fold_multilinears_large_truncated_both_orders(hal, oracle):
         assert int(new_lens[t]) == len(exp)
         assert _same(hal.to_host(outs[t].slice(0, len(exp))), exp), t
         assert _same(hal.to_host(dev[t]), host[t])  # inputs untouched
+
+
+@pytest.mark.parametrize("log_q", [0, 3, 7])
+def test_fold_left_b1_fast_path(hal, oracle, log_q):
+    """evaluate_partial_high of a bit-packed (B1) multilinear by a short tensor query: the
+    warp-transposed byte-LUT kernel (n_out >= 4096, a multiple of 128) against the oracle's fold_left."""
+    import binius_b200
+
+    log_out = 13
+    n_mat = 1 << (log_out + log_q - 7)
+    mat, vec = oracle.rand_b128(800 + log_q, n_mat), oracle.rand_b128(810 + log_q, 1 << log_q)
+    dm, dv, do = hal.to_device(mat), hal.to_device(vec), hal.dev_alloc(1 << log_out)
+    hal.execute(lambda ex: (ex.fold_left(binius_b200.SubfieldSlice(dm, 0), dv, do), [])[1])
+    assert _same(hal.to_host(do), oracle.fold_left(mat, 0, vec, 1 << log_out))
+
+
+def test_inner_product_b128_large(hal, oracle):
+    """B128 x B128 inner products of >= 4096 elements run as tensor-core jobs (split in two halves)."""
+    import binius_b200
+
+    for n in (4096, 4096 + 64, 1 << 15):
+        a, b = oracle.rand_b128(820 + n % 7, n), oracle.rand_b128(830 + n % 5, n)
+        da, db = hal.to_device(a), hal.to_device(b)
+        got = hal.execute(lambda ex: [ex.inner_product(binius_b200.SubfieldSlice(da, 7), db)])
+        assert got == [oracle.inner_product(a, 7, b)]
