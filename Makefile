@@ -13,7 +13,7 @@ $(LIB): $(CSRC)/capi.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) incl
 oracle:
 	$(MAKE) -s -C oracle
 
-tests/cpp/conformance: tests/cpp/conformance.cpp binius_b200/host/compute_layer.hpp $(LIB) oracle
+tests/cpp/conformance: tests/cpp/conformance.cpp binius_b200/host/compute_layer.hpp binius_b200/host/computation_backend.hpp $(LIB) oracle
 	g++ -O1 -std=c++17 -o $@ tests/cpp/conformance.cpp -Lbinius_b200 -lbinius_b200 -Loracle -loracle \
 	    -Wl,-rpath,'$$ORIGIN/../../binius_b200' -Wl,-rpath,'$$ORIGIN/../../oracle'
 

@@ -1,0 +1,200 @@
+// computation_backend.hpp -- C++ host-side mirror of the reference's old HAL,
+// `binius_hal::ComputationBackend` (crates/hal/src/backend.rs:35-83), over the C ABI, for
+// device-resident multilinears.  Same names and argument meaning as the trait:
+//   tensor_product_full_query      backend.rs:42-45
+//   sumcheck_compute_round_evals   backend.rs:48-62  (sumcheck_round_calculation.rs:126-349)
+//   sumcheck_fold_multilinears     backend.rs:65-75  (sumcheck_folding.rs:37-262)
+//   evaluate_partial_high          backend.rs:78-82
+// plus fold_partial_eq_ind (core/src/protocols/sumcheck/prove/common.rs:13-73), which the provers
+// call next to the backend.  `SumcheckMultilinear` (hal/src/sumcheck_multilinear.rs:8-40) keeps both
+// variants; a Transparent multilinear is a packed sub-field multilinear on the device that is
+// partially evaluated by the tensor-query expansion (fold_left / fold_right at its tower level) per
+// round until its switchover round, then replaced by the Folded result.
+#pragma once
+#include <algorithm>
+#include <map>
+#include <memory>
+
+#include "compute_layer.hpp"
+
+namespace binius_b200 {
+
+enum class EvaluationOrder : uint32_t { LowToHigh = B200_LOW_TO_HIGH, HighToLow = B200_HIGH_TO_LOW };
+
+struct SumcheckMultilinear {
+	enum Kind { Transparent, Folded } kind = Folded;
+	// Folded { large_field_folded_evals, suffix_eval }: stored prefix, the rest equals suffix_eval
+	DevSlice evals;
+	F128 suffix_eval;
+	// Transparent { multilinear, switchover_round, const_suffix }: 2^n_vars scalars of tower level `tower_level`
+	uint32_t tower_level = 7, n_vars = 0, switchover_round = 0;
+	uint64_t suffix_len = 0;
+
+	static SumcheckMultilinear folded(DevSlice evals, F128 suffix = {}) {
+		SumcheckMultilinear m;
+		m.kind = Folded; m.evals = evals; m.suffix_eval = suffix;
+		return m;
+	}
+	static SumcheckMultilinear transparent(DevSlice packed, uint32_t tower_level, uint32_t n_vars, uint32_t switchover_round) {
+		SumcheckMultilinear m;
+		m.kind = Transparent; m.evals = packed; m.tower_level = tower_level; m.n_vars = n_vars; m.switchover_round = switchover_round;
+		return m;
+	}
+};
+
+// What reaches the backend of a SumcheckEvaluator: the composition (and its leading term, used at the
+// infinity point), the evaluation-point range, and whether sums are weighted by eq_ind_partial_eval().
+struct SumcheckEvaluator {
+	const ExprEval *composition = nullptr;
+	const ExprEval *composition_at_infinity = nullptr;
+	uint32_t first_point = 1, end_point = 2;  // eval_point_indices(): 1 = at 1, 2 = infinity, k >= 3 finite
+};
+
+class B200Backend {
+	B200Layer &l_;
+	DevSlice unit_{};
+
+	DevSlice one() {
+		if (!unit_.n) {
+			unit_ = l_.dev_alloc(1);
+			l_.fill(unit_, F128{1, 0});
+		}
+		return unit_;
+	}
+	DevSlice partial_eval(EvaluationOrder order, const SumcheckMultilinear &m, const DevSlice *tensor_query) {
+		DevSlice q = tensor_query ? *tensor_query : one();
+		const uint64_t n_scalars = 1ull << m.n_vars;
+		if (!q.n || n_scalars % q.n) throw InputValidation(1, "tensor query does not divide the multilinear");
+		DevSlice out = l_.dev_alloc(n_scalars / q.n);
+		auto fn = order == EvaluationOrder::HighToLow ? b200_fold_left : b200_fold_right;
+		l_.check(fn(l_.ctx(), m.evals.ptr, m.evals.n, m.tower_level, q.ptr, q.n, out.ptr, out.n));
+		return out;
+	}
+
+  public:
+	explicit B200Backend(B200Layer &l) : l_(l) {}
+
+	DevSlice tensor_product_full_query(const std::vector<F128> &query) {
+		DevSlice out = l_.dev_alloc(1ull << query.size());
+		l_.check(b200_tensor_product_full_query(l_.ctx(), (const uint64_t *)query.data(), (uint32_t)query.size(), out.ptr, out.n));
+		return out;
+	}
+
+	// RoundEvals per evaluator (values at its eval_point_indices()).  eq_ind_partial_evals = nullptr: regular evaluator.
+	std::vector<std::vector<F128>> sumcheck_compute_round_evals(EvaluationOrder order, uint32_t n_vars, const DevSlice *tensor_query,
+																const std::vector<SumcheckMultilinear> &multilinears,
+																const std::vector<SumcheckEvaluator> &evaluators, const DevSlice *eq_ind_partial_evals,
+																const std::vector<F128> &nontrivial_evaluation_points) {
+		if (n_vars == 0) throw InputValidation(1, "Computing round evaluations requires at least a single variable.");
+		uint32_t lo = ~0u, hi = 0;
+		for (auto &e : evaluators) { lo = std::min(lo, e.first_point); hi = std::max(hi, e.end_point); }
+		if (evaluators.empty() || lo >= hi) return std::vector<std::vector<F128>>(evaluators.size());
+		if (nontrivial_evaluation_points.size() != (hi > 3 ? hi - 3 : 0)) throw InputValidation(1, "IncorrectNontrivialEvalPointsLength");
+		if (eq_ind_partial_evals && eq_ind_partial_evals->n != (1ull << (n_vars - 1))) throw InputValidation(1, "eq_ind_partial_evals must have 2^(n_vars-1) elements");
+		std::vector<uint32_t> codes;
+		std::vector<F128> pts;
+		for (uint32_t c = lo; c < hi; c++) { codes.push_back(c); pts.push_back(c < 3 ? F128{} : nontrivial_evaluation_points[c - 3]); }
+		std::vector<DevSlice> temps;
+		std::vector<b200_dev_ptr> ptrs;
+		std::vector<uint64_t> lens;
+		std::vector<F128> sfx;
+		for (auto &m : multilinears) {
+			DevSlice v = m.evals;
+			F128 s = m.suffix_eval;
+			if (m.kind == SumcheckMultilinear::Transparent) {
+				v = partial_eval(order, m, tensor_query);
+				if (v.n != (1ull << n_vars)) throw InputValidation(1, "transparent multilinear does not match n_vars and the tensor query");
+				temps.push_back(v);
+				if (!m.suffix_len) s = F128{};
+			}
+			ptrs.push_back(v.ptr);
+			lens.push_back(std::min<uint64_t>(v.n, 1ull << n_vars));
+			sfx.push_back(s);
+		}
+		std::vector<const b200_expr *> comps, leads;
+		for (auto &e : evaluators) { comps.push_back(e.composition->raw()); leads.push_back(e.composition_at_infinity->raw()); }
+		uint32_t first = 0;
+		l_.check(b200_results_reset(l_.ctx()));
+		l_.check(b200_sumcheck_round_evals(l_.ctx(), (uint32_t)order, ptrs.data(), lens.data(), (const uint64_t *)sfx.data(), (uint32_t)ptrs.size(), n_vars,
+										   eq_ind_partial_evals ? eq_ind_partial_evals->ptr : nullptr, comps.data(), leads.data(), (uint32_t)comps.size(),
+										   codes.data(), (const uint64_t *)pts.data(), (uint32_t)codes.size(), &first));
+		const uint32_t total = (uint32_t)(comps.size() * codes.size());
+		std::vector<uint32_t> slots(total);
+		for (uint32_t i = 0; i < total; i++) slots[i] = first + i;
+		std::vector<F128> vals(total);
+		l_.check(b200_results_fetch(l_.ctx(), slots.data(), total, (uint64_t *)vals.data()));  // synchronises
+		for (auto &t : temps) l_.dev_free(t);
+		std::vector<std::vector<F128>> res;
+		for (size_t e = 0; e < evaluators.size(); e++) {
+			std::vector<F128> r;
+			for (uint32_t k = evaluators[e].first_point; k < evaluators[e].end_point; k++) r.push_back(vals[e * codes.size() + (k - lo)]);
+			res.push_back(r);
+		}
+		return res;
+	}
+
+	// returns any_transparent_left; `tensor_query` already includes `challenge` (prover_state.rs:161-181)
+	bool sumcheck_fold_multilinears(EvaluationOrder order, uint32_t n_vars, std::vector<SumcheckMultilinear> &multilinears, F128 challenge,
+									const DevSlice *tensor_query) {
+		bool any_transparent_left = false;
+		std::vector<SumcheckMultilinear *> folded;
+		for (auto &m : multilinears) {
+			if (m.kind == SumcheckMultilinear::Transparent) {
+				if (m.switchover_round == 0) {
+					if (!tensor_query) throw InputValidation(1, "tensor_query is required while a multilinear is transparent");
+					m = SumcheckMultilinear::folded(partial_eval(order, m, tensor_query), m.suffix_len ? m.suffix_eval : F128{});
+				} else {
+					m.switchover_round--;
+					any_transparent_left = true;
+				}
+			} else {
+				folded.push_back(&m);
+			}
+		}
+		if (folded.empty()) return any_transparent_left;
+		std::vector<b200_dev_ptr> ptrs, outs;
+		std::vector<uint64_t> prefix, new_lens(folded.size());
+		std::vector<F128> sfx;
+		std::vector<DevSlice> out_slices;
+		for (auto *m : folded) {
+			ptrs.push_back(m->evals.ptr);
+			prefix.push_back(std::min<uint64_t>(m->evals.n, 1ull << n_vars));
+			sfx.push_back(m->suffix_eval);
+		}
+		uint64_t z[2] = {challenge.lo, challenge.hi};
+		if (order == EvaluationOrder::HighToLow) {
+			l_.check(b200_fold_multilinears_high_to_low(l_.ctx(), ptrs.data(), (uint32_t)ptrs.size(), n_vars, prefix.data(), (const uint64_t *)sfx.data(), z, new_lens.data()));
+			for (size_t t = 0; t < folded.size(); t++) folded[t]->evals = folded[t]->evals.slice(0, new_lens[t]);
+		} else {
+			for (auto p : prefix) {
+				out_slices.push_back(l_.dev_alloc(std::max<uint64_t>((p + 1) / 2, 1)));
+				outs.push_back(out_slices.back().ptr);
+			}
+			l_.check(b200_fold_multilinears_low_to_high(l_.ctx(), ptrs.data(), outs.data(), (uint32_t)ptrs.size(), n_vars, prefix.data(), (const uint64_t *)sfx.data(), z, new_lens.data()));
+			for (size_t t = 0; t < folded.size(); t++) folded[t]->evals = out_slices[t].slice(0, new_lens[t]);
+		}
+		return any_transparent_left;
+	}
+
+	DevSlice evaluate_partial_high(DevSlice multilinear, DevSlice query_expansion) {
+		if (!query_expansion.n || multilinear.n % query_expansion.n) throw InputValidation(1, "query expansion must divide the multilinear");
+		DevSlice out = l_.dev_alloc(multilinear.n / query_expansion.n);
+		l_.check(b200_fold_left(l_.ctx(), multilinear.ptr, multilinear.n, 7, query_expansion.ptr, query_expansion.n, out.ptr, out.n));
+		return out;
+	}
+
+	DevSlice fold_partial_eq_ind(EvaluationOrder order, uint32_t n_vars, DevSlice eq_ind) {
+		if (n_vars == 0) return eq_ind;
+		if (order == EvaluationOrder::LowToHigh) {
+			DevSlice ones = l_.dev_alloc(2), out = l_.dev_alloc(1ull << (n_vars - 1));
+			l_.fill(ones, F128{1, 0});
+			l_.check(b200_fold_right(l_.ctx(), eq_ind.ptr, eq_ind.n, 7, ones.ptr, 2, out.ptr, out.n));
+			return out;
+		}
+		auto halves = eq_ind.split_half();
+		l_.check(b200_kernel_add(l_.ctx(), n_vars - 1, halves.first.ptr, halves.second.ptr, halves.first.ptr));
+		return halves.first;
+	}
+};
+
+}  // namespace binius_b200

@@ -121,6 +121,7 @@ class ExprEval {
 	ExprEval(ExprEval &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
 	~ExprEval() { if (h_) b200_expr_free(h_); }
 	uint32_t n_vars() const { return b200_expr_n_vars(h_); }
+	const b200_expr *raw() const { return h_; }
 };
 
 class B200KernelExec {

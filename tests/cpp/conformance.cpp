@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../binius_b200/host/compute_layer.hpp"
+#include "../../binius_b200/host/computation_backend.hpp"
 
 using namespace binius_b200;
 typedef unsigned __int128 u128;
@@ -17,6 +18,12 @@ int orc_bivariate_round_evals(const void *const *mls, uint32_t m, uint32_t n_var
 int orc_ntt_s_evals(uint32_t kt, uint32_t d, void *s);
 int orc_ntt_transform(int inverse, const void *s, uint32_t kt, uint32_t d, void *data, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip);
 void orc_mul(const void *a, const void *b, uint32_t k, void *out);
+typedef struct { uint32_t op, l; uint64_t r; uint64_t c_lo, c_hi; } orc_expr_step;
+int orc_sumcheck_round_evals(uint32_t order, const void *const *mls, const uint64_t *lens, const void *suffix, uint32_t m, uint32_t n_vars, const void *eq_ind,
+							 const orc_expr_step *const *comps, const uint32_t *comp_steps, const orc_expr_step *const *leads, const uint32_t *lead_steps,
+							 uint32_t n_comp, const uint32_t *codes, const void *points, uint32_t n_points, void *out);
+uint64_t orc_fold_left_lerp_inplace(void *evals, uint64_t prefix, const void *suffix, uint32_t log_n, const void *z);
+uint64_t orc_fold_right_lerp(const void *evals, uint64_t evals_size, const void *suffix, const void *z, void *out);
 }
 
 static uint64_t sm_state;
@@ -128,6 +135,55 @@ int main() {
 		bool threw = false;
 		try { ntt.forward_transform(a.data(), 5, a.size(), NTTShape{3, 11, 0}, 4, 2, 0); } catch (const NttError &e) { threw = e.code == B200_ERR_NTT_COSET; }
 		CHECK(threw);
+	}
+	// ComputationBackend mirror: a regular (unweighted) sumcheck over 3 folded multilinears, composition
+	// x*y + w at the points 1 and infinity, all rounds, in both evaluation orders, one truncated input
+	for (int ord = 0; ord < 2; ord++) {
+		const EvaluationOrder order = ord ? EvaluationOrder::HighToLow : EvaluationOrder::LowToHigh;
+		B200Backend be(hal);
+		const uint32_t n_vars = 9, m = 3;
+		const uint64_t plen[3] = {1u << n_vars, (1u << n_vars) - 5, 300};
+		F128 sfx[3] = {F128{}, rnd(90, 1)[0], F128{7, 0}};
+		std::vector<std::vector<F128>> h(m);
+		std::vector<SumcheckMultilinear> mls;
+		for (uint32_t t = 0; t < m; t++) {
+			h[t] = rnd(100 + t + 10 * ord, plen[t]);
+			DevSlice d = hal.dev_alloc(plen[t]);
+			hal.copy_h2d(h[t].data(), plen[t], d);
+			mls.push_back(SumcheckMultilinear::folded(d, sfx[t]));
+		}
+		ExprEval comp = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::mul(0, 1), ExprStep::var(2), ExprStep::add(2, 3)});
+		ExprEval lead = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::mul(0, 1)});
+		const orc_expr_step oc[5] = {{4, 0, 0, 0, 0}, {4, 1, 0, 0, 0}, {1, 0, 1, 0, 0}, {4, 2, 0, 0, 0}, {0, 2, 3, 0, 0}};
+		const orc_expr_step ol[3] = {{4, 0, 0, 0, 0}, {4, 1, 0, 0, 0}, {1, 0, 1, 0, 0}};
+		const orc_expr_step *pc[1] = {oc}, *pl[1] = {ol};
+		const uint32_t nc[1] = {5}, nl[1] = {3}, codes[2] = {1, 2};
+		F128 zero2[2] = {};
+		for (uint32_t rnd_i = 0; rnd_i < n_vars; rnd_i++) {
+			const uint32_t nv = n_vars - rnd_i;
+			SumcheckEvaluator ev{&comp, &lead, 1, 3};
+			auto got = be.sumcheck_compute_round_evals(order, nv, nullptr, mls, {ev}, nullptr, {});
+			const void *ptrs[3] = {h[0].data(), h[1].data(), h[2].data()};
+			uint64_t lens[3] = {h[0].size(), h[1].size(), h[2].size()};
+			F128 exp[2];
+			orc_sumcheck_round_evals((uint32_t)order, ptrs, lens, sfx, m, nv, nullptr, pc, nc, pl, nl, 1, codes, zero2, 2, exp);
+			CHECK(got.size() == 1 && got[0].size() == 2 && got[0][0] == exp[0] && got[0][1] == exp[1]);
+			F128 ch = rnd(500 + rnd_i, 1)[0];
+			CHECK(be.sumcheck_fold_multilinears(order, nv, mls, ch, nullptr) == false);
+			for (uint32_t t = 0; t < m; t++) {
+				if (ord) {
+					h[t].resize(orc_fold_left_lerp_inplace(h[t].data(), h[t].size(), &sfx[t], nv, &ch));
+				} else {
+					std::vector<F128> o((h[t].size() + 1) / 2 + 1);
+					o.resize(orc_fold_right_lerp(h[t].data(), h[t].size(), &sfx[t], &ch, o.data()));
+					h[t] = o;
+				}
+				CHECK(mls[t].evals.n == h[t].size());
+				std::vector<F128> back(h[t].size());
+				hal.copy_d2h(mls[t].evals, back.data(), back.size());
+				CHECK(memcmp(back.data(), h[t].data(), 16 * back.size()) == 0);
+			}
+		}
 	}
 	bool oom = false;
 	try { data.dev_alloc.alloc(1 << 20); } catch (const AllocError &) { oom = true; }

@@ -19,6 +19,6 @@ def test_cpp_conformance():
 
 def test_cpp_host_header_compiles():
     # CPU-only: the header is self-contained C++17 over the C ABI
-    src = '#include "binius_b200/host/compute_layer.hpp"\nint main() { return 0; }\n'
+    src = '#include "binius_b200/host/compute_layer.hpp"\n#include "binius_b200/host/computation_backend.hpp"\nint main() { return 0; }\n'
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", ROOT, "-"], input=src, text=True, capture_output=True, cwd=ROOT)
     assert r.returncode == 0, r.stderr
