@@ -26,7 +26,7 @@ struct b200_ctx {
 	cudaStream_t own_stream = nullptr;
 	// copy streams + events of the host-buffer pipeline (b200_extrapolate_line_host), created lazily
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-	cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_k[3] = {nullptr, nullptr, nullptr}, ev_out[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t ev_in[4] = {}, ev_k[4] = {}, ev_out[4] = {};
 	std::string err;
 	uint64_t launches = 0;
 	std::vector<b200_pending_lerp> pending;
