@@ -320,8 +320,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint32_t>, FIELD_TABLE_BYTES + 4 * 8192 + 4 * 8192);
 	SET(k_ntt_pass<uint16_t>, FIELD_TABLE_BYTES + 4 * 8192 + 2 * 8192);
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
-	SET(k_ntt_bs_pass, 4 * 1024 + 128 * 1024);
-	SET(k_ntt_bs_low, 152 * 1024 + 640);
+	SET(k_ntt_bs_pass, 36 * 1024 + 16 + 128 * 1024);
+	SET(k_ntt_bs_low, 184 * 1024 + 640 + 16);
 	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
 	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
 #undef SET
@@ -1143,7 +1143,7 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 		if (lx < 5 && lx + log_y >= 5) {
 			// kind 2: lowest pass on units of 32 consecutive scalars (intra-unit layers + up to Rt inter-unit)
 			uint32_t L0 = 5 - lx;
-			uint32_t Rt = std::min(10u, lx + log_y - 5);
+			uint32_t Rt = std::min(NTT_BS_LOG_TILE, lx + log_y - 5);
 			uint32_t n_intra = std::min(n_layers, L0);
 			uint32_t n_inter = std::min(n_layers - n_intra, Rt);
 			uint32_t rest = n_layers - n_intra - n_inter;
@@ -1154,13 +1154,13 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			plan.push_back(Pass{0, 0, log_y, n_layers, lx});  // transform smaller than one unit
 			i_lo = n_layers;
 		}
-		// tiles of 2^(R + log_cu) = 1024 units (128 KiB of shared memory): 512 butterfly-units per layer,
-		// two per thread, so no thread idles between the per-layer barriers
+		// tiles of 2^(R + log_cu) = 2^NTT_BS_LOG_TILE units: one butterfly-unit per thread and layer
+		const uint32_t LT = NTT_BS_LOG_TILE;
 		while (i_lo < n_layers) {
-			uint32_t log_cu = std::min(lx + i_lo - 5, 2u);
-			uint32_t R = std::min(n_layers - i_lo, 10 - log_cu);
+			uint32_t log_cu = std::min(lx + i_lo - 5, 1u);
+			uint32_t R = std::min(n_layers - i_lo, LT - log_cu);
 			if (n_layers - i_lo - R > 0 && n_layers - i_lo - R < 4) R = (n_layers - i_lo + 1) / 2;  // avoid a tiny last pass
-			log_cu = std::min(lx + i_lo - 5, 10 - R);  // short passes take wider tiles: always ~1024 units
+			log_cu = std::min(lx + i_lo - 5, LT - R);  // short passes take wider tiles: always 2^LT units
 			plan.push_back(Pass{1, i_lo, R, R, log_cu});
 			i_lo += R;
 		}
@@ -1200,7 +1200,7 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			L.out_sliced = out_sliced;
 			uint64_t n_blocks = 1ull << (lx + log_y - 5 - P.R);
 			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
-			uint32_t smem = (152u << P.R) + 640;
+			uint32_t smem = (184u << P.R) + 640 + 16;
 			k_ntt_bs_low<<<dim3((uint32_t)n_blocks, n_z), NTT_BS_THREADS, smem, ctx->stream>>>(L);
 			B200_LAUNCH_CHECK(ctx);
 			continue;
@@ -1222,7 +1222,7 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			B.out_sliced = out_sliced;
 			uint64_t n_blocks = 1ull << (log_y - (P.i_lo + P.R) + (lx + P.i_lo - 5 - P.log_c));
 			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
-			uint32_t smem = (4u << P.R) + (128u << (P.R + P.log_c));
+			uint32_t smem = (36u << P.R) + 16 + (128u << (P.R + P.log_c));
 			k_ntt_bs_pass<<<dim3((uint32_t)n_blocks, n_z), NTT_BS_THREADS, smem, ctx->stream>>>(B);
 			B200_LAUNCH_CHECK(ctx);
 			continue;

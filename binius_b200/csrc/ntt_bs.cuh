@@ -101,33 +101,83 @@ template <> struct BS<1> {
 	static __device__ __forceinline__ void mul(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&r)[1]) { r[0] = a[0] & b[0]; }
 };
 
+// The same circuit for a SCALAR second operand: b[i] in {0, 1} (bit i of a twiddle shared by the 32
+// bit-sliced lanes).  A leaf product a & (0 - b) is then the integer product a * b, which issues on the
+// FMA pipe (IMAD) instead of the ALU pipe that carries all the XORs: the kernel is ALU-pipe bound, and
+// this moves the 324 leaf ANDs of a T(32) off it (2 LOP3 + 4 IMAD per GF(4) product instead of 4 LOP3).
+template <int N> struct BSs {
+	static constexpr int H = N / 2;
+	static __device__ __forceinline__ void mul(const uint32_t (&a)[N], const uint32_t (&b)[N], uint32_t (&r)[N]) {
+		uint32_t a0[H], a1[H], b0[H], b1[H], sa[H], sb[H], z0[H], z2[H], m[H], al[H];
+#pragma unroll
+		for (int i = 0; i < H; i++) {
+			a0[i] = a[i]; a1[i] = a[H + i];
+			b0[i] = b[i]; b1[i] = b[H + i];
+			sa[i] = a0[i] ^ a1[i];
+			sb[i] = b0[i] ^ b1[i];
+		}
+		BSs<H>::mul(a0, b0, z0);
+		BSs<H>::mul(a1, b1, z2);
+		BSs<H>::mul(sa, sb, m);
+		BS<H>::alpha(z2, al);
+#pragma unroll
+		for (int i = 0; i < H; i++) {
+			uint32_t lo = z0[i] ^ z2[i];
+			r[i] = lo;
+			r[H + i] = m[i] ^ lo ^ al[i];
+		}
+	}
+};
+template <> struct BSs<2> {
+	static __device__ __forceinline__ void mul(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&r)[2]) {
+		const uint32_t p00 = a[0] * b[0], p11 = a[1] * b[1], p01 = a[0] * b[1], p10 = a[1] * b[0];
+		r[0] = p00 ^ p11;
+		r[1] = p01 ^ p10 ^ p11;
+	}
+};
+template <> struct BSs<1> {
+	static __device__ __forceinline__ void mul(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&r)[1]) { r[0] = a[0] * b[0]; }
+};
+
 // v (bit-sliced, 32 planes) times a scalar twiddle t: p = v * t.  Sub-field twiddles use the
 // limb-wise product (binary_field.rs:363-393): B32 x B16 = 2 x T(16), B32 x B8 = 4 x T(8).
+// `bits` = the twiddle expanded to one byte (0 / 1) per bit in shared memory: the operand words come
+// straight out of LDS.U8 (the LSU pipe idles in this kernel) instead of 2 ALU ops per bit.
 template <int N>
-__device__ __forceinline__ void bs_mul_limbs(const uint32_t (&v)[32], uint32_t t, uint32_t (&p)[32]) {
+__device__ __forceinline__ void bs_mul_limbs(const uint32_t (&v)[32], const uint8_t *bits, uint32_t (&p)[32]) {
 	uint32_t b[N];
 #pragma unroll
-	for (int i = 0; i < N; i++) b[i] = 0u - ((t >> i) & 1u);
+	for (int i = 0; i < N; i++) b[i] = bits[i];
 #pragma unroll
 	for (int l = 0; l < 32 / N; l++) {
 		uint32_t a[N], r[N];
 #pragma unroll
 		for (int i = 0; i < N; i++) a[i] = v[l * N + i];
-		BS<N>::mul(a, b, r);
+		BSs<N>::mul(a, b, r);
 #pragma unroll
 		for (int i = 0; i < N; i++) p[l * N + i] = r[i];
 	}
 }
 
-__device__ __forceinline__ void bs_mul_scalar(const uint32_t (&v)[32], uint32_t t, uint32_t (&p)[32]) {
-	if (t >> 16) bs_mul_limbs<32>(v, t, p);
-	else if (t >> 8) bs_mul_limbs<16>(v, t, p);
-	else if (t >> 1) bs_mul_limbs<8>(v, t, p);
+__device__ __forceinline__ void bs_mul_scalar(const uint32_t (&v)[32], uint32_t t, const uint8_t *bits, uint32_t (&p)[32]) {
+	if (t >> 16) bs_mul_limbs<32>(v, bits, p);
+	else if (t >> 8) bs_mul_limbs<16>(v, bits, p);
+	else if (t >> 1) bs_mul_limbs<8>(v, bits, p);
 	else {
 		uint32_t m = 0u - (t & 1u);
 #pragma unroll
 		for (int i = 0; i < 32; i++) p[i] = v[i] & m;
 	}
+}
+
+// t -> 32 bytes of 0 / 1 (8 words: nibble q of t spread over the bytes of word q)
+__device__ __forceinline__ void ntt_store_bits(uint8_t *dst, uint32_t t) {
+	uint4 lo, hi;
+	auto spread = [](uint32_t nib) { return ((nib & 0xFu) * 0x00204081u) & 0x01010101u; };
+	lo = make_uint4(spread(t), spread(t >> 4), spread(t >> 8), spread(t >> 12));
+	hi = make_uint4(spread(t >> 16), spread(t >> 20), spread(t >> 24), spread(t >> 28));
+	reinterpret_cast<uint4 *>(dst)[0] = lo;
+	reinterpret_cast<uint4 *>(dst)[1] = hi;
 }
 
 struct NttBsArgs {
@@ -144,13 +194,19 @@ struct NttBsArgs {
 	uint32_t in_sliced, out_sliced;
 };
 
-constexpr uint32_t NTT_BS_THREADS = 256;
+// Tiles of 2^NTT_BS_LOG_TILE = 256 units (32 KiB of planes) on 128 threads, two CTAs per SM (2 x 128 x 255
+// registers fill the register file): a pass has 8x more CTAs than CTA slots, so the last wave is nearly
+// full (1024-unit tiles on one CTA per SM lost 13.5% at 2^24 to a 3.46-wave grid), the global load/store
+// phases of one CTA overlap the butterflies of the other, and the per-layer barriers are decoupled.
+constexpr uint32_t NTT_BS_THREADS = 128;
+constexpr uint32_t NTT_BS_LOG_TILE = 8;
 
-// dyn smem = 4 * 2^R (twiddles) + 128 * 2^(R + log_cu) (bit-sliced tile, plane-major: tile[p * NU + unit])
-__global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_pass(const NttBsArgs A) {
+// dyn smem = 36 * 2^R (twiddles + their bit expansion) + 128 * 2^(R + log_cu) (bit-sliced tile, plane-major: tile[p * NU + unit])
+__global__ void __launch_bounds__(NTT_BS_THREADS, 4) k_ntt_bs_pass(const NttBsArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint32_t *tw = reinterpret_cast<uint32_t *>(smem);
-	uint32_t *tile = reinterpret_cast<uint32_t *>(smem + (4u << A.R));
+	uint8_t *twb = smem + (((4u << A.R) + 15u) & ~15u);  // [2^R][32] bit-expanded twiddles
+	uint32_t *tile = reinterpret_cast<uint32_t *>(twb + (32u << A.R));
 	const uint32_t R = A.R, i_hi = A.i_lo + R, log_cu = A.log_cu;
 	const uint32_t log_inner = A.log_x + A.i_lo;           // >= 5
 	const uint32_t log_chunks = log_inner - 5 - log_cu;    // chunks of 2^log_cu units along the inner axis
@@ -173,6 +229,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_pass(const NttBsAr
 		for (uint32_t b = 0; b < nb; b++)
 			if ((idx >> b) & 1) t ^= srow[b];
 		tw[e] = t;
+		ntt_store_bits(twb + e * 32, t);
 	}
 	// load + transpose
 	for (uint32_t uid = threadIdx.x; uid < NU; uid += blockDim.x) {
@@ -196,13 +253,15 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_pass(const NttBsAr
 			uint32_t c = bfi & ((1u << log_cu) - 1), q = bfi >> log_cu;
 			uint32_t kk = q & ((1u << li) - 1), jr = q >> li;
 			uint32_t r0 = (jr << (li + 1)) | kk, r1 = r0 | (1u << li);
-			uint32_t t = tw[(1u << (R - 1 - li)) + jr];
+			const uint32_t te = (1u << (R - 1 - li)) + jr;
+			const uint32_t t = tw[te];
+			const uint8_t *tb = twb + te * 32;
 			uint32_t iu = (r0 << log_cu) | c, iv = (r1 << log_cu) | c;
 			uint32_t v[32], p[32];
 #pragma unroll
 			for (int k = 0; k < 32; k++) v[k] = tile[k * NU + iv];
 			if (!A.inverse) {
-				bs_mul_scalar(v, t, p);
+				bs_mul_scalar(v, t, tb, p);
 #pragma unroll
 				for (int k = 0; k < 32; k++) {
 					uint32_t u = tile[k * NU + iu] ^ p[k];
@@ -215,7 +274,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_pass(const NttBsAr
 					v[k] ^= tile[k * NU + iu];
 					tile[k * NU + iv] = v[k];
 				}
-				bs_mul_scalar(v, t, p);
+				bs_mul_scalar(v, t, tb, p);
 #pragma unroll
 				for (int k = 0; k < 32; k++) tile[k * NU + iu] ^= p[k];
 			}
@@ -262,26 +321,28 @@ __device__ __forceinline__ uint32_t ntt_subset_sum(const uint32_t *srow, uint32_
 	return t;
 }
 
-// dyn smem = 4*2^Rt (inter twiddles) + 5*4*2^Rt (per-unit intra twiddles) + 5*32*4 (lane planes) + 128*2^Rt (tile)
-__global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_low(const NttBsLowArgs A) {
+// dyn smem = 4*2^Rt (inter twiddles) + 5*4*2^Rt (per-unit intra twiddles) + 5*32*4 (lane planes) + 32*2^Rt (bit-expanded twiddles) + 128*2^Rt (tile)
+__global__ void __launch_bounds__(NTT_BS_THREADS, 4) k_ntt_bs_low(const NttBsLowArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const uint32_t Rt = A.Rt, NU = 1u << Rt, L0 = 5 - A.log_x;
 	uint32_t *tw = reinterpret_cast<uint32_t *>(smem);            // [2^Rt] heap for inter-unit layers
 	uint32_t *thi = tw + NU;                                       // [5][2^Rt]
 	uint32_t *tl = thi + 5 * NU;                                   // [5][32] bit-sliced lane twiddles
-	uint32_t *tile = tl + 5 * 32;                                  // [32][NU]
+	uint8_t *twb = smem + ((24u * NU + 640u + 15u) & ~15u);        // [NU][32] bit-expanded inter-unit twiddles
+	uint32_t *tile = reinterpret_cast<uint32_t *>(twb + 32 * NU);  // [32][NU]
 	const uint64_t outer = blockIdx.x;                             // unit-index bits above the tile
 	uint32_t *base = A.data + ((uint64_t)blockIdx.y << (A.log_x + A.log_y)) + (outer << (Rt + 5));
 
 	for (uint32_t e = threadIdx.x + 1; e < NU; e += blockDim.x) {
 		uint32_t lvl_bits = 31 - __clz(e);
 		uint32_t li = Rt - 1 - lvl_bits;
-		if (li >= A.n_inter) { tw[e] = 0; continue; }
+		if (li >= A.n_inter) { tw[e] = 0; ntt_store_bits(twb + e * 32, 0); continue; }
 		uint32_t jr = e - (1u << lvl_bits);
 		uint32_t i = L0 + li;
 		uint64_t idx = (A.coset << (A.log_y - 1 - i)) | (outer << (Rt - li - 1)) | jr;
 		uint32_t row = A.row0 + i;
 		tw[e] = ntt_subset_sum(A.s_evals + row * 32, A.d - 1 - row, idx);
+		ntt_store_bits(twb + e * 32, tw[e]);
 	}
 	for (uint32_t e = threadIdx.x; e < A.n_intra * NU; e += blockDim.x) {
 		uint32_t i = e >> Rt, r = e & (NU - 1);
@@ -325,12 +386,14 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_low(const NttBsLow
 			for (uint32_t q = threadIdx.x; q < (NU >> 1); q += blockDim.x) {
 				uint32_t kk = q & ((1u << li) - 1), jr = q >> li;
 				uint32_t iu = (jr << (li + 1)) | kk, iv = iu | (1u << li);
-				uint32_t t = tw[(1u << (Rt - 1 - li)) + jr];
+				const uint32_t te = (1u << (Rt - 1 - li)) + jr;
+				const uint32_t t = tw[te];
+				const uint8_t *tb = twb + te * 32;
 				uint32_t v[32], p[32];
 #pragma unroll
 				for (int k = 0; k < 32; k++) v[k] = tile[k * NU + iv];
 				if (!A.inverse) {
-					bs_mul_scalar(v, t, p);
+					bs_mul_scalar(v, t, tb, p);
 #pragma unroll
 					for (int k = 0; k < 32; k++) {
 						uint32_t u = tile[k * NU + iu] ^ p[k];
@@ -343,7 +406,7 @@ __global__ void __launch_bounds__(NTT_BS_THREADS, 1) k_ntt_bs_low(const NttBsLow
 						v[k] ^= tile[k * NU + iu];
 						tile[k * NU + iv] = v[k];
 					}
-					bs_mul_scalar(v, t, p);
+					bs_mul_scalar(v, t, tb, p);
 #pragma unroll
 					for (int k = 0; k < 32; k++) tile[k * NU + iu] ^= p[k];
 				}
