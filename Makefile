@@ -5,7 +5,7 @@ NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -X
 CSRC := binius_b200/csrc
 LIB := binius_b200/libbinius_b200.so
 
-all: $(LIB) oracle tests/cpp/conformance
+all: $(LIB) oracle tests/cpp/conformance tools/keccak_replay_cpp
 
 $(LIB): $(CSRC)/capi.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) include/binius_b200.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/capi.cu
@@ -16,6 +16,9 @@ oracle:
 tests/cpp/conformance: tests/cpp/conformance.cpp binius_b200/host/compute_layer.hpp binius_b200/host/computation_backend.hpp $(LIB) oracle
 	g++ -O1 -std=c++17 -o $@ tests/cpp/conformance.cpp -Lbinius_b200 -lbinius_b200 -Loracle -loracle \
 	    -Wl,-rpath,'$$ORIGIN/../../binius_b200' -Wl,-rpath,'$$ORIGIN/../../oracle'
+
+tools/keccak_replay_cpp: tools/keccak_replay.cpp binius_b200/host/compute_layer.hpp binius_b200/host/computation_backend.hpp $(LIB)
+	g++ -O2 -std=c++17 -o $@ tools/keccak_replay.cpp -Lbinius_b200 -lbinius_b200 -Wl,-rpath,'$$ORIGIN/../binius_b200'
 
 clean:
 	rm -f $(LIB) oracle/liboracle.so tests/cpp/conformance

@@ -72,7 +72,43 @@ inline u128 invert(u128 a, int k) {
 	default: return Tw<7>::invert(a);
 	}
 }
-inline u128 mul128(u128 a, u128 b) { return Tw<7>::mul(a, b); }
+// Table-driven variant for hot host paths (batch-coefficient powers: one product per composition and
+// round): the 8-bit level comes from a 64 KiB product table built once from the bit-level recursion,
+// 81 lookups per B128 product (~0.2 us) instead of 3^7 bit products (~3.5 us).
+struct Tab8 {
+	uint8_t mul[65536], alpha[256];
+	Tab8() {
+		for (int a = 0; a < 256; a++) {
+			for (int b = a; b < 256; b++) mul[(a << 8) | b] = mul[(b << 8) | a] = (uint8_t)Tw<3>::mul((u128)a, (u128)b);
+			alpha[a] = (uint8_t)Tw<3>::mul_alpha((u128)a);
+		}
+	}
+};
+inline const Tab8 &tab8() {
+	static const Tab8 t;
+	return t;
+}
+template <int K>
+struct FastTw {
+	static constexpr int H = 1 << (K - 1);
+	static inline u128 mul_alpha(u128 a) {
+		u128 a0 = Tw<K>::lo(a), a1 = Tw<K>::hi(a);
+		return a1 | ((a0 ^ FastTw<K - 1>::mul_alpha(a1)) << H);
+	}
+	static inline u128 mul(u128 a, u128 b) {
+		u128 a0 = Tw<K>::lo(a), a1 = Tw<K>::hi(a), b0 = Tw<K>::lo(b), b1 = Tw<K>::hi(b);
+		u128 p0 = FastTw<K - 1>::mul(a0, b0);
+		u128 p2 = FastTw<K - 1>::mul(a1, b1);
+		u128 pm = FastTw<K - 1>::mul(a0 ^ a1, b0 ^ b1);
+		return (p0 ^ p2) | ((pm ^ p0 ^ p2 ^ FastTw<K - 1>::mul_alpha(p2)) << H);
+	}
+};
+template <>
+struct FastTw<3> {
+	static inline u128 mul_alpha(u128 a) { return tab8().alpha[(uint8_t)a]; }
+	static inline u128 mul(u128 a, u128 b) { return tab8().mul[((uint32_t)(uint8_t)a << 8) | (uint8_t)b]; }
+};
+inline u128 mul128(u128 a, u128 b) { return FastTw<7>::mul(a, b); }
 inline u128 from_words(const uint64_t w[2]) { return ((u128)w[1] << 64) | w[0]; }
 
 }  // namespace hostf

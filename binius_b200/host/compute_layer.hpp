@@ -298,6 +298,7 @@ class B200Ntt {
 	B200Ntt(const B200Ntt &) = delete;
 	~B200Ntt() { b200_ntt_destroy(h_); }
 	uint32_t log_domain_size() const { return b200_ntt_log_domain_size(h_); }
+	const b200_ntt *raw() const { return h_; }
 	F128 get_subspace_eval(uint32_t i, uint64_t j) const {
 		F128 o;
 		if (b200_ntt_get_subspace_eval(h_, i, j, &o.lo)) throw InputValidation(1, "get_subspace_eval out of range");

@@ -1,0 +1,177 @@
+// keccak_replay.cpp -- the op-sequence replay of tools/keccak_replay.py driven from COMPILED host code
+// (binius_b200/host/*.hpp over the C ABI), so that the per-call host time is that of a compiled prover
+// (the reference host is Rust) and not of the Python mirror.  Same shapes, same phases, synthetic data.
+//   g++ -O2 -std=c++17 -o tools/keccak_replay_cpp tools/keccak_replay.cpp -Lbinius_b200 -lbinius_b200 -Wl,-rpath,'$ORIGIN/../binius_b200'
+//   tools/keccak_replay_cpp [log_n_permutations = 18]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../binius_b200/host/computation_backend.hpp"
+
+using namespace binius_b200;
+
+static uint64_t sm_state = 1;
+static uint64_t splitmix() {
+	uint64_t z = (sm_state += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+static F128 rnd() { return F128{splitmix(), splitmix()}; }
+
+struct Timer {
+	B200Layer &hal;
+	void *a = nullptr, *b = nullptr;
+	uint64_t l0 = 0;
+	explicit Timer(B200Layer &h) : hal(h) {
+		hal.check(b200_event_create(hal.ctx(), &a));
+		hal.check(b200_event_create(hal.ctx(), &b));
+	}
+	void start() {
+		hal.check(b200_sync(hal.ctx()));
+		l0 = b200_ctx_launch_count(hal.ctx());
+		hal.check(b200_event_record(hal.ctx(), a));
+	}
+	double stop(uint64_t *launches = nullptr) {
+		hal.check(b200_event_record(hal.ctx(), b));
+		float ms = 0;
+		hal.check(b200_event_elapsed_ms(hal.ctx(), a, b, &ms));
+		if (launches) *launches += b200_ctx_launch_count(hal.ctx()) - l0;
+		return ms;
+	}
+};
+
+int main(int argc, char **argv) {
+	const uint32_t log_n = argc > 1 ? (uint32_t)atoi(argv[1]) : 18;
+	const uint32_t nv = log_n + 2;
+	B200Layer hal(0);
+	B200Backend be(hal);
+	const uint64_t n_code = 1ull << (log_n + 10);
+	const uint64_t arena_elems = std::max<uint64_t>(n_code, 200ull << nv);
+	DevSlice arena = hal.dev_alloc(arena_elems);
+	hal.fill(arena, F128{0xFEDCBA9876543211ull, 0x0123456789ABCDEFull});
+	Timer t(hal);
+	double ntt_ms = 0, zc_ev = 0, zc_fold = 0, pi_ev = 0, pi_fold = 0, fri_ms = 0, rs_ms = 0;
+	uint64_t launches = 0;
+	for (int pass = 0; pass < 2; pass++) {  // pass 0 warms the context, pass 1 is reported
+		ntt_ms = zc_ev = zc_fold = pi_ev = pi_fold = fri_ms = rs_ms = 0;
+		launches = 0;
+		// ---- commit: RS-encode NTT (log_x = 6, log_y = log_n + 6, skip 1) on the device codeword
+		{
+			B200Ntt ntt(hal, 5, log_n + 6);
+			t.start();
+			hal.check(b200_ntt_forward(hal.ctx(), ntt.raw(), arena.ptr, 5, n_code * 4, 6, log_n + 6, 0, 0, 0, 1));
+			ntt_ms = t.stop(&launches);
+		}
+		// ---- zerocheck multilinear rounds: 153 multilinears, 75 chi constraints out - (b0 + (b1 - 1) * b2)
+		{
+			const uint32_t m = 153;
+			std::vector<SumcheckMultilinear> mls;
+			for (uint32_t i = 0; i < m; i++) mls.push_back(SumcheckMultilinear::folded(arena.slice((uint64_t)i << nv, (uint64_t)(i + 1) << nv)));
+			std::vector<ExprEval> comps, leads;
+			for (uint32_t c = 0; c < 75; c++) {
+				const uint32_t o = c, b0 = 75 + (c % 26), b1 = 75 + ((c + 1) % 26), b2 = 75 + ((c + 2) % 26);
+				// steps: 0 out, 1 b0, 2 b1, 3 one, 4 b1+1, 5 b2, 6 (b1+1)*b2, 7 b0+.., 8 out+..
+				comps.push_back(hal.compile_expr({ExprStep::var(o), ExprStep::var(b0), ExprStep::var(b1), ExprStep::constant(F128{1, 0}), ExprStep::add(2, 3),
+												  ExprStep::var(b2), ExprStep::mul(4, 5), ExprStep::add(1, 6), ExprStep::add(0, 7)}));
+				leads.push_back(hal.compile_expr({ExprStep::var(b1), ExprStep::var(b2), ExprStep::mul(0, 1)}));  // leading term b1*b2
+			}
+			std::vector<F128> q(nv - 1);
+			for (auto &x : q) x = rnd();
+			DevSlice eq = be.tensor_product_full_query(q);
+			for (uint32_t rnd_i = 0; rnd_i < nv; rnd_i++) {
+				const uint32_t v = nv - rnd_i;
+				std::vector<SumcheckEvaluator> evs;
+				for (uint32_t c = 0; c < 75; c++) evs.push_back(SumcheckEvaluator{&comps[c], &leads[c], rnd_i == 0 ? 2u : 1u, 3u});
+				t.start();
+				be.sumcheck_compute_round_evals(EvaluationOrder::HighToLow, v, nullptr, mls, evs, &eq, {});
+				zc_ev += t.stop(&launches);
+				t.start();
+				be.sumcheck_fold_multilinears(EvaluationOrder::HighToLow, v, mls, rnd(), nullptr);
+				if (v > 1) eq = be.fold_partial_eq_ind(EvaluationOrder::HighToLow, v - 1, eq);
+				zc_fold += t.stop(&launches);
+			}
+		}
+		// ---- PIOP bivariate sumcheck: 200 multilinears, 100 pairs
+		{
+			hal.fill(arena, F128{0x8796A5B4C3D2E1F1ull, 0x0F1E2D3C4B5A6978ull});
+			const uint32_t m = 200;
+			std::vector<SumcheckMultilinear> mls;
+			for (uint32_t i = 0; i < m; i++) mls.push_back(SumcheckMultilinear::folded(arena.slice((uint64_t)i << nv, (uint64_t)(i + 1) << nv)));
+			std::vector<uint32_t> ia(100), ib(100);
+			for (uint32_t i = 0; i < 100; i++) { ia[i] = i; ib[i] = 100 + i; }
+			for (uint32_t rnd_i = 0; rnd_i < nv; rnd_i++) {
+				const uint32_t v = nv - rnd_i;
+				std::vector<b200_dev_ptr> ptrs;
+				for (auto &x : mls) ptrs.push_back(x.evals.ptr);
+				F128 alpha = rnd();
+				uint32_t s1, s2;
+				t.start();
+				hal.check(b200_results_reset(hal.ctx()));
+				hal.check(b200_bivariate_round_evals(hal.ctx(), ptrs.data(), m, v, ia.data(), ib.data(), 100, &alpha.lo, &s1, &s2));
+				uint32_t slots[2] = {s1, s2};
+				F128 out[2];
+				hal.check(b200_results_fetch(hal.ctx(), slots, 2, &out[0].lo));
+				pi_ev += t.stop(&launches);
+				t.start();
+				be.sumcheck_fold_multilinears(EvaluationOrder::HighToLow, v, mls, rnd(), nullptr);
+				pi_fold += t.stop(&launches);
+			}
+		}
+		// ---- FRI folds: first fold of the interleaved codeword (log_batch 4), then arity-4 folds down to 2^12
+		{
+			B200Ntt fri_ntt(hal, 5, std::min(32u, log_n + 10));
+			uint32_t cur_log = log_n + 6;
+			std::vector<F128> ch(4);
+			for (auto &x : ch) x = rnd();
+			DevSlice out = hal.dev_alloc(1ull << cur_log);
+			t.start();
+			hal.check(b200_fri_fold(hal.ctx(), fri_ntt.raw(), cur_log, 4, &ch[0].lo, 4, arena.ptr, n_code, out.ptr, out.n));
+			fri_ms += t.stop(&launches);
+			DevSlice src = out;
+			std::vector<DevSlice> tmp{out};
+			while (cur_log >= 16) {
+				DevSlice dst = hal.dev_alloc(1ull << (cur_log - 4));
+				tmp.push_back(dst);
+				for (auto &x : ch) x = rnd();
+				t.start();
+				hal.check(b200_fri_fold(hal.ctx(), fri_ntt.raw(), cur_log, 0, &ch[0].lo, 4, src.ptr, src.n, dst.ptr, dst.n));
+				fri_ms += t.stop(&launches);
+				src = dst;
+				cur_log -= 4;
+			}
+			hal.check(b200_sync(hal.ctx()));
+			for (auto &d : tmp) hal.dev_free(d);
+		}
+		// ---- ring switch: 8 x (tensor_expand k = nv, fold_right with 128 row-batch coefficients over B1)
+		{
+			std::vector<F128> qv(128);
+			for (auto &x : qv) x = rnd();
+			DevSlice q = hal.dev_alloc(128);
+			hal.copy_h2d(qv.data(), 128, q);
+			DevSlice mle = hal.dev_alloc(1ull << nv);
+			for (int claim = 0; claim < 8; claim++) {
+				DevSlice buf = arena.slice((uint64_t)claim << nv, (uint64_t)(claim + 1) << nv);
+				hal.fill(buf.slice(0, 1), F128{1, 0});
+				std::vector<F128> coords(nv);
+				for (auto &x : coords) x = rnd();
+				t.start();
+				hal.check(b200_tensor_expand(hal.ctx(), buf.ptr, buf.n, 0, &coords[0].lo, nv));
+				hal.check(b200_fold_right(hal.ctx(), buf.ptr, buf.n, 0, q.ptr, 128, mle.ptr, mle.n));
+				rs_ms += t.stop(&launches);
+			}
+			hal.check(b200_sync(hal.ctx()));
+			hal.dev_free(mle);
+			hal.dev_free(q);
+		}
+	}
+	const double total = ntt_ms + zc_ev + zc_fold + pi_ev + pi_fold + fri_ms + rs_ms;
+	printf("{\"workload\": \"keccak op-sequence replay (compiled host), n_permutations = 2^%u (synthetic data)\", \"phases\": {"
+		   "\"commit_rs_encode_ntt\": {\"ms\": %.3f}, \"zerocheck_rounds\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, "
+		   "\"piop_bivariate_sumcheck\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, \"fri_folds\": {\"ms\": %.3f}, "
+		   "\"ring_switch_eq_inds\": {\"ms\": %.3f}}, \"total_ms\": %.3f, \"gpu_launches\": %llu}\n",
+		   log_n, ntt_ms, zc_ev, zc_fold, zc_ev + zc_fold, pi_ev, pi_fold, pi_ev + pi_fold, fri_ms, rs_ms, total, (unsigned long long)launches);
+	return 0;
+}
