@@ -54,6 +54,26 @@ def profiled_traffic(kernel="k_lerp_tma"):
         return None
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank (and therefore the pinned host buffers it first-touches) to the CPUs next to its GPU,
+    so that at N > 1 the host<->device copies of the e2e path do not cross the socket interconnect."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1 and 64 * w + b < n_cpu}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -92,7 +112,8 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region + 0.6 s of the same kernel back to back"}
 
 
 class Ev:
@@ -168,6 +189,8 @@ def main():
     from binius_b200 import NTTShape
 
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hal = binius_b200.B200Layer(local_rank)
@@ -213,6 +236,15 @@ def main():
     barrier()
     t1 = time.time()
     launches = hal.launch_count() - l0
+
+    # the timed region lasts ~1.5 ms, shorter than nvidia-smi's 100 ms sampling period: keep the same kernel
+    # running back to back for 0.6 s so that the clock / throttle-reason samples are taken under this load
+    tp0 = time.time()
+    while time.time() - tp0 < 0.6:
+        for _ in range(200):
+            fold_step()
+        hal.sync()
+    t1 = time.time()
 
     # per-launch duration of the dominant kernel (k_lerp_tma), CUDA events around single launches
     kern_ms = []
@@ -384,7 +416,8 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u128 (GF(2^128) tower, integer/bitwise)", "data": "synthetic",
             "config": {"workload": f"fold-high (extrapolate_line) over BinaryField128b, 2^{args.log_coeffs} coefficients per GPU",
-                       "l2_policy": "inputs (256 MiB) larger than L2; no flush", "parallelism": f"independent multilinears x{world}"},
+                       "l2_policy": "inputs (256 MiB) larger than L2; no flush", "parallelism": f"independent multilinears x{world}",
+                       "host_cpus_bound_per_rank": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * n_in / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_in * 16, "d2h_bytes_per_step": half * 16,
                     "ms_per_step": e2e_ms},
@@ -400,6 +433,7 @@ def main():
             line["ops"] = ops
         line["sumcheck_chain"] = chain
         if not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core
             line["cpu_baseline"] = cpu_fold_baseline(args.log_coeffs)
             from oracle import binding as orc
 
