@@ -74,6 +74,45 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
+class NvmlClocks:
+    """In-process NVML reads (~0.1 ms each): the timed region of the fold bench lasts ~1.5 ms, shorter than
+    nvidia-smi's sampling period, so the clocks and throttle reasons are read by the host thread WHILE the
+    queued steps execute (after submission, before the synchronising event read)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
+
+    def __init__(self, gpu_index):
+        self.h = None
+        self.sm, self.reasons = [], set()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def sample(self, n=1):
+        if self.h is None:
+            return
+        for _ in range(n):
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                return
+
+    def result(self):
+        if self.h is None or not self.sm:
+            return None
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "window": "NVML reads by the host thread while the timed steps execute"}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -113,7 +152,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "window": "timed region + 0.6 s of the same kernel back to back"}
+                "window": "nvidia-smi -lms 100 around the timed region"}
 
 
 class Ev:
@@ -127,6 +166,14 @@ class Ev:
 
     def start(self):
         self.hal._check(self.hal._lib.b200_event_record(self.hal._ctx, self.a))
+
+    def record_stop(self):
+        self.hal._check(self.hal._lib.b200_event_record(self.hal._ctx, self.b))
+
+    def elapsed_ms(self):
+        ms = C.c_float()
+        self.hal._check(self.hal._lib.b200_event_elapsed_ms(self.hal._ctx, self.a, self.b, C.byref(ms)))
+        return float(ms.value)
 
     def stop_ms(self):
         self.hal._check(self.hal._lib.b200_event_record(self.hal._ctx, self.b))
@@ -229,22 +276,16 @@ def main():
     barrier()
     l0 = hal.launch_count()
     t0 = time.time()
+    nvml = NvmlClocks(local_rank)
     ev.start()
     for _ in range(args.steps):
         fold_step()
-    ms_total = ev.stop_ms()
+    ev.record_stop()
+    nvml.sample(6)  # the queued steps are executing now
+    ms_total = ev.elapsed_ms()
     barrier()
     t1 = time.time()
     launches = hal.launch_count() - l0
-
-    # the timed region lasts ~1.5 ms, shorter than nvidia-smi's 100 ms sampling period: keep the same kernel
-    # running back to back for 0.6 s so that the clock / throttle-reason samples are taken under this load
-    tp0 = time.time()
-    while time.time() - tp0 < 0.6:
-        for _ in range(200):
-            fold_step()
-        hal.sync()
-    t1 = time.time()
 
     # per-launch duration of the dominant kernel (k_lerp_tma), CUDA events around single launches
     kern_ms = []
@@ -268,6 +309,8 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
     clocks = sampler.stop(t0, t1)
+    if nvml.result() is not None:
+        clocks = dict(nvml.result(), nvidia_smi=clocks)
 
     # ---- sumcheck chain: what the prover does with one multilinear over a whole sumcheck -- upload once,
     #      fold-high log_coeffs times (2^24, 2^23, ..., 2 coefficients, a fresh challenge per round), read the
