@@ -210,7 +210,11 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 			}
 	}
 	if (targets.empty()) return B200_OK;  // all compositions vanish identically: slots stay zero
-	const uint64_t n_scale = scales.size();
+	// regular (unweighted) evaluator: E is the all-ones vector, so a "scaled" vector is the operand itself
+	// (code 1) or hi + lo (code 2, formed by the job's second pointer) and no product kernel runs
+	const bool weighted = eq_ind != nullptr;
+	if (!weighted) need_ones = true;
+	const uint64_t n_scale = weighted ? scales.size() : 0;
 	const uint64_t off_ones = n_scale * half * 16, off_g = off_ones + (need_ones ? half * 16 : 0);
 	int32_t rc = ensure_scratch(ctx, off_g + (uint64_t)(ajobs.size() + 1) * 512 * 4);
 	if (rc) return rc;
@@ -236,8 +240,17 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 	for (size_t j = 0; j < ajobs.size(); j++) {
 		const AJob &a = ajobs[j];
 		const uint4 *y = a.y < 0 ? nullptr : (const uint4 *)mls[a.y];
-		jobs[j] = tc::TcJob{a.scaled < 0 ? (const uint4 *)eq_ind : base + (uint64_t)a.scaled * half, nullptr, y ? y + half : ones,
-							(y && a.code == 2) ? y : nullptr};
+		const uint4 *a0, *a1 = nullptr;
+		if (a.scaled < 0) {
+			a0 = weighted ? (const uint4 *)eq_ind : ones;
+		} else if (weighted) {
+			a0 = base + (uint64_t)a.scaled * half;
+		} else {
+			const uint4 *x = (const uint4 *)mls[scales[a.scaled].x];
+			a0 = x + half;
+			a1 = a.code == 2 ? x : nullptr;
+		}
+		jobs[j] = tc::TcJob{a0, a1, y ? y + half : ones, (y && a.code == 2) ? y : nullptr};
 	}
 	return launch_tc_pairs(ctx, jobs, half, targets, off_g);
 }
@@ -1008,7 +1021,7 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 	}
 	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
 	const uint64_t half = 1ull << (n_vars - 1);
-	if (tc_mode >= 1 && tc_mode != 2 && half >= 4096 && half % tc::CHUNK == 0 && eq_ind && order == B200_HIGH_TO_LOW) {
+	if (tc_mode >= 1 && tc_mode != 2 && half >= 4096 && half % tc::CHUNK == 0 && order == B200_HIGH_TO_LOW) {
 		// points 1 / infinity only, full-length multilinears, degree <= 2: monomial plan, no interpreter
 		bool ok = true;
 		for (uint32_t t = 0; t < m && ok; t++) ok = hlen[t] == 2 * half;

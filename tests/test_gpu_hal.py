@@ -287,3 +287,31 @@ def test_transparent_multilinears_switchover(hal, oracle, order_name, lvl):
             assert isinstance(d, FoldedMultilinear) == (t <= rnd or t == 3)
             if isinstance(d, FoldedMultilinear):
                 assert _same(hal.to_host(d.evals), h)
+
+
+def test_regular_evaluator_monomial_plan(hal, oracle):
+    """RegularSumcheckEvaluator (no eq-indicator weighting) on large HighToLow rounds takes the monomial
+    plan with the all-ones vector in place of E: shared variables, a square, constants, a linear and an
+    identically-zero composition; against the brute-force oracle, a few rounds."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, FoldedMultilinear, RegularSumcheckEvaluator
+
+    be = B200Backend(hal)
+    n_vars, m = 14, 6
+    rng = random.Random(123)
+    v = [A.var(i) for i in range(m)]
+    comps = [v[0] * v[1] + v[2], v[3] * v[3] + A.constant(rng.getrandbits(128)) * v[4] * v[5] + A.constant(rng.getrandbits(128)),
+             v[0] + v[5] + A.one(), v[1] * v[2] + v[2] * v[1], (v[0] + v[1]) * (v[2] + A.one())]
+    mls_h = [oracle.rand_b128(1500 + t, 1 << n_vars) for t in range(m)]
+    mls = [FoldedMultilinear(hal.to_device(x), 0) for x in mls_h]
+    for rnd in range(3):
+        nv = n_vars - rnd
+        evs = [RegularSumcheckEvaluator(c) for c in comps]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, None, [])
+        exp = oracle.sumcheck_round_evals(1, mls_h, [len(x) for x in mls_h], [0] * m, nv, None, [c.steps for c in comps],
+                                          [c.leading_term().steps for c in comps], [1, 2], [0, 0])
+        for ev, g, e in zip(evs, got, exp):
+            assert g == [e[k - 1] for k in ev.eval_point_indices()]
+        ch = rng.getrandbits(128)
+        be.sumcheck_fold_multilinears(nv, mls, ch)
+        mls_h = [oracle.fold_left_lerp_inplace(x, len(x), 0, nv, ch) for x in mls_h]
