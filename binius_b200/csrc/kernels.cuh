@@ -608,6 +608,12 @@ __global__ void __launch_bounds__(256) k_fri_fold_lut(const uint8_t *__restrict_
 // codeword, fri/prove.rs:343-386 with log_batch = arity): per output a binary lerp tree over 2^NCH
 // consecutive inputs.  Rounds 0..2 (8 + 4 + 2 of the 15 products at NCH = 4) use one Karatsuba-64 table
 // each (linmap.cuh), a fourth round the 8 KiB nibble table.  dyn smem = min(NCH,3)*LUT_BYTES + 6144 + NLUT_BYTES
+//
+// A warp owns 32 consecutive outputs = 32 * 2^NCH consecutive inputs and reads them COALESCED: lane l
+// loads elements j*32 + l.  The lerp tree then runs across lanes: in round r the two children of a node
+// sit in lanes that differ in bit r, so lanes exchange one value per product with __shfl_xor (the lane
+// with bit r = 0 finishes the node of register 2q, its partner the node of register 2q+1) and every lane
+// does the same number of products in every round.  After NCH rounds lane l holds one output.
 constexpr uint32_t FRI_K64_THREADS = 512;
 template <uint32_t NCH>
 __global__ void __launch_bounds__(FRI_K64_THREADS, 1) k_fri_lerp_k64(FriArgs A) {
@@ -624,20 +630,36 @@ __global__ void __launch_bounds__(FRI_K64_THREADS, 1) k_fri_lerp_k64(FriArgs A) 
 	const uint32_t sbase = L.sbase;
 	const NLutLane NL = nlut_lane_init();
 	constexpr uint32_t CHUNK = 1u << NCH;
-	for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < A.n_out; c += (uint64_t)gridDim.x * blockDim.x) {
+	const uint32_t lane = threadIdx.x & 31;
+	// output index of this lane inside its warp-tile
+	// the lane whose bit r is set finishes the odd register of round r, so it ends up with register
+	// j = lane mod 2^NCH of the load phase, i.e. output j * (32 >> NCH) + (lane >> NCH)
+	const uint32_t o_lane = (lane & (CHUNK - 1)) * (32u >> NCH) + (lane >> NCH);
+	const uint64_t n_tiles = A.n_out >> 5, warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;  // n_out is a multiple of 32
+	for (uint64_t tile = (((uint64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+		const uint4 *src = A.in + tile * (32 * CHUNK) + lane;
 		uint4 v[CHUNK];
 #pragma unroll
-		for (uint32_t i = 0; i < CHUNK; i++) v[i] = __ldg(A.in + c * CHUNK + i);
+		for (uint32_t j = 0; j < CHUNK; j++) v[j] = __ldg(src + 32 * j);
 #pragma unroll
 		for (uint32_t r = 0; r < NCH; r++) {
 			if (r < NK) L.sbase = sbase + r * LUT_BYTES;
+			const bool odd = (lane >> r) & 1u;
 #pragma unroll
-			for (uint32_t o = 0; o < (CHUNK >> (r + 1)); o++) {
-				const uint4 x = v[2 * o] ^ v[2 * o + 1];
-				v[o] = v[2 * o] ^ (r < NK ? k64_apply(L, x) : nlut_apply(nl, NL, x));
+			for (uint32_t q = 0; q < (CHUNK >> (r + 1)); q++) {
+				// even-side lanes finish register 2q (they hold child 0), odd-side lanes register 2q+1 (child 1)
+				const uint4 mine = odd ? v[2 * q + 1] : v[2 * q], send = odd ? v[2 * q] : v[2 * q + 1];
+				uint4 recv;
+				recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1u << r);
+				recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1u << r);
+				recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1u << r);
+				recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1u << r);
+				const uint4 x = mine ^ recv;          // child 0 + child 1
+				const uint4 c0 = odd ? recv : mine;   // child 0
+				v[q] = c0 ^ (r < NK ? k64_apply(L, x) : nlut_apply(nl, NL, x));
 			}
 		}
-		A.out[c] = v[0];
+		A.out[tile * 32 + o_lane] = v[0];
 	}
 }
 
