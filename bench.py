@@ -406,6 +406,43 @@ def main():
                   "tensor_expand_k22": {"ms": te_ms, "elems_per_s": (1 << k) / (te_ms * 1e-3),
                                         "hbm_frac": (16 * (1 << k) / (te_ms * 1e-3)) / (peak * 1e9)}}
 
+    # ---- BASELINE config #3: zerocheck round reduction of the u32_add circuit at 2^20 rows --
+    #      5 multilinears of 18 variables after the univariate skip, eq-ind of 2^17, compositions
+    #      (x+c)(y+c)+c-o and x+y+c-z (m3/src/gadgets/add.rs:71-76), HighToLow, 18 rounds of {round
+    #      evaluations at 1 and infinity, fold of every multilinear, halving of the eq-indicator}
+    cfg3 = None
+    if not args.no_ntt:
+        from binius_b200 import ArithCircuit as A
+        from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
+
+        be = B200Backend(hal)
+        nv3 = 18
+        xv, yv, cin, cout, zv = (A.var(i) for i in range(5))
+        comps3 = [(xv + cin) * (yv + cin) + cin - cout, xv + yv + cin - zv]
+
+        def run_cfg3():
+            mls3 = [FoldedMultilinear(dev.slice(t << nv3, (t + 1) << nv3), 0) for t in range(5)]
+            eq3 = be.tensor_product_full_query([rr.getrandbits(128) for _ in range(nv3 - 1)])
+            for r in range(nv3):
+                v = nv3 - r
+                be.sumcheck_compute_round_evals(v, mls3, [EqIndEvaluator(c, have_first_round_eval_1s=(r == 0)) for c in comps3], eq3, [])
+                be.sumcheck_fold_multilinears(v, mls3, rr.getrandbits(128))
+                if v > 1:
+                    eq3 = be.fold_partial_eq_ind(v - 1, eq3)
+
+        run_cfg3()
+        hal.sync()
+        ev.start()
+        for _ in range(3):
+            run_cfg3()
+        c3_ms = ev.stop_ms() / 3
+        c3_bytes = sum(16 * (5 * 2**v + 2**(v - 1)) + 16 * 5 * 2**v + 8 * 5 * 2**v for v in range(1, nv3 + 1))
+        cfg3 = {"ms_per_sumcheck": c3_ms, "rounds_per_s": nv3 / (c3_ms * 1e-3), "algorithmic_bytes": c3_bytes,
+                "hbm_frac": c3_bytes / (c3_ms * 1e-3) / 1e9 / peak,
+                "note": "18 rounds incl. the eq-indicator expansion; 21 MB of multilinears, so the run is launch- and "
+                        "host-latency bound (about 190 us per round, about half of it the Python mirror and the "
+                        "synchronising read of the round values), not bandwidth bound"}
+
     # ---- the remaining ComputeLayer ops of SURVEY.md 8a (rows a6, a7, a9, a10) at 2^22 B128 elements:
     #      device time, algorithmic GB/s and fraction of the HBM peak
     ops = None
@@ -477,6 +514,8 @@ def main():
             line["ntt"] = ntt_res
         if extras:
             line["sumcheck_round"] = extras
+        if cfg3:
+            line["zerocheck_u32_add_2^20_rows"] = cfg3
         if ops:
             line["ops"] = ops
         line["sumcheck_chain"] = chain
