@@ -130,9 +130,25 @@ static int32_t launch_tc_pairs(b200_ctx *ctx, std::vector<tc::TcJob> &jobs, uint
 	T.len = len;
 	T.gmat = gmat;
 	const uint64_t n_chunks = len / tc::CHUNK;
-	// whole waves only: 2 CTAs per SM are resident (256 TMEM columns each); a partial extra wave costs a full one
+	// 2 CTAs per SM are resident (256 TMEM columns each).  Split every job pair over gx CTAs so that the
+	// number of waves times the work per CTA is smallest: cost(gx) = ceil(gx * n_pairs / resident) *
+	// (n_chunks / gx + fixed), `fixed` = prologue + epilogue of a CTA in units of one 64-point chunk.
+	// (100 pairs on 296 slots: gx = 2 leaves a third of the slots idle; gx = 29 runs 9.8 -> 10 waves.)
 	const uint32_t resident = 2 * ctx->n_sms;
-	uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, resident / std::min(n_pairs, resident)));
+	uint32_t gx = 1;
+	{
+		const double fixed = 24.0;
+		double best = 1e300;
+		const uint32_t gmax = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n_chunks / 16, 1), std::max<uint64_t>(64, 4 * (uint64_t)resident / n_pairs));
+		for (uint32_t g = 1; g <= gmax; g++) {
+			const uint64_t waves = ((uint64_t)g * n_pairs + resident - 1) / resident;
+			const double cost = (double)waves * ((double)n_chunks / g + fixed);
+			if (cost < best * 0.999) {
+				best = cost;
+				gx = g;
+			}
+		}
+	}
 	tc::k_pair_tc<<<dim3(gx, n_pairs), tc::THREADS, tc::NSTAGE * tc::STAGE_BYTES + 1024, ctx->stream>>>(T);
 	B200_LAUNCH_CHECK(ctx);
 	tc::k_pair_tc_combine<<<(uint32_t)targets.size(), 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, gmat, (const tc::TcTarget *)(dbase + o_t), ctx->d_results);
