@@ -320,6 +320,12 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	// opt in to large dynamic shared memory once
 	int32_t rc = B200_OK;
 #define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
+	// (function attributes are per device: set them for every context, not once per process)
+	SET(k_lerp_tma<false>, FT_SMEM);
+	SET(k_lerp_tma<true>, FT_SMEM);
+	SET((k_lerp_lut<512, 2, 2, true>), LUT_BYTES + 2048);
+	SET((k_lerp_lut<512, 2, 2, false>), LUT_BYTES + 2048);
+	SET((k_lerp_pairs_lut<512, 2, 2, true>), LUT_BYTES + 2048);
 	SET(k_expand_k64<1>, 1 * LUT_BYTES + 6144);
 	SET(k_expand_k64<2>, 2 * LUT_BYTES + 6144);
 	SET(k_expand_k64<3>, 3 * LUT_BYTES + 6144);
@@ -518,12 +524,7 @@ int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uin
 template <uint32_t THREADS, uint32_t UNR, int MINB, bool PAIRS = false, bool K64 = true>
 static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
 	constexpr uint32_t TILE = THREADS * UNR;
-	static bool attr_set = false;
-	auto kernel = PAIRS ? k_lerp_pairs_lut<THREADS, UNR, MINB, K64> : k_lerp_lut<THREADS, UNR, MINB, K64>;
-	if (!attr_set) {
-		B200_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LUT_BYTES + 2048)));
-		attr_set = true;
-	}
+	auto kernel = PAIRS ? k_lerp_pairs_lut<THREADS, UNR, MINB, K64> : k_lerp_lut<THREADS, UNR, MINB, K64>;  // smem opt-in: b200_ctx_create
 	// segments travel by value in the kernel parameters: no staging copy, one launch per <= 48 segments
 	for (size_t s0 = 0; s0 < live.size(); s0 += LERP_MAX_SEGS) {
 		LerpArgs A;
@@ -546,11 +547,6 @@ static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &li
 // TMA-staged persistent kernel (fold_tma.cuh): tiles of FT_TILE outputs, one CTA per SM
 template <bool PAIRS>
 static int32_t launch_lerp_tma(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
-	static bool attr_set = false;
-	if (!attr_set) {
-		B200_CUDA(ctx, cudaFuncSetAttribute(k_lerp_tma<PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-		attr_set = true;
-	}
 	for (size_t s0 = 0; s0 < live.size(); s0 += LERP_MAX_SEGS) {
 		LerpArgs A;
 		A.n_segs = (uint32_t)std::min<size_t>(LERP_MAX_SEGS, live.size() - s0);
