@@ -420,9 +420,15 @@ def main():
         xv, yv, cin, cout, zv = (A.var(i) for i in range(5))
         comps3 = [(xv + cin) * (yv + cin) + cin - cout, xv + yv + cin - zv]
 
+        eq3_buf = hal.dev_alloc(1 << (nv3 - 1))  # arena memory, allocated once as the prover's bump allocator would
+
         def run_cfg3():
             mls3 = [FoldedMultilinear(dev.slice(t << nv3, (t + 1) << nv3), 0) for t in range(5)]
-            eq3 = be.tensor_product_full_query([rr.getrandbits(128) for _ in range(nv3 - 1)])
+            from binius_b200.layer import _u64_list
+
+            hal._check(hal._lib.b200_tensor_product_full_query(hal._ctx, _u64_list([rr.getrandbits(128) for _ in range(nv3 - 1)]), nv3 - 1,
+                                                               eq3_buf.ptr, eq3_buf.len()))
+            eq3 = eq3_buf
             for r in range(nv3):
                 v = nv3 - r
                 be.sumcheck_compute_round_evals(v, mls3, [EqIndEvaluator(c, have_first_round_eval_1s=(r == 0)) for c in comps3], eq3, [])
@@ -440,8 +446,8 @@ def main():
         cfg3 = {"ms_per_sumcheck": c3_ms, "rounds_per_s": nv3 / (c3_ms * 1e-3), "algorithmic_bytes": c3_bytes,
                 "hbm_frac": c3_bytes / (c3_ms * 1e-3) / 1e9 / peak,
                 "note": "18 rounds incl. the eq-indicator expansion; 21 MB of multilinears, so the run is launch- and "
-                        "host-latency bound (about 190 us per round, about half of it the Python mirror and the "
-                        "synchronising read of the round values), not bandwidth bound"}
+                        "host-latency bound (Python mirror in the loop; tools/keccak_replay_cpp cfg3 is the same "
+                        "sequence from compiled host code), not bandwidth bound"}
 
     # ---- the remaining ComputeLayer ops of SURVEY.md 8a (rows a6, a7, a9, a10) at 2^22 B128 elements:
     #      device time, algorithmic GB/s and fraction of the HBM peak

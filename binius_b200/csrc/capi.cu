@@ -302,7 +302,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	ctx->stream = ctx->own_stream;
 	bool ok = cudaMalloc(&ctx->d_tables, FIELD_TABLE_BYTES) == cudaSuccess &&
 			  cudaMalloc(&ctx->d_results, sizeof(uint4) * MAX_RESULTS) == cudaSuccess &&
-			  cudaMalloc(&ctx->d_args, ARGS_BYTES) == cudaSuccess && cudaMallocHost(&ctx->h_args, ARGS_BYTES) == cudaSuccess;
+			  cudaMalloc(&ctx->d_args, ARGS_BYTES) == cudaSuccess && cudaMallocHost(&ctx->h_args, ARGS_BYTES) == cudaSuccess &&
+			  cudaMallocHost(&ctx->h_results, 16 * H_RESULTS) == cudaSuccess;
 	if (!ok) return B200_ERR_ALLOC;
 	// 8-bit tables from the bit-level tower recursion (host_field.hpp)
 	std::vector<uint8_t> tables(FIELD_TABLE_BYTES);
@@ -374,6 +375,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	cudaFree(ctx->d_results);
 	cudaFree(ctx->d_args);
 	cudaFreeHost(ctx->h_args);
+	cudaFreeHost(ctx->h_results);
 	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
 	if (ctx->s_h2d) {
 		cudaStreamDestroy(ctx->s_h2d);
@@ -509,8 +511,15 @@ int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uin
 		if (slots[i] >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "result slot %u out of range", slots[i]);
 		hi = std::max(hi, slots[i]);
 	}
-	std::vector<uint64_t> tmp(2 * (size_t)(hi + 1));
-	B200_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->d_results, 16 * (size_t)(hi + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	// the round values of a sumcheck round are a handful of slots: read them through the pinned mirror
+	// (a pageable destination costs an extra staging copy inside the driver, ~10 us per round)
+	std::vector<uint64_t> big;
+	uint64_t *tmp = ctx->h_results;
+	if (hi + 1 > H_RESULTS) {
+		big.resize(2 * (size_t)(hi + 1));
+		tmp = big.data();
+	}
+	B200_CUDA(ctx, cudaMemcpyAsync(tmp, ctx->d_results, 16 * (size_t)(hi + 1), cudaMemcpyDeviceToHost, ctx->stream));
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	for (uint32_t i = 0; i < n; i++) {
 		host_out[2 * i] = tmp[2 * slots[i]];

@@ -37,6 +37,7 @@ struct b200_ctx {
 	// deferred scalar results (OpValue slots)
 	uint4 *d_results = nullptr;
 	uint32_t n_results = 0;
+	uint64_t *h_results = nullptr;  // pinned mirror of the first slots (b200_results_fetch reads through it)
 	// small device scratch for argument arrays (pointer lists etc.), ring-allocated
 	uint8_t *d_args = nullptr;
 	uint64_t args_off = 0;
@@ -50,6 +51,7 @@ struct b200_ctx {
 namespace b200 {
 
 constexpr uint32_t MAX_RESULTS = 1u << 16;
+constexpr uint32_t H_RESULTS = 4096;  // slots mirrored in pinned host memory
 constexpr uint64_t ARGS_BYTES = 4u << 20;
 
 inline int32_t fail(b200_ctx *ctx, int32_t code, const char *fmt, ...) {

@@ -43,7 +43,56 @@ struct Timer {
 	}
 };
 
+// BASELINE config #3: zerocheck rounds of the u32_add circuit at 2^20 rows (5 multilinears of 18 variables,
+// compositions (x+c)(y+c)+c-o and x+y+c-z, 18 rounds of {round evals, fold, eq-ind halving}), compiled host
+static int run_cfg3() {
+	B200Layer hal(0);
+	B200Backend be(hal);
+	const uint32_t nv = 18, m = 5;
+	DevSlice arena = hal.dev_alloc((uint64_t)m << nv);
+	hal.fill(arena, F128{0xFEDCBA9876543211ull, 0x0123456789ABCDEFull});
+	// vars: 0 x, 1 y, 2 cin, 3 cout, 4 z
+	ExprEval c1 = hal.compile_expr({ExprStep::var(0), ExprStep::var(2), ExprStep::add(0, 1), ExprStep::var(1), ExprStep::add(3, 1), ExprStep::mul(2, 4),
+									ExprStep::add(5, 1), ExprStep::var(3), ExprStep::add(6, 7)});
+	ExprEval l1 = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::mul(0, 1)});
+	ExprEval c2 = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::add(0, 1), ExprStep::var(2), ExprStep::add(2, 3), ExprStep::var(4), ExprStep::add(4, 5)});
+	ExprEval l2 = hal.compile_expr({ExprStep::constant(F128{})});
+	Timer t(hal);
+	double ms = 0;
+	const int reps = 5;
+	DevSlice eq_buf = hal.dev_alloc(1ull << (nv - 1));  // arena memory: allocated once, as the prover's bump allocator would
+	for (int rep = -1; rep < reps; rep++) {
+		std::vector<SumcheckMultilinear> mls;
+		for (uint32_t i = 0; i < m; i++) mls.push_back(SumcheckMultilinear::folded(arena.slice((uint64_t)i << nv, (uint64_t)(i + 1) << nv)));
+		std::vector<F128> q(nv - 1);
+		for (auto &x : q) x = rnd();
+		t.start();
+		hal.check(b200_tensor_product_full_query(hal.ctx(), &q[0].lo, nv - 1, eq_buf.ptr, eq_buf.n));
+		DevSlice eq = eq_buf;
+		for (uint32_t r = 0; r < nv; r++) {
+			const uint32_t v = nv - r;
+			std::vector<SumcheckEvaluator> evs{SumcheckEvaluator{&c1, &l1, r == 0 ? 2u : 1u, 3u}, SumcheckEvaluator{&c2, &l2, r == 0 ? 2u : 1u, 2u}};
+			auto w0 = std::chrono::steady_clock::now();
+			be.sumcheck_compute_round_evals(EvaluationOrder::HighToLow, v, nullptr, mls, evs, &eq, {});
+			auto w1 = std::chrono::steady_clock::now();
+			be.sumcheck_fold_multilinears(EvaluationOrder::HighToLow, v, mls, rnd(), nullptr);
+			if (v > 1) eq = be.fold_partial_eq_ind(EvaluationOrder::HighToLow, v - 1, eq);
+			auto w2 = std::chrono::steady_clock::now();
+			if (getenv("REPLAY_VERBOSE") && rep == 0)
+				fprintf(stderr, "n_vars=%u evals %.1f us fold %.1f us (host wall)\n", v, std::chrono::duration<double, std::micro>(w1 - w0).count(),
+						std::chrono::duration<double, std::micro>(w2 - w1).count());
+		}
+		const double one = t.stop();
+		if (rep >= 0) ms += one;
+		hal.check(b200_sync(hal.ctx()));
+	}
+	printf("{\"workload\": \"zerocheck rounds, u32_add at 2^20 rows (5 multilinears x 2^18, 18 rounds), compiled host\", \"ms_per_sumcheck\": %.4f, \"rounds_per_s\": %.1f}\n",
+		   ms / reps, 18.0 / (ms / reps * 1e-3));
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc > 1 && std::string(argv[1]) == "cfg3") return run_cfg3();
 	const uint32_t log_n = argc > 1 ? (uint32_t)atoi(argv[1]) : 18;
 	const uint32_t nv = log_n + 2;
 	B200Layer hal(0);
