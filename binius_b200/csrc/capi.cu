@@ -322,8 +322,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	int32_t rc = B200_OK;
 #define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
 	// (function attributes are per device: set them for every context, not once per process)
-	SET(k_lerp_tma<false>, FT_SMEM);
-	SET(k_lerp_tma<true>, FT_SMEM);
+	SET(k_lerp_tma<false>, FT_SMEM + FT_MAX_SEGS * sizeof(LerpSeg));
+	SET(k_lerp_tma<true>, FT_SMEM + FT_MAX_SEGS * sizeof(LerpSeg));
 	SET((k_lerp_lut<512, 2, 2, true>), LUT_BYTES + 2048);
 	SET((k_lerp_lut<512, 2, 2, false>), LUT_BYTES + 2048);
 	SET((k_lerp_pairs_lut<512, 2, 2, true>), LUT_BYTES + 2048);
@@ -537,6 +537,7 @@ static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &li
 	// segments travel by value in the kernel parameters: no staging copy, one launch per <= 48 segments
 	for (size_t s0 = 0; s0 < live.size(); s0 += LERP_MAX_SEGS) {
 		LerpArgs A;
+		A.segs_dev = nullptr;
 		A.n_segs = (uint32_t)std::min<size_t>(LERP_MAX_SEGS, live.size() - s0);
 		uint64_t tiles = 0;
 		for (uint32_t i = 0; i < A.n_segs; i++) {
@@ -556,19 +557,35 @@ static int32_t launch_lerp_variant(b200_ctx *ctx, const std::vector<LerpSeg> &li
 // TMA-staged persistent kernel (fold_tma.cuh): tiles of FT_TILE outputs, one CTA per SM
 template <bool PAIRS>
 static int32_t launch_lerp_tma(b200_ctx *ctx, const std::vector<LerpSeg> &live, const uint64_t z[2]) {
-	for (size_t s0 = 0; s0 < live.size(); s0 += LERP_MAX_SEGS) {
+	// one launch per FT_MAX_SEGS segments: up to LERP_MAX_SEGS by value, longer lists staged in device
+	// memory (the kernel copies them to shared memory)
+	for (size_t s0 = 0; s0 < live.size(); s0 += FT_MAX_SEGS) {
+		const size_t cnt = std::min<size_t>(FT_MAX_SEGS, live.size() - s0);
 		LerpArgs A;
-		A.n_segs = (uint32_t)std::min<size_t>(LERP_MAX_SEGS, live.size() - s0);
+		std::vector<LerpSeg> all;
+		const bool by_value = cnt <= LERP_MAX_SEGS;
+		if (!by_value) all.resize(cnt);
+		LerpSeg *dst = by_value ? A.segs : all.data();
 		uint64_t tiles = 0;
-		for (uint32_t i = 0; i < A.n_segs; i++) {
-			A.segs[i] = live[s0 + i];
-			A.segs[i].tile_start = tiles;
-			tiles += (A.segs[i].upper + FT_TILE - 1) / FT_TILE;
+		for (size_t i = 0; i < cnt; i++) {
+			dst[i] = live[s0 + i];
+			dst[i].tile_start = tiles;
+			tiles += (live[s0 + i].upper + FT_TILE - 1) / FT_TILE;
 		}
+		if (tiles >> 32) return fail(ctx, B200_ERR_INPUT_VALIDATION, "fold: too many tiles in one call");
+		A.segs_dev = nullptr;
+		if (!by_value) {
+			void *d;
+			int32_t rc = stage_args(ctx, all.data(), sizeof(LerpSeg) * cnt, &d);
+			if (rc) return rc;
+			A.segs_dev = (const LerpSeg *)d;
+		}
+		A.n_segs = (uint32_t)cnt;
 		A.n_tiles = tiles;
 		A.z = to_u4(z);
 		uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + FT_WARPS - 1) / FT_WARPS, (uint64_t)ctx->n_sms);
-		k_lerp_tma<PAIRS><<<grid, FT_THREADS, FT_SMEM, ctx->stream>>>(A);
+		const uint32_t smem = FT_SMEM + (by_value ? 0 : (uint32_t)(sizeof(LerpSeg) * cnt));
+		k_lerp_tma<PAIRS><<<grid, FT_THREADS, smem, ctx->stream>>>(A);
 		B200_LAUNCH_CHECK(ctx);
 	}
 	return B200_OK;

@@ -25,6 +25,7 @@ constexpr uint32_t FT_TILE = 32 * FT_UNR;              // outputs per warp-tile:
 constexpr uint32_t FT_NSTAGE = 2;
 constexpr uint32_t FT_STAGE_BYTES = 2 * FT_TILE * 16;  // 2 KiB: [e0 tile | e1 tile] or 2*TILE interleaved inputs
 constexpr uint32_t FT_SMEM = LUT_BYTES + 2048 + FT_WARPS * FT_NSTAGE * FT_STAGE_BYTES + FT_WARPS * FT_NSTAGE * 8;
+constexpr uint32_t FT_MAX_SEGS = 448;  // segment lists beyond the by-value 48 are copied to shared memory (28 KiB)
 
 __device__ __forceinline__ uint32_t ft_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ft_mbar_init(uint64_t *bar, uint32_t count) {
@@ -70,7 +71,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 	const uint32_t n_tiles = (uint32_t)A.n_tiles, tile_step = gridDim.x * FT_WARPS;
 	uint32_t next_tile = blockIdx.x * FT_WARPS + warp;  // tile of the next descriptor to build
 
-	FtCursor C{0, 0, A.n_segs > 1 ? (uint32_t)A.segs[1].tile_start : n_tiles};
+	// up to LERP_MAX_SEGS segments travel by value in the kernel parameters; longer lists are staged in
+	// device memory and copied to shared memory once per CTA (descriptor reads sit on the critical path
+	// of every tile request: constant bank or LDS, never a global load)
+	const LerpSeg *segs = A.segs;
+	if (A.segs_dev) {
+		uint4 *sseg = reinterpret_cast<uint4 *>(smem + FT_SMEM);
+		const uint4 *g = reinterpret_cast<const uint4 *>(A.segs_dev);
+		for (uint32_t i = threadIdx.x; i < A.n_segs * (sizeof(LerpSeg) / 16); i += blockDim.x) sseg[i] = __ldg(g + i);
+		__syncthreads();
+		segs = reinterpret_cast<const LerpSeg *>(sseg);
+	}
+	FtCursor C{0, 0, A.n_segs > 1 ? (uint32_t)segs[1].tile_start : n_tiles};
 	// build the descriptor of `next_tile` (warp-uniform), have lane 0 request it into stage `s`, advance
 	auto request = [&](uint32_t s) -> FtDesc {
 		FtDesc d{0, 0, 0, 0};
@@ -78,9 +90,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 			while (next_tile >= C.seg_end) {
 				C.seg++;
 				C.seg_start = C.seg_end;
-				C.seg_end = C.seg + 1 < A.n_segs ? (uint32_t)A.segs[C.seg + 1].tile_start : n_tiles;
+				C.seg_end = C.seg + 1 < A.n_segs ? (uint32_t)segs[C.seg + 1].tile_start : n_tiles;
 			}
-			const LerpSeg &S = A.segs[C.seg];
+			const LerpSeg &S = segs[C.seg];
 			d.seg = C.seg;
 			d.base = (next_tile - C.seg_start) * FT_TILE;
 			d.cnt = min(FT_TILE, (uint32_t)S.upper - d.base);
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 
 	for (uint32_t k = 0; d0.cnt; k++) {
 		const uint32_t s = k & 1u;
-		const LerpSeg &S = A.segs[d0.seg];
+		const LerpSeg &S = segs[d0.seg];
 		const uint4 *st = reinterpret_cast<const uint4 *>(ring + s * FT_STAGE_BYTES);
 		ft_mbar_wait(&full[s], (k >> 1) & 1u);
 		uint4 a[FT_UNR], x[FT_UNR];

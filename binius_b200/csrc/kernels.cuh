@@ -24,6 +24,7 @@ struct LerpSeg {
 constexpr uint32_t LERP_MAX_SEGS = 48;  // segments passed by value in the kernel parameters
 struct LerpArgs {
 	LerpSeg segs[LERP_MAX_SEGS];
+	const LerpSeg *segs_dev;  // more than LERP_MAX_SEGS segments: the list staged in device memory (else null)
 	uint32_t n_segs;
 	uint64_t n_tiles;
 	uint4 z;

@@ -112,3 +112,28 @@ def test_fuzz_ntt_shapes(hal, oracle):
         assert np.array_equal(f, ontt.forward(data, 5, log_x, log_y, log_z, coset, coset_bits, skip)), (case, log_x, log_y, log_z, coset, skip)
         ntt.inverse_transform(f, NTTShape(log_x, log_y, log_z), coset, coset_bits, skip)
         assert np.array_equal(f, data), (case, "round trip")
+
+
+def test_fold_many_multilinears_one_launch(hal, oracle):
+    """More multilinears than fit the kernel-parameter segment list (48): the list is staged in device
+    memory and the whole fold is one launch."""
+    rng = random.Random(99)
+    n_vars, m = 11, 130
+    full = 1 << n_vars
+    prefixes = [rng.choice([full, full, rng.randint(1, full)]) for _ in range(m)]
+    suffixes = [rng.choice([0, rng.getrandbits(128)]) for _ in range(m)]
+    z = rng.getrandbits(128)
+    host = [oracle.rand_b128(7000 + t, p) for t, p in enumerate(prefixes)]
+    devs = [hal.to_device(h) for h in host]
+    zs = (C.c_uint64 * 2)(z & (2**64 - 1), z >> 64)
+    sfx = (C.c_uint64 * (2 * m))(*[w for s in suffixes for w in (s & (2**64 - 1), s >> 64)])
+    lens = (C.c_uint64 * m)(*prefixes)
+    new_lens = (C.c_uint64 * m)()
+    ptrs = (C.c_void_p * m)(*[d.ptr for d in devs])
+    l0 = hal.launch_count()
+    hal._check(hal._lib.b200_fold_multilinears_high_to_low(hal._ctx, ptrs, m, n_vars, lens, sfx, zs, new_lens))
+    assert hal.launch_count() - l0 == 1
+    for t in range(m):
+        exp = oracle.fold_left_lerp_inplace(host[t], prefixes[t], suffixes[t], n_vars, z)
+        assert int(new_lens[t]) == len(exp)
+        assert _same(hal.to_host(devs[t].slice(0, len(exp))), exp), t
