@@ -322,8 +322,10 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	int32_t rc = B200_OK;
 #define SET(k, bytes) if (rc == B200_OK) rc = set_smem(c, k, bytes)
 	// (function attributes are per device: set them for every context, not once per process)
-	SET(k_lerp_tma<false>, FT_SMEM + FT_MAX_SEGS * sizeof(LerpSeg));
-	SET(k_lerp_tma<true>, FT_SMEM + FT_MAX_SEGS * sizeof(LerpSeg));
+	SET((k_lerp_tma<false, false>), FT_SMEM);
+	SET((k_lerp_tma<true, false>), FT_SMEM);
+	SET((k_lerp_tma<false, true>), FT_SMEM + FT_MAX_SEGS * sizeof(LerpSeg));
+	SET((k_lerp_tma<true, true>), FT_SMEM + FT_MAX_SEGS * sizeof(LerpSeg));
 	SET((k_lerp_lut<512, 2, 2, true>), LUT_BYTES + 2048);
 	SET((k_lerp_lut<512, 2, 2, false>), LUT_BYTES + 2048);
 	SET((k_lerp_pairs_lut<512, 2, 2, true>), LUT_BYTES + 2048);
@@ -585,7 +587,8 @@ static int32_t launch_lerp_tma(b200_ctx *ctx, const std::vector<LerpSeg> &live, 
 		A.z = to_u4(z);
 		uint32_t grid = (uint32_t)std::min<uint64_t>((tiles + FT_WARPS - 1) / FT_WARPS, (uint64_t)ctx->n_sms);
 		const uint32_t smem = FT_SMEM + (by_value ? 0 : (uint32_t)(sizeof(LerpSeg) * cnt));
-		k_lerp_tma<PAIRS><<<grid, FT_THREADS, smem, ctx->stream>>>(A);
+		if (by_value) k_lerp_tma<PAIRS, false><<<grid, FT_THREADS, smem, ctx->stream>>>(A);
+		else k_lerp_tma<PAIRS, true><<<grid, FT_THREADS, smem, ctx->stream>>>(A);
 		B200_LAUNCH_CHECK(ctx);
 	}
 	return B200_OK;

@@ -62,7 +62,7 @@ struct FtCursor {
 	uint32_t seg, seg_start, seg_end;
 };
 
-template <bool PAIRS>
+template <bool PAIRS, bool SMEM_SEGS>
 __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constant__ LerpArgs A) {
 	extern __shared__ __align__(256) uint8_t smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,18 +71,19 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 	const uint32_t n_tiles = (uint32_t)A.n_tiles, tile_step = gridDim.x * FT_WARPS;
 	uint32_t next_tile = blockIdx.x * FT_WARPS + warp;  // tile of the next descriptor to build
 
-	// up to LERP_MAX_SEGS segments travel by value in the kernel parameters; longer lists are staged in
-	// device memory and copied to shared memory once per CTA (descriptor reads sit on the critical path
-	// of every tile request: constant bank or LDS, never a global load)
+	// up to LERP_MAX_SEGS segments travel by value in the kernel parameters (SMEM_SEGS = false: read straight
+	// from the constant bank); longer lists are staged in device memory and copied to shared memory once per
+	// CTA (descriptor reads sit on the critical path of every tile request: never a global load)
 	const LerpSeg *segs = A.segs;
-	if (A.segs_dev) {
+	if (SMEM_SEGS) {
 		uint4 *sseg = reinterpret_cast<uint4 *>(smem + FT_SMEM);
 		const uint4 *g = reinterpret_cast<const uint4 *>(A.segs_dev);
 		for (uint32_t i = threadIdx.x; i < A.n_segs * (sizeof(LerpSeg) / 16); i += blockDim.x) sseg[i] = __ldg(g + i);
 		__syncthreads();
 		segs = reinterpret_cast<const LerpSeg *>(sseg);
 	}
-	FtCursor C{0, 0, A.n_segs > 1 ? (uint32_t)segs[1].tile_start : n_tiles};
+#define FT_SEG(i) (SMEM_SEGS ? segs[i] : A.segs[i])
+	FtCursor C{0, 0, A.n_segs > 1 ? (uint32_t)FT_SEG(1).tile_start : n_tiles};
 	// build the descriptor of `next_tile` (warp-uniform), have lane 0 request it into stage `s`, advance
 	auto request = [&](uint32_t s) -> FtDesc {
 		FtDesc d{0, 0, 0, 0};
@@ -90,9 +91,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 			while (next_tile >= C.seg_end) {
 				C.seg++;
 				C.seg_start = C.seg_end;
-				C.seg_end = C.seg + 1 < A.n_segs ? (uint32_t)segs[C.seg + 1].tile_start : n_tiles;
+				C.seg_end = C.seg + 1 < A.n_segs ? (uint32_t)FT_SEG(C.seg + 1).tile_start : n_tiles;
 			}
-			const LerpSeg &S = segs[C.seg];
+			const LerpSeg &S = FT_SEG(C.seg);
 			d.seg = C.seg;
 			d.base = (next_tile - C.seg_start) * FT_TILE;
 			d.cnt = min(FT_TILE, (uint32_t)S.upper - d.base);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 
 	for (uint32_t k = 0; d0.cnt; k++) {
 		const uint32_t s = k & 1u;
-		const LerpSeg &S = segs[d0.seg];
+		const LerpSeg &S = FT_SEG(d0.seg);
 		const uint4 *st = reinterpret_cast<const uint4 *>(ring + s * FT_STAGE_BYTES);
 		ft_mbar_wait(&full[s], (k >> 1) & 1u);
 		uint4 a[FT_UNR], x[FT_UNR];
@@ -152,5 +153,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_lerp_tma(const __grid_constan
 		d1 = d2;
 	}
 }
+
+#undef FT_SEG
 
 }  // namespace b200
