@@ -1,6 +1,6 @@
 """Run under torchrun on N GPUs: sharded bivariate sumcheck (binius_b200/sharding.py) on real B200s
 with NCCL for the combine, checked round-by-round against the CPU oracle.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_sumcheck_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/sharded_sumcheck_check.py
 """
 import os
 import random
