@@ -194,10 +194,11 @@ struct NttBsArgs {
 	uint32_t in_sliced, out_sliced;
 };
 
-// Tiles of 2^NTT_BS_LOG_TILE = 256 units (32 KiB of planes) on 128 threads, two CTAs per SM (2 x 128 x 255
-// registers fill the register file): a pass has 8x more CTAs than CTA slots, so the last wave is nearly
-// full (1024-unit tiles on one CTA per SM lost 13.5% at 2^24 to a 3.46-wave grid), the global load/store
-// phases of one CTA overlap the butterflies of the other, and the per-layer barriers are decoupled.
+// Tiles of 2^NTT_BS_LOG_TILE = 256 units (32 KiB of planes) on 128 threads, four CTAs per SM (ptxas fits
+// the 32-plane product in 128 registers with ~150 bytes of spills; 168 registers / 3 CTAs is spill-free and
+// as fast): a pass has many more CTAs than CTA slots, so the tail of the grid is short (1024-unit tiles
+// on one CTA per SM ran a 3.46-wave grid at 2^24), the global load/store phases of one CTA overlap the
+// butterflies of the others, and the per-layer barriers are decoupled.
 constexpr uint32_t NTT_BS_THREADS = 128;
 constexpr uint32_t NTT_BS_LOG_TILE = 8;
 
