@@ -1189,6 +1189,8 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 	// pass plan, bottom-up.  kind 0 = table-driven scalar pass (ntt.cuh), kind 1 = bit-sliced pass
 	// (ntt_bs.cuh; needs >= 32 contiguous positions sharing every twiddle: lx + i_lo >= 5, B32 only).
 	struct Pass { uint32_t kind, i_lo, R, R_exec, log_c; };
+	// bit-sliced tile size (ntt_bs.cuh): 512-unit tiles up to 2^25 coefficients, 256-unit tiles above
+	const uint32_t LT = ((n_elems << (kd - ntt->kt)) >> 25) ? 8u : NTT_BS_MAX_LOG_TILE;
 	std::vector<Pass> plan;
 	const uint32_t MAX_LOG_TILE = 13;
 	static int force_scalar = getenv("B200_NTT_SCALAR") ? atoi(getenv("B200_NTT_SCALAR")) : 0;
@@ -1197,7 +1199,7 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 		if (lx < 5 && lx + log_y >= 5) {
 			// kind 2: lowest pass on units of 32 consecutive scalars (intra-unit layers + up to Rt inter-unit)
 			uint32_t L0 = 5 - lx;
-			uint32_t Rt = std::min(NTT_BS_LOG_TILE, lx + log_y - 5);
+			uint32_t Rt = std::min(LT, lx + log_y - 5);
 			uint32_t n_intra = std::min(n_layers, L0);
 			uint32_t n_inter = std::min(n_layers - n_intra, Rt);
 			uint32_t rest = n_layers - n_intra - n_inter;
@@ -1208,11 +1210,11 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			plan.push_back(Pass{0, 0, log_y, n_layers, lx});  // transform smaller than one unit
 			i_lo = n_layers;
 		}
-		// tiles of 2^(R + log_cu) = 2^NTT_BS_LOG_TILE units: one butterfly-unit per thread and layer
-		const uint32_t LT = NTT_BS_LOG_TILE;
+		// tiles of 2^(R + log_cu) = 2^LT units: one butterfly-unit per thread and layer
 		while (i_lo < n_layers) {
-			uint32_t log_cu = std::min(lx + i_lo - 5, 1u);
-			uint32_t R = std::min(n_layers - i_lo, LT - log_cu);
+			const uint32_t rem = n_layers - i_lo;
+			uint32_t log_cu = rem <= LT ? 0u : std::min(lx + i_lo - 5, 1u);  // a last pass of exactly LT layers takes single-unit rows
+			uint32_t R = std::min(rem, LT - log_cu);
 			if (n_layers - i_lo - R > 0 && n_layers - i_lo - R < 4) R = (n_layers - i_lo + 1) / 2;  // avoid a tiny last pass
 			log_cu = std::min(lx + i_lo - 5, LT - R);  // short passes take wider tiles: always 2^LT units
 			plan.push_back(Pass{1, i_lo, R, R, log_cu});
@@ -1255,7 +1257,7 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			uint64_t n_blocks = 1ull << (lx + log_y - 5 - P.R);
 			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
 			uint32_t smem = (184u << P.R) + 640 + 16;
-			k_ntt_bs_low<<<dim3((uint32_t)n_blocks, n_z), NTT_BS_THREADS, smem, ctx->stream>>>(L);
+			k_ntt_bs_low<<<dim3((uint32_t)n_blocks, n_z), ntt_bs_threads(LT), smem, ctx->stream>>>(L);
 			B200_LAUNCH_CHECK(ctx);
 			continue;
 		}
@@ -1277,7 +1279,7 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			uint64_t n_blocks = 1ull << (log_y - (P.i_lo + P.R) + (lx + P.i_lo - 5 - P.log_c));
 			if (n_blocks > 0x7fffffffull) return fail(ctx, B200_ERR_INPUT_VALIDATION, "transform too large");
 			uint32_t smem = (36u << P.R) + 16 + (128u << (P.R + P.log_c));
-			k_ntt_bs_pass<<<dim3((uint32_t)n_blocks, n_z), NTT_BS_THREADS, smem, ctx->stream>>>(B);
+			k_ntt_bs_pass<<<dim3((uint32_t)n_blocks, n_z), ntt_bs_threads(LT), smem, ctx->stream>>>(B);
 			B200_LAUNCH_CHECK(ctx);
 			continue;
 		}

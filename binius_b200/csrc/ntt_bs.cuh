@@ -194,16 +194,20 @@ struct NttBsArgs {
 	uint32_t in_sliced, out_sliced;
 };
 
-// Tiles of 2^NTT_BS_LOG_TILE = 256 units (32 KiB of planes) on 128 threads, four CTAs per SM (ptxas fits
-// the 32-plane product in 128 registers with ~150 bytes of spills; 168 registers / 3 CTAs is spill-free and
-// as fast): a pass has many more CTAs than CTA slots, so the tail of the grid is short (1024-unit tiles
-// on one CTA per SM ran a 3.46-wave grid at 2^24), the global load/store phases of one CTA overlap the
-// butterflies of the others, and the per-layer barriers are decoupled.
-constexpr uint32_t NTT_BS_THREADS = 128;
-constexpr uint32_t NTT_BS_LOG_TILE = 8;
+// Tiles of 2^LT units, LT = 8 or 9 (32 / 64 KiB of planes), one butterfly-unit per thread and layer: 128
+// threads x 4 CTAs per SM or 256 threads x 2 CTAs per SM.  Both fit the register file at 128 registers per
+// thread (ptxas fits the 32-plane product there with ~150 bytes of spills; 168 registers are spill-free and
+// as fast).  A pass has many more CTAs than CTA slots, so the tail of the grid is short (1024-unit tiles on
+// one CTA per SM ran a 3.46-wave grid at 2^24), the global load/store phases of one CTA overlap the
+// butterflies of the others, and the per-layer barriers are decoupled.  The host picks LT per transform:
+// 9 up to 2^25 coefficients (fewer passes: 17 layers = 8 + 9), 8 above (measured: RS-encode shape at 2^24
+// 0.348 vs 0.358 ms, at 2^30 29.6 vs 29.1 ms).
+constexpr uint32_t NTT_BS_MAX_THREADS = 256;
+constexpr uint32_t NTT_BS_MAX_LOG_TILE = 9;
+__host__ __device__ constexpr uint32_t ntt_bs_threads(uint32_t log_tile) { return 128u << (log_tile - 8); }
 
 // dyn smem = 36 * 2^R (twiddles + their bit expansion) + 128 * 2^(R + log_cu) (bit-sliced tile, plane-major: tile[p * NU + unit])
-__global__ void __launch_bounds__(NTT_BS_THREADS, 4) k_ntt_bs_pass(const NttBsArgs A) {
+__global__ void __launch_bounds__(NTT_BS_MAX_THREADS, 2) k_ntt_bs_pass(const NttBsArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint32_t *tw = reinterpret_cast<uint32_t *>(smem);
 	uint8_t *twb = smem + (((4u << A.R) + 15u) & ~15u);  // [2^R][32] bit-expanded twiddles
@@ -323,7 +327,7 @@ __device__ __forceinline__ uint32_t ntt_subset_sum(const uint32_t *srow, uint32_
 }
 
 // dyn smem = 4*2^Rt (inter twiddles) + 5*4*2^Rt (per-unit intra twiddles) + 5*32*4 (lane planes) + 32*2^Rt (bit-expanded twiddles) + 128*2^Rt (tile)
-__global__ void __launch_bounds__(NTT_BS_THREADS, 4) k_ntt_bs_low(const NttBsLowArgs A) {
+__global__ void __launch_bounds__(NTT_BS_MAX_THREADS, 2) k_ntt_bs_low(const NttBsLowArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	const uint32_t Rt = A.Rt, NU = 1u << Rt, L0 = 5 - A.log_x;
 	uint32_t *tw = reinterpret_cast<uint32_t *>(smem);            // [2^Rt] heap for inter-unit layers
