@@ -359,6 +359,50 @@ def fold_partial_eq_ind(e):
 
 
 # ------------------------------------------------------------------------------------------------
+# zerocheck univariate-skip round (oracle/univariate.c): the specification of SURVEY.md 8f rank 1
+def lagrange_evals(k: int, x: int):
+    out = np.zeros((1 << k, 2), np.uint64)
+    lib().orc_lagrange_evals(C.c_uint32(k), _p(one(x)), _p(out))
+    return to_ints(out)
+
+
+def zerocheck_univariate_evals(mls, levels, n_vars: int, skip: int, eq_ind, comps, max_domain_size: int):
+    """mls: packed sub-field multilinears (arrays of B128 words), levels: their tower levels; returns
+    [[R_c(x_i) for i < max_domain_size - 2^skip] for each composition]."""
+    mls = [_c(x) for x in mls]
+    m = len(mls)
+    enc = [encode_expr(s) for s in comps]
+    pc = (C.c_void_p * len(comps))(*[C.addressof(e) for e in enc])
+    nc = (C.c_uint32 * len(comps))(*[len(s) for s in comps])
+    n_points = max_domain_size - (1 << skip)
+    out = np.zeros((max(len(comps) * n_points, 1), 2), np.uint64)
+    rc = lib().orc_zerocheck_univariate_evals(_ptr_array(mls), (C.c_uint32 * m)(*levels), C.c_uint32(m), C.c_uint32(n_vars), C.c_uint32(skip),
+                                              _p(_c(eq_ind)), pc, nc, C.c_uint32(len(comps)), C.c_uint32(max_domain_size), _p(out))
+    _check(rc)
+    vals = to_ints(out)
+    return [vals[c * n_points:(c + 1) * n_points] for c in range(len(comps))]
+
+
+def extrapolate_round_evals(staggered, skip: int, degree: int, max_domain_size: int):
+    """univariate.rs:565-640: `staggered` = the (degree-1)*2^skip evaluations after the skipped domain (a longer
+    list is truncated to them); returns the max_domain_size - 2^skip round evals the reference outputs."""
+    n_points = max_domain_size - (1 << skip)
+    n_in = max(degree - 1, 0) << skip
+    vals = np.zeros((max(n_points, 1), 2), np.uint64)
+    if n_in:
+        vals[:n_in] = to_arr(list(staggered[:n_in]))
+    lib().orc_extrapolate_round_evals(C.c_uint32(skip), C.c_uint32(degree), C.c_uint32(max_domain_size), _p(vals))
+    return to_ints(vals)[:n_points]
+
+
+def zerocheck_univariate_evals_reference(mls, levels, n_vars, skip, eq_ind, comps, degrees, max_domain_size):
+    """What the reference's zerocheck_univariate_evals returns (univariate.rs:235-500): each composition
+    evaluated at its (deg-1)*2^skip points, then extended to max_domain_size assuming zeros on the skipped domain."""
+    full = zerocheck_univariate_evals(mls, levels, n_vars, skip, eq_ind, comps, max_domain_size)
+    return [extrapolate_round_evals(v, skip, d, max_domain_size) for v, d in zip(full, degrees)]
+
+
+# ------------------------------------------------------------------------------------------------
 # additive NTT
 _NP_DT = {3: np.uint8, 4: np.uint16, 5: np.uint32, 6: np.uint64}
 

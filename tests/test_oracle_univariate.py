@@ -1,0 +1,124 @@
+"""Oracle of the zerocheck univariate-skip round (oracle/univariate.c) checked against independent
+restatements: Lagrange-basis identities, the skip = 0 degenerate case (plain eq-weighted sums), linearity
+(a degree-1 "composition" = an inner product with L(x_i) (x) eq), and the reference's own test setting
+(core/src/protocols/sumcheck/prove/univariate.rs:806-915: zero-product B1 multilinears), on which the
+definition and the reference's evaluate-then-extrapolate route (univariate.rs:565-640) must coincide."""
+import random
+
+import numpy as np
+import pytest
+
+
+def pack_scalars(vals, lvl):
+    """2^(7-lvl) scalars of 2^lvl bits per B128 word, low limb first (binary_field.rs:600-607)"""
+    per = 1 << (7 - lvl)
+    bits = 1 << lvl
+    words = []
+    for w in range((len(vals) + per - 1) // per):
+        x = 0
+        for j, v in enumerate(vals[w * per:(w + 1) * per]):
+            x |= v << (j * bits)
+        words.append(x)
+    return words
+
+
+def zero_product_columns(rng, n_vars, degree):
+    """generate_zero_product_multilinears (core test_utils): B1 columns whose product vanishes everywhere"""
+    n = 1 << n_vars
+    cols = [[rng.getrandbits(1) for _ in range(n)] for _ in range(degree)]
+    for i in range(n):
+        cols[rng.randrange(degree)][i] = 0
+    return cols
+
+
+def product(ix):
+    steps = [("var", i) for i in ix]
+    acc = 0
+    for t in range(1, len(ix)):
+        steps.append(("mul", acc, t))
+        acc = len(steps) - 1
+    return steps
+
+
+def test_lagrange_basis_identities(oracle):
+    for k in (0, 1, 3, 5):
+        n = 1 << k
+        for u in range(n):  # L_t(u) = [t == u]
+            assert oracle.lagrange_evals(k, u) == [int(t == u) for t in range(n)]
+        for x in (n, n + 1, 0xAB, 0xFF):  # partition of unity, and values stay in B8
+            ev = oracle.lagrange_evals(k, x)
+            acc = 0
+            for v in ev:
+                acc ^= v
+                assert v < 256
+            assert acc == 1
+        # extrapolating f(t) = t (degree 1) reproduces f
+        if k >= 1:
+            ev = oracle.lagrange_evals(k, 0xC5)
+            acc = 0
+            for t, v in enumerate(ev):
+                acc ^= oracle.mul(v, t)
+            assert acc == 0xC5
+
+
+def test_skip_zero_is_a_plain_weighted_sum(oracle):
+    rng = random.Random(5)
+    n_vars = 6
+    cols = [[rng.getrandbits(8) for _ in range(1 << n_vars)] for _ in range(3)]
+    mls = [oracle.to_arr(pack_scalars(c, 3)) for c in cols]
+    eq = [rng.getrandbits(128) for _ in range(1 << n_vars)]
+    comp = product([0, 1, 2])
+    got = oracle.zerocheck_univariate_evals(mls, [3, 3, 3], n_vars, 0, oracle.to_arr(eq), [comp], 4)
+    exp = 0
+    for s in range(1 << n_vars):
+        exp ^= oracle.mul(eq[s], oracle.mul(oracle.mul(cols[0][s], cols[1][s]), cols[2][s]))
+    assert got == [[exp] * 3]
+
+
+@pytest.mark.parametrize("lvl", [0, 3, 5])
+def test_linear_composition_is_an_inner_product(oracle, lvl):
+    rng = random.Random(lvl)
+    n_vars, skip = 8, 3
+    K = 1 << skip
+    col = [rng.getrandbits(1 << lvl) for _ in range(1 << n_vars)]
+    ml = oracle.to_arr(pack_scalars(col, lvl))
+    eq = [rng.getrandbits(128) for _ in range(1 << (n_vars - skip))]
+    got = oracle.zerocheck_univariate_evals([ml], [lvl], n_vars, skip, oracle.to_arr(eq), [[("var", 0)]], 3 * K)[0]
+    for i in (0, 1, K, 2 * K - 1):
+        lag = oracle.lagrange_evals(skip, K + i)
+        weights = [oracle.mul(eq[s], lag[t]) for s in range(len(eq)) for t in range(K)]
+        assert got[i] == oracle.inner_product(ml, lvl, oracle.to_arr(weights))
+
+
+@pytest.mark.parametrize("skip", [0, 1, 2, 4])
+def test_reference_setting_definition_equals_extrapolation(oracle, skip):
+    """On a true zerocheck instance the reference's route (evaluate at (deg-1)*2^k points, prepend zeros,
+    interpolate, extend) equals the definition at every point of the domain."""
+    rng = random.Random(100 + skip)
+    n_vars = 6
+    cols = zero_product_columns(rng, n_vars, 2) + zero_product_columns(rng, n_vars, 3) + zero_product_columns(rng, n_vars, 4)
+    mls = [oracle.to_arr(pack_scalars(c, 0)) for c in cols]
+    comps = [product([0, 1]), product([2, 3, 4]), product([5, 6, 7, 8])]
+    degrees = [2, 3, 4]
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    eq = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << len(ch)) - 1)), 0, ch)
+    max_domain = 5 << skip
+    full = oracle.zerocheck_univariate_evals(mls, [0] * 9, n_vars, skip, eq, comps, max_domain)
+    ref = oracle.zerocheck_univariate_evals_reference(mls, [0] * 9, n_vars, skip, eq, comps, degrees, max_domain)
+    assert all(len(v) == 4 << skip for v in full)
+    assert full == ref
+    assert skip == 0 or any(v != 0 for v in full[0])
+
+
+def test_extrapolation_differs_off_a_true_instance(oracle):
+    """With a composition that does not vanish on the cube the two routes differ beyond deg*2^k points --
+    the product follows the reference's route (zeros assumed on the skipped domain)."""
+    rng = random.Random(9)
+    n_vars, skip = 5, 2
+    cols = [[rng.getrandbits(1) for _ in range(1 << n_vars)] for _ in range(2)]
+    mls = [oracle.to_arr(pack_scalars(c, 0)) for c in cols]
+    eq = oracle.rand_b128(3, 1 << (n_vars - skip))
+    comps = [product([0, 1])]
+    full = oracle.zerocheck_univariate_evals(mls, [0, 0], n_vars, skip, eq, comps, 16)[0]
+    ref = oracle.zerocheck_univariate_evals_reference(mls, [0, 0], n_vars, skip, eq, comps, [2], 16)[0]
+    assert full[:4] == ref[:4] and full[4:] != ref[4:]
