@@ -26,7 +26,7 @@ SYMBOLS = [
     "b200_ntt_destroy", "b200_ntt_log_domain_size", "b200_ntt_get_subspace_eval", "b200_ntt_forward",
     "b200_ntt_inverse", "b200_ntt_forward_host", "b200_ntt_inverse_host", "b200_fri_fold",
     "b200_tensor_product_full_query", "b200_fold_multilinears_high_to_low", "b200_eq_ind_round_evals",
-    "b200_sumcheck_round_evals", "b200_fold_multilinears_low_to_high",
+    "b200_sumcheck_round_evals", "b200_fold_multilinears_low_to_high", "b200_zerocheck_univariate_evals",
 ]
 
 
@@ -101,6 +101,7 @@ def load() -> C.CDLL:
         "b200_eq_ind_round_evals": (i32, [vp, P(vp), P(u64), P(u64), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(u32)]),
         "b200_sumcheck_round_evals": (i32, [vp, u32, P(vp), P(u64), P(u64), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(u32)]),
         "b200_fold_multilinears_low_to_high": (i32, [vp, P(vp), P(vp), u32, u32, P(u64), P(u64), P(u64), P(u64)]),
+        "b200_zerocheck_univariate_evals": (i32, [vp, P(vp), P(u32), u32, u32, u32, vp, u64, P(vp), P(u32), u32, u32, P(u64)]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the build is stale: fail loudly

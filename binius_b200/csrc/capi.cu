@@ -16,6 +16,7 @@
 #include "ntt.cuh"
 #include "ntt_bs.cuh"
 #include "roundevals_tc.cuh"
+#include "univariate.cuh"
 
 using namespace b200;
 
@@ -1381,3 +1382,141 @@ int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint
 }
 
 }  // extern "C"
+
+// ---- zerocheck univariate-skip round (core/src/protocols/sumcheck/prove/univariate.rs:235-500) ---------
+// Lagrange basis over the B8 points 0..n-1 at x (x not a node): L_t(x) = w_t * prod_u (x - u) / (x - t)
+static void lagrange_b8(uint32_t n, uint32_t x, uint8_t *out) {
+	const hostf::Tab8 &tb = hostf::tab8();
+	auto mul = [&](uint32_t a, uint32_t b) -> uint32_t { return tb.mul[(a << 8) | b]; };
+	uint32_t full = 1;
+	for (uint32_t u = 0; u < n; u++) full = mul(full, x ^ u);
+	for (uint32_t t = 0; t < n; t++) {
+		uint32_t den = 1;
+		for (uint32_t u = 0; u < n; u++)
+			if (u != t) den = mul(den, t ^ u);
+		den = mul(den, x ^ t);
+		out[t] = (uint8_t)mul(full, (uint32_t)hostf::invert((hostf::u128)den, 3));
+	}
+}
+static uint32_t const_level(uint64_t lo, uint64_t hi) {
+	if (hi) return 7;
+	if (lo >> 32) return 6;
+	if (lo >> 16) return 5;
+	if (lo >> 8) return 4;
+	return 3;
+}
+
+int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint64_t *host_out) {
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
+	if (n_vars - skip > 40) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars - skip_rounds must be <= 40");
+	if (n_eq != (1ull << (n_vars - skip))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectZerocheckChallengesLength: eq_ind must hold 2^(n_vars - skip_rounds) elements");
+	if (max_domain_size > 256) return fail(ctx, B200_ERR_INPUT_VALIDATION, "DomainSizeTooLarge: max_domain_size %u exceeds the B8 domain field", max_domain_size);
+	if (m > uni::MAX_MLS || n_comp > uni::MAX_COMP) return fail(ctx, B200_ERR_INPUT_VALIDATION, "at most %u multilinears and %u compositions per call", uni::MAX_MLS, uni::MAX_COMP);
+	uint32_t max_deg = 0, lvl = 3;
+	for (uint32_t c = 0; c < n_comp; c++) {
+		if (!comps[c] || comps[c]->n_vars > m) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition %u does not match the multilinears", c);
+		max_deg = std::max(max_deg, degrees[c]);
+		for (const b200_expr_step &st : comps[c]->steps)
+			if (st.op == 3) lvl = std::max(lvl, const_level(st.c_lo, st.c_hi));
+	}
+	if (skip >= 8 || (uint64_t)max_deg << skip > max_domain_size || max_domain_size < (1u << skip)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "LagrangeDomainTooSmall: max_domain_size %u < %u << %u", max_domain_size, max_deg, skip);
+	for (uint32_t j = 0; j < m; j++) {
+		if (!valid_level(levels[j])) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: unsupported tower level %u", j, levels[j]);
+		if (!mls[j]) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u is null", j);
+		lvl = std::max(lvl, levels[j]);
+	}
+	if (lvl == 6) lvl = 7;
+	const uint32_t K = 1u << skip, n_out = max_domain_size - K;
+	if (n_out == 0 || n_comp == 0) return B200_OK;
+	if (!host_out) return B200_ERR_INPUT_VALIDATION;
+	const uint32_t n_pts = max_deg > 1 ? (max_deg - 1) << skip : 0;
+
+	int32_t rc = ensure_scratch(ctx, (uint64_t)n_comp * n_out * 16);
+	if (rc) return rc;
+	uint4 *d_out = reinterpret_cast<uint4 *>(ctx->d_scratch);
+	B200_CUDA(ctx, cudaMemsetAsync(d_out, 0, (uint64_t)n_comp * n_out * 16, ctx->stream));
+	if (n_pts) {
+		std::vector<uint8_t> lag((size_t)n_pts * K);
+		for (uint32_t i = 0; i < n_pts; i++) lagrange_b8(K, K + i, lag.data() + (size_t)i * K);
+		std::vector<DevExpr> hc(n_comp);
+		std::vector<uint32_t> pts(n_comp), ext_off(n_comp, 0);
+		// extension matrices, one per distinct degree below the maximum
+		std::vector<uint8_t> ext;
+		std::map<uint32_t, uint32_t> ext_of_deg;
+		bool need_ext = false;
+		for (uint32_t c = 0; c < n_comp; c++) {
+			hc[c] = dev_expr(comps[c]);
+			pts[c] = degrees[c] > 1 ? (degrees[c] - 1) << skip : 0;
+			if (pts[c] == 0 || pts[c] >= n_out) continue;
+			need_ext = true;
+			auto it = ext_of_deg.find(degrees[c]);
+			if (it == ext_of_deg.end()) {
+				const uint32_t n_nodes = degrees[c] << skip, n_in = pts[c];
+				uint32_t off = (uint32_t)ext.size();
+				ext.resize(off + (size_t)(n_out - n_in) * n_in);
+				std::vector<uint8_t> row(n_nodes);
+				for (uint32_t i = n_in; i < n_out; i++) {
+					lagrange_b8(n_nodes, K + i, row.data());
+					memcpy(ext.data() + off + (size_t)(i - n_in) * n_in, row.data() + K, n_in);
+				}
+				it = ext_of_deg.emplace(degrees[c], off).first;
+			}
+			ext_off[c] = it->second;
+		}
+		ArgPack pk;
+		size_t o_mls = pk.add(mls, sizeof(void *) * m), o_lv = pk.add(levels, 4 * m), o_c = pk.add(hc.data(), sizeof(DevExpr) * n_comp);
+		size_t o_p = pk.add(pts.data(), 4 * n_comp), o_l = pk.add(lag.data(), lag.size()), o_eo = pk.add(ext_off.data(), 4 * n_comp);
+		size_t o_e = pk.add(ext.data(), ext.size());
+		uint8_t *base;
+		rc = pk.commit(ctx, &base);
+		if (rc) return rc;
+		uni::Args A;
+		A.mls = (const uint4 *const *)(base + o_mls);
+		A.levels = (const uint32_t *)(base + o_lv);
+		A.comps = (const DevExpr *)(base + o_c);
+		A.comp_pts = (const uint32_t *)(base + o_p);
+		A.lag = base + o_l;
+		A.eq = (const uint4 *)eq_ind;
+		A.out = d_out;
+		A.n_sub = n_eq;
+		A.m = m, A.n_comp = n_comp, A.skip = skip, A.n_pts = n_pts, A.n_out = n_out;
+		A.off_nl = (FIELD_TABLE_BYTES + K * K + 15) & ~15u;
+		A.off_red = A.off_nl + (K >= 4 ? 4 * K * K : 0);
+		const uint32_t smem = A.off_red + uni::THREADS * 16;
+		const uint32_t SL = uni::THREADS >> skip, gy = n_pts >> skip;
+		const uint32_t per_sm = std::max(1u, std::min(8u, (227u * 1024u) / (smem + 1024u)));
+		const uint64_t want = (n_eq + SL - 1) / SL;
+		const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, std::max(1u, ctx->n_sms * per_sm / gy)));
+		dim3 grid(gx, gy);
+		switch (lvl) {
+		case 3:
+			if ((rc = set_smem(ctx, uni::k_uni_evals<3>, smem))) return rc;
+			uni::k_uni_evals<3><<<grid, uni::THREADS, smem, ctx->stream>>>(ctx->d_tables, A);
+			break;
+		case 4:
+			if ((rc = set_smem(ctx, uni::k_uni_evals<4>, smem))) return rc;
+			uni::k_uni_evals<4><<<grid, uni::THREADS, smem, ctx->stream>>>(ctx->d_tables, A);
+			break;
+		case 5:
+			if ((rc = set_smem(ctx, uni::k_uni_evals<5>, smem))) return rc;
+			uni::k_uni_evals<5><<<grid, uni::THREADS, smem, ctx->stream>>>(ctx->d_tables, A);
+			break;
+		default:
+			if ((rc = set_smem(ctx, uni::k_uni_evals<7>, smem))) return rc;
+			uni::k_uni_evals<7><<<grid, uni::THREADS, smem, ctx->stream>>>(ctx->d_tables, A);
+			break;
+		}
+		B200_LAUNCH_CHECK(ctx);
+		if (need_ext) {
+			uni::ExtArgs X{A.comp_pts, (const uint32_t *)(base + o_eo), base + o_e, d_out, n_out};
+			if ((rc = set_smem(ctx, uni::k_uni_extend, FIELD_TABLE_BYTES))) return rc;
+			uni::k_uni_extend<<<n_comp, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, X);
+			B200_LAUNCH_CHECK(ctx);
+		}
+	}
+	B200_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (uint64_t)n_comp * n_out * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return B200_OK;
+}

@@ -1,0 +1,244 @@
+// univariate.cuh -- the zerocheck univariate-skip round.
+//
+// Reference: zerocheck_univariate_evals, core/src/protocols/sumcheck/prove/univariate.rs:235-500, with
+// ntt_extrapolate (:642-678), spread_product (:503-563) and extrapolate_round_evals (:565-640).
+//
+//   R[c][i] = sum_{s < 2^(n-k)} eq[s] * C_c( P_0(s, x_i), ..., P_{m-1}(s, x_i) ),      x_i = B8(2^k + i)
+//   P_j(s, x) = extrapolation of M_j[s*2^k .. (s+1)*2^k) from the B8 points 0..2^k-1 to x
+//
+// The reference extrapolates with an inverse + coset-forward additive NTT over B8; any exact evaluation of
+// the same polynomial is bit-identical, and this kernel uses the Lagrange form with the B8 coefficients
+// L_t(x_i) staged in shared memory: a B1 column needs no multiplication at all (the extrapolated value is
+// the XOR of the coefficients selected by the sub-cube's bits, four bits per nibble-table lookup).  All
+// composition arithmetic runs in the base field FBase = smallest tower level >= B8 holding every column and
+// constant (B8 products are one shared-memory table lookup), as the reference's PackedSubfield<P, FBase>
+// evaluation does; only the final eq[s] * value product touches B128 (limb-wise, binary_field.rs:363-393).
+//
+// Thread mapping: a CTA owns 2^k consecutive evaluation points (blockIdx.y) and walks sub-cubes
+// (blockIdx.x, grid-stride); thread = (point, sub-cube lane).  Per-thread accumulators, one per
+// composition, live in local memory; they are combined across sub-cube lanes in shared memory and across
+// CTAs by XOR atomics on the [composition][point] table.
+#pragma once
+#include "field.cuh"
+#include "kernels.cuh"
+
+namespace b200 {
+namespace uni {
+
+constexpr uint32_t THREADS = 256;
+constexpr uint32_t MAX_COMP = 128;  // compositions per call (accumulators per thread)
+constexpr uint32_t MAX_MLS = 256;   // multilinears per call
+
+struct Args {
+	const uint4 *const *mls;   // device [m]: packed sub-field multilinears
+	const uint32_t *levels;    // device [m]: their tower levels
+	const DevExpr *comps;      // device [n_comp]
+	const uint32_t *comp_pts;  // device [n_comp]: (deg_c - 1) << skip evaluation points of composition c
+	const uint8_t *lag;        // device [n_pts][2^skip]: L_t(x_i) in B8
+	const uint4 *eq;           // 2^(n_vars - skip) B128
+	uint4 *out;                // [n_comp][n_out] accumulators (zeroed)
+	uint64_t n_sub;
+	uint32_t m, n_comp, skip, n_pts, n_out;
+	uint32_t off_nl, off_red;  // shared-memory offsets of the nibble table and the reduction buffer
+};
+
+// base-field value types
+template <uint32_t LVL> struct Fb;
+template <> struct Fb<3> {
+	typedef uint32_t V;
+	static __device__ __forceinline__ V from_u32(uint32_t x) { return x; }
+	static __device__ __forceinline__ V from128(uint4 a) { return a.x & 0xffu; }
+	static __device__ __forceinline__ uint4 to128(V a) { return make_uint4(a, 0, 0, 0); }
+	static __device__ __forceinline__ V mul(const FieldTables &T, V a, V b) { return f_mul8(T, a, b); }
+	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8(T, a, c); }
+};
+template <> struct Fb<4> {
+	typedef uint32_t V;
+	static __device__ __forceinline__ V from_u32(uint32_t x) { return x; }
+	static __device__ __forceinline__ V from128(uint4 a) { return a.x & 0xffffu; }
+	static __device__ __forceinline__ uint4 to128(V a) { return make_uint4(a, 0, 0, 0); }
+	static __device__ __forceinline__ V mul(const FieldTables &T, V a, V b) { return f_mul16(T, a, b); }
+	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8(T, a & 0xff, c) | (f_mul8(T, a >> 8, c) << 8); }
+};
+template <> struct Fb<5> {
+	typedef uint32_t V;
+	static __device__ __forceinline__ V from_u32(uint32_t x) { return x; }
+	static __device__ __forceinline__ V from128(uint4 a) { return a.x; }
+	static __device__ __forceinline__ uint4 to128(V a) { return make_uint4(a, 0, 0, 0); }
+	static __device__ __forceinline__ V mul(const FieldTables &T, V a, V b) { return f_mul32(T, a, b); }
+	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8x4(T, a, c); }
+};
+template <> struct Fb<7> {
+	typedef uint4 V;
+	static __device__ __forceinline__ V from_u32(uint32_t x) { return make_uint4(x, 0, 0, 0); }
+	static __device__ __forceinline__ V from128(uint4 a) { return a; }
+	static __device__ __forceinline__ uint4 to128(V a) { return a; }
+	static __device__ __forceinline__ V mul(const FieldTables &T, V a, V b) { return f_mul128(T, a, b); }
+	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul128_sub(T, a, make_uint4(c, 0, 0, 0), 3); }
+};
+
+// scalar `idx` of a packed sub-field multilinear (2^(7-lvl) scalars per B128 word, low limb first)
+template <uint32_t LVL>
+__device__ __forceinline__ typename Fb<LVL>::V load_scalar(const uint4 *ml, uint32_t lvl, uint64_t idx) {
+	typedef Fb<LVL> F;
+	switch (lvl) {
+	case 0: return F::from_u32((__ldg(reinterpret_cast<const uint32_t *>(ml) + (idx >> 5)) >> (idx & 31)) & 1u);
+	case 3: return F::from_u32(__ldg(reinterpret_cast<const uint8_t *>(ml) + idx));
+	case 4: return F::from_u32(__ldg(reinterpret_cast<const uint16_t *>(ml) + idx));
+	case 5: return F::from_u32(__ldg(reinterpret_cast<const uint32_t *>(ml) + idx));
+	default:
+		if constexpr (LVL == 7) {
+			if (lvl == 6) {
+				uint2 v = __ldg(reinterpret_cast<const uint2 *>(ml) + idx);
+				return make_uint4(v.x, v.y, 0, 0);
+			}
+			return __ldg(ml + idx);
+		} else {
+			return F::from_u32(0);
+		}
+	}
+}
+
+// ArithCircuit over the base field (math/src/arith_expr.rs:367-383)
+template <uint32_t LVL>
+__device__ __forceinline__ typename Fb<LVL>::V expr_eval_fb(const FieldTables &T, const DevExpr &E, const typename Fb<LVL>::V *q) {
+	typedef Fb<LVL> F;
+	typename F::V tmp[MAX_EXPR_STEPS];
+	for (uint32_t s = 0; s < E.n_steps; s++) {
+		const b200_expr_step st = E.steps[s];
+		typename F::V v;
+		switch (st.op) {
+		case 0: v = tmp[st.l] ^ tmp[st.r]; break;
+		case 1: v = F::mul(T, tmp[st.l], tmp[st.r]); break;
+		case 2: {
+			typename F::V x = tmp[st.l];
+			uint64_t e = st.r;
+			v = F::from_u32(1);
+			while (e) {
+				if (e & 1) v = F::mul(T, v, x);
+				e >>= 1;
+				if (e) x = F::mul(T, x, x);
+			}
+			break;
+		}
+		case 3: v = F::from128(make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32))); break;
+		default: v = q[st.l]; break;
+		}
+		tmp[s] = v;
+	}
+	return E.n_steps ? tmp[E.n_steps - 1] : F::from_u32(0);
+}
+
+template <uint32_t LVL>
+__global__ void __launch_bounds__(THREADS) k_uni_evals(const uint8_t *__restrict__ g_tables, const Args A) {
+	typedef Fb<LVL> F;
+	typedef typename F::V V;
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	const uint32_t K = 1u << A.skip, tid = threadIdx.x;
+	uint8_t *lagS = smem + FIELD_TABLE_BYTES;  // [t][point]: L_t(x_point)
+	uint8_t *NL = smem + A.off_nl;             // [nibble][pattern][point]: XOR of the coefficients the pattern selects
+	uint4 *red = reinterpret_cast<uint4 *>(smem + A.off_red);
+	const uint32_t p0 = blockIdx.y * K;
+	for (uint32_t idx = tid; idx < K * K; idx += THREADS) {
+		uint32_t t = idx >> A.skip, il = idx & (K - 1);
+		lagS[idx] = A.lag[(uint64_t)(p0 + il) * K + t];
+	}
+	__syncthreads();
+	const bool use_nl = K >= 4;
+	if (use_nl) {
+		for (uint32_t idx = tid; idx < 4 * K * K; idx += THREADS) {
+			uint32_t il = idx & (K - 1), e = idx >> A.skip, pat = e & 15, nib = e >> 4;
+			uint32_t v = 0;
+#pragma unroll
+			for (uint32_t b = 0; b < 4; b++)
+				if (pat >> b & 1) v ^= lagS[((4 * nib + b) << A.skip) + il];
+			NL[idx] = (uint8_t)v;
+		}
+		__syncthreads();
+	}
+	const uint32_t il = tid & (K - 1), sl = tid >> A.skip, SL = THREADS >> A.skip;
+	const uint32_t i = p0 + il;
+
+	uint4 acc[MAX_COMP];
+	V q[MAX_MLS];
+	for (uint32_t c = 0; c < A.n_comp; c++) acc[c] = u4_zero();
+
+	for (uint64_t s = (uint64_t)blockIdx.x * SL + sl; s < A.n_sub; s += (uint64_t)gridDim.x * SL) {
+		const uint64_t base = s << A.skip;
+		for (uint32_t j = 0; j < A.m; j++) {
+			const uint4 *ml = A.mls[j];
+			const uint32_t lvl = A.levels[j];
+			V v = F::from_u32(0);
+			if (lvl == 0 && use_nl) {
+				const uint32_t *w = reinterpret_cast<const uint32_t *>(ml) + (base >> 5);
+				if (K >= 32) {
+					for (uint32_t ww = 0; ww < (K >> 5); ww++) {
+						uint32_t bits = __ldg(w + ww);
+						uint32_t x = 0;
+#pragma unroll
+						for (uint32_t n = 0; n < 8; n++) x ^= NL[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) * K + il];
+						v = v ^ F::from_u32(x);
+					}
+				} else {
+					uint32_t bits = __ldg(w) >> (base & 31);
+					uint32_t x = 0;
+					for (uint32_t n = 0; n < (K >> 2); n++) x ^= NL[((n << 4) + ((bits >> (4 * n)) & 15u)) * K + il];
+					v = F::from_u32(x);
+				}
+			} else if (lvl == 0) {
+				for (uint32_t t = 0; t < K; t++) {
+					uint32_t bit = (__ldg(reinterpret_cast<const uint32_t *>(ml) + ((base + t) >> 5)) >> ((base + t) & 31)) & 1u;
+					if (bit) v = v ^ F::from_u32(lagS[(t << A.skip) + il]);
+				}
+			} else {
+				for (uint32_t t = 0; t < K; t++) v = v ^ F::mulc(T, load_scalar<LVL>(ml, lvl, base + t), lagS[(t << A.skip) + il]);
+			}
+			q[j] = v;
+		}
+		const uint4 e = __ldg(A.eq + s);
+		for (uint32_t c = 0; c < A.n_comp; c++) {
+			if (i >= A.comp_pts[c]) continue;
+			V val = expr_eval_fb<LVL>(T, A.comps[c], q);
+			acc[c] ^= f_mul128_sub(T, e, F::to128(val), LVL);
+		}
+	}
+	for (uint32_t c = 0; c < A.n_comp; c++) {
+		red[tid] = acc[c];
+		__syncthreads();
+		if (sl == 0 && i < A.comp_pts[c]) {
+			uint4 v = red[il];
+			for (uint32_t l = 1; l < SL; l++) v ^= red[(l << A.skip) + il];
+			atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, v);
+		}
+		__syncthreads();
+	}
+}
+
+// extrapolate_round_evals (univariate.rs:565-640): composition c was evaluated at n_in = (deg_c-1)*2^k
+// points; with zeros on the skipped domain those values determine a polynomial of degree < deg_c*2^k,
+// whose values on the rest of the domain are B8-linear combinations of the evaluations:
+//   out[c][i] = sum_{t < n_in} E_c[i - n_in][t] * out[c][t]        (i >= n_in)
+struct ExtArgs {
+	const uint32_t *comp_pts;  // device [n_comp]
+	const uint32_t *ext_off;   // device [n_comp]: byte offset of E_c in `ext`
+	const uint8_t *ext;
+	uint4 *out;
+	uint32_t n_out;
+};
+__global__ void __launch_bounds__(256) k_uni_extend(const uint8_t *__restrict__ g_tables, const ExtArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	const uint32_t c = blockIdx.x, n_in = A.comp_pts[c];
+	if (n_in == 0 || n_in >= A.n_out) return;
+	uint4 *row = A.out + (uint64_t)c * A.n_out;
+	const uint8_t *E = A.ext + A.ext_off[c];
+	for (uint32_t i = n_in + threadIdx.x; i < A.n_out; i += blockDim.x) {
+		uint4 acc = u4_zero();
+		for (uint32_t t = 0; t < n_in; t++) acc ^= f_mul128_sub(T, row[t], make_uint4(E[(uint64_t)(i - n_in) * n_in + t], 0, 0, 0), 3);
+		row[i] = acc;
+	}
+}
+
+}  // namespace uni
+}  // namespace b200

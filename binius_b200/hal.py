@@ -104,6 +104,62 @@ class EqIndEvaluator:
         return range(2 if self.have_first_round_eval_1s else 1, self.degree() + 1)
 
 
+@dataclass
+class ZerocheckUnivariateEvalsOutput:
+    """core/src/protocols/sumcheck/prove/univariate.rs:37-50"""
+    round_evals: List[List[int]]
+    skip_rounds: int
+    remaining_rounds: int
+    max_domain_size: int
+    partial_eq_ind_evals: DevSlice
+
+
+def domain_size(composition_degree: int, skip_rounds: int) -> int:
+    """core/src/protocols/sumcheck/zerocheck.rs:131-133"""
+    return composition_degree << skip_rounds
+
+
+def zerocheck_univariate_evals(backend: "B200Backend", multilinears: Sequence[TransparentMultilinear],
+                               compositions: Sequence[ArithCircuit], zerocheck_challenges: Sequence[int],
+                               skip_rounds: int, max_domain_size: int) -> ZerocheckUnivariateEvalsOutput:
+    """Mirror of `zerocheck_univariate_evals` (core/src/protocols/sumcheck/prove/univariate.rs:235-500) with
+    FDomain = BinaryField8b: the round evaluations of every composition at the max_domain_size - 2^skip_rounds
+    domain points after the skipped sub-cube, and the eq-indicator expansion of the remaining challenges.
+    Multilinears are packed sub-field columns on the device (the MLEEmbeddingAdapter layout)."""
+    if not multilinears:
+        raise InputValidation("NumberOfVariablesMismatch: no multilinears")
+    n_vars = multilinears[0].n_vars
+    if any(ml.n_vars != n_vars for ml in multilinears):
+        raise InputValidation("NumberOfVariablesMismatch")
+    if skip_rounds > n_vars:
+        raise InputValidation("TooManySkippedRounds")
+    remaining_rounds = n_vars - skip_rounds
+    if len(zerocheck_challenges) != remaining_rounds:
+        raise InputValidation("IncorrectZerocheckChallengesLength")
+    degrees = [_degree(c) for c in compositions]
+    if max_domain_size < domain_size(max(degrees, default=0), skip_rounds):
+        raise InputValidation("LagrangeDomainTooSmall")
+    if max_domain_size > 256:
+        raise InputValidation("DomainSizeTooLarge")
+    L = backend._l
+    partial_eq_ind_evals = backend.tensor_product_full_query(zerocheck_challenges)
+    m, nc = len(multilinears), len(compositions)
+    n_out = max_domain_size - (1 << skip_rounds)
+    ptrs = (C.c_void_p * m)(*[ml.evals.ptr for ml in multilinears])
+    lvls = (C.c_uint32 * m)(*[ml.tower_level for ml in multilinears])
+    for ml in multilinears:
+        if ml.evals.len() << (7 - ml.tower_level) < 1 << n_vars:
+            raise InputValidation("multilinear buffer shorter than 2^n_vars scalars")
+    comps = (C.c_void_p * max(nc, 1))(*[backend._compiled(c)[0].handle.value for c in compositions])
+    degs = (C.c_uint32 * max(nc, 1))(*degrees)
+    out = (C.c_uint64 * max(2 * nc * n_out, 2))()
+    L._check(L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lvls, m, n_vars, skip_rounds, partial_eq_ind_evals.ptr,
+                                                    partial_eq_ind_evals.len(), comps, degs, nc, max_domain_size, out))
+    vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(nc * n_out)]
+    return ZerocheckUnivariateEvalsOutput([vals[c * n_out:(c + 1) * n_out] for c in range(nc)], skip_rounds,
+                                          remaining_rounds, max_domain_size, partial_eq_ind_evals)
+
+
 class B200Backend:
     """ComputationBackend over one B200Layer."""
 

@@ -231,6 +231,28 @@ int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *mu
 										   const uint64_t *suffix_evals /* 2*m */, const uint64_t challenge[2],
 										   uint64_t *new_lens);
 
+/* ---- zerocheck univariate-skip round ----------------------------------------------------------------
+ * zerocheck_univariate_evals (core/src/protocols/sumcheck/prove/univariate.rs:235-500, with ntt_extrapolate
+ * :642-678, spread_product :503-563, extrapolate_round_evals :565-640), FDomain = BinaryField8b:
+ *   R[c][i] = sum_{s < 2^(n_vars-skip)} eq_ind[s] * C_c(P_0(s, x_i), ..., P_{m-1}(s, x_i)),  x_i = B8(2^skip + i),
+ * P_j(s, .) = the polynomial of degree < 2^skip through the sub-cube M_j[s*2^skip ..] at the B8 points
+ * 0..2^skip-1.  Composition c is evaluated at its (degree_c - 1) << skip points and extended to
+ * max_domain_size with zeros assumed on the skipped domain, exactly as the reference does.
+ * multilins[j]: DEVICE packed sub-field multilinear of 2^n_vars scalars at tower level tower_levels[j]
+ * (0, 3..7; MLEEmbeddingAdapter layout, 2^(7-level) scalars per B128 word, low limb first); the base field
+ * FBase is the smallest level >= 3 holding every column and composition constant.  eq_ind: DEVICE,
+ * tensor_product_full_query(zerocheck_challenges) -- the reference makes that backend call itself
+ * (univariate.rs:313-314) and returns the table as partial_eq_ind_evals.
+ * host_round_evals: 2 * n_compositions * (max_domain_size - 2^skip) words, [composition][point]; synchronous.
+ * Errors (InputValidation): TooManySkippedRounds, IncorrectZerocheckChallengesLength (n_eq),
+ * LagrangeDomainTooSmall (max_domain_size < max degree << skip), DomainSizeTooLarge (max_domain_size > 256);
+ * at most 256 multilinears and 128 compositions per call. */
+int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *multilins, const uint32_t *tower_levels,
+										uint32_t n_multilins, uint32_t n_vars, uint32_t skip_rounds,
+										b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *compositions,
+										const uint32_t *composition_degrees, uint32_t n_compositions,
+										uint32_t max_domain_size, uint64_t *host_round_evals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,169 @@
+"""GPU parity tests of the zerocheck univariate-skip round (b200_zerocheck_univariate_evals) against the
+oracle (oracle/univariate.c), through the C ABI via the Python mirror of
+`zerocheck_univariate_evals` (core/src/protocols/sumcheck/prove/univariate.rs:235-500)."""
+import random
+
+import numpy as np
+import pytest
+
+from test_oracle_univariate import pack_scalars, zero_product_columns
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hal():
+    import binius_b200
+
+    layer = binius_b200.B200Layer(0)
+    yield layer
+    layer.close()
+
+
+def _product(ix):
+    from binius_b200 import ArithCircuit as A
+
+    acc = A.var(ix[0])
+    for i in ix[1:]:
+        acc = acc * A.var(i)
+    return acc
+
+
+def _run(hal, oracle, cols, levels, n_vars, skip, comps, max_domain, challenges):
+    from binius_b200.hal import B200Backend, TransparentMultilinear, _degree, zerocheck_univariate_evals
+
+    be = B200Backend(hal)
+    packed = [oracle.to_arr(pack_scalars(c, l)) for c, l in zip(cols, levels)]
+    mls = [TransparentMultilinear(hal.to_device(p), l, n_vars) for p, l in zip(packed, levels)]
+    out = zerocheck_univariate_evals(be, mls, comps, challenges, skip, max_domain)
+    eq = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << len(challenges)) - 1)), 0, challenges)
+    assert np.array_equal(hal.to_host(out.partial_eq_ind_evals), eq)
+    exp = oracle.zerocheck_univariate_evals_reference(packed, levels, n_vars, skip, eq, [list(c.steps) for c in comps],
+                                                      [_degree(c) for c in comps], max_domain)
+    assert out.skip_rounds == skip and out.remaining_rounds == n_vars - skip and out.max_domain_size == max_domain
+    return out.round_evals, exp, packed, eq
+
+
+@pytest.mark.parametrize("skip", [0, 1, 2, 3, 4, 5])
+def test_reference_test_setting(hal, oracle, skip):
+    """univariate.rs:806-915: n_vars = 7, zero-product B1 multilinears of degree 2, 3 and 4,
+    max_domain_size = domain_size(5, skip); compared with the definition (the reference's naive check)."""
+    rng = random.Random(skip)
+    n_vars = 7
+    cols = zero_product_columns(rng, n_vars, 2) + zero_product_columns(rng, n_vars, 3) + zero_product_columns(rng, n_vars, 4)
+    comps = [_product([0, 1]), _product([2, 3, 4]), _product([5, 6, 7, 8])]
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    got, exp, packed, eq = _run(hal, oracle, cols, [0] * 9, n_vars, skip, comps, 5 << skip, ch)
+    assert all(len(v) == 4 << skip for v in got)
+    assert got == exp
+    naive = oracle.zerocheck_univariate_evals(packed, [0] * 9, n_vars, skip, eq, [list(c.steps) for c in comps], 5 << skip)
+    assert got == naive
+
+
+@pytest.mark.parametrize("levels,skip,n_vars", [((0, 3, 0, 3), 3, 8), ((0, 4, 3, 0), 2, 7), ((5, 0, 3, 4), 4, 8), ((7, 0, 6, 3), 1, 6),
+                                                ((0, 0, 0, 0), 6, 10), ((3, 3, 0, 0), 7, 9)])
+def test_mixed_levels_random_instances(hal, oracle, levels, skip, n_vars):
+    """Random (unsatisfied) instances over mixed sub-fields, constants and powers in the compositions, a
+    composition of lower degree than the maximum (extended the reference's way) and a linear one (all zero)."""
+    from binius_b200 import ArithCircuit as A
+
+    rng = random.Random(hash((levels, skip)) & 0xFFFF)
+    cols = [[rng.getrandbits(1 << l) for _ in range(1 << n_vars)] for l in levels]
+    base = max(max(levels), 3)
+    cst = rng.getrandbits(1 << base) | 1
+    x, y, z, w = (A.var(i) for i in range(4))
+    comps = [(x + z) * (y + w) + A.constant(cst) * z, x + y + w, (x * y + z).pow(2) if skip < 6 else x * y, x * w * (y + A.constant(1))]
+    from binius_b200.hal import _degree
+
+    max_deg = max(_degree(c) for c in comps)
+    max_domain = min(256, (max_deg << skip) + (3 if skip < 5 else 0))
+    if max_deg << skip > 256:
+        comps = comps[:2]
+        max_domain = 256 if skip == 7 else 2 << skip
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    got, exp, _, _ = _run(hal, oracle, cols, list(levels), n_vars, skip, comps, max_domain, ch)
+    assert got == exp
+    assert all(v == 0 for v in got[1])
+
+
+def test_many_subcubes_keccak_like_shape(hal, oracle):
+    """B1 columns, skip = 6 (64-point sub-cubes), degree-2 chi-like constraints, 2^14 rows: many sub-cubes per
+    CTA lane and several CTAs per point block."""
+    from binius_b200 import ArithCircuit as A
+
+    rng = random.Random(77)
+    n_vars, skip, m = 14, 6, 6
+    cols = [[rng.getrandbits(1) for _ in range(1 << n_vars)] for _ in range(m)]
+    v = [A.var(i) for i in range(m)]
+    comps = [(v[0] + A.constant(1)) * v[1] + v[2] + v[3], v[4] * v[5] + v[0], v[1] * v[3] + v[2] * v[5]]
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    got, exp, _, _ = _run(hal, oracle, cols, [0] * m, n_vars, skip, comps, 128, ch)
+    assert all(len(r) == 64 for r in got)
+    assert got == exp
+
+
+def test_linear_composition_at_full_size(hal, oracle):
+    """Size-independent property at 2^20 rows (the keccak 2^18 column length after packing is 2^27 bits; this
+    is the largest size whose host-side weights are built in seconds): for a composition equal to var(0),
+    R[i] = <M_0, L(x_i) (x) eq>, checked with the device inner product on the tensor built on the host.
+    The composition is written x0 + x1*x1 + x1*x1 (= x0 in characteristic 2) so that its declared degree is 2
+    and it is evaluated at 2^skip real points instead of being short-circuited to zero."""
+    from binius_b200 import ArithCircuit as A, SubfieldSlice
+    from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals
+
+    n_vars, skip = 20, 6
+    K = 1 << skip
+    be = B200Backend(hal)
+    mls = [TransparentMultilinear(hal.to_device(oracle.rand_b128(41 + j, 1 << (n_vars - 7))), 0, n_vars) for j in range(2)]
+    rng = random.Random(3)
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    x0, x1 = A.var(0), A.var(1)
+    out = zerocheck_univariate_evals(be, mls, [x0 + x1 * x1 + x1 * x1], ch, skip, 2 * K)
+    eq = hal.to_host(out.partial_eq_ind_evals)
+    for i in (0, 37, K - 1):
+        lag = oracle.lagrange_evals(skip, K + i)
+        w = np.zeros((len(eq), K, 2), np.uint64)  # w[s][t] = eq[s] * L_t(x_i)
+        for t in range(K):
+            w[:, t, :] = oracle.mul_vec(eq, oracle.to_arr([lag[t]] * len(eq)))
+        wd = hal.to_device(w.reshape(-1, 2))
+        got_ip = hal.execute(lambda ex: [ex.inner_product(SubfieldSlice(mls[0].evals, 0), wd)])[0]
+        hal.dev_free(wd)
+        assert out.round_evals[0][i] == got_ip
+
+
+def test_error_behaviour(hal, oracle):
+    from binius_b200 import ArithCircuit as A, InputValidation
+    from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals
+
+    be = B200Backend(hal)
+    n_vars = 6
+    ml = TransparentMultilinear(hal.to_device(oracle.rand_b128(1, 1)), 0, n_vars)
+    comp = A.var(0) * A.var(0)
+    with pytest.raises(InputValidation):  # TooManySkippedRounds
+        zerocheck_univariate_evals(be, [ml], [comp], [], 7, 256)
+    with pytest.raises(InputValidation):  # IncorrectZerocheckChallengesLength
+        zerocheck_univariate_evals(be, [ml], [comp], [1, 2, 3], 2, 8)
+    with pytest.raises(InputValidation):  # LagrangeDomainTooSmall
+        zerocheck_univariate_evals(be, [ml], [comp], [1, 2, 3, 4], 2, 7)
+    with pytest.raises(InputValidation):  # DomainSizeTooLarge
+        zerocheck_univariate_evals(be, [ml], [comp], [1, 2, 3, 4], 2, 300)
+    # the C ABI validates on its own as well
+    import ctypes as C
+
+    L = hal
+    eq = be.tensor_product_full_query([1, 2, 3, 4])
+    ptrs = (C.c_void_p * 1)(ml.evals.ptr)
+    lv = (C.c_uint32 * 1)(0)
+    ce = (C.c_void_p * 1)(be._compiled(comp)[0].handle.value)
+    dg = (C.c_uint32 * 1)(2)
+    out = (C.c_uint64 * 64)()
+    assert L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lv, 1, n_vars, 2, eq.ptr, 15, ce, dg, 1, 8, out) == 1
+    assert L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lv, 1, n_vars, 2, eq.ptr, 16, ce, dg, 1, 7, out) == 1
+    assert L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lv, 1, n_vars, 7, eq.ptr, 16, ce, dg, 1, 8, out) == 1
+    lv[0] = 2
+    assert L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lv, 1, n_vars, 2, eq.ptr, 16, ce, dg, 1, 8, out) == 1
+    # max_domain_size == 2^skip: nothing to evaluate
+    lv[0] = 0
+    dg[0] = 1
+    lin = (C.c_void_p * 1)(be._compiled(A.var(0))[0].handle.value)
+    assert L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lv, 1, n_vars, 2, eq.ptr, 16, lin, dg, 1, 4, out) == 0
