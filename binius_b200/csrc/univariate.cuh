@@ -215,6 +215,145 @@ __global__ void __launch_bounds__(THREADS) k_uni_evals(const uint8_t *__restrict
 	}
 }
 
+// ---- B8 fast path ------------------------------------------------------------------------------------
+// FBase = B8 (every column B1 or B8, constants in B8) and every composition a sum of monomials of degree
+// <= 2 (eqind_plan.hpp) -- the keccak / u32 gadget shape.  Work is organised in batches of SUBS sub-cubes
+// per CTA so that nothing but the final accumulators leaves shared memory:
+//   phase A: thread = (quad of 4 points, sub-cube, column lane): extrapolates 4 points at once -- the nibble
+//            table holds the four B8 coefficients of a point quad in one 32-bit word, so a 64-bit B1
+//            sub-cube costs 16 LDS.32 + 16 XOR for 4 points -- and stores them to qS[column][sub-cube][point].
+//   phase B: thread = (point, composition lane): evaluates its compositions from the monomial list on qS
+//            bytes (one mul8 table lookup per product) and multiplies by eq[s] through two 16-entry B128
+//            tables eq[s]*n and eq[s]*(n<<4) built once per sub-cube (x -> eq[s]*x is GF(2)-linear), i.e.
+//            2 LDS.128 instead of 16 byte products; sums over the batch stay in registers, the per-thread
+//            accumulator (local memory) is touched once per composition and batch.
+constexpr uint32_t B8_THREADS = 512;
+constexpr uint32_t SUBS = 8;
+constexpr uint32_t MONO_NONE = 511;
+struct B8Args {
+	const uint4 *const *mls;   // device [m]
+	const uint32_t *levels;    // device [m] (0 or 3)
+	const uint32_t *mono;      // device: a | b << 9 | coef << 18 per monomial (MONO_NONE = no factor)
+	const uint32_t *comp_tab;  // device [n_comp][3]: first monomial, monomial count, evaluation points
+	const uint8_t *lag;        // device [n_pts][K]
+	const uint4 *eq;
+	uint4 *out;
+	uint64_t n_sub;
+	uint32_t m, n_comp, n_mono, skip, n_out;
+	uint32_t off_nl, off_q, off_es, off_mono, off_ctab, off_cols;  // shared-memory layout
+};
+
+__global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restrict__ g_tables, const B8Args A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	const uint32_t K = 1u << A.skip, PQ = K >> 2, tid = threadIdx.x;
+	uint8_t *lagS = smem + FIELD_TABLE_BYTES;
+	uint32_t *NLw = reinterpret_cast<uint32_t *>(smem + A.off_nl);  // [nibble][pattern][quad]
+	uint8_t *qS = smem + A.off_q;                                   // [column][sub-cube][point]
+	uint4 *ES = reinterpret_cast<uint4 *>(smem + A.off_es);         // [sub-cube][32]
+	uint32_t *monoS = reinterpret_cast<uint32_t *>(smem + A.off_mono);
+	uint32_t *ctabS = reinterpret_cast<uint32_t *>(smem + A.off_ctab);
+	const uint32_t **colP = reinterpret_cast<const uint32_t **>(smem + A.off_cols);
+	uint32_t *colL = reinterpret_cast<uint32_t *>(smem + A.off_cols + 8 * A.m);
+	const uint32_t p0 = blockIdx.y * K;
+	for (uint32_t idx = tid; idx < K * K; idx += B8_THREADS) lagS[idx] = A.lag[(uint64_t)(p0 + (idx & (K - 1))) * K + (idx >> A.skip)];
+	for (uint32_t idx = tid; idx < A.n_mono; idx += B8_THREADS) monoS[idx] = A.mono[idx];
+	for (uint32_t idx = tid; idx < 3 * A.n_comp; idx += B8_THREADS) ctabS[idx] = A.comp_tab[idx];
+	for (uint32_t idx = tid; idx < A.m; idx += B8_THREADS) {
+		colP[idx] = reinterpret_cast<const uint32_t *>(A.mls[idx]);
+		colL[idx] = A.levels[idx];
+	}
+	__syncthreads();
+	for (uint32_t idx = tid; idx < (K >> 2) * 16 * PQ; idx += B8_THREADS) {
+		uint32_t pq = idx % PQ, e = idx / PQ, pat = e & 15, nib = e >> 4, word = 0;
+#pragma unroll
+		for (uint32_t p = 0; p < 4; p++) {
+			uint32_t v = 0;
+#pragma unroll
+			for (uint32_t b = 0; b < 4; b++)
+				if (pat >> b & 1) v ^= lagS[((4 * nib + b) << A.skip) + 4 * pq + p];
+			word |= v << (8 * p);
+		}
+		NLw[idx] = word;
+	}
+	__syncthreads();
+	// phase A coordinates
+	const uint32_t a_pq = tid % PQ, a_r = tid / PQ, a_sb = a_r % SUBS, a_jl = a_r / SUBS, JL = B8_THREADS / (PQ * SUBS);
+	// phase B coordinates
+	const uint32_t il = tid & (K - 1), g = tid >> A.skip, G = B8_THREADS >> A.skip, i = p0 + il;
+	uint4 accL[MAX_COMP / 4];
+#pragma unroll
+	for (uint32_t c = 0; c < MAX_COMP / 4; c++) accL[c] = u4_zero();
+
+	const uint64_t n_batches = (A.n_sub + SUBS - 1) / SUBS;
+	for (uint64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
+		const uint64_t s0 = bt * SUBS;
+		if (tid < SUBS * 32) {
+			uint32_t sb = tid >> 5, e = tid & 31;
+			uint4 eqv = s0 + sb < A.n_sub ? __ldg(A.eq + s0 + sb) : u4_zero();
+			ES[tid] = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
+		}
+		{
+			const uint64_t s = s0 + a_sb;
+			if (s < A.n_sub) {
+				const uint64_t base = s << A.skip;
+				for (uint32_t j = a_jl; j < A.m; j += JL) {
+					uint32_t x = 0;
+					if (colL[j] == 0) {
+						const uint32_t *w = colP[j] + (base >> 5);
+						if (K >= 32) {
+							for (uint32_t ww = 0; ww < (K >> 5); ww++) {
+								const uint32_t bits = __ldg(w + ww);
+#pragma unroll
+								for (uint32_t n = 0; n < 8; n++) x ^= NLw[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) * PQ + a_pq];
+							}
+						} else {
+							const uint32_t bits = __ldg(w) >> (base & 31);
+							for (uint32_t n = 0; n < (K >> 2); n++) x ^= NLw[((n << 4) + ((bits >> (4 * n)) & 15u)) * PQ + a_pq];
+						}
+					} else {
+						const uint8_t *col = reinterpret_cast<const uint8_t *>(colP[j]) + base;
+						for (uint32_t t = 0; t < K; t++) {
+							const uint32_t mv = (uint32_t)__ldg(col + t) << 8;
+							const uint32_t lw = *reinterpret_cast<const uint32_t *>(lagS + (t << A.skip) + 4 * a_pq);
+							x ^= (uint32_t)T.mul8[mv | (lw & 0xff)] | ((uint32_t)T.mul8[mv | ((lw >> 8) & 0xff)] << 8) |
+								 ((uint32_t)T.mul8[mv | ((lw >> 16) & 0xff)] << 16) | ((uint32_t)T.mul8[mv | (lw >> 24)] << 24);
+						}
+					}
+					reinterpret_cast<uint32_t *>(qS)[(j * SUBS + a_sb) * PQ + a_pq] = x;
+				}
+			}
+		}
+		__syncthreads();
+		const uint32_t n_live = (uint32_t)min((uint64_t)SUBS, A.n_sub - s0);
+		for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++) {
+			const uint32_t m0 = ctabS[3 * c], mc = ctabS[3 * c + 1];
+			if (i >= ctabS[3 * c + 2]) continue;
+			uint4 acc = u4_zero();
+			for (uint32_t sb = 0; sb < n_live; sb++) {
+				const uint8_t *qq = qS + sb * K + il;
+				uint32_t val = 0;
+				for (uint32_t t = 0; t < mc; t++) {
+					const uint32_t d = monoS[m0 + t], a = d & 511u, b = (d >> 9) & 511u, cf = d >> 18;
+					uint32_t v;
+					if (a == MONO_NONE) v = cf;
+					else {
+						v = qq[a * SUBS * K];
+						if (b != MONO_NONE) v = T.mul8[(v << 8) | qq[b * SUBS * K]];
+						if (cf != 1) v = T.mul8[(v << 8) | cf];
+					}
+					val ^= v;
+				}
+				acc ^= ES[sb * 32 + (val & 15u)] ^ ES[sb * 32 + 16 + (val >> 4)];
+			}
+			accL[k] ^= acc;
+		}
+		__syncthreads();
+	}
+	for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++)
+		if (i < ctabS[3 * c + 2]) atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, accL[k]);
+}
+
 // extrapolate_round_evals (univariate.rs:565-640): composition c was evaluated at n_in = (deg_c-1)*2^k
 // points; with zeros on the skipped domain those values determine a polynomial of degree < deg_c*2^k,
 // whose values on the rest of the domain are B8-linear combinations of the evaluations:

@@ -1,0 +1,41 @@
+"""Timing of the zerocheck univariate-skip round (b200_zerocheck_univariate_evals) at the keccak shape
+(153 B1 columns, 75 degree-2 chi constraints a*b + c + d, skip_rounds = 6,
+max_domain_size = 128) on synthetic columns.  `python tools/univariate_bench.py [n_vars] [m] [n_comp]`;
+n_vars = 27 is the 2^18-permutation trace (16 MiB per column).  Run on a B200."""
+import ctypes as C
+import os
+import random
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import binius_b200
+from binius_b200 import ArithCircuit as A
+from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals
+
+n_vars = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 153
+n_comp = int(sys.argv[3]) if len(sys.argv) > 3 else 75
+skip = 6
+hal = binius_b200.B200Layer(0)
+be = B200Backend(hal)
+words = 1 << (n_vars - 7)
+arena = hal.dev_alloc(m * words)
+hal.fill(arena, 0x0123456789ABCDEF0F1E2D3C4B5A6978)
+rng = random.Random(1)  # (the kernel's work does not depend on the column values)
+mls = [TransparentMultilinear(arena.slice(j * words, (j + 1) * words), 0, n_vars) for j in range(m)]
+comps = []
+for c in range(n_comp):
+    a, b, d, e = (A.var((2 * c + o) % m) for o in (0, 1, 5, 11))
+    comps.append(a * b + d + e)
+ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+for rep in range(3):
+    hal.sync()
+    t0 = time.perf_counter()
+    out = zerocheck_univariate_evals(be, mls, comps, ch, skip, 2 << skip)  # synchronous (returns host values)
+    dt = time.perf_counter() - t0
+    n_sub = 1 << (n_vars - skip)
+    print(f"n_vars={n_vars} m={m} compositions={n_comp}: {dt * 1e3:.2f} ms per call "
+          f"({n_sub * m / dt / 1e9:.2f} G sub-cube columns/s, {m * words * 16 / dt / 1e9:.1f} GB/s of column data), "
+          f"nonzero={sum(1 for r in out.round_evals for v in r if v)}")
+    hal.dev_free(out.partial_eq_ind_evals)
