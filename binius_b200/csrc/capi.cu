@@ -1492,19 +1492,28 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 		dim3 grid(gx, gy);
 		// B8 fast path: B1/B8 columns, B8 constants, every composition a sum of monomials of degree <= 2
 		bool fast = lvl == 3 && skip >= 2 && !getenv("B200_UNI_GENERIC");
-		std::vector<uint32_t> mono, ctab(3 * (size_t)n_comp);
+		std::vector<uint2> mono;
+		std::vector<uint32_t> ctab(uni::CTAB * (size_t)n_comp);
 		for (uint32_t c = 0; fast && c < n_comp; c++) {
-			if (!comps[c]->poly_ok) fast = false;
-			else {
-				ctab[3 * c] = (uint32_t)mono.size();
-				for (auto &t : comps[c]->poly) {
-					uint32_t a = t.first.size() > 0 ? t.first[0] : uni::MONO_NONE, b = t.first.size() > 1 ? t.first[1] : uni::MONO_NONE;
-					if (t.second >> 8) fast = false;
-					mono.push_back(a | (b << 9) | ((uint32_t)t.second << 18));
-				}
-				ctab[3 * c + 1] = (uint32_t)mono.size() - ctab[3 * c];
-				ctab[3 * c + 2] = pts[c];
+			if (!comps[c]->poly_ok) {
+				fast = false;
+				break;
 			}
+			// monomials in three runs: x_a * x_b and x_a with coefficient 1 (byte offsets into the staged
+			// extrapolations), then everything else
+			std::vector<uint2> quad, lin, gen;
+			for (auto &t : comps[c]->poly) {
+				if (t.second >> 8) fast = false;
+				const size_t deg = t.first.size();
+				if (t.second == 1 && deg == 2) quad.push_back(make_uint2(t.first[0] * uni::SUBS * K, t.first[1] * uni::SUBS * K));
+				else if (t.second == 1 && deg == 1) lin.push_back(make_uint2(t.first[0] * uni::SUBS * K, 0));
+				else gen.push_back(make_uint2((deg > 0 ? t.first[0] : uni::MONO_NONE) | ((deg > 1 ? t.first[1] : uni::MONO_NONE) << 9) | ((uint32_t)t.second << 18), 0));
+			}
+			uint32_t *ct = &ctab[uni::CTAB * c];
+			ct[0] = (uint32_t)mono.size(), ct[1] = (uint32_t)quad.size(), ct[2] = (uint32_t)lin.size(), ct[3] = (uint32_t)gen.size(), ct[4] = pts[c];
+			mono.insert(mono.end(), quad.begin(), quad.end());
+			mono.insert(mono.end(), lin.begin(), lin.end());
+			mono.insert(mono.end(), gen.begin(), gen.end());
 		}
 		if (fast) {
 			uni::B8Args B;
@@ -1512,22 +1521,34 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 			B.off_q = B.off_nl + 4 * K * K;
 			B.off_es = B.off_q + ((m * uni::SUBS * K + 15) & ~15u);
 			B.off_mono = B.off_es + uni::SUBS * 32 * 16;
-			B.off_ctab = B.off_mono + 4 * (uint32_t)std::max<size_t>(mono.size(), 1);
-			B.off_cols = (B.off_ctab + 12 * n_comp + 15) & ~15u;
+			B.off_ctab = B.off_mono + 8 * (uint32_t)std::max<size_t>(mono.size(), 1);
+			B.off_cols = (B.off_ctab + 4 * uni::CTAB * n_comp + 15) & ~15u;
 			const uint32_t smem8 = B.off_cols + 12 * m + 16;
 			if (smem8 <= 227u * 1024u) {
 				ArgPack pk2;
-				size_t o_m = pk2.add(mono.data(), 4 * mono.size()), o_t = pk2.add(ctab.data(), 4 * ctab.size());
+				size_t o_m = pk2.add(mono.data(), 8 * mono.size()), o_t = pk2.add(ctab.data(), 4 * ctab.size());
 				uint8_t *base2;
 				if ((rc = pk2.commit(ctx, &base2))) return rc;
 				B.mls = A.mls, B.levels = A.levels, B.lag = A.lag, B.eq = A.eq, B.out = A.out, B.n_sub = n_eq;
-				B.mono = (const uint32_t *)(base2 + o_m);
+				B.mono = (const uint2 *)(base2 + o_m);
 				B.comp_tab = (const uint32_t *)(base2 + o_t);
-				B.m = m, B.n_comp = n_comp, B.n_mono = (uint32_t)mono.size(), B.skip = skip, B.n_out = n_out;
+				B.m = m, B.n_comp = n_comp, B.n_mono = (uint32_t)mono.size(), B.n_out = n_out;
 				const uint64_t n_batches = (n_eq + uni::SUBS - 1) / uni::SUBS;
 				dim3 grid8((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_batches, std::max(1u, (uint32_t)ctx->n_sms / gy))), gy);
-				if ((rc = set_smem(ctx, uni::k_uni_b8, smem8))) return rc;
-				uni::k_uni_b8<<<grid8, uni::B8_THREADS, smem8, ctx->stream>>>(ctx->d_tables, B);
+#define B200_UNI_B8(S)                                                                          \
+	case S:                                                                                     \
+		if ((rc = set_smem(ctx, uni::k_uni_b8<S>, smem8))) return rc;                           \
+		uni::k_uni_b8<S><<<grid8, uni::B8_THREADS, smem8, ctx->stream>>>(ctx->d_tables, B); \
+		break;
+				switch (skip) {
+					B200_UNI_B8(2)
+					B200_UNI_B8(3)
+					B200_UNI_B8(4)
+					B200_UNI_B8(5)
+					B200_UNI_B8(6)
+					B200_UNI_B8(7)
+				}
+#undef B200_UNI_B8
 			} else
 				fast = false;
 		}

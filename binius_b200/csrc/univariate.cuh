@@ -230,57 +230,65 @@ __global__ void __launch_bounds__(THREADS) k_uni_evals(const uint8_t *__restrict
 constexpr uint32_t B8_THREADS = 512;
 constexpr uint32_t SUBS = 8;
 constexpr uint32_t MONO_NONE = 511;
+constexpr uint32_t CTAB = 5;  // words per composition: first monomial, #quadratic (coef 1), #linear (coef 1), #general, points
 struct B8Args {
 	const uint4 *const *mls;   // device [m]
 	const uint32_t *levels;    // device [m] (0 or 3)
-	const uint32_t *mono;      // device: a | b << 9 | coef << 18 per monomial (MONO_NONE = no factor)
-	const uint32_t *comp_tab;  // device [n_comp][3]: first monomial, monomial count, evaluation points
+	const uint2 *mono;         // device: per monomial {a * SUBS * K, b * SUBS * K} (byte offsets into qS) for the coef-1
+							   // quadratic / linear runs, {a | b << 9 | coef << 18, 0} for the general run
+	const uint32_t *comp_tab;  // device [n_comp][CTAB]
 	const uint8_t *lag;        // device [n_pts][K]
 	const uint4 *eq;
 	uint4 *out;
 	uint64_t n_sub;
-	uint32_t m, n_comp, n_mono, skip, n_out;
+	uint32_t m, n_comp, n_mono, n_out;
 	uint32_t off_nl, off_q, off_es, off_mono, off_ctab, off_cols;  // shared-memory layout
 };
 
+template <uint32_t SKIP>
 __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restrict__ g_tables, const B8Args A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	FieldTables T = load_field_tables(smem, g_tables);
-	const uint32_t K = 1u << A.skip, PQ = K >> 2, tid = threadIdx.x;
+	constexpr uint32_t K = 1u << SKIP, PQ = K >> 2;
+	const uint32_t tid = threadIdx.x;
 	uint8_t *lagS = smem + FIELD_TABLE_BYTES;
 	uint32_t *NLw = reinterpret_cast<uint32_t *>(smem + A.off_nl);  // [nibble][pattern][quad]
 	uint8_t *qS = smem + A.off_q;                                   // [column][sub-cube][point]
 	uint4 *ES = reinterpret_cast<uint4 *>(smem + A.off_es);         // [sub-cube][32]
-	uint32_t *monoS = reinterpret_cast<uint32_t *>(smem + A.off_mono);
+	uint2 *monoS = reinterpret_cast<uint2 *>(smem + A.off_mono);
 	uint32_t *ctabS = reinterpret_cast<uint32_t *>(smem + A.off_ctab);
 	const uint32_t **colP = reinterpret_cast<const uint32_t **>(smem + A.off_cols);
 	uint32_t *colL = reinterpret_cast<uint32_t *>(smem + A.off_cols + 8 * A.m);
 	const uint32_t p0 = blockIdx.y * K;
-	for (uint32_t idx = tid; idx < K * K; idx += B8_THREADS) lagS[idx] = A.lag[(uint64_t)(p0 + (idx & (K - 1))) * K + (idx >> A.skip)];
+	for (uint32_t idx = tid; idx < K * K; idx += B8_THREADS) lagS[idx] = A.lag[(uint64_t)(p0 + (idx & (K - 1))) * K + (idx >> SKIP)];
 	for (uint32_t idx = tid; idx < A.n_mono; idx += B8_THREADS) monoS[idx] = A.mono[idx];
-	for (uint32_t idx = tid; idx < 3 * A.n_comp; idx += B8_THREADS) ctabS[idx] = A.comp_tab[idx];
+	for (uint32_t idx = tid; idx < CTAB * A.n_comp; idx += B8_THREADS) ctabS[idx] = A.comp_tab[idx];
 	for (uint32_t idx = tid; idx < A.m; idx += B8_THREADS) {
 		colP[idx] = reinterpret_cast<const uint32_t *>(A.mls[idx]);
 		colL[idx] = A.levels[idx];
 	}
+	// stale bytes of qS are read (and multiplied by a zero eq table) for sub-cubes past the end: keep them defined
+	for (uint32_t idx = tid; idx < (A.m * SUBS * K) / 4; idx += B8_THREADS) reinterpret_cast<uint32_t *>(qS)[idx] = 0;
 	__syncthreads();
-	for (uint32_t idx = tid; idx < (K >> 2) * 16 * PQ; idx += B8_THREADS) {
+	for (uint32_t idx = tid; idx < PQ * 16 * PQ; idx += B8_THREADS) {
 		uint32_t pq = idx % PQ, e = idx / PQ, pat = e & 15, nib = e >> 4, word = 0;
 #pragma unroll
 		for (uint32_t p = 0; p < 4; p++) {
 			uint32_t v = 0;
 #pragma unroll
 			for (uint32_t b = 0; b < 4; b++)
-				if (pat >> b & 1) v ^= lagS[((4 * nib + b) << A.skip) + 4 * pq + p];
+				if (pat >> b & 1) v ^= lagS[((4 * nib + b) << SKIP) + 4 * pq + p];
 			word |= v << (8 * p);
 		}
 		NLw[idx] = word;
 	}
 	__syncthreads();
 	// phase A coordinates
-	const uint32_t a_pq = tid % PQ, a_r = tid / PQ, a_sb = a_r % SUBS, a_jl = a_r / SUBS, JL = B8_THREADS / (PQ * SUBS);
+	constexpr uint32_t JL = B8_THREADS / (PQ * SUBS);
+	const uint32_t a_pq = tid % PQ, a_r = tid / PQ, a_sb = a_r % SUBS, a_jl = a_r / SUBS;
 	// phase B coordinates
-	const uint32_t il = tid & (K - 1), g = tid >> A.skip, G = B8_THREADS >> A.skip, i = p0 + il;
+	constexpr uint32_t G = B8_THREADS >> SKIP;
+	const uint32_t il = tid & (K - 1), g = tid >> SKIP, i = p0 + il;
 	uint4 accL[MAX_COMP / 4];
 #pragma unroll
 	for (uint32_t c = 0; c < MAX_COMP / 4; c++) accL[c] = u4_zero();
@@ -293,65 +301,81 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			uint4 eqv = s0 + sb < A.n_sub ? __ldg(A.eq + s0 + sb) : u4_zero();
 			ES[tid] = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
 		}
-		{
-			const uint64_t s = s0 + a_sb;
-			if (s < A.n_sub) {
-				const uint64_t base = s << A.skip;
-				for (uint32_t j = a_jl; j < A.m; j += JL) {
-					uint32_t x = 0;
-					if (colL[j] == 0) {
-						const uint32_t *w = colP[j] + (base >> 5);
-						if (K >= 32) {
-							for (uint32_t ww = 0; ww < (K >> 5); ww++) {
-								const uint32_t bits = __ldg(w + ww);
+		const uint64_t s = s0 + a_sb;
+		if (s < A.n_sub) {
+			const uint64_t base = s << SKIP;
+			const uint32_t *nl = NLw + a_pq;
+			for (uint32_t j = a_jl; j < A.m; j += JL) {
+				uint32_t x = 0;
+				if (colL[j] == 0) {
+					const uint32_t *w = colP[j] + (base >> 5);
+					if constexpr (K >= 32) {
 #pragma unroll
-								for (uint32_t n = 0; n < 8; n++) x ^= NLw[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) * PQ + a_pq];
-							}
-						} else {
-							const uint32_t bits = __ldg(w) >> (base & 31);
-							for (uint32_t n = 0; n < (K >> 2); n++) x ^= NLw[((n << 4) + ((bits >> (4 * n)) & 15u)) * PQ + a_pq];
+						for (uint32_t ww = 0; ww < (K >> 5); ww++) {
+							const uint32_t bits = __ldg(w + ww);
+#pragma unroll
+							for (uint32_t n = 0; n < 8; n++) x ^= nl[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) * PQ];
 						}
 					} else {
-						const uint8_t *col = reinterpret_cast<const uint8_t *>(colP[j]) + base;
-						for (uint32_t t = 0; t < K; t++) {
-							const uint32_t mv = (uint32_t)__ldg(col + t) << 8;
-							const uint32_t lw = *reinterpret_cast<const uint32_t *>(lagS + (t << A.skip) + 4 * a_pq);
-							x ^= (uint32_t)T.mul8[mv | (lw & 0xff)] | ((uint32_t)T.mul8[mv | ((lw >> 8) & 0xff)] << 8) |
-								 ((uint32_t)T.mul8[mv | ((lw >> 16) & 0xff)] << 16) | ((uint32_t)T.mul8[mv | (lw >> 24)] << 24);
-						}
+						const uint32_t bits = __ldg(w) >> (base & 31);
+#pragma unroll
+						for (uint32_t n = 0; n < (K >> 2); n++) x ^= nl[((n << 4) + ((bits >> (4 * n)) & 15u)) * PQ];
 					}
-					reinterpret_cast<uint32_t *>(qS)[(j * SUBS + a_sb) * PQ + a_pq] = x;
+				} else {
+					const uint8_t *col = reinterpret_cast<const uint8_t *>(colP[j]) + base;
+					for (uint32_t t = 0; t < K; t++) {
+						const uint32_t mv = (uint32_t)__ldg(col + t) << 8;
+						const uint32_t lw = *reinterpret_cast<const uint32_t *>(lagS + (t << SKIP) + 4 * a_pq);
+						x ^= (uint32_t)T.mul8[mv | (lw & 0xff)] | ((uint32_t)T.mul8[mv | ((lw >> 8) & 0xff)] << 8) |
+							 ((uint32_t)T.mul8[mv | ((lw >> 16) & 0xff)] << 16) | ((uint32_t)T.mul8[mv | (lw >> 24)] << 24);
+					}
 				}
+				reinterpret_cast<uint32_t *>(qS)[(j * SUBS + a_sb) * PQ + a_pq] = x;
 			}
 		}
 		__syncthreads();
-		const uint32_t n_live = (uint32_t)min((uint64_t)SUBS, A.n_sub - s0);
+		const uint8_t *qb = qS + il;
 		for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++) {
-			const uint32_t m0 = ctabS[3 * c], mc = ctabS[3 * c + 1];
-			if (i >= ctabS[3 * c + 2]) continue;
-			uint4 acc = u4_zero();
-			for (uint32_t sb = 0; sb < n_live; sb++) {
-				const uint8_t *qq = qS + sb * K + il;
-				uint32_t val = 0;
-				for (uint32_t t = 0; t < mc; t++) {
-					const uint32_t d = monoS[m0 + t], a = d & 511u, b = (d >> 9) & 511u, cf = d >> 18;
-					uint32_t v;
-					if (a == MONO_NONE) v = cf;
-					else {
-						v = qq[a * SUBS * K];
-						if (b != MONO_NONE) v = T.mul8[(v << 8) | qq[b * SUBS * K]];
-						if (cf != 1) v = T.mul8[(v << 8) | cf];
-					}
-					val ^= v;
-				}
-				acc ^= ES[sb * 32 + (val & 15u)] ^ ES[sb * 32 + 16 + (val >> 4)];
+			const uint32_t *ct = ctabS + CTAB * c;
+			if (i >= ct[4]) continue;
+			const uint2 *mp = monoS + ct[0];
+			uint32_t val[SUBS];
+#pragma unroll
+			for (uint32_t sb = 0; sb < SUBS; sb++) val[sb] = 0;
+			for (uint32_t t = 0; t < ct[1]; t++) {  // x_a * x_b
+				const uint2 d = mp[t];
+#pragma unroll
+				for (uint32_t sb = 0; sb < SUBS; sb++) val[sb] ^= T.mul8[((uint32_t)qb[d.x + sb * K] << 8) | qb[d.y + sb * K]];
 			}
+			mp += ct[1];
+			for (uint32_t t = 0; t < ct[2]; t++) {  // x_a
+				const uint32_t d = mp[t].x;
+#pragma unroll
+				for (uint32_t sb = 0; sb < SUBS; sb++) val[sb] ^= qb[d + sb * K];
+			}
+			mp += ct[2];
+			for (uint32_t t = 0; t < ct[3]; t++) {  // coef * (1 | x_a | x_a * x_b)
+				const uint32_t d = mp[t].x, a = d & 511u, b = (d >> 9) & 511u, cf = d >> 18;
+#pragma unroll
+				for (uint32_t sb = 0; sb < SUBS; sb++) {
+					uint32_t v = cf;
+					if (a != MONO_NONE) {
+						v = qb[(a * SUBS + sb) * K];
+						if (b != MONO_NONE) v = T.mul8[(v << 8) | qb[(b * SUBS + sb) * K]];
+						v = T.mul8[(v << 8) | cf];
+					}
+					val[sb] ^= v;
+				}
+			}
+			uint4 acc = u4_zero();
+#pragma unroll
+			for (uint32_t sb = 0; sb < SUBS; sb++) acc ^= ES[sb * 32 + (val[sb] & 15u)] ^ ES[sb * 32 + 16 + (val[sb] >> 4)];
 			accL[k] ^= acc;
 		}
 		__syncthreads();
 	}
 	for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++)
-		if (i < ctabS[3 * c + 2]) atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, accL[k]);
+		if (i < ctabS[CTAB * c + 4]) atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, accL[k]);
 }
 
 // extrapolate_round_evals (univariate.rs:565-640): composition c was evaluated at n_in = (deg_c-1)*2^k
