@@ -487,6 +487,41 @@ def main():
             "fri_fold_first_2^24_in_batch4": timed(lambda ex: (ex.fri_fold(ntt12, 20, 4, chs, dev.slice(0, 1 << 24), obuf.slice(0, 1 << 20)), [])[1], 16 * (1 << 24) + 16 * (1 << 20)),
         }
 
+    # ---- zerocheck univariate-skip round at the keccak shape scaled to 2^24 rows:
+    #      153 B1 columns, 75 degree-2 constraints, skip 6, domain 128 (tools/univariate_bench.py runs 2^27)
+    uni = None
+    if not args.no_ntt and rank == 0:
+        try:
+            from binius_b200 import ArithCircuit as A
+            from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals
+
+            nvu, mu, ncu, sku = 24, 153, 75, 6
+            wu = 1 << (nvu - 7)
+            import random as _random
+
+            arena_u = hal.dev_alloc(mu * wu)
+            hal.fill(arena_u, 0x0123456789ABCDEF0F1E2D3C4B5A6978)
+            mls_u = [TransparentMultilinear(arena_u.slice(j * wu, (j + 1) * wu), 0, nvu) for j in range(mu)]
+            comps_u = [A.var((2 * c) % mu) * A.var((2 * c + 1) % mu) + A.var((2 * c + 5) % mu) + A.var((2 * c + 11) % mu) for c in range(ncu)]
+            _r = _random.Random(7)
+            ch_u = [_r.getrandbits(128) for _ in range(nvu - sku)]
+            be_u = B200Backend(hal)
+            times = []
+            for _ in range(3):
+                hal.sync()
+                t0 = time.perf_counter()
+                o = zerocheck_univariate_evals(be_u, mls_u, comps_u, ch_u, sku, 2 << sku)  # synchronous: returns host values
+                times.append((time.perf_counter() - t0) * 1e3)
+                hal.dev_free(o.partial_eq_ind_evals)
+            hal.dev_free(arena_u)
+            alg = mu * wu * 16 + 16 * (1 << (nvu - sku))
+            uni = {"ms_per_call": min(times), "rows_log2": nvu, "columns": mu, "compositions": ncu, "skip_rounds": sku,
+                   "algorithmic_bytes": alg, "hbm_frac": alg / (min(times) * 1e-3) / 1e9 / peak,
+                   "note": "host wall time of the synchronous call (eq-ind expansion + k_uni_b8 + result copy); "
+                           "shared-memory-pipe bound, see DESIGN.md section 9"}
+        except Exception as e:  # never lose the headline line to the extra measurement
+            uni = {"error": repr(e)}
+
     # ---- reduce over ranks: max time ----------------------------------------------------------------
     ms_step = ms_total / args.steps
     if world > 1:
@@ -524,6 +559,8 @@ def main():
             line["zerocheck_u32_add_2^20_rows"] = cfg3
         if ops:
             line["ops"] = ops
+        if uni:
+            line["zerocheck_univariate_skip_2^24_rows"] = uni
         line["sumcheck_chain"] = chain
         if not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core

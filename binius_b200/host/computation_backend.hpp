@@ -195,6 +195,52 @@ class B200Backend {
 		l_.check(b200_kernel_add(l_.ctx(), n_vars - 1, halves.first.ptr, halves.second.ptr, halves.first.ptr));
 		return halves.first;
 	}
+
+	B200Layer &layer() { return l_; }
 };
+
+// core/src/protocols/sumcheck/prove/univariate.rs:37-50
+struct ZerocheckUnivariateEvalsOutput {
+	std::vector<std::vector<F128>> round_evals;
+	uint32_t skip_rounds = 0, remaining_rounds = 0, max_domain_size = 0;
+	DevSlice partial_eq_ind_evals;
+};
+
+// zerocheck_univariate_evals (core/src/protocols/sumcheck/prove/univariate.rs:235-500), FDomain = BinaryField8b.
+// `multilinears`: Transparent (packed sub-field) multilinears of equal n_vars; `composition_degrees[c]` =
+// CompositionPoly::degree() of compositions[c].  Same checks and error order as the reference.
+inline ZerocheckUnivariateEvalsOutput zerocheck_univariate_evals(B200Backend &backend, const std::vector<SumcheckMultilinear> &multilinears,
+																   const std::vector<const ExprEval *> &compositions,
+																   const std::vector<uint32_t> &composition_degrees,
+																   const std::vector<F128> &zerocheck_challenges, uint32_t skip_rounds,
+																   uint32_t max_domain_size) {
+	if (multilinears.empty()) throw InputValidation(1, "NumberOfVariablesMismatch: no multilinears");
+	const uint32_t n_vars = multilinears[0].n_vars;
+	for (auto &m : multilinears)
+		if (m.kind != SumcheckMultilinear::Transparent || m.n_vars != n_vars) throw InputValidation(1, "NumberOfVariablesMismatch");
+	if (skip_rounds > n_vars) throw InputValidation(1, "TooManySkippedRounds");
+	if (zerocheck_challenges.size() != n_vars - skip_rounds) throw InputValidation(1, "IncorrectZerocheckChallengesLength");
+	if (compositions.size() != composition_degrees.size()) throw InputValidation(1, "one degree per composition");
+	uint32_t max_deg = 0;
+	for (uint32_t d : composition_degrees) max_deg = std::max(max_deg, d);
+	if ((uint64_t)max_domain_size < ((uint64_t)max_deg << skip_rounds)) throw InputValidation(1, "LagrangeDomainTooSmall");
+	if (max_domain_size > 256) throw InputValidation(1, "DomainSizeTooLarge");
+	ZerocheckUnivariateEvalsOutput out;
+	out.skip_rounds = skip_rounds, out.remaining_rounds = n_vars - skip_rounds, out.max_domain_size = max_domain_size;
+	out.partial_eq_ind_evals = backend.tensor_product_full_query(zerocheck_challenges);
+	std::vector<b200_dev_ptr> ptrs;
+	std::vector<uint32_t> levels;
+	for (auto &m : multilinears) { ptrs.push_back(m.evals.ptr); levels.push_back(m.tower_level); }
+	std::vector<const b200_expr *> exprs;
+	for (auto *c : compositions) exprs.push_back(c->raw());
+	const uint32_t n_out = max_domain_size - (1u << skip_rounds);
+	std::vector<F128> flat(std::max<size_t>(compositions.size() * n_out, 1));
+	B200Layer &l = backend.layer();
+	l.check(b200_zerocheck_univariate_evals(l.ctx(), ptrs.data(), levels.data(), (uint32_t)ptrs.size(), n_vars, skip_rounds,
+											out.partial_eq_ind_evals.ptr, out.partial_eq_ind_evals.n, exprs.data(), composition_degrees.data(),
+											(uint32_t)exprs.size(), max_domain_size, (uint64_t *)flat.data()));
+	for (size_t c = 0; c < compositions.size(); c++) out.round_evals.emplace_back(flat.begin() + c * n_out, flat.begin() + (c + 1) * n_out);
+	return out;
+}
 
 }  // namespace binius_b200

@@ -24,6 +24,9 @@ int orc_sumcheck_round_evals(uint32_t order, const void *const *mls, const uint6
 							 uint32_t n_comp, const uint32_t *codes, const void *points, uint32_t n_points, void *out);
 uint64_t orc_fold_left_lerp_inplace(void *evals, uint64_t prefix, const void *suffix, uint32_t log_n, const void *z);
 uint64_t orc_fold_right_lerp(const void *evals, uint64_t evals_size, const void *suffix, const void *z, void *out);
+int orc_zerocheck_univariate_evals(const void *const *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, const void *eq_ind,
+								   const orc_expr_step *const *comps, const uint32_t *comp_steps, uint32_t n_comp, uint32_t max_domain_size, void *out);
+void orc_extrapolate_round_evals(uint32_t skip, uint32_t degree, uint32_t max_domain_size, void *vals);
 }
 
 static uint64_t sm_state;
@@ -184,6 +187,45 @@ int main() {
 				CHECK(memcmp(back.data(), h[t].data(), 16 * back.size()) == 0);
 			}
 		}
+	}
+	// zerocheck univariate-skip round (core/src/protocols/sumcheck/prove/univariate.rs:235-500): 3 B1 columns of 2^11
+	// rows, skip 5, a degree-2 and a degree-3 composition, domain 3 * 2^5 + 7
+	{
+		B200Backend be(hal);
+		const uint32_t n_vars = 11, skip = 5, max_domain = 103, n_out = max_domain - 32;
+		std::vector<std::vector<F128>> h(3);
+		std::vector<SumcheckMultilinear> mls;
+		for (uint32_t t = 0; t < 3; t++) {
+			h[t] = rnd(700 + t, 1u << (n_vars - 7));
+			DevSlice d = hal.dev_alloc(h[t].size());
+			hal.copy_h2d(h[t].data(), h[t].size(), d);
+			mls.push_back(SumcheckMultilinear::transparent(d, 0, n_vars, 0));
+		}
+		ExprEval c2 = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::mul(0, 1), ExprStep::var(2), ExprStep::add(2, 3)});
+		ExprEval c3 = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::mul(0, 1), ExprStep::var(2), ExprStep::mul(2, 3)});
+		auto ch = rnd(710, n_vars - skip);
+		auto out = zerocheck_univariate_evals(be, mls, {&c2, &c3}, {2, 3}, ch, skip, max_domain);
+		CHECK(out.round_evals.size() == 2 && out.round_evals[0].size() == n_out && out.remaining_rounds == n_vars - skip);
+		std::vector<F128> eq(1u << (n_vars - skip));
+		eq[0] = F128{1, 0};
+		orc_tensor_expand(eq.data(), eq.size(), 0, ch.data(), n_vars - skip);
+		std::vector<F128> back(eq.size());
+		hal.copy_d2h(out.partial_eq_ind_evals, back.data(), back.size());
+		CHECK(memcmp(back.data(), eq.data(), 16 * eq.size()) == 0);
+		const orc_expr_step o2[5] = {{4, 0, 0, 0, 0}, {4, 1, 0, 0, 0}, {1, 0, 1, 0, 0}, {4, 2, 0, 0, 0}, {0, 2, 3, 0, 0}};
+		const orc_expr_step o3[5] = {{4, 0, 0, 0, 0}, {4, 1, 0, 0, 0}, {1, 0, 1, 0, 0}, {4, 2, 0, 0, 0}, {1, 2, 3, 0, 0}};
+		const orc_expr_step *pc[2] = {o2, o3};
+		const uint32_t nc[2] = {5, 5}, lv[3] = {0, 0, 0}, deg[2] = {2, 3};
+		const void *ptrs[3] = {h[0].data(), h[1].data(), h[2].data()};
+		std::vector<F128> exp(2 * n_out);
+		CHECK(orc_zerocheck_univariate_evals(ptrs, lv, 3, n_vars, skip, eq.data(), pc, nc, 2, max_domain, exp.data()) == 0);
+		for (uint32_t c = 0; c < 2; c++) {
+			orc_extrapolate_round_evals(skip, deg[c], max_domain, exp.data() + c * n_out);
+			CHECK(memcmp(out.round_evals[c].data(), exp.data() + c * n_out, 16 * n_out) == 0);
+		}
+		bool threw = false;
+		try { zerocheck_univariate_evals(be, mls, {&c2, &c3}, {2, 3}, ch, skip, 95); } catch (const InputValidation &) { threw = true; }
+		CHECK(threw);  // LagrangeDomainTooSmall
 	}
 	bool oom = false;
 	try { data.dev_alloc.alloc(1 << 20); } catch (const AllocError &) { oom = true; }
