@@ -1523,8 +1523,9 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 			B.off_mono = B.off_es + uni::SUBS * 32 * 16;
 			B.off_ctab = B.off_mono + 8 * (uint32_t)std::max<size_t>(mono.size(), 1);
 			B.off_cols = (B.off_ctab + 4 * uni::CTAB * n_comp + 15) & ~15u;
-			const uint32_t smem8 = B.off_cols + 12 * m + 16;
-			if (smem8 <= 227u * 1024u) {
+			B.off_bits = (B.off_cols + 12 * m + 15) & ~15u;
+			const uint32_t smem8 = B.off_bits + m * K + 16;  // m * (SUBS * K / 32) words
+			if (smem8 <= 227u * 1024u && m * (uni::SUBS * K / 32) <= 8 * uni::B8_THREADS) {
 				ArgPack pk2;
 				size_t o_m = pk2.add(mono.data(), 8 * mono.size()), o_t = pk2.add(ctab.data(), 4 * ctab.size());
 				uint8_t *base2;

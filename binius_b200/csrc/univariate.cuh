@@ -242,7 +242,7 @@ struct B8Args {
 	uint4 *out;
 	uint64_t n_sub;
 	uint32_t m, n_comp, n_mono, n_out;
-	uint32_t off_nl, off_q, off_es, off_mono, off_ctab, off_cols;  // shared-memory layout
+	uint32_t off_nl, off_q, off_es, off_mono, off_ctab, off_cols, off_bits;  // shared-memory layout
 };
 
 template <uint32_t SKIP>
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 	uint32_t *ctabS = reinterpret_cast<uint32_t *>(smem + A.off_ctab);
 	const uint32_t **colP = reinterpret_cast<const uint32_t **>(smem + A.off_cols);
 	uint32_t *colL = reinterpret_cast<uint32_t *>(smem + A.off_cols + 8 * A.m);
+	uint32_t *bitsS = reinterpret_cast<uint32_t *>(smem + A.off_bits);  // [column][WPC]: the batch's B1 sub-cubes
 	const uint32_t p0 = blockIdx.y * K;
 	for (uint32_t idx = tid; idx < K * K; idx += B8_THREADS) lagS[idx] = A.lag[(uint64_t)(p0 + (idx & (K - 1))) * K + (idx >> SKIP)];
 	for (uint32_t idx = tid; idx < A.n_mono; idx += B8_THREADS) monoS[idx] = A.mono[idx];
@@ -293,7 +294,33 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 #pragma unroll
 	for (uint32_t c = 0; c < MAX_COMP / 4; c++) accL[c] = u4_zero();
 
+	// B1 column words of a batch (WPC consecutive 32-bit words per column) are fetched one batch ahead into
+	// registers while phase B runs, and parked in shared memory for phase A
+	constexpr uint32_t WPC = (SUBS * K) / 32, NPRE = 8;
+	const uint32_t n_words = A.m * WPC;  // <= NPRE * B8_THREADS (host-checked)
+	const uint64_t col_words = max((A.n_sub << SKIP) >> 5, (uint64_t)1);
+	uint32_t pre[NPRE];
+	auto prefetch = [&](uint64_t batch) {
+#pragma unroll
+		for (uint32_t r = 0; r < NPRE; r++) {
+			const uint32_t idx = tid + r * B8_THREADS, j = idx / WPC, w = idx % WPC;
+			const uint64_t wi = batch * WPC + w;
+			pre[r] = (idx < n_words && colL[j] == 0 && wi < col_words) ? __ldg(colP[j] + wi) : 0u;
+		}
+	};
+	auto park = [&]() {
+#pragma unroll
+		for (uint32_t r = 0; r < NPRE; r++) {
+			const uint32_t idx = tid + r * B8_THREADS;
+			if (idx < n_words) bitsS[idx] = pre[r];
+		}
+	};
 	const uint64_t n_batches = (A.n_sub + SUBS - 1) / SUBS;
+	if (blockIdx.x < n_batches) {
+		prefetch(blockIdx.x);
+		park();
+	}
+	__syncthreads();
 	for (uint64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
 		const uint64_t s0 = bt * SUBS;
 		if (tid < SUBS * 32) {
@@ -308,16 +335,16 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			for (uint32_t j = a_jl; j < A.m; j += JL) {
 				uint32_t x = 0;
 				if (colL[j] == 0) {
-					const uint32_t *w = colP[j] + (base >> 5);
 					if constexpr (K >= 32) {
+						const uint32_t *w = bitsS + j * WPC + a_sb * (K >> 5);
 #pragma unroll
 						for (uint32_t ww = 0; ww < (K >> 5); ww++) {
-							const uint32_t bits = __ldg(w + ww);
+							const uint32_t bits = w[ww];
 #pragma unroll
 							for (uint32_t n = 0; n < 8; n++) x ^= nl[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) * PQ];
 						}
 					} else {
-						const uint32_t bits = __ldg(w) >> (base & 31);
+						const uint32_t bits = bitsS[j * WPC + ((a_sb * K) >> 5)] >> ((a_sb * K) & 31);
 #pragma unroll
 						for (uint32_t n = 0; n < (K >> 2); n++) x ^= nl[((n << 4) + ((bits >> (4 * n)) & 15u)) * PQ];
 					}
@@ -334,6 +361,8 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			}
 		}
 		__syncthreads();
+		const bool more = bt + gridDim.x < n_batches;
+		if (more) prefetch(bt + gridDim.x);
 		const uint8_t *qb = qS + il;
 		for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++) {
 			const uint32_t *ct = ctabS + CTAB * c;
@@ -372,6 +401,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			for (uint32_t sb = 0; sb < SUBS; sb++) acc ^= ES[sb * 32 + (val[sb] & 15u)] ^ ES[sb * 32 + 16 + (val[sb] >> 4)];
 			accL[k] ^= acc;
 		}
+		if (more) park();
 		__syncthreads();
 	}
 	for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++)
