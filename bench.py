@@ -518,7 +518,7 @@ def main():
             uni = {"ms_per_call": min(times), "rows_log2": nvu, "columns": mu, "compositions": ncu, "skip_rounds": sku,
                    "algorithmic_bytes": alg, "hbm_frac": alg / (min(times) * 1e-3) / 1e9 / peak,
                    "note": "host wall time of the synchronous call (eq-ind expansion + k_uni_b8 + result copy); "
-                           "shared-memory-pipe bound, see DESIGN.md section 9"}
+                           "shared-memory-pipe bound (ncu: LSU wavefronts 88 % of peak), see DESIGN.md section 9"}
         except Exception as e:  # never lose the headline line to the extra measurement
             uni = {"error": repr(e)}
 
