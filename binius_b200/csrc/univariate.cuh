@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(THREADS) k_uni_evals(const uint8_t *__restrict
 //   phase B: thread = (point, composition lane): evaluates its compositions from the monomial list on qS
 //            bytes (one mul8 table lookup per product) and multiplies by eq[s] through two 16-entry B128
 //            tables eq[s]*n and eq[s]*(n<<4) built once per sub-cube (x -> eq[s]*x is GF(2)-linear), i.e.
-//            2 LDS.128 instead of 16 byte products; sums over the batch stay in registers, the per-thread
+//            8 conflict-free LDS.32 instead of 16 byte products; sums over the batch stay in registers, the per-thread
 //            accumulator (local memory) is touched once per composition and batch.
 constexpr uint32_t B8_THREADS = 512;
 constexpr uint32_t SUBS = 8;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 	uint8_t *lagS = smem + FIELD_TABLE_BYTES;
 	uint32_t *NLw = reinterpret_cast<uint32_t *>(smem + A.off_nl);  // [nibble][pattern][quad]
 	uint8_t *qS = smem + A.off_q;                                   // [column][sub-cube][point]
-	uint4 *ES = reinterpret_cast<uint4 *>(smem + A.off_es);         // [sub-cube][32]
+	uint32_t *ESw = reinterpret_cast<uint32_t *>(smem + A.off_es);  // [word][sub-cube][32]
 	uint2 *monoS = reinterpret_cast<uint2 *>(smem + A.off_mono);
 	uint32_t *ctabS = reinterpret_cast<uint32_t *>(smem + A.off_ctab);
 	const uint32_t **colP = reinterpret_cast<const uint32_t **>(smem + A.off_cols);
@@ -326,7 +326,10 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 		if (tid < SUBS * 32) {
 			uint32_t sb = tid >> 5, e = tid & 31;
 			uint4 eqv = s0 + sb < A.n_sub ? __ldg(A.eq + s0 + sb) : u4_zero();
-			ES[tid] = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
+			// four 32-bit planes [word][sub-cube][32]: the 16 entries of a nibble table sit in 16 distinct banks,
+			// so the gathers of phase B are conflict-free whatever the values (an LDS.128 gather is not)
+			const uint4 v = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
+			ESw[tid] = v.x, ESw[SUBS * 32 + tid] = v.y, ESw[2 * SUBS * 32 + tid] = v.z, ESw[3 * SUBS * 32 + tid] = v.w;
 		}
 		const uint64_t s = s0 + a_sb;
 		if (s < A.n_sub) {
@@ -398,7 +401,13 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			}
 			uint4 acc = u4_zero();
 #pragma unroll
-			for (uint32_t sb = 0; sb < SUBS; sb++) acc ^= ES[sb * 32 + (val[sb] & 15u)] ^ ES[sb * 32 + 16 + (val[sb] >> 4)];
+			for (uint32_t sb = 0; sb < SUBS; sb++) {
+				const uint32_t *lo = ESw + sb * 32 + (val[sb] & 15u), *hi = ESw + sb * 32 + 16 + (val[sb] >> 4);
+				acc.x ^= lo[0] ^ hi[0];
+				acc.y ^= lo[SUBS * 32] ^ hi[SUBS * 32];
+				acc.z ^= lo[2 * SUBS * 32] ^ hi[2 * SUBS * 32];
+				acc.w ^= lo[3 * SUBS * 32] ^ hi[3 * SUBS * 32];
+			}
 			accL[k] ^= acc;
 		}
 		if (more) park();
