@@ -1518,7 +1518,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 		if (fast) {
 			uni::B8Args B;
 			B.off_nl = A.off_nl;
-			B.off_q = B.off_nl + 4 * K * K;
+			B.off_q = B.off_nl + 512 * K;  // (K/4 nibbles) x 16 patterns x 32-word rows
 			B.off_es = B.off_q + ((m * uni::SUBS * K + 15) & ~15u);
 			B.off_mono = B.off_es + uni::SUBS * 32 * 16;
 			B.off_ctab = B.off_mono + 8 * (uint32_t)std::max<size_t>(mono.size(), 1);

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 	constexpr uint32_t K = 1u << SKIP, PQ = K >> 2;
 	const uint32_t tid = threadIdx.x;
 	uint8_t *lagS = smem + FIELD_TABLE_BYTES;
-	uint32_t *NLw = reinterpret_cast<uint32_t *>(smem + A.off_nl);  // [nibble][pattern][quad]
+	uint32_t *NLw = reinterpret_cast<uint32_t *>(smem + A.off_nl);  // [nibble][pattern][32 words = 128/K copies of the K points]
 	uint8_t *qS = smem + A.off_q;                                   // [column][sub-cube][point]
 	uint32_t *ESw = reinterpret_cast<uint32_t *>(smem + A.off_es);  // [word][sub-cube][32]
 	uint2 *monoS = reinterpret_cast<uint2 *>(smem + A.off_mono);
@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 	// stale bytes of qS are read (and multiplied by a zero eq table) for sub-cubes past the end: keep them defined
 	for (uint32_t idx = tid; idx < (A.m * SUBS * K) / 4; idx += B8_THREADS) reinterpret_cast<uint32_t *>(qS)[idx] = 0;
 	__syncthreads();
-	for (uint32_t idx = tid; idx < PQ * 16 * PQ; idx += B8_THREADS) {
-		uint32_t pq = idx % PQ, e = idx / PQ, pat = e & 15, nib = e >> 4, word = 0;
+	// rows are 32 words: 128 / K copies of the K coefficient bytes side by side, so that the 32 / PQ different
+	// (sub-cube, column) pairs a warp works on read their rows from disjoint banks (lane l reads word l)
+	for (uint32_t idx = tid; idx < PQ * 16 * 32; idx += B8_THREADS) {
+		uint32_t pq = (idx & 31) % PQ, e = idx >> 5, pat = e & 15, nib = e >> 4, word = 0;
 #pragma unroll
 		for (uint32_t p = 0; p < 4; p++) {
 			uint32_t v = 0;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 		const uint64_t s = s0 + a_sb;
 		if (s < A.n_sub) {
 			const uint64_t base = s << SKIP;
-			const uint32_t *nl = NLw + a_pq;
+			const uint32_t *nl = NLw + (tid & 31);
 			for (uint32_t j = a_jl; j < A.m; j += JL) {
 				uint32_t x = 0;
 				if (colL[j] == 0) {
@@ -344,12 +346,12 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 						for (uint32_t ww = 0; ww < (K >> 5); ww++) {
 							const uint32_t bits = w[ww];
 #pragma unroll
-							for (uint32_t n = 0; n < 8; n++) x ^= nl[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) * PQ];
+							for (uint32_t n = 0; n < 8; n++) x ^= nl[((((ww << 3) + n) << 4) + ((bits >> (4 * n)) & 15u)) << 5];
 						}
 					} else {
 						const uint32_t bits = bitsS[j * WPC + ((a_sb * K) >> 5)] >> ((a_sb * K) & 31);
 #pragma unroll
-						for (uint32_t n = 0; n < (K >> 2); n++) x ^= nl[((n << 4) + ((bits >> (4 * n)) & 15u)) * PQ];
+						for (uint32_t n = 0; n < (K >> 2); n++) x ^= nl[((n << 4) + ((bits >> (4 * n)) & 15u)) << 5];
 					}
 				} else {
 					const uint8_t *col = reinterpret_cast<const uint8_t *>(colP[j]) + base;
