@@ -131,3 +131,59 @@ def shard_units(n_units: int, world: int, rank: int) -> range:
     per, rem = divmod(n_units, world)
     start = rank * per + min(rank, rem)
     return range(start, start + per + (1 if rank < rem else 0))
+
+
+# ---- zerocheck univariate-skip round (core/src/protocols/sumcheck/prove/univariate.rs:235-500) -------------
+# The round evaluations are XOR-sums over sub-cubes s, and eq[s] = eq(low bits of s; r_low) * eq(high bits; r_high),
+# so rank g takes the sub-cubes s = g (mod W) -- the same low-variable partition the multilinear rounds use
+# afterwards --, evaluates them against the expansion of the HIGH challenges only, and scales its partial
+# result by the scalar eq(bits(g), r_low).  The reference's domain extension (extrapolate_round_evals) is
+# linear, so it commutes with the combine.  One all-gather of n_compositions * n_points B128 values.
+def shard_subcubes(packed: np.ndarray, tower_level: int, skip_rounds: int, world: int, rank: int) -> np.ndarray:
+    """sub-cubes s = rank (mod world) of a packed sub-field column ((n, 2) uint64 B128 words), compacted"""
+    assert world & (world - 1) == 0
+    cube_bits = (1 << skip_rounds) << tower_level
+    raw = np.ascontiguousarray(packed).view(np.uint8).reshape(-1)
+    if cube_bits % 8 == 0:
+        mine = raw.reshape(-1, cube_bits // 8)[rank::world].reshape(-1)
+    else:
+        bits = np.unpackbits(raw, bitorder="little").reshape(-1, cube_bits)[rank::world].reshape(-1)
+        mine = np.packbits(bits, bitorder="little")
+    out = np.zeros(max((len(mine) + 15) // 16, 1) * 16, np.uint8)
+    out[: len(mine)] = mine
+    return out.view(np.uint64).reshape(-1, 2)
+
+
+def sharded_zerocheck_univariate_evals(evaluate, columns: Sequence[np.ndarray], tower_levels: Sequence[int], n_vars: int,
+                                       skip_rounds: int, compositions, zerocheck_challenges: Sequence[int], max_domain_size: int,
+                                       world: int = 1, rank: int = 0, dist=None, device="cpu") -> List[List[int]]:
+    """`evaluate(local_columns, tower_levels, n_vars_local, skip_rounds, compositions, challenges, max_domain_size)`
+    returns the round evals of the rank-local instance (`device_univariate_evaluator` in production)."""
+    lw = world.bit_length() - 1
+    if n_vars - skip_rounds < lw:
+        raise ValueError("fewer sub-cubes than ranks")
+    low, high = list(zerocheck_challenges[:lw]), list(zerocheck_challenges[lw:])
+    local = [shard_subcubes(c, l, skip_rounds, world, rank) for c, l in zip(columns, tower_levels)]
+    part = evaluate(local, list(tower_levels), n_vars - lw, skip_rounds, compositions, high, max_domain_size)
+    scale = hostfield.eq_ind_scalar(rank, low)
+    flat = [hostfield.mul(scale, v) for row in part for v in row]
+    tot = xor_all_gather(flat, dist, device) if flat else []
+    n_out = len(part[0]) if part else 0
+    return [tot[c * n_out:(c + 1) * n_out] for c in range(len(part))]
+
+
+def device_univariate_evaluator(backend):
+    """the rank-local evaluation on this rank's GPU (binius_b200.hal.zerocheck_univariate_evals)"""
+    from .hal import TransparentMultilinear, zerocheck_univariate_evals
+
+    def evaluate(local, levels, n_vars_local, skip, compositions, challenges, max_domain_size):
+        layer = backend._l
+        devs = [layer.to_device(c) for c in local]
+        out = zerocheck_univariate_evals(backend, [TransparentMultilinear(d, l, n_vars_local) for d, l in zip(devs, levels)],
+                                         compositions, challenges, skip, max_domain_size)
+        layer.dev_free(out.partial_eq_ind_evals)
+        for d in devs:
+            layer.dev_free(d)
+        return out.round_evals
+
+    return evaluate

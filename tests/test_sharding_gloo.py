@@ -126,3 +126,75 @@ def test_single_process_sharding_is_identity(oracle):
         assert sc.round_evals(3) == exp[r]
         sc.fold(7)
     assert sc.finish() == fin
+
+
+# ---- zerocheck univariate-skip round sharded over sub-cubes ---------------------------------------------
+def _uni_instance(orc, n_vars, skip):
+    from binius_b200 import ArithCircuit as A
+    from test_oracle_univariate import pack_scalars
+
+    rng = random.Random(31 + skip)
+    levels = [0, 3, 0]
+    cols = [orc.to_arr(pack_scalars([rng.getrandbits(1 << l) for _ in range(1 << n_vars)], l)) for l in levels]
+    comps = [A.var(0) * A.var(1) + A.var(2), A.var(0) * A.var(1) * A.var(2), A.var(0) + A.var(2)]
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    return levels, cols, comps, ch
+
+
+def _oracle_evaluator(orc):
+    from binius_b200.hal import _degree
+
+    def evaluate(local, levels, n_vars_local, skip, comps, challenges, max_domain):
+        eq = orc.tensor_expand(orc.to_arr([1] + [0] * ((1 << len(challenges)) - 1)), 0, challenges)
+        return orc.zerocheck_univariate_evals_reference(local, levels, n_vars_local, skip, eq, [list(c.steps) for c in comps],
+                                                        [_degree(c) for c in comps], max_domain)
+
+    return evaluate
+
+
+def _uni_worker(rank, world, port, n_vars, skip, ret):
+    import torch.distributed as dist
+
+    from binius_b200 import sharding
+    from oracle import binding as orc
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        levels, cols, comps, ch = _uni_instance(orc, n_vars, skip)
+        max_domain = (3 << skip) + 2
+        exp = _oracle_evaluator(orc)(cols, levels, n_vars, skip, comps, ch, max_domain)
+        got = sharding.sharded_zerocheck_univariate_evals(_oracle_evaluator(orc), cols, levels, n_vars, skip, comps, ch, max_domain,
+                                                          world, rank, dist)
+        assert got == exp, f"rank {rank}"
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_vars,skip", [(2, 7, 3), (4, 6, 1), (2, 6, 4)])
+def test_sharded_univariate_round_gloo(world, n_vars, skip):
+    import torch.multiprocessing as mp
+
+    port = 31500 + random.randrange(2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_uni_worker, args=(world, port, n_vars, skip, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))
+
+
+def test_shard_subcubes_partitions_every_subcube(oracle):
+    from binius_b200 import sharding
+    from test_oracle_univariate import pack_scalars
+
+    rng = random.Random(2)
+    for lvl, skip, n_vars in ((0, 1, 9), (0, 6, 9), (3, 2, 6), (5, 0, 5)):
+        vals = [rng.getrandbits(1 << lvl) for _ in range(1 << n_vars)]
+        col = oracle.to_arr(pack_scalars(vals, lvl))
+        K = 1 << skip
+        for world in (2, 4):
+            for g in range(world):
+                mine = [v for s in range(g, (1 << n_vars) // K, world) for v in vals[s * K:(s + 1) * K]]
+                exp = oracle.to_arr(pack_scalars(mine, lvl))
+                assert np.array_equal(sharding.shard_subcubes(col, lvl, skip, world, g)[: len(exp)], exp)
