@@ -1516,29 +1516,35 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 			mono.insert(mono.end(), gen.begin(), gen.end());
 		}
 		if (fast) {
-			uni::B8Args B;
-			B.off_nl = A.off_nl;
-			B.off_q = B.off_nl + 512 * K;  // (K/4 nibbles) x 16 patterns x 32-word rows
-			B.off_es = B.off_q + ((m * uni::SUBS * K + 15) & ~15u);
-			B.off_mono = B.off_es + uni::SUBS * 32 * 16;
-			B.off_ctab = B.off_mono + 8 * (uint32_t)std::max<size_t>(mono.size(), 1);
-			B.off_cols = (B.off_ctab + 4 * uni::CTAB * n_comp + 15) & ~15u;
-			B.off_bits = (B.off_cols + 12 * m + 15) & ~15u;
-			const uint32_t smem8 = B.off_bits + m * K + 16;  // m * (SUBS * K / 32) words
-			if (smem8 <= 227u * 1024u && m * (uni::SUBS * K / 32) <= 8 * uni::B8_THREADS) {
+			// shared-memory layout for `ml` columns / `nc` compositions / `nm` monomials; returns the dynamic size
+			auto layout = [&](uni::B8Args &B, uint32_t ml, uint32_t nc, size_t nm) -> uint32_t {
+				B.off_nl = A.off_nl;
+				B.off_q = B.off_nl + 512 * K;  // (K/4 nibbles) x 16 patterns x 32-word rows
+				B.off_es = B.off_q + ((ml * uni::SUBS * K + 15) & ~15u);
+				B.off_mono = B.off_es + uni::SUBS * 32 * 16;
+				B.off_ctab = B.off_mono + 8 * (uint32_t)std::max<size_t>(nm, 1);
+				B.off_cols = (B.off_ctab + 4 * uni::CTAB * nc + 15) & ~15u;
+				B.off_bits = (B.off_cols + 12 * ml + 15) & ~15u;
+				return B.off_bits + ml * K + 16;  // ml * (SUBS * K / 32) words
+			};
+			auto fits = [&](uint32_t smem8, uint32_t ml) { return smem8 <= 227u * 1024u && ml * (uni::SUBS * K / 32) <= 8 * uni::B8_THREADS; };
+			// one launch over compositions [c0, c0 + nc) (rows c0.. of the output table) and the given column list
+			auto launch = [&](uni::B8Args &B, uint32_t smem8, const uint4 *const *d_mls, const uint32_t *d_levels, uint32_t ml, uint32_t c0, uint32_t nc,
+							  const std::vector<uint2> &mn, const std::vector<uint32_t> &ct) -> int32_t {
 				ArgPack pk2;
-				size_t o_m = pk2.add(mono.data(), 8 * mono.size()), o_t = pk2.add(ctab.data(), 4 * ctab.size());
+				size_t o_m = pk2.add(mn.data(), 8 * mn.size()), o_t = pk2.add(ct.data(), 4 * ct.size());
 				uint8_t *base2;
-				if ((rc = pk2.commit(ctx, &base2))) return rc;
-				B.mls = A.mls, B.levels = A.levels, B.lag = A.lag, B.eq = A.eq, B.out = A.out, B.n_sub = n_eq;
+				int32_t r = pk2.commit(ctx, &base2);
+				if (r) return r;
+				B.mls = d_mls, B.levels = d_levels, B.lag = A.lag, B.eq = A.eq, B.out = A.out + (uint64_t)c0 * n_out, B.n_sub = n_eq;
 				B.mono = (const uint2 *)(base2 + o_m);
 				B.comp_tab = (const uint32_t *)(base2 + o_t);
-				B.m = m, B.n_comp = n_comp, B.n_mono = (uint32_t)mono.size(), B.n_out = n_out;
+				B.m = ml, B.n_comp = nc, B.n_mono = (uint32_t)mn.size(), B.n_out = n_out;
 				const uint64_t n_batches = (n_eq + uni::SUBS - 1) / uni::SUBS;
 				dim3 grid8((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_batches, std::max(1u, (uint32_t)ctx->n_sms / gy))), gy);
 #define B200_UNI_B8(S)                                                                          \
 	case S:                                                                                     \
-		if ((rc = set_smem(ctx, uni::k_uni_b8<S>, smem8))) return rc;                           \
+		if ((r = set_smem(ctx, uni::k_uni_b8<S>, smem8))) return r;                             \
 		uni::k_uni_b8<S><<<grid8, uni::B8_THREADS, smem8, ctx->stream>>>(ctx->d_tables, B); \
 		break;
 				switch (skip) {
@@ -1550,6 +1556,86 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 					B200_UNI_B8(7)
 				}
 #undef B200_UNI_B8
+				return B200_OK;
+			};
+			uni::B8Args B;
+			const uint32_t smem8 = layout(B, m, n_comp, mono.size());
+			if (fits(smem8, m)) {
+				if ((rc = launch(B, smem8, A.mls, A.levels, m, 0, n_comp, mono, ctab))) return rc;
+			} else if (getenv("B200_UNI_SPLIT")) {
+				// Too many columns for one CTA's shared memory (e.g. 153 columns at skip 7): constraints are local,
+				// so split the compositions into contiguous ranges whose referenced columns fit and launch the same
+				// kernel per range on the compacted column list.  OPT-IN until verified on a GPU.
+				const uint32_t cube = uni::SUBS * K;
+				auto vars_of = [&](uint32_t c, std::set<uint32_t> &cols) {
+					const uint32_t *ct = &ctab[uni::CTAB * c];
+					for (uint32_t t = 0; t < ct[1] + ct[2] + ct[3]; t++) {
+						const uint2 d = mono[ct[0] + t];
+						if (t < ct[1]) cols.insert(d.x / cube), cols.insert(d.y / cube);
+						else if (t < ct[1] + ct[2]) cols.insert(d.x / cube);
+						else {
+							if ((d.x & 511u) != uni::MONO_NONE) cols.insert(d.x & 511u);
+							if (((d.x >> 9) & 511u) != uni::MONO_NONE) cols.insert((d.x >> 9) & 511u);
+						}
+					}
+				};
+				struct Range { uint32_t c0, c1; std::vector<uint32_t> cols; };
+				std::vector<Range> ranges;
+				for (uint32_t c0 = 0; fast && c0 < n_comp;) {
+					std::set<uint32_t> cols;
+					uint32_t c1 = c0;
+					while (c1 < n_comp) {
+						std::set<uint32_t> t = cols;
+						vars_of(c1, t);
+						uni::B8Args probe;
+						if (!fits(layout(probe, (uint32_t)std::max<size_t>(t.size(), 1), c1 + 1 - c0, mono.size()), (uint32_t)t.size())) break;
+						cols.swap(t);
+						c1++;
+					}
+					if (c1 == c0) fast = false;  // a single composition does not fit: generic kernel
+					else ranges.push_back(Range{c0, c1, std::vector<uint32_t>(cols.begin(), cols.end())});
+					c0 = c1;
+				}
+				for (size_t ri = 0; fast && ri < ranges.size(); ri++) {
+					const Range &R = ranges[ri];
+					std::vector<uint32_t> local(m, 0);
+					std::vector<b200_dev_ptr> h_mls;
+					std::vector<uint32_t> h_lv;
+					for (uint32_t g : R.cols) {
+						local[g] = (uint32_t)h_mls.size();
+						h_mls.push_back(mls[g]);
+						h_lv.push_back(levels[g]);
+					}
+					if (h_mls.empty()) h_mls.push_back(mls[0]), h_lv.push_back(levels[0]);  // constants only
+					std::vector<uint2> mn;
+					std::vector<uint32_t> ct2(uni::CTAB * (size_t)(R.c1 - R.c0));
+					for (uint32_t c = R.c0; c < R.c1; c++) {
+						const uint32_t *ct = &ctab[uni::CTAB * c];
+						uint32_t *o = &ct2[uni::CTAB * (c - R.c0)];
+						o[0] = (uint32_t)mn.size(), o[1] = ct[1], o[2] = ct[2], o[3] = ct[3], o[4] = ct[4];
+						for (uint32_t t = 0; t < ct[1] + ct[2] + ct[3]; t++) {
+							uint2 d = mono[ct[0] + t];
+							if (t < ct[1]) d = make_uint2(local[d.x / cube] * cube, local[d.y / cube] * cube);
+							else if (t < ct[1] + ct[2]) d = make_uint2(local[d.x / cube] * cube, 0);
+							else {
+								uint32_t a = d.x & 511u, b = (d.x >> 9) & 511u;
+								if (a != uni::MONO_NONE) a = local[a];
+								if (b != uni::MONO_NONE) b = local[b];
+								d = make_uint2(a | (b << 9) | (d.x & ~0x3FFFFu), 0);
+							}
+							mn.push_back(d);
+						}
+					}
+					ArgPack pk3;
+					size_t o_p = pk3.add(h_mls.data(), sizeof(void *) * h_mls.size()), o_l = pk3.add(h_lv.data(), 4 * h_lv.size());
+					uint8_t *base3;
+					if ((rc = pk3.commit(ctx, &base3))) return rc;
+					uni::B8Args Br;
+					const uint32_t ml = (uint32_t)h_mls.size();
+					const uint32_t sm = layout(Br, ml, R.c1 - R.c0, mn.size());
+					if ((rc = launch(Br, sm, (const uint4 *const *)(base3 + o_p), (const uint32_t *)(base3 + o_l), ml, R.c0, R.c1 - R.c0, mn, ct2))) return rc;
+					if (ri + 1 < ranges.size()) B200_LAUNCH_CHECK(ctx);
+				}
 			} else
 				fast = false;
 		}
