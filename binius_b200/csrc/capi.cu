@@ -1421,7 +1421,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 		for (const b200_expr_step &st : comps[c]->steps)
 			if (st.op == 3) lvl = std::max(lvl, const_level(st.c_lo, st.c_hi));
 	}
-	if (skip >= 8 || (uint64_t)max_deg << skip > max_domain_size || max_domain_size < (1u << skip)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "LagrangeDomainTooSmall: max_domain_size %u < %u << %u", max_domain_size, max_deg, skip);
+	if (skip > 8 || (uint64_t)max_deg << skip > max_domain_size || max_domain_size < (1u << skip)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "LagrangeDomainTooSmall: max_domain_size %u < %u << %u", max_domain_size, max_deg, skip);
 	for (uint32_t j = 0; j < m; j++) {
 		if (!valid_level(levels[j])) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: unsupported tower level %u", j, levels[j]);
 		if (!mls[j]) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u is null", j);
