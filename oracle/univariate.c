@@ -68,8 +68,10 @@ static void lagrange_n(uint32_t n, u128 x, u128u *out) {
 /*
  * extrapolate_round_evals (univariate.rs:565-640): the reference evaluates composition c only at the
  * (deg_c - 1) * 2^k points following the skipped domain, re-adds 2^k ZERO evaluations in front (an honest
- * prover's values there), interpolates those deg_c * 2^k values (OddInterpolate + forward NTT = the unique
- * polynomial of degree < deg_c * 2^k through them) and evaluates it on the rest of the domain.  Restated as
+ * prover's values there), interpolates those deg_c * 2^k values (OddInterpolate::inverse_transform,
+ * ntt/src/odd_interpolate.rs:60-72: "the unique univariate polynomial P of degree less than d * 2^l" whose
+ * evaluations on the first d * 2^l field elements are the data; then a forward NTT) and evaluates it on the rest
+ * of the domain.  Restated as
  * Lagrange extrapolation.  vals: n_points = max_domain_size - 2^k entries of which the first
  * (deg - 1) * 2^k are inputs; the rest are overwritten.
  */

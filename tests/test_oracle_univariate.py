@@ -122,3 +122,27 @@ def test_extrapolation_differs_off_a_true_instance(oracle):
     full = oracle.zerocheck_univariate_evals(mls, [0, 0], n_vars, skip, eq, comps, 16)[0]
     ref = oracle.zerocheck_univariate_evals_reference(mls, [0, 0], n_vars, skip, eq, comps, [2], 16)[0]
     assert full[:4] == ref[:4] and full[4:] != ref[4:]
+
+
+@pytest.mark.parametrize("skip,log_domain", [(1, 3), (2, 4), (3, 5), (5, 7), (6, 8), (7, 8)])
+def test_lagrange_form_equals_the_reference_ntt_route(oracle, skip, log_domain):
+    """ntt_extrapolate (univariate.rs:642-678): the reference turns a sub-cube's values into novel-basis
+    coefficients with an inverse additive NTT over B8 (coset 0, coset_bits = log_domain - skip) and evaluates
+    them on the following cosets with forward NTTs; coset c covers the domain points c*2^skip + t.  The oracle
+    (and the kernels) use the Lagrange form instead -- same polynomial, so the same values.  The NTT used here is
+    the oracle's restatement of ntt/src/tests/reference.rs, pinned on its own in test_oracle_ops.py."""
+    K = 1 << skip
+    ntt = oracle.NTT(3, log_domain)
+    rng = random.Random(1000 + skip)
+    evals = np.array([rng.getrandbits(8) for _ in range(K)], np.uint8)
+    coset_bits = log_domain - skip
+    coeffs = ntt.inverse(evals, 3, 0, skip, 0, 0, coset_bits, 0)
+    assert np.array_equal(ntt.forward(coeffs, 3, 0, skip, 0, 0, coset_bits, 0), evals)
+    for coset in range(1, 1 << coset_bits):
+        ext = ntt.forward(coeffs, 3, 0, skip, 0, coset, coset_bits, 0)
+        for t in sorted({0, 1, K // 2, K - 1}):
+            lag = oracle.lagrange_evals(skip, coset * K + t)
+            acc = 0
+            for u in range(K):
+                acc ^= oracle.mul(lag[u], int(evals[u]))
+            assert acc == int(ext[t]), (coset, t)
