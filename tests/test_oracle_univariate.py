@@ -146,3 +146,23 @@ def test_lagrange_form_equals_the_reference_ntt_route(oracle, skip, log_domain):
             for u in range(K):
                 acc ^= oracle.mul(lag[u], int(evals[u]))
             assert acc == int(ext[t]), (coset, t)
+
+
+@pytest.mark.parametrize("skip,degree,log_domain", [(3, 2, 6), (2, 4, 6), (4, 2, 7), (5, 4, 8), (0, 2, 3)])
+def test_round_eval_extension_equals_the_reference_ntt_route(oracle, skip, degree, log_domain):
+    """extrapolate_round_evals (univariate.rs:565-640) for a power-of-two number of evaluations, where
+    OddInterpolate reduces to an inverse NTT: prepend 2^skip zeros, inverse NTT over the first deg*2^skip domain
+    points, zero-pad the novel-basis coefficients to the domain, forward NTT, drop the skipped prefix."""
+    K = 1 << skip
+    n = degree * K
+    rng = random.Random(77 + skip)
+    stag = [rng.getrandbits(128) for _ in range(n - K)]
+    ntt = oracle.NTT(3, log_domain)
+    j = n.bit_length() - 1
+    coeffs = ntt.inverse(oracle.to_arr([0] * K + stag), 7, 0, j, 0, 0, log_domain - j, 0)
+    padded = np.zeros((1 << log_domain, 2), np.uint64)
+    padded[:n] = coeffs
+    full = oracle.to_ints(ntt.forward(padded, 7, 0, log_domain, 0, 0, 0, 0))
+    assert full[:K] == [0] * K and full[K:n] == stag
+    for max_domain in (1 << log_domain, n + 3):
+        assert oracle.extrapolate_round_evals(stag, skip, degree, max_domain) == full[K:max_domain]
