@@ -191,6 +191,24 @@ def cpu_fold_baseline(log_coeffs, budget_s=12.0):
     return orc.cpu_fold_parallel(log_coeffs, budget_s)
 
 
+def cpu_univariate_baseline(rows_log2=21, columns=153, compositions=75, skip=6):
+    """CPU arm of the univariate-skip round (oracle/cpu_univariate.c: table-driven port, all host threads) on a
+    bounded sample of the bench shape: the same columns/constraints on 2^rows_log2 rows."""
+    from oracle import binding as orc
+
+    words = 1 << (rows_log2 - 7)
+    cols = [orc.rand_b128(j, words) for j in range(columns)]
+    m = columns
+    comps = [[("var", (2 * c) % m), ("var", (2 * c + 1) % m), ("mul", 0, 1), ("var", (2 * c + 5) % m), ("add", 2, 3),
+              ("var", (2 * c + 11) % m), ("add", 4, 5)] for c in range(compositions)]
+    eq = orc.rand_b128(999, 1 << (rows_log2 - skip))
+    cores = len(os.sched_getaffinity(0))
+    best = min(orc.cpu_univariate_b1(cols, rows_log2, skip, eq, comps, 1 << skip, cores)[1] for _ in range(2))
+    return {"value": columns * (1 << (rows_log2 - skip)) / best, "unit": "sub-cube columns/s", "cores": cores, "kind": "port",
+            "sample": f"{columns} B1 columns x 2^{rows_log2} rows, {compositions} degree-2 constraints, skip {skip}: {best * 1e3:.1f} ms "
+                      "(table-driven C restatement, pthreads; includes the table setup)"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -568,6 +586,13 @@ def main():
             from oracle import binding as orc
 
             line["sumcheck_chain"]["cpu_baseline"] = orc.cpu_fold_chain_parallel(args.log_coeffs, 5.0)
+            if uni and "error" not in uni:
+                try:
+                    uni["value"] = uni["columns"] * (1 << (uni["rows_log2"] - uni["skip_rounds"])) / (uni["ms_per_call"] * 1e-3)
+                    uni["unit"] = "sub-cube columns/s"
+                    uni["cpu_baseline"] = cpu_univariate_baseline()
+                except Exception as e:
+                    uni["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -402,6 +402,79 @@ def zerocheck_univariate_evals_reference(mls, levels, n_vars, skip, eq_ind, comp
     return [extrapolate_round_evals(v, skip, d, max_domain_size) for v, d in zip(full, degrees)]
 
 
+def expand_monomials(steps, max_degree=2):
+    """ArithCircuit steps -> {sorted tuple of variable indices: coefficient} (polynomials of degree <= max_degree)"""
+    polys = []
+    for st in steps:
+        k = st[0]
+        if k == "const":
+            p = {(): st[1]} if st[1] else {}
+        elif k == "var":
+            p = {(st[1],): 1}
+        elif k == "add":
+            p = dict(polys[st[1]])
+            for mono, c in polys[st[2]].items():
+                v = p.get(mono, 0) ^ c
+                if v:
+                    p[mono] = v
+                else:
+                    p.pop(mono, None)
+        elif k in ("mul", "pow"):
+            factors = [polys[st[1]], polys[st[2]]] if k == "mul" else [polys[st[1]]] * st[2]
+            p = {(): 1}
+            for f in factors:
+                nxt = {}
+                for m1, c1 in p.items():
+                    for m2, c2 in f.items():
+                        mono = tuple(sorted(m1 + m2))
+                        if len(mono) > max_degree:
+                            raise ValueError("degree above max_degree")
+                        v = nxt.get(mono, 0) ^ mul(c1, c2)
+                        if v:
+                            nxt[mono] = v
+                        else:
+                            nxt.pop(mono, None)
+                p = nxt
+        else:
+            raise ValueError(k)
+        polys.append(p)
+    return polys[-1] if polys else {}
+
+
+def cpu_univariate_b1(cols, n_vars: int, skip: int, eq_ind, comps, n_pts: int, n_threads: int = 0):
+    """Threaded CPU arm of the univariate-skip round (oracle/cpu_univariate.c): B1 columns, compositions of degree <= 2
+    with B8 constants, every composition evaluated at the n_pts points after the skipped domain.
+    Returns (round evals [composition][point], seconds inside the C call)."""
+    import os
+    import time
+
+    cols = [np.ascontiguousarray(c).view(np.uint8).reshape(-1) for c in cols]
+    ma, mb, mc, first, cnt = [], [], [], [], []
+    for steps in comps:
+        poly = expand_monomials(steps)
+        first.append(len(ma))
+        for mono, c in poly.items():
+            if c >> 8:
+                raise ValueError("constant outside B8")
+            ma.append(mono[0] if len(mono) > 0 else 0xFFFF)
+            mb.append(mono[1] if len(mono) > 1 else 0xFFFF)
+            mc.append(c)
+        cnt.append(len(ma) - first[-1])
+    nm, nc = max(len(ma), 1), len(comps)
+    out = np.zeros((max(nc * n_pts, 1), 2), np.uint64)
+    ptrs = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    n_threads = n_threads or len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    rc = lib().orc_cpu_univariate_b1(ptrs, C.c_uint32(len(cols)), C.c_uint32(n_vars), C.c_uint32(skip), _p(_c(eq_ind)),
+                                     (C.c_uint16 * nm)(*ma), (C.c_uint16 * nm)(*mb), (C.c_uint8 * nm)(*mc),
+                                     (C.c_uint32 * max(nc, 1))(*first), (C.c_uint32 * max(nc, 1))(*cnt), C.c_uint32(nc),
+                                     C.c_uint32(n_pts), C.c_uint32(n_threads), _p(out))
+    dt = time.perf_counter() - t0
+    _check(rc)
+    vals = to_ints(out)
+    return [vals[c * n_pts:(c + 1) * n_pts] for c in range(nc)], dt
+
+
 # ------------------------------------------------------------------------------------------------
 # additive NTT
 _NP_DT = {3: np.uint8, 4: np.uint16, 5: np.uint32, 6: np.uint64}

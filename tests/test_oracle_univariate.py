@@ -166,3 +166,18 @@ def test_round_eval_extension_equals_the_reference_ntt_route(oracle, skip, degre
     assert full[:K] == [0] * K and full[K:n] == stag
     for max_domain in (1 << log_domain, n + 3):
         assert oracle.extrapolate_round_evals(stag, skip, degree, max_domain) == full[K:max_domain]
+
+
+@pytest.mark.parametrize("skip,n_vars,threads", [(3, 8, 1), (4, 9, 3), (6, 10, 2)])
+def test_threaded_cpu_arm_matches_the_oracle(oracle, skip, n_vars, threads):
+    """oracle/cpu_univariate.c (the timed CPU baseline of the univariate-skip round) against the definition."""
+    rng = random.Random(500 + skip)
+    m = 6
+    cols = [oracle.to_arr(pack_scalars([rng.getrandbits(1) for _ in range(1 << n_vars)], 0)) for _ in range(m)]
+    comps = [[("var", 0), ("var", 1), ("mul", 0, 1), ("var", 2), ("add", 2, 3), ("var", 5), ("add", 4, 5)],
+             [("var", 3), ("const", 0x1D), ("mul", 0, 1), ("var", 4), ("var", 4), ("mul", 3, 4), ("add", 2, 5), ("const", 7), ("add", 6, 7)]]
+    eq = oracle.rand_b128(9, 1 << (n_vars - skip))
+    K = 1 << skip
+    got, _ = oracle.cpu_univariate_b1(cols, n_vars, skip, eq, comps, K, threads)
+    exp = oracle.zerocheck_univariate_evals(cols, [0] * m, n_vars, skip, eq, comps, 2 * K)
+    assert got == exp
