@@ -17,6 +17,7 @@
 #include "ntt_bs.cuh"
 #include "roundevals_tc.cuh"
 #include "univariate.cuh"
+#include "uni_split.hpp"
 
 using namespace b200;
 
@@ -1566,66 +1567,27 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 				// Too many columns for one CTA's shared memory (e.g. 153 columns at skip 7): constraints are local,
 				// so split the compositions into contiguous ranges whose referenced columns fit and launch the same
 				// kernel per range on the compacted column list.  OPT-IN until verified on a GPU.
+				static_assert(uni::SPLIT_MONO_NONE == uni::MONO_NONE && uni::SPLIT_CTAB == uni::CTAB && sizeof(uni::MonoW) == sizeof(uint2), "uni_split.hpp mirrors univariate.cuh");
 				const uint32_t cube = uni::SUBS * K;
-				auto vars_of = [&](uint32_t c, std::set<uint32_t> &cols) {
-					const uint32_t *ct = &ctab[uni::CTAB * c];
-					for (uint32_t t = 0; t < ct[1] + ct[2] + ct[3]; t++) {
-						const uint2 d = mono[ct[0] + t];
-						if (t < ct[1]) cols.insert(d.x / cube), cols.insert(d.y / cube);
-						else if (t < ct[1] + ct[2]) cols.insert(d.x / cube);
-						else {
-							if ((d.x & 511u) != uni::MONO_NONE) cols.insert(d.x & 511u);
-							if (((d.x >> 9) & 511u) != uni::MONO_NONE) cols.insert((d.x >> 9) & 511u);
-						}
-					}
-				};
-				struct Range { uint32_t c0, c1; std::vector<uint32_t> cols; };
-				std::vector<Range> ranges;
-				for (uint32_t c0 = 0; fast && c0 < n_comp;) {
-					std::set<uint32_t> cols;
-					uint32_t c1 = c0;
-					while (c1 < n_comp) {
-						std::set<uint32_t> t = cols;
-						vars_of(c1, t);
-						uni::B8Args probe;
-						if (!fits(layout(probe, (uint32_t)std::max<size_t>(t.size(), 1), c1 + 1 - c0, mono.size()), (uint32_t)t.size())) break;
-						cols.swap(t);
-						c1++;
-					}
-					if (c1 == c0) fast = false;  // a single composition does not fit: generic kernel
-					else ranges.push_back(Range{c0, c1, std::vector<uint32_t>(cols.begin(), cols.end())});
-					c0 = c1;
-				}
+				std::vector<uni::MonoW> mw(mono.size());
+				if (!mono.empty()) memcpy(mw.data(), mono.data(), 8 * mono.size());
+				std::vector<uni::SplitRange> ranges;
+				const size_t nm_all = mono.size();
+				fast = uni::plan_split(mw, ctab, n_comp, m, cube, [&](uint32_t ncols, uint32_t ncomp) {
+					uni::B8Args probe;
+					return fits(layout(probe, ncols, ncomp, nm_all), ncols);
+				}, ranges);
 				for (size_t ri = 0; fast && ri < ranges.size(); ri++) {
-					const Range &R = ranges[ri];
-					std::vector<uint32_t> local(m, 0);
+					const uni::SplitRange &R = ranges[ri];
 					std::vector<b200_dev_ptr> h_mls;
 					std::vector<uint32_t> h_lv;
 					for (uint32_t g : R.cols) {
-						local[g] = (uint32_t)h_mls.size();
 						h_mls.push_back(mls[g]);
 						h_lv.push_back(levels[g]);
 					}
 					if (h_mls.empty()) h_mls.push_back(mls[0]), h_lv.push_back(levels[0]);  // constants only
-					std::vector<uint2> mn;
-					std::vector<uint32_t> ct2(uni::CTAB * (size_t)(R.c1 - R.c0));
-					for (uint32_t c = R.c0; c < R.c1; c++) {
-						const uint32_t *ct = &ctab[uni::CTAB * c];
-						uint32_t *o = &ct2[uni::CTAB * (c - R.c0)];
-						o[0] = (uint32_t)mn.size(), o[1] = ct[1], o[2] = ct[2], o[3] = ct[3], o[4] = ct[4];
-						for (uint32_t t = 0; t < ct[1] + ct[2] + ct[3]; t++) {
-							uint2 d = mono[ct[0] + t];
-							if (t < ct[1]) d = make_uint2(local[d.x / cube] * cube, local[d.y / cube] * cube);
-							else if (t < ct[1] + ct[2]) d = make_uint2(local[d.x / cube] * cube, 0);
-							else {
-								uint32_t a = d.x & 511u, b = (d.x >> 9) & 511u;
-								if (a != uni::MONO_NONE) a = local[a];
-								if (b != uni::MONO_NONE) b = local[b];
-								d = make_uint2(a | (b << 9) | (d.x & ~0x3FFFFu), 0);
-							}
-							mn.push_back(d);
-						}
-					}
+					std::vector<uint2> mn(R.mono.size());
+					if (!mn.empty()) memcpy(mn.data(), R.mono.data(), 8 * mn.size());
 					ArgPack pk3;
 					size_t o_p = pk3.add(h_mls.data(), sizeof(void *) * h_mls.size()), o_l = pk3.add(h_lv.data(), 4 * h_lv.size());
 					uint8_t *base3;
@@ -1633,7 +1595,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 					uni::B8Args Br;
 					const uint32_t ml = (uint32_t)h_mls.size();
 					const uint32_t sm = layout(Br, ml, R.c1 - R.c0, mn.size());
-					if ((rc = launch(Br, sm, (const uint4 *const *)(base3 + o_p), (const uint32_t *)(base3 + o_l), ml, R.c0, R.c1 - R.c0, mn, ct2))) return rc;
+					if ((rc = launch(Br, sm, (const uint4 *const *)(base3 + o_p), (const uint32_t *)(base3 + o_l), ml, R.c0, R.c1 - R.c0, mn, R.ctab))) return rc;
 					if (ri + 1 < ranges.size()) B200_LAUNCH_CHECK(ctx);
 				}
 			} else
