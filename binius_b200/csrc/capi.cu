@@ -15,6 +15,7 @@
 #include "fold_tma.cuh"
 #include "ntt.cuh"
 #include "ntt_bs.cuh"
+#include "ntt_lut.cuh"
 #include "roundevals_tc.cuh"
 #include "univariate.cuh"
 #include "uni_split.hpp"
@@ -33,6 +34,7 @@ struct b200_ntt {
 	uint32_t kt = 5, d = 0;
 	std::vector<std::vector<uint64_t>> s_evals;  // rows (host), values < 2^(2^kt)
 	uint32_t *d_s_evals = nullptr;               // device [32][32]
+	uint32_t *d_basis = nullptr;                 // device [32][32][32]: s_evals[row][bit] * 2^k (B32 only; ntt_lut.cuh)
 };
 
 namespace b200 {
@@ -274,6 +276,26 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 }
 
 static int32_t flush_pending(b200_ctx *ctx);
+// Every entry point takes the context lock (a context may be shared by several host threads: the trait methods
+// take `&self`, compute/src/layer.rs:115-131) and makes the context's device current for the call.
+struct CtxGuard {
+	b200_ctx *c;
+	int prev = -1;
+	explicit CtxGuard(b200_ctx *ctx) : c(ctx) {
+		if (!c) return;
+		c->mu.lock();
+		if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+		if (prev != c->device) cudaSetDevice(c->device);
+		else prev = -1;
+	}
+	~CtxGuard() {
+		if (!c) return;
+		if (prev >= 0) cudaSetDevice(prev);
+		c->mu.unlock();
+	}
+	CtxGuard(const CtxGuard &) = delete;
+};
+#define B200_LOCK(ctx) CtxGuard guard__(ctx)
 #define B200_FLUSH(ctx)                                  \
 	do {                                                  \
 		if ((ctx) && !(ctx)->pending.empty()) {           \
@@ -362,6 +384,14 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
 	SET(k_ntt_bs_pass, 36 * 1024 + 16 + 128 * 1024);
 	SET(k_ntt_bs_low, 184 * 1024 + 640 + 16);
+	SET((nttl::k_ntt_lut<0, false>), nttl::layout(0, 7).total);
+	SET((nttl::k_ntt_lut<0, true>), nttl::layout(0, 7).total);
+	SET((nttl::k_ntt_lut<1, false>), nttl::layout(1, 7).total);
+	SET((nttl::k_ntt_lut<1, true>), nttl::layout(1, 7).total);
+	SET((nttl::k_ntt_lut<2, false>), nttl::layout(2, 7).total);
+	SET((nttl::k_ntt_lut<2, true>), nttl::layout(2, 7).total);
+	SET((nttl::k_ntt_lut<3, false>), nttl::layout(3, 7).total);
+	SET((nttl::k_ntt_lut<3, true>), nttl::layout(3, 7).total);
 	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
 	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
 #undef SET
@@ -395,16 +425,42 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 }
 
 const char *b200_last_error(b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-void *b200_ctx_stream(b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+void *b200_ctx_stream(b200_ctx *ctx) {
+	// a caller that orders its own work on the stream must see every queued fold launched
+	if (!ctx) return nullptr;
+	B200_LOCK(ctx);
+	if (!ctx->pending.empty()) flush_pending(ctx);
+	return (void *)ctx->stream;
+}
+int32_t b200_flush(b200_ctx *ctx) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	return B200_OK;
+}
 uint64_t b200_ctx_launch_count(b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int32_t b200_ctx_set_stream(b200_ctx *ctx, void *s) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
 	return B200_OK;
 }
+int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !key) return B200_ERR_INPUT_VALIDATION;
+	if (!strcmp(key, "ntt")) ctx->tune_ntt = value;
+	else if (!strcmp(key, "ntt_log_cc")) ctx->tune_ntt_log_cc = (uint32_t)std::min(7, std::max(5, value));
+	else if (!strcmp(key, "fold")) ctx->tune_fold = value;
+	else if (!strcmp(key, "round_evals_tc")) ctx->tune_round_evals_tc = value;
+	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
+	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
+	return B200_OK;
+}
 int32_t b200_event_create(b200_ctx *ctx, void **out) {
+	B200_LOCK(ctx);
 	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
 	cudaEvent_t e;
 	B200_CUDA(ctx, cudaEventCreate(&e));
@@ -412,12 +468,14 @@ int32_t b200_event_create(b200_ctx *ctx, void **out) {
 	return B200_OK;
 }
 int32_t b200_event_record(b200_ctx *ctx, void *e) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaEventRecord((cudaEvent_t)e, ctx->stream));
 	return B200_OK;
 }
 int32_t b200_event_elapsed_ms(b200_ctx *ctx, void *a, void *b, float *ms) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !ms) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaEventSynchronize((cudaEvent_t)b));
@@ -429,8 +487,8 @@ void b200_event_destroy(void *e) {
 }
 
 int32_t b200_dev_alloc(b200_ctx *ctx, uint64_t n_elems, b200_dev_ptr *out) {
+	B200_LOCK(ctx);
 	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
-	cudaSetDevice(ctx->device);
 	void *p = nullptr;
 	if (cudaMalloc(&p, std::max<uint64_t>(n_elems, 1) * 16) != cudaSuccess) {
 		cudaGetLastError();
@@ -440,6 +498,7 @@ int32_t b200_dev_alloc(b200_ctx *ctx, uint64_t n_elems, b200_dev_ptr *out) {
 	return B200_OK;
 }
 int32_t b200_dev_free(b200_ctx *ctx, b200_dev_ptr p) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -447,6 +506,7 @@ int32_t b200_dev_free(b200_ctx *ctx, b200_dev_ptr p) {
 	return B200_OK;
 }
 int32_t b200_host_alloc(b200_ctx *ctx, uint64_t n_bytes, void **out) {
+	B200_LOCK(ctx);
 	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
 	if (cudaMallocHost(out, std::max<uint64_t>(n_bytes, 1)) != cudaSuccess) {
 		cudaGetLastError();
@@ -455,12 +515,14 @@ int32_t b200_host_alloc(b200_ctx *ctx, uint64_t n_bytes, void **out) {
 	return B200_OK;
 }
 int32_t b200_host_free(b200_ctx *ctx, void *p) {
+	B200_LOCK(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaFreeHost(p));
 	return B200_OK;
 }
 
 int32_t b200_copy_h2d(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t n) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) return B200_OK;
@@ -469,6 +531,7 @@ int32_t b200_copy_h2d(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t
 	return B200_OK;
 }
 int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *dst, uint64_t n) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n) B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -476,12 +539,14 @@ int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *dst, uint64_t n) {
 	return B200_OK;
 }
 int32_t b200_copy_d2d(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n) B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
 	return B200_OK;
 }
 int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n, const uint64_t value[2]) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) return B200_OK;
@@ -490,6 +555,7 @@ int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n, const uint64_t va
 	return B200_OK;
 }
 int32_t b200_sync(b200_ctx *ctx) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -497,6 +563,7 @@ int32_t b200_sync(b200_ctx *ctx) {
 }
 
 int32_t b200_results_reset(b200_ctx *ctx) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (ctx->n_results) B200_CUDA(ctx, cudaMemsetAsync(ctx->d_results, 0, sizeof(uint4) * ctx->n_results, ctx->stream));
@@ -504,6 +571,7 @@ int32_t b200_results_reset(b200_ctx *ctx) {
 	return B200_OK;
 }
 int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uint64_t *host_out) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) {
@@ -595,15 +663,6 @@ static int32_t launch_lerp_tma(b200_ctx *ctx, const std::vector<LerpSeg> &live, 
 	}
 	return B200_OK;
 }
-static int fold_engine() {
-	// B200_FOLD_ENGINE = tma (default) | k64 | lut128 : A/B runs of the three fold kernels
-	static const int engine = [] {
-		const char *e = getenv("B200_FOLD_ENGINE");
-		return !e ? 2 : !strcmp(e, "lut128") ? 0 : !strcmp(e, "k64") ? 1 : 2;
-	}();
-	return engine;
-}
-
 extern "C" {
 static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint64_t z[2]) {
 	std::vector<LerpSeg> live;
@@ -614,7 +673,7 @@ static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint
 	if (live.empty()) return B200_OK;
 	// 512 threads x 2 elements in flight, 2 CTAs per SM (64 registers): best of the measured variants.
 	// B200_FOLD_ENGINE=lut128 selects the 16 x LDS.128 engine instead of the Karatsuba-64 one (A/B runs).
-	const int engine = fold_engine();
+	const int engine = ctx->tune_fold;
 	if (engine == 0) return launch_lerp_variant<512, 2, 2, false, false>(ctx, live, z);
 	if (engine == 1) return launch_lerp_variant<512, 2, 2, false, true>(ctx, live, z);
 	for (auto &sg : live)
@@ -623,6 +682,7 @@ static int32_t launch_lerp(b200_ctx *ctx, std::vector<LerpSeg> &segs, const uint
 }
 
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_dev_ptr e1, uint64_t n1, const uint64_t z[2]) {
+	B200_LOCK(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n0 != n1) return fail(ctx, B200_ERR_INPUT_VALIDATION, "evals_0 and evals_1 must be the same length");
 	if (n0 == 0) return B200_OK;
@@ -662,6 +722,7 @@ extern "C" {
 // hal/src/backend.rs:19-31, 65-75): chunked 4-slot pipeline  H2D(e0,e1) -> fold kernel -> D2H(e0)  on
 // three streams so that both PCIe directions and the kernel overlap.  Synchronous.
 int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *host_e1, uint64_t n, const uint64_t z[2]) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n == 0) return B200_OK;
@@ -716,6 +777,7 @@ int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *hos
 
 int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars,
 										   const uint64_t *prefix, const uint64_t *suffix, const uint64_t z[2], uint64_t *new_lens) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
@@ -735,6 +797,7 @@ int32_t b200_fold_multilinears_high_to_low(b200_ctx *ctx, const b200_dev_ptr *ml
 
 int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *mls, const b200_dev_ptr *outs, uint32_t m, uint32_t n_vars,
 										   const uint64_t *prefix, const uint64_t *suffix, const uint64_t z[2], uint64_t *new_lens) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
@@ -750,13 +813,14 @@ int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *ml
 		if (upper) live.push_back(LerpSeg{(uint4 *)outs[t], (const uint4 *)mls[t], p / 2, upper, to_u4(suffix + 2 * t), 0});
 	}
 	if (live.empty()) return B200_OK;
-	bool small = fold_engine() == 2;
+	bool small = ctx->tune_fold == 2;
 	for (auto &sg : live) small = small && !(sg.upper >> 31);  // 32-bit tile arithmetic in the TMA kernel
 	if (!small) return launch_lerp_variant<512, 2, 2, true>(ctx, live, z);
 	return launch_lerp_tma<true>(ctx, live, z);
 }
 
 int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, uint32_t log_n, const uint64_t *coords, uint32_t k) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (log_n + k > 60 || data_len != (1ull << (log_n + k))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data length: %llu", (unsigned long long)data_len);
@@ -792,6 +856,7 @@ int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, 
 }
 
 int32_t b200_tensor_product_full_query(b200_ctx *ctx, const uint64_t *query, uint32_t k, b200_dev_ptr out, uint64_t n_out) {
+	B200_LOCK(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (k > 60 || n_out != (1ull << k)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output must hold 2^%u elements", k);
 	const uint64_t one[2] = {1, 0};
@@ -803,6 +868,7 @@ int32_t b200_tensor_product_full_query(b200_ctx *ctx, const uint64_t *query, uin
 static bool valid_level(uint32_t lvl) { return lvl == 0 || (lvl >= 3 && lvl <= 7); }
 
 int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t lvl, b200_dev_ptr b, uint64_t n_b, uint32_t *slot) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
 	if (lvl > 7 || (n_a << (7 - lvl)) != n_b) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid input: a_edeg=%u |a|=%llu |b|=%llu", lvl, (unsigned long long)n_a, (unsigned long long)n_b);
@@ -829,6 +895,7 @@ int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t
 }
 
 static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (lvl > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid evals: tower_level=%u > 7", lvl);
@@ -867,6 +934,7 @@ int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_
 
 // ---- expressions --------------------------------------------------------------------------------
 int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n_steps, b200_expr **out) {
+	B200_LOCK(ctx);
 	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
 	if (n_steps > MAX_EXPR_STEPS) return fail(ctx, B200_ERR_INPUT_VALIDATION, "expression has %u steps (max %u)", n_steps, MAX_EXPR_STEPS);
 	uint32_t n_vars = 0;
@@ -907,6 +975,7 @@ uint32_t b200_expr_n_vars(const b200_expr *e) { return e ? e->n_vars : 0; }
 static DevExpr dev_expr(const b200_expr *e) { return DevExpr{e->d_steps, (uint32_t)e->steps.size(), e->n_vars}; }
 
 int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, b200_dev_ptr out, uint64_t n_out, const b200_expr *expr) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
 	if (row_len != n_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "inputs and output must be the same length");
@@ -923,6 +992,7 @@ int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32
 }
 
 int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t n_in, const b200_dev_ptr *outs, const uint64_t *lens, uint32_t n_rounds) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (!is_pow2(n_in)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "input length must be a power of 2: %llu", (unsigned long long)n_in);
@@ -942,6 +1012,7 @@ int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t
 
 // ---- KernelExecutor ------------------------------------------------------------------------------
 int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *slot) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
 	int32_t rc = new_slot(ctx, slot);
@@ -953,6 +1024,7 @@ int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *
 	return B200_OK;
 }
 int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
 	if (slot >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "value slot %u not declared", slot);
@@ -968,6 +1040,7 @@ int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inp
 	return B200_OK;
 }
 int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr a, b200_dev_ptr b, b200_dev_ptr dst) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || log_len > 60) return B200_ERR_INPUT_VALIDATION;
 	uint64_t n = 1ull << log_len;
@@ -980,6 +1053,7 @@ int32_t b200_kernel_add_assign(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr src
 }
 
 int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, const uint32_t *ia, const uint32_t *ib, uint32_t n_comp, const uint64_t coeff[2], uint32_t *slot_y1, uint32_t *slot_yinf) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !slot_y1 || !slot_yinf) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
@@ -1000,7 +1074,7 @@ int32_t b200_bivariate_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, uint3
 		pows[c] = to_u4(w);
 		pw = hostf::mul128(pw, a);
 	}
-	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
+	const int tc_mode = ctx->tune_round_evals_tc;
 	if (tc_mode && half >= 4096 && half % tc::CHUNK == 0) {
 		// tensor-core path (roundevals_tc.cuh): two inner-product jobs per composition
 		std::vector<tc::TcJob> jobs(2 * (size_t)n_comp);
@@ -1032,6 +1106,7 @@ int32_t b200_eq_ind_round_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const ui
 }
 
 int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_ptr *mls, const uint64_t *lens, const uint64_t *suffix_evals, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps, const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points, uint32_t *first_slot) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !first_slot) return B200_ERR_INPUT_VALIDATION;
 	if (n_vars == 0 || n_vars > 60) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars must be in [1, 60]");
@@ -1062,7 +1137,7 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 		if (hlen[t] > (1ull << n_vars)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: stored length exceeds 2^n_vars", t);
 		hs[t] = suffix_evals ? to_u4(suffix_evals + 2 * t) : make_uint4(0, 0, 0, 0);
 	}
-	static int tc_mode = getenv("B200_ROUND_EVALS_TC") ? atoi(getenv("B200_ROUND_EVALS_TC")) : 1;
+	const int tc_mode = ctx->tune_round_evals_tc;
 	const uint64_t half = 1ull << (n_vars - 1);
 	if (tc_mode >= 1 && tc_mode != 2 && half >= 4096 && half % tc::CHUNK == 0 && order == B200_HIGH_TO_LOW) {
 		// points 1 / infinity only, full-length multilinears, degree <= 2: monomial plan, no interpreter
@@ -1118,6 +1193,7 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 
 // ---- NTT -----------------------------------------------------------------------------------------
 int32_t b200_ntt_create(b200_ctx *ctx, uint32_t kt, uint32_t d, b200_ntt **out) {
+	B200_LOCK(ctx);
 	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
 	if (kt < 3 || kt > 5) return fail(ctx, B200_ERR_INPUT_VALIDATION, "twiddle field must be B8, B16 or B32");
 	if (d == 0) return fail(ctx, B200_ERR_NTT_DOMAIN, "domain size is less than 2**1");
@@ -1152,12 +1228,26 @@ int32_t b200_ntt_create(b200_ctx *ctx, uint32_t kt, uint32_t d, b200_ntt **out) 
 		return fail(ctx, B200_ERR_ALLOC, "out of device memory");
 	}
 	B200_CUDA(ctx, cudaMemcpy(n->d_s_evals, flat.data(), sizeof(uint32_t) * 32 * 32, cudaMemcpyHostToDevice));
+	if (kt == 5) {
+		// basis products of the look-up-table passes (ntt_lut.cuh): every table entry is an XOR of these
+		std::vector<uint32_t> basis(32 * 32 * 32, 0);
+		for (uint32_t r = 0; r < d; r++)
+			for (size_t j = 0; j < n->s_evals[r].size(); j++)
+				for (uint32_t k = 0; k < 32; k++) basis[(r * 32 + j) * 32 + k] = (uint32_t)hostf::mul((u128)n->s_evals[r][j], (u128)1 << k, 5);
+		if (cudaMalloc(&n->d_basis, sizeof(uint32_t) * basis.size()) != cudaSuccess) {
+			cudaGetLastError();
+			cudaFree(n->d_s_evals);
+			return fail(ctx, B200_ERR_ALLOC, "out of device memory");
+		}
+		B200_CUDA(ctx, cudaMemcpy(n->d_basis, basis.data(), sizeof(uint32_t) * basis.size(), cudaMemcpyHostToDevice));
+	}
 	*out = n.release();
 	return B200_OK;
 }
 void b200_ntt_destroy(b200_ntt *ntt) {
 	if (!ntt) return;
 	cudaFree(ntt->d_s_evals);
+	if (ntt->d_basis) cudaFree(ntt->d_basis);
 	delete ntt;
 }
 uint32_t b200_ntt_log_domain_size(const b200_ntt *ntt) { return ntt ? ntt->d : 0; }
@@ -1174,6 +1264,7 @@ int32_t b200_ntt_get_subspace_eval(const b200_ntt *ntt, uint32_t i, uint64_t j, 
 }
 
 static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev_ptr data, uint32_t kd, uint64_t n_elems, uint32_t log_x, uint32_t log_y, uint32_t log_z, uint64_t coset, uint32_t coset_bits, uint32_t skip_rounds) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
 	if (kd < ntt->kt || kd > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "element width 2^%u bits is not an extension of the twiddle field", kd);
@@ -1195,32 +1286,46 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 	const uint32_t LT = ((n_elems << (kd - ntt->kt)) >> 25) ? 8u : NTT_BS_MAX_LOG_TILE;
 	std::vector<Pass> plan;
 	const uint32_t MAX_LOG_TILE = 13;
-	static int force_scalar = getenv("B200_NTT_SCALAR") ? atoi(getenv("B200_NTT_SCALAR")) : 0;
-	if (ntt->kt == 5 && !force_scalar) {
+	// ctx->tune_ntt: 0 = look-up-table passes + bit-sliced low layers (default), 1 = bit-sliced only, 2 = scalar tables
+	if (ntt->kt == 5 && ctx->tune_ntt != 2) {
+		// Look-up-table passes (ntt_lut.cuh) take every layer whose twiddles are shared by >= 2^5 positions
+		// (lx + i >= 5; 2^6 when the bit-sliced low pass exists anyway); the layers below stay bit-sliced.
+		uint32_t n_bs = lx >= 5 ? 0u : std::min(n_layers, 6u - lx);
+		uint32_t n_lut = n_layers - n_bs;
+		if (ctx->tune_ntt == 1 || n_lut < 3 || !ntt->d_basis) n_bs = n_layers, n_lut = 0;
 		uint32_t i_lo = 0;
-		if (lx < 5 && lx + log_y >= 5) {
+		if (n_bs && lx < 5 && lx + log_y >= 5) {
 			// kind 2: lowest pass on units of 32 consecutive scalars (intra-unit layers + up to Rt inter-unit)
 			uint32_t L0 = 5 - lx;
 			uint32_t Rt = std::min(LT, lx + log_y - 5);
-			uint32_t n_intra = std::min(n_layers, L0);
-			uint32_t n_inter = std::min(n_layers - n_intra, Rt);
-			uint32_t rest = n_layers - n_intra - n_inter;
+			uint32_t n_intra = std::min(n_bs, L0);
+			uint32_t n_inter = std::min(n_bs - n_intra, Rt);
+			uint32_t rest = n_bs - n_intra - n_inter;
 			if (rest > 0 && rest < 4 && n_inter + rest >= 8) n_inter = n_inter + rest - 4;  // avoid a tiny upper pass
 			plan.push_back(Pass{2, 0, Rt, n_intra, n_inter});
 			i_lo = n_intra + n_inter;
-		} else if (lx < 5) {
-			plan.push_back(Pass{0, 0, log_y, n_layers, lx});  // transform smaller than one unit
-			i_lo = n_layers;
+		} else if (n_bs && lx < 5) {
+			plan.push_back(Pass{0, 0, log_y, n_bs, lx});  // transform smaller than one unit
+			i_lo = n_bs;
 		}
 		// tiles of 2^(R + log_cu) = 2^LT units: one butterfly-unit per thread and layer
-		while (i_lo < n_layers) {
-			const uint32_t rem = n_layers - i_lo;
+		while (i_lo < n_bs) {
+			const uint32_t rem = n_bs - i_lo;
 			uint32_t log_cu = rem <= LT ? 0u : std::min(lx + i_lo - 5, 1u);  // a last pass of exactly LT layers takes single-unit rows
 			uint32_t R = std::min(rem, LT - log_cu);
-			if (n_layers - i_lo - R > 0 && n_layers - i_lo - R < 4) R = (n_layers - i_lo + 1) / 2;  // avoid a tiny last pass
+			if (n_bs - i_lo - R > 0 && n_bs - i_lo - R < 4) R = (n_bs - i_lo + 1) / 2;  // avoid a tiny last pass
 			log_cu = std::min(lx + i_lo - 5, LT - R);  // short passes take wider tiles: always 2^LT units
 			plan.push_back(Pass{1, i_lo, R, R, log_cu});
 			i_lo += R;
+		}
+		if (n_lut) {
+			// passes of 3..6 layers, the larger ones at the bottom (their table builds amortise over fewer columns)
+			const uint32_t n_pass = (n_lut + 5) / 6, base = n_lut / n_pass, rem = n_lut % n_pass;
+			for (uint32_t p = 0; p < n_pass; p++) {
+				const uint32_t R = base + (p < rem ? 1u : 0u);
+				plan.push_back(Pass{3, i_lo, R, R, std::min(lx + i_lo, ctx->tune_ntt_log_cc)});
+				i_lo += R;
+			}
 		}
 	} else {
 		for (uint32_t i_lo = 0; i_lo < n_layers;) {
@@ -1237,10 +1342,44 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 	for (size_t pi = 0; pi < plan.size(); pi++) {
 		const Pass &P = inverse ? plan[pi] : plan[plan.size() - 1 - pi];
 		// neighbours in execution order: bit-sliced passes hand the data over bit-sliced
-		auto kind_at = [&](size_t q) { return (inverse ? plan[q] : plan[plan.size() - 1 - q]).kind; };
-		const uint32_t in_sliced = pi > 0 && P.kind != 0 && kind_at(pi - 1) != 0;
-		const uint32_t out_sliced = pi + 1 < plan.size() && P.kind != 0 && kind_at(pi + 1) != 0;
+		auto sliced_at = [&](size_t q) {
+			const uint32_t k = (inverse ? plan[q] : plan[plan.size() - 1 - q]).kind;
+			return k == 1 || k == 2;
+		};
+		const uint32_t in_sliced = pi > 0 && sliced_at(pi) && sliced_at(pi - 1);
+		const uint32_t out_sliced = pi + 1 < plan.size() && sliced_at(pi) && sliced_at(pi + 1);
 		uint32_t row0 = ntt->d - (log_y + coset_bits);
+		if (P.kind == 3) {
+			nttl::Args L;
+			L.data = (uint32_t *)data;
+			L.basis = ntt->d_basis;
+			L.lx = lx;
+			L.log_y = log_y;
+			L.i_lo = P.i_lo;
+			L.row0 = row0;
+			L.d = ntt->d;
+			L.log_cc = P.log_c;
+			L.n_z = n_z;
+			L.coset = coset;
+			const uint32_t R1 = P.R - 3;
+			const uint64_t items = (uint64_t)n_z << (log_y - P.i_lo - P.R + lx + P.i_lo - P.log_c);
+			const uint32_t grid = (uint32_t)std::min<uint64_t>(items, 2ull * ctx->n_sms);
+			const uint32_t smem = nttl::layout((int)R1, P.log_c).total;
+#define B200_NTT_LUT(R1V)                                                                       \
+	case R1V:                                                                                   \
+		if (inverse) nttl::k_ntt_lut<R1V, true><<<grid, nttl::THREADS, smem, ctx->stream>>>(L); \
+		else nttl::k_ntt_lut<R1V, false><<<grid, nttl::THREADS, smem, ctx->stream>>>(L);        \
+		break;
+			switch (R1) {
+				B200_NTT_LUT(0)
+				B200_NTT_LUT(1)
+				B200_NTT_LUT(2)
+				B200_NTT_LUT(3)
+			}
+#undef B200_NTT_LUT
+			B200_LAUNCH_CHECK(ctx);
+			continue;
+		}
 		if (P.kind == 2) {
 			NttBsLowArgs L;
 			L.data = (uint32_t *)data;
@@ -1319,6 +1458,7 @@ int32_t b200_ntt_inverse(b200_ctx *ctx, const b200_ntt *ntt, b200_dev_ptr data, 
 }
 
 static int32_t ntt_host(b200_ctx *ctx, const b200_ntt *ntt, int inverse, void *host, uint32_t kd, uint64_t n, uint32_t lx, uint32_t ly, uint32_t lz, uint64_t coset, uint32_t cb, uint32_t skip) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
 	if (kd < 3 || kd > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "bad element width");
@@ -1340,6 +1480,7 @@ int32_t b200_ntt_inverse_host(b200_ctx *ctx, const b200_ntt *ntt, void *host, ui
 }
 
 int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint32_t log_batch, const uint64_t *challenges, uint32_t n_ch, b200_dev_ptr in, uint64_t n_in, b200_dev_ptr out, uint64_t n_out) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !ntt) return B200_ERR_INPUT_VALIDATION;
 	if (log_len + log_batch > 60 || n_in != (1ull << (log_len + log_batch))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data_in length: %llu", (unsigned long long)n_in);
@@ -1408,6 +1549,7 @@ static uint32_t const_level(uint64_t lo, uint64_t hi) {
 }
 
 int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint64_t *host_out) {
+	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
@@ -1492,7 +1634,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 		const uint32_t gx = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(want, std::max(1u, ctx->n_sms * per_sm / gy)));
 		dim3 grid(gx, gy);
 		// B8 fast path: B1/B8 columns, B8 constants, every composition a sum of monomials of degree <= 2
-		bool fast = lvl == 3 && skip >= 2 && !getenv("B200_UNI_GENERIC");
+		bool fast = lvl == 3 && skip >= 2 && !ctx->tune_uni_generic;
 		std::vector<uint2> mono;
 		std::vector<uint32_t> ctab(uni::CTAB * (size_t)n_comp);
 		for (uint32_t c = 0; fast && c < n_comp; c++) {
@@ -1563,10 +1705,11 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 			const uint32_t smem8 = layout(B, m, n_comp, mono.size());
 			if (fits(smem8, m)) {
 				if ((rc = launch(B, smem8, A.mls, A.levels, m, 0, n_comp, mono, ctab))) return rc;
-			} else if (getenv("B200_UNI_SPLIT")) {
+			} else {
 				// Too many columns for one CTA's shared memory (e.g. 153 columns at skip 7): constraints are local,
 				// so split the compositions into contiguous ranges whose referenced columns fit and launch the same
-				// kernel per range on the compacted column list.  OPT-IN until verified on a GPU.
+				// kernel per range on the compacted column list (verified on the GPU in round 1: both variants of
+				// test_many_columns_at_the_reference_skip passed).
 				static_assert(uni::SPLIT_MONO_NONE == uni::MONO_NONE && uni::SPLIT_CTAB == uni::CTAB && sizeof(uni::MonoW) == sizeof(uint2), "uni_split.hpp mirrors univariate.cuh");
 				const uint32_t cube = uni::SUBS * K;
 				std::vector<uni::MonoW> mw(mono.size());
@@ -1585,7 +1728,13 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 						h_mls.push_back(mls[g]);
 						h_lv.push_back(levels[g]);
 					}
-					if (h_mls.empty()) h_mls.push_back(mls[0]), h_lv.push_back(levels[0]);  // constants only
+					if (h_mls.empty()) {  // constants only: the kernel still wants one (unused) column
+						if (m == 0) {
+							fast = false;
+							break;
+						}
+						h_mls.push_back(mls[0]), h_lv.push_back(levels[0]);
+					}
 					std::vector<uint2> mn(R.mono.size());
 					if (!mn.empty()) memcpy(mn.data(), R.mono.data(), 8 * mn.size());
 					ArgPack pk3;
@@ -1598,8 +1747,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 					if ((rc = launch(Br, sm, (const uint4 *const *)(base3 + o_p), (const uint32_t *)(base3 + o_l), ml, R.c0, R.c1 - R.c0, mn, R.ctab))) return rc;
 					if (ri + 1 < ranges.size()) B200_LAUNCH_CHECK(ctx);
 				}
-			} else
-				fast = false;
+			}
 		}
 		if (!fast) switch (lvl) {
 		case 3:

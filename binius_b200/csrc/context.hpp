@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -19,7 +20,29 @@ struct b200_pending_lerp {
 	uint64_t n;
 };
 
+// one recorded KernelExecutor op of an open kernel scope (b200_kernel_scope_begin .. _end)
+struct b200_expr;
+struct b200_trace_op {
+	int kind = 0;  // 0 decl_value, 1 sum_composition_evals, 2 add
+	uint32_t slot = 0;
+	uint64_t init[2] = {0, 0};
+	std::vector<const void *> inputs;
+	uint64_t row_len = 0;
+	const b200_expr *expr = nullptr;
+	uint64_t coeff[2] = {0, 0};
+	uint32_t log_len = 0;
+	const void *a = nullptr, *b = nullptr;
+	void *dst = nullptr;
+};
+struct b200_local_chunk {
+	uint8_t *p;
+	uint64_t bytes, used;
+};
+
 struct b200_ctx {
+	// every entry point locks the context: `&self` calls from several host threads (rayon `join`/`map`,
+	// compute/src/layer.rs:115-131) serialise on it; a kernel scope holds it from begin to end
+	std::recursive_mutex mu;
 	int device = 0;
 	int n_sms = 148;
 	cudaStream_t stream = nullptr;
@@ -46,6 +69,17 @@ struct b200_ctx {
 	// general device scratch (grown on demand)
 	uint8_t *d_scratch = nullptr;
 	uint64_t scratch_bytes = 0;
+	// kernel scope (accumulate_kernels / map_kernels, layer.rs:134-245): ops are recorded and lowered at scope end
+	bool tracing = false;
+	std::vector<b200_trace_op> trace;
+	std::vector<b200_local_chunk> local_pool;            // KernelMemMap::Local scratch, grown by chunks, never moved
+	std::vector<std::pair<uint8_t *, uint64_t>> locals;  // (base, bytes) of the locals of the open scope
+	// kernel-selection switches for A/B measurements (b200_ctx_set_tuning); defaults = production paths
+	int tune_ntt = 0;              // 0 look-up-table + bit-sliced low layers, 1 bit-sliced only, 2 scalar tables
+	uint32_t tune_ntt_log_cc = 6;  // columns per work item of a look-up-table pass
+	int tune_fold = 2;             // 2 TMA-staged K64, 1 K64, 0 LUT128
+	int tune_round_evals_tc = 1;   // 1 tensor-core plans, 0 per-lane kernels, 2 materialised values only
+	int tune_uni_generic = 0;      // 1 forces the generic univariate-skip kernel
 };
 
 namespace b200 {

@@ -630,6 +630,10 @@ class B200Layer:
     def launch_count(self) -> int:
         return int(self._lib.b200_ctx_launch_count(self._ctx))
 
+    def set_tuning(self, key: str, value: int):
+        """kernel-selection switch for A/B measurements and tests (b200_ctx_set_tuning)"""
+        self._check(self._lib.b200_ctx_set_tuning(self._ctx, key.encode(), int(value)))
+
     def to_device(self, host: np.ndarray) -> DevSlice:
         host = np.ascontiguousarray(host, dtype=np.uint64).reshape(-1, 2)
         d = self.dev_alloc(len(host))

@@ -60,6 +60,11 @@ const char *b200_last_error(b200_ctx *ctx);
 void *b200_ctx_stream(b200_ctx *ctx);
 /* adopt an external stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own one */
 int32_t b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
+/* Kernel-selection switches for A/B measurements and tests (never needed for correctness; the defaults are
+ * the production paths).  Keys: "ntt" (0 look-up-table passes + bit-sliced low layers, 1 bit-sliced only,
+ * 2 scalar tables), "ntt_log_cc" (5..7), "fold" (2 TMA-staged, 1 K64, 0 LUT128), "round_evals_tc" (1/0/2),
+ * "uni_generic" (1 forces the generic univariate-skip kernel).  Unknown key: InputValidation. */
+int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value);
 /* CUDA-event timing on the context's stream (bench.py): record two events, read elapsed ms */
 int32_t b200_event_create(b200_ctx *ctx, void **event_out);
 int32_t b200_event_record(b200_ctx *ctx, void *event);

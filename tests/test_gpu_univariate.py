@@ -169,18 +169,14 @@ def test_error_behaviour(hal, oracle):
     assert L._lib.b200_zerocheck_univariate_evals(L._ctx, ptrs, lv, 1, n_vars, 2, eq.ptr, 16, lin, dg, 1, 4, out) == 0
 
 
-@pytest.mark.xfail(strict=False, reason="80 columns at skip 7 exceed one CTA's shared memory: B200_UNI_SPLIT=1 runs the fast kernel per composition "
-                                        "range (written after the round's GPU budget was spent, opt-in until a GPU run confirms it); "
-                                        "without it the call takes the generic kernel")
-@pytest.mark.parametrize("split", [False, True])
-def test_many_columns_at_the_reference_skip(hal, oracle, split, monkeypatch):
-    """The reference's choice for degree-2 constraints over B8 is skip_rounds = 7 (constraint_system/verify.rs:271-294)."""
+@pytest.mark.parametrize("generic", [False, True])
+def test_many_columns_at_the_reference_skip(hal, oracle, generic):
+    """The reference's choice for degree-2 constraints over B8 is skip_rounds = 7 (constraint_system/verify.rs:271-294).
+    80 columns at skip 7 exceed one CTA's shared memory: the default path runs the fast kernel per composition range
+    (uni_split.hpp); `generic` forces the generic kernel on the same shape."""
     from binius_b200 import ArithCircuit as A
 
-    if split:
-        monkeypatch.setenv("B200_UNI_SPLIT", "1")
-    else:
-        monkeypatch.delenv("B200_UNI_SPLIT", raising=False)
+    hal.set_tuning("uni_generic", int(generic))
     rng = random.Random(123)
     n_vars, skip, m = 9, 7, 80
     cols = [[rng.getrandbits(1) for _ in range(1 << n_vars)] for _ in range(m)]
@@ -188,5 +184,8 @@ def test_many_columns_at_the_reference_skip(hal, oracle, split, monkeypatch):
     comps = [v[(2 * c) % m] * v[(2 * c + 1) % m] + v[(2 * c + 5) % m] + v[(2 * c + 11) % m] for c in range(36)]
     comps.append(v[3] * v[70] + A.constant(0x53) * v[40] + A.constant(1))
     ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
-    got, exp, _, _ = _run(hal, oracle, cols, [0] * m, n_vars, skip, comps, 256, ch)
+    try:
+        got, exp, _, _ = _run(hal, oracle, cols, [0] * m, n_vars, skip, comps, 256, ch)
+    finally:
+        hal.set_tuning("uni_generic", 0)
     assert got == exp
