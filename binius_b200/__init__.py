@@ -10,7 +10,7 @@ from . import _lib  # noqa: F401
 from .layer import (AllocError, ArithCircuit, B200Executor, B200KernelExecutor, B200Layer, B200LayerHolder,  # noqa: F401
                     BumpAllocator, ComputeData, DevSlice, DeviceError, Error, ExprEval, HostBumpAllocator,
                     InputValidation, KernelBuffer, KernelMemMap, NttError, OpValue, SlicesBatch, SubfieldSlice,
-                    eq_ind_partial_eval, to_arr, to_ints)
+                    calculate_round_evals, eq_ind_partial_eval, to_arr, to_ints)
 from .ntt import B200AdditiveNTT, NTTShape  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

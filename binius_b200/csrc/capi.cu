@@ -384,14 +384,14 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
 	SET(k_ntt_bs_pass, 36 * 1024 + 16 + 128 * 1024);
 	SET(k_ntt_bs_low, 184 * 1024 + 640 + 16);
-	SET((nttl::k_ntt_lut<0, false>), nttl::layout(0, 7).total);
-	SET((nttl::k_ntt_lut<0, true>), nttl::layout(0, 7).total);
-	SET((nttl::k_ntt_lut<1, false>), nttl::layout(1, 7).total);
-	SET((nttl::k_ntt_lut<1, true>), nttl::layout(1, 7).total);
-	SET((nttl::k_ntt_lut<2, false>), nttl::layout(2, 7).total);
-	SET((nttl::k_ntt_lut<2, true>), nttl::layout(2, 7).total);
-	SET((nttl::k_ntt_lut<3, false>), nttl::layout(3, 7).total);
-	SET((nttl::k_ntt_lut<3, true>), nttl::layout(3, 7).total);
+	SET((nttl::k_ntt_lut<0, false>), nttl::layout(0, 7, 32).total);
+	SET((nttl::k_ntt_lut<0, true>), nttl::layout(0, 7, 32).total);
+	SET((nttl::k_ntt_lut<1, false>), nttl::layout(1, 7, 32).total);
+	SET((nttl::k_ntt_lut<1, true>), nttl::layout(1, 7, 32).total);
+	SET((nttl::k_ntt_lut<2, false>), nttl::layout(2, 7, 32).total);
+	SET((nttl::k_ntt_lut<2, true>), nttl::layout(2, 7, 32).total);
+	SET((nttl::k_ntt_lut<3, false>), nttl::layout(3, 7, 32).total);
+	SET((nttl::k_ntt_lut<3, true>), nttl::layout(3, 7, 32).total);
 	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
 	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
 #undef SET
@@ -411,6 +411,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	cudaFreeHost(ctx->h_args);
 	cudaFreeHost(ctx->h_results);
 	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+	for (auto &c : ctx->local_pool) cudaFree(c.p);
 	if (ctx->s_h2d) {
 		cudaStreamDestroy(ctx->s_h2d);
 		cudaStreamDestroy(ctx->s_d2h);
@@ -1011,24 +1012,21 @@ int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t
 }
 
 // ---- KernelExecutor ------------------------------------------------------------------------------
-int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *slot) {
-	B200_LOCK(ctx);
-	B200_FLUSH(ctx);
-	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
-	int32_t rc = new_slot(ctx, slot);
-	if (rc) return rc;
+// Outside a kernel scope every op launches at once.  Inside one (b200_kernel_scope_begin .. _end, what the
+// layer's accumulate_kernels / map_kernels wrap around the caller's closure, layer.rs:134-245) the ops are
+// RECORDED and lowered together at scope end: the only closure the reference prover issues
+// (core/src/protocols/sumcheck/v3/bivariate_product.rs:343-405: sums of Var*Var over the high halves, add(lo, hi)
+// into the Local buffers, sums of Var*Var over the Locals) becomes inner-product jobs of the tensor-core kernel
+// with the (lo, hi) pointer pairs as operands -- the Local buffers are never written.
+}  // extern "C"
+static int32_t kernel_decl_now(b200_ctx *ctx, const uint64_t init[2], uint32_t slot) {
 	if (init[0] | init[1]) {
-		k_set_slot<<<1, 1, 0, ctx->stream>>>(ctx->d_results + *slot, to_u4(init));
+		k_set_slot<<<1, 1, 0, ctx->stream>>>(ctx->d_results + slot, to_u4(init));
 		B200_LAUNCH_CHECK(ctx);
 	}
 	return B200_OK;
 }
-int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
-	B200_LOCK(ctx);
-	B200_FLUSH(ctx);
-	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
-	if (slot >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "value slot %u not declared", slot);
-	if (expr->n_vars > n_inputs) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition not match with input");
+static int32_t kernel_sum_now(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
 	if (row_len == 0) return B200_OK;
 	void *dptrs = nullptr;
 	if (n_inputs) {
@@ -1039,14 +1037,199 @@ int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inp
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
 }
-int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr a, b200_dev_ptr b, b200_dev_ptr dst) {
-	B200_LOCK(ctx);
-	B200_FLUSH(ctx);
-	if (!ctx || log_len > 60) return B200_ERR_INPUT_VALIDATION;
+static int32_t kernel_add_now(b200_ctx *ctx, uint32_t log_len, const void *a, const void *b, void *dst) {
 	uint64_t n = 1ull << log_len;
 	k_add<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)dst, n);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
+}
+
+// Lower the recorded ops of a scope.  Fused when every sum is a polynomial of degree <= 2 over rows of one length
+// (>= 4096, a multiple of the tensor-core chunk), every add writes a whole Local exactly once from two non-Local
+// sources before any sum reads it, and sums read only such Locals or buffers the scope never writes.
+static int32_t run_trace(b200_ctx *ctx) {
+	std::vector<b200_trace_op> &ops = ctx->trace;
+	auto local_ix = [&](const void *p) -> int {
+		for (size_t i = 0; i < ctx->locals.size(); i++)
+			if ((const uint8_t *)p >= ctx->locals[i].first && (const uint8_t *)p < ctx->locals[i].first + ctx->locals[i].second) return (int)i;
+		return -1;
+	};
+	bool ok = ctx->tune_round_evals_tc != 0;
+	uint64_t len = 0;
+	std::map<const void *, std::pair<const void *, const void *>> defs;
+	for (size_t i = 0; i < ops.size() && ok; i++) {
+		const b200_trace_op &op = ops[i];
+		if (op.kind == 2) {
+			const int li = local_ix(op.dst);
+			ok = li >= 0 && op.dst == ctx->locals[li].first && (16ull << op.log_len) == ctx->locals[li].second && local_ix(op.a) < 0 && local_ix(op.b) < 0 && !defs.count(op.dst);
+			if (ok) defs[op.dst] = {op.a, op.b};
+		} else if (op.kind == 1) {
+			ok = op.expr->poly_ok && (len == 0 || len == op.row_len);
+			len = op.row_len;
+			for (auto &t : op.expr->poly)
+				for (uint32_t v : t.first) {
+					const void *p = op.inputs[v];
+					if (local_ix(p) >= 0 && !(defs.count(p) && (16ull * op.row_len) == ctx->locals[local_ix(p)].second)) ok = false;
+				}
+		}
+	}
+	ok = ok && len >= 4096 && len % tc::CHUNK == 0;
+	if (!ok) {
+		// in order, as recorded; Locals are zero-initialised (layer.rs:617-644)
+		for (auto &l : ctx->locals) B200_CUDA(ctx, cudaMemsetAsync(l.first, 0, l.second, ctx->stream));
+		for (const b200_trace_op &op : ops) {
+			int32_t rc = op.kind == 0   ? kernel_decl_now(ctx, op.init, op.slot)
+						 : op.kind == 1 ? kernel_sum_now(ctx, (const b200_dev_ptr *)op.inputs.data(), (uint32_t)op.inputs.size(), op.row_len, op.expr, op.coeff, op.slot)
+										: kernel_add_now(ctx, op.log_len, op.a, op.b, op.dst);
+			if (rc) return rc;
+		}
+		return B200_OK;
+	}
+	std::vector<tc::TcJob> jobs;
+	std::vector<tc::TcTarget> targets;
+	std::map<std::tuple<const void *, const void *, const void *, const void *>, uint32_t> job_ix;
+	bool need_ones = false;
+	for (const b200_trace_op &op : ops)
+		if (op.kind == 1)
+			for (auto &t : op.expr->poly) need_ones = need_ones || t.first.size() == 1;
+	const uint64_t off_g = need_ones ? len * 16 : 0;
+	{
+		size_t n_jobs = 1;
+		for (const b200_trace_op &op : ops)
+			if (op.kind == 1) n_jobs += op.expr->poly.size();
+		int32_t rc = ensure_scratch(ctx, off_g + (uint64_t)(n_jobs + 1) * 512 * 4);
+		if (rc) return rc;
+	}
+	const uint4 *ones = (const uint4 *)ctx->d_scratch;
+	if (need_ones) {
+		k_fill<<<grid_for(ctx, len, 256, 8), 256, 0, ctx->stream>>>((uint4 *)ctx->d_scratch, len, make_uint4(1, 0, 0, 0));
+		B200_LAUNCH_CHECK(ctx);
+	}
+	for (const b200_trace_op &op : ops) {
+		if (op.kind == 0) {
+			int32_t rc = kernel_decl_now(ctx, op.init, op.slot);
+			if (rc) return rc;
+		}
+		if (op.kind != 1) continue;
+		const hostf::u128 cf = hostf::from_words(op.coeff);
+		for (auto &t : op.expr->poly) {
+			if (t.first.empty()) continue;  // a constant summed over an even number of points vanishes
+			const void *o[4] = {nullptr, nullptr, need_ones ? (const void *)ones : nullptr, nullptr};
+			for (size_t f = 0; f < t.first.size(); f++) {
+				const void *p = op.inputs[t.first[f]];
+				auto d = defs.find(p);
+				o[2 * f] = d == defs.end() ? p : d->second.first;
+				o[2 * f + 1] = d == defs.end() ? nullptr : d->second.second;
+			}
+			auto key = std::make_tuple(o[0], o[1], o[2], o[3]);
+			auto it = job_ix.find(key);
+			if (it == job_ix.end()) {
+				it = job_ix.emplace(key, (uint32_t)jobs.size()).first;
+				jobs.push_back(tc::TcJob{(const uint4 *)o[0], (const uint4 *)o[1], (const uint4 *)o[2], (const uint4 *)o[3]});
+			}
+			const hostf::u128 wgt = hostf::mul128(cf, t.second);
+			uint64_t w[2] = {(uint64_t)wgt, (uint64_t)(wgt >> 64)};
+			if (wgt) targets.push_back(tc::TcTarget{it->second, op.slot, to_u4(w)});
+		}
+	}
+	return launch_tc_pairs(ctx, jobs, len, targets, off_g);
+}
+extern "C" {
+
+int32_t b200_kernel_scope_begin(b200_ctx *ctx) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (ctx->tracing) return fail(ctx, B200_ERR_INPUT_VALIDATION, "kernel scopes do not nest");
+	ctx->mu.lock();  // held until b200_kernel_scope_end: the scope belongs to the calling thread
+	ctx->tracing = true;
+	ctx->trace.clear();
+	ctx->locals.clear();
+	for (auto &c : ctx->local_pool) c.used = 0;
+	return B200_OK;
+}
+int32_t b200_kernel_local(b200_ctx *ctx, uint32_t log_size, b200_dev_ptr *out) {
+	B200_LOCK(ctx);
+	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
+	if (!ctx->tracing) return fail(ctx, B200_ERR_INPUT_VALIDATION, "b200_kernel_local outside a kernel scope");
+	if (log_size > 40) return fail(ctx, B200_ERR_INPUT_VALIDATION, "Local buffer too large");
+	const uint64_t bytes = std::max<uint64_t>(16ull << log_size, 256);
+	for (auto &c : ctx->local_pool)
+		if (c.bytes - c.used >= bytes) {
+			*out = c.p + c.used;
+			ctx->locals.push_back({c.p + c.used, 16ull << log_size});
+			c.used += bytes;
+			return B200_OK;
+		}
+	// chunks are never moved or freed before the context dies: pointers handed out earlier stay valid
+	const uint64_t want = std::max<uint64_t>(bytes, 64ull << 20);
+	void *p = nullptr;
+	if (cudaMalloc(&p, want) != cudaSuccess) {
+		cudaGetLastError();
+		if (want == bytes || cudaMalloc(&p, bytes) != cudaSuccess) {
+			cudaGetLastError();
+			return fail(ctx, B200_ERR_ALLOC, "out of device memory (kernel-local scratch of %llu bytes)", (unsigned long long)bytes);
+		}
+		ctx->local_pool.push_back(b200_local_chunk{(uint8_t *)p, bytes, bytes});
+	} else {
+		ctx->local_pool.push_back(b200_local_chunk{(uint8_t *)p, want, bytes});
+	}
+	*out = p;
+	ctx->locals.push_back({(uint8_t *)p, 16ull << log_size});
+	return B200_OK;
+}
+int32_t b200_kernel_scope_end(b200_ctx *ctx) {
+	B200_LOCK(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (!ctx->tracing) return fail(ctx, B200_ERR_INPUT_VALIDATION, "b200_kernel_scope_end without a scope");
+	const int32_t rc = run_trace(ctx);
+	ctx->tracing = false;
+	ctx->trace.clear();
+	ctx->mu.unlock();
+	return rc;
+}
+
+int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *slot) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
+	int32_t rc = new_slot(ctx, slot);
+	if (rc) return rc;
+	if (ctx->tracing) {
+		b200_trace_op op;
+		op.kind = 0, op.slot = *slot, op.init[0] = init[0], op.init[1] = init[1];
+		ctx->trace.push_back(op);
+		return B200_OK;
+	}
+	return kernel_decl_now(ctx, init, *slot);
+}
+int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
+	if (slot >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "value slot %u not declared", slot);
+	if (expr->n_vars > n_inputs) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition not match with input");
+	if (ctx->tracing) {
+		if (row_len == 0) return B200_OK;
+		b200_trace_op op;
+		op.kind = 1, op.slot = slot, op.row_len = row_len, op.expr = expr, op.coeff[0] = coeff[0], op.coeff[1] = coeff[1];
+		op.inputs.assign(inputs, inputs + n_inputs);
+		ctx->trace.push_back(std::move(op));
+		return B200_OK;
+	}
+	return kernel_sum_now(ctx, inputs, n_inputs, row_len, expr, coeff, slot);
+}
+int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr a, b200_dev_ptr b, b200_dev_ptr dst) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || log_len > 60) return B200_ERR_INPUT_VALIDATION;
+	if (ctx->tracing) {
+		b200_trace_op op;
+		op.kind = 2, op.log_len = log_len, op.a = a, op.b = b, op.dst = dst;
+		ctx->trace.push_back(op);
+		return B200_OK;
+	}
+	return kernel_add_now(ctx, log_len, a, b, dst);
 }
 int32_t b200_kernel_add_assign(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr src, b200_dev_ptr dst) {
 	return b200_kernel_add(ctx, log_len, dst, src, dst);
@@ -1360,11 +1543,12 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			L.d = ntt->d;
 			L.log_cc = P.log_c;
 			L.n_z = n_z;
+			L.nbits = std::min(32u, log_y - 1 - P.i_lo + coset_bits);
 			L.coset = coset;
 			const uint32_t R1 = P.R - 3;
 			const uint64_t items = (uint64_t)n_z << (log_y - P.i_lo - P.R + lx + P.i_lo - P.log_c);
 			const uint32_t grid = (uint32_t)std::min<uint64_t>(items, 2ull * ctx->n_sms);
-			const uint32_t smem = nttl::layout((int)R1, P.log_c).total;
+			const uint32_t smem = nttl::layout((int)R1, P.log_c, L.nbits).total;
 #define B200_NTT_LUT(R1V)                                                                       \
 	case R1V:                                                                                   \
 		if (inverse) nttl::k_ntt_lut<R1V, true><<<grid, nttl::THREADS, smem, ctx->stream>>>(L); \

@@ -167,6 +167,30 @@ class B200Backend:
         self._l = layer
         self._exprs = {}
         self._unit = None
+        self._ones2 = None
+        # out-of-place results of the LowToHigh paths (fold_right_lerp, eq-ind halving) come from this pool and the
+        # buffer they replace goes back to it: two buffers per multilinear ping-pong instead of one allocation per
+        # round (buffers the caller handed in are never recycled: only pointers taken from the pool are given back)
+        self._mine = {}
+        self._free = []
+
+    def _take(self, n: int) -> DevSlice:
+        n = max(n, 1)
+        best = None
+        for i, (_, cap) in enumerate(self._free):
+            if cap >= n and (best is None or cap < self._free[best][1]):
+                best = i
+        if best is not None:
+            ptr, cap = self._free.pop(best)
+        else:
+            ptr, cap = self._l.dev_alloc(n).ptr, n
+        self._mine[ptr] = cap
+        return DevSlice(ptr, n)
+
+    def _give(self, s: DevSlice):
+        cap = self._mine.pop(s.ptr, None)
+        if cap is not None:  # one in-order stream: a later kernel that reuses the buffer runs after its last reader
+            self._free.append((s.ptr, cap))
 
     def _compiled(self, circuit: ArithCircuit) -> ExprEval:
         hit = getattr(circuit, "_b200_compiled", None)
@@ -303,10 +327,11 @@ class B200Backend:
             for ml, n in zip(mls, new_lens):
                 ml.evals = ml.evals.slice(0, int(n))
         else:
-            outs = [L.dev_alloc(max((int(p) + 1) // 2, 1)) for p in prefix]
+            outs = [self._take((int(p) + 1) // 2) for p in prefix]
             optrs = (C.c_void_p * m)(*[o.ptr for o in outs])
             L._check(L._lib.b200_fold_multilinears_low_to_high(L._ctx, ptrs, optrs, m, n_vars, prefix, sfx, _u64x2(challenge), new_lens))
             for ml, o, n in zip(mls, outs, new_lens):
+                self._give(ml.evals)
                 ml.evals = o.slice(0, int(n))
         return any_transparent_left
 
@@ -316,10 +341,12 @@ class B200Backend:
             return eq_ind
         if evaluation_order == EvaluationOrder.LowToHigh:
             # E'[i] = E[2i] + E[2i+1] (common.rs:50-58) = fold_right of E by the all-ones pair
-            ones = self._l.dev_alloc(2)
-            self._l.fill(ones, 1)
-            out = self._l.dev_alloc(1 << (n_vars - 1))
-            self._l._check(self._l._lib.b200_fold_right(self._l._ctx, eq_ind.ptr, eq_ind.len(), 7, ones.ptr, 2, out.ptr, out.len()))
+            if self._ones2 is None:
+                self._ones2 = self._l.dev_alloc(2)
+                self._l.fill(self._ones2, 1)
+            out = self._take(1 << (n_vars - 1))
+            self._l._check(self._l._lib.b200_fold_right(self._l._ctx, eq_ind.ptr, eq_ind.len(), 7, self._ones2.ptr, 2, out.ptr, out.len()))
+            self._give(eq_ind)
             return out
         lo, hi = eq_ind.split_half()
         self._l._check(self._l._lib.b200_kernel_add(self._l._ctx, n_vars - 1, lo.ptr, hi.ptr, lo.ptr))

@@ -52,7 +52,36 @@ struct SumcheckEvaluator {
 
 class B200Backend {
 	B200Layer &l_;
-	DevSlice unit_{};
+	DevSlice unit_{}, ones2_{};
+	// Out-of-place results of the LowToHigh paths (fold_right_lerp, eq-ind halving) come from this pool and the
+	// buffer they replace goes back to it, so two buffers per multilinear ping-pong instead of one allocation
+	// (= one device synchronisation) per round.  Buffers the caller handed in are never recycled; the pool is
+	// released with the backend.
+	std::map<uint8_t *, uint64_t> mine_;
+	std::vector<std::pair<uint8_t *, uint64_t>> free_, all_;
+	DevSlice take(uint64_t n) {
+		n = std::max<uint64_t>(n, 1);
+		size_t best = free_.size();
+		for (size_t i = 0; i < free_.size(); i++)
+			if (free_[i].second >= n && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+		uint8_t *p;
+		uint64_t cap;
+		if (best != free_.size()) {
+			p = free_[best].first, cap = free_[best].second;
+			free_.erase(free_.begin() + best);
+		} else {
+			p = l_.dev_alloc(n).ptr, cap = n;
+			all_.push_back({p, cap});
+		}
+		mine_[p] = cap;
+		return DevSlice{p, n};
+	}
+	void give(DevSlice s) {
+		auto it = mine_.find(s.ptr);
+		if (it == mine_.end()) return;
+		free_.push_back({it->first, it->second});  // one in-order stream: a later writer runs after the last reader
+		mine_.erase(it);
+	}
 
 	DevSlice one() {
 		if (!unit_.n) {
@@ -73,6 +102,10 @@ class B200Backend {
 
   public:
 	explicit B200Backend(B200Layer &l) : l_(l) {}
+	~B200Backend() {
+		for (auto &b : all_) b200_dev_free(l_.ctx(), b.first);
+	}
+	B200Backend(const B200Backend &) = delete;
 
 	DevSlice tensor_product_full_query(const std::vector<F128> &query) {
 		DevSlice out = l_.dev_alloc(1ull << query.size());
@@ -167,11 +200,14 @@ class B200Backend {
 			for (size_t t = 0; t < folded.size(); t++) folded[t]->evals = folded[t]->evals.slice(0, new_lens[t]);
 		} else {
 			for (auto p : prefix) {
-				out_slices.push_back(l_.dev_alloc(std::max<uint64_t>((p + 1) / 2, 1)));
+				out_slices.push_back(take((p + 1) / 2));
 				outs.push_back(out_slices.back().ptr);
 			}
 			l_.check(b200_fold_multilinears_low_to_high(l_.ctx(), ptrs.data(), outs.data(), (uint32_t)ptrs.size(), n_vars, prefix.data(), (const uint64_t *)sfx.data(), z, new_lens.data()));
-			for (size_t t = 0; t < folded.size(); t++) folded[t]->evals = out_slices[t].slice(0, new_lens[t]);
+			for (size_t t = 0; t < folded.size(); t++) {
+				give(folded[t]->evals);
+				folded[t]->evals = out_slices[t].slice(0, new_lens[t]);
+			}
 		}
 		return any_transparent_left;
 	}
@@ -186,9 +222,13 @@ class B200Backend {
 	DevSlice fold_partial_eq_ind(EvaluationOrder order, uint32_t n_vars, DevSlice eq_ind) {
 		if (n_vars == 0) return eq_ind;
 		if (order == EvaluationOrder::LowToHigh) {
-			DevSlice ones = l_.dev_alloc(2), out = l_.dev_alloc(1ull << (n_vars - 1));
-			l_.fill(ones, F128{1, 0});
-			l_.check(b200_fold_right(l_.ctx(), eq_ind.ptr, eq_ind.n, 7, ones.ptr, 2, out.ptr, out.n));
+			if (!ones2_.n) {
+				ones2_ = l_.dev_alloc(2);
+				l_.fill(ones2_, F128{1, 0});
+			}
+			DevSlice out = take(1ull << (n_vars - 1));
+			l_.check(b200_fold_right(l_.ctx(), eq_ind.ptr, eq_ind.n, 7, ones2_.ptr, 2, out.ptr, out.n));
+			give(eq_ind);
 			return out;
 		}
 		auto halves = eq_ind.split_half();

@@ -242,19 +242,29 @@ inline void B200KernelExec::add_assign(uint32_t log_len, DevSlice s, DevSlice d)
 
 inline std::vector<OpValue> B200Exec::accumulate_kernels(const KernelFn &map, const std::vector<KernelMemMap> &mem_maps) {
 	if (mem_maps.empty()) throw InputValidation(1, "Many variant must have at least one entry");
-	std::vector<KernelBuffer> bufs;
-	for (auto &m : mem_maps) {
-		if (m.kind == KernelMemMap::Local) {
-			DevSlice s = l_.dev_alloc(1ull << m.log_size);
-			l_.scratch_.push_back(s);
-			l_.fill(s, F128{});
-			bufs.push_back({s, true});
-		} else {
-			bufs.push_back({m.data, m.kind == KernelMemMap::ChunkedMut});
+	// a kernel scope: the ops the closure issues are recorded by the library and lowered together at scope end
+	// (the bivariate round-evaluation closure becomes tensor-core inner-product jobs; Locals are never written)
+	l_.check(b200_kernel_scope_begin(l_.ctx_));
+	std::vector<OpValue> out;
+	try {
+		std::vector<KernelBuffer> bufs;
+		for (auto &m : mem_maps) {
+			if (m.kind == KernelMemMap::Local) {
+				void *p;
+				l_.check(b200_kernel_local(l_.ctx_, m.log_size, &p));
+				bufs.push_back({DevSlice{(uint8_t *)p, 1ull << m.log_size}, true});
+			} else {
+				bufs.push_back({m.data, m.kind == KernelMemMap::ChunkedMut});
+			}
 		}
+		B200KernelExec kex(l_);
+		out = map(kex, 0, bufs);  // the layer always selects log_chunks = 0 (layer.rs:149-160 allows any value in range)
+	} catch (...) {
+		b200_kernel_scope_end(l_.ctx_);
+		throw;
 	}
-	B200KernelExec kex(l_);
-	return map(kex, 0, bufs);  // the layer always selects log_chunks = 0 (layer.rs:149-160 allows any value in range)
+	l_.check(b200_kernel_scope_end(l_.ctx_));
+	return out;
 }
 inline OpValue B200Exec::inner_product(SubfieldSlice a, DevSlice b) {
 	OpValue v;

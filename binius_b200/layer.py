@@ -462,22 +462,33 @@ class B200Executor:
         bufs = []
         for m in mem_maps:
             if m.kind == "local":
-                s = self._l._scratch_alloc(1 << m.log_size)
-                self._lib.b200_fill(self._ctx, s.ptr, s.len(), _u64x2(0))
-                bufs.append(KernelBuffer(s, True))
+                # KernelMemMap::Local: library-owned scratch of the open scope (never written when the scope fuses)
+                p = C.c_void_p()
+                self._l._check(self._lib.b200_kernel_local(self._ctx, m.log_size, C.byref(p)))
+                bufs.append(KernelBuffer(DevSlice(p.value, 1 << m.log_size), True))
             else:
                 bufs.append(KernelBuffer(m.data, m.kind == "chunked_mut"))
         return bufs
 
+    def _kernel_scope(self, map_fn, mem_maps):
+        self._l._check(self._lib.b200_kernel_scope_begin(self._ctx))
+        try:
+            bufs = self._map_kernel_mem(mem_maps)
+            out = map_fn(B200KernelExecutor(self._l), 0, bufs)
+        except BaseException:
+            self._lib.b200_kernel_scope_end(self._ctx)  # release the scope; the original error wins
+            raise
+        self._l._check(self._lib.b200_kernel_scope_end(self._ctx))
+        return out
+
     def accumulate_kernels(self, map_fn: Callable, mem_maps: List[KernelMemMap]) -> List[OpValue]:
-        """layer.rs:134-192; closure signature map_fn(kernel_exec, log_chunks, buffers) -> [Value]."""
-        bufs = self._map_kernel_mem(mem_maps)
-        return list(map_fn(B200KernelExecutor(self._l), 0, bufs))
+        """layer.rs:134-192; closure signature map_fn(kernel_exec, log_chunks, buffers) -> [Value].  The ops the
+        closure issues are recorded by the library and lowered together when the scope ends."""
+        return list(self._kernel_scope(map_fn, mem_maps))
 
     def map_kernels(self, map_fn: Callable, mem_maps: List[KernelMemMap]):
         """layer.rs:194-245"""
-        bufs = self._map_kernel_mem(mem_maps)
-        map_fn(B200KernelExecutor(self._l), 0, bufs)
+        self._kernel_scope(map_fn, mem_maps)
 
     # -- ops
     def inner_product(self, a_in: SubfieldSlice, b_in: DevSlice) -> OpValue:
@@ -684,6 +695,42 @@ class B200LayerHolder:
 
     def to_data(self) -> ComputeData:
         return ComputeData(self.layer, HostBumpAllocator(self.host_mem), BumpAllocator(self.dev_mem))
+
+
+def calculate_round_evals(hal: B200Layer, n_vars: int, batch_coeff: int, multilins: Sequence[DevSlice], compositions) -> List[int]:
+    """v3::calculate_round_evals (core/src/protocols/sumcheck/v3/bivariate_product.rs:303-408), literally: the
+    accumulate_kernels program the reference prover issues -- per composition (an index pair = IndexComposition<
+    BivariateProduct>, expression Var(i0) * Var(i1) over ALL multilinears) a sum over the high halves, add(lo, hi) into
+    the Local buffers, the same sums over the Locals.  Returns [y_1, y_inf]."""
+    m = len(multilins)
+    evaluators = [hal.compile_expr(ArithCircuit.var(i0) * ArithCircuit.var(i1)) for (i0, i1) in compositions]
+    split_n_vars = n_vars - 1
+    mappings = []
+    for ml in multilins:
+        lo, hi = ml.split_half()
+        mappings += [KernelMemMap.Chunked(lo, 0), KernelMemMap.Chunked(hi, 0), KernelMemMap.Local(split_n_vars)]
+    coeffs, pw = [], 1
+    from .hostfield import mul as _fmul  # batch-coefficient powers (host scalar work)
+
+    for _ in compositions:
+        coeffs.append(pw)
+        pw = _fmul(pw, batch_coeff)
+
+    def kernel(kex, log_chunks, buffers):
+        log_chunk_size = split_n_vars - log_chunks
+        acc_1 = kex.decl_value(0)
+        eval_1s = SlicesBatch([buffers[3 * i + 1].to_ref() for i in range(m)], 1 << log_chunk_size)
+        for c, ev in zip(coeffs, evaluators):
+            kex.sum_composition_evals(eval_1s, ev, c, acc_1)
+        for i in range(m):
+            kex.add(log_chunk_size, buffers[3 * i].to_ref(), buffers[3 * i + 1].to_ref(), buffers[3 * i + 2].data)
+        acc_inf = kex.decl_value(0)
+        eval_infs = SlicesBatch([buffers[3 * i + 2].to_ref() for i in range(m)], 1 << log_chunk_size)
+        for c, ev in zip(coeffs, evaluators):
+            kex.sum_composition_evals(eval_infs, ev, c, acc_inf)
+        return [acc_1, acc_inf]
+
+    return hal.execute(lambda ex: ex.accumulate_kernels(kernel, mappings))
 
 
 def eq_ind_partial_eval(hal: B200Layer, dev_alloc: BumpAllocator, point: Sequence[int]) -> DevSlice:

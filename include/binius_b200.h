@@ -21,7 +21,13 @@
  *   - All work of one context is issued on one CUDA stream in call order, so the store-to-load
  *     ordering contract of ComputeLayerExecutor (layer.rs:90-99) holds.  Calls are asynchronous
  *     unless stated; scalar results are deferred "OpValue" slots read back by b200_results_fetch.
- *   - A context is not thread-safe; use one context per host thread (or serialise externally).
+ *     Two kinds of call are DEFERRED inside the library (layer.rs:90-99 allows it): consecutive
+ *     b200_extrapolate_line calls with one challenge are queued and launched together by the next call of
+ *     any other entry point (b200_ctx_stream, b200_event_record and b200_flush included), and the ops
+ *     of an open kernel scope are lowered at b200_kernel_scope_end.
+ *   - A context may be shared by several host threads (the trait methods take `&self` and `join`/`map`
+ *     closures run on rayon threads, layer.rs:115-131): every entry point takes the context's lock and
+ *     makes its device current for the call; a kernel scope holds the lock from begin to end.
  *   - There is no CPU fallback: every entry point fails with B200_ERR_DEVICE when no sm_100 device
  *     is usable.
  */
@@ -56,8 +62,11 @@ enum {
 int32_t b200_ctx_create(int32_t device, b200_ctx **out);
 void b200_ctx_destroy(b200_ctx *ctx);
 const char *b200_last_error(b200_ctx *ctx);
-/* the CUDA stream of the context (cudaStream_t as void*) so callers can record events on it */
+/* the CUDA stream of the context (cudaStream_t as void*) so callers can record events on it; launches
+ * every queued fold first, so work the caller enqueues on the stream afterwards is ordered behind it */
 void *b200_ctx_stream(b200_ctx *ctx);
+/* launch everything the library has deferred (queued folds); asynchronous */
+int32_t b200_flush(b200_ctx *ctx);
 /* adopt an external stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own one */
 int32_t b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
 /* Kernel-selection switches for A/B measurements and tests (never needed for correctness; the defaults are
@@ -93,7 +102,9 @@ int32_t b200_results_reset(b200_ctx *ctx);
 int32_t b200_results_fetch(b200_ctx *ctx, const uint32_t *slots, uint32_t n, uint64_t *host_out /* 2*n */);
 
 /* ---- ComputeLayerExecutor ops ------------------------------------------------------------------ */
-/* extrapolate_line (layer.rs:402-426; cpu/layer.rs:393-408): e0[i] += (e1[i]-e0[i])*z */
+/* extrapolate_line (layer.rs:402-426; cpu/layer.rs:393-408): e0[i] += (e1[i]-e0[i])*z.
+ * Deferred: the call only queues the fold; folds with the same z on disjoint slices go out as ONE
+ * multi-segment launch when any other entry point (or a conflicting fold) arrives -- see b200_flush. */
 int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr evals_0, uint64_t n0, b200_dev_ptr evals_1,
 							  uint64_t n1, const uint64_t z[2]);
 /* The same fold on HOST buffers (a ComputationBackend whose Vec<P> is host-dereferenceable,
@@ -133,7 +144,19 @@ int32_t b200_pairwise_product_reduce(b200_ctx *ctx, b200_dev_ptr input, uint64_t
 									 const b200_dev_ptr *round_outputs, const uint64_t *round_output_lens,
 									 uint32_t n_rounds);
 
-/* ---- KernelExecutor ops (layer.rs:518-590), issued with log_chunks = 0 (whole buffers) --------- */
+/* ---- accumulate_kernels / map_kernels (layer.rs:134-245) and KernelExecutor ops (layer.rs:518-590) ------
+ * The layer's accumulate_kernels(map, mem_maps) = b200_kernel_scope_begin; one b200_kernel_local per
+ * KernelMemMap::Local (layer.rs:617-644; zero-initialised scratch that lives until the scope ends); the
+ * caller's closure with log_chunks = 0 (whole buffers) issuing the four ops below; b200_kernel_scope_end.
+ * Inside a scope the ops are recorded and lowered together ("free to call the specification closure",
+ * layer.rs:176-177; a Value "is a promise", layer.rs:522): sums of degree <= 2 expressions over inputs that
+ * are mapped buffers or Locals written by one add(src1, src2) become tensor-core inner-product jobs on the
+ * (src1, src2) pointer pairs and the Locals are never materialised -- the round evaluation of
+ * core/src/protocols/sumcheck/v3/bivariate_product.rs:343-405; anything else runs op by op as recorded.
+ * Outside a scope each op launches at once. */
+int32_t b200_kernel_scope_begin(b200_ctx *ctx);
+int32_t b200_kernel_local(b200_ctx *ctx, uint32_t log_size, b200_dev_ptr *out);
+int32_t b200_kernel_scope_end(b200_ctx *ctx);
 /* decl_value */
 int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *value_slot);
 /* sum_composition_evals: slot += batch_coeff * sum_i expr(inputs[.][i]) */

@@ -65,7 +65,7 @@ def test_cfg3_u32_add_zerocheck_n18_every_round(hal, oracle):
 def test_bivariate_round_evals_m8_n20(hal, oracle):
     """v3::calculate_round_evals (bivariate_product.rs:303-408) at the size bench.py times: the fused entry point
     and the traced accumulate_kernels route must both equal the oracle."""
-    from binius_b200.layer import bivariate_round_evals_traced
+    from binius_b200.layer import calculate_round_evals
 
     n_vars, m = 20, 8
     rng = random.Random(2008)
@@ -77,7 +77,7 @@ def test_bivariate_round_evals_m8_n20(hal, oracle):
     got = hal.execute(lambda ex: list(ex.bivariate_round_evals(mls, n_vars, pairs, coeff)))
     assert got == exp
     before = hal.launch_count()
-    traced = bivariate_round_evals_traced(hal, mls, n_vars, pairs, coeff)
+    traced = calculate_round_evals(hal, n_vars, coeff, mls, pairs)
     assert traced == exp
     # the traced route must reach the tensor-core kernel: k_pair_tc + combine (+ the gmat memset is not a kernel)
     assert hal.launch_count() - before <= 3
