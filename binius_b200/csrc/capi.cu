@@ -384,14 +384,18 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_ntt_pass<uint8_t>, FIELD_TABLE_BYTES + 4 * 8192 + 1 * 8192);
 	SET(k_ntt_bs_pass, 36 * 1024 + 16 + 128 * 1024);
 	SET(k_ntt_bs_low, 184 * 1024 + 640 + 16);
-	SET((nttl::k_ntt_lut<0, false>), nttl::layout(0, 7, 32).total);
-	SET((nttl::k_ntt_lut<0, true>), nttl::layout(0, 7, 32).total);
-	SET((nttl::k_ntt_lut<1, false>), nttl::layout(1, 7, 32).total);
-	SET((nttl::k_ntt_lut<1, true>), nttl::layout(1, 7, 32).total);
-	SET((nttl::k_ntt_lut<2, false>), nttl::layout(2, 7, 32).total);
-	SET((nttl::k_ntt_lut<2, true>), nttl::layout(2, 7, 32).total);
-	SET((nttl::k_ntt_lut<3, false>), nttl::layout(3, 7, 32).total);
-	SET((nttl::k_ntt_lut<3, true>), nttl::layout(3, 7, 32).total);
+	SET((nttl::k_ntt_lut<0, false, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<0, true, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<1, false, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<1, true, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<2, false, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<2, false, true>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<2, true, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<2, true, true>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<3, false, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<3, false, true>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<3, true, false>), 227u * 1024u);
+	SET((nttl::k_ntt_lut<3, true, true>), 227u * 1024u);
 	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
 	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
 #undef SET
@@ -454,6 +458,8 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	if (!ctx || !key) return B200_ERR_INPUT_VALIDATION;
 	if (!strcmp(key, "ntt")) ctx->tune_ntt = value;
 	else if (!strcmp(key, "ntt_log_cc")) ctx->tune_ntt_log_cc = (uint32_t)std::min(7, std::max(5, value));
+	else if (!strcmp(key, "ntt_cw")) ctx->tune_ntt_cw = value;
+	else if (!strcmp(key, "ntt_byte")) ctx->tune_ntt_byte = value;
 	else if (!strcmp(key, "fold")) ctx->tune_fold = value;
 	else if (!strcmp(key, "round_evals_tc")) ctx->tune_round_evals_tc = value;
 	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
@@ -1547,19 +1553,33 @@ static int32_t ntt_run(b200_ctx *ctx, const b200_ntt *ntt, int inverse, b200_dev
 			L.coset = coset;
 			const uint32_t R1 = P.R - 3;
 			const uint64_t items = (uint64_t)n_z << (log_y - P.i_lo - P.R + lx + P.i_lo - P.log_c);
-			const uint32_t grid = (uint32_t)std::min<uint64_t>(items, 2ull * ctx->n_sms);
-			const uint32_t smem = nttl::layout((int)R1, P.log_c, L.nbits).total;
-#define B200_NTT_LUT(R1V)                                                                       \
-	case R1V:                                                                                   \
-		if (inverse) nttl::k_ntt_lut<R1V, true><<<grid, nttl::THREADS, smem, ctx->stream>>>(L); \
-		else nttl::k_ntt_lut<R1V, false><<<grid, nttl::THREADS, smem, ctx->stream>>>(L);        \
+			// tables that live for many tiles: one CTA per SM, 16 compute warps, a deep tile ring; tables rebuilt
+			// for every tile (a CTA-wide rendezvous): two CTAs of 8 compute warps per SM
+			const bool per_tile_tables = lx + P.i_lo == P.log_c;
+			L.cw = per_tile_tables || ctx->tune_ntt_cw == 8 ? 8 : nttl::MAX_CW;
+			// byte tables (64 KiB more) for the two widest-shared layers when the tables live for many tiles
+			const bool byte_tabs = !per_tile_tables && L.cw == nttl::MAX_CW && R1 >= 2 && ctx->tune_ntt_byte;
+			L.nbuf = nttl::MAX_NBUF;
+			const uint32_t budget = L.cw == 8 ? 112u * 1024u : 226u * 1024u;
+			while (L.nbuf > 2 && nttl::layout((int)R1, P.log_c, L.nbits, L.nbuf, byte_tabs).total > budget) L.nbuf--;
+			const uint32_t grid = (uint32_t)std::min<uint64_t>(items, (L.cw == 8 ? 2ull : 1ull) * ctx->n_sms);
+			const uint32_t smem = nttl::layout((int)R1, P.log_c, L.nbits, L.nbuf, byte_tabs).total;
+			const uint32_t threads = 32u * (L.cw + 2);
+#define B200_NTT_LUT(R1V, BYTE)                                                                         \
+	case R1V:                                                                                           \
+		if (inverse) nttl::k_ntt_lut<R1V, true, BYTE><<<grid, threads, smem, ctx->stream>>>(L);         \
+		else nttl::k_ntt_lut<R1V, false, BYTE><<<grid, threads, smem, ctx->stream>>>(L);                \
 		break;
-			switch (R1) {
-				B200_NTT_LUT(0)
-				B200_NTT_LUT(1)
-				B200_NTT_LUT(2)
-				B200_NTT_LUT(3)
-			}
+			if (byte_tabs) switch (R1) {
+					B200_NTT_LUT(2, true)
+					B200_NTT_LUT(3, true)
+				}
+			else switch (R1) {
+					B200_NTT_LUT(0, false)
+					B200_NTT_LUT(1, false)
+					B200_NTT_LUT(2, false)
+					B200_NTT_LUT(3, false)
+				}
 #undef B200_NTT_LUT
 			B200_LAUNCH_CHECK(ctx);
 			continue;

@@ -77,6 +77,8 @@ struct b200_ctx {
 	// kernel-selection switches for A/B measurements (b200_ctx_set_tuning); defaults = production paths
 	int tune_ntt = 0;              // 0 look-up-table + bit-sliced low layers, 1 bit-sliced only, 2 scalar tables
 	uint32_t tune_ntt_log_cc = 7;  // columns per work item of a look-up-table pass
+	int tune_ntt_byte = 1;         // byte tables for the widest-shared layers of a look-up-table pass
+	int tune_ntt_cw = 16;          // compute warps per CTA of a look-up-table pass (8: two CTAs per SM everywhere)
 	int tune_fold = 2;             // 2 TMA-staged K64, 1 K64, 0 LUT128
 	int tune_round_evals_tc = 1;   // 1 tensor-core plans, 0 per-lane kernels, 2 materialised values only
 	int tune_uni_generic = 0;      // 1 forces the generic univariate-skip kernel

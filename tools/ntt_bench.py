@@ -38,12 +38,13 @@ ntt = binius_b200.B200AdditiveNTT(hal, 5, 26)
 dev = hal.dev_alloc(1 << (28 if big else 22))
 for mode in modes:
     hal.set_tuning("ntt", mode)
-    for cc in ((5, 6, 7) if mode == 0 and "--cc" in sys.argv else (6,)):
+    for cc, cw in ([(c, w) for c in (6, 7) for w in (8, 16)] if mode == 0 and "--cc" in sys.argv else [(7, 16)]):
         hal.set_tuning("ntt_log_cc", cc)
+        hal.set_tuning("ntt_cw", cw)
         for name, (ln, lx, ly, lz, skip) in shapes.items():
             l0 = hal.launch_count()
             f = timed(lambda: ntt.forward_device(dev.ptr, 5, 1 << ln, NTTShape(lx, ly, lz), 0, 0, skip))
             launches = (hal.launch_count() - l0) // 13
             i = timed(lambda: ntt.inverse_device(dev.ptr, 5, 1 << ln, NTTShape(lx, ly, lz), 0, 0, skip))
-            out[f"mode{mode}_cc{cc}_{name}"] = {"fwd_ms": round(f, 4), "inv_ms": round(i, 4), "passes": launches}
+            out[f"mode{mode}_cc{cc}_cw{cw}_{name}"] = {"fwd_ms": round(f, 4), "inv_ms": round(i, 4), "passes": launches}
 print(json.dumps(out, indent=1))
