@@ -4,12 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-coeffs 24]
 
 A "step" = one fold-high (sumcheck fold / extrapolate_line) over one multilinear
-of 2^24 GF(2^128) input coefficients per GPU (256 MiB read, 128 MiB written: larger than the 126 MB
-L2, so no flush is needed between steps).  `value` = coefficients/s over all ranks with inputs resident
-in HBM; `e2e` = the same metric through the plugin API with HOST buffers (copy_h2d + fold + copy_d2h
-inside the timed region).  The additive-NTT numbers (BASELINE config #2) ride along under "ntt".
+of 2^24 GF(2^128) input coefficients per GPU (256 MiB read, 128 MiB written); the steps rotate over 4
+resident multilinears (1 GiB, far larger than the 126 MB L2, so no flush is needed).  `value` =
+coefficients/s over all ranks with inputs resident in HBM; `e2e` = the same metric through the plugin
+call with HOST buffers (copy_h2d + fold + copy_d2h inside the timed region).  Next to the headline:
+  sumcheck_e2e     whole sumchecks through the trait calls with ONE upload (what the ComputeLayer contract
+                   exercises): the fold chain of one 2^24 multilinear and a bivariate-product sumcheck
+                   (m = 8, n = 20, round evaluations through traced accumulate_kernels), each with a CPU arm
+  ntt              BASELINE config #2 (S1/S2/S3) with the CPU arm of S1
+  keccak_replay    the compiled op-sequence replay of the keccak example at 2^18 permutations incl. the
+                   witness upload and the univariate-skip round, with a CPU arm assembled from bounded samples
+  sharded_sumcheck (N > 1) the low-variable-sharded bivariate sumcheck over NCCL, bit-exact vs the oracle
 N > 1: one process per GPU (torchrun), independent multilinears per rank (weak scaling, no data-path
-collective); the only collective is the timing max-reduce.
+collective in the headline); the only collective of the headline is the timing max-reduce.
 """
 import argparse
 import ctypes as C
@@ -27,6 +34,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sumcheck_fold_high_gf2_128_coeffs_per_s"
 UNIT = "coeffs/s"
+N_BUFFERS = 4
+
+
+def bench_config(log_coeffs):
+    """identical in both arms (`--impl ours` and `--impl reference`)"""
+    return {"workload": f"fold-high (extrapolate_line) over BinaryField128b, 2^{log_coeffs} coefficients per GPU",
+            "l2_policy": f"{N_BUFFERS} rotating multilinears of 2^{log_coeffs} coefficients (larger than L2); no flush"}
 
 
 def peaks():
@@ -191,7 +205,7 @@ def cpu_fold_baseline(log_coeffs, budget_s=12.0):
     return orc.cpu_fold_parallel(log_coeffs, budget_s)
 
 
-def cpu_univariate_baseline(rows_log2=21, columns=153, compositions=75, skip=6):
+def cpu_univariate_baseline(rows_log2=21, columns=153, compositions=75, skip=7):
     """CPU arm of the univariate-skip round (oracle/cpu_univariate.c: table-driven port, all host threads) on a
     bounded sample of the bench shape: the same columns/constraints on 2^rows_log2 rows."""
     from oracle import binding as orc
@@ -209,6 +223,29 @@ def cpu_univariate_baseline(rows_log2=21, columns=153, compositions=75, skip=6):
                       "(table-driven C restatement, pthreads; includes the table setup)"}
 
 
+def cpu_keccak_replay_baseline():
+    """CPU arm of the keccak replay, assembled from bounded samples of the same phases (each a threaded C restatement
+    of the reference's GFNI path, oracle/cpu_baseline.c + cpu_univariate.c) and scaled to the 2^18-permutation sizes;
+    the FRI folds and ring-switch eq-indicators (small on both arms) are left out."""
+    from oracle import binding as orc
+
+    cores = len(os.sched_getaffinity(0))
+    uni = cpu_univariate_baseline(rows_log2=21)               # 153 columns x 2^21 rows, skip 7  -> x 64
+    uni_ms = 153 * (1 << (27 - 7)) / uni["value"] * 1e3
+    ntt = orc.cpu_ntt_parallel(6, 20, 1, 3.0, d=24)           # 2^26 coefficients, 19 layers     -> x 16 x 23/19
+    ntt_ms = ntt["ms_per_transform"] * 16 * 23 / 19
+    zc = orc.cpu_chi_zerocheck_parallel(75, 78, 16, 3.0)      # 153 multilinears of 2^16         -> x 16
+    zc_ms = zc["ms_per_sumcheck"] * 16
+    pi = orc.cpu_bivariate_sumcheck_parallel(40, 18, 20, 3.0)  # 40 multilinears of 2^18, 20 pairs -> x 5 x 4
+    pi_ms = pi["ms_per_sumcheck"] * 20
+    return {"total_ms": uni_ms + ntt_ms + zc_ms + pi_ms, "cores": cores, "kind": "port",
+            "phases": {"zerocheck_univariate_skip_round": {"ms": uni_ms}, "commit_rs_encode_ntt": {"ms": ntt_ms},
+                       "zerocheck_rounds": {"ms": zc_ms}, "piop_bivariate_sumcheck": {"ms": pi_ms}},
+            "sample": "extrapolated from bounded samples: univariate round at 2^21 rows (x64), NTT at 2^26 coefficients / 19 layers "
+                      "(x16 x 23/19), chi zerocheck at 2^16 (x16), bivariate sumcheck at 40 x 2^18 / 20 pairs (x20); no witness upload, "
+                      "no FRI / ring-switch phases; C restatements of the reference GFNI path, not the Rust binary"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -222,7 +259,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u128 (GF(2^128) tower)", "data": "synthetic",
-            "config": {"workload": f"fold-high over BinaryField128b, 2^{args.log_coeffs} coefficients (bounded CPU sample)"},
+            "config": bench_config(args.log_coeffs),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -231,12 +268,13 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--log-coeffs", type=int, default=24)
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-keccak", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -270,14 +308,20 @@ def main():
     hal._check(hal._lib.b200_host_alloc(hal._ctx, n_in * 16, C.byref(ph)))
     pinned = np.ctypeslib.as_array((C.c_uint64 * (2 * n_in)).from_address(ph.value)).reshape(n_in, 2)
     pinned[:] = host
-    dev = hal.dev_alloc(n_in)
-    hal._check(hal._lib.b200_copy_h2d(hal._ctx, ph.value, dev.ptr, n_in))
-    lo, hi = dev.split_half_mut()
+    arena = hal.dev_alloc(N_BUFFERS * n_in)  # 4 resident multilinears (1 GiB at 2^24): the steps rotate over them
+    bufs = [arena.slice(k * n_in, (k + 1) * n_in) for k in range(N_BUFFERS)]
+    for b in bufs:
+        hal._check(hal._lib.b200_copy_h2d(hal._ctx, ph.value, b.ptr, n_in))
+    dev = bufs[0]
     z = 0x2E895399AF449ACE499596F6E5FCCAFA
     zs = (C.c_uint64 * 2)(z & (2**64 - 1), z >> 64)
+    step_no = [0]
 
     def fold_step():
-        hal._check(hal._lib.b200_extrapolate_line(hal._ctx, lo.ptr, half, hi.ptr, half, zs))
+        b = bufs[step_no[0] % N_BUFFERS]
+        step_no[0] += 1
+        hal._check(hal._lib.b200_extrapolate_line(hal._ctx, b.ptr, half, b.ptr + 16 * half, half, zs))
+        hal._check(hal._lib.b200_flush(hal._ctx))  # one launch per step (consecutive folds would otherwise batch)
 
     def barrier():
         hal.sync()
@@ -366,6 +410,61 @@ def main():
              "device_coeffs_per_s": chain_coeffs / (chain_ms * 1e-3), "e2e_ms": chain_e2e_ms,
              "e2e_coeffs_per_s": chain_coeffs / (chain_e2e_ms * 1e-3), "h2d_bytes": n_in * 16, "d2h_bytes": 16}
 
+    # ---- whole bivariate-product sumcheck through the trait calls (v3::BivariateSumcheckProver's data plane,
+    #      bivariate_product.rs:168-232, 303-408): upload m = 8 multilinears of 2^20 once, then 20 rounds of
+    #      {calculate_round_evals = the traced accumulate_kernels closure, fold of every multilinear}, read the finals
+    biv = None
+    if not args.no_ntt:
+        import random as _rb
+
+        from binius_b200 import calculate_round_evals
+
+        nvb, mb = 20, 8
+        rb = _rb.Random(11)
+        pairs_b = [((5 * c + 1) % mb, (3 * c + 2) % mb) for c in range(8)]
+        h_mls = pinned[: mb << nvb]
+        d_mls = bufs[1].slice(0, mb << nvb)
+        finals = np.zeros((mb, 2), np.uint64)
+
+        def biv_sumcheck(upload):
+            if upload:
+                hal._check(hal._lib.b200_copy_h2d(hal._ctx, h_mls.ctypes.data, d_mls.ptr, mb << nvb))
+            cur = [d_mls.slice(t << nvb, (t + 1) << nvb) for t in range(mb)]
+            for r in range(nvb):
+                calculate_round_evals(hal, nvb - r, rb.getrandbits(128), cur, pairs_b)  # synchronous: the transcript needs the values
+                ch = rb.getrandbits(128)
+
+                def fold(ex):
+                    for t in range(mb):
+                        lo_, hi_ = cur[t].split_half_mut()
+                        ex.extrapolate_line(lo_, hi_, ch)
+                        cur[t] = lo_
+                    return []
+
+                hal.execute(fold)
+            if upload:
+                for t in range(mb):
+                    hal._check(hal._lib.b200_copy_d2h(hal._ctx, cur[t].ptr, finals[t:].ctypes.data, 1))
+
+        biv_sumcheck(True)
+        barrier()
+        lb0 = hal.launch_count()
+        ev.start()
+        for _ in range(3):
+            biv_sumcheck(False)
+        biv_dev_ms = ev.stop_ms() / 3
+        biv_launches = (hal.launch_count() - lb0) // 3
+        barrier()
+        tb0 = time.perf_counter()
+        for _ in range(3):
+            biv_sumcheck(True)
+        barrier()
+        biv_e2e_ms = (time.perf_counter() - tb0) * 1e3 / 3
+        biv = {"multilinears": mb, "n_vars": nvb, "compositions": len(pairs_b), "route": "accumulate_kernels traced in the library -> k_pair_tc",
+               "launches": int(biv_launches), "device_ms": biv_dev_ms, "device_rounds_per_s": nvb / (biv_dev_ms * 1e-3), "e2e_ms": biv_e2e_ms,
+               "e2e_rounds_per_s": nvb / (biv_e2e_ms * 1e-3), "h2d_bytes": (mb << nvb) * 16, "d2h_bytes": 16 * mb + 32 * nvb,
+               "note": "device_ms includes the per-round synchronising fetch of the round values (Python mirror in the loop)"}
+
     # ---- NTT (BASELINE config #2): B32, 2^24 coefficients, S1/S2/S3 shapes ------------------------
     ntt_res = None
     if not args.no_ntt:
@@ -388,8 +487,13 @@ def main():
             for _ in range(reps):
                 ntt.inverse_device(dev.ptr, 5, n32, S, 0, 0, skip)
             inv_ms = ev.stop_ms() / reps
+            n_prod = (ly - skip) * n32 // 2
             ntt_res[name] = {"fwd_ms": fwd_ms, "inv_ms": inv_ms, "coeffs_per_s": n32 / (fwd_ms * 1e-3), "passes": passes,
-                             "roofline_frac": (8 * n32 / (fwd_ms * 1e-3)) / (peak * 1e9)}
+                             "roofline_frac": (8 * n32 / (fwd_ms * 1e-3)) / (peak * 1e9),
+                             "roofline": {"hbm_frac": (8 * n32 / (fwd_ms * 1e-3)) / (peak * 1e9), "b32_products_per_s": n_prod / (fwd_ms * 1e-3),
+                                          "sm_cycles_per_product": fwd_ms * 1e-3 * 1.965e9 * 148 / n_prod,
+                                          "limiting_pipes": "ALU + LSU (nibble/byte look-up tables: 8-19 ALU-pipe instructions and 4-8 shared-memory "
+                                                            "gathers per product; profiles/r2_ntt_k_ntt_lut_ncu_full.csv)"}}
 
     # ---- sumcheck round (BASELINE config #3 shape, v3 bivariate variant): m = 8 multilinears, n = 20,
     #      8 compositions: round evaluations + fold of every multilinear; and one tensor expansion ------
@@ -399,16 +503,22 @@ def main():
 
         rr = _r.Random(7)
         nv, m = 20, 8
-        sub = [dev.slice(t << nv, (t + 1) << nv) for t in range(m)]  # 8 x 2^20 elements of the resident buffer
+        sub = [dev.slice(t << nv, (t + 1) << nv) for t in range(m)]  # 8 x 2^20 elements of a resident buffer
         pairs = [(rr.randrange(m), rr.randrange(m)) for _ in range(m)]
         alpha = rr.getrandbits(128)
+        from binius_b200 import calculate_round_evals as _cre
+
         for _ in range(2):
-            hal.execute(lambda ex: list(ex.bivariate_round_evals(sub, nv, pairs, alpha)))
+            _cre(hal, nv, alpha, sub, pairs)
         ev.start()
         reps = 5
         for _ in range(reps):
-            hal.execute(lambda ex: list(ex.bivariate_round_evals(sub, nv, pairs, alpha)))
+            _cre(hal, nv, alpha, sub, pairs)  # the TRAIT route: accumulate_kernels closure traced by the library
         re_ms = ev.stop_ms() / reps
+        ev.start()
+        for _ in range(reps):
+            hal.execute(lambda ex: list(ex.bivariate_round_evals(sub, nv, pairs, alpha)))
+        re_fused_ms = ev.stop_ms() / reps
         k = 22
         coords = [rr.getrandbits(128) for _ in range(k)]
         te = dev.slice(0, 1 << k)
@@ -419,7 +529,8 @@ def main():
         for _ in range(reps):
             hal.execute(lambda ex: (ex.tensor_expand(0, coords, te), [])[1])
         te_ms = ev.stop_ms() / reps
-        extras = {"bivariate_round_evals_m8_n20": {"ms": re_ms, "products_per_s": 2 * len(pairs) * (1 << (nv - 1)) / (re_ms * 1e-3),
+        extras = {"bivariate_round_evals_m8_n20": {"ms": re_ms, "route": "accumulate_kernels (traced)", "fused_entry_point_ms": re_fused_ms,
+                                                   "products_per_s": 2 * len(pairs) * (1 << (nv - 1)) / (re_ms * 1e-3),
                                                    "hbm_frac": (16 * m * (1 << nv) / (re_ms * 1e-3)) / (peak * 1e9)},
                   "tensor_expand_k22": {"ms": te_ms, "elems_per_s": (1 << k) / (te_ms * 1e-3),
                                         "hbm_frac": (16 * (1 << k) / (te_ms * 1e-3)) / (peak * 1e9)}}
@@ -506,14 +617,14 @@ def main():
         }
 
     # ---- zerocheck univariate-skip round at the keccak shape scaled to 2^24 rows:
-    #      153 B1 columns, 75 degree-2 constraints, skip 6, domain 128 (tools/univariate_bench.py runs 2^27)
+    #      153 B1 columns, 75 degree-2 constraints, skip 7, domain 256 (the compiled replay below runs 2^27 rows)
     uni = None
     if not args.no_ntt and rank == 0:
         try:
             from binius_b200 import ArithCircuit as A
             from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals
 
-            nvu, mu, ncu, sku = 24, 153, 75, 6
+            nvu, mu, ncu, sku = 24, 153, 75, 7  # skip 7 = the reference's choice for degree 2 over B8 (verify.rs:271-294)
             wu = 1 << (nvu - 7)
             import random as _random
 
@@ -535,10 +646,70 @@ def main():
             alg = mu * wu * 16 + 16 * (1 << (nvu - sku))
             uni = {"ms_per_call": min(times), "rows_log2": nvu, "columns": mu, "compositions": ncu, "skip_rounds": sku,
                    "algorithmic_bytes": alg, "hbm_frac": alg / (min(times) * 1e-3) / 1e9 / peak,
-                   "note": "host wall time of the synchronous call (eq-ind expansion + k_uni_b8 + result copy); "
-                           "shared-memory-pipe bound (ncu: LSU wavefronts 88 % of peak), see DESIGN.md section 9"}
+                   "note": "host wall time of the synchronous call (eq-ind expansion + k_uni_b8 per composition range + result copy); "
+                           "shared-memory-pipe bound, see DESIGN.md section 9"}
         except Exception as e:  # never lose the headline line to the extra measurement
             uni = {"error": repr(e)}
+
+    # ---- keccak example, n_permutations = 2^18 (BASELINE config #4): the compiled op-sequence replay
+    #      (tools/keccak_replay.cpp over binius_b200/host/*.hpp): witness upload, univariate-skip round, RS-encode NTT,
+    #      zerocheck rounds, PIOP bivariate sumcheck (kernel scopes), FRI folds, ring-switch eq-indicators
+    keccak = None
+    if not args.no_ntt and rank == 0 and not args.no_keccak:
+        exe = os.path.join(ROOT, "tools", "keccak_replay_cpp")
+        try:
+            hal.sync()
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank] if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local_rank))
+            out = subprocess.run([exe, "18"], capture_output=True, text=True, timeout=240, env=env)
+            keccak = json.loads(out.stdout.strip().splitlines()[-1])
+            keccak["host"] = "compiled C++ over the C ABI (binius_b200/host/*.hpp), separate process"
+        except Exception as e:  # never lose the headline line to the extra measurement
+            keccak = {"error": repr(e)}
+
+    # ---- sharded sumcheck on the real layer over NCCL: low-variable partition, every round local,
+    #      per-round XOR of the partial round values (all-gather), one final gather.  First a run checked round by
+    #      round against the oracle (n = 16), then a timed one (n = 22).
+    sharded = None
+    if world > 1 and not args.no_ntt:
+        import random as _rs
+
+        from binius_b200 import sharding
+        from oracle import binding as orc_chk  # checker only (never on the timed path)
+
+        try:
+            rs_ = _rs.Random(5)
+            m_s, n_chk = 6, 16
+            mls_chk = [orc_chk.rand_b128(100 + t, 1 << n_chk) for t in range(m_s)]
+            pairs_s = [(0, 1), (2, 3), (4, 5), (1, 4)]
+            al = [rs_.getrandbits(128) for _ in range(n_chk)]
+            chs = [rs_.getrandbits(128) for _ in range(n_chk)]
+            sc = sharding.ShardedBivariateSumcheck(hal, mls_chk, n_chk, pairs_s, world, rank, dist, comm_device=f"cuda:{local_rank}")
+            cur = [x.copy() for x in mls_chk]
+            exact = True
+            for r in range(n_chk):
+                exp = tuple(orc_chk.bivariate_round_evals(cur, n_chk - r, pairs_s, al[r]))
+                exact = exact and sc.round_evals(al[r]) == exp
+                sc.fold(chs[r])
+                cur = [orc_chk.extrapolate_line(x[: len(x) // 2], x[len(x) // 2:], chs[r]) for x in cur]
+            exact = exact and sc.finish() == [orc_chk.to_ints(x)[0] for x in cur]
+            n_t = 22
+            big = [np.ascontiguousarray(pinned[(t << n_t) % n_in: (t << n_t) % n_in + (1 << n_t)]) for t in range(m_s)]
+            sc = sharding.ShardedBivariateSumcheck(hal, big, n_t, pairs_s, world, rank, dist, comm_device=f"cuda:{local_rank}")
+            barrier()
+            ts0 = time.perf_counter()
+            for r in range(n_t):
+                sc.round_evals(al[r % n_chk])
+                sc.fold(chs[r % n_chk])
+            barrier()
+            sh_ms = (time.perf_counter() - ts0) * 1e3
+            t_ex = torch.tensor([1 if exact else 0], device="cuda")
+            dist.all_reduce(t_ex, op=dist.ReduceOp.MIN)
+            sharded = {"bit_exact": bool(t_ex.item()), "checked": f"{n_chk} rounds vs the oracle on every rank (m = {m_s}, 4 pairs)",
+                       "timed": {"n_vars": n_t, "multilinears": m_s, "ms": sh_ms, "rounds_per_s": n_t / (sh_ms * 1e-3),
+                                 "coeffs_per_s": m_s * ((2 << n_t) - 2) / (sh_ms * 1e-3)},
+                       "collective": "all_gather of 2 x B128 per round + one final gather (NCCL); no data-plane exchange"}
+        except Exception as e:
+            sharded = {"error": repr(e)}
 
     # ---- reduce over ranks: max time ----------------------------------------------------------------
     ms_step = ms_total / args.steps
@@ -558,9 +729,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u128 (GF(2^128) tower, integer/bitwise)", "data": "synthetic",
-            "config": {"workload": f"fold-high (extrapolate_line) over BinaryField128b, 2^{args.log_coeffs} coefficients per GPU",
-                       "l2_policy": "inputs (256 MiB) larger than L2; no flush", "parallelism": f"independent multilinears x{world}",
-                       "host_cpus_bound_per_rank": numa},
+            "config": bench_config(args.log_coeffs),
+            "host": {"parallelism": f"independent multilinears x{world}", "host_cpus_bound_per_rank": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * n_in / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_in * 16, "d2h_bytes_per_step": half * 16,
                     "ms_per_step": e2e_ms},
@@ -569,6 +739,10 @@ def main():
                          "algorithmic_bytes": 24.0 * n_in, "kernel_ms": ms_step, "kernel_ms_isolated": kern_ms_avg,
                          "frac_isolated": 24.0 * n_in / (kern_ms_avg * 1e-3) / 1e9 / peak},
         }
+        line["sumcheck_e2e"] = {"what": "whole sumchecks through the trait calls with ONE upload (host buffers in, final values out)",
+                                "fold_chain_2^%d" % args.log_coeffs: chain}
+        if biv:
+            line["sumcheck_e2e"]["bivariate_m8_n20"] = biv
         if ntt_res:
             line["ntt"] = ntt_res
         if extras:
@@ -579,20 +753,34 @@ def main():
             line["ops"] = ops
         if uni:
             line["zerocheck_univariate_skip_2^24_rows"] = uni
-        line["sumcheck_chain"] = chain
-        if not args.no_cpu:
-            os.sched_setaffinity(0, all_cpus)  # the CPU arm uses every host core
+        if keccak:
+            line["keccak_replay_2^18"] = keccak
+        if sharded:
+            line["sharded_sumcheck"] = sharded
+        if world > 1:
+            line["e2e"]["aggregate_h2d_gbs"] = world * n_in * 16 / (e2e_ms * 1e-3) / 1e9
+        if not args.no_cpu and world == 1:
+            os.sched_setaffinity(0, all_cpus)  # the CPU arms use every host core
             line["cpu_baseline"] = cpu_fold_baseline(args.log_coeffs)
             from oracle import binding as orc
 
-            line["sumcheck_chain"]["cpu_baseline"] = orc.cpu_fold_chain_parallel(args.log_coeffs, 5.0)
-            if uni and "error" not in uni:
+            def arm(fn):
                 try:
-                    uni["value"] = uni["columns"] * (1 << (uni["rows_log2"] - uni["skip_rounds"])) / (uni["ms_per_call"] * 1e-3)
-                    uni["unit"] = "sub-cube columns/s"
-                    uni["cpu_baseline"] = cpu_univariate_baseline()
+                    return fn()
                 except Exception as e:
-                    uni["cpu_baseline"] = {"error": repr(e)}
+                    return {"error": repr(e)}
+
+            chain["cpu_baseline"] = arm(lambda: orc.cpu_fold_chain_parallel(args.log_coeffs, 5.0))
+            if biv:
+                biv["cpu_baseline"] = arm(lambda: orc.cpu_bivariate_sumcheck_parallel(8, 20, 8, 5.0))
+            if ntt_res:
+                ntt_res["S1_rs_encode"]["cpu_baseline"] = arm(lambda: orc.cpu_ntt_parallel(6, 18, 1, 5.0, d=24))
+            if uni and "error" not in uni:
+                uni["value"] = uni["columns"] * (1 << (uni["rows_log2"] - uni["skip_rounds"])) / (uni["ms_per_call"] * 1e-3)
+                uni["unit"] = "sub-cube columns/s"
+                uni["cpu_baseline"] = arm(cpu_univariate_baseline)
+            if keccak and "error" not in keccak:
+                keccak["cpu_baseline"] = arm(cpu_keccak_replay_baseline)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

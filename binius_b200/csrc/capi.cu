@@ -398,6 +398,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET((nttl::k_ntt_lut<3, true, true>), 227u * 1024u);
 	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
 	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
+	SET(tc::k_jobs_small, FIELD_TABLE_BYTES);
 #undef SET
 	if (rc != B200_OK) return rc;
 	*out = ctx.release();
@@ -465,6 +466,11 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
 	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
 	return B200_OK;
+}
+void b200_host_mul128(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+	const hostf::u128 p = hostf::mul128(hostf::from_words(a), hostf::from_words(b));
+	out[0] = (uint64_t)p;
+	out[1] = (uint64_t)(p >> 64);
 }
 int32_t b200_event_create(b200_ctx *ctx, void **out) {
 	B200_LOCK(ctx);
@@ -964,22 +970,33 @@ int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n
 	e->steps.assign(steps, steps + n_steps);
 	e->n_vars = n_vars;
 	e->poly_ok = plan::expand(steps, n_steps, 2, 64, e->poly);
-	if (cudaMalloc(&e->d_steps, sizeof(b200_expr_step) * std::max(n_steps, 1u)) != cudaSuccess) {
-		cudaGetLastError();
-		return fail(ctx, B200_ERR_ALLOC, "out of device memory");
-	}
-	if (n_steps) B200_CUDA(ctx, cudaMemcpy(e->d_steps, steps, sizeof(b200_expr_step) * n_steps, cudaMemcpyHostToDevice));
 	*out = e.release();
 	return B200_OK;
 }
 void b200_expr_free(b200_expr *e) {
 	if (!e) return;
-	cudaFree(e->d_steps);
+	if (e->d_steps) cudaFree(e->d_steps);
 	delete e;
 }
 uint32_t b200_expr_n_vars(const b200_expr *e) { return e ? e->n_vars : 0; }
 
-static DevExpr dev_expr(const b200_expr *e) { return DevExpr{e->d_steps, (uint32_t)e->steps.size(), e->n_vars}; }
+// The device copy of the steps is made on first use by an interpreter kernel: compile_expr itself stays a host-side
+// operation (the prover compiles its compositions every round, bivariate_product.rs:311-314; the traced and monomial
+// paths never read the steps on the device), so it must not cost a cudaMalloc.
+static DevExpr dev_expr(const b200_expr *e) {
+	b200_expr *m = const_cast<b200_expr *>(e);
+	if (!m->d_steps && !m->steps.empty()) {
+		if (cudaMalloc(&m->d_steps, sizeof(b200_expr_step) * m->steps.size()) != cudaSuccess ||
+			cudaMemcpy(m->d_steps, m->steps.data(), sizeof(b200_expr_step) * m->steps.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+			cudaGetLastError();
+			if (m->d_steps) cudaFree(m->d_steps);
+			m->d_steps = nullptr;
+		}
+	}
+	return DevExpr{m->d_steps, (uint32_t)m->steps.size(), m->n_vars};
+}
+#define B200_EXPR_READY(ctx, de) \
+	if ((de).n_steps && !(de).steps) return fail(ctx, B200_ERR_ALLOC, "out of device memory (expression steps)")
 
 int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, b200_dev_ptr out, uint64_t n_out, const b200_expr *expr) {
 	B200_LOCK(ctx);
@@ -993,7 +1010,9 @@ int32_t b200_compute_composite(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32
 		int32_t rc = stage_args(ctx, inputs, sizeof(void *) * n_inputs, &dptrs);
 		if (rc) return rc;
 	}
-	k_compute_composite<<<grid_for(ctx, n_out, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, PtrList{(const uint4 *const *)dptrs, n_inputs}, dev_expr(expr), (uint4 *)out, n_out);
+	const DevExpr de = dev_expr(expr);
+	B200_EXPR_READY(ctx, de);
+	k_compute_composite<<<grid_for(ctx, n_out, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, PtrList{(const uint4 *const *)dptrs, n_inputs}, de, (uint4 *)out, n_out);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
 }
@@ -1039,7 +1058,9 @@ static int32_t kernel_sum_now(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_
 		int32_t rc = stage_args(ctx, inputs, sizeof(void *) * n_inputs, &dptrs);
 		if (rc) return rc;
 	}
-	k_sum_composition<<<grid_for(ctx, row_len, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, PtrList{(const uint4 *const *)dptrs, n_inputs}, dev_expr(expr), row_len, to_u4(coeff), ctx->d_results + slot);
+	const DevExpr de = dev_expr(expr);
+	B200_EXPR_READY(ctx, de);
+	k_sum_composition<<<grid_for(ctx, row_len, 256, 2), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, PtrList{(const uint4 *const *)dptrs, n_inputs}, de, row_len, to_u4(coeff), ctx->d_results + slot);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
 }
@@ -1055,10 +1076,15 @@ static int32_t kernel_add_now(b200_ctx *ctx, uint32_t log_len, const void *a, co
 // sources before any sum reads it, and sums read only such Locals or buffers the scope never writes.
 static int32_t run_trace(b200_ctx *ctx) {
 	std::vector<b200_trace_op> &ops = ctx->trace;
+	// Locals sorted by address: membership of a pointer in O(log n) (a PIOP round maps 200 Locals and issues 600 ops)
+	std::vector<std::pair<const uint8_t *, int>> order(ctx->locals.size());
+	for (size_t i = 0; i < order.size(); i++) order[i] = {ctx->locals[i].first, (int)i};
+	std::sort(order.begin(), order.end());
 	auto local_ix = [&](const void *p) -> int {
-		for (size_t i = 0; i < ctx->locals.size(); i++)
-			if ((const uint8_t *)p >= ctx->locals[i].first && (const uint8_t *)p < ctx->locals[i].first + ctx->locals[i].second) return (int)i;
-		return -1;
+		auto it = std::upper_bound(order.begin(), order.end(), std::make_pair((const uint8_t *)p, INT32_MAX));
+		if (it == order.begin()) return -1;
+		--it;
+		return (const uint8_t *)p < it->first + ctx->locals[it->second].second ? it->second : -1;
 	};
 	bool ok = ctx->tune_round_evals_tc != 0;
 	uint64_t len = 0;
@@ -1079,7 +1105,8 @@ static int32_t run_trace(b200_ctx *ctx) {
 				}
 		}
 	}
-	ok = ok && len >= 4096 && len % tc::CHUNK == 0;
+	const bool small = len < 4096 || len % tc::CHUNK != 0;  // below the tensor-core kernel's granularity: k_jobs_small
+	ok = ok && len >= 1;
 	if (!ok) {
 		// in order, as recorded; Locals are zero-initialised (layer.rs:617-644)
 		for (auto &l : ctx->locals) B200_CUDA(ctx, cudaMemsetAsync(l.first, 0, l.second, ctx->stream));
@@ -1093,6 +1120,7 @@ static int32_t run_trace(b200_ctx *ctx) {
 	}
 	std::vector<tc::TcJob> jobs;
 	std::vector<tc::TcTarget> targets;
+	std::vector<std::pair<uint32_t, uint4>> const_terms;
 	std::map<std::tuple<const void *, const void *, const void *, const void *>, uint32_t> job_ix;
 	bool need_ones = false;
 	for (const b200_trace_op &op : ops)
@@ -1119,7 +1147,14 @@ static int32_t run_trace(b200_ctx *ctx) {
 		if (op.kind != 1) continue;
 		const hostf::u128 cf = hostf::from_words(op.coeff);
 		for (auto &t : op.expr->poly) {
-			if (t.first.empty()) continue;  // a constant summed over an even number of points vanishes
+			if (t.first.empty()) {  // a constant c summed over len points: c if len is odd, else 0
+				if (len & 1) {
+					const hostf::u128 wgt = hostf::mul128(cf, t.second);
+					uint64_t w[2] = {(uint64_t)wgt, (uint64_t)(wgt >> 64)};
+					const_terms.push_back({op.slot, to_u4(w)});
+				}
+				continue;
+			}
 			const void *o[4] = {nullptr, nullptr, need_ones ? (const void *)ones : nullptr, nullptr};
 			for (size_t f = 0; f < t.first.size(); f++) {
 				const void *p = op.inputs[t.first[f]];
@@ -1137,6 +1172,21 @@ static int32_t run_trace(b200_ctx *ctx) {
 			uint64_t w[2] = {(uint64_t)wgt, (uint64_t)(wgt >> 64)};
 			if (wgt) targets.push_back(tc::TcTarget{it->second, op.slot, to_u4(w)});
 		}
+	}
+	for (auto &ct : const_terms) {
+		k_xor_slot<<<1, 1, 0, ctx->stream>>>(ctx->d_results + ct.first, ct.second);
+		B200_LAUNCH_CHECK(ctx);
+	}
+	if (targets.empty()) return B200_OK;
+	if (small) {
+		ArgPack pack;
+		size_t o_j = pack.add(jobs.data(), sizeof(tc::TcJob) * jobs.size()), o_t = pack.add(targets.data(), sizeof(tc::TcTarget) * targets.size());
+		uint8_t *dbase;
+		int32_t rc = pack.commit(ctx, &dbase);
+		if (rc) return rc;
+		tc::k_jobs_small<<<(uint32_t)targets.size(), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, (const tc::TcJob *)(dbase + o_j), (const tc::TcTarget *)(dbase + o_t), len, ctx->d_results);
+		B200_LAUNCH_CHECK(ctx);
+		return B200_OK;
 	}
 	return launch_tc_pairs(ctx, jobs, len, targets, off_g);
 }
@@ -1310,11 +1360,6 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 	*first_slot = ctx->n_results;
 	ctx->n_results += total;
 	if (total == 0) return B200_OK;
-	std::vector<DevExpr> hc(n_comp), hl(n_comp);
-	for (uint32_t c = 0; c < n_comp; c++) {
-		hc[c] = dev_expr(comps[c]);
-		hl[c] = dev_expr(leads[c]);
-	}
 	std::vector<uint4> hp(n_points);
 	for (uint32_t p = 0; p < n_points; p++) hp[p] = to_u4(points + 2 * p);
 	EqIndArgs A;
@@ -1337,6 +1382,14 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 			for (uint32_t c = 0; c < n_comp && ok; c++) ok = codes[p] == 1 ? comps[c]->poly_ok : leads[c]->poly_ok;
 		}
 		if (ok) return eq_ind_monomial_plan(ctx, mls, half, eq_ind, comps, leads, n_comp, codes, n_points, *first_slot);
+	}
+	// the interpreter kernels read the steps on the device (uploaded on first use)
+	std::vector<DevExpr> hc(n_comp), hl(n_comp);
+	for (uint32_t c = 0; c < n_comp; c++) {
+		hc[c] = dev_expr(comps[c]);
+		hl[c] = dev_expr(leads[c]);
+		B200_EXPR_READY(ctx, hc[c]);
+		B200_EXPR_READY(ctx, hl[c]);
 	}
 	ArgPack pack;
 	size_t o_m = pack.add(mls, sizeof(void *) * m), o_l = pack.add(hlen.data(), 8 * hlen.size()), o_s = pack.add(hs.data(), 16 * hs.size());
@@ -1795,6 +1848,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 		bool need_ext = false;
 		for (uint32_t c = 0; c < n_comp; c++) {
 			hc[c] = dev_expr(comps[c]);
+			B200_EXPR_READY(ctx, hc[c]);
 			pts[c] = degrees[c] > 1 ? (degrees[c] - 1) << skip : 0;
 			if (pts[c] == 0 || pts[c] >= n_out) continue;
 			need_ext = true;

@@ -200,6 +200,7 @@ __global__ void k_add(const uint4 *__restrict__ a, const uint4 *__restrict__ b, 
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = a[i] ^ b[i];
 }
 __global__ void k_set_slot(uint4 *slot, uint4 v) { *slot = v; }
+__global__ void k_xor_slot(uint4 *slot, uint4 v) { *slot ^= v; }
 
 // ------------------------------------------------------------------------------------------------
 // inner_product(SubfieldSlice{a, lvl}, b) = sum_i sum_j b[i*L + j] * limb_j(a[i])

@@ -277,5 +277,30 @@ __global__ void __launch_bounds__(128) k_pair_tc_combine(const uint8_t *__restri
 	}
 }
 
+// The same jobs on rounds too small for the tensor cores (len < 4096 points): one CTA per target evaluates its job
+// sum_i (a0 + a1)[i] * (b0 + b1)[i] with the per-lane multiply, scales it by the target's coefficient and XORs it
+// into the slot -- ONE launch for all compositions of a small round.  grid = n_targets, block = 256, dyn smem = FIELD_TABLE_BYTES
+__global__ void __launch_bounds__(256) k_jobs_small(const uint8_t *__restrict__ g_tables, const TcJob *__restrict__ jobs, const TcTarget *__restrict__ targets,
+													uint64_t len, uint4 *__restrict__ slots) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	__shared__ uint4 red[32];
+	const TcTarget tg = targets[blockIdx.x];
+	const TcJob J = jobs[tg.job];
+	uint4 acc = u4_zero();
+	for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) {
+		uint4 a = __ldg(J.a0 + i), b = __ldg(J.b0 + i);
+		if (J.a1) a ^= __ldg(J.a1 + i);
+		if (J.b1) b ^= __ldg(J.b1 + i);
+		acc ^= f_mul128(T, a, b);
+	}
+	acc = block_xor(acc, red);
+	if (threadIdx.x == 0 && !is_zero(acc)) {
+		const uint4 cf = tg.coef;
+		const bool one = cf.x == 1 && (cf.y | cf.z | cf.w) == 0;
+		atomic_xor_u4(slots + tg.slot, one ? acc : f_mul128(T, acc, cf));
+	}
+}
+
 }  // namespace tc
 }  // namespace b200

@@ -34,8 +34,25 @@ def _mul(a: int, b: int, k: int, use_cache: bool = True) -> int:
     return (z0 ^ z2) | ((z1 ^ _mul_alpha(z2, k - 1)) << h)
 
 
+_M64 = (1 << 64) - 1
+
+
 def mul(a: int, b: int, k: int = 7) -> int:
-    """product in T_k (k = 7: BinaryField128b)"""
+    """product in T_k (k = 7: BinaryField128b).  B128 products go through the library's host-side helper
+    (b200_host_mul128, ~1 us) when it is loaded; the pure-Python recursion is the definition and the fallback."""
+    if k == 7:
+        try:
+            import ctypes as C
+
+            from . import _lib
+
+            lib = _lib.load()
+            A2 = C.c_uint64 * 2
+            out = A2()
+            lib.b200_host_mul128(A2(a & _M64, a >> 64), A2(b & _M64, b >> 64), out)
+            return int(out[0]) | (int(out[1]) << 64)
+        except ImportError:
+            pass
     return _mul(a, b, k)
 
 

@@ -74,6 +74,9 @@ int32_t b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
  * 2 scalar tables), "ntt_log_cc" (5..7), "fold" (2 TMA-staged, 1 K64, 0 LUT128), "round_evals_tc" (1/0/2),
  * "uni_generic" (1 forces the generic univariate-skip kernel).  Unknown key: InputValidation. */
 int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value);
+/* Host-side scalar product in BinaryField128b (no device involved): the O(1)-per-round scalar work of a host
+ * mirror without its own field arithmetic -- batch-coefficient powers (bivariate_product.rs:337-339), eq factors. */
+void b200_host_mul128(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
 /* CUDA-event timing on the context's stream (bench.py): record two events, read elapsed ms */
 int32_t b200_event_create(b200_ctx *ctx, void **event_out);
 int32_t b200_event_record(b200_ctx *ctx, void *event);

@@ -286,6 +286,97 @@ def cpu_fold_chain_parallel(log_coeffs: int, budget_s: float = 6.0, n_threads: i
             "sample": f"{reps} x full fold chain of a 2^{log_coeffs}-coefficient multilinear, {n_threads} threads"}
 
 
+def cpu_ntt_forward(data, log_x: int, log_y: int, skip: int = 0, d: int = 24, n_threads: int = 1, use_gfni: bool = True):
+    """Threaded GFNI forward NTT over B32 (oracle/cpu_baseline.c, port of crates/ntt/src/multithreaded.rs:100-228),
+    shape (log_x >= 4, log_y, 0), coset 0; returns the transformed copy."""
+    a = np.ascontiguousarray(data, dtype=np.uint32).copy()
+    assert a.shape[0] == 1 << (log_x + log_y)
+    ntt = NTT(5, d)
+    rc = lib().cpu_ntt_forward(_p(a), C.c_uint32(log_x), C.c_uint32(log_y), C.c_uint32(skip), _p(ntt.s), C.c_uint32(d),
+                               C.c_int(n_threads), C.c_int(int(use_gfni)))
+    _check(rc)
+    return a
+
+
+def cpu_ntt_parallel(log_x: int, log_y: int, skip: int, budget_s: float = 6.0, n_threads: int = 0, d: int = 0):
+    """Times the forward NTT of 2^(log_x+log_y) B32 coefficients on this host; returns a cpu_baseline object."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    d = d or max(log_y, 1)
+    ntt = NTT(5, d)
+    fn = lib().cpu_ntt_bench
+    fn.restype = C.c_double
+    args = (C.c_uint32(log_x), C.c_uint32(log_y), C.c_uint32(skip))
+    t1 = fn(*args, C.c_int(1), C.c_int(n_threads), _p(ntt.s), C.c_uint32(d), C.c_int(1))
+    reps = max(1, min(100, int(budget_s / max(t1, 1e-4))))
+    t = fn(*args, C.c_int(reps), C.c_int(n_threads), _p(ntt.s), C.c_uint32(d), C.c_int(1))
+    n = 1 << (log_x + log_y)
+    how = "AVX-512+GFNI" if lib().cpu_has_gfni512() else "scalar (host CPU lacks AVX-512/GFNI)"
+    return {"value": reps * n / t, "unit": "coeffs/s", "ms_per_transform": t / reps * 1e3, "cores": n_threads, "kind": "port",
+            "sample": f"{reps} x forward NTT (log_x {log_x}, log_y {log_y}, skip {skip}) of 2^{log_x + log_y} B32 coefficients, "
+                      f"{n_threads} threads, {how}; C restatement of crates/ntt/src/multithreaded.rs, not the Rust binary"}
+
+
+def cpu_bivariate_round_evals(multilins, n_vars: int, pairs, batch_coeff: int, n_threads: int = 1, use_gfni: bool = True):
+    """[y_1, y_inf] by the threaded GFNI CPU arm (oracle/cpu_baseline.c)"""
+    ms = [_c(x) for x in multilins]
+    ptrs = (C.c_void_p * len(ms))(*[x.ctypes.data for x in ms])
+    ia = (C.c_uint32 * max(len(pairs), 1))(*[p[0] for p in pairs])
+    ib = (C.c_uint32 * max(len(pairs), 1))(*[p[1] for p in pairs])
+    out = np.zeros((2, 2), np.uint64)
+    lib().cpu_bivariate_round_evals(ptrs, C.c_uint32(n_vars), ia, ib, C.c_uint32(len(pairs)), _p(one(batch_coeff)), C.c_int(n_threads),
+                                    C.c_int(int(use_gfni)), _p(out))
+    return to_ints(out)
+
+
+def cpu_bivariate_sumcheck_parallel(m: int, n_vars: int, n_comp: int, budget_s: float = 6.0, n_threads: int = 0):
+    """Times the data plane of a whole bivariate-product sumcheck (n_vars rounds of round evaluations + fold of every
+    multilinear) on this host; returns a cpu_baseline object in rounds/s."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    fn = lib().cpu_bivariate_sumcheck_bench
+    fn.restype = C.c_double
+    chk = np.zeros((1, 2), np.uint64)
+    args = (C.c_uint32(m), C.c_uint32(n_vars), C.c_uint32(n_comp))
+    t1 = fn(*args, C.c_int(1), C.c_int(n_threads), C.c_int(1), _p(chk))
+    reps = max(1, min(20, int(budget_s / max(t1, 1e-4))))
+    t = fn(*args, C.c_int(reps), C.c_int(n_threads), C.c_int(1), _p(chk))
+    return {"value": reps * n_vars / t, "unit": "rounds/s", "ms_per_sumcheck": t / reps * 1e3, "cores": n_threads, "kind": "port",
+            "sample": f"{reps} x sumcheck over {m} multilinears of 2^{n_vars} B128 elements, {n_comp} index pairs, {n_threads} threads; "
+                      "C restatement of v3::BivariateSumcheckProver over FastCpuLayer (GFNI multiply), not the Rust binary"}
+
+
+def cpu_chi_round_evals(cols, n_out: int, n_b: int, n_vars: int, eq, with_eval_1: bool, n_threads: int = 1, use_gfni: bool = True):
+    """[constraint][at 1, at infinity] of the keccak chi constraints out_c - (b_c + (b_{c+1} - 1) * b_{c+2}) by the threaded
+    GFNI CPU arm; cols = n_out `out` columns followed by n_b `b` columns of 2^n_vars B128 elements"""
+    cs = [_c(x) for x in cols]
+    ptrs = (C.c_void_p * len(cs))(*[x.ctypes.data for x in cs])
+    out = np.zeros((2 * n_out, 2), np.uint64)
+    lib().cpu_chi_round_evals(ptrs, C.c_uint32(n_out), C.c_uint32(n_b), C.c_uint32(n_vars), _p(_c(eq)), C.c_int(int(with_eval_1)),
+                              C.c_int(n_threads), C.c_int(int(use_gfni)), _p(out))
+    v = to_ints(out)
+    return [[v[2 * c], v[2 * c + 1]] for c in range(n_out)]
+
+
+def cpu_chi_zerocheck_parallel(n_out: int, n_b: int, n_vars: int, budget_s: float = 6.0, n_threads: int = 0):
+    """Times all rounds of the chi-constraint zerocheck (round values + folds + eq halving) on this host."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    fn = lib().cpu_chi_zerocheck_bench
+    fn.restype = C.c_double
+    chk = np.zeros((1, 2), np.uint64)
+    args = (C.c_uint32(n_out), C.c_uint32(n_b), C.c_uint32(n_vars))
+    t1 = fn(*args, C.c_int(1), C.c_int(n_threads), C.c_int(1), _p(chk))
+    reps = max(1, min(10, int(budget_s / max(t1, 1e-4))))
+    t = fn(*args, C.c_int(reps), C.c_int(n_threads), C.c_int(1), _p(chk)) if reps > 1 else t1
+    return {"value": reps * n_vars / t, "unit": "rounds/s", "ms_per_sumcheck": t / reps * 1e3, "cores": n_threads, "kind": "port",
+            "sample": f"{reps} x zerocheck rounds over {n_out + n_b} multilinears of 2^{n_vars} B128 elements, {n_out} chi constraints, "
+                      f"{n_threads} threads; C restatement of the eq-ind evaluator loop (GFNI multiply), not the Rust binary"}
+
+
 # ------------------------------------------------------------------------------------------------
 # old HAL (ComputationBackend) restatements, oracle/hal.c
 def fold_left_lerp_inplace(evals, prefix: int, suffix: int, log_n: int, z: int):

@@ -207,3 +207,442 @@ double cpu_fold_chain_bench(uint32_t log_n, int reps, int n_threads, int use_gfn
 	free(buf);
 	return total;
 }
+
+/* =================================================================================================
+ * CPU arm of the additive NTT over B32 (BASELINE config #2 and the RS-encode phase of the keccak replay).
+ * "Port" of the reference's multithreaded NTT, crates/ntt/src/multithreaded.rs:100-228:
+ *   phase 1  the top `par_rounds` layers as strided column transforms, one stride of packed columns per thread
+ *   phase 2  one single-threaded transform (single_threaded.rs:134-246) per row chunk, coset = the row index
+ * on PackedBinaryField16x32b = one __m512i, twiddle broadcast per block (precomputed per-layer tables,
+ * twiddle.rs:324-353), multiply = the GFNI strategy above at tower level 5.  Requires log_x >= 4 (every run of
+ * butterflies sharing a twiddle is at least one 512-bit register long), which covers S1 and the RS-encode shapes.
+ * Checked against the scalar oracle NTT in tests/test_oracle_ops.py.
+ * ================================================================================================= */
+
+typedef struct {
+	uint32_t *data;
+	uint32_t log_x, log_y, skip;
+	const uint32_t *const *tw; /* tw[I][j]: twiddle of global layer I, block j (coset 0), I < log_y */
+	uint32_t par_rounds, log_rows_elems; /* phase 1: rows of 2^log_row elements */
+	uint64_t begin, end;                 /* phase 1: element-column range [begin, end) in units of 16 scalars; phase 2: chunk range */
+	int phase, gfni;
+	uint64_t t2a, a2t;
+} ntt_job;
+
+TGT static void ntt_butterfly_run_gfni(uint32_t *u, uint32_t *v, uint64_t n16, uint32_t t, uint64_t t2a, uint64_t a2t) {
+	const __m512i mt = _mm512_set1_epi64((long long)t2a), mb = _mm512_set1_epi64((long long)a2t);
+	const __m512i tv = _mm512_gf2p8affine_epi64_epi8(_mm512_set1_epi32((int)t), mt, 0);
+	for (uint64_t i = 0; i < n16; i++) {
+		__m512i a = _mm512_loadu_si512((const void *)(u + 16 * i));
+		__m512i b = _mm512_loadu_si512((const void *)(v + 16 * i));
+		__m512i p = _mm512_gf2p8affine_epi64_epi8(aes_mul5(_mm512_gf2p8affine_epi64_epi8(b, mt, 0), tv), mb, 0);
+		a = _mm512_xor_si512(a, p);
+		b = _mm512_xor_si512(b, a);
+		_mm512_storeu_si512((void *)(u + 16 * i), a);
+		_mm512_storeu_si512((void *)(v + 16 * i), b);
+	}
+}
+static void ntt_butterfly_run_scalar(uint32_t *u, uint32_t *v, uint64_t n, uint32_t t) {
+	for (uint64_t i = 0; i < n; i++) {
+		u[i] ^= (uint32_t)tower_mul(v[i], t, 5);
+		v[i] ^= u[i];
+	}
+}
+
+static void *ntt_worker(void *p) {
+	ntt_job *J = (ntt_job *)p;
+	const uint32_t lx = J->log_x, ly = J->log_y;
+	if (J->phase == 1) {
+		/* rows = the top par_rounds bits of y; a row holds 2^(lx + ly - par_rounds) scalars; this thread owns the
+		 * 16-scalar columns [begin, end) of every row */
+		const uint32_t pr = J->par_rounds, log_row = lx + ly - pr;
+		for (int i = (int)pr - 1 - (int)J->skip; i >= 0; i--) {
+			const uint32_t I = ly - pr + (uint32_t)i;
+			for (uint64_t k = 0; k < ((uint64_t)1 << (pr - 1 - i)); k++) {
+				const uint32_t t = J->tw[I][k];
+				for (uint64_t l = 0; l < ((uint64_t)1 << i); l++) {
+					uint64_t r0 = k << (i + 1) | l, r1 = r0 | (uint64_t)1 << i;
+					uint32_t *u = J->data + (r0 << log_row) + 16 * J->begin, *v = J->data + (r1 << log_row) + 16 * J->begin;
+					if (J->gfni) ntt_butterfly_run_gfni(u, v, J->end - J->begin, t, J->t2a, J->a2t);
+					else ntt_butterfly_run_scalar(u, v, 16 * (J->end - J->begin), t);
+				}
+			}
+		}
+	} else {
+		/* chunk c (a row of phase 1) = an independent transform of log_y' = ly - par_rounds layers with
+		 * coset = c, coset_bits = par_rounds, i.e. block index c << (ly'-1-i) | k of the global layer i */
+		const uint32_t pr = J->par_rounds, lyp = ly - pr, log_row = lx + lyp;
+		const uint32_t skip2 = J->skip > pr ? J->skip - pr : 0;
+		for (uint64_t c = J->begin; c < J->end; c++) {
+			uint32_t *chunk = J->data + (c << log_row);
+			for (int i = (int)lyp - 1 - (int)skip2; i >= 0; i--) {
+				const uint64_t run = (uint64_t)1 << (lx + i);
+				for (uint64_t k = 0; k < ((uint64_t)1 << (lyp - 1 - i)); k++) {
+					const uint32_t t = J->tw[i][c << (lyp - 1 - i) | k];
+					uint32_t *u = chunk + (k << (lx + i + 1)), *v = u + run;
+					if (J->gfni) ntt_butterfly_run_gfni(u, v, run / 16, t, J->t2a, J->a2t);
+					else ntt_butterfly_run_scalar(u, v, run, t);
+				}
+			}
+		}
+	}
+	return NULL;
+}
+
+/* forward transform, shape (log_x, log_y, 0), coset 0; s = the oracle's s_evals (orc_ntt_s_evals, kt = 5) */
+int cpu_ntt_forward(uint32_t *data, uint32_t log_x, uint32_t log_y, uint32_t skip, const u128u *s, uint32_t d, int n_threads, int use_gfni) {
+	tower_init();
+	if (log_x < 4 || log_y > d || skip > log_y) return 1;
+	int gfni = use_gfni && cpu_has_gfni512();
+	if (n_threads < 1) n_threads = 1;
+	uint32_t log_thr = 0;
+	while ((2u << log_thr) <= (uint32_t)n_threads) log_thr++;
+	/* precomputed twiddles per layer (PrecomputedTwiddleAccess) */
+	uint32_t **tw = malloc(sizeof(uint32_t *) * log_y);
+	const uint32_t W = d - 1, row0 = d - log_y;
+	for (uint32_t I = 0; I < log_y; I++) {
+		uint64_t n = (uint64_t)1 << (log_y - 1 - I);
+		tw[I] = malloc(sizeof(uint32_t) * n);
+		tw[I][0] = 0;
+		for (uint64_t j = 1; j < n; j++) {
+			uint32_t b = (uint32_t)__builtin_ctzll(j);
+			tw[I][j] = tw[I][j & (j - 1)] ^ (uint32_t)s[(row0 + I) * W + b];
+		}
+	}
+	/* multithreaded.rs:139-152 with P = 16 x 32b: log_w = 4 */
+	const uint32_t log_w = 4, total = log_x + log_y;
+	uint32_t min_lw = log_w + 1 > log_x ? log_w + 1 : log_x;
+	uint32_t log_height = total - min_lw < log_thr ? total - min_lw : log_thr;
+	uint32_t log_width = total - (log_w + log_height); /* packed elements per row */
+	uint32_t par_rounds = log_height;
+	pthread_t *th = malloc(sizeof(pthread_t) * n_threads);
+	ntt_job *jobs = malloc(sizeof(ntt_job) * n_threads);
+	for (int phase = 1; phase <= 2; phase++) {
+		uint64_t units = phase == 1 ? (uint64_t)1 << log_width : (uint64_t)1 << par_rounds;
+		if (phase == 1 && par_rounds <= skip) continue;
+		int started = 0;
+		for (int t = 0; t < n_threads; t++) {
+			uint64_t b = units * t / n_threads, e = units * (t + 1) / n_threads;
+			if (b == e) continue;
+			jobs[started] = (ntt_job){data, log_x, log_y, skip, (const uint32_t *const *)tw, par_rounds, 0, b, e, phase, gfni,
+									  affine_matrix(TOWER_TO_AES), affine_matrix(AES_TO_TOWER)};
+			pthread_create(&th[started], NULL, ntt_worker, &jobs[started]);
+			started++;
+		}
+		for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+	}
+	for (uint32_t I = 0; I < log_y; I++) free(tw[I]);
+	free(tw);
+	free(th);
+	free(jobs);
+	return 0;
+}
+
+/* timed loop for bench.py: forward NTT of 2^(log_x+log_y) B32 coefficients, `reps` times; returns seconds */
+double cpu_ntt_bench(uint32_t log_x, uint32_t log_y, uint32_t skip, int reps, int n_threads, const u128u *s, uint32_t d, int use_gfni) {
+	uint64_t n = (uint64_t)1 << (log_x + log_y);
+	uint32_t *buf = aligned_alloc(64, sizeof(uint32_t) * n);
+	uint64_t x = 0x9876543;
+	for (uint64_t i = 0; i < n; i++) {
+		x = x * 6364136223846793005ull + 1442695040888963407ull;
+		buf[i] = (uint32_t)(x >> 32);
+	}
+	cpu_ntt_forward(buf, log_x, log_y, skip, s, d, n_threads, use_gfni); /* warm-up, page-in */
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int r = 0; r < reps; r++) cpu_ntt_forward(buf, log_x, log_y, skip, s, d, n_threads, use_gfni);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	free(buf);
+	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* =================================================================================================
+ * CPU arm of the bivariate-product sumcheck data plane (v3::BivariateSumcheckProver over FastCpuLayer,
+ * core/src/protocols/sumcheck/v3/bivariate_product.rs:168-232, 303-408; the per-chunk kernel is
+ * fast_compute/src/layer.rs:797-846): per round the two batched sums over all compositions, then the fold of
+ * every multilinear.  Products on 4 x B128 per __m512i with the GFNI multiply; sums stay in the AES-tower basis
+ * (the basis change is GF(2)-linear) and are converted once per thread.
+ * ================================================================================================= */
+typedef struct {
+	u128u *const *mls;
+	uint64_t begin, end, half;
+	const uint32_t *ia, *ib;
+	uint32_t n_comp;
+	u128 *out; /* [2 * n_comp]: per composition sum at 1 and at infinity (tower basis) */
+	int gfni;
+} re_job;
+
+TGT static void round_evals_gfni(re_job *J) {
+	const __m512i t2a = _mm512_set1_epi64((long long)affine_matrix(TOWER_TO_AES));
+	const __m512i a2t = _mm512_set1_epi64((long long)affine_matrix(AES_TO_TOWER));
+	for (uint32_t c = 0; c < J->n_comp; c++) {
+		const u128u *a = J->mls[J->ia[c]], *b = J->mls[J->ib[c]];
+		__m512i s1 = _mm512_setzero_si512(), sinf = _mm512_setzero_si512();
+		uint64_t i = J->begin;
+		for (; i + 4 <= J->end; i += 4) {
+			__m512i alo = _mm512_loadu_si512((const void *)(a + i)), ahi = _mm512_loadu_si512((const void *)(a + J->half + i));
+			__m512i blo = _mm512_loadu_si512((const void *)(b + i)), bhi = _mm512_loadu_si512((const void *)(b + J->half + i));
+			__m512i xa = _mm512_gf2p8affine_epi64_epi8(ahi, t2a, 0), xb = _mm512_gf2p8affine_epi64_epi8(bhi, t2a, 0);
+			__m512i ya = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(alo, ahi), t2a, 0);
+			__m512i yb = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(blo, bhi), t2a, 0);
+			s1 = _mm512_xor_si512(s1, aes_mul7(xa, xb));
+			sinf = _mm512_xor_si512(sinf, aes_mul7(ya, yb));
+		}
+		u128 lanes[4], r1 = 0, rinf = 0;
+		_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(s1, a2t, 0));
+		r1 = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+		_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(sinf, a2t, 0));
+		rinf = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+		for (; i < J->end; i++) {
+			r1 ^= b128_mul(a[J->half + i], b[J->half + i]);
+			rinf ^= b128_mul(a[i] ^ a[J->half + i], b[i] ^ b[J->half + i]);
+		}
+		J->out[2 * c] = r1;
+		J->out[2 * c + 1] = rinf;
+	}
+}
+static void *re_worker(void *p) {
+	re_job *J = (re_job *)p;
+	if (J->gfni) {
+		round_evals_gfni(J);
+		return NULL;
+	}
+	for (uint32_t c = 0; c < J->n_comp; c++) {
+		const u128u *a = J->mls[J->ia[c]], *b = J->mls[J->ib[c]];
+		u128 r1 = 0, rinf = 0;
+		for (uint64_t i = J->begin; i < J->end; i++) {
+			r1 ^= b128_mul(a[J->half + i], b[J->half + i]);
+			rinf ^= b128_mul(a[i] ^ a[J->half + i], b[i] ^ b[J->half + i]);
+		}
+		J->out[2 * c] = r1;
+		J->out[2 * c + 1] = rinf;
+	}
+	return NULL;
+}
+
+/* [y_1, y_inf] of one round over m multilinears of 2^n_vars elements (bivariate_product.rs:303-408) */
+int cpu_bivariate_round_evals(u128u *const *mls, uint32_t n_vars, const uint32_t *ia, const uint32_t *ib, uint32_t n_comp,
+							  const u128u *batch_coeff, int n_threads, int use_gfni, u128u *out2) {
+	tower_init();
+	int gfni = use_gfni && cpu_has_gfni512();
+	uint64_t half = (uint64_t)1 << (n_vars - 1);
+	if (n_threads < 1 || half < (1u << 12)) n_threads = 1;
+	pthread_t *th = malloc(sizeof(pthread_t) * n_threads);
+	re_job *jobs = malloc(sizeof(re_job) * n_threads);
+	u128 *parts = calloc((size_t)2 * n_comp * n_threads, sizeof(u128));
+	int started = 0;
+	for (int t = 0; t < n_threads; t++) {
+		uint64_t b = (half * t / n_threads) & ~3ull, e = t + 1 == n_threads ? half : (half * (t + 1) / n_threads) & ~3ull;
+		if (b >= e) continue;
+		jobs[started] = (re_job){mls, b, e, half, ia, ib, n_comp, parts + (size_t)2 * n_comp * started, gfni};
+		if (n_threads == 1) re_worker(&jobs[started]);
+		else pthread_create(&th[started], NULL, re_worker, &jobs[started]);
+		started++;
+	}
+	if (n_threads > 1)
+		for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+	u128 y1 = 0, yinf = 0, pw = 1;
+	for (uint32_t c = 0; c < n_comp; c++) {
+		u128 s1 = 0, sinf = 0;
+		for (int t = 0; t < started; t++) {
+			s1 ^= parts[(size_t)2 * n_comp * t + 2 * c];
+			sinf ^= parts[(size_t)2 * n_comp * t + 2 * c + 1];
+		}
+		y1 ^= b128_mul(s1, pw);
+		yinf ^= b128_mul(sinf, pw);
+		pw = b128_mul(pw, *batch_coeff);
+	}
+	out2[0] = y1;
+	out2[1] = yinf;
+	free(th);
+	free(jobs);
+	free(parts);
+	return gfni;
+}
+
+/* timed loop for bench.py: the whole sumcheck (n_vars rounds of round evaluations + fold of every multilinear)
+ * over m multilinears and n_comp index pairs, `reps` times; returns seconds.  Writes a checksum of the round values. */
+double cpu_bivariate_sumcheck_bench(uint32_t m, uint32_t n_vars, uint32_t n_comp, int reps, int n_threads, int use_gfni, u128u *checksum) {
+	uint64_t n = (uint64_t)1 << n_vars;
+	u128u **src = malloc(sizeof(u128u *) * m), **buf = malloc(sizeof(u128u *) * m);
+	uint64_t s = 0x7777777;
+	for (uint32_t t = 0; t < m; t++) {
+		src[t] = aligned_alloc(64, sizeof(u128) * n);
+		buf[t] = aligned_alloc(64, sizeof(u128) * n);
+		for (uint64_t i = 0; i < n; i++) {
+			s = s * 6364136223846793005ull + 1442695040888963407ull;
+			src[t][i] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+		}
+	}
+	uint32_t *ia = malloc(4 * n_comp), *ib = malloc(4 * n_comp);
+	for (uint32_t c = 0; c < n_comp; c++) {
+		ia[c] = (c * 5 + 1) % m;
+		ib[c] = (c * 3 + 2) % m;
+	}
+	u128 alpha = ((u128)0x0123456789ABCDEFull << 64) | 0x0F1E2D3C4B5A6978ull, z = ((u128)0x2E895399AF449ACEull << 64) | 0x499596F6E5FCCAFAull;
+	u128 acc = 0;
+	double total = 0;
+	for (int r = -1; r < reps; r++) {
+		for (uint32_t t = 0; t < m; t++) memcpy(buf[t], src[t], sizeof(u128) * n);
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		for (uint32_t v = n_vars; v >= 1; v--) {
+			u128 y[2];
+			cpu_bivariate_round_evals(buf, v, ia, ib, n_comp, (const u128u *)&alpha, n_threads, use_gfni, (u128u *)y);
+			acc ^= y[0] ^ (y[1] << 1);
+			uint64_t half = (uint64_t)1 << (v - 1);
+			for (uint32_t t = 0; t < m; t++) cpu_fold(buf[t], buf[t] + half, half, (const u128u *)&z, half >= (1u << 13) ? n_threads : 1, use_gfni);
+			z = z * 3 + 1;
+		}
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (r >= 0) total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+	}
+	if (checksum) *checksum = acc;
+	for (uint32_t t = 0; t < m; t++) {
+		free(src[t]);
+		free(buf[t]);
+	}
+	free(src);
+	free(buf);
+	free(ia);
+	free(ib);
+	return total;
+}
+
+/* =================================================================================================
+ * CPU arm of the zerocheck multilinear rounds of the keccak chi constraints (keccak replay, phase
+ * "zerocheck_rounds"): port of the eq-ind evaluator's hot loop (hal/src/sumcheck_round_calculation.rs:222-297
+ * with core/src/protocols/sumcheck/prove/eq_ind.rs:646-731): per round and constraint
+ *     C = out - (b0 + (b1 - 1) * b2)      at 1:        sum_i E[i] * C(hi[i])
+ *                                         at infinity: sum_i E[i] * (b1' * b2')[i],  x' = hi - lo  (leading term)
+ * then the fold of every multilinear and the halving of the eq-indicator.  GFNI multiply on 4 x B128 per register;
+ * operands are converted to the AES-tower basis once per (column, chunk) the way the reference's batch_evaluate
+ * works on packed slices.  Constraint c reads out = col[c], b_k = col[n_out + (c + k) % n_b].
+ * ================================================================================================= */
+typedef struct {
+	u128u *const *cols;
+	const u128u *eq;
+	uint64_t begin, end, half;
+	uint32_t n_out, n_b;
+	int with_eval_1;
+	u128 *out; /* [2 * n_out] */
+} chi_job;
+
+TGT static void *chi_worker_gfni(void *p) {
+	chi_job *J = (chi_job *)p;
+	const __m512i t2a = _mm512_set1_epi64((long long)affine_matrix(TOWER_TO_AES));
+	const __m512i a2t = _mm512_set1_epi64((long long)affine_matrix(AES_TO_TOWER));
+	const __m512i one = _mm512_gf2p8affine_epi64_epi8(_mm512_broadcast_i32x4(_mm_set_epi32(0, 0, 0, 1)), t2a, 0);
+	for (uint32_t c = 0; c < J->n_out; c++) {
+		const u128u *o = J->cols[c], *b0 = J->cols[J->n_out + c % J->n_b], *b1 = J->cols[J->n_out + (c + 1) % J->n_b], *b2 = J->cols[J->n_out + (c + 2) % J->n_b];
+		__m512i s1 = _mm512_setzero_si512(), sinf = _mm512_setzero_si512();
+		for (uint64_t i = J->begin; i + 4 <= J->end; i += 4) {
+			const uint64_t h = J->half + i;
+			__m512i e = _mm512_gf2p8affine_epi64_epi8(_mm512_loadu_si512((const void *)(J->eq + i)), t2a, 0);
+			__m512i b1h = _mm512_loadu_si512((const void *)(b1 + h)), b2h = _mm512_loadu_si512((const void *)(b2 + h));
+			__m512i b1p = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(b1h, _mm512_loadu_si512((const void *)(b1 + i))), t2a, 0);
+			__m512i b2p = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(b2h, _mm512_loadu_si512((const void *)(b2 + i))), t2a, 0);
+			sinf = _mm512_xor_si512(sinf, aes_mul7(e, aes_mul7(b1p, b2p)));
+			if (J->with_eval_1) {
+				__m512i x1 = _mm512_xor_si512(_mm512_gf2p8affine_epi64_epi8(b1h, t2a, 0), one), x2 = _mm512_gf2p8affine_epi64_epi8(b2h, t2a, 0);
+				__m512i lin = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(_mm512_loadu_si512((const void *)(o + h)), _mm512_loadu_si512((const void *)(b0 + h))), t2a, 0);
+				s1 = _mm512_xor_si512(s1, aes_mul7(e, _mm512_xor_si512(lin, aes_mul7(x1, x2))));
+			}
+		}
+		u128 lanes[4];
+		_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(s1, a2t, 0));
+		J->out[2 * c] = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+		_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(sinf, a2t, 0));
+		J->out[2 * c + 1] = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+	}
+	return NULL;
+}
+static void *chi_worker_scalar(void *p) {
+	chi_job *J = (chi_job *)p;
+	for (uint32_t c = 0; c < J->n_out; c++) {
+		const u128u *o = J->cols[c], *b0 = J->cols[J->n_out + c % J->n_b], *b1 = J->cols[J->n_out + (c + 1) % J->n_b], *b2 = J->cols[J->n_out + (c + 2) % J->n_b];
+		u128 s1 = 0, sinf = 0;
+		for (uint64_t i = J->begin; i < J->end; i++) {
+			const uint64_t h = J->half + i;
+			sinf ^= b128_mul(J->eq[i], b128_mul(b1[h] ^ b1[i], b2[h] ^ b2[i]));
+			if (J->with_eval_1) s1 ^= b128_mul(J->eq[i], o[h] ^ b0[h] ^ b128_mul(b1[h] ^ 1, b2[h]));
+		}
+		J->out[2 * c] = s1;
+		J->out[2 * c + 1] = sinf;
+	}
+	return NULL;
+}
+
+/* round values [constraint][at 1, at infinity] of one round; half a multiple of 4 or below 4 (scalar) */
+int cpu_chi_round_evals(u128u *const *cols, uint32_t n_out, uint32_t n_b, uint32_t n_vars, const u128u *eq, int with_eval_1, int n_threads,
+						int use_gfni, u128u *out /* 2 * n_out */) {
+	tower_init();
+	uint64_t half = (uint64_t)1 << (n_vars - 1);
+	int gfni = use_gfni && cpu_has_gfni512() && half >= 4;
+	if (n_threads < 1 || half < (1u << 10)) n_threads = 1;
+	pthread_t *th = malloc(sizeof(pthread_t) * n_threads);
+	chi_job *jobs = malloc(sizeof(chi_job) * n_threads);
+	u128 *parts = calloc((size_t)2 * n_out * n_threads, sizeof(u128));
+	int started = 0;
+	for (int t = 0; t < n_threads; t++) {
+		uint64_t b = (half * t / n_threads) & ~3ull, e = t + 1 == n_threads ? half : (half * (t + 1) / n_threads) & ~3ull;
+		if (b >= e) continue;
+		jobs[started] = (chi_job){cols, eq, b, e, half, n_out, n_b, with_eval_1, parts + (size_t)2 * n_out * started};
+		if (n_threads == 1) (gfni ? chi_worker_gfni : chi_worker_scalar)(&jobs[started]);
+		else pthread_create(&th[started], NULL, gfni ? chi_worker_gfni : chi_worker_scalar, &jobs[started]);
+		started++;
+	}
+	if (n_threads > 1)
+		for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+	for (uint32_t k = 0; k < 2 * n_out; k++) {
+		u128 s = 0;
+		for (int t = 0; t < started; t++) s ^= parts[(size_t)2 * n_out * t + k];
+		out[k] = s;
+	}
+	free(th);
+	free(jobs);
+	free(parts);
+	return gfni;
+}
+
+/* timed loop: all n_vars rounds (round values, fold of the n_out + n_b multilinears, eq halving), `reps` times */
+double cpu_chi_zerocheck_bench(uint32_t n_out, uint32_t n_b, uint32_t n_vars, int reps, int n_threads, int use_gfni, u128u *checksum) {
+	const uint32_t m = n_out + n_b;
+	uint64_t n = (uint64_t)1 << n_vars;
+	u128u **buf = malloc(sizeof(u128u *) * m);
+	u128u *eq = aligned_alloc(64, sizeof(u128) * (n / 2 > 4 ? n / 2 : 4));
+	u128 *vals = malloc(sizeof(u128) * 2 * n_out);
+	uint64_t s = 0x5151515;
+	for (uint32_t t = 0; t < m; t++) buf[t] = aligned_alloc(64, sizeof(u128) * n);
+	u128 z = ((u128)0x2E895399AF449ACEull << 64) | 0x499596F6E5FCCAFAull, acc = 0;
+	double total = 0;
+	for (int r = -1; r < reps; r++) {
+		for (uint32_t t = 0; t < m; t++)
+			for (uint64_t i = 0; i < n; i++) {
+				s = s * 6364136223846793005ull + 1442695040888963407ull;
+				buf[t][i] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+			}
+		for (uint64_t i = 0; i < n / 2; i++) {
+			s = s * 6364136223846793005ull + 1442695040888963407ull;
+			eq[i] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+		}
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		for (uint32_t v = n_vars; v >= 1; v--) {
+			cpu_chi_round_evals(buf, n_out, n_b, v, eq, v != n_vars, n_threads, use_gfni, (u128u *)vals);
+			for (uint32_t k = 0; k < 2 * n_out; k++) acc ^= vals[k];
+			uint64_t half = (uint64_t)1 << (v - 1);
+			for (uint32_t t = 0; t < m; t++) cpu_fold(buf[t], buf[t] + half, half, (const u128u *)&z, half >= (1u << 13) ? n_threads : 1, use_gfni);
+			for (uint64_t i = 0; i < half / 2; i++) eq[i] ^= eq[half / 2 + i]; /* fold_partial_eq_ind: E'[i] = E[i] + E[half + i] */
+			z = z * 3 + 1;
+		}
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (r >= 0) total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+	}
+	if (checksum) *checksum = acc;
+	for (uint32_t t = 0; t < m; t++) free(buf[t]);
+	free(buf);
+	free(eq);
+	free(vals);
+	return total;
+}

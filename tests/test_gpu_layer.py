@@ -498,3 +498,78 @@ def test_inner_product_b128_large(hal, oracle):
         da, db = hal.to_device(a), hal.to_device(b)
         got = hal.execute(lambda ex: [ex.inner_product(binius_b200.SubfieldSlice(da, 7), db)])
         assert got == [oracle.inner_product(a, 7, b)]
+
+
+@pytest.mark.parametrize("n_vars", [3, 9, 13])
+def test_kernel_scope_general_programs(hal, oracle, n_vars):
+    """accumulate_kernels programs other than the prover's bivariate closure (layer.rs:134-245): degree-1 and constant
+    monomials, a scaled monomial, a square, add_assign into a Local, a sum over a Local before and after it is written
+    (fused lowering), and a program that writes a ChunkedMut buffer (runs op by op).  Checked against the oracle's
+    sum_composition_evals on host-side copies of the buffers."""
+    import random
+
+    import binius_b200
+    from binius_b200 import ArithCircuit as A
+
+    rng = random.Random(900 + n_vars)
+    n = 1 << n_vars
+    m = 3
+    host = [oracle.rand_b128(700 + t, n) for t in range(m)]
+    dev = [hal.to_device(x) for x in host]
+    M, SB = binius_b200.KernelMemMap, binius_b200.SlicesBatch
+    exprs = [A.var(0) * A.var(1) + A.var(2) + A.constant(rng.getrandbits(128)),
+             A.constant(rng.getrandbits(128)) * A.var(2) * A.var(2) + A.var(0),
+             A.var(1)]
+    evs = [hal.compile_expr(e) for e in exprs]
+    coeffs = [rng.getrandbits(128) for _ in exprs]
+    init = rng.getrandbits(128)
+    xor = lambda a, b: a ^ b  # noqa: E731
+
+    # (1) fusable: sums over mapped buffers, add into Locals, sums over the Locals
+    def kern(kex, log_chunks, bufs):
+        a, b, c, l0, l1, l2 = bufs
+        acc = kex.decl_value(init)
+        for ev, cf in zip(evs, coeffs):
+            kex.sum_composition_evals(SB([a.to_ref(), b.to_ref(), c.to_ref()], n), ev, cf, acc)
+        kex.add(n_vars, a.to_ref(), b.to_ref(), l0.data)
+        kex.add(n_vars, b.to_ref(), c.to_ref(), l1.data)
+        kex.add(n_vars, c.to_ref(), a.to_ref(), l2.data)
+        acc2 = kex.decl_value(0)
+        for ev, cf in zip(evs, coeffs):
+            kex.sum_composition_evals(SB([l0.to_ref(), l1.to_ref(), c.to_ref()], n), ev, cf, acc2)
+        kex.sum_composition_evals(SB([l2.to_ref(), l2.to_ref(), l0.to_ref()], n), evs[0], coeffs[1], acc2)
+        return [acc, acc2]
+
+    maps = [M.Chunked(d, 0) for d in dev] + [M.Local(n_vars)] * 3
+    got = hal.execute(lambda ex: ex.accumulate_kernels(kern, maps))
+    l0, l1, l2 = host[0] ^ host[1], host[1] ^ host[2], host[2] ^ host[0]
+    exp1 = init
+    for e, cf in zip(exprs, coeffs):
+        exp1 = oracle.sum_composition_evals(host, e.steps, cf, exp1)
+    exp2 = 0
+    for e, cf in zip(exprs, coeffs):
+        exp2 = oracle.sum_composition_evals([l0, l1, host[2]], e.steps, cf, exp2)
+    exp2 = oracle.sum_composition_evals([l2, l2, l0], exprs[0].steps, coeffs[1], exp2)
+    assert got == [exp1, exp2]
+
+    # (2) not fusable: add_assign into a Local that is read before (zero) and after, and a write into a ChunkedMut buffer
+    out = hal.dev_alloc(n)
+    hal.fill(out, 0)
+
+    def kern2(kex, log_chunks, bufs):
+        a, b, c, o, l0 = bufs
+        acc = kex.decl_value(0)
+        kex.sum_composition_evals(SB([l0.to_ref(), a.to_ref(), b.to_ref()], n), evs[0], coeffs[0], acc)  # Local still zero
+        kex.add_assign(n_vars, a.to_ref(), l0.data)
+        kex.add_assign(n_vars, b.to_ref(), l0.data)
+        kex.sum_composition_evals(SB([l0.to_ref(), a.to_ref(), b.to_ref()], n), evs[0], coeffs[2], acc)
+        kex.add(n_vars, l0.to_ref(), c.to_ref(), o.data)
+        return [acc]
+
+    maps2 = [M.Chunked(d, 0) for d in dev] + [M.ChunkedMut(out, 0), M.Local(n_vars)]
+    got2 = hal.execute(lambda ex: ex.accumulate_kernels(kern2, maps2))
+    zero = np.zeros_like(host[0])
+    e = oracle.sum_composition_evals([zero, host[0], host[1]], exprs[0].steps, coeffs[0], 0)
+    e = oracle.sum_composition_evals([l0, host[0], host[1]], exprs[0].steps, coeffs[2], e)
+    assert got2 == [e]
+    assert np.array_equal(hal.to_host(out), l0 ^ host[2])

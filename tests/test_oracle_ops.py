@@ -360,6 +360,45 @@ def test_cpu_baseline_matches_oracle(oracle):
             assert np.array_equal(got, exp)
 
 
+def test_cpu_ntt_and_round_eval_arms_match_oracle(oracle):
+    """the timed CPU arms of the NTT (port of crates/ntt/src/multithreaded.rs:100-228) and of the bivariate round
+    evaluations (fast_compute/src/layer.rs:797-846) are bit-identical to the scalar oracle, GFNI and scalar, any thread count"""
+    import random
+
+    o = oracle
+    rng = np.random.default_rng(1)
+    for (lx, ly, skip, thr) in [(4, 6, 0, 1), (6, 10, 1, 3), (5, 9, 0, 8), (6, 12, 2, 8), (4, 13, 0, 5)]:
+        a = rng.integers(0, 1 << 32, size=1 << (lx + ly), dtype=np.uint64).astype(np.uint32)
+        exp = o.NTT(5, 16).forward(a, 5, lx, ly, 0, 0, 0, skip)
+        for gfni in (True, False):
+            assert np.array_equal(o.cpu_ntt_forward(a, lx, ly, skip, 16, thr, gfni), exp), (lx, ly, skip, thr, gfni)
+    r = random.Random(2)
+    for nv, m, thr in [(4, 3, 1), (13, 4, 3), (14, 5, 8)]:
+        mls = [o.rand_b128(50 + t, 1 << nv) for t in range(m)]
+        pairs = [(r.randrange(m), r.randrange(m)) for _ in range(5)]
+        al = r.getrandbits(128)
+        exp = list(o.bivariate_round_evals(mls, nv, pairs, al))
+        for gfni in (True, False):
+            assert list(o.cpu_bivariate_round_evals(mls, nv, pairs, al, thr, gfni)) == exp, (nv, m, thr, gfni)
+
+
+def test_cpu_chi_zerocheck_arm_matches_oracle(oracle):
+    """the timed CPU arm of the keccak chi zerocheck rounds against the generic eq-ind evaluator restatement"""
+    from binius_b200 import ArithCircuit as A
+
+    o = oracle
+    n_out, n_b = 5, 7
+    for nv, thr in [(3, 1), (11, 3), (12, 8)]:
+        cols = [o.rand_b128(900 + t, 1 << nv) for t in range(n_out + n_b)]
+        eq = o.rand_b128(77, 1 << (nv - 1))
+        v = [A.var(i) for i in range(n_out + n_b)]
+        comps = [v[c] - (v[n_out + c % n_b] + (v[n_out + (c + 1) % n_b] - A.one()) * v[n_out + (c + 2) % n_b]) for c in range(n_out)]
+        exp = o.eq_ind_round_evals(cols, [len(c) for c in cols], [0] * len(cols), nv, eq, [c.steps for c in comps],
+                                   [c.leading_term().steps for c in comps], [1, 2], [0, 0])
+        for gfni in (True, False):
+            assert o.cpu_chi_round_evals(cols, n_out, n_b, nv, eq, True, thr, gfni) == [list(e) for e in exp], (nv, thr, gfni)
+
+
 def _bitrev(i, n):
     return int(format(i, f"0{n}b")[::-1], 2) if n else 0
 

@@ -168,7 +168,7 @@ def test_round_eval_extension_equals_the_reference_ntt_route(oracle, skip, degre
         assert oracle.extrapolate_round_evals(stag, skip, degree, max_domain) == full[K:max_domain]
 
 
-@pytest.mark.parametrize("skip,n_vars,threads", [(3, 8, 1), (4, 9, 3), (6, 10, 2)])
+@pytest.mark.parametrize("skip,n_vars,threads", [(3, 8, 1), (4, 9, 3), (6, 10, 2), (7, 10, 3)])
 def test_threaded_cpu_arm_matches_the_oracle(oracle, skip, n_vars, threads):
     """oracle/cpu_univariate.c (the timed CPU baseline of the univariate-skip round) against the definition."""
     rng = random.Random(500 + skip)

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <string>
 
+#include "../binius_b200/csrc/host_field.hpp"
 #include "../binius_b200/host/computation_backend.hpp"
 
 using namespace binius_b200;
@@ -20,6 +21,11 @@ static uint64_t splitmix() {
 	return z ^ (z >> 31);
 }
 static F128 rnd() { return F128{splitmix(), splitmix()}; }
+static F128 host_mul(F128 a, F128 b) {  // batch-coefficient powers (host scalar work of the prover)
+	using b200::hostf::u128;
+	u128 p = b200::hostf::mul128(((u128)a.hi << 64) | a.lo, ((u128)b.hi << 64) | b.lo);
+	return F128{(uint64_t)p, (uint64_t)(p >> 64)};
+}
 
 struct Timer {
 	B200Layer &hal;
@@ -102,11 +108,47 @@ int main(int argc, char **argv) {
 	DevSlice arena = hal.dev_alloc(arena_elems);
 	hal.fill(arena, F128{0xFEDCBA9876543211ull, 0x0123456789ABCDEFull});
 	Timer t(hal);
-	double ntt_ms = 0, zc_ev = 0, zc_fold = 0, pi_ev = 0, pi_fold = 0, fri_ms = 0, rs_ms = 0;
+	double ntt_ms = 0, zc_ev = 0, zc_fold = 0, pi_ev = 0, pi_fold = 0, fri_ms = 0, rs_ms = 0, up_ms = 0, uni_ms = 0;
 	uint64_t launches = 0;
+	// the B1 witness columns of the zerocheck (153 columns of 2^(log_n + 9) bits) in pinned host memory
+	const uint32_t n_cols = 153, uni_vars = log_n + 9, uni_skip = 7;
+	const uint64_t col_words = 1ull << (uni_vars - 7);
+	void *h_wit = nullptr;
+	hal.check(b200_host_alloc(hal.ctx(), n_cols * col_words * 16, &h_wit));
+	{
+		uint64_t *w = (uint64_t *)h_wit;
+		for (uint64_t i = 0; i < n_cols * col_words * 2; i++) w[i] = splitmix();
+	}
+	DevSlice d_wit = hal.dev_alloc(n_cols * col_words);
 	for (int pass = 0; pass < 2; pass++) {  // pass 0 warms the context, pass 1 is reported
-		ntt_ms = zc_ev = zc_fold = pi_ev = pi_fold = fri_ms = rs_ms = 0;
+		ntt_ms = zc_ev = zc_fold = pi_ev = pi_fold = fri_ms = rs_ms = up_ms = uni_ms = 0;
 		launches = 0;
+		// ---- witness upload: the committed / constrained B1 columns cross PCIe once (ComputeLayer::copy_h2d)
+		{
+			t.start();
+			hal.check(b200_copy_h2d(hal.ctx(), h_wit, d_wit.ptr, n_cols * col_words));
+			up_ms = t.stop(&launches);
+		}
+		// ---- zerocheck univariate-skip round: skip 7 (constraint_system/verify.rs:271-294), 75 chi constraints, domain 256
+		{
+			std::vector<SumcheckMultilinear> cols;
+			for (uint32_t j = 0; j < n_cols; j++) cols.push_back(SumcheckMultilinear::transparent(d_wit.slice(j * col_words, (j + 1) * col_words), 0, uni_vars, 0));
+			std::vector<ExprEval> comps;
+			for (uint32_t c = 0; c < 75; c++) {
+				const uint32_t o = c, b0 = 75 + (c % 26), b1 = 75 + ((c + 1) % 26), b2 = 75 + ((c + 2) % 26);
+				comps.push_back(hal.compile_expr({ExprStep::var(o), ExprStep::var(b0), ExprStep::var(b1), ExprStep::constant(F128{1, 0}), ExprStep::add(2, 3),
+												  ExprStep::var(b2), ExprStep::mul(4, 5), ExprStep::add(1, 6), ExprStep::add(0, 7)}));
+			}
+			std::vector<const ExprEval *> cp;
+			for (auto &c : comps) cp.push_back(&c);
+			std::vector<uint32_t> deg(75, 2);
+			std::vector<F128> ch(uni_vars - uni_skip);
+			for (auto &x : ch) x = rnd();
+			auto w0 = std::chrono::steady_clock::now();
+			auto out = zerocheck_univariate_evals(be, cols, cp, deg, ch, uni_skip, 256);  // synchronous: returns host values
+			uni_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+			hal.dev_free(out.partial_eq_ind_evals);
+		}
 		// ---- commit: RS-encode NTT (log_x = 6, log_y = log_n + 6, skip 1) on the device codeword
 		{
 			B200Ntt ntt(hal, 5, log_n + 6);
@@ -151,6 +193,8 @@ int main(int argc, char **argv) {
 			for (uint32_t i = 0; i < m; i++) mls.push_back(SumcheckMultilinear::folded(arena.slice((uint64_t)i << nv, (uint64_t)(i + 1) << nv)));
 			std::vector<uint32_t> ia(100), ib(100);
 			for (uint32_t i = 0; i < 100; i++) { ia[i] = i; ib[i] = 100 + i; }
+			std::vector<ExprEval> pair_exprs;  // IndexComposition<BivariateProduct>: Var(i0) * Var(i1) over all multilinears
+			for (uint32_t i = 0; i < 100; i++) pair_exprs.push_back(hal.compile_expr({ExprStep::var(ia[i]), ExprStep::var(ib[i]), ExprStep::mul(0, 1)}));
 			for (uint32_t rnd_i = 0; rnd_i < nv; rnd_i++) {
 				const uint32_t v = nv - rnd_i;
 				std::vector<b200_dev_ptr> ptrs;
@@ -159,7 +203,27 @@ int main(int argc, char **argv) {
 				uint32_t s1, s2;
 				t.start();
 				hal.check(b200_results_reset(hal.ctx()));
-				hal.check(b200_bivariate_round_evals(hal.ctx(), ptrs.data(), m, v, ia.data(), ib.data(), 100, &alpha.lo, &s1, &s2));
+				// the literal accumulate_kernels closure of v3::calculate_round_evals (bivariate_product.rs:343-405) through a kernel
+				// scope: sums over the high halves, add(lo, hi) into the Locals, sums over the Locals
+				const uint64_t half = 1ull << (v - 1);
+				hal.check(b200_kernel_scope_begin(hal.ctx()));
+				std::vector<b200_dev_ptr> his(m), infs(m);
+				for (uint32_t i = 0; i < m; i++) {
+					his[i] = (uint8_t *)ptrs[i] + 16 * half;
+					hal.check(b200_kernel_local(hal.ctx(), v - 1, &infs[i]));
+				}
+				F128 zero{}, pw{1, 0};
+				hal.check(b200_kernel_decl_value(hal.ctx(), &zero.lo, &s1));
+				std::vector<F128> pws(100);
+				for (uint32_t c = 0; c < 100; c++) {
+					pws[c] = pw;
+					pw = host_mul(pw, alpha);
+					hal.check(b200_kernel_sum_composition_evals(hal.ctx(), his.data(), m, half, pair_exprs[c].raw(), &pws[c].lo, s1));
+				}
+				for (uint32_t i = 0; i < m; i++) hal.check(b200_kernel_add(hal.ctx(), v - 1, ptrs[i], his[i], infs[i]));
+				hal.check(b200_kernel_decl_value(hal.ctx(), &zero.lo, &s2));
+				for (uint32_t c = 0; c < 100; c++) hal.check(b200_kernel_sum_composition_evals(hal.ctx(), infs.data(), m, half, pair_exprs[c].raw(), &pws[c].lo, s2));
+				hal.check(b200_kernel_scope_end(hal.ctx()));
 				uint32_t slots[2] = {s1, s2};
 				F128 out[2];
 				hal.check(b200_results_fetch(hal.ctx(), slots, 2, &out[0].lo));
@@ -216,11 +280,12 @@ int main(int argc, char **argv) {
 			hal.dev_free(q);
 		}
 	}
-	const double total = ntt_ms + zc_ev + zc_fold + pi_ev + pi_fold + fri_ms + rs_ms;
+	const double total = up_ms + uni_ms + ntt_ms + zc_ev + zc_fold + pi_ev + pi_fold + fri_ms + rs_ms;
 	printf("{\"workload\": \"keccak op-sequence replay (compiled host), n_permutations = 2^%u (synthetic data)\", \"phases\": {"
+		   "\"witness_upload\": {\"ms\": %.3f, \"h2d_bytes\": %llu}, \"zerocheck_univariate_skip_round\": {\"ms\": %.3f}, "
 		   "\"commit_rs_encode_ntt\": {\"ms\": %.3f}, \"zerocheck_rounds\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, "
 		   "\"piop_bivariate_sumcheck\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, \"fri_folds\": {\"ms\": %.3f}, "
 		   "\"ring_switch_eq_inds\": {\"ms\": %.3f}}, \"total_ms\": %.3f, \"gpu_launches\": %llu}\n",
-		   log_n, ntt_ms, zc_ev, zc_fold, zc_ev + zc_fold, pi_ev, pi_fold, pi_ev + pi_fold, fri_ms, rs_ms, total, (unsigned long long)launches);
+		   log_n, up_ms, (unsigned long long)(n_cols * col_words * 16), uni_ms, ntt_ms, zc_ev, zc_fold, zc_ev + zc_fold, pi_ev, pi_fold, pi_ev + pi_fold, fri_ms, rs_ms, total, (unsigned long long)launches);
 	return 0;
 }
