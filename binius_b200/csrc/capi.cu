@@ -361,6 +361,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
 	SET(k_fold_right_lut, LUT_BYTES + 2048);
 	SET(k_fold_left_b1_lut, LUT_BYTES + 2048);
+	SET(k_linear_map, LUT_BYTES + 2048);
 	SET(k_fold_mat<true>, FIELD_TABLE_BYTES);
 	SET(k_compute_composite, FIELD_TABLE_BYTES);
 	SET(k_sum_composition, FIELD_TABLE_BYTES);
@@ -943,6 +944,70 @@ int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t
 }
 int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
 	return fold_mat(ctx, true, mat, n_mat, lvl, vec, n_vec, out, n_out);
+}
+
+// ---- GF(2)-linear maps on B128 (basis changes) ------------------------------------------------------
+int32_t b200_linear_map(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n, const uint64_t *basis_images) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !basis_images) return B200_ERR_INPUT_VALIDATION;
+	if (n == 0) return B200_OK;
+	const uint8_t *a = (const uint8_t *)src, *b = (const uint8_t *)dst;
+	if (a != b && a < b + n * 16 && b < a + n * 16) return fail(ctx, B200_ERR_INPUT_VALIDATION, "linear_map: partially overlapping source and destination");
+	void *dw;
+	int32_t rc = stage_args(ctx, basis_images, 128 * 16, &dw);
+	if (rc) return rc;
+	k_linear_map<<<grid_for(ctx, n, FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const uint4 *)src, (const uint4 *)dw, (uint4 *)dst, n);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+
+// BinaryField128bPolyval (field/src/polyval.rs): GF(2)[X] / (X^128 + X^127 + X^126 + X^121 + 1), elements stored in
+// Montgomery form; product = a * b * X^-128 (arch/portable/packed_polyval_128.rs:88-122).  Host-side, bit-serial: used
+// for one-off scalar work only (deriving the basis change, converting round values).
+void b200_host_polyval_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+	const hostf::u128 p = hostf::polyval_mul(hostf::from_words(a), hostf::from_words(b));
+	out[0] = (uint64_t)p;
+	out[1] = (uint64_t)(p >> 64);
+}
+// The tower <-> POLYVAL isomorphism as 128 basis images each way (images[k] = phi(beta_k), 2 words per image),
+// DERIVED from the two published multiplicative generators (binary_field.rs:747, polyval.rs:496): phi is the field
+// isomorphism with phi(g_tower) = g_polyval, so phi(sum_k c_k g^k) = sum_k c_k g'^k; the coordinates of beta_i in the
+// power basis of g come from inverting a 128 x 128 GF(2) matrix.  tests/ compare the result with the reference's
+// BINARY_TO_POLYVAL_TRANSFORMATION / POLYVAL_TO_BINARY_TRANSFORMATION tables (polyval.rs:516-788).
+int32_t b200_host_polyval_basis_change(uint64_t tower_to_polyval[256], uint64_t polyval_to_tower[256]) {
+	using hostf::u128;
+	const u128 g_t = ((u128)0x2E895399AF449ACEull << 64) | 0x499596F6E5FCCAFAull;  // BinaryField128b::MULTIPLICATIVE_GENERATOR
+	const u128 g_p = ((u128)0x072bdf2504ce49c0ull << 64) | 0x3105433c1c25a4a7ull;  // BinaryField128bPolyval::MULTIPLICATIVE_GENERATOR (stored form)
+	const u128 one_p = ((u128)0xc200000000000000ull << 64) | 1ull;                 // BinaryField128bPolyval::ONE (X^128 mod p)
+	u128 pw_t[128], pw_p[128];
+	pw_t[0] = 1, pw_p[0] = one_p;
+	for (int k = 1; k < 128; k++) {
+		pw_t[k] = hostf::mul128(pw_t[k - 1], g_t);
+		pw_p[k] = hostf::polyval_mul(pw_p[k - 1], g_p);
+	}
+	auto solve = [](const u128 *from, const u128 *to, uint64_t *out) -> bool {
+		// rows: (from[k] | to[k]); Gaussian elimination brings `from` to the identity, `to` then holds the images
+		u128 a[128], b[128];
+		for (int k = 0; k < 128; k++) a[k] = from[k], b[k] = to[k];
+		for (int col = 0; col < 128; col++) {
+			int piv = -1;
+			for (int r = col; r < 128; r++)
+				if ((a[r] >> col) & 1) {
+					piv = r;
+					break;
+				}
+			if (piv < 0) return false;
+			std::swap(a[piv], a[col]);
+			std::swap(b[piv], b[col]);
+			for (int r = 0; r < 128; r++)
+				if (r != col && ((a[r] >> col) & 1)) a[r] ^= a[col], b[r] ^= b[col];
+		}
+		for (int k = 0; k < 128; k++) out[2 * k] = (uint64_t)b[k], out[2 * k + 1] = (uint64_t)(b[k] >> 64);
+		return true;
+	};
+	if (!solve(pw_t, pw_p, tower_to_polyval) || !solve(pw_p, pw_t, polyval_to_tower)) return B200_ERR_INPUT_VALIDATION;
+	return B200_OK;
 }
 
 // ---- expressions --------------------------------------------------------------------------------

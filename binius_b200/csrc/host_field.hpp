@@ -109,6 +109,25 @@ struct FastTw<3> {
 	static inline u128 mul(u128 a, u128 b) { return tab8().mul[((uint32_t)(uint8_t)a << 8) | (uint8_t)b]; }
 };
 inline u128 mul128(u128 a, u128 b) { return FastTw<7>::mul(a, b); }
+// BinaryField128bPolyval product on stored (Montgomery) forms: a * b * X^-128 mod X^128 + X^127 + X^126 + X^121 + 1
+// (reference crates/field/src/arch/portable/packed_polyval_128.rs:88-122).  Bit-serial carry-less product and
+// bit-serial Montgomery reduction: whenever bit i of the 256-bit product is set, adding p << i clears it (p has
+// constant term 1), and the result is the upper half.
+inline u128 polyval_mul(u128 a, u128 b) {
+	u128 lo = 0, hi = 0;
+	for (int i = 0; i < 128; i++)
+		if ((b >> i) & 1) {
+			lo ^= a << i;
+			if (i) hi ^= a >> (128 - i);
+		}
+	const u128 p_lo = ((u128)0xC200000000000000ull << 64) | 1ull;  // X^127 + X^126 + X^121 + 1 (X^128 is the carry into `hi`)
+	for (int i = 0; i < 128; i++)
+		if ((lo >> i) & 1) {
+			lo ^= p_lo << i;
+			hi ^= (i ? p_lo >> (128 - i) : (u128)0) ^ ((u128)1 << i);  // p << i spills into the upper half; X^128 << i = bit i of hi
+		}
+	return hi;
+}
 inline u128 from_words(const uint64_t w[2]) { return ((u128)w[1] << 64) | w[0]; }
 
 }  // namespace hostf

@@ -260,6 +260,19 @@ __global__ void __launch_bounds__(FOLD_THREADS, 2) k_fold_right_lut(const uint4 
 		out[i] = lut_apply(tbl, L, __ldg(mat + i));
 }
 
+// out[i] = L(in[i]) for a GF(2)-linear map L: B128 -> B128 given by its 128 basis images W[k] = L(beta_k)
+// (FieldLinearTransformation::transform, field/src/linear_transformation.rs; the tower <-> POLYVAL basis change of
+// convert_witnesses_to_fast_ext, core/src/constraint_system/prove.rs:291-292, with the tables of field/src/polyval.rs:
+// 516-788): the byte-LUT engine, 16 conflict-free LDS.128 per element.  In place allowed (out == in).
+__global__ void __launch_bounds__(FOLD_THREADS, 2) k_linear_map(const uint4 *in, const uint4 *__restrict__ W, uint4 *out, uint64_t n) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *tbl = smem;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
+	lut_build(tbl, stage, W);
+	const LutLane L = lut_lane_init();
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = lut_apply(tbl, L, in[i]);
+}
+
 // fold_left fast path for B1 matrices (the switchover / evaluate_partial_high of bit-packed columns,
 // math/src/fold.rs:358-516 are the reference's own B1 fast paths): with nq = vec.len() <= 128 and
 // n_out a multiple of 128,

@@ -127,6 +127,21 @@ int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t
 int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t tower_level,
 						b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out);
 
+/* ---- GF(2)-linear maps on B128 and the POLYVAL ("fast") field ---------------------------------------------
+ * dst[i] = L(src[i]), L given by its 128 basis images (2 words each): FieldLinearTransformation::transform
+ * (crates/field/src/linear_transformation.rs), the device side of convert_witnesses_to_fast_ext
+ * (core/src/constraint_system/prove.rs:291-292) with the tables of crates/field/src/polyval.rs:516-788.
+ * In place (dst == src) allowed.  The GKR grand-product prover (core/src/protocols/gkr_gpa) runs in
+ * BinaryField128bPolyval on the CPU because CLMUL makes that field cheap there; it is ISOMORPHIC to the tower
+ * field, so on this device the layers and sumcheck rounds run on the tower kernels and only what crosses the
+ * interface is mapped: phi(a * b) = phi(a) * phi(b) bit for bit (tests pin this against the Montgomery arithmetic). */
+int32_t b200_linear_map(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n_elems, const uint64_t *basis_images /* 2*128 */);
+/* host-side: product of two BinaryField128bPolyval elements in stored (Montgomery) form
+ * (crates/field/src/arch/portable/packed_polyval_128.rs:88-122) */
+void b200_host_polyval_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
+/* host-side: the tower <-> POLYVAL basis change (128 images each way), derived from the two published generators */
+int32_t b200_host_polyval_basis_change(uint64_t tower_to_polyval[256], uint64_t polyval_to_tower[256]);
+
 /* Arithmetic circuit (crates/math/src/arith_expr.rs:200-206); ComputeLayer::compile_expr */
 typedef struct {
 	uint32_t op; /* 0 Add(l,r)  1 Mul(l,r)  2 Pow(l, r = exponent)  3 Const(c)  4 Var(l) */

@@ -620,6 +620,49 @@ class NTT:
 
 
 # ------------------------------------------------------------------------------------------------
+# BinaryField128bPolyval (oracle/polyval.c)
+def polyval_mul(a: int, b: int) -> int:
+    out = one(0)
+    lib().orc_polyval_mul(_p(one(a)), _p(one(b)), _p(out))
+    return to_ints(out)[0]
+
+
+def polyval_mul_vec(a, b):
+    a, b = _c(a), _c(b)
+    out = np.zeros_like(a)
+    lib().orc_polyval_mul_vec(_p(a), _p(b), _p(out), C.c_uint64(len(a)))
+    return out
+
+
+def linear_map(images, x):
+    """FieldLinearTransformation::transform with the 128 basis images (python ints)"""
+    x = _c(x)
+    out = np.zeros_like(x)
+    lib().orc_linear_map(_p(to_arr(list(images))), _p(x), _p(out), C.c_uint64(len(x)))
+    return out
+
+
+def polyval_gpa_layers(inp, n_vars: int):
+    """GrandProductWitness::new over POLYVAL elements: list of layers (2^n_vars, 2^(n_vars-1), ..., 1 elements)"""
+    inp = _c(inp)
+    assert len(inp) == 1 << n_vars
+    out = np.zeros(((2 << n_vars) - 1, 2), np.uint64)
+    lib().orc_polyval_gpa_layers(_p(inp), C.c_uint32(n_vars), _p(out))
+    layers, off = [], 0
+    for k in range(n_vars + 1):
+        ln = 1 << (n_vars - k)
+        layers.append(out[off:off + ln])
+        off += ln
+    return layers
+
+
+def polyval_gpa_round_evals(a, b, eq, n_vars: int):
+    out = np.zeros((2, 2), np.uint64)
+    lib().orc_polyval_gpa_round_evals(_p(_c(a)), _p(_c(b)), _p(_c(eq)), C.c_uint32(n_vars), _p(out))
+    return to_ints(out)
+
+
+# ------------------------------------------------------------------------------------------------
 # deterministic inputs: SplitMix64 (documented generator of SURVEY.md 8d; the reference's rand 0.9
 # ChaCha12 StdRng is not available outside Rust and the reference stores no golden op outputs)
 def splitmix64(seed: int, n: int) -> np.ndarray:
