@@ -16,6 +16,7 @@
 #include "ntt.cuh"
 #include "ntt_bs.cuh"
 #include "ntt_lut.cuh"
+#include "groestl.cuh"
 #include "roundevals_tc.cuh"
 #include "univariate.cuh"
 #include "uni_split.hpp"
@@ -340,6 +341,31 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 		tables[65536 + a] = (uint8_t)hostf::Tw<3>::mul_alpha((hostf::u128)a);
 	}
 	if (cudaMemcpy(ctx->d_tables, tables.data(), FIELD_TABLE_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) return B200_ERR_DEVICE;
+	{
+		// Groestl T_0: the MixBytes column circ(02,02,03,04,05,03,05,07) * S(x), row 0 in the most significant byte;
+		// S = the AES S-box (inverse in GF(2^8) mod x^8+x^4+x^3+x+1, then the affine map)
+		auto gmul = [](uint32_t a, uint32_t b) {
+			uint32_t r = 0;
+			for (; b; b >>= 1, a = ((a << 1) ^ ((a & 0x80) ? 0x11Bu : 0u)) & 0xFFu)
+				if (b & 1) r ^= a;
+			return r;
+		};
+		static const uint32_t MIX[8] = {2, 2, 3, 4, 5, 3, 5, 7};
+		std::vector<uint64_t> t0(256);
+		for (uint32_t x = 0; x < 256; x++) {
+			uint32_t inv = 0;
+			for (uint32_t y = 1; y < 256 && x; y++)
+				if (gmul(x, y) == 1) inv = y;
+			uint32_t sb = inv;
+			for (int k = 1; k <= 4; k++) sb ^= ((inv << k) | (inv >> (8 - k))) & 0xFFu;
+			sb ^= 0x63;
+			uint64_t col = 0;
+			for (uint32_t row = 0; row < 8; row++) col |= (uint64_t)gmul(MIX[(8 - row) & 7], sb) << (8 * (7 - row));
+			t0[x] = col;
+		}
+		if (cudaMalloc(&ctx->d_groestl_t0, 2048) != cudaSuccess) return B200_ERR_ALLOC;
+		if (cudaMemcpy(ctx->d_groestl_t0, t0.data(), 2048, cudaMemcpyHostToDevice) != cudaSuccess) return B200_ERR_DEVICE;
+	}
 	if (cudaMemset(ctx->d_results, 0, sizeof(uint4) * MAX_RESULTS) != cudaSuccess) return B200_ERR_DEVICE;
 	b200_ctx *c = ctx.get();
 	// opt in to large dynamic shared memory once
@@ -400,6 +426,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(tc::k_pair_tc, tc::NSTAGE * tc::STAGE_BYTES + 1024);
 	SET(tc::k_pair_tc_combine, FIELD_TABLE_BYTES);
 	SET(tc::k_jobs_small, FIELD_TABLE_BYTES);
+	SET(groestl::k_groestl_leaves, groestl::SMEM);
+	SET(groestl::k_groestl_compress_pairs, groestl::SMEM);
 #undef SET
 	if (rc != B200_OK) return rc;
 	*out = ctx.release();
@@ -412,6 +440,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	if (!ctx->pending.empty()) flush_pending(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_tables);
+	if (ctx->d_groestl_t0) cudaFree(ctx->d_groestl_t0);
 	cudaFree(ctx->d_results);
 	cudaFree(ctx->d_args);
 	cudaFreeHost(ctx->h_args);
@@ -944,6 +973,45 @@ int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t
 }
 int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
 	return fold_mat(ctx, true, mat, n_mat, lvl, vec, n_vec, out, n_out);
+}
+
+// ---- Groestl-256 Merkle commitments on device-resident data ----------------------------------------------
+int32_t b200_groestl256_leaves(b200_ctx *ctx, b200_dev_ptr data, uint64_t n_leaves, uint64_t leaf_elems, b200_dev_ptr digests) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (leaf_elems == 0 || leaf_elems > (1u << 24)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectBatchSize: leaves of %llu elements", (unsigned long long)leaf_elems);
+	if (n_leaves == 0) return B200_OK;
+	groestl::k_groestl_leaves<<<grid_for(ctx, n_leaves, groestl::THREADS, 3), groestl::THREADS, groestl::SMEM, ctx->stream>>>(
+		(const uint2 *)ctx->d_groestl_t0, (const uint4 *)data, n_leaves, (uint32_t)(leaf_elems * 16), (uint4 *)digests);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+int32_t b200_groestl256_compress_pairs(b200_ctx *ctx, b200_dev_ptr in_digests, uint64_t n_pairs, b200_dev_ptr out_digests) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n_pairs == 0) return B200_OK;
+	groestl::k_groestl_compress_pairs<<<grid_for(ctx, n_pairs, groestl::THREADS, 3), groestl::THREADS, groestl::SMEM, ctx->stream>>>(
+		(const uint2 *)ctx->d_groestl_t0, (const uint4 *)in_digests, n_pairs, (uint4 *)out_digests);
+	B200_LAUNCH_CHECK(ctx);
+	return B200_OK;
+}
+int32_t b200_merkle_build(b200_ctx *ctx, b200_dev_ptr elements, uint64_t n_elems, uint64_t batch_size, b200_dev_ptr nodes, uint64_t n_nodes) {
+	B200_LOCK(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (batch_size == 0 || n_elems % batch_size) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectBatchSize");
+	const uint64_t n_leaves = n_elems / batch_size;
+	if (!is_pow2(n_leaves)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "PowerOfTwoLengthRequired");
+	if (n_nodes != 2 * n_leaves - 1) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectVectorLen: the tree has %llu nodes", (unsigned long long)(2 * n_leaves - 1));
+	int32_t rc = b200_groestl256_leaves(ctx, elements, n_leaves, batch_size, nodes);
+	uint8_t *prev = (uint8_t *)nodes, *cur = prev + 32 * n_leaves;
+	for (uint64_t n = n_leaves / 2; n >= 1 && !rc; n /= 2) {
+		rc = b200_groestl256_compress_pairs(ctx, prev, n, cur);
+		prev = cur;
+		cur += 32 * n;
+	}
+	return rc;
 }
 
 // ---- GF(2)-linear maps on B128 (basis changes) ------------------------------------------------------

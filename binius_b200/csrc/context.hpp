@@ -57,6 +57,7 @@ struct b200_ctx {
 
 	// field tables (64 KiB B8 product table + 256 B times-X_2 table), device global memory
 	uint8_t *d_tables = nullptr;
+	uint64_t *d_groestl_t0 = nullptr;  // Groestl T_0 table (256 x 8 bytes), groestl.cuh
 	// deferred scalar results (OpValue slots)
 	uint4 *d_results = nullptr;
 	uint32_t n_results = 0;

@@ -127,6 +127,18 @@ int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t
 int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t tower_level,
 						b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out);
 
+/* ---- Groestl-256 Merkle commitments over device-resident data (commit pipeline) ----------
+ * A digest is 32 bytes = 2 B128 slots of device memory.  Leaves: digests[i] = Groestl256 of leaf i's `leaf_elems`
+ * B128 elements in their 16-byte little-endian serialisation (hash_interleaved, crates/core/src/merkle_tree/
+ * binary_merkle_tree.rs:170-211 with crates/hash/src/groestl/digest.rs:60-90); pairs: out[i] =
+ * Groestl256ByteCompression(in[2i], in[2i+1]) (crates/hash/src/groestl/compression.rs:22-36);
+ * b200_merkle_build = BinaryMerkleTree::build (binary_merkle_tree.rs:27-102): `nodes` receives the leaf layer followed
+ * by every inner layer, root last (n_nodes = 2 * n_elems / batch_size - 1 digests).  Errors mirror
+ * merkle_tree/errors.rs: IncorrectBatchSize, PowerOfTwoLengthRequired, IncorrectVectorLen. */
+int32_t b200_groestl256_leaves(b200_ctx *ctx, b200_dev_ptr data, uint64_t n_leaves, uint64_t leaf_elems, b200_dev_ptr digests);
+int32_t b200_groestl256_compress_pairs(b200_ctx *ctx, b200_dev_ptr in_digests, uint64_t n_pairs, b200_dev_ptr out_digests);
+int32_t b200_merkle_build(b200_ctx *ctx, b200_dev_ptr elements, uint64_t n_elems, uint64_t batch_size, b200_dev_ptr nodes, uint64_t n_nodes);
+
 /* ---- GF(2)-linear maps on B128 and the POLYVAL ("fast") field ---------------------------------------------
  * dst[i] = L(src[i]), L given by its 128 basis images (2 words each): FieldLinearTransformation::transform
  * (crates/field/src/linear_transformation.rs), the device side of convert_witnesses_to_fast_ext

@@ -663,6 +663,30 @@ def polyval_gpa_round_evals(a, b, eq, n_vars: int):
 
 
 # ------------------------------------------------------------------------------------------------
+# Groestl-256 / binary Merkle tree (oracle/groestl.c)
+def groestl256(msg: bytes) -> bytes:
+    out = (C.c_uint8 * 32)()
+    buf = (C.c_uint8 * max(len(msg), 1)).from_buffer_copy(msg if msg else b"\0")
+    lib().orc_groestl256(buf, C.c_uint64(len(msg)), out)
+    return bytes(out)
+
+
+def groestl256_compress_pair(left: bytes, right: bytes) -> bytes:
+    out = (C.c_uint8 * 32)()
+    lib().orc_groestl256_compress_pair((C.c_uint8 * 32).from_buffer_copy(left), (C.c_uint8 * 32).from_buffer_copy(right), out)
+    return bytes(out)
+
+
+def merkle_build(elements, batch_size: int):
+    """BinaryMerkleTree::build over B128 elements ((n, 2) uint64): list of 2 * n_leaves - 1 digests, root last"""
+    e = _c(elements)
+    n_leaves = len(e) // batch_size
+    nodes = np.zeros((2 * n_leaves - 1) * 32, np.uint8)
+    lib().orc_merkle_build(_p(e), C.c_uint64(n_leaves), C.c_uint64(16 * batch_size), _p(nodes))
+    return [bytes(nodes[32 * i: 32 * i + 32]) for i in range(2 * n_leaves - 1)]
+
+
+# ------------------------------------------------------------------------------------------------
 # deterministic inputs: SplitMix64 (documented generator of SURVEY.md 8d; the reference's rand 0.9
 # ChaCha12 StdRng is not available outside Rust and the reference stores no golden op outputs)
 def splitmix64(seed: int, n: int) -> np.ndarray:
