@@ -596,6 +596,7 @@ def main():
             red_outs.append(obuf.slice(off, off + (n22 >> (r + 1))))
             off += n22 >> (r + 1)
         chs = [rr.getrandbits(128) for _ in range(4)]
+        merkle_nodes = hal.dev_alloc(2 * ((2 << 20) - 1))
 
         def timed(fn, alg_bytes, reps=5):
             for _ in range(2):
@@ -613,6 +614,7 @@ def main():
             "fold_right_b1_q128_out2^22": timed(lambda ex: (ex.fold_right(SubfieldSlice(va, 0), small, obuf.slice(0, n22)), [])[1], 32 * n22),
             "compute_composite_xy+z_2^22": timed(lambda ex: (ex.compute_composite(SlicesBatch([va, vb, vc], n22), obuf.slice(0, n22), expr), [])[1], 64 * n22),
             "pairwise_product_reduce_2^22": timed(lambda ex: (ex.pairwise_product_reduce(va, red_outs), [])[1], 32 * n22),
+            "merkle_commit_groestl_2^24_elems_batch16": timed(lambda ex: (hal._check(hal._lib.b200_merkle_build(hal._ctx, dev.ptr, 1 << 24, 16, merkle_nodes.ptr, (2 << 20) - 1)), [])[1], 16 * (1 << 24) + 32 * ((2 << 20) - 1), reps=3),
             "fri_fold_first_2^24_in_batch4": timed(lambda ex: (ex.fri_fold(ntt12, 20, 4, chs, dev.slice(0, 1 << 24), obuf.slice(0, 1 << 20)), [])[1], 16 * (1 << 24) + 16 * (1 << 20)),
         }
 

@@ -116,8 +116,8 @@ static int32_t set_smem(b200_ctx *ctx, K kernel, uint32_t bytes) {
 
 // Inner-product jobs on the tensor cores: gmat scratch, k_pair_tc over job pairs, combine into result slots.
 static int32_t launch_tc_pairs(b200_ctx *ctx, std::vector<tc::TcJob> &jobs, uint64_t len, const std::vector<tc::TcTarget> &targets,
-							   uint64_t scratch_offset = 0) {
-	if (jobs.empty() || targets.empty()) return B200_OK;
+							   uint64_t scratch_offset = 0, uint32_t **gmat_out = nullptr) {
+	if (jobs.empty() || (targets.empty() && !gmat_out)) return B200_OK;
 	if (jobs.size() & 1) jobs.push_back(jobs.back());  // pad to a pair; the duplicate's result is ignored
 	const uint32_t n_pairs = (uint32_t)(jobs.size() / 2);
 	if (n_pairs > 65535) return fail(ctx, B200_ERR_INPUT_VALIDATION, "too many inner-product jobs");
@@ -156,6 +156,10 @@ static int32_t launch_tc_pairs(b200_ctx *ctx, std::vector<tc::TcJob> &jobs, uint
 	}
 	tc::k_pair_tc<<<dim3(gx, n_pairs), tc::THREADS, tc::NSTAGE * tc::STAGE_BYTES + 1024, ctx->stream>>>(T);
 	B200_LAUNCH_CHECK(ctx);
+	if (gmat_out) {  // the caller combines the parity matrices itself
+		*gmat_out = gmat;
+		return B200_OK;
+	}
 	tc::k_pair_tc_combine<<<(uint32_t)targets.size(), 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, gmat, (const tc::TcTarget *)(dbase + o_t), ctx->d_results);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
@@ -951,6 +955,19 @@ static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_
 	if (n_out != expect_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output has %llu elements, expected %llu", (unsigned long long)n_out, (unsigned long long)expect_out);
 	if (right && (n_vec << lvl) == 128 && n_out >= 1024) {
 		k_fold_right_lut<<<grid_for(ctx, n_out, FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const uint4 *)mat, lvl, (const uint4 *)vec, (uint4 *)out, n_out);
+		B200_LAUNCH_CHECK(ctx);
+		return B200_OK;
+	}
+	if (!right && lvl == 0 && n_out == 128 && n_vec >= 8192 && n_vec % (2 * tc::CHUNK) == 0 && ctx->tune_round_evals_tc) {
+		// bit-packed matrix, LONG query, 128 outputs (evaluate_partial_high down to 7 variables: ring-switch partial
+		// evaluations): out[q] = sum_j vec[j] * bit_q(word_j) = an outer-product bit-GEMM on the tensor cores
+		const uint64_t len = n_vec / 2;
+		std::vector<tc::TcJob> jobs{tc::TcJob{(const uint4 *)vec, nullptr, (const uint4 *)mat, nullptr},
+									tc::TcJob{(const uint4 *)vec + len, nullptr, (const uint4 *)mat + len, nullptr}};
+		uint32_t *gmat = nullptr;
+		int32_t rc = launch_tc_pairs(ctx, jobs, len, {}, 0, &gmat);
+		if (rc) return rc;
+		tc::k_tc_outer_combine<<<1, 128, 0, ctx->stream>>>(gmat, 2, (uint4 *)out);
 		B200_LAUNCH_CHECK(ctx);
 		return B200_OK;
 	}

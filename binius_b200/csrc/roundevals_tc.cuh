@@ -277,6 +277,29 @@ __global__ void __launch_bounds__(128) k_pair_tc_combine(const uint8_t *__restri
 	}
 }
 
+// G of one or more jobs -> 128 field elements: out[q] = the element whose bit p is (XOR over the jobs of) G[p][q].
+// This is the OUTER-PRODUCT use of the bit-GEMM: with a = a B128 vector v and b = the 128-bit words w of a bit-packed B1
+// matrix,  out[q] = sum_j v[j] * bit_q(w[j])  -- fold_left / evaluate_partial_high of a B1 multilinear by a large tensor
+// query down to 7 variables (ring-switch partial evaluations, core/src/ring_switch/prove.rs:147-208).  grid = 1, block = 128.
+__global__ void __launch_bounds__(128) k_tc_outer_combine(const uint32_t *__restrict__ gmat, uint32_t n_jobs, uint4 *__restrict__ out) {
+	__shared__ uint32_t o[128][4];
+	const uint32_t m = threadIdx.x, p = rho(m);
+	o[m][0] = o[m][1] = o[m][2] = o[m][3] = 0;
+	__syncthreads();
+	for (uint32_t j = 0; j < n_jobs; j++)
+#pragma unroll
+		for (uint32_t q = 0; q < 4; q++) {
+			uint32_t wbits = gmat[(size_t)j * 512 + m * 4 + q];
+			while (wbits) {
+				const uint32_t k = __ffs(wbits) - 1;
+				wbits &= wbits - 1;
+				atomicXor(&o[rho(32 * q + k)][p >> 5], 1u << (p & 31));
+			}
+		}
+	__syncthreads();
+	out[m] = make_uint4(o[m][0], o[m][1], o[m][2], o[m][3]);
+}
+
 // The same jobs on rounds too small for the tensor cores (len < 4096 points): one CTA per target evaluates its job
 // sum_i (a0 + a1)[i] * (b0 + b1)[i] with the per-lane multiply, scales it by the target's coefficient and XORs it
 // into the slot -- ONE launch for all compositions of a small round.  grid = n_targets, block = 256, dyn smem = FIELD_TABLE_BYTES

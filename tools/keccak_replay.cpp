@@ -108,7 +108,7 @@ int main(int argc, char **argv) {
 	DevSlice arena = hal.dev_alloc(arena_elems);
 	hal.fill(arena, F128{0xFEDCBA9876543211ull, 0x0123456789ABCDEFull});
 	Timer t(hal);
-	double ntt_ms = 0, zc_ev = 0, zc_fold = 0, pi_ev = 0, pi_fold = 0, fri_ms = 0, rs_ms = 0, up_ms = 0, uni_ms = 0;
+	double ntt_ms = 0, zc_ev = 0, zc_fold = 0, pi_ev = 0, pi_fold = 0, fri_ms = 0, rs_ms = 0, up_ms = 0, uni_ms = 0, mk_ms = 0;
 	uint64_t launches = 0;
 	// the B1 witness columns of the zerocheck (153 columns of 2^(log_n + 9) bits) in pinned host memory
 	const uint32_t n_cols = 153, uni_vars = log_n + 9, uni_skip = 7;
@@ -121,7 +121,7 @@ int main(int argc, char **argv) {
 	}
 	DevSlice d_wit = hal.dev_alloc(n_cols * col_words);
 	for (int pass = 0; pass < 2; pass++) {  // pass 0 warms the context, pass 1 is reported
-		ntt_ms = zc_ev = zc_fold = pi_ev = pi_fold = fri_ms = rs_ms = up_ms = uni_ms = 0;
+		ntt_ms = zc_ev = zc_fold = pi_ev = pi_fold = fri_ms = rs_ms = up_ms = uni_ms = mk_ms = 0;
 		launches = 0;
 		// ---- witness upload: the committed / constrained B1 columns cross PCIe once (ComputeLayer::copy_h2d)
 		{
@@ -155,6 +155,16 @@ int main(int argc, char **argv) {
 			t.start();
 			hal.check(b200_ntt_forward(hal.ctx(), ntt.raw(), arena.ptr, 5, n_code * 4, 6, log_n + 6, 0, 0, 0, 1));
 			ntt_ms = t.stop(&launches);
+		}
+		// ---- commit: Groestl-256 Merkle tree over the device codeword, leaves = cosets of 2^4 elements (fri/prove.rs:120-198)
+		{
+			const uint64_t n_leaves = n_code / 16, n_nodes = 2 * n_leaves - 1;
+			DevSlice nodes = hal.dev_alloc(2 * n_nodes);
+			t.start();
+			hal.check(b200_merkle_build(hal.ctx(), arena.ptr, n_code, 16, nodes.ptr, n_nodes));
+			mk_ms = t.stop(&launches);
+			hal.check(b200_sync(hal.ctx()));
+			hal.dev_free(nodes);
 		}
 		// ---- zerocheck multilinear rounds: 153 multilinears, 75 chi constraints out - (b0 + (b1 - 1) * b2)
 		{
@@ -280,12 +290,12 @@ int main(int argc, char **argv) {
 			hal.dev_free(q);
 		}
 	}
-	const double total = up_ms + uni_ms + ntt_ms + zc_ev + zc_fold + pi_ev + pi_fold + fri_ms + rs_ms;
+	const double total = up_ms + uni_ms + ntt_ms + mk_ms + zc_ev + zc_fold + pi_ev + pi_fold + fri_ms + rs_ms;
 	printf("{\"workload\": \"keccak op-sequence replay (compiled host), n_permutations = 2^%u (synthetic data)\", \"phases\": {"
 		   "\"witness_upload\": {\"ms\": %.3f, \"h2d_bytes\": %llu}, \"zerocheck_univariate_skip_round\": {\"ms\": %.3f}, "
-		   "\"commit_rs_encode_ntt\": {\"ms\": %.3f}, \"zerocheck_rounds\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, "
+		   "\"commit_rs_encode_ntt\": {\"ms\": %.3f}, \"commit_merkle_groestl\": {\"ms\": %.3f}, \"zerocheck_rounds\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, "
 		   "\"piop_bivariate_sumcheck\": {\"round_evals_ms\": %.3f, \"fold_ms\": %.3f, \"ms\": %.3f}, \"fri_folds\": {\"ms\": %.3f}, "
 		   "\"ring_switch_eq_inds\": {\"ms\": %.3f}}, \"total_ms\": %.3f, \"gpu_launches\": %llu}\n",
-		   log_n, up_ms, (unsigned long long)(n_cols * col_words * 16), uni_ms, ntt_ms, zc_ev, zc_fold, zc_ev + zc_fold, pi_ev, pi_fold, pi_ev + pi_fold, fri_ms, rs_ms, total, (unsigned long long)launches);
+		   log_n, up_ms, (unsigned long long)(n_cols * col_words * 16), uni_ms, ntt_ms, mk_ms, zc_ev, zc_fold, zc_ev + zc_fold, pi_ev, pi_fold, pi_ev + pi_fold, fri_ms, rs_ms, total, (unsigned long long)launches);
 	return 0;
 }
