@@ -16,7 +16,8 @@ ERR_NTT_POWER_OF_TWO, ERR_NTT_SKIP_ROUNDS, ERR_NTT_BATCH, ERR_NTT_COSET, ERR_NTT
 # every symbol include/binius_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error", "b200_ctx_stream", "b200_flush", "b200_ctx_set_stream", "b200_ctx_set_tuning",
-    "b200_kernel_scope_begin", "b200_kernel_local", "b200_kernel_scope_end", "b200_host_mul128", "b200_groestl256_leaves", "b200_groestl256_compress_pairs", "b200_merkle_build", "b200_linear_map", "b200_host_polyval_mul", "b200_host_polyval_basis_change",
+    "b200_kernel_scope_begin", "b200_kernel_local", "b200_kernel_scope_end", "b200_host_mul128", "b200_sumcheck_tail_start", "b200_sumcheck_tail_round_evals", "b200_sumcheck_tail_challenge",
+    "b200_sumcheck_tail_finish", "b200_groestl256_leaves", "b200_groestl256_compress_pairs", "b200_merkle_build", "b200_linear_map", "b200_host_polyval_mul", "b200_host_polyval_basis_change",
     "b200_event_create", "b200_event_record", "b200_event_elapsed_ms", "b200_event_destroy",
     "b200_ctx_launch_count", "b200_dev_alloc", "b200_dev_free", "b200_host_alloc", "b200_host_free",
     "b200_copy_h2d", "b200_copy_d2h", "b200_copy_d2d", "b200_fill", "b200_sync", "b200_results_reset",
@@ -60,6 +61,10 @@ def load() -> C.CDLL:
         "b200_flush": (i32, [vp]),
         "b200_host_mul128": (None, [P(u64), P(u64), P(u64)]),
         "b200_linear_map": (i32, [vp, vp, vp, u64, P(u64)]),
+        "b200_sumcheck_tail_start": (i32, [vp, P(vp), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(vp)]),
+        "b200_sumcheck_tail_round_evals": (i32, [vp, P(u64)]),
+        "b200_sumcheck_tail_challenge": (i32, [vp, P(u64)]),
+        "b200_sumcheck_tail_finish": (i32, [vp]),
         "b200_groestl256_leaves": (i32, [vp, vp, u64, u64, vp]),
         "b200_groestl256_compress_pairs": (i32, [vp, vp, u64, vp]),
         "b200_merkle_build": (i32, [vp, vp, u64, u64, vp, u64]),

@@ -1,6 +1,8 @@
 // capi.cu -- C ABI (include/binius_b200.h): validation + kernel launches.  No CPU fallback: every
 // compute entry point launches sm_100a kernels on the context's stream or fails.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <memory>
 
@@ -24,6 +26,7 @@
 using namespace b200;
 
 struct b200_expr {
+	b200_ctx *ctx = nullptr;
 	std::vector<b200_expr_step> steps;
 	b200_expr_step *d_steps = nullptr;
 	uint32_t n_vars = 0;
@@ -31,7 +34,17 @@ struct b200_expr {
 	bool poly_ok = false;  // degree <= 2 and few terms
 };
 
+// persistent sumcheck tail (k_sumcheck_tail): host-mapped mailboxes + progress
+struct b200_tail {
+	b200_ctx *ctx = nullptr;
+	uint8_t *h_mb = nullptr;  // pinned, mapped
+	uint8_t *d_mb = nullptr;  // device alias
+	uint32_t n_vars = 0, n_vals = 0, round_out = 0, round_in = 0;
+	size_t off_seq = 0, off_chal = 0, off_chal_seq = 0, off_status = 0;
+};
+
 struct b200_ntt {
+	b200_ctx *ctx = nullptr;
 	uint32_t kt = 5, d = 0;
 	std::vector<std::vector<uint64_t>> s_evals;  // rows (host), values < 2^(2^kt)
 	uint32_t *d_s_evals = nullptr;               // device [32][32]
@@ -281,6 +294,27 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 }
 
 static int32_t flush_pending(b200_ctx *ctx);
+// cudaFree synchronises with ALL running device work, i.e. it would block on a persistent sumcheck tail whose next step
+// needs this very host thread: releases that arrive while a tail runs (typically a garbage-collected expression or NTT
+// handle) are parked and performed when the tail finishes.
+// (handles may outlive their context -- a garbage-collected wrapper released after b200_ctx_destroy --, so the
+// context is only touched while it is in the registry of live contexts)
+static std::mutex g_live_mu;
+static std::set<b200_ctx *> g_live;
+static void ctx_free(b200_ctx *ctx, void *p) {
+	if (!p) return;
+	{
+		std::lock_guard<std::mutex> reg(g_live_mu);
+		if (ctx && g_live.count(ctx)) {
+			std::lock_guard<std::recursive_mutex> g(ctx->mu);
+			if (ctx->tail_active) {
+				ctx->deferred_free.push_back(p);
+				return;
+			}
+		}
+	}
+	cudaFree(p);
+}
 // Every entry point takes the context lock (a context may be shared by several host threads: the trait methods
 // take `&self`, compute/src/layer.rs:115-131) and makes the context's device current for the call.
 struct CtxGuard {
@@ -303,6 +337,8 @@ struct CtxGuard {
 #define B200_LOCK(ctx) CtxGuard guard__(ctx)
 #define B200_FLUSH(ctx)                                  \
 	do {                                                  \
+		if ((ctx) && (ctx)->tail_active)                  \
+			return b200::fail(ctx, B200_ERR_INPUT_VALIDATION, "a persistent sumcheck tail owns the stream: only b200_sumcheck_tail_* calls until it is finished"); \
 		if ((ctx) && !(ctx)->pending.empty()) {           \
 			int32_t rc__ = flush_pending(ctx);            \
 			if (rc__) return rc__;                        \
@@ -400,6 +436,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_eq_ind_round_evals, FIELD_TABLE_BYTES);
 	SET(k_eq_ind_vals, FIELD_TABLE_BYTES);
 	SET(k_eq_scale, FIELD_TABLE_BYTES);
+	SET(k_sumcheck_tail, FIELD_TABLE_BYTES);
 	SET(k_fri_fold, FIELD_TABLE_BYTES);
 	SET(k_fri_lerp_k64<1>, 1 * LUT_BYTES + 6144 + NLUT_BYTES);
 	SET(k_fri_lerp_k64<2>, 2 * LUT_BYTES + 6144 + NLUT_BYTES);
@@ -435,11 +472,19 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 #undef SET
 	if (rc != B200_OK) return rc;
 	*out = ctx.release();
+	{
+		std::lock_guard<std::mutex> reg(g_live_mu);
+		g_live.insert(*out);
+	}
 	return B200_OK;
 }
 
 void b200_ctx_destroy(b200_ctx *ctx) {
 	if (!ctx) return;
+	{
+		std::lock_guard<std::mutex> reg(g_live_mu);
+		g_live.erase(ctx);
+	}
 	cudaSetDevice(ctx->device);
 	if (!ctx->pending.empty()) flush_pending(ctx);
 	cudaStreamSynchronize(ctx->stream);
@@ -451,6 +496,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	cudaFreeHost(ctx->h_results);
 	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
 	for (auto &c : ctx->local_pool) cudaFree(c.p);
+	if (ctx->h_tail_mb) cudaFreeHost(ctx->h_tail_mb);
 	if (ctx->s_h2d) {
 		cudaStreamDestroy(ctx->s_h2d);
 		cudaStreamDestroy(ctx->s_d2h);
@@ -1117,6 +1163,7 @@ int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n
 		}
 	}
 	std::unique_ptr<b200_expr> e(new b200_expr);
+	e->ctx = ctx;
 	e->steps.assign(steps, steps + n_steps);
 	e->n_vars = n_vars;
 	e->poly_ok = plan::expand(steps, n_steps, 2, 64, e->poly);
@@ -1125,7 +1172,7 @@ int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n
 }
 void b200_expr_free(b200_expr *e) {
 	if (!e) return;
-	if (e->d_steps) cudaFree(e->d_steps);
+	ctx_free(e->ctx, e->d_steps);
 	delete e;
 }
 uint32_t b200_expr_n_vars(const b200_expr *e) { return e ? e->n_vars : 0; }
@@ -1583,6 +1630,129 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 	return B200_OK;
 }
 
+// ---- persistent tail of an eq-ind sumcheck ---------------------------------------------------------------
+int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps,
+								 const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points,
+								 b200_tail **out) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !out || !eq_ind) return B200_ERR_INPUT_VALIDATION;
+	if (n_vars == 0 || n_vars > 20) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: n_vars must be in [1, 20]");
+	const uint32_t n_vals = n_comp * n_points;
+	if (n_vals == 0 || n_vals > 4096) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: 1..4096 (composition, point) pairs");
+	for (uint32_t c = 0; c < n_comp; c++)
+		if (!comps[c] || !leads[c] || comps[c]->n_vars > m || leads[c]->n_vars > m) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition %u does not match the multilinears", c);
+	for (uint32_t p = 0; p < n_points; p++)
+		if (codes[p] == 0) return fail(ctx, B200_ERR_INPUT_VALIDATION, "evaluation point code 0 is never computed by the prover");
+	std::unique_ptr<b200_tail> t(new b200_tail);
+	t->ctx = ctx, t->n_vars = n_vars, t->n_vals = n_vals;
+	t->off_seq = (size_t)n_vars * n_vals * 16;
+	t->off_chal = (t->off_seq + 4 * n_vars + 15) & ~(size_t)15;
+	t->off_chal_seq = t->off_chal + 16 * (size_t)n_vars;
+	t->off_status = t->off_chal_seq + 4 * (size_t)n_vars;
+	const size_t bytes = t->off_status + 16;
+	// one host-mapped mailbox per context, allocated on first use (pinned allocations cost ~100 us: not per sumcheck)
+	if (ctx->tail_mb_bytes < bytes) {
+		if (ctx->h_tail_mb) {
+			B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFreeHost(ctx->h_tail_mb);
+			ctx->h_tail_mb = nullptr, ctx->tail_mb_bytes = 0;
+		}
+		const size_t want = std::max<size_t>(bytes, 256u << 10);
+		if (cudaHostAlloc((void **)&ctx->h_tail_mb, want, cudaHostAllocMapped) != cudaSuccess) {
+			cudaGetLastError();
+			return fail(ctx, B200_ERR_ALLOC, "out of pinned host memory (sumcheck tail mailbox)");
+		}
+		if (cudaHostGetDevicePointer((void **)&ctx->d_tail_mb, ctx->h_tail_mb, 0) != cudaSuccess) {
+			cudaGetLastError();
+			cudaFreeHost(ctx->h_tail_mb);
+			ctx->h_tail_mb = nullptr;
+			return fail(ctx, B200_ERR_DEVICE, "host-mapped memory is not available");
+		}
+		ctx->tail_mb_bytes = want;
+	}
+	if (ctx->tail_active) return fail(ctx, B200_ERR_INPUT_VALIDATION, "a sumcheck tail is already running on this context");
+	t->h_mb = ctx->h_tail_mb, t->d_mb = ctx->d_tail_mb;
+	memset(t->h_mb + t->off_seq, 0, bytes - t->off_seq);
+	std::vector<DevExpr> hc(n_comp), hl(n_comp);
+	for (uint32_t c = 0; c < n_comp; c++) {
+		hc[c] = dev_expr(comps[c]);
+		hl[c] = dev_expr(leads[c]);
+		if ((hc[c].n_steps && !hc[c].steps) || (hl[c].n_steps && !hl[c].steps)) return fail(ctx, B200_ERR_ALLOC, "out of device memory (expression steps)");
+	}
+	std::vector<uint4> hp(n_points);
+	for (uint32_t p = 0; p < n_points; p++) hp[p] = to_u4(points + 2 * p);
+	ArgPack pack;
+	size_t o_m = pack.add(mls, sizeof(void *) * m), o_c = pack.add(hc.data(), sizeof(DevExpr) * n_comp), o_l = pack.add(hl.data(), sizeof(DevExpr) * n_comp);
+	size_t o_k = pack.add(codes, 4 * n_points), o_p = pack.add(hp.data(), 16 * n_points);
+	uint8_t *dbase;
+	int32_t rc = pack.commit(ctx, &dbase);
+	if (rc) return rc;
+	TailArgs A;
+	A.mls = (uint4 *const *)(dbase + o_m), A.m = m, A.n_vars = n_vars, A.eq_ind = (uint4 *)eq_ind;
+	A.comps = (const DevExpr *)(dbase + o_c), A.leads = (const DevExpr *)(dbase + o_l), A.n_comp = n_comp, A.n_points = n_points;
+	A.codes = (const uint32_t *)(dbase + o_k), A.points = (const uint4 *)(dbase + o_p);
+	A.mb_vals = (volatile uint4 *)t->d_mb, A.mb_seq = (volatile uint32_t *)(t->d_mb + t->off_seq);
+	A.mb_chal = (volatile uint4 *)(t->d_mb + t->off_chal), A.mb_chal_seq = (volatile uint32_t *)(t->d_mb + t->off_chal_seq);
+	A.status = (volatile uint32_t *)(t->d_mb + t->off_status);
+	A.timeout_ns = 5ull * 1000 * 1000 * 1000;
+	k_sumcheck_tail<<<1, 1024, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	B200_LAUNCH_CHECK(ctx);
+	ctx->tail_active = true;
+	*out = t.release();
+	return B200_OK;
+}
+// the values of the next round (n_comp * n_points elements, [composition][point]); blocks until the kernel posts them
+int32_t b200_sumcheck_tail_round_evals(b200_tail *t, uint64_t *out) {
+	if (!t || !out) return B200_ERR_INPUT_VALIDATION;
+	b200_ctx *ctx = t->ctx;
+	if (t->round_out >= t->n_vars || t->round_out != t->round_in) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: round values requested out of order");
+	const uint32_t r = t->round_out;
+	volatile uint32_t *seq = (volatile uint32_t *)(t->h_mb + t->off_seq), *status = (volatile uint32_t *)(t->h_mb + t->off_status);
+	const auto t0 = std::chrono::steady_clock::now();
+	for (uint64_t spins = 0; seq[r] != r + 1; spins++) {
+		if (*status) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel's watchdog expired");
+		if ((spins & 0xFFFF) == 0xFFFF) {
+			if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady && seq[r] != r + 1) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel ended before posting round %u", r);
+			if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: timed out waiting for round %u", r);
+		}
+	}
+	std::atomic_thread_fence(std::memory_order_acquire);
+	memcpy(out, t->h_mb + (size_t)r * t->n_vals * 16, (size_t)t->n_vals * 16);
+	t->round_out++;
+	return B200_OK;
+}
+// post the challenge of the round whose values were just read: the kernel folds and goes on to the next round
+int32_t b200_sumcheck_tail_challenge(b200_tail *t, const uint64_t z[2]) {
+	if (!t || !z) return B200_ERR_INPUT_VALIDATION;
+	if (t->round_in + 1 != t->round_out) return fail(t->ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: challenge posted out of order");
+	const uint32_t r = t->round_in;
+	memcpy(t->h_mb + t->off_chal + 16 * (size_t)r, z, 16);
+	std::atomic_thread_fence(std::memory_order_release);
+	((volatile uint32_t *)(t->h_mb + t->off_chal_seq))[r] = r + 1;
+	t->round_in++;
+	return B200_OK;
+}
+// wait for the kernel to end (all challenges posted) and release the mailbox; the multilinears hold their final folds
+int32_t b200_sumcheck_tail_finish(b200_tail *t) {
+	if (!t) return B200_ERR_INPUT_VALIDATION;
+	b200_ctx *ctx = t->ctx;
+	B200_LOCK(ctx);
+	int32_t rc = B200_OK;
+	if (t->round_in != t->n_vars) {
+		// abandoned: let the watchdog end the kernel quickly instead of waiting 5 s
+		rc = fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail finished after %u of %u challenges", t->round_in, t->n_vars);
+	}
+	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	if (e != cudaSuccess && rc == B200_OK) rc = fail(ctx, B200_ERR_DEVICE, "sumcheck tail: %s", cudaGetErrorString(e));
+	if (rc == B200_OK && *(volatile uint32_t *)(t->h_mb + t->off_status)) rc = fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel's watchdog expired");
+	ctx->tail_active = false;
+	for (void *p : ctx->deferred_free) cudaFree(p);
+	ctx->deferred_free.clear();
+	delete t;
+	return rc;
+}
+
 // ---- NTT -----------------------------------------------------------------------------------------
 int32_t b200_ntt_create(b200_ctx *ctx, uint32_t kt, uint32_t d, b200_ntt **out) {
 	B200_LOCK(ctx);
@@ -1591,6 +1761,7 @@ int32_t b200_ntt_create(b200_ctx *ctx, uint32_t kt, uint32_t d, b200_ntt **out) 
 	if (d == 0) return fail(ctx, B200_ERR_NTT_DOMAIN, "domain size is less than 2**1");
 	if (d > (1u << kt)) return fail(ctx, B200_ERR_NTT_FIELD, "field order must be at least 2**%u", d);
 	std::unique_ptr<b200_ntt> n(new b200_ntt);
+	n->ctx = ctx;
 	n->kt = kt;
 	n->d = d;
 	// precompute_subspace_evals (crates/ntt/src/twiddle.rs:244-313) over the basis beta_j = 1 << j
@@ -1638,8 +1809,8 @@ int32_t b200_ntt_create(b200_ctx *ctx, uint32_t kt, uint32_t d, b200_ntt **out) 
 }
 void b200_ntt_destroy(b200_ntt *ntt) {
 	if (!ntt) return;
-	cudaFree(ntt->d_s_evals);
-	if (ntt->d_basis) cudaFree(ntt->d_basis);
+	ctx_free(ntt->ctx, ntt->d_s_evals);
+	ctx_free(ntt->ctx, ntt->d_basis);
 	delete ntt;
 }
 uint32_t b200_ntt_log_domain_size(const b200_ntt *ntt) { return ntt ? ntt->d : 0; }

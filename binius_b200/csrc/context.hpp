@@ -75,6 +75,11 @@ struct b200_ctx {
 	std::vector<b200_trace_op> trace;
 	std::vector<b200_local_chunk> local_pool;            // KernelMemMap::Local scratch, grown by chunks, never moved
 	std::vector<std::pair<uint8_t *, uint64_t>> locals;  // (base, bytes) of the locals of the open scope
+	// host-mapped mailbox of the persistent sumcheck tail (b200_sumcheck_tail_*), allocated on first use
+	uint8_t *h_tail_mb = nullptr, *d_tail_mb = nullptr;
+	size_t tail_mb_bytes = 0;
+	bool tail_active = false;
+	std::vector<void *> deferred_free;  // device releases that arrived while a tail was running
 	// kernel-selection switches for A/B measurements (b200_ctx_set_tuning); defaults = production paths
 	int tune_ntt = 0;              // 0 look-up-table + bit-sliced low layers, 1 bit-sliced only, 2 scalar tables
 	uint32_t tune_ntt_log_cc = 7;  // columns per work item of a look-up-table pass

@@ -163,7 +163,7 @@ def zerocheck_univariate_evals(backend: "B200Backend", multilinears: Sequence[Tr
 class B200Backend:
     """ComputationBackend over one B200Layer."""
 
-    def __init__(self, layer: B200Layer):
+    def __init__(self, layer: B200Layer, sumcheck_tail: bool = False):
         self._l = layer
         self._exprs = {}
         self._unit = None
@@ -173,6 +173,13 @@ class B200Backend:
         # round (buffers the caller handed in are never recycled: only pointers taken from the pool are given back)
         self._mine = {}
         self._free = []
+        # persistent sumcheck tail (b200_sumcheck_tail_*): when the (composition, point, hypercube index) triples of a
+        # round drop below `tail_threshold`, the remaining rounds of an eq-ind prover run in ONE kernel and the trait
+        # calls of those rounds only read / post through its host-mapped mailboxes
+        # (opt-in: while the tail kernel runs it owns the context's stream -- any other call on the layer is refused --,
+        # so only a caller whose round loop does nothing else on the layer, like the prover's, should switch it on)
+        self.tail_threshold = (1 << 8) if sumcheck_tail else 0
+        self._tail = None
 
     def _take(self, n: int) -> DevSlice:
         n = max(n, 1)
@@ -254,6 +261,8 @@ class B200Backend:
         if not codes or not evaluators:
             return [[] for _ in evaluators]
         pts = [0 if c < 3 else finite_evaluation_points[c - 3] for c in codes]
+        if self._tail is not None or self._tail_eligible(n_vars, multilinears, evaluators, weighted, evaluation_order, codes):
+            return self._tail_round_evals(n_vars, multilinears, evaluators, eq_ind_partial_evals, codes, pts, lo)
         temps = []
         views = []
         for ml in multilinears:
@@ -292,6 +301,52 @@ class B200Backend:
             res.append([vals[e * len(codes) + (k - lo)] for k in rng])
         return res
 
+    # -- persistent tail -------------------------------------------------------------------------------------------
+    def _tail_eligible(self, n_vars, multilinears, evaluators, weighted, order, codes) -> bool:
+        if not self.tail_threshold or not weighted or order != EvaluationOrder.HighToLow or n_vars > 20:
+            return False
+        if any(ev.have_first_round_eval_1s for ev in evaluators):  # the first round of a prover has its own point set
+            return False
+        if any(not isinstance(ml, FoldedMultilinear) or ml.evals.len() != 1 << n_vars for ml in multilinears):
+            return False
+        return (len(evaluators) * len(codes)) << (n_vars - 1) <= self.tail_threshold
+
+    def _tail_round_evals(self, n_vars, multilinears, evaluators, eq_ind, codes, pts, lo):
+        L = self._l
+        if self._tail is None:
+            compiled = [self._compiled(ev.composition) for ev in evaluators]
+            m = len(multilinears)
+            ptrs = (C.c_void_p * max(m, 1))(*[ml.evals.ptr for ml in multilinears])
+            comps = (C.c_void_p * len(evaluators))(*[c[0].handle.value for c in compiled])
+            leads = (C.c_void_p * len(evaluators))(*[c[1].handle.value for c in compiled])
+            h = C.c_void_p()
+            L._check(L._lib.b200_sumcheck_tail_start(L._ctx, ptrs, m, n_vars, eq_ind.ptr, comps, leads, len(evaluators),
+                                                     (C.c_uint32 * len(codes))(*codes), _u64_list(pts), len(codes), C.byref(h)))
+            self._tail = {"h": h, "n_vars": n_vars, "n_comp": len(evaluators), "codes": list(codes), "eq_ptr": eq_ind.ptr, "eq_pending": 0}
+        t = self._tail
+        if t["n_vars"] != n_vars or t["n_comp"] != len(evaluators) or t["codes"] != list(codes):
+            raise InputValidation("the running sumcheck tail was started for a different round shape")
+        total = len(evaluators) * len(codes)
+        out = (C.c_uint64 * (2 * total))()
+        L._check(L._lib.b200_sumcheck_tail_round_evals(t["h"], out))
+        vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(total)]
+        return [[vals[e * len(codes) + (k - lo)] for k in ev.eval_point_indices()] for e, ev in enumerate(evaluators)]
+
+    def _tail_fold(self, n_vars, multilinears, challenge):
+        L, t = self._l, self._tail
+        if t["n_vars"] != n_vars:
+            raise InputValidation("fold does not match the running sumcheck tail")
+        L._check(L._lib.b200_sumcheck_tail_challenge(t["h"], _u64x2(challenge)))
+        for ml in multilinears:
+            ml.evals = ml.evals.slice(0, 1 << (n_vars - 1))
+        t["n_vars"] -= 1
+        t["eq_pending"] += 1  # the kernel halves the eq-indicator itself: the next fold_partial_eq_ind is a view change
+        if t["n_vars"] == 0:
+            self._tail = None
+            L._check(L._lib.b200_sumcheck_tail_finish(t["h"]))
+            self._tail_done_eq = t["eq_ptr"]
+        return False
+
     # -- backend.rs:65-75: folds every multilinear by `challenge`; Folded ones by a single-variable lerp
     #    (in place for HighToLow, into a fresh buffer for LowToHigh), Transparent ones are materialised by
     #    `tensor_query` (which already includes `challenge`, prover_state.rs fold()) at their switchover
@@ -300,6 +355,8 @@ class B200Backend:
                                    challenge: int, tensor_query: Optional[DevSlice] = None, *,
                                    evaluation_order: EvaluationOrder = EvaluationOrder.HighToLow) -> bool:
         L = self._l
+        if self._tail is not None:
+            return self._tail_fold(n_vars, multilinears, challenge)
         any_transparent_left = False
         folded_ix = []
         for t, ml in enumerate(multilinears):
@@ -339,6 +396,9 @@ class B200Backend:
     def fold_partial_eq_ind(self, n_vars: int, eq_ind: DevSlice, evaluation_order: EvaluationOrder = EvaluationOrder.HighToLow) -> DevSlice:
         if n_vars == 0:
             return eq_ind
+        if self._tail is not None and self._tail["eq_ptr"] == eq_ind.ptr and self._tail["eq_pending"] > 0:
+            self._tail["eq_pending"] -= 1  # halved in place by the tail kernel
+            return eq_ind.slice(0, 1 << (n_vars - 1))
         if evaluation_order == EvaluationOrder.LowToHigh:
             # E'[i] = E[2i] + E[2i+1] (common.rs:50-58) = fold_right of E by the all-ones pair
             if self._ones2 is None:

@@ -57,6 +57,12 @@ class B200Backend {
 	// buffer they replace goes back to it, so two buffers per multilinear ping-pong instead of one allocation
 	// (= one device synchronisation) per round.  Buffers the caller handed in are never recycled; the pool is
 	// released with the backend.
+	// persistent sumcheck tail (b200_sumcheck_tail_*), opt-in: while it runs the layer accepts no other call, so only
+	// a caller whose round loop does nothing else on the layer (the prover's) should switch it on
+	uint64_t tail_threshold_ = 0;
+	b200_tail *tail_ = nullptr;
+	uint32_t tail_vars_ = 0, tail_eq_pending_ = 0;
+	uint8_t *tail_eq_ptr_ = nullptr;
 	std::map<uint8_t *, uint64_t> mine_;
 	std::vector<std::pair<uint8_t *, uint64_t>> free_, all_;
 	DevSlice take(uint64_t n) {
@@ -101,7 +107,7 @@ class B200Backend {
 	}
 
   public:
-	explicit B200Backend(B200Layer &l) : l_(l) {}
+	explicit B200Backend(B200Layer &l, bool sumcheck_tail = false) : l_(l), tail_threshold_(sumcheck_tail ? (1u << 8) : 0) {}
 	~B200Backend() {
 		for (auto &b : all_) b200_dev_free(l_.ctx(), b.first);
 	}
@@ -127,6 +133,35 @@ class B200Backend {
 		std::vector<uint32_t> codes;
 		std::vector<F128> pts;
 		for (uint32_t c = lo; c < hi; c++) { codes.push_back(c); pts.push_back(c < 3 ? F128{} : nontrivial_evaluation_points[c - 3]); }
+		// ---- persistent tail: start it when the round is small enough, then only read its mailbox
+		bool tail_ok = tail_ != nullptr;
+		if (!tail_ok && tail_threshold_ && eq_ind_partial_evals && order == EvaluationOrder::HighToLow && n_vars <= 20 &&
+			((uint64_t)(evaluators.size() * codes.size()) << (n_vars - 1)) <= tail_threshold_) {
+			tail_ok = true;
+			for (auto &e : evaluators) tail_ok = tail_ok && e.first_point == 1;  // not the first round of a prover
+			for (auto &m : multilinears) tail_ok = tail_ok && m.kind == SumcheckMultilinear::Folded && m.evals.n == (1ull << n_vars);
+			if (tail_ok) {
+				std::vector<b200_dev_ptr> p;
+				for (auto &m : multilinears) p.push_back(m.evals.ptr);
+				std::vector<const b200_expr *> cs, ls;
+				for (auto &e : evaluators) { cs.push_back(e.composition->raw()); ls.push_back(e.composition_at_infinity->raw()); }
+				l_.check(b200_sumcheck_tail_start(l_.ctx(), p.data(), (uint32_t)p.size(), n_vars, eq_ind_partial_evals->ptr, cs.data(), ls.data(),
+												  (uint32_t)cs.size(), codes.data(), (const uint64_t *)pts.data(), (uint32_t)codes.size(), &tail_));
+				tail_vars_ = n_vars, tail_eq_ptr_ = eq_ind_partial_evals->ptr, tail_eq_pending_ = 0;
+			}
+		}
+		if (tail_ok) {
+			if (tail_vars_ != n_vars) throw InputValidation(1, "the running sumcheck tail was started for a different round");
+			std::vector<F128> vals(evaluators.size() * codes.size());
+			l_.check(b200_sumcheck_tail_round_evals(tail_, (uint64_t *)vals.data()));
+			std::vector<std::vector<F128>> res;
+			for (size_t e = 0; e < evaluators.size(); e++) {
+				std::vector<F128> r;
+				for (uint32_t k = evaluators[e].first_point; k < evaluators[e].end_point; k++) r.push_back(vals[e * codes.size() + (k - lo)]);
+				res.push_back(r);
+			}
+			return res;
+		}
 		std::vector<DevSlice> temps;
 		std::vector<b200_dev_ptr> ptrs;
 		std::vector<uint64_t> lens;
@@ -169,6 +204,19 @@ class B200Backend {
 	// returns any_transparent_left; `tensor_query` already includes `challenge` (prover_state.rs:161-181)
 	bool sumcheck_fold_multilinears(EvaluationOrder order, uint32_t n_vars, std::vector<SumcheckMultilinear> &multilinears, F128 challenge,
 									const DevSlice *tensor_query) {
+		if (tail_) {
+			if (tail_vars_ != n_vars) throw InputValidation(1, "fold does not match the running sumcheck tail");
+			uint64_t z[2] = {challenge.lo, challenge.hi};
+			l_.check(b200_sumcheck_tail_challenge(tail_, z));
+			for (auto &m : multilinears) m.evals = m.evals.slice(0, 1ull << (n_vars - 1));
+			tail_eq_pending_++;
+			if (--tail_vars_ == 0) {
+				b200_tail *t = tail_;
+				tail_ = nullptr;
+				l_.check(b200_sumcheck_tail_finish(t));
+			}
+			return false;
+		}
 		bool any_transparent_left = false;
 		std::vector<SumcheckMultilinear *> folded;
 		for (auto &m : multilinears) {
@@ -221,6 +269,10 @@ class B200Backend {
 
 	DevSlice fold_partial_eq_ind(EvaluationOrder order, uint32_t n_vars, DevSlice eq_ind) {
 		if (n_vars == 0) return eq_ind;
+		if (tail_ && tail_eq_ptr_ == eq_ind.ptr && tail_eq_pending_) {  // halved in place by the tail kernel
+			tail_eq_pending_--;
+			return eq_ind.slice(0, 1ull << (n_vars - 1));
+		}
 		if (order == EvaluationOrder::LowToHigh) {
 			if (!ones2_.n) {
 				ones2_ = l_.dev_alloc(2);

@@ -289,6 +289,25 @@ int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *mu
 										   const uint64_t *suffix_evals /* 2*m */, const uint64_t challenge[2],
 										   uint64_t *new_lens);
 
+/* ---- persistent tail of an eq-ind sumcheck ------------------------------------------------------------------
+ * The last rounds of a sumcheck are a few kilobytes of data: through separate calls every round pays launches, an
+ * argument copy and a synchronising read (~40 us).  b200_sumcheck_tail_start launches ONE kernel that runs all
+ * remaining `n_vars` rounds of an eq-ind (zerocheck) prover on full-length folded multilinears (HighToLow): per round
+ * it posts the round values ([composition][point], semantics of b200_sumcheck_round_evals) to a host-mapped mailbox,
+ * waits for the challenge in a host-mapped mailbox, folds every multilinear in place (fold_left_lerp_inplace) and
+ * halves the eq-indicator (fold_partial_eq_ind, core/src/protocols/sumcheck/prove/common.rs:60-68).  Host side per
+ * round: b200_sumcheck_tail_round_evals (blocks until the values are there), then b200_sumcheck_tail_challenge;
+ * after the last challenge b200_sumcheck_tail_finish.  A backend maps the trait calls of those rounds
+ * (sumcheck_compute_round_evals / sumcheck_fold_multilinears, hal/src/backend.rs:48-75) onto this triple.  A watchdog
+ * ends the kernel if no challenge arrives within 5 s (the calls then fail with B200_ERR_DEVICE). */
+typedef struct b200_tail b200_tail;
+int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *multilins, uint32_t n_multilins, uint32_t n_vars, b200_dev_ptr eq_ind,
+								 const b200_expr *const *compositions, const b200_expr *const *compositions_leading, uint32_t n_compositions,
+								 const uint32_t *point_codes, const uint64_t *domain_points, uint32_t n_points, b200_tail **out);
+int32_t b200_sumcheck_tail_round_evals(b200_tail *tail, uint64_t *host_out /* 2 * n_compositions * n_points */);
+int32_t b200_sumcheck_tail_challenge(b200_tail *tail, const uint64_t challenge[2]);
+int32_t b200_sumcheck_tail_finish(b200_tail *tail);
+
 /* ---- zerocheck univariate-skip round ----------------------------------------------------------------
  * zerocheck_univariate_evals (core/src/protocols/sumcheck/prove/univariate.rs:235-500, with ntt_extrapolate
  * :642-678, spread_product :503-563, extrapolate_round_evals :565-640), FDomain = BinaryField8b:

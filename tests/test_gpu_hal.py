@@ -315,3 +315,66 @@ def test_regular_evaluator_monomial_plan(hal, oracle):
         ch = rng.getrandbits(128)
         be.sumcheck_fold_multilinears(nv, mls, ch)
         mls_h = [oracle.fold_left_lerp_inplace(x, len(x), 0, nv, ch) for x in mls_h]
+
+
+@pytest.mark.parametrize("n_vars,with_cubic", [(1, False), (6, True), (13, False), (16, True)])
+def test_persistent_sumcheck_tail(hal, oracle, n_vars, with_cubic):
+    """The persistent tail kernel (b200_sumcheck_tail_*): once a round is small enough, all remaining rounds run in one
+    kernel that talks to the host through mapped mailboxes.  Every round's values and the final folds must equal the
+    oracle's; rounds above the threshold (n_vars = 16) still take the per-call path.  Includes a degree-3 composition
+    (finite evaluation point 3) next to the u32_add ones."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
+
+    be = B200Backend(hal, sumcheck_tail=True)
+    be.tail_threshold = 1 << 14  # exercise the tail on rounds of up to 2^14 (composition, point, index) triples
+    rng = random.Random(4000 + n_vars)
+    comps = u32_add_compositions() + ([A.var(0) * A.var(1) * A.var(4) + A.var(2)] if with_cubic else [])
+    mls_h = [oracle.rand_b128(4100 + t, 1 << n_vars) for t in range(5)]
+    eq_pt = [rng.getrandbits(128) for _ in range(n_vars - 1)]
+    eq_h = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << max(n_vars - 1, 0)) - 1)), 0, eq_pt)
+    mls = [FoldedMultilinear(hal.to_device(m), 0) for m in mls_h]
+    eq_d = be.tensor_product_full_query(eq_pt)
+    finite = [oracle.mul(0x2, 0x2)] if with_cubic else []
+    used_tail = False
+    for rnd in range(n_vars):
+        nv = n_vars - rnd
+        evs = [EqIndEvaluator(c, have_first_round_eval_1s=(rnd == 0)) for c in comps]
+        got = be.sumcheck_compute_round_evals(nv, mls, evs, eq_d, finite)
+        used_tail = used_tail or be._tail is not None
+        exp_all = oracle.eq_ind_round_evals(mls_h, [len(m) for m in mls_h], [0] * 5, nv, eq_h, [c.steps for c in comps],
+                                            [c.leading_term().steps for c in comps], [1, 2, 3], [0, 0, finite[0] if finite else 0])
+        for ev, g, e in zip(evs, got, exp_all):
+            assert g == [e[k - 1] for k in ev.eval_point_indices()], f"round {rnd}"
+        ch = rng.getrandbits(128)
+        be.sumcheck_fold_multilinears(nv, mls, ch)
+        mls_h = [oracle.fold_left_lerp_inplace(m, len(m), 0, nv, ch) for m in mls_h]
+        if nv > 1:
+            eq_d = be.fold_partial_eq_ind(nv - 1, eq_d)
+            eq_h = oracle.fold_partial_eq_ind(eq_h)
+    assert be._tail is None and (used_tail or n_vars == 1)
+    for d, h in zip(mls, mls_h):
+        assert d.evals.len() == 1 and _same(hal.to_host(d.evals), h)
+
+
+def test_layer_calls_are_refused_while_a_tail_runs(hal, oracle):
+    import binius_b200
+    from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
+
+    be = B200Backend(hal, sumcheck_tail=True)
+    n_vars = 4
+    comps = u32_add_compositions()
+    mls = [FoldedMultilinear(hal.to_device(oracle.rand_b128(4200 + t, 1 << n_vars)), 0) for t in range(5)]
+    eq_d = be.tensor_product_full_query([3, 5, 7])
+    be.sumcheck_compute_round_evals(n_vars, mls, [EqIndEvaluator(c) for c in comps], eq_d, [])
+    assert be._tail is not None
+    with pytest.raises(binius_b200.InputValidation):
+        hal.to_host(eq_d)  # would otherwise queue behind the persistent kernel and deadlock
+    for nv in range(n_vars, 0, -1):  # drive the tail to its end
+        if nv < n_vars:
+            be.sumcheck_compute_round_evals(nv, mls, [EqIndEvaluator(c) for c in comps], eq_d, [])
+        be.sumcheck_fold_multilinears(nv, mls, 0x1234 + nv)
+        if nv > 1:
+            eq_d = be.fold_partial_eq_ind(nv - 1, eq_d)
+    assert be._tail is None
+    hal.to_host(eq_d)

@@ -51,9 +51,9 @@ struct Timer {
 
 // BASELINE config #3: zerocheck rounds of the u32_add circuit at 2^20 rows (5 multilinears of 18 variables,
 // compositions (x+c)(y+c)+c-o and x+y+c-z, 18 rounds of {round evals, fold, eq-ind halving}), compiled host
-static int run_cfg3() {
+static int run_cfg3(bool tail) {
 	B200Layer hal(0);
-	B200Backend be(hal);
+	B200Backend be(hal, tail);
 	const uint32_t nv = 18, m = 5;
 	DevSlice arena = hal.dev_alloc((uint64_t)m << nv);
 	hal.fill(arena, F128{0xFEDCBA9876543211ull, 0x0123456789ABCDEFull});
@@ -92,13 +92,13 @@ static int run_cfg3() {
 		if (rep >= 0) ms += one;
 		hal.check(b200_sync(hal.ctx()));
 	}
-	printf("{\"workload\": \"zerocheck rounds, u32_add at 2^20 rows (5 multilinears x 2^18, 18 rounds), compiled host\", \"ms_per_sumcheck\": %.4f, \"rounds_per_s\": %.1f}\n",
-		   ms / reps, 18.0 / (ms / reps * 1e-3));
+	printf("{\"workload\": \"zerocheck rounds, u32_add at 2^20 rows (5 multilinears x 2^18, 18 rounds), compiled host\", \"persistent_tail\": %s, \"ms_per_sumcheck\": %.4f, \"rounds_per_s\": %.1f}\n",
+		   tail ? "true" : "false", ms / reps, 18.0 / (ms / reps * 1e-3));
 	return 0;
 }
 
 int main(int argc, char **argv) {
-	if (argc > 1 && std::string(argv[1]) == "cfg3") return run_cfg3();
+	if (argc > 1 && std::string(argv[1]) == "cfg3") return run_cfg3(!(argc > 2 && std::string(argv[2]) == "notail"));
 	const uint32_t log_n = argc > 1 ? (uint32_t)atoi(argv[1]) : 18;
 	const uint32_t nv = log_n + 2;
 	B200Layer hal(0);
