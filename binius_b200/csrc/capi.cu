@@ -1045,7 +1045,7 @@ int32_t b200_groestl256_leaves(b200_ctx *ctx, b200_dev_ptr data, uint64_t n_leav
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (leaf_elems == 0 || leaf_elems > (1u << 24)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectBatchSize: leaves of %llu elements", (unsigned long long)leaf_elems);
 	if (n_leaves == 0) return B200_OK;
-	groestl::k_groestl_leaves<<<grid_for(ctx, n_leaves, groestl::THREADS, 3), groestl::THREADS, groestl::SMEM, ctx->stream>>>(
+	groestl::k_groestl_leaves<<<grid_for(ctx, n_leaves, groestl::THREADS, 1), groestl::THREADS, groestl::SMEM, ctx->stream>>>(
 		(const uint2 *)ctx->d_groestl_t0, (const uint4 *)data, n_leaves, (uint32_t)(leaf_elems * 16), (uint4 *)digests);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;
@@ -1055,7 +1055,7 @@ int32_t b200_groestl256_compress_pairs(b200_ctx *ctx, b200_dev_ptr in_digests, u
 	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (n_pairs == 0) return B200_OK;
-	groestl::k_groestl_compress_pairs<<<grid_for(ctx, n_pairs, groestl::THREADS, 3), groestl::THREADS, groestl::SMEM, ctx->stream>>>(
+	groestl::k_groestl_compress_pairs<<<grid_for(ctx, n_pairs, groestl::THREADS, 1), groestl::THREADS, groestl::SMEM, ctx->stream>>>(
 		(const uint2 *)ctx->d_groestl_t0, (const uint4 *)in_digests, n_pairs, (uint4 *)out_digests);
 	B200_LAUNCH_CHECK(ctx);
 	return B200_OK;

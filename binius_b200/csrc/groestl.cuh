@@ -8,8 +8,10 @@
 // significant byte); one round = AddRoundConstant, then for every output column the XOR of 8 table entries
 //     T_r[ S-box input byte of row r taken from column (j + shift[r]) mod 8 ],   T_r[x] = rotr64(T_0[x], 8 r),
 // T_0[x] = the MixBytes column circ(02,02,03,04,05,03,05,07) * S(x) (SubBytes, ShiftBytes and MixBytes fused).
-// The 8 tables (16 KiB) live in shared memory, REPLICATED 4x (64 KiB, replica = lane % 4) to thin out bank conflicts of
-// the data-dependent gathers; one thread hashes one leaf / one pair.
+// Shared-memory layout for conflict-free data-dependent gathers: an LDS.64 is served per half-warp (16 lanes x 8 B), so
+// lane l only ever touches the bank pair l % 16 -- every table is stored as 16 REPLICAS, entry e of replica r at byte
+// e * 128 + r * 8.  Four tables (rotations by 0, 8, 16, 24 bits = 128 KiB) are stored; T_{r+4} is T_r with its 32-bit
+// halves swapped, which costs nothing.  One thread hashes one leaf / one pair.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -18,9 +20,10 @@
 namespace b200 {
 namespace groestl {
 
-constexpr uint32_t THREADS = 256;
-constexpr uint32_t REPL = 4;
-constexpr uint32_t SMEM = REPL * 8 * 256 * 8;  // 64 KiB
+constexpr uint32_t THREADS = 512;
+constexpr uint32_t REPL = 16;
+constexpr uint32_t TBL = 256 * REPL * 8;  // one rotated table with its 16 replicas: 32 KiB
+constexpr uint32_t SMEM = 4 * TBL;        // 128 KiB
 
 // tbl: this lane's replica, [8][256] uint2 {lo, hi}
 template <bool Q>
@@ -46,10 +49,10 @@ __device__ __forceinline__ void permutation(uint32_t (&hi)[8], uint32_t (&lo)[8]
 				const int src = (j + SH[rr]) & 7;
 				const uint32_t w = rr < 4 ? hi[src] : lo[src];
 				const int sft = 8 * (3 - (rr & 3));  // byte rr of the big-endian column
-				const uint32_t off = sft >= 3 ? (w >> (sft - 3)) & 0x7F8u : (w << 3) & 0x7F8u;
-				const uint2 t = *reinterpret_cast<const uint2 *>(tbl + rr * 2048 + off);
-				al ^= t.x;
-				ah ^= t.y;
+				const uint32_t off = sft >= 7 ? (w >> (sft - 7)) & 0x7F80u : (w << 7) & 0x7F80u;  // entry * 128
+				const uint2 t = *reinterpret_cast<const uint2 *>(tbl + (rr & 3) * TBL + off);
+				al ^= rr < 4 ? t.x : t.y;  // rotation by 32 more bits = swapped halves
+				ah ^= rr < 4 ? t.y : t.x;
 			}
 			nh[j] = ah;
 			nl[j] = al;
@@ -80,16 +83,17 @@ __device__ __forceinline__ void compress(uint32_t (&hh)[8], uint32_t (&hl)[8], c
 	}
 }
 
-// T_0 (256 x 8 bytes, {lo, hi}) from global memory -> 8 rotated tables x REPL replicas in shared memory
+// T_0 (256 x 8 bytes, {lo, hi}) from global memory -> 4 rotated tables x 16 replicas in shared memory;
+// returns the lane's replica (byte offset lane % 16 * 8)
 __device__ __forceinline__ const uint8_t *load_tables(uint8_t *smem, const uint2 *__restrict__ t0) {
-	for (uint32_t e = threadIdx.x; e < REPL * 8 * 256; e += blockDim.x) {
-		const uint32_t x = e & 255u, rr = (e >> 8) & 7u;
+	for (uint32_t e = threadIdx.x; e < 4 * 256 * REPL; e += blockDim.x) {
+		const uint32_t rep = e & (REPL - 1), x = (e >> 4) & 255u, rr = e >> 12;
 		const uint2 v = __ldg(t0 + x);
 		const uint64_t w = ((uint64_t)v.y << 32) | v.x, rot = rr ? (w >> (8 * rr)) | (w << (64 - 8 * rr)) : w;
-		reinterpret_cast<uint2 *>(smem)[e] = make_uint2((uint32_t)rot, (uint32_t)(rot >> 32));
+		*reinterpret_cast<uint2 *>(smem + rr * TBL + x * 128 + rep * 8) = make_uint2((uint32_t)rot, (uint32_t)(rot >> 32));
 	}
 	__syncthreads();
-	return smem + (threadIdx.x & (REPL - 1)) * (8 * 2048);
+	return smem + (threadIdx.x & (REPL - 1)) * 8;
 }
 
 // digests[i] = Groestl256(data[i * leaf_bytes .. (i + 1) * leaf_bytes)); leaf_bytes a multiple of 16
