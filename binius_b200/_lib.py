@@ -20,7 +20,7 @@ SYMBOLS = [
     "b200_sumcheck_tail_finish", "b200_groestl256_leaves", "b200_groestl256_compress_pairs", "b200_merkle_build", "b200_linear_map", "b200_host_polyval_mul", "b200_host_polyval_basis_change",
     "b200_event_create", "b200_event_record", "b200_event_elapsed_ms", "b200_event_destroy",
     "b200_ctx_launch_count", "b200_dev_alloc", "b200_dev_free", "b200_host_alloc", "b200_host_free",
-    "b200_copy_h2d", "b200_copy_d2h", "b200_copy_d2d", "b200_fill", "b200_sync", "b200_results_reset",
+    "b200_copy_h2d", "b200_copy_h2d_side", "b200_side_join", "b200_copy_d2h", "b200_copy_d2d", "b200_fill", "b200_sync", "b200_results_reset",
     "b200_results_fetch", "b200_extrapolate_line", "b200_extrapolate_line_host", "b200_tensor_expand", "b200_inner_product", "b200_fold_left",
     "b200_fold_right", "b200_expr_compile", "b200_expr_free", "b200_expr_n_vars", "b200_compute_composite",
     "b200_pairwise_product_reduce", "b200_kernel_decl_value", "b200_kernel_sum_composition_evals",
@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200_ntt_destroy", "b200_ntt_log_domain_size", "b200_ntt_get_subspace_eval", "b200_ntt_forward",
     "b200_ntt_inverse", "b200_ntt_forward_host", "b200_ntt_inverse_host", "b200_fri_fold",
     "b200_tensor_product_full_query", "b200_fold_multilinears_high_to_low", "b200_eq_ind_round_evals",
-    "b200_sumcheck_round_evals", "b200_fold_multilinears_low_to_high", "b200_zerocheck_univariate_evals",
+    "b200_sumcheck_round_evals", "b200_fold_multilinears_low_to_high", "b200_zerocheck_univariate_evals", "b200_zerocheck_univariate_evals_streamed",
 ]
 
 
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
         "b200_host_free": (i32, [vp, vp]),
         "b200_copy_h2d": (i32, [vp, vp, vp, u64]),
         "b200_copy_d2h": (i32, [vp, vp, vp, u64]),
+        "b200_copy_h2d_side": (i32, [vp, vp, vp, u64]),
+        "b200_side_join": (i32, [vp]),
         "b200_copy_d2d": (i32, [vp, vp, vp, u64]),
         "b200_fill": (i32, [vp, vp, u64, P(u64)]),
         "b200_sync": (i32, [vp]),
@@ -120,6 +122,7 @@ def load() -> C.CDLL:
         "b200_sumcheck_round_evals": (i32, [vp, u32, P(vp), P(u64), P(u64), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(u32)]),
         "b200_fold_multilinears_low_to_high": (i32, [vp, P(vp), P(vp), u32, u32, P(u64), P(u64), P(u64), P(u64)]),
         "b200_zerocheck_univariate_evals": (i32, [vp, P(vp), P(u32), u32, u32, u32, vp, u64, P(vp), P(u32), u32, u32, P(u64)]),
+        "b200_zerocheck_univariate_evals_streamed": (i32, [vp, P(vp), P(vp), P(u32), u32, u32, u32, vp, u64, P(vp), P(u32), u32, u32, u32, P(u64)]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the build is stale: fail loudly

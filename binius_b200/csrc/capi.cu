@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <mutex>
 
 #include <map>
 #include <set>
@@ -53,6 +54,10 @@ struct b200_ntt {
 
 namespace b200 {
 
+__global__ void k_fetch_args(const uint4 *__restrict__ src, uint4 *__restrict__ dst, uint32_t n) {
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
 int32_t stage_args(b200_ctx *ctx, const void *host, uint64_t bytes, void **dev_out) {
 	uint64_t need = (bytes + 255) & ~255ull;
 	if (need > ARGS_BYTES) return fail(ctx, B200_ERR_ALLOC, "argument block of %llu bytes too large", (unsigned long long)bytes);
@@ -61,7 +66,13 @@ int32_t stage_args(b200_ctx *ctx, const void *host, uint64_t bytes, void **dev_o
 		ctx->args_off = 0;
 	}
 	memcpy(ctx->h_args + ctx->args_off, host, bytes);
-	B200_CUDA(ctx, cudaMemcpyAsync(ctx->d_args + ctx->args_off, ctx->h_args + ctx->args_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	if (ctx->side_uploads) {
+		// pinned host memory is device-accessible under unified addressing (cudaMallocHost)
+		k_fetch_args<<<1, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->h_args + ctx->args_off), reinterpret_cast<uint4 *>(ctx->d_args + ctx->args_off), (uint32_t)((bytes + 15) / 16));
+		B200_CUDA(ctx, cudaGetLastError());
+	} else {
+		B200_CUDA(ctx, cudaMemcpyAsync(ctx->d_args + ctx->args_off, ctx->h_args + ctx->args_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	}
 	*dev_out = ctx->d_args + ctx->args_off;
 	ctx->args_off += need;
 	return B200_OK;
@@ -623,6 +634,38 @@ int32_t b200_copy_h2d(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t
 	// pageable sources are staged synchronously by the runtime; pinned ones stay async
 	return B200_OK;
 }
+// Host-to-device copy on the context's SIDE stream: it overlaps with everything already (and subsequently) issued on the
+// main stream until b200_side_join makes the main stream wait for it.  For streaming a witness in while earlier chunks
+// are being processed (the caller keeps the destination untouched by main-stream work until the join).
+static int32_t ensure_side_streams(b200_ctx *ctx) {
+	if (ctx->s_h2d) return B200_OK;
+	B200_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+	B200_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+	for (uint32_t i = 0; i < 4; i++) {
+		B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+		B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+		B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+	}
+	return B200_OK;
+}
+int32_t b200_copy_h2d_side(b200_ctx *ctx, const void *src, b200_dev_ptr dst, uint64_t n) {
+	B200_LOCK(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (n == 0) return B200_OK;
+	int32_t rc = ensure_side_streams(ctx);
+	if (rc) return rc;
+	B200_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+	return B200_OK;
+}
+int32_t b200_side_join(b200_ctx *ctx) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	if (!ctx->s_h2d) return B200_OK;
+	B200_CUDA(ctx, cudaEventRecord(ctx->ev_in[0], ctx->s_h2d));
+	B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[0], 0));
+	return B200_OK;
+}
 int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *dst, uint64_t n) {
 	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
@@ -827,15 +870,7 @@ int32_t b200_extrapolate_line_host(b200_ctx *ctx, void *host_e0, const void *hos
 	const uint32_t NS = 4;
 	int32_t rc = ensure_scratch(ctx, NS * 2 * CH * 16);
 	if (rc) return rc;
-	if (!ctx->s_h2d) {
-		B200_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-		B200_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-		for (uint32_t i = 0; i < NS; i++) {
-			B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-			B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
-			B200_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
-		}
-	}
+	if ((rc = ensure_side_streams(ctx))) return rc;
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	uint8_t *h0 = (uint8_t *)host_e0;
 	const uint8_t *h1 = (const uint8_t *)host_e1;
@@ -2108,15 +2143,29 @@ int32_t b200_fri_fold(b200_ctx *ctx, const b200_ntt *ntt, uint32_t log_len, uint
 static void lagrange_b8(uint32_t n, uint32_t x, uint8_t *out) {
 	const hostf::Tab8 &tb = hostf::tab8();
 	auto mul = [&](uint32_t a, uint32_t b) -> uint32_t { return tb.mul[(a << 8) | b]; };
+	// node weights w_t = 1 / prod_{u != t} (t - u): computed once per n (the host-side cost of a call used to be
+	// O(points * n^2) table products, ~5 ms at n = 128, paid again by every chunk of a streamed round)
+	static std::mutex mu;
+	static std::map<uint32_t, std::vector<uint8_t>> weights;
+	const uint8_t *w;
+	{
+		std::lock_guard<std::mutex> g(mu);
+		auto it = weights.find(n);
+		if (it == weights.end()) {
+			std::vector<uint8_t> wv(n);
+			for (uint32_t t = 0; t < n; t++) {
+				uint32_t den = 1;
+				for (uint32_t u = 0; u < n; u++)
+					if (u != t) den = mul(den, t ^ u);
+				wv[t] = (uint8_t)hostf::invert((hostf::u128)den, 3);
+			}
+			it = weights.emplace(n, std::move(wv)).first;
+		}
+		w = it->second.data();
+	}
 	uint32_t full = 1;
 	for (uint32_t u = 0; u < n; u++) full = mul(full, x ^ u);
-	for (uint32_t t = 0; t < n; t++) {
-		uint32_t den = 1;
-		for (uint32_t u = 0; u < n; u++)
-			if (u != t) den = mul(den, t ^ u);
-		den = mul(den, x ^ t);
-		out[t] = (uint8_t)mul(full, (uint32_t)hostf::invert((hostf::u128)den, 3));
-	}
+	for (uint32_t t = 0; t < n; t++) out[t] = (uint8_t)mul(mul(full, w[t]), (uint32_t)hostf::invert((hostf::u128)(x ^ t), 3));
 }
 static uint32_t const_level(uint64_t lo, uint64_t hi) {
 	if (hi) return 7;
@@ -2126,10 +2175,12 @@ static uint32_t const_level(uint64_t lo, uint64_t hi) {
 	return 3;
 }
 
-int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint64_t *host_out) {
-	B200_LOCK(ctx);
-	B200_FLUSH(ctx);
-	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+// Validates and launches the round on the context's stream; *d_out_p = the [n_comp][n_out] device table (context scratch),
+// nullptr when there is nothing to compute.  The kernels XOR into the table: `zero_out` clears it first, `extend` runs the
+// (linear) domain extension afterwards -- a caller summing several sub-cube ranges clears once and extends once.  The caller copies it back (and may issue other copies first: the argument
+// blocks of this call are already queued on the copy engine).
+static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint4 **d_out_p, bool zero_out = true, bool extend = true) {
+	*d_out_p = nullptr;
 	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
 	if (n_vars - skip > 40) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars - skip_rounds must be <= 40");
 	if (n_eq != (1ull << (n_vars - skip))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectZerocheckChallengesLength: eq_ind must hold 2^(n_vars - skip_rounds) elements");
@@ -2151,13 +2202,12 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 	if (lvl == 6) lvl = 7;
 	const uint32_t K = 1u << skip, n_out = max_domain_size - K;
 	if (n_out == 0 || n_comp == 0) return B200_OK;
-	if (!host_out) return B200_ERR_INPUT_VALIDATION;
 	const uint32_t n_pts = max_deg > 1 ? (max_deg - 1) << skip : 0;
 
 	int32_t rc = ensure_scratch(ctx, (uint64_t)n_comp * n_out * 16);
 	if (rc) return rc;
 	uint4 *d_out = reinterpret_cast<uint4 *>(ctx->d_scratch);
-	B200_CUDA(ctx, cudaMemsetAsync(d_out, 0, (uint64_t)n_comp * n_out * 16, ctx->stream));
+	if (zero_out) B200_CUDA(ctx, cudaMemsetAsync(d_out, 0, (uint64_t)n_comp * n_out * 16, ctx->stream));
 	if (n_pts) {
 		std::vector<uint8_t> lag((size_t)n_pts * K);
 		for (uint32_t i = 0; i < n_pts; i++) lagrange_b8(K, K + i, lag.data() + (size_t)i * K);
@@ -2250,9 +2300,12 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 				return B.off_bits + ml * K + 16;  // ml * (SUBS * K / 32) words
 			};
 			auto fits = [&](uint32_t smem8, uint32_t ml) { return smem8 <= 227u * 1024u && ml * (uni::SUBS * K / 32) <= 8 * uni::B8_THREADS; };
-			// one launch over compositions [c0, c0 + nc) (rows c0.. of the output table) and the given column list
-			auto launch = [&](uni::B8Args &B, uint32_t smem8, const uint4 *const *d_mls, const uint32_t *d_levels, uint32_t ml, uint32_t c0, uint32_t nc,
-							  const std::vector<uint2> &mn, const std::vector<uint32_t> &ct) -> int32_t {
+			// one launch over compositions [c0, c0 + nc) (rows c0.. of the output table) and the given column list.
+			// Two steps, so that a multi-range call stages ALL its argument blocks before its first kernel: an argument copy
+			// queued between two kernels would wait behind whatever else occupies the host-to-device copy engine by then
+			// (the next witness chunk of b200_zerocheck_univariate_evals_streamed) and stall the remaining ranges.
+			auto stage = [&](uni::B8Args &B, const uint4 *const *d_mls, const uint32_t *d_levels, uint32_t ml, uint32_t c0, uint32_t nc,
+							 const std::vector<uint2> &mn, const std::vector<uint32_t> &ct) -> int32_t {
 				ArgPack pk2;
 				size_t o_m = pk2.add(mn.data(), 8 * mn.size()), o_t = pk2.add(ct.data(), 4 * ct.size());
 				uint8_t *base2;
@@ -2262,6 +2315,10 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 				B.mono = (const uint2 *)(base2 + o_m);
 				B.comp_tab = (const uint32_t *)(base2 + o_t);
 				B.m = ml, B.n_comp = nc, B.n_mono = (uint32_t)mn.size(), B.n_out = n_out;
+				return B200_OK;
+			};
+			auto launch = [&](const uni::B8Args &B, uint32_t smem8) -> int32_t {
+				int32_t r;
 				const uint64_t n_batches = (n_eq + uni::SUBS - 1) / uni::SUBS;
 				dim3 grid8((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_batches, std::max(1u, (uint32_t)ctx->n_sms / gy))), gy);
 #define B200_UNI_B8(S)                                                                          \
@@ -2283,7 +2340,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 			uni::B8Args B;
 			const uint32_t smem8 = layout(B, m, n_comp, mono.size());
 			if (fits(smem8, m)) {
-				if ((rc = launch(B, smem8, A.mls, A.levels, m, 0, n_comp, mono, ctab))) return rc;
+				if ((rc = stage(B, A.mls, A.levels, m, 0, n_comp, mono, ctab)) || (rc = launch(B, smem8))) return rc;
 			} else {
 				// Too many columns for one CTA's shared memory (e.g. 153 columns at skip 7): constraints are local,
 				// so split the compositions into contiguous ranges whose referenced columns fit and launch the same
@@ -2299,6 +2356,7 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 					uni::B8Args probe;
 					return fits(layout(probe, ncols, ncomp, nm_all), ncols);
 				}, ranges);
+				std::vector<std::pair<uni::B8Args, uint32_t>> staged;
 				for (size_t ri = 0; fast && ri < ranges.size(); ri++) {
 					const uni::SplitRange &R = ranges[ri];
 					std::vector<b200_dev_ptr> h_mls;
@@ -2323,8 +2381,12 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 					uni::B8Args Br;
 					const uint32_t ml = (uint32_t)h_mls.size();
 					const uint32_t sm = layout(Br, ml, R.c1 - R.c0, mn.size());
-					if ((rc = launch(Br, sm, (const uint4 *const *)(base3 + o_p), (const uint32_t *)(base3 + o_l), ml, R.c0, R.c1 - R.c0, mn, R.ctab))) return rc;
-					if (ri + 1 < ranges.size()) B200_LAUNCH_CHECK(ctx);
+					if ((rc = stage(Br, (const uint4 *const *)(base3 + o_p), (const uint32_t *)(base3 + o_l), ml, R.c0, R.c1 - R.c0, mn, R.ctab))) return rc;
+					staged.emplace_back(Br, sm);
+				}
+				for (size_t ri = 0; fast && ri < staged.size(); ri++) {
+					if ((rc = launch(staged[ri].first, staged[ri].second))) return rc;
+					if (ri + 1 < staged.size()) B200_LAUNCH_CHECK(ctx);
 				}
 			}
 		}
@@ -2347,14 +2409,93 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 			break;
 		}
 		B200_LAUNCH_CHECK(ctx);
-		if (need_ext) {
+		if (need_ext && extend) {
 			uni::ExtArgs X{A.comp_pts, (const uint32_t *)(base + o_eo), base + o_e, d_out, n_out};
 			if ((rc = set_smem(ctx, uni::k_uni_extend, FIELD_TABLE_BYTES))) return rc;
 			uni::k_uni_extend<<<n_comp, 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, X);
 			B200_LAUNCH_CHECK(ctx);
 		}
 	}
-	B200_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (uint64_t)n_comp * n_out * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	*d_out_p = d_out;
+	return B200_OK;
+}
+
+int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint64_t *host_out) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	uint4 *d_out;
+	int32_t rc = uni_issue(ctx, mls, levels, m, n_vars, skip, eq_ind, n_eq, comps, degrees, n_comp, max_domain_size, &d_out);
+	if (rc || !d_out) return rc;
+	if (!host_out) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (uint64_t)n_comp * (max_domain_size - (1u << skip)) * 16, cudaMemcpyDeviceToHost, ctx->stream));
 	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return B200_OK;
+}
+
+// The same round with the witness still in HOST memory: column j (pinned, packed as on the device) is uploaded into mls[j]
+// in 2^log_chunks row chunks on the side stream while the previous chunk is evaluated -- the round values are XOR-sums
+// over sub-cubes and the domain extension is linear, so the chunks' tables add up.  The kernels of chunk c are issued
+// BEFORE the copies of chunk c + 1: their (small) argument blocks travel through the same host-to-device copy engine
+// and would otherwise queue behind 1/2^log_chunks of the witness.  Afterwards the columns are resident in mls[].
+int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *const *host_cols, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint32_t log_chunks, uint64_t *host_out) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !host_cols || !mls || !levels) return B200_ERR_INPUT_VALIDATION;
+	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
+	if (n_eq != (1ull << (n_vars - skip))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectZerocheckChallengesLength: eq_ind must hold 2^(n_vars - skip_rounds) elements");
+	if (m == 0) return fail(ctx, B200_ERR_INPUT_VALIDATION, "NumberOfVariablesMismatch: no multilinears");
+	log_chunks = std::min(log_chunks, n_vars - skip);
+	for (uint32_t j = 0; j < m; j++) {
+		if (!valid_level(levels[j])) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u: unsupported tower level %u", j, levels[j]);
+		if (!host_cols[j] || !mls[j]) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u is null", j);
+		while (log_chunks && (((1ull << (n_vars - log_chunks)) << levels[j]) & 127)) log_chunks--;  // a chunk of every column is whole B128 words
+	}
+	int32_t rc = ensure_side_streams(ctx);
+	if (rc) return rc;
+	const uint32_t n_chunks = 1u << log_chunks;
+	const uint64_t sub_per_chunk = n_eq >> log_chunks;
+	const uint64_t n_vals = max_domain_size > (1u << skip) ? (uint64_t)n_comp * (max_domain_size - (1u << skip)) : 0;
+	std::vector<uint64_t> bytes(m);
+	for (uint32_t j = 0; j < m; j++) bytes[j] = std::max<uint64_t>(((1ull << (n_vars - log_chunks)) << levels[j]) / 8, 1);
+	auto upload = [&](uint32_t c) -> int32_t {
+		for (uint32_t j = 0; j < m; j++)
+			B200_CUDA(ctx, cudaMemcpyAsync((uint8_t *)mls[j] + c * bytes[j], (const uint8_t *)host_cols[j] + c * bytes[j], bytes[j], cudaMemcpyHostToDevice, ctx->s_h2d));
+		B200_CUDA(ctx, cudaEventRecord(ctx->ev_in[c & 3], ctx->s_h2d));
+		return B200_OK;
+	};
+	std::vector<b200_dev_ptr> ptrs(m);
+	for (uint32_t c = 0; c < n_comp; c++)  // the lazy device copies of the expressions go first, while the copy engine is idle
+		if (comps[c]) {
+			DevExpr de = dev_expr(comps[c]);
+			B200_EXPR_READY(ctx, de);
+		}
+	struct SideFlag {  // argument blocks bypass the copy engine while the witness is in flight (stage_args)
+		b200_ctx *c;
+		explicit SideFlag(b200_ctx *x) : c(x) { c->side_uploads = true; }
+		~SideFlag() { c->side_uploads = false; }
+	} side_flag(ctx);
+	if ((rc = upload(0))) return rc;
+	uint4 *d_out = nullptr;
+	// no host synchronisation inside the loop: the chunks XOR into one device table, so the host-side planning of chunk
+	// c + 1 overlaps with the kernels of chunk c, and every copy is queued as early as it can be
+	for (uint32_t c = 0; c < n_chunks; c++) {
+		B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c & 3], 0));
+		for (uint32_t j = 0; j < m; j++) ptrs[j] = (b200_dev_ptr)((uint8_t *)mls[j] + c * bytes[j]);
+		rc = uni_issue(ctx, ptrs.data(), levels, m, n_vars - log_chunks, skip, (b200_dev_ptr)((uint4 *)eq_ind + c * sub_per_chunk), sub_per_chunk, comps, degrees, n_comp, max_domain_size, &d_out,
+					   c == 0, c + 1 == n_chunks);
+		if (rc) {
+			cudaStreamSynchronize(ctx->s_h2d);
+			cudaStreamSynchronize(ctx->stream);
+			return rc;
+		}
+		if (c + 1 < n_chunks && (rc = upload(c + 1))) return rc;
+	}
+	if (d_out) {
+		if (!host_out) return B200_ERR_INPUT_VALIDATION;
+		B200_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, 16 * n_vals, cudaMemcpyDeviceToHost, ctx->stream));
+		B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[(n_chunks - 1) & 3], 0));
 	return B200_OK;
 }

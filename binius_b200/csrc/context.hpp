@@ -50,6 +50,10 @@ struct b200_ctx {
 	// copy streams + events of the host-buffer pipeline (b200_extrapolate_line_host), created lazily
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
 	cudaEvent_t ev_in[4] = {}, ev_k[4] = {}, ev_out[4] = {};
+	// true while side-stream uploads may occupy the host-to-device copy engine: argument blocks are then fetched by a
+	// one-CTA kernel from the (mapped) pinned mirror instead of a copy that would queue behind the upload -- the engine
+	// does not arbitrate between streams, it drains the side stream's queue first (measured: tools/mb_overlap.cu)
+	bool side_uploads = false;
 	std::string err;
 	uint64_t launches = 0;
 	std::vector<b200_pending_lerp> pending;

@@ -25,6 +25,8 @@ import enum
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple, Union
 
+import numpy as np
+
 from .layer import (ArithCircuit, B200Layer, DevSlice, ExprEval, InputValidation, _u64_list, _u64x2)
 
 
@@ -158,6 +160,44 @@ def zerocheck_univariate_evals(backend: "B200Backend", multilinears: Sequence[Tr
     vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(nc * n_out)]
     return ZerocheckUnivariateEvalsOutput([vals[c * n_out:(c + 1) * n_out] for c in range(nc)], skip_rounds,
                                           remaining_rounds, max_domain_size, partial_eq_ind_evals)
+
+
+def zerocheck_univariate_evals_streamed(backend: "B200Backend", host_columns: Sequence[np.ndarray], multilinears: Sequence[TransparentMultilinear],
+                                        compositions: Sequence[ArithCircuit], zerocheck_challenges: Sequence[int],
+                                        skip_rounds: int, max_domain_size: int, log_chunks: int = 3) -> ZerocheckUnivariateEvalsOutput:
+    """The same round with the witness still in HOST memory (pinned `host_columns`, one per multilinear): the columns are
+    uploaded into `multilinears[j].evals` in 2^log_chunks row chunks on the side stream while the previous chunk is
+    evaluated (b200_zerocheck_univariate_evals_streamed) -- the round values are XOR-sums over sub-cubes, so the chunks' values add up and the
+    reference's domain extension is linear --, i.e. the witness upload hides behind the univariate round.  Afterwards
+    the columns are resident on the device for the multilinear rounds."""
+    if not multilinears or len(host_columns) != len(multilinears):
+        raise InputValidation("one host column per multilinear")
+    n_vars = multilinears[0].n_vars
+    remaining = n_vars - skip_rounds
+    if remaining < 0 or len(zerocheck_challenges) != remaining:
+        raise InputValidation("IncorrectZerocheckChallengesLength")
+    degrees = [_degree(c) for c in compositions]
+    if max_domain_size < domain_size(max(degrees, default=0), skip_rounds):
+        raise InputValidation("LagrangeDomainTooSmall")
+    if max_domain_size > 256:
+        raise InputValidation("DomainSizeTooLarge")
+    for ml, h in zip(multilinears, host_columns):
+        if ml.n_vars != n_vars or h.nbytes < max(((1 << n_vars) << ml.tower_level) // 8, 1):
+            raise InputValidation("NumberOfVariablesMismatch")
+    L = backend._l
+    eq = backend.tensor_product_full_query(zerocheck_challenges)
+    m, nc = len(multilinears), len(compositions)
+    n_out = max_domain_size - (1 << skip_rounds)
+    hosts = (C.c_void_p * m)(*[h.ctypes.data for h in host_columns])
+    ptrs = (C.c_void_p * m)(*[ml.evals.ptr for ml in multilinears])
+    lvls = (C.c_uint32 * m)(*[ml.tower_level for ml in multilinears])
+    comps = (C.c_void_p * max(nc, 1))(*[backend._compiled(c)[0].handle.value for c in compositions])
+    degs = (C.c_uint32 * max(nc, 1))(*degrees)
+    out = (C.c_uint64 * max(2 * nc * n_out, 2))()
+    L._check(L._lib.b200_zerocheck_univariate_evals_streamed(L._ctx, hosts, ptrs, lvls, m, n_vars, skip_rounds, eq.ptr, 1 << remaining, comps, degs, nc,
+                                                             max_domain_size, max(0, log_chunks), out))
+    vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(nc * n_out)]
+    return ZerocheckUnivariateEvalsOutput([vals[c * n_out:(c + 1) * n_out] for c in range(nc)], skip_rounds, remaining, max_domain_size, eq)
 
 
 class B200Backend:

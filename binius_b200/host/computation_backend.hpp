@@ -335,4 +335,42 @@ inline ZerocheckUnivariateEvalsOutput zerocheck_univariate_evals(B200Backend &ba
 	return out;
 }
 
+// The same round with the witness columns still in (pinned) HOST memory: b200_zerocheck_univariate_evals_streamed uploads
+// host_columns[j] into multilinears[j].evals chunk by chunk behind the evaluation of the previous chunk; afterwards the
+// columns are device-resident for the multilinear rounds.  Values are identical to copy_h2d + zerocheck_univariate_evals.
+inline ZerocheckUnivariateEvalsOutput zerocheck_univariate_evals_streamed(B200Backend &backend, const std::vector<const void *> &host_columns,
+																		   const std::vector<SumcheckMultilinear> &multilinears,
+																		   const std::vector<const ExprEval *> &compositions,
+																		   const std::vector<uint32_t> &composition_degrees,
+																		   const std::vector<F128> &zerocheck_challenges, uint32_t skip_rounds,
+																		   uint32_t max_domain_size, uint32_t log_chunks = 3) {
+	if (multilinears.empty() || host_columns.size() != multilinears.size()) throw InputValidation(1, "NumberOfVariablesMismatch: one host column per multilinear");
+	const uint32_t n_vars = multilinears[0].n_vars;
+	for (auto &m : multilinears)
+		if (m.kind != SumcheckMultilinear::Transparent || m.n_vars != n_vars) throw InputValidation(1, "NumberOfVariablesMismatch");
+	if (skip_rounds > n_vars) throw InputValidation(1, "TooManySkippedRounds");
+	if (zerocheck_challenges.size() != n_vars - skip_rounds) throw InputValidation(1, "IncorrectZerocheckChallengesLength");
+	if (compositions.size() != composition_degrees.size()) throw InputValidation(1, "one degree per composition");
+	uint32_t max_deg = 0;
+	for (uint32_t d : composition_degrees) max_deg = std::max(max_deg, d);
+	if ((uint64_t)max_domain_size < ((uint64_t)max_deg << skip_rounds)) throw InputValidation(1, "LagrangeDomainTooSmall");
+	if (max_domain_size > 256) throw InputValidation(1, "DomainSizeTooLarge");
+	ZerocheckUnivariateEvalsOutput out;
+	out.skip_rounds = skip_rounds, out.remaining_rounds = n_vars - skip_rounds, out.max_domain_size = max_domain_size;
+	out.partial_eq_ind_evals = backend.tensor_product_full_query(zerocheck_challenges);
+	std::vector<b200_dev_ptr> ptrs;
+	std::vector<uint32_t> levels;
+	for (auto &m : multilinears) { ptrs.push_back(m.evals.ptr); levels.push_back(m.tower_level); }
+	std::vector<const b200_expr *> exprs;
+	for (auto *c : compositions) exprs.push_back(c->raw());
+	const uint32_t n_out = max_domain_size - (1u << skip_rounds);
+	std::vector<F128> flat(std::max<size_t>(compositions.size() * n_out, 1));
+	B200Layer &l = backend.layer();
+	l.check(b200_zerocheck_univariate_evals_streamed(l.ctx(), host_columns.data(), ptrs.data(), levels.data(), (uint32_t)ptrs.size(), n_vars, skip_rounds,
+													 out.partial_eq_ind_evals.ptr, out.partial_eq_ind_evals.n, exprs.data(), composition_degrees.data(),
+													 (uint32_t)exprs.size(), max_domain_size, log_chunks, (uint64_t *)flat.data()));
+	for (size_t c = 0; c < compositions.size(); c++) out.round_evals.emplace_back(flat.begin() + c * n_out, flat.begin() + (c + 1) * n_out);
+	return out;
+}
+
 }  // namespace binius_b200

@@ -94,6 +94,11 @@ int32_t b200_host_free(b200_ctx *ctx, void *p);
 
 int32_t b200_copy_h2d(b200_ctx *ctx, const void *host_src, b200_dev_ptr dst, uint64_t n_elems);
 int32_t b200_copy_d2h(b200_ctx *ctx, b200_dev_ptr src, void *host_dst, uint64_t n_elems); /* synchronous */
+/* copy_h2d on the context's SIDE stream (pinned source): overlaps with the work of the main stream until
+ * b200_side_join makes the main stream wait for every side copy issued so far.  For streaming a witness in while
+ * earlier chunks are processed; the destination must not be used by main-stream work before the join. */
+int32_t b200_copy_h2d_side(b200_ctx *ctx, const void *host_src, b200_dev_ptr dst, uint64_t n_elems);
+int32_t b200_side_join(b200_ctx *ctx);
 int32_t b200_copy_d2d(b200_ctx *ctx, b200_dev_ptr src, b200_dev_ptr dst, uint64_t n_elems);
 /* ComputeLayer::fill (layer.rs:74-87) */
 int32_t b200_fill(b200_ctx *ctx, b200_dev_ptr dst, uint64_t n_elems, const uint64_t value[2]);
@@ -329,6 +334,18 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *multi
 										b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *compositions,
 										const uint32_t *composition_degrees, uint32_t n_compositions,
 										uint32_t max_domain_size, uint64_t *host_round_evals);
+
+/* The same round with the witness still in HOST memory (ComputeLayer::copy_h2d of the columns fused into the round):
+ * host_columns[j] (pinned; same packing as the device column) is uploaded into multilins[j] in 2^log_chunks row chunks
+ * on the context's side stream while the previous chunk is evaluated -- the round values are XOR-sums over sub-cubes and
+ * the domain extension is linear, so the per-chunk tables add up; values are identical to upload + the call above.
+ * log_chunks is reduced until a chunk of every column is whole B128 words.  Afterwards the columns are resident in
+ * multilins[] for the multilinear rounds.  Same errors as above. */
+int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *const *host_columns, const b200_dev_ptr *multilins,
+												 const uint32_t *tower_levels, uint32_t n_multilins, uint32_t n_vars, uint32_t skip_rounds,
+												 b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *compositions,
+												 const uint32_t *composition_degrees, uint32_t n_compositions,
+												 uint32_t max_domain_size, uint32_t log_chunks, uint64_t *host_round_evals);
 
 #ifdef __cplusplus
 }

@@ -189,3 +189,39 @@ def test_many_columns_at_the_reference_skip(hal, oracle, generic):
     finally:
         hal.set_tuning("uni_generic", 0)
     assert got == exp
+
+
+@pytest.mark.parametrize("skip,log_chunks", [(7, 2), (5, 3), (3, 1)])
+def test_streamed_round_equals_the_resident_one(hal, oracle, skip, log_chunks):
+    """zerocheck_univariate_evals_streamed: the witness starts in pinned host memory and is uploaded chunk by chunk on the
+    side stream while the previous chunk is evaluated; values, eq-indicator and the uploaded columns must equal the
+    resident call's (mixed B1 / B8 columns, degree 2 and 3 compositions -> the domain extension runs per chunk)."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals, zerocheck_univariate_evals_streamed
+
+    be = B200Backend(hal)
+    rng = random.Random(skip)
+    n_vars = 13
+    levels = [0, 0, 0, 3, 0]
+    host_cols = []
+    for j, lvl in enumerate(levels):
+        h = hal.host_alloc((1 << n_vars << lvl) // 128)
+        h[:] = oracle.rand_b128(7000 + j, len(h))
+        host_cols.append(h)
+    v = [A.var(i) for i in range(5)]
+    comps = [v[0] * v[1] + v[2] + v[4], v[3] * v[4] + A.constant(0x35) * v[0]]
+    if skip < 7:  # degree 3 at skip 7 would need a 384-point domain (> 256 = |B8|)
+        comps.append(v[0] * v[2] * v[4] + v[1])
+    max_domain = min(3 << skip, 256)
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    resident = [TransparentMultilinear(hal.to_device(h.copy()), lvl, n_vars) for h, lvl in zip(host_cols, levels)]
+    exp = zerocheck_univariate_evals(be, resident, comps, ch, skip, max_domain)
+    dst = [TransparentMultilinear(hal.dev_alloc(len(h)), lvl, n_vars) for h, lvl in zip(host_cols, levels)]
+    for d in dst:
+        hal.fill(d.evals, 0)
+    hal.sync()
+    got = zerocheck_univariate_evals_streamed(be, host_cols, dst, comps, ch, skip, max_domain, log_chunks)
+    assert got.round_evals == exp.round_evals
+    assert np.array_equal(hal.to_host(got.partial_eq_ind_evals), hal.to_host(exp.partial_eq_ind_evals))
+    for d, h in zip(dst, host_cols):
+        assert np.array_equal(hal.to_host(d.evals), h)
