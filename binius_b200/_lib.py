@@ -61,7 +61,7 @@ def load() -> C.CDLL:
         "b200_flush": (i32, [vp]),
         "b200_host_mul128": (None, [P(u64), P(u64), P(u64)]),
         "b200_linear_map": (i32, [vp, vp, vp, u64, P(u64)]),
-        "b200_sumcheck_tail_start": (i32, [vp, P(vp), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, P(vp)]),
+        "b200_sumcheck_tail_start": (i32, [vp, P(vp), u32, u32, vp, P(vp), P(vp), u32, P(u32), P(u64), u32, u32, P(vp)]),
         "b200_sumcheck_tail_round_evals": (i32, [vp, P(u64)]),
         "b200_sumcheck_tail_challenge": (i32, [vp, P(u64)]),
         "b200_sumcheck_tail_finish": (i32, [vp]),

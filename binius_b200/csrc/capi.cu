@@ -22,6 +22,7 @@
 #include "groestl.cuh"
 #include "roundevals_tc.cuh"
 #include "univariate.cuh"
+#include "tail_grid.cuh"
 #include "uni_split.hpp"
 
 using namespace b200;
@@ -448,6 +449,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_eq_ind_vals, FIELD_TABLE_BYTES);
 	SET(k_eq_scale, FIELD_TABLE_BYTES);
 	SET(k_sumcheck_tail, FIELD_TABLE_BYTES);
+	SET(k_sumcheck_tail_grid, ((FIELD_TABLE_BYTES + 127) & ~127u) + 16 * TG_MAX_VALS);
 	SET(k_fri_fold, FIELD_TABLE_BYTES);
 	SET(k_fri_lerp_k64<1>, 1 * LUT_BYTES + 6144 + NLUT_BYTES);
 	SET(k_fri_lerp_k64<2>, 2 * LUT_BYTES + 6144 + NLUT_BYTES);
@@ -508,6 +510,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
 	for (auto &c : ctx->local_pool) cudaFree(c.p);
 	if (ctx->h_tail_mb) cudaFreeHost(ctx->h_tail_mb);
+	if (ctx->d_tail_ws) cudaFree(ctx->d_tail_ws);
 	if (ctx->s_h2d) {
 		cudaStreamDestroy(ctx->s_h2d);
 		cudaStreamDestroy(ctx->s_d2h);
@@ -555,6 +558,7 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	else if (!strcmp(key, "fold")) ctx->tune_fold = value;
 	else if (!strcmp(key, "round_evals_tc")) ctx->tune_round_evals_tc = value;
 	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
+	else if (!strcmp(key, "tail_grid")) ctx->tune_tail_grid = value;
 	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
 	return B200_OK;
 }
@@ -1668,11 +1672,12 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 // ---- persistent tail of an eq-ind sumcheck ---------------------------------------------------------------
 int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps,
 								 const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points,
-								 b200_tail **out) {
+								 uint32_t first_round_skip, b200_tail **out) {
 	B200_LOCK(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !out || !eq_ind) return B200_ERR_INPUT_VALIDATION;
-	if (n_vars == 0 || n_vars > 20) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: n_vars must be in [1, 20]");
+	if (n_vars == 0 || n_vars > 28) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: n_vars must be in [1, 28]");
+	if (first_round_skip >= n_points) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: the first round must keep at least one evaluation point");
 	const uint32_t n_vals = n_comp * n_points;
 	if (n_vals == 0 || n_vals > 4096) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: 1..4096 (composition, point) pairs");
 	for (uint32_t c = 0; c < n_comp; c++)
@@ -1731,7 +1736,28 @@ int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_
 	A.mb_chal = (volatile uint4 *)(t->d_mb + t->off_chal), A.mb_chal_seq = (volatile uint32_t *)(t->d_mb + t->off_chal_seq);
 	A.status = (volatile uint32_t *)(t->d_mb + t->off_status);
 	A.timeout_ns = 5ull * 1000 * 1000 * 1000;
-	k_sumcheck_tail<<<1, 1024, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	// more than one warp-chunk of hypercube indices: the co-resident grid (tail_grid.cuh); else one CTA
+	const uint64_t n_chunks = ((1ull << (n_vars - 1)) + 31) >> 5;
+	if (n_chunks > 1 && n_vals <= TG_MAX_VALS && ctx->tune_tail_grid) {
+		constexpr size_t WS_ACC = 28 * (size_t)TG_MAX_VALS * 16, WS_BYTES = WS_ACC + 28 * 16 + 28 * 4 + 16;
+		if (!ctx->d_tail_ws) B200_CUDA(ctx, cudaMalloc((void **)&ctx->d_tail_ws, WS_BYTES));
+		B200_CUDA(ctx, cudaMemsetAsync(ctx->d_tail_ws, 0, (size_t)n_vars * n_vals * 16, ctx->stream));
+		B200_CUDA(ctx, cudaMemsetAsync(ctx->d_tail_ws + WS_ACC, 0, WS_BYTES - WS_ACC, ctx->stream));
+		TailGridArgs GA;
+		GA.t = A;
+		GA.acc = (uint4 *)ctx->d_tail_ws, GA.g_chal = (uint4 *)(ctx->d_tail_ws + WS_ACC);
+		GA.g_chal_seq = (uint32_t *)(ctx->d_tail_ws + WS_ACC + 28 * 16), GA.bar = GA.g_chal_seq + 28, GA.g_abort = GA.bar + 1;
+		GA.first_skip = first_round_skip;
+		uint32_t G = 1;
+		while (G * 2 <= std::min<uint64_t>({(uint64_t)TG_MAX_CTAS, n_chunks, (uint64_t)ctx->n_sms})) G *= 2;
+		const uint8_t *tables = ctx->d_tables;
+		void *kargs[] = {(void *)&tables, (void *)&GA};
+		B200_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_sumcheck_tail_grid, dim3(G), dim3(TG_THREADS), kargs,
+												   ((FIELD_TABLE_BYTES + 127) & ~127u) + 16 * (size_t)n_vals, ctx->stream));
+	} else {
+		if (first_round_skip) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: first_round_skip needs the grid kernel (more than 32 hypercube points, at most 1024 values)");
+		k_sumcheck_tail<<<1, 1024, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	}
 	B200_LAUNCH_CHECK(ctx);
 	ctx->tail_active = true;
 	*out = t.release();

@@ -82,6 +82,7 @@ struct b200_ctx {
 	// host-mapped mailbox of the persistent sumcheck tail (b200_sumcheck_tail_*), allocated on first use
 	uint8_t *h_tail_mb = nullptr, *d_tail_mb = nullptr;
 	size_t tail_mb_bytes = 0;
+	uint8_t *d_tail_ws = nullptr;  // device workspace of the grid variant (accumulators, barrier, challenge relay)
 	bool tail_active = false;
 	std::vector<void *> deferred_free;  // device releases that arrived while a tail was running
 	// kernel-selection switches for A/B measurements (b200_ctx_set_tuning); defaults = production paths
@@ -92,6 +93,7 @@ struct b200_ctx {
 	int tune_fold = 2;             // 2 TMA-staged K64, 1 K64, 0 LUT128
 	int tune_round_evals_tc = 1;   // 1 tensor-core plans, 0 per-lane kernels, 2 materialised values only
 	int tune_uni_generic = 0;      // 1 forces the generic univariate-skip kernel
+	int tune_tail_grid = 1;        // 0: the persistent sumcheck tail always runs on one CTA
 };
 
 namespace b200 {

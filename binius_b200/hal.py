@@ -214,11 +214,13 @@ class B200Backend:
         self._mine = {}
         self._free = []
         # persistent sumcheck tail (b200_sumcheck_tail_*): when the (composition, point, hypercube index) triples of a
-        # round drop below `tail_threshold`, the remaining rounds of an eq-ind prover run in ONE kernel and the trait
+        # round drop below `tail_threshold` (2^20: above it the tensor-core route of the separate calls is faster than
+        # the per-lane products of the persistent kernel), the remaining rounds of an eq-ind prover -- all of them for
+        # a cache-sized instance like BASELINE config #3 -- run in ONE kernel and the trait
         # calls of those rounds only read / post through its host-mapped mailboxes
         # (opt-in: while the tail kernel runs it owns the context's stream -- any other call on the layer is refused --,
         # so only a caller whose round loop does nothing else on the layer, like the prover's, should switch it on)
-        self.tail_threshold = (1 << 8) if sumcheck_tail else 0
+        self.tail_threshold = (1 << 20) if sumcheck_tail else 0
         self._tail = None
 
     def _take(self, n: int) -> DevSlice:
@@ -343,16 +345,20 @@ class B200Backend:
 
     # -- persistent tail -------------------------------------------------------------------------------------------
     def _tail_eligible(self, n_vars, multilinears, evaluators, weighted, order, codes) -> bool:
-        if not self.tail_threshold or not weighted or order != EvaluationOrder.HighToLow or n_vars > 20:
-            return False
-        if any(ev.have_first_round_eval_1s for ev in evaluators):  # the first round of a prover has its own point set
+        if not self.tail_threshold or not weighted or order != EvaluationOrder.HighToLow or n_vars > 28:
             return False
         if any(not isinstance(ml, FoldedMultilinear) or ml.evals.len() != 1 << n_vars for ml in multilinears):
             return False
-        return (len(evaluators) * len(codes)) << (n_vars - 1) <= self.tail_threshold
+        n_vals = len(evaluators) * (codes[-1] + 1 - 1)  # the tail computes the points 1..hi-1 of every evaluator
+        grid = n_vars - 1 > 5  # more than 32 hypercube points: the co-resident grid kernel
+        if (grid and n_vals > 1024) or (not grid and (n_vals > 4096 or codes[0] != 1)):
+            return False
+        return n_vals << (n_vars - 1) <= self.tail_threshold
 
     def _tail_round_evals(self, n_vars, multilinears, evaluators, eq_ind, codes, pts, lo):
         L = self._l
+        hi = codes[-1] + 1
+        n_codes = hi - 1  # the tail's point list is 1..hi-1 in every round; a prover's first round starts at `lo` = 2
         if self._tail is None:
             compiled = [self._compiled(ev.composition) for ev in evaluators]
             m = len(multilinears)
@@ -361,16 +367,18 @@ class B200Backend:
             leads = (C.c_void_p * len(evaluators))(*[c[1].handle.value for c in compiled])
             h = C.c_void_p()
             L._check(L._lib.b200_sumcheck_tail_start(L._ctx, ptrs, m, n_vars, eq_ind.ptr, comps, leads, len(evaluators),
-                                                     (C.c_uint32 * len(codes))(*codes), _u64_list(pts), len(codes), C.byref(h)))
-            self._tail = {"h": h, "n_vars": n_vars, "n_comp": len(evaluators), "codes": list(codes), "eq_ptr": eq_ind.ptr, "eq_pending": 0}
+                                                     (C.c_uint32 * n_codes)(*range(1, hi)), _u64_list([0] * (lo - 1) + list(pts)), n_codes, lo - 1,
+                                                     C.byref(h)))
+            self._tail = {"h": h, "n_vars": n_vars, "n_comp": len(evaluators), "hi": hi, "eq_ptr": eq_ind.ptr, "eq_pending": 0, "first": True}
         t = self._tail
-        if t["n_vars"] != n_vars or t["n_comp"] != len(evaluators) or t["codes"] != list(codes):
+        if t["n_vars"] != n_vars or t["n_comp"] != len(evaluators) or t["hi"] != hi or (lo != 1 and not t["first"]):
             raise InputValidation("the running sumcheck tail was started for a different round shape")
-        total = len(evaluators) * len(codes)
+        t["first"] = False
+        total = len(evaluators) * n_codes
         out = (C.c_uint64 * (2 * total))()
         L._check(L._lib.b200_sumcheck_tail_round_evals(t["h"], out))
         vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(total)]
-        return [[vals[e * len(codes) + (k - lo)] for k in ev.eval_point_indices()] for e, ev in enumerate(evaluators)]
+        return [[vals[e * n_codes + (k - 1)] for k in ev.eval_point_indices()] for e, ev in enumerate(evaluators)]
 
     def _tail_fold(self, n_vars, multilinears, challenge):
         L, t = self._l, self._tail

@@ -61,7 +61,8 @@ class B200Backend {
 	// a caller whose round loop does nothing else on the layer (the prover's) should switch it on
 	uint64_t tail_threshold_ = 0;
 	b200_tail *tail_ = nullptr;
-	uint32_t tail_vars_ = 0, tail_eq_pending_ = 0;
+	uint32_t tail_vars_ = 0, tail_eq_pending_ = 0, tail_hi_ = 0;
+	bool tail_first_ = false;
 	uint8_t *tail_eq_ptr_ = nullptr;
 	std::map<uint8_t *, uint64_t> mine_;
 	std::vector<std::pair<uint8_t *, uint64_t>> free_, all_;
@@ -107,7 +108,7 @@ class B200Backend {
 	}
 
   public:
-	explicit B200Backend(B200Layer &l, bool sumcheck_tail = false) : l_(l), tail_threshold_(sumcheck_tail ? (1u << 8) : 0) {}
+	explicit B200Backend(B200Layer &l, bool sumcheck_tail = false) : l_(l), tail_threshold_(sumcheck_tail ? (1u << 20) : 0) {}
 	~B200Backend() {
 		for (auto &b : all_) b200_dev_free(l_.ctx(), b.first);
 	}
@@ -133,31 +134,37 @@ class B200Backend {
 		std::vector<uint32_t> codes;
 		std::vector<F128> pts;
 		for (uint32_t c = lo; c < hi; c++) { codes.push_back(c); pts.push_back(c < 3 ? F128{} : nontrivial_evaluation_points[c - 3]); }
-		// ---- persistent tail: start it when the round is small enough, then only read its mailbox
+		// ---- persistent tail: start it when the round is small enough, then only read its mailbox.  The tail's point
+		//      list is 1..hi-1 in every round; a prover's first round starts at lo = 2 (first_round_skip = lo - 1).
+		const uint32_t n_tail_codes = hi - 1;
 		bool tail_ok = tail_ != nullptr;
-		if (!tail_ok && tail_threshold_ && eq_ind_partial_evals && order == EvaluationOrder::HighToLow && n_vars <= 20 &&
-			((uint64_t)(evaluators.size() * codes.size()) << (n_vars - 1)) <= tail_threshold_) {
-			tail_ok = true;
-			for (auto &e : evaluators) tail_ok = tail_ok && e.first_point == 1;  // not the first round of a prover
+		if (!tail_ok && tail_threshold_ && eq_ind_partial_evals && order == EvaluationOrder::HighToLow && n_vars <= 28) {
+			const uint64_t n_vals = (uint64_t)evaluators.size() * n_tail_codes;
+			const bool grid = n_vars - 1 > 5;  // more than 32 hypercube points: the co-resident grid kernel
+			tail_ok = (n_vals << (n_vars - 1)) <= tail_threshold_ && (grid ? n_vals <= 1024 : (n_vals <= 4096 && lo == 1));
 			for (auto &m : multilinears) tail_ok = tail_ok && m.kind == SumcheckMultilinear::Folded && m.evals.n == (1ull << n_vars);
 			if (tail_ok) {
 				std::vector<b200_dev_ptr> p;
 				for (auto &m : multilinears) p.push_back(m.evals.ptr);
 				std::vector<const b200_expr *> cs, ls;
 				for (auto &e : evaluators) { cs.push_back(e.composition->raw()); ls.push_back(e.composition_at_infinity->raw()); }
+				std::vector<uint32_t> tc;
+				std::vector<F128> tp;
+				for (uint32_t c = 1; c < hi; c++) { tc.push_back(c); tp.push_back(c < 3 ? F128{} : nontrivial_evaluation_points[c - 3]); }
 				l_.check(b200_sumcheck_tail_start(l_.ctx(), p.data(), (uint32_t)p.size(), n_vars, eq_ind_partial_evals->ptr, cs.data(), ls.data(),
-												  (uint32_t)cs.size(), codes.data(), (const uint64_t *)pts.data(), (uint32_t)codes.size(), &tail_));
-				tail_vars_ = n_vars, tail_eq_ptr_ = eq_ind_partial_evals->ptr, tail_eq_pending_ = 0;
+												  (uint32_t)cs.size(), tc.data(), (const uint64_t *)tp.data(), n_tail_codes, lo - 1, &tail_));
+				tail_vars_ = n_vars, tail_hi_ = hi, tail_first_ = true, tail_eq_ptr_ = eq_ind_partial_evals->ptr, tail_eq_pending_ = 0;
 			}
 		}
 		if (tail_ok) {
-			if (tail_vars_ != n_vars) throw InputValidation(1, "the running sumcheck tail was started for a different round");
-			std::vector<F128> vals(evaluators.size() * codes.size());
+			if (tail_vars_ != n_vars || tail_hi_ != hi || (lo != 1 && !tail_first_)) throw InputValidation(1, "the running sumcheck tail was started for a different round");
+			tail_first_ = false;
+			std::vector<F128> vals(evaluators.size() * n_tail_codes);
 			l_.check(b200_sumcheck_tail_round_evals(tail_, (uint64_t *)vals.data()));
 			std::vector<std::vector<F128>> res;
 			for (size_t e = 0; e < evaluators.size(); e++) {
 				std::vector<F128> r;
-				for (uint32_t k = evaluators[e].first_point; k < evaluators[e].end_point; k++) r.push_back(vals[e * codes.size() + (k - lo)]);
+				for (uint32_t k = evaluators[e].first_point; k < evaluators[e].end_point; k++) r.push_back(vals[e * n_tail_codes + (k - 1)]);
 				res.push_back(r);
 			}
 			return res;

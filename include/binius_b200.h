@@ -304,11 +304,17 @@ int32_t b200_fold_multilinears_low_to_high(b200_ctx *ctx, const b200_dev_ptr *mu
  * round: b200_sumcheck_tail_round_evals (blocks until the values are there), then b200_sumcheck_tail_challenge;
  * after the last challenge b200_sumcheck_tail_finish.  A backend maps the trait calls of those rounds
  * (sumcheck_compute_round_evals / sumcheck_fold_multilinears, hal/src/backend.rs:48-75) onto this triple.  A watchdog
- * ends the kernel if no challenge arrives within 5 s (the calls then fail with B200_ERR_DEVICE). */
+ * ends the kernel if no challenge arrives within 5 s (the calls then fail with B200_ERR_DEVICE).
+ * Instances of more than 32 hypercube points (n_vars in [7, 28], at most 1024 values per round) run on a co-resident
+ * grid of up to 128 CTAs (cooperative launch, csrc/tail_grid.cuh), so a WHOLE cache-sized sumcheck (BASELINE config #3)
+ * is one kernel; smaller ones on a single CTA.  `first_round_skip` = number of leading entries of `point_codes` the
+ * first round of the tail does not need (a zerocheck prover's first round evaluates at infinity only, its later rounds
+ * at 1 and infinity: prove/eq_ind.rs:646-731); their values are posted as zero.  Grid kernel only. */
 typedef struct b200_tail b200_tail;
 int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *multilins, uint32_t n_multilins, uint32_t n_vars, b200_dev_ptr eq_ind,
 								 const b200_expr *const *compositions, const b200_expr *const *compositions_leading, uint32_t n_compositions,
-								 const uint32_t *point_codes, const uint64_t *domain_points, uint32_t n_points, b200_tail **out);
+								 const uint32_t *point_codes, const uint64_t *domain_points, uint32_t n_points, uint32_t first_round_skip,
+								 b200_tail **out);
 int32_t b200_sumcheck_tail_round_evals(b200_tail *tail, uint64_t *host_out /* 2 * n_compositions * n_points */);
 int32_t b200_sumcheck_tail_challenge(b200_tail *tail, const uint64_t challenge[2]);
 int32_t b200_sumcheck_tail_finish(b200_tail *tail);

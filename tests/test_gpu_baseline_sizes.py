@@ -28,10 +28,13 @@ def hal():
     layer.close()
 
 
-def test_cfg3_u32_add_zerocheck_n18_every_round(hal, oracle):
+@pytest.mark.parametrize("tail", [False, True])
+def test_cfg3_u32_add_zerocheck_n18_every_round(hal, oracle, tail):
+    """tail=True: the whole sumcheck (all 18 rounds, from the first one with its own point set) runs in ONE persistent
+    kernel on a co-resident grid (csrc/tail_grid.cuh); the multilinears are only readable after the last round."""
     from binius_b200.hal import B200Backend, EqIndEvaluator, FoldedMultilinear
 
-    be = B200Backend(hal)
+    be = B200Backend(hal, sumcheck_tail=tail)
     n_vars = 18
     rng = random.Random(1803)
     comps = u32_add_compositions()
@@ -52,7 +55,8 @@ def test_cfg3_u32_add_zerocheck_n18_every_round(hal, oracle):
         ch = rng.getrandbits(128)
         be.sumcheck_fold_multilinears(nv, mls, ch)
         mls_h = [oracle.fold_left_lerp_inplace(m, len(m), 0, nv, ch) for m in mls_h]
-        if rnd in (0, 1, 5, 12, n_vars - 1):  # full download of the folded multilinears on a few rounds
+        assert (be._tail is not None) == (tail and nv > 1), "the persistent kernel must cover every round from the first"
+        if not tail and rnd in (0, 1, 5, 12, n_vars - 1):  # full download of the folded multilinears on a few rounds
             for d, h in zip(mls, mls_h):
                 assert d.evals.len() == len(h) and _same(hal.to_host(d.evals), h), f"fold of round {rnd}"
         if nv > 1:

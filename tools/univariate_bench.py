@@ -1,6 +1,6 @@
 """Timing of the zerocheck univariate-skip round (b200_zerocheck_univariate_evals) at the keccak shape
-(153 B1 columns, 75 degree-2 chi constraints a*b + c + d, skip_rounds = 6,
-max_domain_size = 128) on synthetic columns.  `python tools/univariate_bench.py [n_vars] [m] [n_comp]`;
+(153 B1 columns, 75 degree-2 chi constraints a*b + c + d, skip_rounds = 7 (constraint_system/verify.rs:271-294),
+max_domain_size = 256) on synthetic columns.  `python tools/univariate_bench.py [n_vars] [m] [n_comp]`;
 n_vars = 27 is the 2^18-permutation trace (16 MiB per column).  Run on a B200."""
 import ctypes as C
 import os
@@ -16,7 +16,7 @@ from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univa
 n_vars = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 153
 n_comp = int(sys.argv[3]) if len(sys.argv) > 3 else 75
-skip = 6
+skip = 7
 hal = binius_b200.B200Layer(0)
 be = B200Backend(hal)
 words = 1 << (n_vars - 7)
