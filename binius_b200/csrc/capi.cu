@@ -42,7 +42,7 @@ struct b200_tail {
 	uint8_t *h_mb = nullptr;  // pinned, mapped
 	uint8_t *d_mb = nullptr;  // device alias
 	uint32_t n_vars = 0, n_vals = 0, round_out = 0, round_in = 0;
-	size_t off_seq = 0, off_chal = 0, off_chal_seq = 0, off_status = 0;
+	size_t off_chal = 0, off_status = 0, off_trace = 0;
 };
 
 struct b200_ntt {
@@ -448,8 +448,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_eq_ind_round_evals, FIELD_TABLE_BYTES);
 	SET(k_eq_ind_vals, FIELD_TABLE_BYTES);
 	SET(k_eq_scale, FIELD_TABLE_BYTES);
-	SET(k_sumcheck_tail, FIELD_TABLE_BYTES);
-	SET(k_sumcheck_tail_grid, ((FIELD_TABLE_BYTES + 127) & ~127u) + 16 * TG_MAX_VALS);
+	SET(k_sumcheck_tail_grid, TG_SMEM_MAX);
 	SET(k_fri_fold, FIELD_TABLE_BYTES);
 	SET(k_fri_lerp_k64<1>, 1 * LUT_BYTES + 6144 + NLUT_BYTES);
 	SET(k_fri_lerp_k64<2>, 2 * LUT_BYTES + 6144 + NLUT_BYTES);
@@ -559,6 +558,7 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	else if (!strcmp(key, "round_evals_tc")) ctx->tune_round_evals_tc = value;
 	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
 	else if (!strcmp(key, "tail_grid")) ctx->tune_tail_grid = value;
+	else if (!strcmp(key, "tail_trace")) ctx->tune_tail_trace = value;
 	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
 	return B200_OK;
 }
@@ -1669,7 +1669,7 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 	return B200_OK;
 }
 
-// ---- persistent tail of an eq-ind sumcheck ---------------------------------------------------------------
+// ---- persistent eq-ind sumcheck (tail_grid.cuh) ----------------------------------------------------------
 int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_t m, uint32_t n_vars, b200_dev_ptr eq_ind, const b200_expr *const *comps,
 								 const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, const uint64_t *points, uint32_t n_points,
 								 uint32_t first_round_skip, b200_tail **out) {
@@ -1679,18 +1679,18 @@ int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_
 	if (n_vars == 0 || n_vars > 28) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: n_vars must be in [1, 28]");
 	if (first_round_skip >= n_points) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: the first round must keep at least one evaluation point");
 	const uint32_t n_vals = n_comp * n_points;
-	if (n_vals == 0 || n_vals > 4096) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: 1..4096 (composition, point) pairs");
+	if (n_vals == 0 || n_vals > TG_MAX_VALS) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: 1..4096 (composition, point) pairs");
 	for (uint32_t c = 0; c < n_comp; c++)
 		if (!comps[c] || !leads[c] || comps[c]->n_vars > m || leads[c]->n_vars > m) return fail(ctx, B200_ERR_INPUT_VALIDATION, "composition %u does not match the multilinears", c);
 	for (uint32_t p = 0; p < n_points; p++)
 		if (codes[p] == 0) return fail(ctx, B200_ERR_INPUT_VALIDATION, "evaluation point code 0 is never computed by the prover");
+	if (ctx->tail_active) return fail(ctx, B200_ERR_INPUT_VALIDATION, "a sumcheck tail is already running on this context");
 	std::unique_ptr<b200_tail> t(new b200_tail);
 	t->ctx = ctx, t->n_vars = n_vars, t->n_vals = n_vals;
-	t->off_seq = (size_t)n_vars * n_vals * 16;
-	t->off_chal = (t->off_seq + 4 * n_vars + 15) & ~(size_t)15;
-	t->off_chal_seq = t->off_chal + 16 * (size_t)n_vars;
-	t->off_status = t->off_chal_seq + 4 * (size_t)n_vars;
-	const size_t bytes = t->off_status + 16;
+	t->off_chal = (size_t)n_vars * n_vals * 32;
+	t->off_status = t->off_chal + 32 * (size_t)n_vars;
+	t->off_trace = t->off_status + 32;
+	const size_t bytes = t->off_trace + 32 * (size_t)n_vars;
 	// one host-mapped mailbox per context, allocated on first use (pinned allocations cost ~100 us: not per sumcheck)
 	if (ctx->tail_mb_bytes < bytes) {
 		if (ctx->h_tail_mb) {
@@ -1711,53 +1711,64 @@ int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_
 		}
 		ctx->tail_mb_bytes = want;
 	}
-	if (ctx->tail_active) return fail(ctx, B200_ERR_INPUT_VALIDATION, "a sumcheck tail is already running on this context");
 	t->h_mb = ctx->h_tail_mb, t->d_mb = ctx->d_tail_mb;
-	memset(t->h_mb + t->off_seq, 0, bytes - t->off_seq);
+	memset(t->h_mb, 0, bytes);  // every slot is validated by its complement: zero = not there yet
 	std::vector<DevExpr> hc(n_comp), hl(n_comp);
+	std::vector<uint32_t> step_off(2 * n_comp + 1, 0);
 	for (uint32_t c = 0; c < n_comp; c++) {
 		hc[c] = dev_expr(comps[c]);
 		hl[c] = dev_expr(leads[c]);
 		if ((hc[c].n_steps && !hc[c].steps) || (hl[c].n_steps && !hl[c].steps)) return fail(ctx, B200_ERR_ALLOC, "out of device memory (expression steps)");
 	}
+	for (uint32_t e = 0; e < 2 * n_comp; e++) step_off[e + 1] = step_off[e] + (e < n_comp ? hc[e] : hl[e - n_comp]).n_steps;
+	const bool cache_steps = 32 * (size_t)step_off[2 * n_comp] + sizeof(DevExpr) * 2 * n_comp <= TG_STEP_CACHE_BYTES;
 	std::vector<uint4> hp(n_points);
 	for (uint32_t p = 0; p < n_points; p++) hp[p] = to_u4(points + 2 * p);
 	ArgPack pack;
 	size_t o_m = pack.add(mls, sizeof(void *) * m), o_c = pack.add(hc.data(), sizeof(DevExpr) * n_comp), o_l = pack.add(hl.data(), sizeof(DevExpr) * n_comp);
-	size_t o_k = pack.add(codes, 4 * n_points), o_p = pack.add(hp.data(), 16 * n_points);
+	size_t o_k = pack.add(codes, 4 * n_points), o_p = pack.add(hp.data(), 16 * n_points), o_s = pack.add(step_off.data(), 4 * step_off.size());
 	uint8_t *dbase;
 	int32_t rc = pack.commit(ctx, &dbase);
 	if (rc) return rc;
-	TailArgs A;
+	TailGridArgs GA;
+	TailArgs &A = GA.t;
 	A.mls = (uint4 *const *)(dbase + o_m), A.m = m, A.n_vars = n_vars, A.eq_ind = (uint4 *)eq_ind;
 	A.comps = (const DevExpr *)(dbase + o_c), A.leads = (const DevExpr *)(dbase + o_l), A.n_comp = n_comp, A.n_points = n_points;
 	A.codes = (const uint32_t *)(dbase + o_k), A.points = (const uint4 *)(dbase + o_p);
-	A.mb_vals = (volatile uint4 *)t->d_mb, A.mb_seq = (volatile uint32_t *)(t->d_mb + t->off_seq);
-	A.mb_chal = (volatile uint4 *)(t->d_mb + t->off_chal), A.mb_chal_seq = (volatile uint32_t *)(t->d_mb + t->off_chal_seq);
+	A.mb_vals = (uint4 *)t->d_mb, A.mb_chal = (uint4 *)(t->d_mb + t->off_chal);
 	A.status = (volatile uint32_t *)(t->d_mb + t->off_status);
+	A.mb_trace = ctx->tune_tail_trace ? (uint64_t *)(t->d_mb + t->off_trace) : nullptr;
 	A.timeout_ns = 5ull * 1000 * 1000 * 1000;
-	// more than one warp-chunk of hypercube indices: the co-resident grid (tail_grid.cuh); else one CTA
+	// hypercube chunks of 32 indices over a co-resident grid (one CTA when there is a single chunk, or on request)
 	const uint64_t n_chunks = ((1ull << (n_vars - 1)) + 31) >> 5;
-	if (n_chunks > 1 && n_vals <= TG_MAX_VALS && ctx->tune_tail_grid) {
-		constexpr size_t WS_ACC = 28 * (size_t)TG_MAX_VALS * 16, WS_BYTES = WS_ACC + 28 * 16 + 28 * 4 + 16;
-		if (!ctx->d_tail_ws) B200_CUDA(ctx, cudaMalloc((void **)&ctx->d_tail_ws, WS_BYTES));
-		B200_CUDA(ctx, cudaMemsetAsync(ctx->d_tail_ws, 0, (size_t)n_vars * n_vals * 16, ctx->stream));
-		B200_CUDA(ctx, cudaMemsetAsync(ctx->d_tail_ws + WS_ACC, 0, WS_BYTES - WS_ACC, ctx->stream));
-		TailGridArgs GA;
-		GA.t = A;
-		GA.acc = (uint4 *)ctx->d_tail_ws, GA.g_chal = (uint4 *)(ctx->d_tail_ws + WS_ACC);
-		GA.g_chal_seq = (uint32_t *)(ctx->d_tail_ws + WS_ACC + 28 * 16), GA.bar = GA.g_chal_seq + 28, GA.g_abort = GA.bar + 1;
-		GA.first_skip = first_round_skip;
-		uint32_t G = 1;
+	uint32_t G = 1;
+	if (ctx->tune_tail_grid)
 		while (G * 2 <= std::min<uint64_t>({(uint64_t)TG_MAX_CTAS, n_chunks, (uint64_t)ctx->n_sms})) G *= 2;
-		const uint8_t *tables = ctx->d_tables;
-		void *kargs[] = {(void *)&tables, (void *)&GA};
-		B200_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_sumcheck_tail_grid, dim3(G), dim3(TG_THREADS), kargs,
-												   ((FIELD_TABLE_BYTES + 127) & ~127u) + 16 * (size_t)n_vals, ctx->stream));
-	} else {
-		if (first_round_skip) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: first_round_skip needs the grid kernel (more than 32 hypercube points, at most 1024 values)");
-		k_sumcheck_tail<<<1, 1024, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A);
+	constexpr size_t WS_ACC = 28 * (size_t)TG_MAX_VALS * 16, WS_BYTES = WS_ACC + 28 * 16 + 28 * 4 + 16;
+	if (!ctx->d_tail_ws) B200_CUDA(ctx, cudaMalloc((void **)&ctx->d_tail_ws, WS_BYTES));
+	if (G > 1) B200_CUDA(ctx, cudaMemsetAsync(ctx->d_tail_ws, 0, (size_t)n_vars * n_vals * 16, ctx->stream));
+	B200_CUDA(ctx, cudaMemsetAsync(ctx->d_tail_ws + WS_ACC, 0, WS_BYTES - WS_ACC, ctx->stream));
+	GA.acc = (uint4 *)ctx->d_tail_ws, GA.g_chal = (uint4 *)(ctx->d_tail_ws + WS_ACC);
+	GA.g_chal_seq = (uint32_t *)(ctx->d_tail_ws + WS_ACC + 28 * 16), GA.bar = GA.g_chal_seq + 28, GA.g_abort = GA.bar + 1;
+	GA.first_skip = first_round_skip;
+	GA.step_off = cache_steps ? (const uint32_t *)(dbase + o_s) : nullptr;
+	GA.off_acc = (FIELD_TABLE_BYTES + 127) & ~127u;
+	GA.off_ex = GA.off_acc + 16 * n_vals;
+	GA.off_steps = GA.off_ex + (cache_steps ? (uint32_t)sizeof(DevExpr) * 2 * n_comp : 0);
+	size_t smem_bytes = GA.off_steps + (cache_steps ? 32 * (size_t)step_off[2 * n_comp] : 0);
+	GA.off_hdr = GA.off_k64 = 0;
+	if (m <= 2048 && n_points <= 64) {
+		GA.off_hdr = (uint32_t)smem_bytes;
+		smem_bytes += 16 * (size_t)n_points + 8 * (size_t)m + 4 * (size_t)n_points;
+		smem_bytes = (smem_bytes + 127) & ~(size_t)127;
 	}
+	if (smem_bytes + LUT_BYTES + 1536 <= TG_SMEM_MAX) {
+		GA.off_k64 = (uint32_t)smem_bytes;
+		smem_bytes += LUT_BYTES + 1536;
+	}
+	const uint8_t *tables = ctx->d_tables;
+	void *kargs[] = {(void *)&tables, (void *)&GA};
+	B200_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_sumcheck_tail_grid, dim3(G), dim3(TG_THREADS), kargs, smem_bytes, ctx->stream));
 	B200_LAUNCH_CHECK(ctx);
 	ctx->tail_active = true;
 	*out = t.release();
@@ -1769,17 +1780,23 @@ int32_t b200_sumcheck_tail_round_evals(b200_tail *t, uint64_t *out) {
 	b200_ctx *ctx = t->ctx;
 	if (t->round_out >= t->n_vars || t->round_out != t->round_in) return fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: round values requested out of order");
 	const uint32_t r = t->round_out;
-	volatile uint32_t *seq = (volatile uint32_t *)(t->h_mb + t->off_seq), *status = (volatile uint32_t *)(t->h_mb + t->off_status);
+	const volatile uint64_t *slot = (const volatile uint64_t *)(t->h_mb + (size_t)r * t->n_vals * 32);
+	volatile uint32_t *status = (volatile uint32_t *)(t->h_mb + t->off_status);
 	const auto t0 = std::chrono::steady_clock::now();
-	for (uint64_t spins = 0; seq[r] != r + 1; spins++) {
-		if (*status) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel's watchdog expired");
-		if ((spins & 0xFFFF) == 0xFFFF) {
-			if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady && seq[r] != r + 1) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel ended before posting round %u", r);
-			if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: timed out waiting for round %u", r);
+	for (uint32_t v = 0; v < t->n_vals; v++) {
+		uint64_t lo, hi;
+		for (uint64_t spins = 0;; spins++) {
+			lo = slot[4 * v], hi = slot[4 * v + 1];
+			if (lo == ~slot[4 * v + 2] && hi == ~slot[4 * v + 3]) break;
+			if (*status) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel's watchdog expired");
+			if ((spins & 0xFFFF) == 0xFFFF) {
+				if (cudaStreamQuery(ctx->stream) != cudaErrorNotReady && !(slot[4 * v] == ~slot[4 * v + 2] && slot[4 * v + 1] == ~slot[4 * v + 3]))
+					return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel ended before posting round %u", r);
+				if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return fail(ctx, B200_ERR_DEVICE, "sumcheck tail: timed out waiting for round %u", r);
+			}
 		}
+		out[2 * v] = lo, out[2 * v + 1] = hi;
 	}
-	std::atomic_thread_fence(std::memory_order_acquire);
-	memcpy(out, t->h_mb + (size_t)r * t->n_vals * 16, (size_t)t->n_vals * 16);
 	t->round_out++;
 	return B200_OK;
 }
@@ -1787,10 +1804,10 @@ int32_t b200_sumcheck_tail_round_evals(b200_tail *t, uint64_t *out) {
 int32_t b200_sumcheck_tail_challenge(b200_tail *t, const uint64_t z[2]) {
 	if (!t || !z) return B200_ERR_INPUT_VALIDATION;
 	if (t->round_in + 1 != t->round_out) return fail(t->ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail: challenge posted out of order");
-	const uint32_t r = t->round_in;
-	memcpy(t->h_mb + t->off_chal + 16 * (size_t)r, z, 16);
+	volatile uint64_t *slot = (volatile uint64_t *)(t->h_mb + t->off_chal + 32 * (size_t)t->round_in);
+	slot[2] = ~z[0], slot[3] = ~z[1];
+	slot[0] = z[0], slot[1] = z[1];
 	std::atomic_thread_fence(std::memory_order_release);
-	((volatile uint32_t *)(t->h_mb + t->off_chal_seq))[r] = r + 1;
 	t->round_in++;
 	return B200_OK;
 }
@@ -1801,12 +1818,19 @@ int32_t b200_sumcheck_tail_finish(b200_tail *t) {
 	B200_LOCK(ctx);
 	int32_t rc = B200_OK;
 	if (t->round_in != t->n_vars) {
-		// abandoned: let the watchdog end the kernel quickly instead of waiting 5 s
+		// abandoned: the watchdog ends the kernel
 		rc = fail(ctx, B200_ERR_INPUT_VALIDATION, "sumcheck tail finished after %u of %u challenges", t->round_in, t->n_vars);
 	}
 	cudaError_t e = cudaStreamSynchronize(ctx->stream);
 	if (e != cudaSuccess && rc == B200_OK) rc = fail(ctx, B200_ERR_DEVICE, "sumcheck tail: %s", cudaGetErrorString(e));
 	if (rc == B200_OK && *(volatile uint32_t *)(t->h_mb + t->off_status)) rc = fail(ctx, B200_ERR_DEVICE, "sumcheck tail: the kernel's watchdog expired");
+	if (ctx->tune_tail_trace) {
+		// debugging aid (b200_ctx_set_tuning "tail_trace"): CTA 0's %globaltimer stamps per round
+		const uint64_t *tr = (const uint64_t *)(t->h_mb + t->off_trace);
+		for (uint32_t r = 0; r < t->n_vars; r++)
+			fprintf(stderr, "tail round %2u: values %6.2f us, mailbox %6.2f us, fold %6.2f us%s\n", r, (tr[4 * r + 1] - tr[4 * r]) * 1e-3, (tr[4 * r + 2] - tr[4 * r + 1]) * 1e-3,
+					r + 1 < t->n_vars ? (tr[4 * r + 3] - tr[4 * r + 2]) * 1e-3 : 0.0, r + 1 < t->n_vars ? "" : " (last)");
+	}
 	ctx->tail_active = false;
 	for (void *p : ctx->deferred_free) cudaFree(p);
 	ctx->deferred_free.clear();

@@ -41,6 +41,11 @@ __device__ __forceinline__ bool is_zero(uint4 a) { return (a.x | a.y | a.z | a.w
 __device__ __forceinline__ uint4 u4_zero() { return make_uint4(0, 0, 0, 0); }
 __device__ __forceinline__ uint4 u4_one() { return make_uint4(1, 0, 0, 0); }
 
+// Bank behaviour of the 64 KiB table: the FIRST operand picks the 256-byte row (64 words = every bank twice), the second
+// the byte inside it.  When one operand is the same in every lane of the warp (a challenge, an evaluation point, a
+// sub-field scalar) it must be the FIRST one: all lanes then read one row (at most 2-way conflicts); as the second
+// operand it would put all 32 lanes on ONE bank (32-way conflict, measured 5x on a fold).  Two per-lane operands see
+// ~3.5-way conflicts either way.
 __device__ __forceinline__ uint32_t f_mul8(const FieldTables &T, uint32_t a, uint32_t b) { return T.mul8[(a << 8) | b]; }
 
 __device__ __forceinline__ uint32_t f_alpha16(const FieldTables &T, uint32_t a) {
@@ -82,12 +87,12 @@ __device__ __noinline__ uint4 f_mul128(const FieldTables &T, uint4 a, uint4 b) {
 // B128 x subfield element of tower level `lvl` (lvl in {0,3,4,5,6,7}), limb-wise
 // (reference crates/field/src/binary_field.rs:363-414)
 __device__ __forceinline__ uint32_t f_mul8x4(const FieldTables &T, uint32_t a, uint32_t s) {
-	return f_mul8(T, a & 0xff, s) | (f_mul8(T, (a >> 8) & 0xff, s) << 8) | (f_mul8(T, (a >> 16) & 0xff, s) << 16) |
-		   (f_mul8(T, a >> 24, s) << 24);
+	return f_mul8(T, s, a & 0xff) | (f_mul8(T, s, (a >> 8) & 0xff) << 8) | (f_mul8(T, s, (a >> 16) & 0xff) << 16) | (f_mul8(T, s, a >> 24) << 24);
 }
 __device__ __forceinline__ uint32_t f_mul16x2(const FieldTables &T, uint32_t a, uint32_t s) {
-	return f_mul16(T, a & 0xffff, s) | (f_mul16(T, a >> 16, s) << 16);
+	return f_mul16(T, s, a & 0xffff) | (f_mul16(T, s, a >> 16) << 16);
 }
+// (the scalar s, often warp-uniform, goes first: see f_mul8)
 __device__ __forceinline__ uint4 f_mul128_sub(const FieldTables &T, uint4 a, uint4 s, uint32_t lvl) {
 	switch (lvl) {
 	case 0: {
@@ -102,13 +107,13 @@ __device__ __forceinline__ uint4 f_mul128_sub(const FieldTables &T, uint4 a, uin
 		uint32_t c = s.x & 0xffff;
 		return make_uint4(f_mul16x2(T, a.x, c), f_mul16x2(T, a.y, c), f_mul16x2(T, a.z, c), f_mul16x2(T, a.w, c));
 	}
-	case 5: return make_uint4(f_mul32(T, a.x, s.x), f_mul32(T, a.y, s.x), f_mul32(T, a.z, s.x), f_mul32(T, a.w, s.x));
+	case 5: return make_uint4(f_mul32(T, s.x, a.x), f_mul32(T, s.x, a.y), f_mul32(T, s.x, a.z), f_mul32(T, s.x, a.w));
 	case 6: {
 		uint2 c = make_uint2(s.x, s.y);
-		uint2 l = f_mul64(T, make_uint2(a.x, a.y), c), h = f_mul64(T, make_uint2(a.z, a.w), c);
+		uint2 l = f_mul64(T, c, make_uint2(a.x, a.y)), h = f_mul64(T, c, make_uint2(a.z, a.w));
 		return make_uint4(l.x, l.y, h.x, h.y);
 	}
-	default: return f_mul128(T, a, s);
+	default: return f_mul128(T, s, a);
 	}
 }
 

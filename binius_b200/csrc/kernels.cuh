@@ -466,33 +466,7 @@ __device__ __forceinline__ uint4 eq_ind_eval_point(const FieldTables &T, const E
 			else {
 				uint4 lo = i_lo < len ? (NC ? __ldg(m + i_lo) : m[i_lo]) : A.suffix[st.l];
 				uint4 d = hi ^ lo;
-				v = code == 2 ? d : (lo ^ f_mul128(T, d, z));
-			}
-		}
-		}
-		tmp[s] = v;
-	}
-	return E.n_steps ? tmp[E.n_steps - 1] : u4_zero();
-}
-
-// the same for full-length multilinears read through the coherent path (persistent tail kernel)
-__device__ __forceinline__ uint4 eq_ind_eval_point_full(const FieldTables &T, const EqIndArgs &A, const DevExpr &E, uint32_t code, uint4 z, uint64_t i) {
-	uint4 tmp[MAX_EXPR_STEPS];
-	for (uint32_t s = 0; s < E.n_steps; s++) {
-		const b200_expr_step st = E.steps[s];
-		uint4 v;
-		switch (st.op) {
-		case 0: v = tmp[st.l] ^ tmp[st.r]; break;
-		case 1: v = f_mul128(T, tmp[st.l], tmp[st.r]); break;
-		case 2: v = f_pow128(T, tmp[st.l], st.r); break;
-		case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
-		default: {
-			const uint4 *m = A.mls[st.l];
-			const uint4 hi = m[A.half + i];
-			if (code == 1) v = hi;
-			else {
-				const uint4 d = hi ^ m[i];
-				v = code == 2 ? d : (m[i] ^ f_mul128(T, d, z));
+				v = code == 2 ? d : (lo ^ f_mul128(T, z, d));  // warp-uniform operand FIRST (field.cuh)
 			}
 		}
 		}
@@ -517,109 +491,6 @@ __global__ void __launch_bounds__(256) k_eq_ind_round_evals(const uint8_t *__res
 	}
 	acc = block_xor(acc, red);
 	if (threadIdx.x == 0) atomic_xor_u4(A.slots + blockIdx.y, acc);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent TAIL of an eq-ind (zerocheck) sumcheck: all remaining rounds of a small instance in ONE kernel.
-// Late sumcheck rounds are a few kilobytes of data and are bounded by launch + copy + synchronisation latency
-// (~40 us per round through separate calls); here a single CTA loops over the rounds
-//     round values (warp w handles the (composition, point) pairs w, w + 32, ...; shuffle reduction)
-//     -> written to a HOST-MAPPED mailbox, sequence number last (the host polls it, hashes, samples the challenge)
-//     -> the CTA polls the challenge mailbox (host-mapped), folds every multilinear in place and halves the eq-indicator
-// so a round costs one PCIe round trip plus the arithmetic.  Semantics per round = k_eq_ind_round_evals (HighToLow,
-// full-length multilinears) + fold_left_lerp_inplace (math/src/fold.rs:648-696) + fold_partial_eq_ind (prove/common.rs:
-// 60-68).  A watchdog on %globaltimer ends the kernel (status = 1) if no challenge arrives within `timeout_ns`.
-struct TailArgs {
-	uint4 *const *mls;   // device [m]
-	uint32_t m, n_vars;  // n_vars rounds remain
-	uint4 *eq_ind;       // 2^(n_vars - 1), halved in place
-	const DevExpr *comps, *leads;
-	uint32_t n_comp, n_points;
-	const uint32_t *codes;
-	const uint4 *points;
-	volatile uint4 *mb_vals;      // host-mapped [n_vars][n_comp * n_points]
-	volatile uint32_t *mb_seq;    // host-mapped [n_vars]: round r's values are complete when mb_seq[r] == r + 1
-	volatile uint4 *mb_chal;      // host-mapped [n_vars]: {z.x, z.y, z.z, z.w}
-	volatile uint32_t *mb_chal_seq;  // host-mapped [n_vars]: challenge r is valid when == r + 1
-	volatile uint32_t *status;    // host-mapped: 0 running / done, 1 watchdog expired
-	uint64_t timeout_ns;
-};
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-	uint64_t t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
-}
-__global__ void __launch_bounds__(1024, 1) k_sumcheck_tail(const uint8_t *__restrict__ g_tables, const TailArgs A) {
-	extern __shared__ __align__(128) uint8_t smem[];
-	FieldTables T = load_field_tables(smem, g_tables);
-	__shared__ uint4 z_s;
-	__shared__ uint32_t abort_s;
-	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
-	const uint32_t n_vals = A.n_comp * A.n_points;
-	EqIndArgs E;  // view of the current round for eq_ind_eval_point
-	E.mls = A.mls, E.lens = nullptr, E.suffix = nullptr, E.n_mls = A.m, E.eq_ind = A.eq_ind, E.comps = A.comps, E.comps_lead = A.leads;
-	E.codes = A.codes, E.points = A.points, E.n_points = A.n_points, E.slots = nullptr, E.low_to_high = 0;
-	if (tid == 0) abort_s = 0;
-	__syncthreads();
-	for (uint32_t r = 0; r < A.n_vars; r++) {
-		const uint64_t half = 1ull << (A.n_vars - 1 - r);
-		E.half = half;
-		{
-			for (uint32_t j = warp; j < n_vals; j += n_warps) {
-				const uint32_t c = j / A.n_points, p = j % A.n_points, code = A.codes[p];
-				const DevExpr X = code == 2 ? A.leads[c] : A.comps[c];
-				const uint4 zp = A.points[p];
-				uint4 acc = u4_zero();
-				for (uint64_t i = lane; i < half; i += 32) {
-					const uint4 v = eq_ind_eval_point_full(T, E, X, code, zp, i);
-					acc ^= f_mul128(T, v, A.eq_ind[i]);
-				}
-#pragma unroll
-				for (uint32_t s = 16; s >= 1; s >>= 1) {
-					acc.x ^= __shfl_xor_sync(0xffffffffu, acc.x, s);
-					acc.y ^= __shfl_xor_sync(0xffffffffu, acc.y, s);
-					acc.z ^= __shfl_xor_sync(0xffffffffu, acc.z, s);
-					acc.w ^= __shfl_xor_sync(0xffffffffu, acc.w, s);
-				}
-				if (lane == 0) {
-					volatile uint4 *dst = A.mb_vals + (uint64_t)r * n_vals + j;
-					dst->x = acc.x, dst->y = acc.y, dst->z = acc.z, dst->w = acc.w;
-					__threadfence_system();
-				}
-			}
-		}
-		__syncthreads();
-		if (tid == 0) {
-			A.mb_seq[r] = r + 1;
-			__threadfence_system();
-			const uint64_t t0 = globaltimer_ns();
-			while (A.mb_chal_seq[r] != r + 1) {
-				if (globaltimer_ns() - t0 > A.timeout_ns) {
-					abort_s = 1;
-					break;
-				}
-			}
-			volatile uint4 *zc = A.mb_chal + r;
-			z_s = make_uint4(zc->x, zc->y, zc->z, zc->w);
-		}
-		__syncthreads();
-		if (abort_s) {
-			if (tid == 0) {
-				*A.status = 1;
-				__threadfence_system();
-			}
-			return;
-		}
-		const uint4 z = z_s;
-		for (uint64_t e = tid; e < (uint64_t)A.m * half; e += blockDim.x) {
-			uint4 *ml = A.mls[e / half];
-			const uint64_t i = e % half;
-			const uint4 lo = ml[i], hi = ml[half + i];
-			ml[i] = lo ^ f_mul128(T, lo ^ hi, z);
-		}
-		for (uint64_t i = tid; i < half / 2; i += blockDim.x) A.eq_ind[i] = A.eq_ind[i] ^ A.eq_ind[half / 2 + i];
-		__syncthreads();
-	}
 }
 
 // Large rounds: the composition values are materialised (vals[(c*n_points + p) * half + i]) and the
@@ -690,7 +561,7 @@ __global__ void __launch_bounds__(128) k_fri_fold(const uint8_t *__restrict__ g_
 		for (uint32_t r = 0; r < A.log_batch; r++) {
 			cur >>= 1;
 			uint4 z = A.challenges[r];
-			for (uint32_t o = 0; o < cur; o++) v[o] = v[2 * o] ^ f_mul128(T, v[2 * o] ^ v[2 * o + 1], z);
+			for (uint32_t o = 0; o < cur; o++) v[o] = v[2 * o] ^ f_mul128(T, z, v[2 * o] ^ v[2 * o + 1]);
 		}
 		uint32_t L = A.log_len, sz = eta;
 		for (uint32_t r = 0; r < eta; r++) {
@@ -701,7 +572,7 @@ __global__ void __launch_bounds__(128) k_fri_fold(const uint8_t *__restrict__ g_
 				uint4 u = v[2 * o], w = v[2 * o + 1];
 				w ^= u;
 				u ^= f_mul128_sub(T, w, make_uint4(t, 0, 0, 0), A.kt);
-				v[o] = u ^ f_mul128(T, u ^ w, z);
+				v[o] = u ^ f_mul128(T, z, u ^ w);
 			}
 			L--;
 			sz--;

@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(256) k_ntt_pass(const uint8_t *__restrict__ g_
 			uint32_t t = tw[(1u << (R - 1 - li)) + jr];
 			uint32_t u = tile[(r0 << log_c) + c], v = tile[(r1 << log_c) + c];
 			if (!A.inverse) {
-				u ^= NttField<S>::mul(T, v, t);
+				u ^= NttField<S>::mul(T, t, v);  // the twiddle is shared by many lanes: first operand (field.cuh)
 				v ^= u;
 			} else {
 				v ^= u;
-				u ^= NttField<S>::mul(T, v, t);
+				u ^= NttField<S>::mul(T, t, v);  // the twiddle is shared by many lanes: first operand (field.cuh)
 			}
 			tile[(r0 << log_c) + c] = (S)u;
 			tile[(r1 << log_c) + c] = (S)v;

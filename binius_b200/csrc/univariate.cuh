@@ -50,7 +50,7 @@ template <> struct Fb<3> {
 	static __device__ __forceinline__ V from128(uint4 a) { return a.x & 0xffu; }
 	static __device__ __forceinline__ uint4 to128(V a) { return make_uint4(a, 0, 0, 0); }
 	static __device__ __forceinline__ V mul(const FieldTables &T, V a, V b) { return f_mul8(T, a, b); }
-	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8(T, a, c); }
+	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8(T, c, a); }  // uniform operand first (field.cuh)
 };
 template <> struct Fb<4> {
 	typedef uint32_t V;
@@ -58,7 +58,7 @@ template <> struct Fb<4> {
 	static __device__ __forceinline__ V from128(uint4 a) { return a.x & 0xffffu; }
 	static __device__ __forceinline__ uint4 to128(V a) { return make_uint4(a, 0, 0, 0); }
 	static __device__ __forceinline__ V mul(const FieldTables &T, V a, V b) { return f_mul16(T, a, b); }
-	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8(T, a & 0xff, c) | (f_mul8(T, a >> 8, c) << 8); }
+	static __device__ __forceinline__ V mulc(const FieldTables &T, V a, uint32_t c) { return f_mul8(T, c, a & 0xff) | (f_mul8(T, c, a >> 8) << 8); }
 };
 template <> struct Fb<5> {
 	typedef uint32_t V;

@@ -54,9 +54,14 @@ struct Timer {
 static int run_cfg3(bool tail) {
 	B200Layer hal(0);
 	B200Backend be(hal, tail);
+	if (getenv("REPLAY_TAIL_TRACE")) hal.check(b200_ctx_set_tuning(hal.ctx(), "tail_trace", 1));
+	if (getenv("REPLAY_TAIL_ONE_CTA")) hal.check(b200_ctx_set_tuning(hal.ctx(), "tail_grid", 0));
 	const uint32_t nv = 18, m = 5;
 	DevSlice arena = hal.dev_alloc((uint64_t)m << nv);
-	hal.fill(arena, F128{0xFEDCBA9876543211ull, 0x0123456789ABCDEFull});
+	// random field elements, uploaded afresh before every repetition (the folds are in place): the general per-lane
+	// product gathers from a 64 KiB table and its bank conflicts depend on the data -- a constant fill would flatter it
+	std::vector<F128> h_arena((size_t)m << nv);
+	for (auto &x : h_arena) x = rnd();
 	// vars: 0 x, 1 y, 2 cin, 3 cout, 4 z
 	ExprEval c1 = hal.compile_expr({ExprStep::var(0), ExprStep::var(2), ExprStep::add(0, 1), ExprStep::var(1), ExprStep::add(3, 1), ExprStep::mul(2, 4),
 									ExprStep::add(5, 1), ExprStep::var(3), ExprStep::add(6, 7)});
@@ -72,6 +77,8 @@ static int run_cfg3(bool tail) {
 		for (uint32_t i = 0; i < m; i++) mls.push_back(SumcheckMultilinear::folded(arena.slice((uint64_t)i << nv, (uint64_t)(i + 1) << nv)));
 		std::vector<F128> q(nv - 1);
 		for (auto &x : q) x = rnd();
+		hal.copy_h2d(h_arena.data(), h_arena.size(), arena);
+		hal.check(b200_sync(hal.ctx()));
 		t.start();
 		hal.check(b200_tensor_product_full_query(hal.ctx(), &q[0].lo, nv - 1, eq_buf.ptr, eq_buf.n));
 		DevSlice eq = eq_buf;
