@@ -377,6 +377,32 @@ def cpu_chi_zerocheck_parallel(n_out: int, n_b: int, n_vars: int, budget_s: floa
                       f"{n_threads} threads; C restatement of the eq-ind evaluator loop (GFNI multiply), not the Rust binary"}
 
 
+def cpu_u32add_round_evals(cols, n_vars: int, eq, with_eval_1: bool, n_threads: int = 1, use_gfni: bool = True):
+    """[C1 at 1, C1 at infinity, C2 at 1] of the u32_add gadget compositions (BASELINE config #3) by the threaded GFNI
+    CPU arm; cols = x, y, cin, cout, z as 2^n_vars B128 elements each"""
+    cs = [_c(x) for x in cols]
+    ptrs = (C.c_void_p * len(cs))(*[x.ctypes.data for x in cs])
+    out = np.zeros((3, 2), np.uint64)
+    lib().cpu_u32add_round_evals(ptrs, C.c_uint32(n_vars), _p(_c(eq)), C.c_int(int(with_eval_1)), C.c_int(n_threads), C.c_int(int(use_gfni)), _p(out))
+    return to_ints(out)
+
+
+def cpu_u32add_zerocheck_parallel(n_vars: int, budget_s: float = 5.0, n_threads: int = 0):
+    """Times all rounds of the u32_add zerocheck (round values + folds + eq halving) on this host."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    fn = lib().cpu_u32add_zerocheck_bench
+    fn.restype = C.c_double
+    chk = np.zeros((1, 2), np.uint64)
+    t1 = fn(C.c_uint32(n_vars), C.c_int(1), C.c_int(n_threads), C.c_int(1), _p(chk))
+    reps = max(1, min(200, int(budget_s / max(t1, 1e-4))))
+    t = fn(C.c_uint32(n_vars), C.c_int(reps), C.c_int(n_threads), C.c_int(1), _p(chk)) if reps > 1 else t1
+    return {"value": reps * n_vars / t, "unit": "rounds/s", "ms_per_sumcheck": t / reps * 1e3, "cores": n_threads, "kind": "port",
+            "sample": f"{reps} x all {n_vars} zerocheck rounds over the 5 u32_add multilinears of 2^{n_vars} B128 elements, {n_threads} threads; "
+                      "C restatement of the eq-ind evaluator loop (GFNI multiply), not the Rust binary"}
+
+
 # ------------------------------------------------------------------------------------------------
 # old HAL (ComputationBackend) restatements, oracle/hal.c
 def fold_left_lerp_inplace(evals, prefix: int, suffix: int, log_n: int, z: int):

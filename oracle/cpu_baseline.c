@@ -646,3 +646,139 @@ double cpu_chi_zerocheck_bench(uint32_t n_out, uint32_t n_b, uint32_t n_vars, in
 	free(vals);
 	return total;
 }
+
+/* =================================================================================================
+ * CPU arm of BASELINE config #3: zerocheck rounds of the u32_add gadget (m3/src/gadgets/add.rs; columns
+ * x, y, cin, cout, z as 5 multilinears of n_vars variables; compositions C1 = (x + cin)(y + cin) + cin - cout and
+ * C2 = x + y + cin - z).  Per round (eq-ind evaluator, hal/src/sumcheck_round_calculation.rs:222-297 with
+ * core/src/protocols/sumcheck/prove/eq_ind.rs:646-731):
+ *     at 1:        sum_i E[i] * C1(hi[i]),  sum_i E[i] * C2(hi[i])            (not in the first round)
+ *     at infinity: sum_i E[i] * ((x' + cin')(y' + cin'))[i],  v' = hi - lo     (C2 is linear: no leading term)
+ * then the fold of the 5 multilinears and the halving of the eq-indicator.  Same GFNI structure as the chi arm.
+ * out = {C1 at 1, C1 at infinity, C2 at 1}
+ * ================================================================================================= */
+typedef struct {
+	u128u *const *cols;
+	const u128u *eq;
+	uint64_t begin, end, half;
+	int with_eval_1;
+	u128 *out; /* [3] */
+} add_job;
+
+TGT static void *add_worker_gfni(void *p) {
+	add_job *J = (add_job *)p;
+	const __m512i t2a = _mm512_set1_epi64((long long)affine_matrix(TOWER_TO_AES));
+	const __m512i a2t = _mm512_set1_epi64((long long)affine_matrix(AES_TO_TOWER));
+	const u128u *x = J->cols[0], *y = J->cols[1], *ci = J->cols[2], *co = J->cols[3], *z = J->cols[4];
+	__m512i s1 = _mm512_setzero_si512(), s2 = _mm512_setzero_si512(), sinf = _mm512_setzero_si512();
+	for (uint64_t i = J->begin; i + 4 <= J->end; i += 4) {
+		const uint64_t h = J->half + i;
+		__m512i e = _mm512_gf2p8affine_epi64_epi8(_mm512_loadu_si512((const void *)(J->eq + i)), t2a, 0);
+		__m512i xh = _mm512_loadu_si512((const void *)(x + h)), yh = _mm512_loadu_si512((const void *)(y + h));
+		__m512i ch = _mm512_loadu_si512((const void *)(ci + h));
+		__m512i cp = _mm512_xor_si512(ch, _mm512_loadu_si512((const void *)(ci + i)));
+		__m512i xp = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(_mm512_xor_si512(xh, _mm512_loadu_si512((const void *)(x + i))), cp), t2a, 0);
+		__m512i yp = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(_mm512_xor_si512(yh, _mm512_loadu_si512((const void *)(y + i))), cp), t2a, 0);
+		sinf = _mm512_xor_si512(sinf, aes_mul7(e, aes_mul7(xp, yp)));
+		if (J->with_eval_1) {
+			__m512i a = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(xh, ch), t2a, 0), b = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(yh, ch), t2a, 0);
+			__m512i lin = _mm512_gf2p8affine_epi64_epi8(_mm512_xor_si512(ch, _mm512_loadu_si512((const void *)(co + h))), t2a, 0);
+			s1 = _mm512_xor_si512(s1, aes_mul7(e, _mm512_xor_si512(lin, aes_mul7(a, b))));
+			__m512i l2 = _mm512_xor_si512(_mm512_xor_si512(xh, yh), _mm512_xor_si512(ch, _mm512_loadu_si512((const void *)(z + h))));
+			s2 = _mm512_xor_si512(s2, aes_mul7(e, _mm512_gf2p8affine_epi64_epi8(l2, t2a, 0)));
+		}
+	}
+	u128 lanes[4];
+	_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(s1, a2t, 0));
+	J->out[0] = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+	_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(sinf, a2t, 0));
+	J->out[1] = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+	_mm512_storeu_si512((void *)lanes, _mm512_gf2p8affine_epi64_epi8(s2, a2t, 0));
+	J->out[2] = lanes[0] ^ lanes[1] ^ lanes[2] ^ lanes[3];
+	return NULL;
+}
+static void *add_worker_scalar(void *p) {
+	add_job *J = (add_job *)p;
+	const u128u *x = J->cols[0], *y = J->cols[1], *ci = J->cols[2], *co = J->cols[3], *z = J->cols[4];
+	u128 s1 = 0, s2 = 0, sinf = 0;
+	for (uint64_t i = J->begin; i < J->end; i++) {
+		const uint64_t h = J->half + i;
+		sinf ^= b128_mul(J->eq[i], b128_mul(x[h] ^ x[i] ^ ci[h] ^ ci[i], y[h] ^ y[i] ^ ci[h] ^ ci[i]));
+		if (J->with_eval_1) {
+			s1 ^= b128_mul(J->eq[i], b128_mul(x[h] ^ ci[h], y[h] ^ ci[h]) ^ ci[h] ^ co[h]);
+			s2 ^= b128_mul(J->eq[i], x[h] ^ y[h] ^ ci[h] ^ z[h]);
+		}
+	}
+	J->out[0] = s1, J->out[1] = sinf, J->out[2] = s2;
+	return NULL;
+}
+
+int cpu_u32add_round_evals(u128u *const *cols, uint32_t n_vars, const u128u *eq, int with_eval_1, int n_threads, int use_gfni, u128u *out /* 3 */) {
+	tower_init();
+	uint64_t half = (uint64_t)1 << (n_vars - 1);
+	int gfni = use_gfni && cpu_has_gfni512() && half >= 4;
+	if (n_threads < 1 || half < (1u << 12)) n_threads = 1;
+	pthread_t *th = malloc(sizeof(pthread_t) * n_threads);
+	add_job *jobs = malloc(sizeof(add_job) * n_threads);
+	u128 *parts = calloc((size_t)3 * n_threads, sizeof(u128));
+	int started = 0;
+	for (int t = 0; t < n_threads; t++) {
+		uint64_t b = (half * t / n_threads) & ~3ull, e = t + 1 == n_threads ? half : (half * (t + 1) / n_threads) & ~3ull;
+		if (b >= e) continue;
+		jobs[started] = (add_job){cols, eq, b, e, half, with_eval_1, parts + (size_t)3 * started};
+		if (n_threads == 1) (gfni ? add_worker_gfni : add_worker_scalar)(&jobs[started]);
+		else pthread_create(&th[started], NULL, gfni ? add_worker_gfni : add_worker_scalar, &jobs[started]);
+		started++;
+	}
+	if (n_threads > 1)
+		for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+	for (uint32_t k = 0; k < 3; k++) {
+		u128 s = 0;
+		for (int t = 0; t < started; t++) s ^= parts[(size_t)3 * t + k];
+		out[k] = s;
+	}
+	free(th);
+	free(jobs);
+	free(parts);
+	return gfni;
+}
+
+/* timed loop: all n_vars rounds (round values, fold of the 5 multilinears, eq halving), `reps` times */
+double cpu_u32add_zerocheck_bench(uint32_t n_vars, int reps, int n_threads, int use_gfni, u128u *checksum) {
+	const uint32_t m = 5;
+	uint64_t n = (uint64_t)1 << n_vars;
+	u128u *buf[5];
+	u128u *eq = aligned_alloc(64, sizeof(u128) * (n / 2 > 4 ? n / 2 : 4));
+	u128 vals[3];
+	uint64_t s = 0x3232323;
+	for (uint32_t t = 0; t < m; t++) buf[t] = aligned_alloc(64, sizeof(u128) * n);
+	u128 z = ((u128)0x2E895399AF449ACEull << 64) | 0x499596F6E5FCCAFAull, acc = 0;
+	double total = 0;
+	for (int r = -1; r < reps; r++) {
+		for (uint32_t t = 0; t < m; t++)
+			for (uint64_t i = 0; i < n; i++) {
+				s = s * 6364136223846793005ull + 1442695040888963407ull;
+				buf[t][i] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+			}
+		for (uint64_t i = 0; i < n / 2; i++) {
+			s = s * 6364136223846793005ull + 1442695040888963407ull;
+			eq[i] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+		}
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		for (uint32_t v = n_vars; v >= 1; v--) {
+			cpu_u32add_round_evals(buf, v, eq, v != n_vars, n_threads, use_gfni, (u128u *)vals);
+			acc ^= vals[0] ^ vals[1] ^ vals[2];
+			uint64_t half = (uint64_t)1 << (v - 1);
+			for (uint32_t t = 0; t < m; t++) cpu_fold(buf[t], buf[t] + half, half, (const u128u *)&z, half >= (1u << 13) ? n_threads : 1, use_gfni);
+			for (uint64_t i = 0; i < half / 2; i++) eq[i] ^= eq[half / 2 + i];
+			z = z * 3 + 1;
+		}
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (r >= 0) total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+	}
+	if (checksum) *checksum = acc;
+	for (uint32_t t = 0; t < m; t++) free(buf[t]);
+	free(eq);
+	return total;
+}

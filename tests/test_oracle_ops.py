@@ -399,6 +399,23 @@ def test_cpu_chi_zerocheck_arm_matches_oracle(oracle):
             assert o.cpu_chi_round_evals(cols, n_out, n_b, nv, eq, True, thr, gfni) == [list(e) for e in exp], (nv, thr, gfni)
 
 
+def test_cpu_u32add_zerocheck_arm_matches_oracle(oracle):
+    """the timed CPU arm of BASELINE config #3 (u32_add zerocheck rounds) against the generic eq-ind evaluator restatement"""
+    from binius_b200 import ArithCircuit as A
+
+    o = oracle
+    v = [A.var(i) for i in range(5)]
+    comps = [(v[0] + v[2]) * (v[1] + v[2]) + v[2] - v[3], v[0] + v[1] + v[2] - v[4]]
+    for nv, thr in [(2, 1), (3, 1), (12, 3), (13, 8)]:
+        cols = [o.rand_b128(950 + t, 1 << nv) for t in range(5)]
+        eq = o.rand_b128(78, 1 << (nv - 1))
+        exp = o.eq_ind_round_evals(cols, [len(c) for c in cols], [0] * 5, nv, eq, [c.steps for c in comps],
+                                   [c.leading_term().steps for c in comps], [1, 2], [0, 0])
+        for gfni in (True, False):
+            assert o.cpu_u32add_round_evals(cols, nv, eq, True, thr, gfni) == [exp[0][0], exp[0][1], exp[1][0]], (nv, thr, gfni)
+    assert o.cpu_u32add_zerocheck_parallel(10, 0.05, 2)["value"] > 0
+
+
 def _bitrev(i, n):
     return int(format(i, f"0{n}b")[::-1], 2) if n else 0
 

@@ -65,7 +65,7 @@ static int run_cfg3(bool tail) {
 	// vars: 0 x, 1 y, 2 cin, 3 cout, 4 z
 	ExprEval c1 = hal.compile_expr({ExprStep::var(0), ExprStep::var(2), ExprStep::add(0, 1), ExprStep::var(1), ExprStep::add(3, 1), ExprStep::mul(2, 4),
 									ExprStep::add(5, 1), ExprStep::var(3), ExprStep::add(6, 7)});
-	ExprEval l1 = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::mul(0, 1)});
+	ExprEval l1 = hal.compile_expr({ExprStep::var(0), ExprStep::var(2), ExprStep::add(0, 1), ExprStep::var(1), ExprStep::add(3, 1), ExprStep::mul(2, 4)});  // leading term (x + cin)(y + cin)
 	ExprEval c2 = hal.compile_expr({ExprStep::var(0), ExprStep::var(1), ExprStep::add(0, 1), ExprStep::var(2), ExprStep::add(2, 3), ExprStep::var(4), ExprStep::add(4, 5)});
 	ExprEval l2 = hal.compile_expr({ExprStep::constant(F128{})});
 	Timer t(hal);
