@@ -1649,10 +1649,18 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 	uint32_t gx = grid_for(ctx, A.half, 256, 2);
 	gx = std::max(1u, std::min(gx, (uint32_t)(ctx->n_sms * 4 / std::min(total, (uint32_t)ctx->n_sms * 4) + 1)));
 	const uint64_t vals_bytes = (uint64_t)total * A.half * 16;
-	if (tc_mode && eq_ind && A.half >= 4096 && A.half % tc::CHUNK == 0 && vals_bytes <= (48ull << 30)) {
-		// materialise C(P(i)), then sum_i E[i] * val[i] as tensor-core inner-product jobs
-		const uint64_t gmat_bytes = (uint64_t)(total + 1) * 512 * 4;
-		if ((rc = ensure_scratch(ctx, vals_bytes + gmat_bytes))) return rc;
+	// materialise C(P(i)), then sum_i E[i] * val[i] as tensor-core inner-product jobs -- when the values fit: at most
+	// half of the free device memory beyond the scratch already held, and a failed allocation falls through to the
+	// scratch-free per-lane kernel instead of failing the round
+	const uint64_t gmat_bytes = (uint64_t)(total + 1) * 512 * 4;
+	bool materialise = tc_mode && eq_ind && A.half >= 4096 && A.half % tc::CHUNK == 0 && vals_bytes <= (48ull << 30);
+	if (materialise && vals_bytes + gmat_bytes > ctx->scratch_bytes) {
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || vals_bytes + gmat_bytes > (free_b + ctx->scratch_bytes) / 2) materialise = false;
+		cudaGetLastError();
+	}
+	if (materialise && ensure_scratch(ctx, vals_bytes + gmat_bytes) != B200_OK) materialise = false;
+	if (materialise) {
 		uint4 *vals = (uint4 *)ctx->d_scratch;
 		k_eq_ind_vals<<<dim3(gx, total), 256, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, A, vals);
 		B200_LAUNCH_CHECK(ctx);
