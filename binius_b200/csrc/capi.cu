@@ -557,6 +557,7 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	else if (!strcmp(key, "fold")) ctx->tune_fold = value;
 	else if (!strcmp(key, "round_evals_tc")) ctx->tune_round_evals_tc = value;
 	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
+	else if (!strcmp(key, "uni_linear")) ctx->tune_uni_linear = value;
 	else if (!strcmp(key, "tail_grid")) ctx->tune_tail_grid = value;
 	else if (!strcmp(key, "tail_trace")) ctx->tune_tail_trace = value;
 	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
@@ -2262,7 +2263,9 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 	if (n_out == 0 || n_comp == 0) return B200_OK;
 	const uint32_t n_pts = max_deg > 1 ? (max_deg - 1) << skip : 0;
 
-	int32_t rc = ensure_scratch(ctx, (uint64_t)n_comp * n_out * 16);
+	// scratch: the output table, then (linear-monomial route) E of up to m columns and the parity matrices of their jobs
+	const uint64_t out_bytes = ((uint64_t)n_comp * n_out * 16 + 255) & ~255ull;
+	int32_t rc = ensure_scratch(ctx, out_bytes + (uint64_t)m * 2048 + (uint64_t)(m + 1) * 2048);
 	if (rc) return rc;
 	uint4 *d_out = reinterpret_cast<uint4 *>(ctx->d_scratch);
 	if (zero_out) B200_CUDA(ctx, cudaMemsetAsync(d_out, 0, (uint64_t)n_comp * n_out * 16, ctx->stream));
@@ -2324,6 +2327,11 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 		bool fast = lvl == 3 && skip >= 2 && !ctx->tune_uni_generic;
 		std::vector<uint2> mono;
 		std::vector<uint32_t> ctab(uni::CTAB * (size_t)n_comp);
+		// coefficient-1 linear monomials leave the kernel when the sub-cube is 128 rows and the tensor-core outer product
+		// applies (univariate.cuh, k_uni_linear)
+		const bool lin_out = fast && skip == 7 && ctx->tune_uni_linear && ctx->tune_round_evals_tc && n_eq >= 8192 && n_eq % tc::CHUNK == 0;
+		std::vector<uint32_t> lin_off(n_comp + 1, 0), lin_cols;
+		std::map<uint32_t, uint32_t> lin_slot;  // column -> row of E
 		for (uint32_t c = 0; fast && c < n_comp; c++) {
 			if (!comps[c]->poly_ok) {
 				fast = false;
@@ -2336,7 +2344,10 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 				if (t.second >> 8) fast = false;
 				const size_t deg = t.first.size();
 				if (t.second == 1 && deg == 2) quad.push_back(make_uint2(t.first[0] * uni::SUBS * K, t.first[1] * uni::SUBS * K));
-				else if (t.second == 1 && deg == 1) lin.push_back(make_uint2(t.first[0] * uni::SUBS * K, 0));
+				else if (t.second == 1 && deg == 1 && lin_out && levels[t.first[0]] == 0 && pts[c]) {
+					auto it = lin_slot.emplace(t.first[0], (uint32_t)lin_slot.size()).first;
+					lin_cols.push_back(it->second);
+				} else if (t.second == 1 && deg == 1) lin.push_back(make_uint2(t.first[0] * uni::SUBS * K, 0));
 				else gen.push_back(make_uint2((deg > 0 ? t.first[0] : uni::MONO_NONE) | ((deg > 1 ? t.first[1] : uni::MONO_NONE) << 9) | ((uint32_t)t.second << 18), 0));
 			}
 			uint32_t *ct = &ctab[uni::CTAB * c];
@@ -2344,6 +2355,7 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 			mono.insert(mono.end(), quad.begin(), quad.end());
 			mono.insert(mono.end(), lin.begin(), lin.end());
 			mono.insert(mono.end(), gen.begin(), gen.end());
+			lin_off[c + 1] = (uint32_t)lin_cols.size();
 		}
 		if (fast) {
 			// shared-memory layout for `ml` columns / `nc` compositions / `nm` monomials; returns the dynamic size
@@ -2397,7 +2409,8 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 			};
 			uni::B8Args B;
 			const uint32_t smem8 = layout(B, m, n_comp, mono.size());
-			if (fits(smem8, m)) {
+			// (with linear monomials taken out some columns may not be referenced any more: the range planner compacts them away)
+			if (lin_slot.empty() && fits(smem8, m)) {
 				if ((rc = stage(B, A.mls, A.levels, m, 0, n_comp, mono, ctab)) || (rc = launch(B, smem8))) return rc;
 			} else {
 				// Too many columns for one CTA's shared memory (e.g. 153 columns at skip 7): constraints are local,
@@ -2446,6 +2459,25 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 					if ((rc = launch(staged[ri].first, staged[ri].second))) return rc;
 					if (ri + 1 < staged.size()) B200_LAUNCH_CHECK(ctx);
 				}
+			}
+			if (fast && !lin_slot.empty()) {
+				B200_LAUNCH_CHECK(ctx);
+				// E_j = evaluate_partial_high of every linearly used column by eq: one job per column, ONE tensor-core launch
+				std::vector<tc::TcJob> jobs(lin_slot.size());
+				for (auto &kv : lin_slot) jobs[kv.second] = tc::TcJob{(const uint4 *)eq_ind, nullptr, (const uint4 *)mls[kv.first], nullptr};
+				const uint32_t n_slots = (uint32_t)lin_slot.size();
+				uint4 *d_E = reinterpret_cast<uint4 *>(ctx->d_scratch + out_bytes);
+				uint32_t *gmat = nullptr;
+				if ((rc = launch_tc_pairs(ctx, jobs, n_eq, {}, out_bytes + (uint64_t)m * 2048, &gmat))) return rc;
+				tc::k_tc_outer_combine<<<n_slots, 128, 0, ctx->stream>>>(gmat, 1, d_E);
+				B200_LAUNCH_CHECK(ctx);
+				ArgPack pk4;
+				size_t o_lo = pk4.add(lin_off.data(), 4 * lin_off.size()), o_lc = pk4.add(lin_cols.data(), 4 * lin_cols.size());
+				uint8_t *base4;
+				if ((rc = pk4.commit(ctx, &base4))) return rc;
+				uni::LinArgs LA{(const uint32_t *)(base4 + o_lo), (const uint32_t *)(base4 + o_lc), A.comp_pts, A.lag, d_E, d_out, n_out};
+				if ((rc = set_smem(ctx, uni::k_uni_linear, FIELD_TABLE_BYTES))) return rc;
+				uni::k_uni_linear<<<n_comp, 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, LA);
 			}
 		}
 		if (!fast) switch (lvl) {

@@ -93,6 +93,7 @@ struct b200_ctx {
 	int tune_fold = 2;             // 2 TMA-staged K64, 1 K64, 0 LUT128
 	int tune_round_evals_tc = 1;   // 1 tensor-core plans, 0 per-lane kernels, 2 materialised values only
 	int tune_uni_generic = 0;      // 1 forces the generic univariate-skip kernel
+	int tune_uni_linear = 1;       // 0: linear monomials of the univariate-skip round stay in k_uni_b8 (A/B, tests)
 	int tune_tail_grid = 1;        // 0: the persistent sumcheck kernel always runs on one CTA
 	int tune_tail_trace = 0;       // 1: b200_sumcheck_tail_finish prints CTA 0's per-round time stamps (debugging aid)
 };

@@ -156,7 +156,11 @@ __global__ void __launch_bounds__(THREADS) k_pair_tc(const TcArgs A) {
 			off += step;
 		};
 		// register ring of raw loads, one slot per pipeline stage (slot u <-> stage u): the HBM latency
-		// spans several stages, and stage / ring indices stay compile-time constants
+		// spans several stages, and stage / ring indices stay compile-time constants.  (A ring twice as deep -- loads
+		// six stages ahead -- measured the same 0.186 ms at m = 8, n = 20: the long_scoreboard stalls ncu shows are
+		// producers with nothing else to do, not the limiter; that is the shared-memory port, which carries every
+		// operand byte twice -- 32 KiB per stage written by the producers, 32 KiB read by the tensor core -- against
+		// 256 tensor cycles per stage: 2 : 1, hence the ~45 % tensor-pipe ceiling of the 8x bit-to-byte expansion.)
 		uint4 rh[NSTAGE], rl[NSTAGE];
 #pragma unroll
 		for (uint32_t u = 0; u < NSTAGE; u++) load(rh[u], rl[u]);
@@ -280,9 +284,12 @@ __global__ void __launch_bounds__(128) k_pair_tc_combine(const uint8_t *__restri
 // G of one or more jobs -> 128 field elements: out[q] = the element whose bit p is (XOR over the jobs of) G[p][q].
 // This is the OUTER-PRODUCT use of the bit-GEMM: with a = a B128 vector v and b = the 128-bit words w of a bit-packed B1
 // matrix,  out[q] = sum_j v[j] * bit_q(w[j])  -- fold_left / evaluate_partial_high of a B1 multilinear by a large tensor
-// query down to 7 variables (ring-switch partial evaluations, core/src/ring_switch/prove.rs:147-208).  grid = 1, block = 128.
+// query down to 7 variables (ring-switch partial evaluations, core/src/ring_switch/prove.rs:147-208).  block = 128.
+// grid = number of outputs; block b combines the jobs b * n_jobs .. and writes out[128 b ..].
 __global__ void __launch_bounds__(128) k_tc_outer_combine(const uint32_t *__restrict__ gmat, uint32_t n_jobs, uint4 *__restrict__ out) {
 	__shared__ uint32_t o[128][4];
+	gmat += (size_t)blockIdx.x * n_jobs * 512;
+	out += (size_t)blockIdx.x * 128;
 	const uint32_t m = threadIdx.x, p = rho(m);
 	o[m][0] = o[m][1] = o[m][2] = o[m][3] = 0;
 	__syncthreads();

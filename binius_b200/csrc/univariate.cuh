@@ -419,6 +419,40 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 		if (i < ctabS[CTAB * c + 4]) atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, accL[k]);
 }
 
+// Linear monomials of the B8 fast path (skip = 7, B1 columns).  sum_s eq[s] * P_j(s, x_i) is linear in the column:
+//     sum_s eq[s] * sum_t bit_j[s][t] * L_t(x_i)  =  sum_t L_t(x_i) * E_j[t],     E_j[t] = sum_s eq[s] * bit_j[s*128 + t],
+// and E_j is evaluate_partial_high of the column by eq (an outer-product bit-GEMM on the tensor cores, roundevals_tc.cuh).
+// So coefficient-1 linear monomials never enter k_uni_b8 (no extrapolation of columns that occur only linearly, fewer
+// gathers per composition); this kernel adds  sum_t L_t(x_i) * (sum_{j in lin(c)} E_j[t])  to out[c][i].
+// grid = n_comp, block = 128 (= 2^skip points per degree), dyn smem = FIELD_TABLE_BYTES
+struct LinArgs {
+	const uint32_t *lin_off;   // device [n_comp + 1]: range of composition c in lin_cols
+	const uint32_t *lin_cols;  // device: slot of the column in E (one per coefficient-1 linear monomial)
+	const uint32_t *comp_pts;  // device [n_comp]
+	const uint8_t *lag;        // device [n_pts][128]
+	const uint4 *E;            // device [n_slots][128]
+	uint4 *out;
+	uint32_t n_out;
+};
+__global__ void __launch_bounds__(128) k_uni_linear(const uint8_t *__restrict__ g_tables, const LinArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	__shared__ uint4 Ec[128];
+	const uint32_t c = blockIdx.x, t = threadIdx.x, n_in = A.comp_pts[c];
+	const uint32_t j0 = A.lin_off[c], j1 = A.lin_off[c + 1];
+	if (j0 == j1 || n_in == 0) return;
+	uint4 e = u4_zero();
+	for (uint32_t j = j0; j < j1; j++) e ^= A.E[(uint64_t)A.lin_cols[j] * 128 + t];
+	Ec[t] = e;
+	__syncthreads();
+	for (uint32_t i = t; i < n_in; i += 128) {
+		const uint8_t *row = A.lag + (uint64_t)i * 128;
+		uint4 acc = u4_zero();
+		for (uint32_t u = 0; u < 128; u++) acc ^= f_mul128_sub(T, Ec[u], make_uint4(row[u], 0, 0, 0), 3);
+		A.out[(uint64_t)c * A.n_out + i] ^= acc;  // the only writer of this element in this launch; stream-ordered after k_uni_b8
+	}
+}
+
 // extrapolate_round_evals (univariate.rs:565-640): composition c was evaluated at n_in = (deg_c-1)*2^k
 // points; with zeros on the skipped domain those values determine a polynomial of degree < deg_c*2^k,
 // whose values on the rest of the domain are B8-linear combinations of the evaluations:

@@ -159,3 +159,38 @@ def test_univariate_skip7_153_columns_2pow16_rows(hal, oracle):
             hal.set_tuning("uni_generic", 0)
         assert np.array_equal(hal.to_host(out.partial_eq_ind_evals), eq)
         assert out.round_evals == exp, "generic kernel" if generic else "split fast path"
+
+
+def test_univariate_skip7_linear_monomial_route_2pow20_rows(hal, oracle):
+    """From 2^12 sub-cubes of 128 rows on, coefficient-1 linear monomials leave k_uni_b8: their sums are
+    evaluate_partial_high of the column by the eq-indicator (tensor-core outer product) folded with the Lagrange
+    coefficients (k_uni_linear).  The keccak shape plus compositions with a constant term, a scaled linear term and a
+    purely linear composition, against the CPU arm and against the kernel with the route switched off."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals
+
+    be = B200Backend(hal)
+    n_vars, skip, m = 20, 7, 153
+    rng = random.Random(2020)
+    cols = [oracle.rand_b128(2530 + j, (1 << n_vars) // 128) for j in range(m)]
+    v = [A.var(i) for i in range(m)]
+    comps = keccak_chi_compositions() + [v[150] * v[151] + v[152] + A.constant(0x53), v[3] * v[77] + A.constant(0x0B) * v[151] + v[0],
+                                         v[1] + v[2] + v[152]]
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    mls = [TransparentMultilinear(hal.to_device(c), 0, n_vars) for c in cols]
+    eq = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << len(ch)) - 1)), 0, ch)
+    exp, _ = oracle.cpu_univariate_b1(cols, n_vars, skip, eq, [list(c.steps) for c in comps[:-1]], 1 << skip)
+    got = {}
+    for lin in (1, 0):
+        hal.set_tuning("uni_linear", lin)
+        try:
+            before = hal.launch_count()
+            got[lin] = zerocheck_univariate_evals(be, mls, comps, ch, skip, 256).round_evals
+            launches = hal.launch_count() - before
+        finally:
+            hal.set_tuning("uni_linear", 1)
+        if lin:
+            routed = launches
+    assert got[1] == got[0], "linear-monomial route vs all monomials in the kernel"
+    assert got[1][:-1] == exp, "vs the CPU arm"
+    assert routed > launches, "the route adds the outer-product, combine and k_uni_linear launches"
