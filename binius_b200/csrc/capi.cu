@@ -2548,9 +2548,21 @@ int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *cons
 	const uint64_t n_vals = max_domain_size > (1u << skip) ? (uint64_t)n_comp * (max_domain_size - (1u << skip)) : 0;
 	std::vector<uint64_t> bytes(m);
 	for (uint32_t j = 0; j < m; j++) bytes[j] = std::max<uint64_t>(((1ull << (n_vars - log_chunks)) << levels[j]) / 8, 1);
+	// Columns laid out at one stride on both sides (a witness arena, the usual case): a chunk of all columns is ONE
+	// pitched copy.  One cudaMemcpyAsync per column and chunk (153 x 8 copies of 2 MiB for keccak 2^18) costs the copy
+	// engine a few microseconds each, ~6 ms over the upload.
+	bool pitched = m > 1;
+	const ptrdiff_t hs = m > 1 ? (const uint8_t *)host_cols[1] - (const uint8_t *)host_cols[0] : 0, ds = m > 1 ? (const uint8_t *)mls[1] - (const uint8_t *)mls[0] : 0;
+	for (uint32_t j = 0; j < m && pitched; j++)
+		pitched = bytes[j] == bytes[0] && (const uint8_t *)host_cols[j] - (const uint8_t *)host_cols[0] == (ptrdiff_t)j * hs && (const uint8_t *)mls[j] - (const uint8_t *)mls[0] == (ptrdiff_t)j * ds;
+	pitched = pitched && hs >= (ptrdiff_t)(bytes[0] << log_chunks) && ds >= (ptrdiff_t)(bytes[0] << log_chunks);
 	auto upload = [&](uint32_t c) -> int32_t {
-		for (uint32_t j = 0; j < m; j++)
-			B200_CUDA(ctx, cudaMemcpyAsync((uint8_t *)mls[j] + c * bytes[j], (const uint8_t *)host_cols[j] + c * bytes[j], bytes[j], cudaMemcpyHostToDevice, ctx->s_h2d));
+		if (pitched) {
+			B200_CUDA(ctx, cudaMemcpy2DAsync((uint8_t *)mls[0] + c * bytes[0], (size_t)ds, (const uint8_t *)host_cols[0] + c * bytes[0], (size_t)hs, bytes[0], m, cudaMemcpyHostToDevice, ctx->s_h2d));
+		} else {
+			for (uint32_t j = 0; j < m; j++)
+				B200_CUDA(ctx, cudaMemcpyAsync((uint8_t *)mls[j] + c * bytes[j], (const uint8_t *)host_cols[j] + c * bytes[j], bytes[j], cudaMemcpyHostToDevice, ctx->s_h2d));
+		}
 		B200_CUDA(ctx, cudaEventRecord(ctx->ev_in[c & 3], ctx->s_h2d));
 		return B200_OK;
 	};

@@ -225,3 +225,34 @@ def test_streamed_round_equals_the_resident_one(hal, oracle, skip, log_chunks):
     assert np.array_equal(hal.to_host(got.partial_eq_ind_evals), hal.to_host(exp.partial_eq_ind_evals))
     for d, h in zip(dst, host_cols):
         assert np.array_equal(hal.to_host(d.evals), h)
+
+
+def test_streamed_round_from_a_witness_arena_with_the_linear_route(hal, oracle):
+    """Columns at one stride in host and device memory: every chunk is ONE pitched copy; at skip 7 with >= 2^12 sub-cubes
+    per chunk the linear monomials of every chunk take the tensor-core route.  Against the resident call with the
+    route switched off."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import B200Backend, TransparentMultilinear, zerocheck_univariate_evals, zerocheck_univariate_evals_streamed
+
+    be = B200Backend(hal)
+    n_vars, skip, m, log_chunks = 21, 7, 6, 1
+    words = (1 << n_vars) // 128
+    h_arena = hal.host_alloc(m * words)
+    h_arena[:] = oracle.rand_b128(7100, m * words)
+    host_cols = [h_arena[j * words:(j + 1) * words] for j in range(m)]
+    v = [A.var(i) for i in range(m)]
+    comps = [v[0] * v[1] + v[2] + v[3], v[4] * v[0] + v[5] + A.constant(0x1D)]
+    ch = [random.Random(71).getrandbits(128) for _ in range(n_vars - skip)]
+    resident = [TransparentMultilinear(hal.to_device(np.array(h)), 0, n_vars) for h in host_cols]
+    hal.set_tuning("uni_linear", 0)
+    try:
+        exp = zerocheck_univariate_evals(be, resident, comps, ch, skip, 256)
+    finally:
+        hal.set_tuning("uni_linear", 1)
+    d_arena = hal.dev_alloc(m * words)
+    hal.fill(d_arena, 0)
+    dst = [TransparentMultilinear(d_arena.slice(j * words, (j + 1) * words), 0, n_vars) for j in range(m)]
+    hal.sync()
+    got = zerocheck_univariate_evals_streamed(be, host_cols, dst, comps, ch, skip, 256, log_chunks)
+    assert got.round_evals == exp.round_evals
+    assert np.array_equal(hal.to_host(d_arena), np.array(h_arena))
