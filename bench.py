@@ -54,7 +54,9 @@ def peaks():
 def profiled_traffic(kernel="k_lerp_tma"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` summary of this same command (profiles/); None when no capture is committed."""
-    path = os.path.join(ROOT, "profiles", f"r1_fold_{kernel}_ncu_full.csv")
+    path = os.path.join(ROOT, "profiles", f"r2_fold_{kernel}_ncu_full.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", f"r1_fold_{kernel}_ncu_full.csv")
     try:
         rd = wr = None
         for line in open(path):
@@ -275,6 +277,8 @@ def main():
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-keccak", action="store_true")
+    ap.add_argument("--no-compiled-cfg3", action="store_true", help="skip the compiled-host runs of config #3 (under ncu the persistent "
+                    "kernel cannot get its challenges: the profiler serialises the launch call)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -295,6 +299,8 @@ def main():
     all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # rank 0 prints ONE line on stdout: no NCCL version banner before it
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hal = binius_b200.B200Layer(local_rank)
     peak, peak_src = peaks()
@@ -576,7 +582,7 @@ def main():
         # persistent kernel (csrc/tail_grid.cuh: every round in ONE cooperative kernel, challenges through host-mapped
         # mailboxes) -- the latter is the configuration's number
         comp3 = {}
-        if rank == 0:
+        if rank == 0 and not args.no_compiled_cfg3:
             exe = os.path.join(ROOT, "tools", "keccak_replay_cpp")
             env3 = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank] if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local_rank))
             for key, extra in (("persistent_kernel", []), ("per_call", ["notail"])):
