@@ -842,6 +842,8 @@ def main():
                 biv["cpu_baseline"] = arm(lambda: orc.cpu_bivariate_sumcheck_parallel(8, 20, 8, 5.0))
             if cfg3:
                 cfg3["cpu_baseline"] = arm(lambda: orc.cpu_u32add_zerocheck_parallel(18, 4.0))
+            if extras and "tensor_expand_k22" in extras:
+                extras["tensor_expand_k22"]["cpu_baseline"] = arm(lambda: orc.cpu_tensor_expand_parallel(22, 3.0))
             if ntt_res:
                 ntt_res["S1_rs_encode"]["cpu_baseline"] = arm(lambda: orc.cpu_ntt_parallel(6, 18, 1, 5.0, d=24))
             if uni and "error" not in uni:

@@ -377,6 +377,32 @@ def cpu_chi_zerocheck_parallel(n_out: int, n_b: int, n_vars: int, budget_s: floa
                       f"{n_threads} threads; C restatement of the eq-ind evaluator loop (GFNI multiply), not the Rust binary"}
 
 
+def cpu_tensor_expand(data, log_n: int, coords, n_threads: int = 1, use_gfni: bool = True):
+    """the threaded GFNI CPU arm of tensor_expand: data[: 2^log_n] filled, returns the 2^(log_n + k) expansion"""
+    k = len(coords)
+    buf = np.zeros(((1 << (log_n + k)), 2), np.uint64)
+    buf[: 1 << log_n] = _c(data)[: 1 << log_n]
+    cs = to_arr(list(coords)) if not isinstance(coords, np.ndarray) else _c(coords)
+    lib().cpu_tensor_expand(_p(buf), C.c_uint32(log_n), _p(cs), C.c_uint32(k), C.c_int(n_threads), C.c_int(int(use_gfni)))
+    return buf
+
+
+def cpu_tensor_expand_parallel(k: int, budget_s: float = 3.0, n_threads: int = 0):
+    """Times the expansion of [1] by k coordinates (tensor_product_full_query) on this host."""
+    import os
+
+    n_threads = n_threads or (os.cpu_count() or 1)
+    fn = lib().cpu_tensor_expand_bench
+    fn.restype = C.c_double
+    chk = np.zeros((1, 2), np.uint64)
+    t1 = fn(C.c_uint32(k), C.c_int(1), C.c_int(n_threads), C.c_int(1), _p(chk))
+    reps = max(1, min(200, int(budget_s / max(t1, 1e-4))))
+    t = fn(C.c_uint32(k), C.c_int(reps), C.c_int(n_threads), C.c_int(1), _p(chk)) if reps > 1 else t1
+    return {"value": reps * (1 << k) / t, "unit": "elems/s", "ms": t / reps * 1e3, "cores": n_threads, "kind": "port",
+            "sample": f"{reps} x expansion of [1] by {k} coordinates (2^{k} B128 elements), {n_threads} threads, AVX-512+GFNI; "
+                      "C restatement of tensor_prod_eq_ind (crates/math/src/tensor_prod_eq_ind.rs:35-77), not the Rust binary"}
+
+
 def cpu_u32add_round_evals(cols, n_vars: int, eq, with_eval_1: bool, n_threads: int = 1, use_gfni: bool = True):
     """[C1 at 1, C1 at infinity, C2 at 1] of the u32_add gadget compositions (BASELINE config #3) by the threaded GFNI
     CPU arm; cols = x, y, cin, cout, z as 2^n_vars B128 elements each"""

@@ -782,3 +782,95 @@ double cpu_u32add_zerocheck_bench(uint32_t n_vars, int reps, int n_threads, int 
 	free(eq);
 	return total;
 }
+
+/* =================================================================================================
+ * CPU arm of the eq-indicator tensor expansion (crates/math/src/tensor_prod_eq_ind.rs:35-77, the FastCpuLayer's
+ * tensor_expand, fast_compute/src/layer.rs): round r maps the 2^r filled elements to 2^(r+1):
+ *     hi[i] = lo[i] * z_r;   lo[i] -= hi[i]
+ * with the GFNI multiply on 4 x B128 per register, the rounds split over threads once they are large enough
+ * (the reference parallelises the large rounds with rayon the same way).
+ * ================================================================================================= */
+typedef struct {
+	u128u *lo, *hi;
+	uint64_t n;
+	u128 z;
+	int gfni;
+} exp_job;
+
+TGT static void expand_gfni(u128u *lo, u128u *hi, uint64_t n, u128 z) {
+	const __m512i t2a = _mm512_set1_epi64((long long)affine_matrix(TOWER_TO_AES));
+	const __m512i a2t = _mm512_set1_epi64((long long)affine_matrix(AES_TO_TOWER));
+	__m512i zv = _mm512_gf2p8affine_epi64_epi8(_mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i *)&z)), t2a, 0);
+	uint64_t i = 0;
+	for (; i + 4 <= n; i += 4) {
+		__m512i a = _mm512_loadu_si512((const void *)(lo + i));
+		__m512i p = _mm512_gf2p8affine_epi64_epi8(aes_mul7(_mm512_gf2p8affine_epi64_epi8(a, t2a, 0), zv), a2t, 0);
+		_mm512_storeu_si512((void *)(hi + i), p);
+		_mm512_storeu_si512((void *)(lo + i), _mm512_xor_si512(a, p));
+	}
+	for (; i < n; i++) {
+		u128 p = b128_mul(lo[i], z);
+		hi[i] = p, lo[i] ^= p;
+	}
+}
+static void *exp_worker(void *p) {
+	exp_job *j = (exp_job *)p;
+	if (j->gfni) expand_gfni(j->lo, j->hi, j->n, j->z);
+	else
+		for (uint64_t i = 0; i < j->n; i++) {
+			u128 q = b128_mul(j->lo[i], j->z);
+			j->hi[i] = q, j->lo[i] ^= q;
+		}
+	return NULL;
+}
+/* data[0 .. 2^log_n) filled; expands by the k coordinates to 2^(log_n + k) elements in place */
+int cpu_tensor_expand(u128u *data, uint32_t log_n, const u128u *coords, uint32_t k, int n_threads, int use_gfni) {
+	tower_init();
+	int gfni = use_gfni && cpu_has_gfni512();
+	if (n_threads < 1) n_threads = 1;
+	pthread_t *th = malloc(sizeof(pthread_t) * n_threads);
+	exp_job *jobs = malloc(sizeof(exp_job) * n_threads);
+	for (uint32_t r = 0; r < k; r++) {
+		uint64_t n = (uint64_t)1 << (log_n + r);
+		int nt = n >= (1u << 14) ? n_threads : 1;
+		int started = 0;
+		for (int t = 0; t < nt; t++) {
+			uint64_t b = (n * t / nt) & ~3ull, e = t + 1 == nt ? n : (n * (t + 1) / nt) & ~3ull;
+			if (b >= e) continue;
+			jobs[started] = (exp_job){data + b, data + n + b, e - b, coords[r], gfni};
+			if (nt == 1) exp_worker(&jobs[started]);
+			else pthread_create(&th[started], NULL, exp_worker, &jobs[started]);
+			started++;
+		}
+		if (nt > 1)
+			for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+	}
+	free(th);
+	free(jobs);
+	return gfni;
+}
+double cpu_tensor_expand_bench(uint32_t k, int reps, int n_threads, int use_gfni, u128u *checksum) {
+	uint64_t n = (uint64_t)1 << k;
+	u128u *data = aligned_alloc(64, sizeof(u128) * n);
+	u128 *coords = malloc(sizeof(u128) * (k ? k : 1));
+	uint64_t s = 0x7E7E7E7;
+	double total = 0;
+	u128 acc = 0;
+	for (int r = -1; r < reps; r++) {
+		for (uint32_t t = 0; t < k; t++) {
+			s = s * 6364136223846793005ull + 1442695040888963407ull;
+			coords[t] = ((u128)s << 64) | (s * 0x9E3779B97F4A7C15ull);
+		}
+		data[0] = 1;
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		cpu_tensor_expand(data, 0, (const u128u *)coords, k, n_threads, use_gfni);
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (r >= 0) total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+		acc ^= data[n - 1] ^ data[n / 2];
+	}
+	if (checksum) *checksum = acc;
+	free(data);
+	free(coords);
+	return total;
+}

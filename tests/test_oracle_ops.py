@@ -399,6 +399,20 @@ def test_cpu_chi_zerocheck_arm_matches_oracle(oracle):
             assert o.cpu_chi_round_evals(cols, n_out, n_b, nv, eq, True, thr, gfni) == [list(e) for e in exp], (nv, thr, gfni)
 
 
+def test_cpu_tensor_expand_arm_matches_oracle(oracle):
+    """the timed CPU arm of the eq-indicator expansion against the oracle's tensor_expand"""
+    o = oracle
+    for log_n, k, thr in [(0, 5, 1), (3, 4, 1), (0, 16, 4), (2, 14, 3)]:
+        data = o.rand_b128(40 + log_n, 1 << log_n) if log_n else o.to_arr([1])
+        coords = o.to_ints(o.rand_b128(41 + k, k))
+        full = np.zeros((1 << (log_n + k), 2), np.uint64)
+        full[: 1 << log_n] = data
+        exp = o.tensor_expand(full, log_n, coords)
+        for gfni in (True, False):
+            assert np.array_equal(o.cpu_tensor_expand(data, log_n, coords, thr, gfni), exp), (log_n, k, thr, gfni)
+    assert o.cpu_tensor_expand_parallel(12, 0.05, 2)["value"] > 0
+
+
 def test_cpu_u32add_zerocheck_arm_matches_oracle(oracle):
     """the timed CPU arm of BASELINE config #3 (u32_add zerocheck rounds) against the generic eq-ind evaluator restatement"""
     from binius_b200 import ArithCircuit as A
