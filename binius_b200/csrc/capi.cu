@@ -435,6 +435,8 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_expand_k64<2>, 2 * LUT_BYTES + 6144);
 	SET(k_expand_k64<3>, 3 * LUT_BYTES + 6144);
 	SET(k_expand_small, EXP_SMALL_LOG * (NLUT_BYTES + 2048) + (16u << EXP_SMALL_LOG));
+	SET(k_expand_pair, ((FIELD_TABLE_BYTES + 127) & ~127u) + 2 * (16u << EXP_SMALL_LOG));
+	SET(k_expand_outer, LUT_BYTES + 2048 + (16u << EXP_SMALL_LOG));
 	SET(k_inner_product, FIELD_TABLE_BYTES);
 	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
 	SET(k_fold_right_lut, LUT_BYTES + 2048);
@@ -510,6 +512,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 	for (auto &c : ctx->local_pool) cudaFree(c.p);
 	if (ctx->h_tail_mb) cudaFreeHost(ctx->h_tail_mb);
 	if (ctx->d_tail_ws) cudaFree(ctx->d_tail_ws);
+	if (ctx->d_expand_ws) cudaFree(ctx->d_expand_ws);
 	if (ctx->s_h2d) {
 		cudaStreamDestroy(ctx->s_h2d);
 		cudaStreamDestroy(ctx->s_d2h);
@@ -558,6 +561,7 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	else if (!strcmp(key, "round_evals_tc")) ctx->tune_round_evals_tc = value;
 	else if (!strcmp(key, "uni_generic")) ctx->tune_uni_generic = value;
 	else if (!strcmp(key, "uni_linear")) ctx->tune_uni_linear = value;
+	else if (!strcmp(key, "expand_outer")) ctx->tune_expand_outer = value;
 	else if (!strcmp(key, "tail_grid")) ctx->tune_tail_grid = value;
 	else if (!strcmp(key, "tail_trace")) ctx->tune_tail_trace = value;
 	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
@@ -958,10 +962,50 @@ int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, 
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
 	if (log_n + k > 60 || data_len != (1ull << (log_n + k))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid data length: %llu", (unsigned long long)data_len);
 	if (k == 0) return B200_OK;
-	// rounds that fit one CTA's shared memory
 	uint32_t k_small = 0;
-	if (log_n <= EXP_SMALL_LOG) k_small = std::min(k, EXP_SMALL_LOG - log_n);
-	if (k_small) {
+	if (log_n <= EXP_SMALL_LOG && ctx->tune_expand_outer) {
+		// outer-product plan (kernels.cuh): ONE k_expand_pair launch for in' (the data brought to 2^6 elements), T_mid
+		// (up to 2^12 / |in'| entries) and T_hi (<= 2^10 entries); then in'' = in' x T_mid and out = in'' x T_hi
+		constexpr uint32_t LOG_A = 6, LOG_HI = 10;
+		const uint32_t a1 = log_n < LOG_A ? std::min(k, LOG_A - log_n) : 0, l1 = log_n + a1;  // |in'| = 2^l1
+		const uint32_t k_mid = std::min(k - a1, EXP_SMALL_LOG - std::min(l1, EXP_SMALL_LOG)), l2 = l1 + k_mid;
+		const uint32_t k_hi = std::min(k - a1 - k_mid, LOG_HI);
+		if (!ctx->d_expand_ws) B200_CUDA(ctx, cudaMalloc((void **)&ctx->d_expand_ws, 4 * (16u << EXP_SMALL_LOG)));
+		uint4 *ws_in = (uint4 *)ctx->d_expand_ws, *ws_mid = ws_in + (1u << EXP_SMALL_LOG), *ws_t1 = ws_mid + (1u << EXP_SMALL_LOG), *ws_t2 = ws_t1 + (1u << EXP_SMALL_LOG);
+		ExpandPairArgs P;
+		memset(&P, 0, sizeof P);
+		uint32_t np = 0, cap_log = 0;
+		// in': from the data; written in place when nothing follows
+		P.src[np] = (const uint4 *)data, P.dst[np] = (k_mid || k_hi) ? ws_in : (uint4 *)data, P.log_n[np] = log_n, P.k[np] = a1;
+		for (uint32_t i = 0; i < a1; i++) P.coords[np][i] = to_u4(coords + 2 * i);
+		cap_log = std::max(cap_log, l1), np++;
+		if (k_mid) {
+			P.dst[np] = ws_t1, P.k[np] = k_mid;
+			for (uint32_t i = 0; i < k_mid; i++) P.coords[np][i] = to_u4(coords + 2 * (a1 + i));
+			cap_log = std::max(cap_log, k_mid), np++;
+		}
+		if (k_hi) {
+			P.dst[np] = ws_t2, P.k[np] = k_hi;
+			for (uint32_t i = 0; i < k_hi; i++) P.coords[np][i] = to_u4(coords + 2 * (a1 + k_mid + i));
+			cap_log = std::max(cap_log, k_hi), np++;
+		}
+		const uint32_t pair_smem = ((FIELD_TABLE_BYTES + 127) & ~127u) + 2 * std::max(16u << cap_log, 32u * EXP_SMALL_LOG);
+		k_expand_pair<<<np, 1024, pair_smem, ctx->stream>>>(ctx->d_tables, P);
+		B200_LAUNCH_CHECK(ctx);
+		const uint4 *cur = ws_in;
+		if (k_mid) {
+			uint4 *dst = k_hi ? ws_mid : (uint4 *)data;
+			k_expand_outer<<<std::min<uint32_t>(1u << k_mid, (uint32_t)ctx->n_sms), 1024, LUT_BYTES + 2048 + (16u << l1), ctx->stream>>>(cur, 1u << l1, ws_t1, 1u << k_mid, dst);
+			B200_LAUNCH_CHECK(ctx);
+			cur = dst;
+		}
+		if (k_hi) {
+			k_expand_outer<<<std::min<uint32_t>(1u << k_hi, (uint32_t)ctx->n_sms), 1024, LUT_BYTES + 2048 + (16u << l2), ctx->stream>>>(cur, 1u << l2, ws_t2, 1u << k_hi, (uint4 *)data);
+			B200_LAUNCH_CHECK(ctx);
+		}
+		k_small = a1 + k_mid + k_hi;  // the rounds done so far; anything beyond 2^22 elements continues with the fused doubling rounds
+	} else if (log_n <= EXP_SMALL_LOG) k_small = std::min(k, EXP_SMALL_LOG - log_n);  // rounds that fit one CTA's shared memory
+	if (k_small && !(log_n <= EXP_SMALL_LOG && ctx->tune_expand_outer)) {
 		std::vector<uint4> h(k_small);
 		for (uint32_t i = 0; i < k_small; i++) h[i] = to_u4(coords + 2 * i);
 		void *dc;

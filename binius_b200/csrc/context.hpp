@@ -82,6 +82,7 @@ struct b200_ctx {
 	// host-mapped mailbox of the persistent sumcheck tail (b200_sumcheck_tail_*), allocated on first use
 	uint8_t *h_tail_mb = nullptr, *d_tail_mb = nullptr;
 	size_t tail_mb_bytes = 0;
+	uint8_t *d_expand_ws = nullptr;  // tensor expansion: in' and T of the outer-product plan (2 x 2^12 elements)
 	uint8_t *d_tail_ws = nullptr;  // device workspace of the grid variant (accumulators, barrier, challenge relay)
 	bool tail_active = false;
 	std::vector<void *> deferred_free;  // device releases that arrived while a tail was running
@@ -93,6 +94,7 @@ struct b200_ctx {
 	int tune_fold = 2;             // 2 TMA-staged K64, 1 K64, 0 LUT128
 	int tune_round_evals_tc = 1;   // 1 tensor-core plans, 0 per-lane kernels, 2 materialised values only
 	int tune_uni_generic = 0;      // 1 forces the generic univariate-skip kernel
+	int tune_expand_outer = 1;     // 0: tensor expansion by the doubling chain only (k_expand_small + k_expand_k64 rounds)
 	int tune_uni_linear = 1;       // 0: linear monomials of the univariate-skip round stay in k_uni_b8 (A/B, tests)
 	int tune_tail_grid = 1;        // 0: the persistent sumcheck kernel always runs on one CTA
 	int tune_tail_trace = 0;       // 1: b200_sumcheck_tail_finish prints CTA 0's per-round time stamps (debugging aid)

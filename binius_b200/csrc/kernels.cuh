@@ -191,6 +191,94 @@ __global__ void __launch_bounds__(1024) k_expand_small(uint4 *__restrict__ data,
 	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) data[i] = buf[i];
 }
 
+// Tensor expansion as an OUTER PRODUCT.  After k rounds  out[j * N + i] = in[i] * T[j]  with T = the expansion of [1]
+// by the same coordinates (the rounds only ever multiply, and multiplication is commutative), so the doubling chain --
+// k dependent launches whose small links are pure latency -- collapses to two independent short chains and one wide
+// kernel:
+//   k_expand_pair : up to three SMALL expansions, one CTA per problem: in' = the data brought to 2^6 elements and the
+//                   tables T_mid (<= 2^6 entries) and T_hi (<= 2^10) of the following coordinates, by general per-lane
+//                   products.  Small on purpose: one SM does ~10^8 general products per second, 4096 of them are 35 us.
+//   k_expand_outer: out[j * N + i] = in[i] * T[j]: a CTA takes table entries j, builds the K64 table of T[j] (~3 us)
+//                   and streams the N <= 4096 staged elements through it.  Used twice: in'' = in' x T_mid (2^12
+//                   elements), then out = in'' x T_hi.
+// reference: compute/src/layer.rs:269-296 (definition), math/src/tensor_prod_eq_ind.rs:35-77
+struct ExpandPairArgs {
+	const uint4 *src[3];   // 2^log_n[p] input elements (null: the single element 1)
+	uint4 *dst[3];         // 2^(log_n[p] + k[p]) outputs
+	uint32_t log_n[3], k[3];
+	uint4 coords[3][EXP_SMALL_LOG];
+};
+// T = the expansion of [1] by k coordinates is the tensor product of the k two-element tables [1 + c_r, c_r]; adjacent
+// tables are merged pairwise (new[hi * |lo| + lo] = lo_tab[lo] * hi_tab[hi]), all merges of a level in parallel:
+// ceil(log2 k) dependent product rounds instead of k (a per-lane product of one warp is ~2 us of latency, and with
+// <= 4096 elements latency is all there is).  A last round multiplies by the input elements when there are any.
+// grid = number of problems (1 or 2), block = 1024, dyn smem = field tables + 2 x 16 * 2^(log_n + k) (ping-pong)
+__global__ void __launch_bounds__(1024) k_expand_pair(const uint8_t *__restrict__ g_tables, const __grid_constant__ ExpandPairArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	const uint32_t p = blockIdx.x, log_n = A.log_n[p], k = A.k[p], n0 = 1u << log_n;
+	const uint32_t cap = 1u << (log_n + k);
+	uint4 *cur = reinterpret_cast<uint4 *>(smem + ((FIELD_TABLE_BYTES + 127) & ~127u)), *nxt = cur + (cap > 2 * k ? cap : 2 * k);
+	// level 0: k tables of one coordinate each, table t at [2t, 2t + 2)
+	for (uint32_t e = threadIdx.x; e < 2 * k; e += blockDim.x) {
+		const uint4 c = A.coords[p][e >> 1];
+		cur[e] = (e & 1) ? c : make_uint4(c.x ^ 1u, c.y, c.z, c.w);
+	}
+	__syncthreads();
+	// every table but the last covers `w` coordinates; the last covers `w_last` (1 <= w_last <= w)
+	uint32_t n_tab = k, w = 1, w_last = 1;
+	while (n_tab > 1) {
+		const uint32_t n_new = (n_tab + 1) / 2, S = 1u << w, S2 = S * S;
+		const bool odd = n_tab & 1;  // the last table has no partner: copied
+		const uint32_t last_bits = odd ? w_last : w + w_last, last_off_new = (n_new - 1) * S2;
+		const uint32_t total = last_off_new + (1u << last_bits);
+		for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+			const uint32_t t = e < last_off_new ? e / S2 : n_new - 1, idx = e - t * S2;
+			const uint32_t lo_off = 2 * t * S;
+			if (t == n_new - 1 && odd) nxt[e] = cur[lo_off + idx];
+			else nxt[e] = f_mul128(T, cur[lo_off + S + (idx >> w)], cur[lo_off + (idx & (S - 1))]);  // the slowly varying operand FIRST (field.cuh)
+		}
+		__syncthreads();
+		uint4 *tmp = cur;
+		cur = nxt, nxt = tmp;
+		w_last = last_bits, w *= 2, n_tab = n_new;
+	}
+	// cur = T (2^k entries; the single entry 1 when k = 0)
+	uint4 *dst = A.dst[p];
+	if (A.src[p]) {
+		// the input may be the head of the output (in-place expansion): stage it before anything is written
+		for (uint32_t e = threadIdx.x; e < n0; e += blockDim.x) nxt[e] = A.src[p][e];
+		__syncthreads();
+		// first operand = the one that takes fewer distinct values inside a warp (field.cuh): the input element while
+		// n0 <= 4 (a single input element is the same in EVERY lane), the table entry from n0 = 8 on
+		const bool x_first = n0 <= 4;
+		for (uint32_t e = threadIdx.x; e < cap; e += blockDim.x) {
+			const uint4 x = nxt[e & (n0 - 1)];
+			dst[e] = !k ? x : x_first ? f_mul128(T, x, cur[e >> log_n]) : f_mul128(T, cur[e >> log_n], x);
+		}
+	} else {
+		for (uint32_t e = threadIdx.x; e < cap; e += blockDim.x) dst[e] = k ? cur[e] : u4_one();
+	}
+}
+// grid <= n_j, block = 1024, dyn smem = LUT_BYTES + 2048 + 16 * n
+__global__ void __launch_bounds__(1024, 1) k_expand_outer(const uint4 *__restrict__ in, uint32_t n, const uint4 *__restrict__ tab, uint32_t n_j,
+																  uint4 *__restrict__ out) {
+	extern __shared__ __align__(256) uint8_t smem[];
+	uint2 *stage = reinterpret_cast<uint2 *>(smem + LUT_BYTES);
+	uint4 *in_s = reinterpret_cast<uint4 *>(smem + LUT_BYTES + 2048);
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) in_s[i] = __ldg(in + i);
+	for (uint32_t j = blockIdx.x; j < n_j; j += gridDim.x) {
+		k64_build_mul(smem, stage, __ldg(tab + j));  // (its first barrier also orders the staging loop / the previous j's reads)
+		const K64Lane L = k64_lane_init(smem);
+		uint4 *o = out + (uint64_t)j * n;
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = k64_apply(L, in_s[i]);
+		__syncthreads();
+	}
+}
+// (A variant with two CTAs of 512 threads per SM and the input read through L1 -- so that one CTA's table build overlaps
+// the other's products -- measured the same 48 us for 1024 tables x 4096 elements: the stage is bound by issue slots,
+// ~6.8 us per table and SM for the build plus 4096 K64 products, not by the latency of the build.)
+
 // ------------------------------------------------------------------------------------------------
 __global__ void k_fill(uint4 *__restrict__ dst, uint64_t n, uint4 v) {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = v;

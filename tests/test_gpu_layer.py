@@ -81,7 +81,8 @@ def test_extrapolate_line_unaligned_subslices(hal, oracle):
         assert _same(hal.to_host(cur), ref)
 
 
-@pytest.mark.parametrize("log_n,k", [(0, 0), (0, 1), (0, 5), (2, 3), (0, 11), (3, 10), (0, 14), (12, 2), (5, 12)])
+@pytest.mark.parametrize("log_n,k", [(0, 0), (0, 1), (0, 5), (2, 3), (0, 11), (3, 10), (0, 14), (12, 2), (5, 12), (0, 12), (0, 13), (12, 0), (12, 1),
+                                     (13, 3), (7, 15), (0, 22), (3, 21), (0, 25)])
 def test_tensor_expand(hal, oracle, log_n, k):
     # compute_test_utils layer.rs:30-71 (zero-filled tail, compare with tensor_prod_eq_ind)
     import random
@@ -93,6 +94,28 @@ def test_tensor_expand(hal, oracle, log_n, k):
     d = hal.to_device(data)
     hal.execute(lambda ex: (ex.tensor_expand(log_n, coords, d), [])[1])
     assert _same(hal.to_host(d), oracle.tensor_expand(data, log_n, coords))
+
+
+def test_tensor_expand_plans_agree(hal, oracle):
+    """the outer-product plan (k_expand_pair + k_expand_outer) against the doubling chain it replaces, incl. zero and one
+    coordinates, at the size bench.py times (k = 22)"""
+    import random
+
+    rng = random.Random(2222)
+    for log_n, k in [(0, 17), (0, 22), (5, 18), (12, 9)]:
+        coords = [rng.choice([rng.getrandbits(128)] * 6 + [0, 1]) for _ in range(k)]
+        data = np.zeros((1 << (log_n + k), 2), np.uint64)
+        data[: 1 << log_n] = oracle.rand_b128(50 + k, 1 << log_n)
+        got = []
+        for outer in (1, 0):
+            hal.set_tuning("expand_outer", outer)
+            try:
+                d = hal.to_device(data)
+                hal.execute(lambda ex: (ex.tensor_expand(log_n, coords, d), [])[1])
+                got.append(hal.to_host(d))
+            finally:
+                hal.set_tuning("expand_outer", 1)
+        assert _same(got[0], got[1]), (log_n, k)
 
 
 def test_tensor_expand_overwrites_and_validates(hal, oracle):
