@@ -563,6 +563,7 @@ int32_t b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int32_t value) {
 	else if (!strcmp(key, "uni_linear")) ctx->tune_uni_linear = value;
 	else if (!strcmp(key, "expand_outer")) ctx->tune_expand_outer = value;
 	else if (!strcmp(key, "tail_grid")) ctx->tune_tail_grid = value;
+	else if (!strcmp(key, "tail_resident")) ctx->tune_tail_resident = value;
 	else if (!strcmp(key, "tail_trace")) ctx->tune_tail_trace = value;
 	else return fail(ctx, B200_ERR_INPUT_VALIDATION, "unknown tuning key %s", key);
 	return B200_OK;
@@ -1815,9 +1816,18 @@ int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_
 		smem_bytes += 16 * (size_t)n_points + 8 * (size_t)m + 4 * (size_t)n_points;
 		smem_bytes = (smem_bytes + 127) & ~(size_t)127;
 	}
+	GA.res_half = 0;
 	if (smem_bytes + LUT_BYTES + 1536 <= TG_SMEM_MAX) {
 		GA.off_k64 = (uint32_t)smem_bytes;
 		smem_bytes += LUT_BYTES + 1536;
+		// the small rounds run on CTA 0 from shared-memory copies held in the same region: (2 m + 1) * half elements
+		if (GA.off_hdr && ctx->tune_tail_resident)
+			// (128 pairs: with 256 one SM alone is slower than eight SMs plus two barriers -- 17.6 us against 11.6 for config #3)
+			for (uint32_t h = 128; h >= 1; h >>= 1)
+				if ((2 * (uint64_t)m + 1) * h * 16 <= LUT_BYTES + 1536) {
+					GA.res_half = h;
+					break;
+				}
 	}
 	const uint8_t *tables = ctx->d_tables;
 	void *kargs[] = {(void *)&tables, (void *)&GA};

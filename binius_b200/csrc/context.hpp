@@ -97,6 +97,7 @@ struct b200_ctx {
 	int tune_expand_outer = 1;     // 0: tensor expansion by the doubling chain only (k_expand_small + k_expand_k64 rounds)
 	int tune_uni_linear = 1;       // 0: linear monomials of the univariate-skip round stay in k_uni_b8 (A/B, tests)
 	int tune_tail_grid = 1;        // 0: the persistent sumcheck kernel always runs on one CTA
+	int tune_tail_resident = 1;    // 0: the small rounds of the persistent sumcheck kernel stay in device memory
 	int tune_tail_trace = 0;       // 1: b200_sumcheck_tail_finish prints CTA 0's per-round time stamps (debugging aid)
 };
 

@@ -56,6 +56,9 @@ struct TailGridArgs {
 	uint32_t off_acc, off_ex, off_steps;  // shared-memory layout (bytes)
 	uint32_t off_hdr;   // multilinear pointers [m], point codes [n_points], points [n_points] (0: read from global memory)
 	uint32_t off_k64;   // 64 KiB + 1.5 KiB for the table of x -> x * challenge (linmap.cuh K64 engine), 0: none
+	uint32_t res_half;  // from the round with this many (or fewer) index pairs on, CTA 0 keeps the multilinears and the
+						// eq-indicator in shared memory (in the K64 region, which only the large rounds use) and runs
+						// alone: no barriers, no L2 latency in the dependent chain of the small rounds.  0: never
 };
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
@@ -78,7 +81,8 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
 	return v;
 }
 
-// C^{(p)}(P(i)) for full-length multilinears, operands through L2
+// C^{(p)}(P(i)) for full-length multilinears, operands through L2 (RES: from the shared-memory copies)
+template <bool RES>
 __device__ __forceinline__ uint4 tg_eval_point(const FieldTables &T, uint4 *const *mls, uint64_t half, const DevExpr &E, uint32_t code, uint4 z, uint64_t i) {
 	uint4 tmp[MAX_EXPR_STEPS];
 	for (uint32_t s = 0; s < E.n_steps; s++) {
@@ -91,10 +95,10 @@ __device__ __forceinline__ uint4 tg_eval_point(const FieldTables &T, uint4 *cons
 		case 3: v = make_uint4((uint32_t)st.c_lo, (uint32_t)(st.c_lo >> 32), (uint32_t)st.c_hi, (uint32_t)(st.c_hi >> 32)); break;
 		default: {
 			const uint4 *m = mls[st.l];
-			const uint4 hi = __ldcg(m + half + i);
+			const uint4 hi = RES ? m[half + i] : __ldcg(m + half + i);
 			if (code == 1) v = hi;
 			else {
-				const uint4 lo = __ldcg(m + i);
+				const uint4 lo = RES ? m[i] : __ldcg(m + i);
 				const uint4 d = hi ^ lo;
 				v = code == 2 ? d : (lo ^ f_mul128(T, z, d));
 			}
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_sumcheck_tail_grid(const uint
 	__shared__ uint32_t abort_s;
 	const TailArgs &A = GA.t;
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-	const uint32_t G = gridDim.x, k = blockIdx.x;
+	const uint32_t k = blockIdx.x;
 	const uint32_t n_vals = A.n_comp * A.n_points;
 	uint32_t bar_target = 0;
 	if (tid == 0) abort_s = 0;
@@ -176,8 +180,27 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_sumcheck_tail_grid(const uint
 	};
 	const bool trace = A.mb_trace != nullptr && k == 0 && tid == 0;
 
+	bool res = false;      // CTA 0 runs alone on its shared-memory copies
+	uint4 *eq = A.eq_ind;
+	uint32_t G = gridDim.x;
 	for (uint32_t r = 0; r < A.n_vars; r++) {
 		const uint64_t half = 1ull << (A.n_vars - 1 - r);
+		if (!res && GA.res_half && half <= GA.res_half) {
+			// every fold of the previous round is visible (that round ended with a grid barrier: half < 32 G)
+			if (k != 0) return;
+			uint4 *base = reinterpret_cast<uint4 *>(smem + GA.off_k64);
+			uint4 **ml_s = const_cast<uint4 **>(mls);  // the pointer table in the shared-memory header (GA.off_hdr != 0 when res_half != 0)
+			for (uint32_t t = warp; t < A.m; t += nw) {
+				const uint4 *src = mls[t];
+				for (uint32_t i = lane; i < 2 * half; i += 32) base[(uint64_t)t * 2 * half + i] = __ldcg(src + i);
+			}
+			for (uint32_t i = tid; i < half; i += blockDim.x) base[(uint64_t)A.m * 2 * half + i] = __ldcg(A.eq_ind + i);
+			__syncthreads();
+			for (uint32_t t = tid; t < A.m; t += blockDim.x) ml_s[t] = base + (uint64_t)t * 2 * half;
+			eq = base + (uint64_t)A.m * 2 * half;
+			res = true, G = 1;
+			__syncthreads();
+		}
 		const uint32_t n_chunks = (uint32_t)((half + 31) >> 5);
 		const uint32_t P = n_chunks < G ? n_chunks : G;  // CTAs that take part in this round (k < P)
 		const uint32_t my_chunks = (n_chunks - k + G - 1) / G;  // chunks k, k + G, ...
@@ -198,8 +221,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_sumcheck_tail_grid(const uint
 			const uint64_t i = 32ull * (k + (uint64_t)G * lc) + lane;
 			uint4 v = u4_zero();
 			if (i < half) {
-				v = tg_eval_point(T, mls, half, X, code, points[p], i);
-				v = f_mul128(T, v, __ldcg(A.eq_ind + i));
+				v = res ? tg_eval_point<true>(T, mls, half, X, code, points[p], i) : tg_eval_point<false>(T, mls, half, X, code, points[p], i);
+				v = f_mul128(T, v, res ? eq[i] : __ldcg(eq + i));
 			}
 			v = warp_xor(v);
 			if (lane == 0) {
@@ -279,7 +302,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_sumcheck_tail_grid(const uint
 		// ---- fold the multilinears, halve the eq-indicator (own chunks only)
 		// (two or more items per warp pay for the ~2 us build of the challenge's K64 table: 24 conflict-free LDS.64 per
 		// product instead of the 121 byte lookups of the general multiply)
-		if (GA.off_k64 && A.m * my_chunks >= 2 * nw) {
+		if (GA.off_k64 && !res && A.m * my_chunks >= 2 * nw) {
 			k64_build_mul(smem + GA.off_k64, reinterpret_cast<uint2 *>(smem + GA.off_k64 + LUT_BYTES), z);
 			const K64Lane L = k64_lane_init(smem + GA.off_k64);
 			for (uint32_t q = warp; q < A.m * my_chunks; q += nw) {
@@ -297,7 +320,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_sumcheck_tail_grid(const uint
 				const uint64_t i = 32ull * (k + (uint64_t)G * lc) + lane;
 				if (i < half) {
 					uint4 *ml = mls[t];
-					const uint4 lo = __ldcg(ml + i), hi = __ldcg(ml + half + i);
+					const uint4 lo = res ? ml[i] : __ldcg(ml + i), hi = res ? ml[half + i] : __ldcg(ml + half + i);
 					ml[i] = lo ^ f_mul128(T, z, lo ^ hi);  // warp-uniform operand first (field.cuh)
 				}
 			}
@@ -305,9 +328,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) k_sumcheck_tail_grid(const uint
 		const uint64_t hn = half >> 1;
 		for (uint32_t lc = warp; lc < my_chunks; lc += nw) {
 			const uint64_t i = 32ull * (k + (uint64_t)G * lc) + lane;
-			if (i < hn) A.eq_ind[i] = __ldcg(A.eq_ind + i) ^ __ldcg(A.eq_ind + hn + i);
+			if (i < hn) eq[i] = res ? eq[i] ^ eq[hn + i] : __ldcg(eq + i) ^ __ldcg(eq + hn + i);
 		}
-		if (r + 1 == A.n_vars) break;
+		if (r + 1 == A.n_vars) {
+			if (res) {  // the final folds go back to device memory (nothing in between is observable: the context refuses calls)
+				__syncthreads();
+				for (uint32_t t = tid; t < A.m; t += blockDim.x) A.mls[t][0] = mls[t][0];
+				if (tid == 0) A.eq_ind[0] = eq[0];
+			}
+			break;
+		}
 		// next round pairs i with i + hn: same owner iff hn is a multiple of 32 G
 		const bool local = hn >= 32ull * G;
 		if (P > 1 && !local) {
