@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -159,6 +160,7 @@ class B200Exec {
 
 class B200Layer {
 	b200_ctx *ctx_ = nullptr;
+	std::recursive_mutex exec_mu_;
 	std::vector<DevSlice> scratch_;
 	friend class B200Exec;
 	friend class B200KernelExec;
@@ -212,7 +214,10 @@ class B200Layer {
 		uint64_t w[2] = {v.lo, v.hi};
 		check(b200_fill(ctx_, s.ptr, s.n, w));
 	}
+	// an execute is a scope over the context's result slots: executes from several host threads take turns (every other
+	// call is serialised by the context's own lock inside the library)
 	std::vector<F128> execute(const std::function<std::vector<OpValue>(B200Exec &)> &f) {
+		std::lock_guard<std::recursive_mutex> scope(exec_mu_);
 		check(b200_results_reset(ctx_));
 		B200Exec ex(*this);
 		std::vector<OpValue> vals = f(ex);

@@ -554,6 +554,12 @@ class B200Layer:
         self._owned = []
         self._scratch = {}
         self._scratch_used = {}
+        # `execute` is a scope over the context's result slots (reset at its start, fetched at its end): executes issued
+        # from several host threads on one layer (`&self` in the reference, layer.rs:90-99) take turns; every other call
+        # is serialised by the context's own lock inside the library
+        import threading
+
+        self._exec_lock = threading.RLock()
 
     def _check(self, rc: int):
         if rc != 0:
@@ -605,17 +611,18 @@ class B200Layer:
         return ExprEval(self, expr)
 
     def execute(self, f: Callable[[B200Executor], List[OpValue]]) -> List[int]:
-        self._check(self._lib.b200_results_reset(self._ctx))
-        ex = B200Executor(self)
-        try:
-            vals = list(f(ex) or [])
-            n = len(vals)
-            slots = (C.c_uint32 * max(n, 1))(*[v.slot for v in vals])
-            out = (C.c_uint64 * max(2 * n, 2))()
-            self._check(self._lib.b200_results_fetch(self._ctx, slots, n, out))
-        finally:
-            self._scratch_release()
-        return [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(n)]
+        with self._exec_lock:
+            self._check(self._lib.b200_results_reset(self._ctx))
+            ex = B200Executor(self)
+            try:
+                vals = list(f(ex) or [])
+                n = len(vals)
+                slots = (C.c_uint32 * max(n, 1))(*[v.slot for v in vals])
+                out = (C.c_uint64 * max(2 * n, 2))()
+                self._check(self._lib.b200_results_fetch(self._ctx, slots, n, out))
+            finally:
+                self._scratch_release()
+            return [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(n)]
 
     def fill(self, slice: DevSlice, value: int):
         self._check(self._lib.b200_fill(self._ctx, slice.ptr, slice.len(), _u64x2(value)))

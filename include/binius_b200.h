@@ -27,7 +27,11 @@
  *     of an open kernel scope are lowered at b200_kernel_scope_end.
  *   - A context may be shared by several host threads (the trait methods take `&self` and `join`/`map`
  *     closures run on rayon threads, layer.rs:115-131): every entry point takes the context's lock and
- *     makes its device current for the call; a kernel scope holds the lock from begin to end.
+ *     makes its device current for the call; a kernel scope holds the lock from begin to end.  The result
+ *     slots are per context and b200_results_reset starts a new numbering, so an `execute` (reset .. fetch) is a
+ *     scope the HOST side must not interleave between threads: the shim holds a mutex per layer around it, as
+ *     binius_b200/layer.py and host/compute_layer.hpp do (tests/test_gpu_layer.py::
+ *     test_one_layer_from_several_host_threads).
  *   - There is no CPU fallback: every entry point fails with B200_ERR_DEVICE when no sm_100 device
  *     is usable.
  */

@@ -596,3 +596,38 @@ def test_kernel_scope_general_programs(hal, oracle, n_vars):
     e = oracle.sum_composition_evals([l0, host[0], host[1]], exprs[0].steps, coeffs[2], e)
     assert got2 == [e]
     assert np.array_equal(hal.to_host(out), l0 ^ host[2])
+
+
+def test_one_layer_from_several_host_threads(hal, oracle):
+    """ComputeLayer is used as `&self` from several host threads (rayon join / map, layer.rs:115-131): the context
+    serialises its entry points and an `execute` is a scope over the result slots, so concurrent executes on ONE layer
+    take turns and every thread gets its own values (ctypes releases the GIL inside the library calls)."""
+    import threading
+
+    import binius_b200
+
+    n = 1 << 14
+    jobs = []
+    for t in range(4):
+        a, b = oracle.rand_b128(9100 + t, n), oracle.rand_b128(9200 + t, n)
+        z = 0x1F2E3D4C5B6A7988 + t
+        jobs.append((a, b, z, hal.to_device(a), hal.to_device(b), hal.to_device(a), hal.to_device(b)))
+    errors = []
+
+    def work(t):
+        try:
+            a, b, z, da, db, fa, fb = jobs[t]
+            for it in range(10):
+                got = hal.execute(lambda ex: [ex.inner_product(binius_b200.SubfieldSlice(da, 7), db)])
+                assert got == [oracle.inner_product(a, 7, b)], (t, it)
+            hal.execute(lambda ex: (ex.extrapolate_line(fa, fb, z), [])[1])
+            assert _same(hal.to_host(fa), oracle.extrapolate_line(a, b, z)), t
+        except Exception as e:  # surfaced in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
