@@ -215,8 +215,12 @@ def cpu_univariate_baseline(rows_log2=21, columns=153, compositions=75, skip=7):
     words = 1 << (rows_log2 - 7)
     cols = [orc.rand_b128(j, words) for j in range(columns)]
     m = columns
-    comps = [[("var", (2 * c) % m), ("var", (2 * c + 1) % m), ("mul", 0, 1), ("var", (2 * c + 5) % m), ("add", 2, 3),
-              ("var", (2 * c + 11) % m), ("add", 4, 5)] for c in range(compositions)]
+    comps = []
+    for c in range(compositions):  # the same chi constraints as the GPU arm: out + b0 + b1 * b2 + b2
+        batch, xy = c // 25, c % 25
+        x, y = xy % 5, xy // 5
+        b0, b1, b2 = (75 + 25 * batch + (x + k) % 5 + 5 * y for k in range(3))
+        comps.append([("var", c % m), ("var", b0 % m), ("add", 0, 1), ("var", b1 % m), ("var", b2 % m), ("mul", 3, 4), ("add", 2, 5), ("add", 6, 4)])
     eq = orc.rand_b128(999, 1 << (rows_log2 - skip))
     cores = len(os.sched_getaffinity(0))
     best = min(orc.cpu_univariate_b1(cols, rows_log2, skip, eq, comps, 1 << skip, cores)[1] for _ in range(2))
@@ -255,7 +259,8 @@ def run_reference(args, rank, world):
     base = None
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        base = cpu_fold_baseline(args.log_coeffs, budget_s=1.5)
+        # a step = a bounded sample of the workload, sized so that the whole run ends within a few minutes at any K
+        base = cpu_fold_baseline(args.log_coeffs, budget_s=min(1.5, 120.0 / max(args.warmup + args.steps, 1)))
         if s >= args.warmup:
             ms.append((time.perf_counter() - t0) * 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -656,7 +661,14 @@ def main():
             arena_u = hal.dev_alloc(mu * wu)
             hal.fill(arena_u, 0x0123456789ABCDEF0F1E2D3C4B5A6978)
             mls_u = [TransparentMultilinear(arena_u.slice(j * wu, (j + 1) * wu), 0, nvu) for j in range(mu)]
-            comps_u = [A.var((2 * c) % mu) * A.var((2 * c + 1) % mu) + A.var((2 * c + 5) % mu) + A.var((2 * c + 11) % mu) for c in range(ncu)]
+            # keccak's chi constraints out - (b0 + (b1 - 1) * b2) with their column structure (m3/src/gadgets/hash/keccak/
+            # stacked.rs:318-366: 75 state_out columns, 75 b columns in three batches, round constant, 2 spare)
+            comps_u = []
+            for c in range(ncu):
+                batch, xy = c // 25, c % 25
+                x, y = xy % 5, xy // 5
+                b0, b1, b2 = (A.var(75 + 25 * batch + (x + k) % 5 + 5 * y) for k in range(3))
+                comps_u.append(A.var(c) - (b0 + (b1 - A.one()) * b2))
             _r = _random.Random(7)
             ch_u = [_r.getrandbits(128) for _ in range(nvu - sku)]
             be_u = B200Backend(hal)

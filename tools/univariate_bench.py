@@ -1,5 +1,5 @@
 """Timing of the zerocheck univariate-skip round (b200_zerocheck_univariate_evals) at the keccak shape
-(153 B1 columns, 75 degree-2 chi constraints a*b + c + d, skip_rounds = 7 (constraint_system/verify.rs:271-294),
+(153 B1 columns, 75 degree-2 chi constraints, skip_rounds = 7 (constraint_system/verify.rs:271-294),
 max_domain_size = 256) on synthetic columns.  `python tools/univariate_bench.py [n_vars] [m] [n_comp]`;
 n_vars = 27 is the 2^18-permutation trace (16 MiB per column).  Run on a B200."""
 import ctypes as C
@@ -25,9 +25,15 @@ hal.fill(arena, 0x0123456789ABCDEF0F1E2D3C4B5A6978)
 rng = random.Random(1)  # (the kernel's work does not depend on the column values)
 mls = [TransparentMultilinear(arena.slice(j * words, (j + 1) * words), 0, n_vars) for j in range(m)]
 comps = []
-for c in range(n_comp):
-    a, b, d, e = (A.var((2 * c + o) % m) for o in (0, 1, 5, 11))
-    comps.append(a * b + d + e)
+for c in range(n_comp):  # keccak chi constraints out - (b0 + (b1 - 1) * b2) (stacked.rs:318-366) when the shape allows
+    if m >= 150 and n_comp <= 75:
+        batch, xy = c // 25, c % 25
+        x, y = xy % 5, xy // 5
+        b0, b1, b2 = (A.var(75 + 25 * batch + (x + k) % 5 + 5 * y) for k in range(3))
+        comps.append(A.var(c) - (b0 + (b1 - A.one()) * b2))
+    else:
+        a, b, d, e = (A.var((2 * c + o) % m) for o in (0, 1, 5, 11))
+        comps.append(a * b + d + e)
 ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
 for rep in range(3):
     hal.sync()
