@@ -745,8 +745,48 @@ def main():
                        "timed": {"n_vars": n_t, "multilinears": m_s, "ms": sh_ms, "rounds_per_s": n_t / (sh_ms * 1e-3),
                                  "coeffs_per_s": m_s * ((2 << n_t) - 2) / (sh_ms * 1e-3)},
                        "collective": "all_gather of 2 x B128 per round + one final gather (NCCL); no data-plane exchange"}
+            # the eq-ind (zerocheck) rounds on the same partition: u32_add compositions (BASELINE config #3's), every round
+            # checked against the unsharded oracle at n = 14, then config #3's own size (n = 18 after the skipped rounds)
+            from binius_b200 import ArithCircuit as _A
+            from binius_b200.hal import B200Backend as _Backend
+
+            xa, ya, ci, co, zo = (_A.var(i) for i in range(5))
+            comps_e = [(xa + ci) * (ya + ci) + ci - co, xa + ya + ci - zo]
+            n_e = 14
+            mls_e = [orc_chk.rand_b128(300 + t, 1 << n_e) for t in range(5)]
+            eq_ch = [rs_.getrandbits(128) for _ in range(n_e - 1)]
+            ch_e = [rs_.getrandbits(128) for _ in range(n_e)]
+            be_s = _Backend(hal)
+            sce = sharding.ShardedEqIndSumcheck(be_s, mls_e, n_e, comps_e, eq_ch, (), world, rank, dist, comm_device=f"cuda:{local_rank}")
+            cur = [x.copy() for x in mls_e]
+            eqo = orc_chk.tensor_expand(orc_chk.to_arr([1] + [0] * ((1 << (n_e - 1)) - 1)), 0, eq_ch)
+            exact_e = True
+            for r in range(n_e):
+                vals = orc_chk.sumcheck_round_evals(1, cur, [len(x) for x in cur], [0] * 5, n_e - r, eqo, [list(c.steps) for c in comps_e],
+                                                    [list(c.leading_term().steps) for c in comps_e], [1, 2], [0, 0])
+                exact_e = exact_e and sce.round_evals() == [vals[0], vals[1][:1]]
+                sce.fold(ch_e[r])
+                cur = [orc_chk.fold_left_lerp_inplace(x, len(x), 0, n_e - r, ch_e[r]) for x in cur]
+                eqo = orc_chk.fold_partial_eq_ind(eqo) if len(eqo) > 1 else eqo
+            exact_e = exact_e and sce.finish() == [orc_chk.to_ints(x)[0] for x in cur]
+            n_te = 18
+            big_e = [np.ascontiguousarray(pinned[(t << n_te) % n_in: (t << n_te) % n_in + (1 << n_te)]) for t in range(5)]
+            eq_t = [rs_.getrandbits(128) for _ in range(n_te - 1)]
+            sce = sharding.ShardedEqIndSumcheck(be_s, big_e, n_te, comps_e, eq_t, (), world, rank, dist, comm_device=f"cuda:{local_rank}")
+            barrier()
+            ts0 = time.perf_counter()
+            for r in range(n_te):
+                sce.round_evals()
+                sce.fold(ch_e[r % n_e])
+            barrier()
+            she_ms = (time.perf_counter() - ts0) * 1e3
+            t_ex = torch.tensor([1 if exact_e else 0], device="cuda")
+            dist.all_reduce(t_ex, op=dist.ReduceOp.MIN)
+            sharded["eq_ind"] = {"bit_exact": bool(t_ex.item()), "checked": f"{n_e} rounds of the u32_add zerocheck vs the unsharded oracle on every rank",
+                                 "timed": {"n_vars": n_te, "multilinears": 5, "compositions": 2, "ms": she_ms, "rounds_per_s": n_te / (she_ms * 1e-3)},
+                                 "collective": "all_gather of 3 x B128 per round + one final gather (NCCL); rank g weights its share by eq(bits(g); r_low)"}
         except Exception as e:
-            sharded = {"error": repr(e)}
+            sharded = dict(sharded or {}, error=repr(e))
 
     # ---- keccak prover sharded over the ranks (BASELINE config #5: n_permutations = 2^22 over 8 GPUs):
     #      the low-variable partition gives every rank 1/N of the rows of every column, every phase of the replay runs

@@ -126,6 +126,152 @@ class ShardedBivariateSumcheck:
         return [v[0] for v in self.tail]
 
 
+def _eval_circuit(circuit, q: Sequence[int]) -> int:
+    """ArithCircuit (math/src/arith_expr.rs:367-383) on host scalars: only the replicated tail rounds of a
+    sharded sumcheck use it (W / 2 hypercube points per round)."""
+    tmp: List[int] = []
+    for st in circuit.steps:
+        k = st[0]
+        if k == "add":
+            v = tmp[st[1]] ^ tmp[st[2]]
+        elif k == "mul":
+            v = hostfield.mul(tmp[st[1]], tmp[st[2]])
+        elif k == "pow":
+            v = hostfield.pow_(tmp[st[1]], st[2])
+        elif k == "const":
+            v = st[1]
+        else:
+            v = q[st[1]]
+        tmp.append(v)
+    return tmp[-1] if tmp else 0
+
+
+class ShardedEqIndSumcheck:
+    """The data plane of the zerocheck / eq-ind multilinear rounds (reference EqIndSumcheckProver,
+    core/src/protocols/sumcheck/prove/eq_ind.rs:300-470: `execute` -> backend.sumcheck_compute_round_evals with the
+    evaluator of :646-731, `fold` -> sumcheck_fold_multilinears + fold_partial_eq_ind, prove/common.rs:13-73), HighToLow,
+    sharded over W ranks by the LOW log2(W) variables like ShardedBivariateSumcheck.
+
+    The eq-indicator is a tensor product, E[i] = eq(low bits of i; r_low) * E_high[high bits of i], and the round
+    values are linear in E: rank g runs the ordinary rounds of its sub-instance (its elements i = g mod W, weighted by
+    the expansion of the HIGH challenges only) and scales its partial values by the scalar eq(bits(g); r_low).  Per
+    round one all-gather of n_compositions * n_points B128 values; no data-plane exchange.  When one element per rank is
+    left the W survivors are gathered and the last log2(W) rounds run replicated on host scalars.
+
+    `backend` is ComputationBackend-shaped (`B200Backend` in production); `eq_challenges` are the n_vars - 1 challenges
+    whose expansion `Evaluator::eq_ind_partial_eval()` holds in round 0 (variables 0 .. n_vars-2; the round variable's
+    own factor is applied by the prover outside the backend, eq_ind.rs:560-640).  Values returned per composition are at
+    the evaluator's points 1 (unless `have_first_round_eval_1s` in round 0), infinity, then `finite_points`."""
+
+    def __init__(self, backend, host_multilinears: Sequence[np.ndarray], n_vars: int, compositions, eq_challenges: Sequence[int],
+                 finite_points: Sequence[int] = (), world: int = 1, rank: int = 0, dist=None, comm_device="cpu",
+                 have_first_round_eval_1s: bool = False):
+        from .hal import EqIndEvaluator, FoldedMultilinear
+
+        assert len(eq_challenges) == max(n_vars - 1, 0)
+        self.backend, self.n_vars, self.compositions = backend, n_vars, list(compositions)
+        self.world, self.rank, self.dist, self.comm_device = world, rank, dist, comm_device
+        self.log_w = world.bit_length() - 1
+        assert 1 << self.log_w == world and self.log_w <= n_vars
+        self.finite_points = list(finite_points)
+        self.first_known = have_first_round_eval_1s
+        self._Evaluator = EqIndEvaluator
+        self.eq_challenges = list(eq_challenges)
+        self.remaining = n_vars
+        self.mls = [FoldedMultilinear(backend._l.to_device(shard_low_vars(m, world, rank))) for m in host_multilinears]
+        self.tail = None
+        lw = self.log_w
+        if n_vars > lw:
+            # variables lw .. n_vars-2 are local; an instance with a single local variable has the empty expansion [1]
+            self.eq = backend.tensor_product_full_query(self.eq_challenges[lw:])
+            self.scale = hostfield.eq_ind_scalar(rank, self.eq_challenges[:lw])
+        else:
+            self._gather()
+
+    def _evaluators(self):
+        first = self.first_known and self.remaining == self.n_vars
+        return [self._Evaluator(c, first) for c in self.compositions]
+
+    def _gather(self):
+        layer = self.backend._l
+        local = np.concatenate([layer.to_host(ml.evals)[:1] for ml in self.mls]) if self.mls else np.zeros((0, 2), np.uint64)
+        allv = gather_elements(local, self.dist, self.comm_device)  # (W, m, 2)
+        self.tail = [[int(allv[g, t, 0]) | (int(allv[g, t, 1]) << 64) for g in range(self.world)] for t in range(len(self.mls))]
+
+    def _tail_round_evals(self) -> List[List[int]]:
+        nv = self.remaining
+        half = 1 << (nv - 1)
+        eq = [hostfield.eq_ind_scalar(i, self.eq_challenges[:nv - 1]) for i in range(half)]
+        out = []
+        for ev in self._evaluators():
+            lead = ev.composition.leading_term()
+            row = []
+            for code in ev.eval_point_indices():
+                acc = 0
+                for i in range(half):
+                    lo = [v[i] for v in self.tail]
+                    hi = [v[half + i] for v in self.tail]
+                    if code == 1:
+                        val = _eval_circuit(ev.composition, hi)
+                    elif code == 2:
+                        val = _eval_circuit(lead, [a ^ b for a, b in zip(lo, hi)])
+                    else:
+                        z = self.finite_points[code - 3]
+                        val = _eval_circuit(ev.composition, [a ^ hostfield.mul(a ^ b, z) for a, b in zip(lo, hi)])
+                    acc ^= hostfield.mul(val, eq[i])
+                row.append(acc)
+            out.append(row)
+        return out
+
+    def round_evals_local(self) -> List[List[int]]:
+        """this rank's share of the round values (already scaled by eq(bits(rank); r_low)): their XOR over the ranks is
+        the round's value"""
+        assert self.tail is None and self.remaining > self.log_w
+        part = self.backend.sumcheck_compute_round_evals(self.remaining - self.log_w, self.mls, self._evaluators(), self.eq,
+                                                         self.finite_points)
+        return [[hostfield.mul(self.scale, v) for v in row] for row in part]
+
+    def round_evals(self) -> List[List[int]]:
+        """RoundEvals of every composition, combined over all ranks"""
+        if self.tail is not None:
+            return self._tail_round_evals()
+        part = self.round_evals_local()
+        flat = [v for row in part for v in row]
+        tot = xor_all_gather(flat, self.dist, self.comm_device) if flat else []
+        out, k = [], 0
+        for row in part:
+            out.append(tot[k:k + len(row)])
+            k += len(row)
+        return out
+
+    def fold_local(self, challenge: int):
+        """fold of this rank's sub-instance (no communication)"""
+        assert self.tail is None and self.remaining > self.log_w
+        nv_local = self.remaining - self.log_w
+        self.backend.sumcheck_fold_multilinears(nv_local, self.mls, challenge)
+        if nv_local > 1:
+            self.eq = self.backend.fold_partial_eq_ind(nv_local - 1, self.eq)
+        self.remaining -= 1
+
+    def fold(self, challenge: int):
+        if self.tail is None:
+            self.fold_local(challenge)
+            if self.remaining == self.log_w:
+                self._gather()
+        else:
+            new = []
+            for vals in self.tail:
+                half = len(vals) // 2
+                new.append([vals[i] ^ hostfield.mul(vals[i] ^ vals[half + i], challenge) for i in range(half)])
+            self.tail = new
+            self.remaining -= 1
+
+    def finish(self) -> List[int]:
+        """the fully folded value of every multilinear (eq_ind.rs `finish`: multilinear_evals)"""
+        assert self.tail is not None and self.remaining == 0
+        return [v[0] for v in self.tail]
+
+
 def shard_units(n_units: int, world: int, rank: int) -> range:
     """contiguous block partition of independent units (NTT batch columns, sumcheck instances)"""
     per, rem = divmod(n_units, world)
