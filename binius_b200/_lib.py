@@ -29,6 +29,7 @@ SYMBOLS = [
     "b200_ntt_inverse", "b200_ntt_forward_host", "b200_ntt_inverse_host", "b200_fri_fold",
     "b200_tensor_product_full_query", "b200_fold_multilinears_high_to_low", "b200_eq_ind_round_evals",
     "b200_sumcheck_round_evals", "b200_fold_multilinears_low_to_high", "b200_zerocheck_univariate_evals", "b200_zerocheck_univariate_evals_streamed",
+    "b200_zerocheck_univariate_store_elems", "b200_zerocheck_univariate_prepare", "b200_zerocheck_univariate_finish",
 ]
 
 
@@ -123,6 +124,9 @@ def load() -> C.CDLL:
         "b200_fold_multilinears_low_to_high": (i32, [vp, P(vp), P(vp), u32, u32, P(u64), P(u64), P(u64), P(u64)]),
         "b200_zerocheck_univariate_evals": (i32, [vp, P(vp), P(u32), u32, u32, u32, vp, u64, P(vp), P(u32), u32, u32, P(u64)]),
         "b200_zerocheck_univariate_evals_streamed": (i32, [vp, P(vp), P(vp), P(u32), u32, u32, u32, vp, u64, P(vp), P(u32), u32, u32, u32, P(u64)]),
+        "b200_zerocheck_univariate_store_elems": (u64, [u32, u32, P(u32), u32]),
+        "b200_zerocheck_univariate_prepare": (i32, [vp, P(vp), P(vp), P(u32), u32, u32, u32, P(vp), P(u32), u32, u32, u32, vp, u64, P(u32)]),
+        "b200_zerocheck_univariate_finish": (i32, [vp, P(vp), P(u32), u32, u32, u32, vp, u64, P(vp), P(u32), u32, u32, vp, u64, P(u64)]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the build is stale: fail loudly

@@ -2292,8 +2292,20 @@ static uint32_t const_level(uint64_t lo, uint64_t hi) {
 // nullptr when there is nothing to compute.  The kernels XOR into the table: `zero_out` clears it first, `extend` runs the
 // (linear) domain extension afterwards -- a caller summing several sub-cube ranges clears once and extends once.  The caller copies it back (and may issue other copies first: the argument
 // blocks of this call are already queued on the copy engine).
-static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint4 **d_out_p, bool zero_out = true, bool extend = true) {
+// The two halves of the B8 fast path (b200_zerocheck_univariate_prepare / _finish, univariate.cuh k_uni_finish): mode 1 runs
+// k_uni_b8<SKIP, true> (values of the non-linear part of every composition to `store`, no challenge needed), mode 2 weights
+// the stored values by eq and adds the linear-monomial route and the domain extension.
+struct UniSplit {
+	int mode = 0;            // 0: the whole round
+	uint8_t *store = nullptr;
+	uint64_t store_bytes = 0;
+	uint64_t batch0 = 0;     // mode 1: first batch (of uni::SUBS sub-cubes) of this row chunk
+	uint64_t n_eq_full = 0;  // mode 1: sub-cubes of the whole instance (the linear-monomial route is decided as mode 2 will)
+	bool done = false;       // out: the fast path applied (otherwise nothing was launched)
+};
+static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint4 **d_out_p, bool zero_out = true, bool extend = true, UniSplit *sp = nullptr) {
 	*d_out_p = nullptr;
+	const int mode = sp ? sp->mode : 0;
 	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
 	if (n_vars - skip > 40) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars - skip_rounds must be <= 40");
 	if (n_eq != (1ull << (n_vars - skip))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectZerocheckChallengesLength: eq_ind must hold 2^(n_vars - skip_rounds) elements");
@@ -2383,7 +2395,8 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 		std::vector<uint32_t> ctab(uni::CTAB * (size_t)n_comp);
 		// coefficient-1 linear monomials leave the kernel when the sub-cube is 128 rows and the tensor-core outer product
 		// applies (univariate.cuh, k_uni_linear)
-		const bool lin_out = fast && skip == 7 && ctx->tune_uni_linear && ctx->tune_round_evals_tc && n_eq >= 8192 && n_eq % tc::CHUNK == 0;
+		const uint64_t n_eq_route = mode == 1 ? sp->n_eq_full : n_eq;
+		const bool lin_out = fast && skip == 7 && ctx->tune_uni_linear && ctx->tune_round_evals_tc && n_eq_route >= 8192 && n_eq_route % tc::CHUNK == 0;
 		std::vector<uint32_t> lin_off(n_comp + 1, 0), lin_cols;
 		std::map<uint32_t, uint32_t> lin_slot;  // column -> row of E
 		for (uint32_t c = 0; fast && c < n_comp; c++) {
@@ -2411,6 +2424,10 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 			mono.insert(mono.end(), gen.begin(), gen.end());
 			lin_off[c + 1] = (uint32_t)lin_cols.size();
 		}
+		const uint64_t rec_bytes = (uint64_t)n_comp * n_pts * uni::SUBS, n_batches_all = (n_eq + uni::SUBS - 1) / uni::SUBS;
+		if (mode && fast && ((mode == 1 ? sp->batch0 : 0) + n_batches_all) * rec_bytes > sp->store_bytes)
+			return fail(ctx, B200_ERR_INPUT_VALIDATION, "store holds %llu bytes, the prepared values need %llu", (unsigned long long)sp->store_bytes,
+						(unsigned long long)(((mode == 1 ? sp->batch0 : 0) + n_batches_all) * rec_bytes));
 		if (fast) {
 			// shared-memory layout for `ml` columns / `nc` compositions / `nm` monomials; returns the dynamic size
 			auto layout = [&](uni::B8Args &B, uint32_t ml, uint32_t nc, size_t nm) -> uint32_t {
@@ -2439,16 +2456,23 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 				B.mono = (const uint2 *)(base2 + o_m);
 				B.comp_tab = (const uint32_t *)(base2 + o_t);
 				B.m = ml, B.n_comp = nc, B.n_mono = (uint32_t)mn.size(), B.n_out = n_out;
+				B.store = mode == 1 ? sp->store + sp->batch0 * rec_bytes + (uint64_t)c0 * n_pts * uni::SUBS : nullptr;
+				B.rec_bytes = rec_bytes, B.n_pts = n_pts;
 				return B200_OK;
 			};
 			auto launch = [&](const uni::B8Args &B, uint32_t smem8) -> int32_t {
 				int32_t r;
 				const uint64_t n_batches = (n_eq + uni::SUBS - 1) / uni::SUBS;
 				dim3 grid8((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_batches, std::max(1u, (uint32_t)ctx->n_sms / gy))), gy);
-#define B200_UNI_B8(S)                                                                          \
-	case S:                                                                                     \
-		if ((r = set_smem(ctx, uni::k_uni_b8<S>, smem8))) return r;                             \
-		uni::k_uni_b8<S><<<grid8, uni::B8_THREADS, smem8, ctx->stream>>>(ctx->d_tables, B); \
+#define B200_UNI_B8(S)                                                                                    \
+	case S:                                                                                               \
+		if (mode == 1) {                                                                                  \
+			if ((r = set_smem(ctx, uni::k_uni_b8<S, true>, smem8))) return r;                             \
+			uni::k_uni_b8<S, true><<<grid8, uni::B8_THREADS, smem8, ctx->stream>>>(ctx->d_tables, B); \
+		} else {                                                                                          \
+			if ((r = set_smem(ctx, uni::k_uni_b8<S>, smem8))) return r;                                   \
+			uni::k_uni_b8<S><<<grid8, uni::B8_THREADS, smem8, ctx->stream>>>(ctx->d_tables, B);       \
+		}                                                                                                 \
 		break;
 				switch (skip) {
 					B200_UNI_B8(2)
@@ -2465,7 +2489,7 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 			const uint32_t smem8 = layout(B, m, n_comp, mono.size());
 			// (with linear monomials taken out some columns may not be referenced any more: the range planner compacts them away)
 			if (lin_slot.empty() && fits(smem8, m)) {
-				if ((rc = stage(B, A.mls, A.levels, m, 0, n_comp, mono, ctab)) || (rc = launch(B, smem8))) return rc;
+				if (mode != 2 && ((rc = stage(B, A.mls, A.levels, m, 0, n_comp, mono, ctab)) || (rc = launch(B, smem8)))) return rc;
 			} else {
 				// Too many columns for one CTA's shared memory (e.g. 153 columns at skip 7): constraints are local,
 				// so split the compositions into contiguous ranges whose referenced columns fit and launch the same
@@ -2482,7 +2506,7 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 					return fits(layout(probe, ncols, ncomp, nm_all), ncols);
 				}, ranges);
 				std::vector<std::pair<uni::B8Args, uint32_t>> staged;
-				for (size_t ri = 0; fast && ri < ranges.size(); ri++) {
+				for (size_t ri = 0; fast && mode != 2 && ri < ranges.size(); ri++) {  // (mode 2 plans only: same eligibility as mode 1)
 					const uni::SplitRange &R = ranges[ri];
 					std::vector<b200_dev_ptr> h_mls;
 					std::vector<uint32_t> h_lv;
@@ -2514,7 +2538,24 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 					if (ri + 1 < staged.size()) B200_LAUNCH_CHECK(ctx);
 				}
 			}
-			if (fast && !lin_slot.empty()) {
+			if (fast && mode == 2) {
+				// the stored values weighted by eq: composition ranges sized to the two-deep ring and the per-thread accumulators
+				const uint32_t buf_max = (227u * 1024u - FIELD_TABLE_BYTES - 16 * uni::SUBS * 32 - 4 * uni::MAX_COMP) / 2;
+				const uint32_t range = std::max(1u, std::min({n_comp, (uni::FIN_ACC * uni::B8_THREADS) / n_pts, buf_max / (n_pts * uni::SUBS)}));
+				if (range * n_pts > uni::FIN_ACC * uni::B8_THREADS || range * n_pts * uni::SUBS > buf_max) fast = false;
+				else {
+					uni::FinArgs FA;
+					FA.store = sp->store, FA.comp_pts = A.comp_pts, FA.eq = A.eq, FA.out = d_out, FA.n_sub = n_eq, FA.rec_bytes = rec_bytes;
+					FA.n_comp = n_comp, FA.n_pts = n_pts, FA.n_out = n_out, FA.range = range;
+					FA.buf_bytes = (range * n_pts * uni::SUBS + 15) & ~15u;
+					const uint32_t smem_f = FIELD_TABLE_BYTES + 16 * uni::SUBS * 32 + 4 * uni::MAX_COMP + 2 * FA.buf_bytes;
+					const uint32_t gy_f = (n_comp + range - 1) / range;
+					if ((rc = set_smem(ctx, uni::k_uni_finish, smem_f))) return rc;
+					dim3 grid_f((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_batches_all, std::max(1u, (uint32_t)ctx->n_sms / gy_f))), gy_f);
+					uni::k_uni_finish<<<grid_f, uni::B8_THREADS, smem_f, ctx->stream>>>(ctx->d_tables, FA);
+				}
+			}
+			if (fast && !lin_slot.empty() && mode != 1) {
 				B200_LAUNCH_CHECK(ctx);
 				// E_j = evaluate_partial_high of every linearly used column by eq: one job per column, ONE tensor-core launch
 				std::vector<tc::TcJob> jobs(lin_slot.size());
@@ -2532,6 +2573,13 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 				uni::LinArgs LA{(const uint32_t *)(base4 + o_lo), (const uint32_t *)(base4 + o_lc), A.comp_pts, A.lag, d_E, d_out, n_out};
 				if ((rc = set_smem(ctx, uni::k_uni_linear, FIELD_TABLE_BYTES))) return rc;
 				uni::k_uni_linear<<<n_comp, 128, FIELD_TABLE_BYTES, ctx->stream>>>(ctx->d_tables, LA);
+			}
+		}
+		if (mode) {
+			sp->done = fast;
+			if (!fast || mode == 1) {  // not a fast-path shape: nothing was launched, the caller runs the whole round instead
+				B200_LAUNCH_CHECK(ctx);
+				return B200_OK;
 			}
 		}
 		if (!fast) switch (lvl) {
@@ -2582,9 +2630,8 @@ int32_t b200_zerocheck_univariate_evals(b200_ctx *ctx, const b200_dev_ptr *mls, 
 // over sub-cubes and the domain extension is linear, so the chunks' tables add up.  The kernels of chunk c are issued
 // BEFORE the copies of chunk c + 1: their (small) argument blocks travel through the same host-to-device copy engine
 // and would otherwise queue behind 1/2^log_chunks of the witness.  Afterwards the columns are resident in mls[].
-int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *const *host_cols, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint32_t log_chunks, uint64_t *host_out) {
-	B200_LOCK(ctx);
-	B200_FLUSH(ctx);
+// (sp != nullptr: the challenge-independent half only -- b200_zerocheck_univariate_prepare -- with the same chunked upload)
+static int32_t uni_streamed(b200_ctx *ctx, const void *const *host_cols, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint32_t log_chunks, uint64_t *host_out, UniSplit *sp) {
 	if (!ctx || !host_cols || !mls || !levels) return B200_ERR_INPUT_VALIDATION;
 	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
 	if (n_eq != (1ull << (n_vars - skip))) return fail(ctx, B200_ERR_INPUT_VALIDATION, "IncorrectZerocheckChallengesLength: eq_ind must hold 2^(n_vars - skip_rounds) elements");
@@ -2595,6 +2642,7 @@ int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *cons
 		if (!host_cols[j] || !mls[j]) return fail(ctx, B200_ERR_INPUT_VALIDATION, "multilinear %u is null", j);
 		while (log_chunks && (((1ull << (n_vars - log_chunks)) << levels[j]) & 127)) log_chunks--;  // a chunk of every column is whole B128 words
 	}
+	while (sp && log_chunks && ((n_eq >> log_chunks) % uni::SUBS)) log_chunks--;  // a chunk is whole batches of the value store
 	int32_t rc = ensure_side_streams(ctx);
 	if (rc) return rc;
 	const uint32_t n_chunks = 1u << log_chunks;
@@ -2638,8 +2686,12 @@ int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *cons
 	for (uint32_t c = 0; c < n_chunks; c++) {
 		B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c & 3], 0));
 		for (uint32_t j = 0; j < m; j++) ptrs[j] = (b200_dev_ptr)((uint8_t *)mls[j] + c * bytes[j]);
-		rc = uni_issue(ctx, ptrs.data(), levels, m, n_vars - log_chunks, skip, (b200_dev_ptr)((uint4 *)eq_ind + c * sub_per_chunk), sub_per_chunk, comps, degrees, n_comp, max_domain_size, &d_out,
-					   c == 0, c + 1 == n_chunks);
+		if (sp) {
+			sp->batch0 = c * sub_per_chunk / uni::SUBS;
+			rc = (c == 0 || sp->done) ? uni_issue(ctx, ptrs.data(), levels, m, n_vars - log_chunks, skip, nullptr, sub_per_chunk, comps, degrees, n_comp, max_domain_size, &d_out, false, false, sp) : B200_OK;
+		} else
+			rc = uni_issue(ctx, ptrs.data(), levels, m, n_vars - log_chunks, skip, (b200_dev_ptr)((uint4 *)eq_ind + c * sub_per_chunk), sub_per_chunk, comps, degrees, n_comp, max_domain_size, &d_out,
+						   c == 0, c + 1 == n_chunks);
 		if (rc) {
 			cudaStreamSynchronize(ctx->s_h2d);
 			cudaStreamSynchronize(ctx->stream);
@@ -2653,5 +2705,60 @@ int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *cons
 		B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	}
 	B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[(n_chunks - 1) & 3], 0));
+	return B200_OK;
+}
+
+int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *const *host_cols, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint32_t log_chunks, uint64_t *host_out) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	return uni_streamed(ctx, host_cols, mls, levels, m, n_vars, skip, eq_ind, n_eq, comps, degrees, n_comp, max_domain_size, log_chunks, host_out, nullptr);
+}
+
+// ---- the round in two halves: everything that needs no challenge first (while the witness is uploaded / committed) -------
+uint64_t b200_zerocheck_univariate_store_elems(uint32_t n_vars, uint32_t skip, const uint32_t *degrees, uint32_t n_comp) {
+	uint32_t max_deg = 0;
+	for (uint32_t c = 0; degrees && c < n_comp; c++) max_deg = std::max(max_deg, degrees[c]);
+	if (skip > n_vars || n_vars - skip > 40 || max_deg < 2 || skip > 8) return 0;
+	const uint64_t n_batches = ((1ull << (n_vars - skip)) + uni::SUBS - 1) / uni::SUBS;
+	return (n_batches * n_comp * ((uint64_t)(max_deg - 1) << skip) * uni::SUBS + 15) / 16;
+}
+
+int32_t b200_zerocheck_univariate_prepare(b200_ctx *ctx, const void *const *host_cols, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, uint32_t log_chunks, b200_dev_ptr store, uint64_t store_elems, uint32_t *prepared) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !mls || !levels || !prepared || (n_comp && (!comps || !degrees))) return B200_ERR_INPUT_VALIDATION;
+	*prepared = 0;
+	if (skip > n_vars) return fail(ctx, B200_ERR_INPUT_VALIDATION, "TooManySkippedRounds: skip_rounds %u > n_vars %u", skip, n_vars);
+	if (m == 0) return fail(ctx, B200_ERR_INPUT_VALIDATION, "NumberOfVariablesMismatch: no multilinears");
+	if (n_vars - skip > 40) return fail(ctx, B200_ERR_INPUT_VALIDATION, "n_vars - skip_rounds must be <= 40");
+	const uint64_t n_eq = 1ull << (n_vars - skip);
+	UniSplit sp;
+	sp.mode = 1, sp.store = (uint8_t *)store, sp.store_bytes = store ? store_elems * 16 : 0, sp.n_eq_full = n_eq;
+	int32_t rc;
+	if (host_cols) rc = uni_streamed(ctx, host_cols, mls, levels, m, n_vars, skip, nullptr, n_eq, comps, degrees, n_comp, max_domain_size, log_chunks, nullptr, &sp);
+	else {
+		uint4 *d_out;
+		rc = uni_issue(ctx, mls, levels, m, n_vars, skip, nullptr, n_eq, comps, degrees, n_comp, max_domain_size, &d_out, false, false, &sp);
+	}
+	if (rc) return rc;
+	*prepared = sp.done ? 1 : 0;
+	return B200_OK;
+}
+
+int32_t b200_zerocheck_univariate_finish(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t *levels, uint32_t m, uint32_t n_vars, uint32_t skip, b200_dev_ptr eq_ind, uint64_t n_eq, const b200_expr *const *comps, const uint32_t *degrees, uint32_t n_comp, uint32_t max_domain_size, b200_dev_ptr store, uint64_t store_elems, uint64_t *host_out) {
+	B200_LOCK(ctx);
+	B200_FLUSH(ctx);
+	if (!ctx || !mls || !levels || !store || !eq_ind) return B200_ERR_INPUT_VALIDATION;
+	if (n_comp == 0 || max_domain_size == (1u << skip)) return B200_OK;
+	UniSplit sp;
+	sp.mode = 2, sp.store = (uint8_t *)store, sp.store_bytes = store_elems * 16;
+	uint4 *d_out;
+	int32_t rc = uni_issue(ctx, mls, levels, m, n_vars, skip, eq_ind, n_eq, comps, degrees, n_comp, max_domain_size, &d_out, true, true, &sp);
+	if (rc) return rc;
+	if (!sp.done) return fail(ctx, B200_ERR_INPUT_VALIDATION, "not a shape b200_zerocheck_univariate_prepare prepares (B1/B8 columns, B8 constants, monomials of degree <= 2, skip_rounds >= 2)");
+	if (!d_out) return B200_OK;
+	if (!host_out) return B200_ERR_INPUT_VALIDATION;
+	B200_CUDA(ctx, cudaMemcpyAsync(host_out, d_out, (uint64_t)n_comp * (max_domain_size - (1u << skip)) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return B200_OK;
 }

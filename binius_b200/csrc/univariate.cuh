@@ -243,9 +243,14 @@ struct B8Args {
 	uint64_t n_sub;
 	uint32_t m, n_comp, n_mono, n_out;
 	uint32_t off_nl, off_q, off_es, off_mono, off_ctab, off_cols, off_bits;  // shared-memory layout
+	// PREP (challenge-independent half of the round, see k_uni_finish): the B8 value of every (batch, composition, point) goes to
+	// store[batch][composition][point][sub-cube of the batch] instead of being weighted by eq
+	uint8_t *store;       // already offset to the first composition of this launch and the first batch of this chunk
+	uint64_t rec_bytes;   // one batch of ALL compositions: n_comp_total * n_pts * SUBS
+	uint32_t n_pts;
 };
 
-template <uint32_t SKIP>
+template <uint32_t SKIP, bool PREP = false>
 __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restrict__ g_tables, const B8Args A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	FieldTables T = load_field_tables(smem, g_tables);
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 	__syncthreads();
 	for (uint64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x) {
 		const uint64_t s0 = bt * SUBS;
-		if (tid < SUBS * 32) {
+		if (!PREP && tid < SUBS * 32) {
 			uint32_t sb = tid >> 5, e = tid & 31;
 			uint4 eqv = s0 + sb < A.n_sub ? __ldg(A.eq + s0 + sb) : u4_zero();
 			// four 32-bit planes [word][sub-cube][32]: the 16 entries of a nibble table sit in 16 distinct banks,
@@ -401,10 +406,96 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 					val[sb] ^= v;
 				}
 			}
+			if constexpr (PREP) {
+				static_assert(SUBS == 8, "one uint2 per (batch, composition, point)");
+				const uint2 w = make_uint2(val[0] | (val[1] << 8) | (val[2] << 16) | (val[3] << 24), val[4] | (val[5] << 8) | (val[6] << 16) | (val[7] << 24));
+				*reinterpret_cast<uint2 *>(A.store + bt * A.rec_bytes + ((uint64_t)c * A.n_pts + i) * SUBS) = w;
+			} else {
+				uint4 acc = u4_zero();
+#pragma unroll
+				for (uint32_t sb = 0; sb < SUBS; sb++) {
+					const uint32_t *lo = ESw + sb * 32 + (val[sb] & 15u), *hi = ESw + sb * 32 + 16 + (val[sb] >> 4);
+					acc.x ^= lo[0] ^ hi[0];
+					acc.y ^= lo[SUBS * 32] ^ hi[SUBS * 32];
+					acc.z ^= lo[2 * SUBS * 32] ^ hi[2 * SUBS * 32];
+					acc.w ^= lo[3 * SUBS * 32] ^ hi[3 * SUBS * 32];
+				}
+				accL[k] ^= acc;
+			}
+		}
+		if (more) park();
+		__syncthreads();
+	}
+	if constexpr (!PREP)
+		for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++)
+			if (i < ctabS[CTAB * c + 4]) atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, accL[k]);
+}
+
+// The challenge-dependent half of the B8 fast path.  k_uni_b8<SKIP, true> (which needs the witness and the constraints
+// but no challenge, so it can run while the witness is still being uploaded / committed) has left the B8 value
+// v[s][c][i] of every composition's non-linear part at every extrapolation point in `store`; what remains of the round is
+//     out[c][i] ^= sum_s eq[s] * v[s][c][i]
+// i.e. per batch of SUBS sub-cubes the two nibble tables eq[s]*n, eq[s]*(n<<4) per sub-cube (as in k_uni_b8) and 16
+// conflict-free gathers of four 32-bit planes per (composition, point).  The records stream from HBM through a
+// two-deep cp.async ring (one batch of a composition range = nc * n_pts * SUBS contiguous bytes).
+// grid = (batches (grid-stride), composition ranges), block = B8_THREADS
+struct FinArgs {
+	const uint8_t *store;
+	const uint32_t *comp_pts;  // device [n_comp]
+	const uint4 *eq;
+	uint4 *out;                // [n_comp][n_out] (XOR-accumulated)
+	uint64_t n_sub, rec_bytes;
+	uint32_t n_comp, n_pts, n_out, range;  // compositions per blockIdx.y
+	uint32_t buf_bytes;                     // bytes of one ring slot (>= range * n_pts * SUBS, multiple of 16)
+};
+constexpr uint32_t FIN_ACC = 32;  // (composition, point) pairs per thread: range * n_pts <= FIN_ACC * B8_THREADS
+__global__ void __launch_bounds__(B8_THREADS, 1) k_uni_finish(const uint8_t *__restrict__ g_tables, const FinArgs A) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	FieldTables T = load_field_tables(smem, g_tables);
+	uint32_t *ESw = reinterpret_cast<uint32_t *>(smem + FIELD_TABLE_BYTES);  // [word][sub-cube][32]
+	uint32_t *ptsS = ESw + 4 * SUBS * 32;                                     // [range]
+	uint8_t *buf = smem + FIELD_TABLE_BYTES + 16 * SUBS * 32 + 4 * MAX_COMP;
+	const uint32_t tid = threadIdx.x, c0 = blockIdx.y * A.range, nc = min(A.range, A.n_comp - c0), total = nc * A.n_pts;
+	for (uint32_t idx = tid; idx < nc; idx += B8_THREADS) ptsS[idx] = A.comp_pts[c0 + idx];
+	uint4 accL[FIN_ACC];
+#pragma unroll
+	for (uint32_t k = 0; k < FIN_ACC; k++) accL[k] = u4_zero();
+	const uint64_t n_batches = (A.n_sub + SUBS - 1) / SUBS;
+	const uint32_t slice = total * SUBS;  // multiple of 16: n_pts is a multiple of 4
+	const uint8_t *src0 = A.store + (uint64_t)c0 * A.n_pts * SUBS;
+	auto fetch = [&](uint64_t bt, uint32_t slot) {
+		const uint8_t *src = src0 + bt * A.rec_bytes;
+		const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + slot * A.buf_bytes);
+		for (uint32_t off = tid * 16; off < slice; off += B8_THREADS * 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	if (blockIdx.x < n_batches) fetch(blockIdx.x, 0);
+	__syncthreads();
+	uint32_t it = 0;
+	for (uint64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x, it++) {
+		const bool more = bt + gridDim.x < n_batches;
+		if (more) fetch(bt + gridDim.x, (it + 1) & 1);
+		if (tid < SUBS * 32) {
+			const uint32_t sb = tid >> 5, e = tid & 31;
+			const uint64_t s = bt * SUBS + sb;
+			const uint4 eqv = s < A.n_sub ? __ldg(A.eq + s) : u4_zero();
+			const uint4 v = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
+			ESw[tid] = v.x, ESw[SUBS * 32 + tid] = v.y, ESw[2 * SUBS * 32 + tid] = v.z, ESw[3 * SUBS * 32 + tid] = v.w;
+		}
+		if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+		else asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads();
+		const uint2 *rb = reinterpret_cast<const uint2 *>(buf + (it & 1) * A.buf_bytes);
+#pragma unroll 1
+		for (uint32_t p = tid, k = 0; p < total; p += B8_THREADS, k++) {
+			const uint32_t c = p / A.n_pts, i = p - c * A.n_pts;
+			if (i >= ptsS[c]) continue;
+			const uint2 w = rb[p];
 			uint4 acc = u4_zero();
 #pragma unroll
 			for (uint32_t sb = 0; sb < SUBS; sb++) {
-				const uint32_t *lo = ESw + sb * 32 + (val[sb] & 15u), *hi = ESw + sb * 32 + 16 + (val[sb] >> 4);
+				const uint32_t v = ((sb < 4 ? w.x : w.y) >> (8 * (sb & 3))) & 0xffu;
+				const uint32_t *lo = ESw + sb * 32 + (v & 15u), *hi = ESw + sb * 32 + 16 + (v >> 4);
 				acc.x ^= lo[0] ^ hi[0];
 				acc.y ^= lo[SUBS * 32] ^ hi[SUBS * 32];
 				acc.z ^= lo[2 * SUBS * 32] ^ hi[2 * SUBS * 32];
@@ -412,11 +503,12 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			}
 			accL[k] ^= acc;
 		}
-		if (more) park();
 		__syncthreads();
 	}
-	for (uint32_t c = g, k = 0; c < A.n_comp; c += G, k++)
-		if (i < ctabS[CTAB * c + 4]) atomic_xor_u4(A.out + (uint64_t)c * A.n_out + i, accL[k]);
+	for (uint32_t p = tid, k = 0; p < total; p += B8_THREADS, k++) {
+		const uint32_t c = p / A.n_pts, i = p - c * A.n_pts;
+		if (i < ptsS[c]) atomic_xor_u4(A.out + (uint64_t)(c0 + c) * A.n_out + i, accL[k]);
+	}
 }
 
 // Linear monomials of the B8 fast path (skip = 7, B1 columns).  sum_s eq[s] * P_j(s, x_i) is linear in the column:

@@ -200,6 +200,99 @@ def zerocheck_univariate_evals_streamed(backend: "B200Backend", host_columns: Se
     return ZerocheckUnivariateEvalsOutput([vals[c * n_out:(c + 1) * n_out] for c in range(nc)], skip_rounds, remaining, max_domain_size, eq)
 
 
+@dataclass
+class PreparedUnivariateRound:
+    """What `zerocheck_univariate_prepare` leaves behind for `zerocheck_univariate_finish`: the B8 values of every
+    composition's non-linear part on the extrapolation domain (`store`, owned by this object until `release`)."""
+    multilinears: Sequence[TransparentMultilinear]
+    compositions: Sequence[ArithCircuit]
+    skip_rounds: int
+    max_domain_size: int
+    store: Optional[DevSlice]
+    prepared: bool
+
+    def release(self, backend: "B200Backend"):
+        if self.store is not None:
+            backend._l.dev_free(self.store)
+            self.store = None
+
+
+def _uni_call_args(backend, multilinears, compositions):
+    m, nc = len(multilinears), len(compositions)
+    ptrs = (C.c_void_p * m)(*[ml.evals.ptr for ml in multilinears])
+    lvls = (C.c_uint32 * m)(*[ml.tower_level for ml in multilinears])
+    comps = (C.c_void_p * max(nc, 1))(*[backend._compiled(c)[0].handle.value for c in compositions])
+    degs = (C.c_uint32 * max(nc, 1))(*[_degree(c) for c in compositions])
+    return ptrs, lvls, comps, degs
+
+
+def zerocheck_univariate_prepare(backend: "B200Backend", multilinears: Sequence[TransparentMultilinear], compositions: Sequence[ArithCircuit],
+                                 skip_rounds: int, max_domain_size: int, host_columns: Optional[Sequence[np.ndarray]] = None,
+                                 log_chunks: int = 3) -> PreparedUnivariateRound:
+    """The challenge-independent half of `zerocheck_univariate_evals` (b200_zerocheck_univariate_prepare): sub-cube
+    extrapolations and composition values on the extrapolation domain (univariate.rs:380-470 need the witness only), run
+    BEFORE the zerocheck challenges exist -- in the reference's order (commit, then zerocheck) that is during the witness
+    upload (`host_columns`: pinned host copies, uploaded chunk by chunk into `multilinears[j].evals` as in the streamed
+    round) and the commitment.  Shapes outside the B8 fast path are left to `zerocheck_univariate_finish`'s fallback."""
+    if not multilinears:
+        raise InputValidation("NumberOfVariablesMismatch: no multilinears")
+    n_vars = multilinears[0].n_vars
+    if any(ml.n_vars != n_vars for ml in multilinears):
+        raise InputValidation("NumberOfVariablesMismatch")
+    if skip_rounds > n_vars:
+        raise InputValidation("TooManySkippedRounds")
+    degrees = [_degree(c) for c in compositions]
+    if max_domain_size < domain_size(max(degrees, default=0), skip_rounds):
+        raise InputValidation("LagrangeDomainTooSmall")
+    if max_domain_size > 256:
+        raise InputValidation("DomainSizeTooLarge")
+    if host_columns is not None:
+        if len(host_columns) != len(multilinears):
+            raise InputValidation("one host column per multilinear")
+        for ml, h in zip(multilinears, host_columns):
+            if h.nbytes < max(((1 << n_vars) << ml.tower_level) // 8, 1):
+                raise InputValidation("NumberOfVariablesMismatch")
+    L = backend._l
+    ptrs, lvls, comps, degs = _uni_call_args(backend, multilinears, compositions)
+    m, nc = len(multilinears), len(compositions)
+    n_store = int(L._lib.b200_zerocheck_univariate_store_elems(n_vars, skip_rounds, degs, nc))
+    store = L.dev_alloc(n_store) if n_store else None
+    hosts = (C.c_void_p * m)(*[h.ctypes.data for h in host_columns]) if host_columns is not None else None
+    done = C.c_uint32()
+    try:
+        L._check(L._lib.b200_zerocheck_univariate_prepare(L._ctx, hosts, ptrs, lvls, m, n_vars, skip_rounds, comps, degs, nc, max_domain_size,
+                                                          max(0, log_chunks), store.ptr if store else None, C.c_uint64(n_store), C.byref(done)))
+    except Exception:
+        if store is not None:
+            L.dev_free(store)
+        raise
+    prep = PreparedUnivariateRound(list(multilinears), list(compositions), skip_rounds, max_domain_size, store, bool(done.value))
+    if not prep.prepared:
+        prep.release(backend)
+    return prep
+
+
+def zerocheck_univariate_finish(backend: "B200Backend", prep: PreparedUnivariateRound, zerocheck_challenges: Sequence[int]) -> ZerocheckUnivariateEvalsOutput:
+    """The challenge-dependent half: weights the prepared values by the eq-indicator of `zerocheck_challenges`
+    (b200_zerocheck_univariate_finish); values identical to `zerocheck_univariate_evals`, which it calls itself when the
+    shape was not a prepared one."""
+    if not prep.prepared:
+        return zerocheck_univariate_evals(backend, prep.multilinears, prep.compositions, zerocheck_challenges, prep.skip_rounds, prep.max_domain_size)
+    n_vars, skip = prep.multilinears[0].n_vars, prep.skip_rounds
+    if len(zerocheck_challenges) != n_vars - skip:
+        raise InputValidation("IncorrectZerocheckChallengesLength")
+    L = backend._l
+    eq = backend.tensor_product_full_query(zerocheck_challenges)
+    ptrs, lvls, comps, degs = _uni_call_args(backend, prep.multilinears, prep.compositions)
+    m, nc = len(prep.multilinears), len(prep.compositions)
+    n_out = prep.max_domain_size - (1 << skip)
+    out = (C.c_uint64 * max(2 * nc * n_out, 2))()
+    L._check(L._lib.b200_zerocheck_univariate_finish(L._ctx, ptrs, lvls, m, n_vars, skip, eq.ptr, C.c_uint64(eq.len()), comps, degs, nc, prep.max_domain_size,
+                                                     prep.store.ptr, C.c_uint64(prep.store.len()), out))
+    vals = [int(out[2 * i]) | (int(out[2 * i + 1]) << 64) for i in range(nc * n_out)]
+    return ZerocheckUnivariateEvalsOutput([vals[c * n_out:(c + 1) * n_out] for c in range(nc)], skip, n_vars - skip, prep.max_domain_size, eq)
+
+
 class B200Backend:
     """ComputationBackend over one B200Layer."""
 

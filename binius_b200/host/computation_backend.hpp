@@ -380,4 +380,86 @@ inline ZerocheckUnivariateEvalsOutput zerocheck_univariate_evals_streamed(B200Ba
 	return out;
 }
 
+// The round in two halves (b200_zerocheck_univariate_prepare / _finish): `zerocheck_univariate_prepare` needs the witness and
+// the constraints but no challenge -- in the reference's order (commit, then zerocheck) it runs while the witness is uploaded
+// (host_columns non-empty: chunked upload into multilinears[j].evals as in the streamed round) and committed;
+// `zerocheck_univariate_finish` weights the prepared values by the eq-indicator of the challenges.  Values are identical to
+// zerocheck_univariate_evals, which finish calls itself for shapes prepare does not cover.
+struct PreparedUnivariateRound {
+	std::vector<SumcheckMultilinear> multilinears;
+	std::vector<const ExprEval *> compositions;
+	std::vector<uint32_t> composition_degrees;
+	uint32_t skip_rounds = 0, max_domain_size = 0;
+	DevSlice store{};
+	bool prepared = false;
+	void release(B200Backend &backend) {
+		if (store.ptr) backend.layer().dev_free(store);
+		store = DevSlice{};
+	}
+};
+
+inline PreparedUnivariateRound zerocheck_univariate_prepare(B200Backend &backend, const std::vector<const void *> &host_columns,
+															const std::vector<SumcheckMultilinear> &multilinears,
+															const std::vector<const ExprEval *> &compositions,
+															const std::vector<uint32_t> &composition_degrees, uint32_t skip_rounds,
+															uint32_t max_domain_size, uint32_t log_chunks = 3) {
+	if (multilinears.empty() || (!host_columns.empty() && host_columns.size() != multilinears.size()))
+		throw InputValidation(1, "NumberOfVariablesMismatch: one host column per multilinear");
+	const uint32_t n_vars = multilinears[0].n_vars;
+	for (auto &m : multilinears)
+		if (m.kind != SumcheckMultilinear::Transparent || m.n_vars != n_vars) throw InputValidation(1, "NumberOfVariablesMismatch");
+	if (skip_rounds > n_vars) throw InputValidation(1, "TooManySkippedRounds");
+	if (compositions.size() != composition_degrees.size()) throw InputValidation(1, "one degree per composition");
+	uint32_t max_deg = 0;
+	for (uint32_t d : composition_degrees) max_deg = std::max(max_deg, d);
+	if ((uint64_t)max_domain_size < ((uint64_t)max_deg << skip_rounds)) throw InputValidation(1, "LagrangeDomainTooSmall");
+	if (max_domain_size > 256) throw InputValidation(1, "DomainSizeTooLarge");
+	PreparedUnivariateRound p;
+	p.multilinears = multilinears, p.compositions = compositions, p.composition_degrees = composition_degrees;
+	p.skip_rounds = skip_rounds, p.max_domain_size = max_domain_size;
+	std::vector<b200_dev_ptr> ptrs;
+	std::vector<uint32_t> levels;
+	for (auto &m : multilinears) { ptrs.push_back(m.evals.ptr); levels.push_back(m.tower_level); }
+	std::vector<const b200_expr *> exprs;
+	for (auto *c : compositions) exprs.push_back(c->raw());
+	B200Layer &l = backend.layer();
+	const uint64_t n_store = b200_zerocheck_univariate_store_elems(n_vars, skip_rounds, composition_degrees.data(), (uint32_t)composition_degrees.size());
+	if (n_store) p.store = l.dev_alloc(n_store);
+	uint32_t done = 0;
+	try {
+		l.check(b200_zerocheck_univariate_prepare(l.ctx(), host_columns.empty() ? nullptr : host_columns.data(), ptrs.data(), levels.data(), (uint32_t)ptrs.size(),
+												  n_vars, skip_rounds, exprs.data(), composition_degrees.data(), (uint32_t)exprs.size(), max_domain_size, log_chunks,
+												  p.store.ptr, n_store, &done));
+	} catch (...) {
+		p.release(backend);
+		throw;
+	}
+	p.prepared = done != 0;
+	if (!p.prepared) p.release(backend);
+	return p;
+}
+
+inline ZerocheckUnivariateEvalsOutput zerocheck_univariate_finish(B200Backend &backend, const PreparedUnivariateRound &p,
+																  const std::vector<F128> &zerocheck_challenges) {
+	if (!p.prepared) return zerocheck_univariate_evals(backend, p.multilinears, p.compositions, p.composition_degrees, zerocheck_challenges, p.skip_rounds, p.max_domain_size);
+	const uint32_t n_vars = p.multilinears[0].n_vars;
+	if (zerocheck_challenges.size() != n_vars - p.skip_rounds) throw InputValidation(1, "IncorrectZerocheckChallengesLength");
+	ZerocheckUnivariateEvalsOutput out;
+	out.skip_rounds = p.skip_rounds, out.remaining_rounds = n_vars - p.skip_rounds, out.max_domain_size = p.max_domain_size;
+	out.partial_eq_ind_evals = backend.tensor_product_full_query(zerocheck_challenges);
+	std::vector<b200_dev_ptr> ptrs;
+	std::vector<uint32_t> levels;
+	for (auto &m : p.multilinears) { ptrs.push_back(m.evals.ptr); levels.push_back(m.tower_level); }
+	std::vector<const b200_expr *> exprs;
+	for (auto *c : p.compositions) exprs.push_back(c->raw());
+	const uint32_t n_out = p.max_domain_size - (1u << p.skip_rounds);
+	std::vector<F128> flat(std::max<size_t>(p.compositions.size() * n_out, 1));
+	B200Layer &l = backend.layer();
+	l.check(b200_zerocheck_univariate_finish(l.ctx(), ptrs.data(), levels.data(), (uint32_t)ptrs.size(), n_vars, p.skip_rounds, out.partial_eq_ind_evals.ptr,
+											 out.partial_eq_ind_evals.n, exprs.data(), p.composition_degrees.data(), (uint32_t)exprs.size(), p.max_domain_size,
+											 p.store.ptr, p.store.n, (uint64_t *)flat.data()));
+	for (size_t c = 0; c < p.compositions.size(); c++) out.round_evals.emplace_back(flat.begin() + c * n_out, flat.begin() + (c + 1) * n_out);
+	return out;
+}
+
 }  // namespace binius_b200

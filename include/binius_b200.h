@@ -357,6 +357,33 @@ int32_t b200_zerocheck_univariate_evals_streamed(b200_ctx *ctx, const void *cons
 												 const uint32_t *composition_degrees, uint32_t n_compositions,
 												 uint32_t max_domain_size, uint32_t log_chunks, uint64_t *host_round_evals);
 
+/* The round in two halves, so that the part which needs NO verifier challenge overlaps with the witness upload and the
+ * commitment (in the reference the zerocheck challenges are sampled after the commitment has been observed,
+ * constraint_system/prove.rs: commit -> zerocheck; the sub-cube extrapolations and the composition values on the
+ * extrapolation domain, univariate.rs:380-470, depend on the witness only).
+ *   prepare: extrapolates the columns and evaluates the non-linear part of every composition at its (deg - 1) * 2^skip
+ *            points for every sub-cube, as B8 values, into `store` (b200_zerocheck_univariate_store_elems B128 elements of
+ *            caller-owned device memory: 2^(n_vars - skip) * n_compositions * (max degree - 1) * 2^skip bytes -- 8x the
+ *            quadratically used witness bits at skip 7).  host_columns non-NULL: the columns are uploaded in
+ *            2^log_chunks row chunks on the side stream as in the streamed call above and chunk c is prepared while
+ *            chunk c + 1 is in flight; NULL: the columns are resident.  *prepared = 1 when the shape is covered
+ *            (B1/B8 columns, B8 constants, monomials of degree <= 2 with byte coefficients, skip_rounds >= 2); 0: nothing
+ *            was stored (the columns were still uploaded) and the caller runs b200_zerocheck_univariate_evals instead.
+ *   finish : out[c][i] = sum_s eq[s] * store[s][c][i] + the linear monomials (evaluate_partial_high of the column by eq on
+ *            the tensor cores) + the reference's domain extension; same arguments as b200_zerocheck_univariate_evals
+ *            plus the store; values identical to that call.  InputValidation when the shape is not a prepared one. */
+uint64_t b200_zerocheck_univariate_store_elems(uint32_t n_vars, uint32_t skip_rounds, const uint32_t *composition_degrees, uint32_t n_compositions);
+int32_t b200_zerocheck_univariate_prepare(b200_ctx *ctx, const void *const *host_columns, const b200_dev_ptr *multilins,
+										  const uint32_t *tower_levels, uint32_t n_multilins, uint32_t n_vars, uint32_t skip_rounds,
+										  const b200_expr *const *compositions, const uint32_t *composition_degrees,
+										  uint32_t n_compositions, uint32_t max_domain_size, uint32_t log_chunks,
+										  b200_dev_ptr store, uint64_t store_elems, uint32_t *prepared);
+int32_t b200_zerocheck_univariate_finish(b200_ctx *ctx, const b200_dev_ptr *multilins, const uint32_t *tower_levels,
+										 uint32_t n_multilins, uint32_t n_vars, uint32_t skip_rounds, b200_dev_ptr eq_ind, uint64_t n_eq,
+										 const b200_expr *const *compositions, const uint32_t *composition_degrees,
+										 uint32_t n_compositions, uint32_t max_domain_size, b200_dev_ptr store, uint64_t store_elems,
+										 uint64_t *host_round_evals);
+
 #ifdef __cplusplus
 }
 #endif

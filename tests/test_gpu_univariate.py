@@ -256,3 +256,87 @@ def test_streamed_round_from_a_witness_arena_with_the_linear_route(hal, oracle):
     got = zerocheck_univariate_evals_streamed(be, host_cols, dst, comps, ch, skip, 256, log_chunks)
     assert got.round_evals == exp.round_evals
     assert np.array_equal(hal.to_host(d_arena), np.array(h_arena))
+
+
+# ---- the round in two halves: prepare (no challenge) + finish (b200_zerocheck_univariate_prepare / _finish) ----
+def _two_halves(hal, oracle, cols, levels, n_vars, skip, comps, max_domain, challenges, streamed, log_chunks=2):
+    """prepare + finish against the one-call round on the same device columns; returns (two halves, one call, prepared)"""
+    from binius_b200.hal import (B200Backend, TransparentMultilinear, zerocheck_univariate_evals, zerocheck_univariate_finish,
+                                 zerocheck_univariate_prepare)
+
+    be = B200Backend(hal)
+    packed = [oracle.to_arr(pack_scalars(c, l)) if not isinstance(c, np.ndarray) else c for c, l in zip(cols, levels)]
+    if streamed:
+        mls = [TransparentMultilinear(hal.dev_alloc(len(p)), l, n_vars) for p, l in zip(packed, levels)]
+        for ml in mls:
+            hal.fill(ml.evals, 0x5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A5A)  # the upload must overwrite this
+        hosts = []
+        for p in packed:
+            h = hal.host_alloc(len(p))
+            h[:] = p
+            hosts.append(h)
+        hal.sync()
+        prep = zerocheck_univariate_prepare(be, mls, comps, skip, max_domain, host_columns=hosts, log_chunks=log_chunks)
+        for ml, p in zip(mls, packed):
+            assert np.array_equal(hal.to_host(ml.evals), p), "columns resident after the streamed prepare"
+    else:
+        mls = [TransparentMultilinear(hal.to_device(p), l, n_vars) for p, l in zip(packed, levels)]
+        prep = zerocheck_univariate_prepare(be, mls, comps, skip, max_domain)
+    prepared = prep.prepared
+    out = zerocheck_univariate_finish(be, prep, challenges)
+    prep.release(be)
+    ref = zerocheck_univariate_evals(be, mls, comps, challenges, skip, max_domain)
+    assert np.array_equal(hal.to_host(out.partial_eq_ind_evals), hal.to_host(ref.partial_eq_ind_evals))
+    return out.round_evals, ref.round_evals, prepared, packed
+
+
+@pytest.mark.parametrize("skip,n_vars,streamed", [(2, 9, False), (4, 11, True), (6, 12, False), (7, 13, True), (5, 5, False)])
+def test_prepare_finish_equals_the_one_call_round(hal, oracle, skip, n_vars, streamed):
+    """B1/B8 columns, degree-2 monomials with constants, a composition of lower degree (extended the reference's way) and a
+    linear one; a ragged last batch (n_vars - skip < 3) at skip 5; vs the one-call round AND vs the oracle."""
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import _degree
+
+    rng = random.Random(100 * skip + n_vars)
+    levels = [0, 3, 0, 0, 3]
+    cols = [[rng.getrandbits(1 << l) for _ in range(1 << n_vars)] for l in levels]
+    x, y, z, w, u = (A.var(i) for i in range(5))
+    comps = [(x + z) * (y + w) + A.constant(rng.getrandbits(8) | 1) * z, x * w + u, x + y + w, u * y + A.constant(0x1D) * (x * z) + A.constant(7)]
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    got, ref, prepared, packed = _two_halves(hal, oracle, cols, levels, n_vars, skip, comps, 2 << skip, ch, streamed)
+    assert prepared
+    assert got == ref
+    eq = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << len(ch)) - 1)), 0, ch)
+    exp = oracle.zerocheck_univariate_evals_reference(packed, levels, n_vars, skip, eq, [list(c.steps) for c in comps], [_degree(c) for c in comps], 2 << skip)
+    assert got == exp
+
+
+def test_prepare_declines_shapes_outside_the_fast_path(hal, oracle):
+    """a B32 column / a cubic composition: prepare stores nothing and finish runs the whole round itself"""
+    from binius_b200 import ArithCircuit as A
+
+    rng = random.Random(9)
+    n_vars, skip = 8, 3
+    for levels, comps in (((0, 5, 0), [A.var(0) * A.var(1) + A.var(2)]), ((0, 0, 0), [A.var(0) * A.var(1) * A.var(2)])):
+        cols = [[rng.getrandbits(1 << l) for _ in range(1 << n_vars)] for l in levels]
+        ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+        got, ref, prepared, _ = _two_halves(hal, oracle, cols, levels, n_vars, skip, comps, 3 << skip, ch, False)
+        assert not prepared
+        assert got == ref
+
+
+def test_prepare_finish_keccak_shape_2pow20_rows(hal, oracle):
+    """153 B1 columns, the 75 chi constraints, skip 7, 2^13 sub-cubes (the linear-monomial route is on): streamed prepare in 4
+    chunks + finish vs the one-call round and vs the CPU arm"""
+    from test_gpu_baseline_sizes import keccak_chi_compositions
+
+    n_vars, skip, m = 20, 7, 153
+    rng = random.Random(77)
+    cols = [oracle.rand_b128(4530 + j, (1 << n_vars) // 128) for j in range(m)]
+    comps = keccak_chi_compositions()
+    ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+    got, ref, prepared, _ = _two_halves(hal, oracle, cols, [0] * m, n_vars, skip, comps, 256, ch, True, log_chunks=2)
+    assert prepared and got == ref
+    eq = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << len(ch)) - 1)), 0, ch)
+    exp, _ = oracle.cpu_univariate_b1(cols, n_vars, skip, eq, [list(c.steps) for c in comps], 1 << skip)
+    assert got == exp

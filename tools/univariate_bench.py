@@ -35,6 +35,22 @@ for c in range(n_comp):  # keccak chi constraints out - (b0 + (b1 - 1) * b2) (st
         a, b, d, e = (A.var((2 * c + o) % m) for o in (0, 1, 5, 11))
         comps.append(a * b + d + e)
 ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
+if len(sys.argv) > 4 and sys.argv[4] == "split":  # the round in two halves (b200_zerocheck_univariate_prepare / _finish)
+    from binius_b200.hal import zerocheck_univariate_finish, zerocheck_univariate_prepare
+
+    for rep in range(3):
+        hal.sync()
+        t0 = time.perf_counter()
+        prep = zerocheck_univariate_prepare(be, mls, comps, skip, 2 << skip)
+        hal.sync()
+        t1 = time.perf_counter()
+        out = zerocheck_univariate_finish(be, prep, ch)
+        t2 = time.perf_counter()
+        print(f"n_vars={n_vars} m={m} compositions={n_comp}: prepare {1e3 * (t1 - t0):.2f} ms (resident columns), finish {1e3 * (t2 - t1):.2f} ms, "
+              f"store {prep.store.len() * 16 / 1e9:.2f} GB, nonzero={sum(1 for r in out.round_evals for v in r if v)}")
+        hal.dev_free(out.partial_eq_ind_evals)
+        prep.release(be)
+    sys.exit(0)
 for rep in range(3):
     hal.sync()
     t0 = time.perf_counter()
