@@ -8,7 +8,7 @@ cap() {  # name, kernel regex, skip, count, command...
 	python tools/ncu_summary.py /tmp/$name.ncu-rep gpurun_out/r2_${name}_ncu_full.csv
 }
 cap univariate_k_uni_finish k_uni_finish 1 1 python tools/univariate_bench.py 22 153 75 split
-cap univariate_k_uni_b8_prep 'k_uni_b8<7, true>|k_uni_b8<7u, true>|k_uni_b8.*true' 3 2 python tools/univariate_bench.py 22 153 75 split
+cap univariate_k_uni_b8_prep k_uni_b8 3 2 python tools/univariate_bench.py 22 153 75 split
 for lc in 3 4 5; do REPLAY_PASSES=2 REPLAY_LOG_CHUNKS=$lc ./tools/keccak_replay_cpp 18 > gpurun_out/s4_replay_lc$lc.json 2>&1; done
 REPLAY_PASSES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches_replay_split.csv ./tools/keccak_replay_cpp 14 > /dev/null 2>&1
 cat gpurun_out/s4_uni_split.log
