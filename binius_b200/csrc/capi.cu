@@ -27,10 +27,17 @@
 
 using namespace b200;
 
+// device copies of several expressions' steps made in one allocation and one copy (upload_exprs): freed with the last user
+struct StepSlab {
+	void *base = nullptr;
+	uint32_t refs = 0;
+};
 struct b200_expr {
 	b200_ctx *ctx = nullptr;
 	std::vector<b200_expr_step> steps;
 	b200_expr_step *d_steps = nullptr;
+	StepSlab *slab = nullptr;  // non-null: d_steps points into slab->base
+	uint64_t uid = 0;          // unique per compiled expression (keys the cached monomial plan)
 	uint32_t n_vars = 0;
 	plan::Poly poly;       // monomial expansion (eqind_plan.hpp), valid when poly_ok
 	bool poly_ok = false;  // degree <= 2 and few terms
@@ -193,8 +200,7 @@ static int32_t launch_tc_pairs(b200_ctx *ctx, std::vector<tc::TcJob> &jobs, uint
 // Monomial plan for eq-ind round evaluations at the points 1 and infinity (eqind_plan.hpp): every
 // (composition, point) sum is a coefficient-weighted combination of inner products shared between the
 // compositions; a degree-2 monomial x*y costs one elementwise product w = E . P_x per covering variable.
-static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint64_t half, b200_dev_ptr eq_ind, const b200_expr *const *comps,
-									const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, uint32_t n_points, uint32_t first_slot) {
+struct MonoPlan {
 	struct AJob {
 		uint32_t code;
 		int32_t scaled;  // -1: the eq-indicator itself, else index of the scaled vector
@@ -205,9 +211,35 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 	};
 	std::vector<AJob> ajobs;
 	std::vector<AScale> scales;
-	std::vector<tc::TcTarget> targets;
-	std::map<std::tuple<uint32_t, int32_t, int32_t>, uint32_t> job_ix;
+	std::vector<tc::TcTarget> targets;  // slots relative to the call's first slot
 	bool need_ones = false;
+};
+static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint64_t half, b200_dev_ptr eq_ind, const b200_expr *const *comps,
+									const b200_expr *const *leads, uint32_t n_comp, const uint32_t *codes, uint32_t n_points, uint32_t first_slot) {
+	typedef MonoPlan::AJob AJob;
+	typedef MonoPlan::AScale AScale;
+	// The plan depends on the expressions and the point codes only, and a prover asks for the same one every round (the
+	// greedy cover below costs ~0.3 ms of host time for the 75 chi constraints of keccak): the last plan is kept.
+	static std::mutex plan_mu;
+	static std::vector<std::pair<std::vector<uint64_t>, std::shared_ptr<const MonoPlan>>> plan_cache;  // most recent first, <= 4
+	std::vector<uint64_t> key;
+	key.reserve(2 * n_comp + n_points + 2);
+	key.push_back(n_comp), key.push_back(n_points);
+	for (uint32_t c = 0; c < n_comp; c++) key.push_back(comps[c]->uid), key.push_back(leads[c]->uid);
+	for (uint32_t p = 0; p < n_points; p++) key.push_back(codes[p]);
+	std::shared_ptr<const MonoPlan> plan;
+	{
+		std::lock_guard<std::mutex> g(plan_mu);
+		for (auto &e : plan_cache)
+			if (e.first == key) plan = e.second;
+	}
+	if (!plan) {
+	MonoPlan P;
+	std::vector<AJob> &ajobs = P.ajobs;
+	std::vector<AScale> &scales = P.scales;
+	std::vector<tc::TcTarget> &targets = P.targets;
+	std::map<std::tuple<uint32_t, int32_t, int32_t>, uint32_t> job_ix;
+	bool &need_ones = P.need_ones;
 	for (uint32_t code = 1; code <= 2; code++) {
 		std::vector<uint32_t> pts;
 		for (uint32_t p = 0; p < n_points; p++)
@@ -256,9 +288,19 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 					j = cx != cover.end() ? job(cx->second, (int32_t)t.first[1]) : job(cover.at(t.first[1]), (int32_t)t.first[0]);
 				}
 				uint64_t w[2] = {(uint64_t)t.second, (uint64_t)(t.second >> 64)};
-				for (uint32_t p : pts) targets.push_back(tc::TcTarget{j, first_slot + c * n_points + p, to_u4(w)});
+				for (uint32_t p : pts) targets.push_back(tc::TcTarget{j, c * n_points + p, to_u4(w)});
 			}
 	}
+	plan = std::make_shared<const MonoPlan>(std::move(P));
+	std::lock_guard<std::mutex> g(plan_mu);
+	plan_cache.insert(plan_cache.begin(), {key, plan});  // (a first round asks for the point at infinity only: two plans per prover)
+	if (plan_cache.size() > 4) plan_cache.pop_back();
+	}
+	const std::vector<AJob> &ajobs = plan->ajobs;
+	const std::vector<AScale> &scales = plan->scales;
+	std::vector<tc::TcTarget> targets = plan->targets;
+	for (auto &t : targets) t.slot += first_slot;
+	bool need_ones = plan->need_ones;
 	if (targets.empty()) return B200_OK;  // all compositions vanish identically: slots stay zero
 	// regular (unweighted) evaluator: E is the all-ones vector, so a "scaled" vector is the operand itself
 	// (code 1) or hi + lo (code 2, formed by the job's second pointer) and no product kernel runs
@@ -1252,12 +1294,26 @@ int32_t b200_expr_compile(b200_ctx *ctx, const b200_expr_step *steps, uint32_t n
 	e->steps.assign(steps, steps + n_steps);
 	e->n_vars = n_vars;
 	e->poly_ok = plan::expand(steps, n_steps, 2, 64, e->poly);
+	static std::atomic<uint64_t> next_uid{1};
+	e->uid = next_uid.fetch_add(1);
 	*out = e.release();
 	return B200_OK;
 }
+static std::mutex g_slab_mu;
 void b200_expr_free(b200_expr *e) {
 	if (!e) return;
-	ctx_free(e->ctx, e->d_steps);
+	if (e->slab) {
+		bool last;
+		{
+			std::lock_guard<std::mutex> g(g_slab_mu);
+			last = --e->slab->refs == 0;
+		}
+		if (last) {
+			ctx_free(e->ctx, e->slab->base);
+			delete e->slab;
+		}
+	} else
+		ctx_free(e->ctx, e->d_steps);
 	delete e;
 }
 uint32_t b200_expr_n_vars(const b200_expr *e) { return e ? e->n_vars : 0; }
@@ -1276,6 +1332,37 @@ static DevExpr dev_expr(const b200_expr *e) {
 		}
 	}
 	return DevExpr{m->d_steps, (uint32_t)m->steps.size(), m->n_vars};
+}
+// First use of MANY expressions by one call (75 compositions + 75 leading terms of a keccak zerocheck round: 150 x
+// (cudaMalloc + synchronous copy) = 1.1 ms): one allocation, one copy.  Failures are left to dev_expr / B200_EXPR_READY.
+static void upload_exprs(std::initializer_list<std::pair<const b200_expr *const *, uint32_t>> lists) {
+	std::vector<b200_expr *> todo;
+	size_t n_steps = 0;
+	for (auto &l : lists)
+		for (uint32_t c = 0; l.first && c < l.second; c++) {
+			b200_expr *m = const_cast<b200_expr *>(l.first[c]);
+			if (m && !m->d_steps && !m->steps.empty() && std::find(todo.begin(), todo.end(), m) == todo.end()) {
+				todo.push_back(m);
+				n_steps += m->steps.size();
+			}
+		}
+	if (todo.size() < 2) return;
+	std::vector<b200_expr_step> host;
+	host.reserve(n_steps);
+	for (b200_expr *m : todo) host.insert(host.end(), m->steps.begin(), m->steps.end());
+	void *base = nullptr;
+	if (cudaMalloc(&base, sizeof(b200_expr_step) * n_steps) != cudaSuccess || cudaMemcpy(base, host.data(), sizeof(b200_expr_step) * n_steps, cudaMemcpyHostToDevice) != cudaSuccess) {
+		cudaGetLastError();
+		if (base) cudaFree(base);
+		return;
+	}
+	StepSlab *slab = new StepSlab{base, (uint32_t)todo.size()};
+	size_t off = 0;
+	for (b200_expr *m : todo) {
+		m->d_steps = reinterpret_cast<b200_expr_step *>(base) + off;
+		m->slab = slab;
+		off += m->steps.size();
+	}
 }
 #define B200_EXPR_READY(ctx, de) \
 	if ((de).n_steps && !(de).steps) return fail(ctx, B200_ERR_ALLOC, "out of device memory (expression steps)")
@@ -1666,6 +1753,7 @@ int32_t b200_sumcheck_round_evals(b200_ctx *ctx, uint32_t order, const b200_dev_
 		if (ok) return eq_ind_monomial_plan(ctx, mls, half, eq_ind, comps, leads, n_comp, codes, n_points, *first_slot);
 	}
 	// the interpreter kernels read the steps on the device (uploaded on first use)
+	upload_exprs({{comps, n_comp}, {leads, n_comp}});
 	std::vector<DevExpr> hc(n_comp), hl(n_comp);
 	for (uint32_t c = 0; c < n_comp; c++) {
 		hc[c] = dev_expr(comps[c]);
@@ -1767,6 +1855,7 @@ int32_t b200_sumcheck_tail_start(b200_ctx *ctx, const b200_dev_ptr *mls, uint32_
 	}
 	t->h_mb = ctx->h_tail_mb, t->d_mb = ctx->d_tail_mb;
 	memset(t->h_mb, 0, bytes);  // every slot is validated by its complement: zero = not there yet
+	upload_exprs({{comps, n_comp}, {leads, n_comp}});
 	std::vector<DevExpr> hc(n_comp), hl(n_comp);
 	std::vector<uint32_t> step_off(2 * n_comp + 1, 0);
 	for (uint32_t c = 0; c < n_comp; c++) {
@@ -2344,6 +2433,7 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 		std::vector<uint8_t> ext;
 		std::map<uint32_t, uint32_t> ext_of_deg;
 		bool need_ext = false;
+		upload_exprs({{comps, n_comp}});
 		for (uint32_t c = 0; c < n_comp; c++) {
 			hc[c] = dev_expr(comps[c]);
 			B200_EXPR_READY(ctx, hc[c]);
@@ -2669,6 +2759,7 @@ static int32_t uni_streamed(b200_ctx *ctx, const void *const *host_cols, const b
 		return B200_OK;
 	};
 	std::vector<b200_dev_ptr> ptrs(m);
+	upload_exprs({{comps, n_comp}});
 	for (uint32_t c = 0; c < n_comp; c++)  // the lazy device copies of the expressions go first, while the copy engine is idle
 		if (comps[c]) {
 			DevExpr de = dev_expr(comps[c]);

@@ -243,19 +243,33 @@ int main(int argc, char **argv) {
 			}
 			std::vector<F128> q(nv - 1);
 			for (auto &x : q) x = rnd();
-			DevSlice eq = be.tensor_product_full_query(q);
+			// REPLAY_ZC_TAIL=1: the persistent sumcheck kernel takes the rounds with <= 2^20 (composition, point, index) triples,
+			// the last 13 of the 20.  Off by default: with 75 compositions its start-up (1.2 ms) outweighs what
+			// the 13 small rounds cost through separate calls (1.0 ms); it pays for few compositions (config #3)
+			B200Backend be_zc(hal, getenv("REPLAY_ZC_TAIL") && atoi(getenv("REPLAY_ZC_TAIL")) == 1);
+			DevSlice eq = be_zc.tensor_product_full_query(q);
+			// wall clock (no events / device syncs inside the loop: the persistent kernel owns the stream while it runs); the
+			// round-evaluation call is synchronous, the fold calls return after queueing, so the split is by host time
+			hal.check(b200_sync(hal.ctx()));
+			const uint64_t l0 = b200_ctx_launch_count(hal.ctx());
 			for (uint32_t rnd_i = 0; rnd_i < nv; rnd_i++) {
 				const uint32_t v = nv - rnd_i;
 				std::vector<SumcheckEvaluator> evs;
 				for (uint32_t c = 0; c < 75; c++) evs.push_back(SumcheckEvaluator{&comps[c], &leads[c], rnd_i == 0 ? 2u : 1u, 3u});
-				t.start();
-				be.sumcheck_compute_round_evals(EvaluationOrder::HighToLow, v, nullptr, mls, evs, &eq, {});
-				zc_ev += t.stop(&launches);
-				t.start();
-				be.sumcheck_fold_multilinears(EvaluationOrder::HighToLow, v, mls, rnd(), nullptr);
-				if (v > 1) eq = be.fold_partial_eq_ind(EvaluationOrder::HighToLow, v - 1, eq);
-				zc_fold += t.stop(&launches);
+				auto w0 = std::chrono::steady_clock::now();
+				be_zc.sumcheck_compute_round_evals(EvaluationOrder::HighToLow, v, nullptr, mls, evs, &eq, {});
+				auto w1 = std::chrono::steady_clock::now();
+				be_zc.sumcheck_fold_multilinears(EvaluationOrder::HighToLow, v, mls, rnd(), nullptr);
+				if (v > 1) eq = be_zc.fold_partial_eq_ind(EvaluationOrder::HighToLow, v - 1, eq);
+				if (rnd_i + 1 == nv) hal.check(b200_sync(hal.ctx()));
+				auto w2 = std::chrono::steady_clock::now();
+				zc_ev += std::chrono::duration<double, std::milli>(w1 - w0).count();
+				zc_fold += std::chrono::duration<double, std::milli>(w2 - w1).count();
+				if (getenv("REPLAY_ZC_TRACE") && pass == 1)
+					fprintf(stderr, "zerocheck round %2u (v = %2u): round evals %.3f ms, fold calls %.3f ms\n", rnd_i, v,
+							std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w2 - w1).count());
 			}
+			launches += b200_ctx_launch_count(hal.ctx()) - l0;
 		}
 		// ---- PIOP bivariate sumcheck: 200 multilinears, 100 pairs
 		{
