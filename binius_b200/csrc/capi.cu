@@ -393,7 +393,7 @@ struct CtxGuard {
 	do {                                                  \
 		if ((ctx) && (ctx)->tail_active)                  \
 			return b200::fail(ctx, B200_ERR_INPUT_VALIDATION, "a persistent sumcheck tail owns the stream: only b200_sumcheck_tail_* calls until it is finished"); \
-		if ((ctx) && !(ctx)->pending.empty()) {           \
+		if ((ctx) && (!(ctx)->pending.empty() || !(ctx)->pending_fr.empty())) { \
 			int32_t rc__ = flush_pending(ctx);            \
 			if (rc__) return rc__;                        \
 		}                                                 \
@@ -482,6 +482,7 @@ int32_t b200_ctx_create(int32_t device, b200_ctx **out) {
 	SET(k_inner_product, FIELD_TABLE_BYTES);
 	SET(k_fold_mat<false>, FIELD_TABLE_BYTES);
 	SET(k_fold_right_lut, LUT_BYTES + 2048);
+	SET(k_fold_right_lut_multi, LUT_BYTES + 2048);
 	SET(k_fold_left_b1_lut, LUT_BYTES + 2048);
 	SET(k_linear_map, LUT_BYTES + 2048);
 	SET(k_fold_mat<true>, FIELD_TABLE_BYTES);
@@ -542,7 +543,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
 		g_live.erase(ctx);
 	}
 	cudaSetDevice(ctx->device);
-	if (!ctx->pending.empty()) flush_pending(ctx);
+	if (!ctx->pending.empty() || !ctx->pending_fr.empty()) flush_pending(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_tables);
 	if (ctx->d_groestl_t0) cudaFree(ctx->d_groestl_t0);
@@ -573,7 +574,7 @@ void *b200_ctx_stream(b200_ctx *ctx) {
 	// a caller that orders its own work on the stream must see every queued fold launched
 	if (!ctx) return nullptr;
 	B200_LOCK(ctx);
-	if (!ctx->pending.empty()) flush_pending(ctx);
+	if (!ctx->pending.empty() || !ctx->pending_fr.empty()) flush_pending(ctx);
 	return (void *)ctx->stream;
 }
 int32_t b200_flush(b200_ctx *ctx) {
@@ -887,7 +888,7 @@ int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_
 		// RAW / WAW on a pending output, or WAR on a pending input
 		conflict = overlap(w0, bytes, p.e0, pb) || overlap(r0, bytes, p.e0, pb) || overlap(w0, bytes, p.e1, pb);
 	}
-	if (conflict) B200_FLUSH(ctx);
+	if (conflict || !ctx->pending_fr.empty()) B200_FLUSH(ctx);
 	ctx->pending_z[0] = z[0];
 	ctx->pending_z[1] = z[1];
 	ctx->pending.push_back(b200_pending_lerp{w0, r0, n0});
@@ -896,6 +897,23 @@ int32_t b200_extrapolate_line(b200_ctx *ctx, b200_dev_ptr e0, uint64_t n0, b200_
 
 }  // extern "C"
 static int32_t flush_pending(b200_ctx *ctx) {
+	if (!ctx->pending_fr.empty()) {
+		std::vector<FrSeg> fs(ctx->pending_fr.size());
+		for (size_t i = 0; i < fs.size(); i++) fs[i] = FrSeg{(const uint4 *)ctx->pending_fr[i].mat, (uint4 *)ctx->pending_fr[i].out};
+		ctx->pending_fr.clear();
+		const uint64_t n_out = ctx->pending_fr_n_out;
+		if (fs.size() == 1) {
+			k_fold_right_lut<<<grid_for(ctx, n_out, FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>(fs[0].mat, ctx->pending_fr_lvl, (const uint4 *)ctx->pending_fr_vec, fs[0].out, n_out);
+		} else {
+			void *d_segs;
+			int32_t rc = stage_args(ctx, fs.data(), sizeof(FrSeg) * fs.size(), &d_segs);
+			if (rc) return rc;
+			k_fold_right_lut_multi<<<grid_for(ctx, n_out * fs.size(), FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>(
+				(const FrSeg *)d_segs, (uint32_t)fs.size(), ilog2(n_out), ctx->pending_fr_lvl, (const uint4 *)ctx->pending_fr_vec);
+		}
+		B200_LAUNCH_CHECK(ctx);
+		if (ctx->pending.empty()) return B200_OK;
+	}
 	std::vector<LerpSeg> segs(ctx->pending.size());
 	for (size_t i = 0; i < segs.size(); i++) {
 		const b200_pending_lerp &p = ctx->pending[i];
@@ -1116,8 +1134,25 @@ int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t
 
 static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_mat, uint32_t lvl, b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out) {
 	B200_LOCK(ctx);
-	B200_FLUSH(ctx);
 	if (!ctx) return B200_ERR_INPUT_VALIDATION;
+	// the byte-LUT fold_right is deferred like extrapolate_line: calls with the same query on disjoint buffers are batched
+	const bool lut_right = right && valid_level(lvl) && is_pow2(n_mat) && is_pow2(n_vec) && (n_vec << lvl) == 128 && n_out >= 1024 && n_out == n_mat;
+	if (lut_right && !ctx->pending_fr.empty() && ctx->pending.empty() && !ctx->tail_active && ctx->pending_fr_vec == vec && ctx->pending_fr_lvl == lvl &&
+		ctx->pending_fr_n_out == n_out && ctx->pending_fr.size() < 4096) {
+		const uint8_t *m8 = (const uint8_t *)mat, *o8 = (const uint8_t *)out, *v8 = (const uint8_t *)vec;
+		const uint64_t bytes = n_out * 16;
+		auto overlap = [](const uint8_t *a, uint64_t an, const uint8_t *b, uint64_t bn) { return a < b + bn && b < a + an; };
+		bool conflict = overlap(o8, bytes, v8, n_vec * 16) || (m8 != o8 && overlap(m8, bytes, o8, bytes));
+		for (size_t i = 0; i < ctx->pending_fr.size() && !conflict; i++) {
+			const b200_pending_fold_right &p = ctx->pending_fr[i];
+			conflict = overlap(o8, bytes, p.out, bytes) || overlap(m8, bytes, p.out, bytes) || overlap(o8, bytes, p.mat, bytes);
+		}
+		if (!conflict) {
+			ctx->pending_fr.push_back(b200_pending_fold_right{m8, (uint8_t *)out});
+			return B200_OK;
+		}
+	}
+	B200_FLUSH(ctx);
 	if (lvl > 7) return fail(ctx, B200_ERR_INPUT_VALIDATION, "invalid evals: tower_level=%u > 7", lvl);
 	if (!valid_level(lvl)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "unsupported tower level %u", lvl);
 	if (!is_pow2(n_mat)) return fail(ctx, B200_ERR_INPUT_VALIDATION, "the length of `mat` must be a power of 2");
@@ -1127,6 +1162,13 @@ static int32_t fold_mat(b200_ctx *ctx, bool right, b200_dev_ptr mat, uint64_t n_
 	uint64_t expect_out = 1ull << (log_evals - log_q);
 	if (n_out != expect_out) return fail(ctx, B200_ERR_INPUT_VALIDATION, "output has %llu elements, expected %llu", (unsigned long long)n_out, (unsigned long long)expect_out);
 	if (right && (n_vec << lvl) == 128 && n_out >= 1024) {
+		const uint8_t *m8 = (const uint8_t *)mat, *o8 = (const uint8_t *)out, *v8 = (const uint8_t *)vec;
+		const bool self_ok = !(o8 < v8 + n_vec * 16 && v8 < o8 + n_out * 16) && (m8 == o8 || !(m8 < o8 + n_out * 16 && o8 < m8 + n_out * 16));
+		if (self_ok) {  // first of a possible batch: launched by the next other entry point (or a conflicting fold)
+			ctx->pending_fr.push_back(b200_pending_fold_right{m8, (uint8_t *)out});
+			ctx->pending_fr_vec = vec, ctx->pending_fr_lvl = lvl, ctx->pending_fr_n_out = n_out;
+			return B200_OK;
+		}
 		k_fold_right_lut<<<grid_for(ctx, n_out, FOLD_THREADS, 2), FOLD_THREADS, LUT_BYTES + 2048, ctx->stream>>>((const uint4 *)mat, lvl, (const uint4 *)vec, (uint4 *)out, n_out);
 		B200_LAUNCH_CHECK(ctx);
 		return B200_OK;

@@ -20,6 +20,14 @@ struct b200_pending_lerp {
 	uint64_t n;
 };
 
+// one deferred fold_right of the byte-LUT route (see fold_mat): consecutive calls with the SAME query (the projection of
+// every witness column onto the rounds after the univariate skip, prove/zerocheck.rs:416-434) go out as one launch that
+// builds the query's table once per CTA instead of once per CTA and column
+struct b200_pending_fold_right {
+	const uint8_t *mat;
+	uint8_t *out;
+};
+
 // one recorded KernelExecutor op of an open kernel scope (b200_kernel_scope_begin .. _end)
 struct b200_expr;
 struct b200_trace_op {
@@ -58,6 +66,10 @@ struct b200_ctx {
 	uint64_t launches = 0;
 	std::vector<b200_pending_lerp> pending;
 	uint64_t pending_z[2] = {0, 0};
+	std::vector<b200_pending_fold_right> pending_fr;  // never non-empty together with `pending`
+	const void *pending_fr_vec = nullptr;
+	uint32_t pending_fr_lvl = 0;
+	uint64_t pending_fr_n_out = 0;
 
 	// field tables (64 KiB B8 product table + 256 B times-X_2 table), device global memory
 	uint8_t *d_tables = nullptr;

@@ -348,6 +348,30 @@ __global__ void __launch_bounds__(FOLD_THREADS, 2) k_fold_right_lut(const uint4 
 		out[i] = lut_apply(tbl, L, __ldg(mat + i));
 }
 
+// several matrices folded by the same query in one launch (the table is built once per CTA): n_out = 2^log_n_out each
+struct FrSeg {
+	const uint4 *mat;
+	uint4 *out;
+};
+__global__ void __launch_bounds__(FOLD_THREADS, 2) k_fold_right_lut_multi(const FrSeg *__restrict__ segs, uint32_t n_segs, uint32_t log_n_out, uint32_t lvl,
+																		 const uint4 *__restrict__ vec) {
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *tbl = smem;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + LUT_BYTES);
+	for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) stage[(i & 7) * 16 + (i >> 3)] = basis_image(__ldg(vec + (i >> lvl)), i & ((1u << lvl) - 1));
+	__syncthreads();
+	lut_build_images(tbl, stage);
+	const LutLane L = lut_lane_init();
+	const uint64_t total = (uint64_t)n_segs << log_n_out, mask = (1ull << log_n_out) - 1;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t sg = (uint32_t)(i >> log_n_out);
+		const uint64_t j = i & mask;
+		const uint4 *m = reinterpret_cast<const uint4 *>(__ldg(reinterpret_cast<const unsigned long long *>(&segs[sg].mat)));
+		uint4 *o = reinterpret_cast<uint4 *>(__ldg(reinterpret_cast<const unsigned long long *>(&segs[sg].out)));
+		o[j] = lut_apply(tbl, L, __ldg(m + j));
+	}
+}
+
 // out[i] = L(in[i]) for a GF(2)-linear map L: B128 -> B128 given by its 128 basis images W[k] = L(beta_k)
 // (FieldLinearTransformation::transform, field/src/linear_transformation.rs; the tower <-> POLYVAL basis change of
 // convert_witnesses_to_fast_ext, core/src/constraint_system/prove.rs:291-292, with the tables of field/src/polyval.rs:

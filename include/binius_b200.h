@@ -130,7 +130,10 @@ int32_t b200_tensor_expand(b200_ctx *ctx, b200_dev_ptr data, uint64_t data_len, 
 /* inner_product (layer.rs:247-267; cpu/layer.rs:205-236): a = SubfieldSlice{a, tower_level} */
 int32_t b200_inner_product(b200_ctx *ctx, b200_dev_ptr a, uint64_t n_a, uint32_t tower_level,
 						   b200_dev_ptr b, uint64_t n_b, uint32_t *result_slot);
-/* fold_left / fold_right (layer.rs:298-356; cpu/layer.rs:238-280, 574-675) */
+/* fold_left / fold_right (layer.rs:298-356; cpu/layer.rs:238-280, 574-675).
+ * fold_right with vec.len() * 2^tower_level == 128 (one output per matrix element: the projection of a packed column
+ * by 128 / 2^level coefficients, prove/zerocheck.rs:416-434) is deferred like extrapolate_line: consecutive calls with the
+ * same `vec` on disjoint buffers go out as ONE launch when any other entry point (or a conflicting fold) arrives. */
 int32_t b200_fold_left(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t tower_level,
 					   b200_dev_ptr vec, uint64_t n_vec, b200_dev_ptr out, uint64_t n_out);
 int32_t b200_fold_right(b200_ctx *ctx, b200_dev_ptr mat, uint64_t n_mat, uint32_t tower_level,

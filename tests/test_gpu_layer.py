@@ -631,3 +631,34 @@ def test_one_layer_from_several_host_threads(hal, oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_fold_right_same_query_batches_and_keeps_order(hal, oracle):
+    """fold_right by a 128-coefficient query over B1 matrices is deferred: calls sharing the query go out as one launch
+    (launch_count), a call that reads an earlier output or uses another query flushes first; values vs the oracle."""
+    import binius_b200
+
+    S = binius_b200.SubfieldSlice
+    n = 1 << 11
+    q1, q2 = oracle.rand_b128(9001, 128), oracle.rand_b128(9002, 128)
+    mats = [oracle.rand_b128(9100 + j, n) for j in range(5)]
+    dq1, dq2 = hal.to_device(q1), hal.to_device(q2)
+    dm = [hal.to_device(m) for m in mats]
+    outs = [hal.dev_alloc(n) for _ in range(6)]
+    hal.sync()
+    before = hal.launch_count()
+
+    def op(ex):
+        for j in range(4):
+            ex.fold_right(S(dm[j], 0), dq1, outs[j])        # one batch of four
+        ex.fold_right(S(outs[0], 0), dq1, outs[4])          # reads an output of the batch: flush, then a new batch
+        ex.fold_right(S(dm[4], 0), dq2, outs[5])            # another query: flush
+        return []
+
+    hal.execute(op)
+    hal.sync()
+    assert hal.launch_count() - before == 3
+    for j in range(4):
+        assert _same(hal.to_host(outs[j]), oracle.fold_right(mats[j], 0, q1, n))
+    assert _same(hal.to_host(outs[4]), oracle.fold_right(oracle.fold_right(mats[0], 0, q1, n), 0, q1, n))
+    assert _same(hal.to_host(outs[5]), oracle.fold_right(mats[4], 0, q2, n))
