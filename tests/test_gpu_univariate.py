@@ -340,3 +340,47 @@ def test_prepare_finish_keccak_shape_2pow20_rows(hal, oracle):
     eq = oracle.tensor_expand(oracle.to_arr([1] + [0] * ((1 << len(ch)) - 1)), 0, ch)
     exp, _ = oracle.cpu_univariate_b1(cols, n_vars, skip, eq, [list(c.steps) for c in comps], 1 << skip)
     assert got == exp
+
+
+def test_prepare_finish_error_classes(hal, oracle):
+    """store too small -> InputValidation from prepare and from finish; finish on a shape prepare does not cover ->
+    InputValidation; wrong number of challenges -> IncorrectZerocheckChallengesLength (Python mirror)"""
+    import ctypes as C
+
+    import binius_b200
+    from binius_b200 import ArithCircuit as A
+    from binius_b200.hal import (B200Backend, TransparentMultilinear, _uni_call_args, zerocheck_univariate_finish, zerocheck_univariate_prepare)
+
+    be = B200Backend(hal)
+    rng = random.Random(5)
+    n_vars, skip = 10, 4
+    cols = [[rng.getrandbits(1) for _ in range(1 << n_vars)] for _ in range(3)]
+    mls = [TransparentMultilinear(hal.to_device(oracle.to_arr(pack_scalars(c, 0))), 0, n_vars) for c in cols]
+    comps = [A.var(0) * A.var(1) + A.var(2)]
+    L = hal
+    ptrs, lvls, cps, degs = _uni_call_args(be, mls, comps)
+    need = int(L._lib.b200_zerocheck_univariate_store_elems(n_vars, skip, degs, 1))
+    assert need == ((1 << (n_vars - skip)) * 1 * (1 << skip)) // 16
+    small = hal.dev_alloc(max(need - 1, 1))
+    done = C.c_uint32()
+    with pytest.raises(binius_b200.InputValidation):
+        L._check(L._lib.b200_zerocheck_univariate_prepare(L._ctx, None, ptrs, lvls, 3, n_vars, skip, cps, degs, 1, 2 << skip, 0, small.ptr, C.c_uint64(small.len()), C.byref(done)))
+    eq = be.tensor_product_full_query([rng.getrandbits(128) for _ in range(n_vars - skip)])
+    out = (C.c_uint64 * (2 * (1 << skip)))()
+    with pytest.raises(binius_b200.InputValidation):
+        L._check(L._lib.b200_zerocheck_univariate_finish(L._ctx, ptrs, lvls, 3, n_vars, skip, eq.ptr, C.c_uint64(eq.len()), cps, degs, 1, 2 << skip, small.ptr,
+                                                         C.c_uint64(small.len()), out))
+    # a cubic composition is not a prepared shape: the C entry point refuses, the mirror falls back to the one-call round
+    cubic = [A.var(0) * A.var(1) * A.var(2)]
+    p2, l2, c2, d2 = _uni_call_args(be, mls, cubic)
+    big = hal.dev_alloc(4 * need + 16)
+    out3 = (C.c_uint64 * (2 * (2 << skip)))()
+    with pytest.raises(binius_b200.InputValidation):
+        L._check(L._lib.b200_zerocheck_univariate_finish(L._ctx, p2, l2, 3, n_vars, skip, eq.ptr, C.c_uint64(eq.len()), c2, d2, 1, 3 << skip, big.ptr, C.c_uint64(big.len()), out3))
+    prep = zerocheck_univariate_prepare(be, mls, comps, skip, 2 << skip)
+    assert prep.prepared
+    with pytest.raises(binius_b200.InputValidation):
+        zerocheck_univariate_finish(be, prep, [1, 2, 3])
+    prep.release(be)
+    for d in (small, big, eq):
+        hal.dev_free(d)
