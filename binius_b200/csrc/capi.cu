@@ -2672,7 +2672,7 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 			}
 			if (fast && mode == 2) {
 				// the stored values weighted by eq: composition ranges sized to the two-deep ring and the per-thread accumulators
-				const uint32_t buf_max = (227u * 1024u - FIELD_TABLE_BYTES - 16 * uni::SUBS * 32 - 4 * uni::MAX_COMP) / 2;
+				const uint32_t buf_max = ((227u * 1024u - FIELD_TABLE_BYTES - uni::FIN_ES_BYTES - 4 * uni::MAX_COMP) / 2) & ~15u;
 				const uint32_t range = std::max(1u, std::min({n_comp, (uni::FIN_ACC * uni::B8_THREADS) / n_pts, buf_max / (n_pts * uni::SUBS)}));
 				if (range * n_pts > uni::FIN_ACC * uni::B8_THREADS || range * n_pts * uni::SUBS > buf_max) fast = false;
 				else {
@@ -2680,7 +2680,7 @@ static int32_t uni_issue(b200_ctx *ctx, const b200_dev_ptr *mls, const uint32_t 
 					FA.store = sp->store, FA.comp_pts = A.comp_pts, FA.eq = A.eq, FA.out = d_out, FA.n_sub = n_eq, FA.rec_bytes = rec_bytes;
 					FA.n_comp = n_comp, FA.n_pts = n_pts, FA.n_out = n_out, FA.range = range;
 					FA.buf_bytes = (range * n_pts * uni::SUBS + 15) & ~15u;
-					const uint32_t smem_f = FIELD_TABLE_BYTES + 16 * uni::SUBS * 32 + 4 * uni::MAX_COMP + 2 * FA.buf_bytes;
+					const uint32_t smem_f = FIELD_TABLE_BYTES + uni::FIN_ES_BYTES + 4 * uni::MAX_COMP + 2 * FA.buf_bytes;
 					const uint32_t gy_f = (n_comp + range - 1) / range;
 					if ((rc = set_smem(ctx, uni::k_uni_finish, smem_f))) return rc;
 					dim3 grid_f((uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_batches_all, std::max(1u, (uint32_t)ctx->n_sms / gy_f))), gy_f);

@@ -92,6 +92,15 @@ __device__ __forceinline__ uint32_t f_mul8x4(const FieldTables &T, uint32_t a, u
 __device__ __forceinline__ uint32_t f_mul16x2(const FieldTables &T, uint32_t a, uint32_t s) {
 	return f_mul16(T, s, a & 0xffff) | (f_mul16(T, s, a >> 16) << 16);
 }
+// B128 x B8 with a WARP-UNIFORM B128 operand and a per-lane B8 scalar (the eq-indicator tables of the univariate-skip
+// round: entry e of a table is eq * e): the uniform bytes pick the table row, so the lanes of a warp read one 256-byte
+// row (<= 2-way conflicts) instead of 32 rows in the same bank.
+__device__ __forceinline__ uint32_t f_mul8x4_uniform(const FieldTables &T, uint32_t a, uint32_t s) {
+	return f_mul8(T, a & 0xff, s) | (f_mul8(T, (a >> 8) & 0xff, s) << 8) | (f_mul8(T, (a >> 16) & 0xff, s) << 16) | (f_mul8(T, a >> 24, s) << 24);
+}
+__device__ __forceinline__ uint4 f_mul128_b8_uniform(const FieldTables &T, uint4 a, uint32_t s) {
+	return make_uint4(f_mul8x4_uniform(T, a.x, s), f_mul8x4_uniform(T, a.y, s), f_mul8x4_uniform(T, a.z, s), f_mul8x4_uniform(T, a.w, s));
+}
 // (the scalar s, often warp-uniform, goes first: see f_mul8)
 __device__ __forceinline__ uint4 f_mul128_sub(const FieldTables &T, uint4 a, uint4 s, uint32_t lvl) {
 	switch (lvl) {

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_b8(const uint8_t *__restr
 			uint4 eqv = s0 + sb < A.n_sub ? __ldg(A.eq + s0 + sb) : u4_zero();
 			// four 32-bit planes [word][sub-cube][32]: the 16 entries of a nibble table sit in 16 distinct banks,
 			// so the gathers of phase B are conflict-free whatever the values (an LDS.128 gather is not)
-			const uint4 v = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
+			const uint4 v = f_mul128_b8_uniform(T, eqv, e < 16 ? e : (e - 16) << 4);  // (eq[s] is uniform in the warp, the entry varies)
 			ESw[tid] = v.x, ESw[SUBS * 32 + tid] = v.y, ESw[2 * SUBS * 32 + tid] = v.z, ESw[3 * SUBS * 32 + tid] = v.w;
 		}
 		const uint64_t s = s0 + a_sb;
@@ -448,13 +448,17 @@ struct FinArgs {
 	uint32_t n_comp, n_pts, n_out, range;  // compositions per blockIdx.y
 	uint32_t buf_bytes;                     // bytes of one ring slot (>= range * n_pts * SUBS, multiple of 16)
 };
-constexpr uint32_t FIN_ACC = 32;  // (composition, point) pairs per thread: range * n_pts <= FIN_ACC * B8_THREADS
+constexpr uint32_t FIN_ACC = 10;  // (composition, point) pairs per thread, accumulators in registers: range * n_pts <= FIN_ACC * B8_THREADS
+// The 64 value bits of a batch (8 sub-cubes x 8 bits) are cut into 13 groups of 5 bits (the last one 4): a 32-entry table of
+// 32-bit planes is one row of the 32 banks, so its gathers are conflict-free whatever the indices -- like the 16-entry
+// nibble tables of k_uni_b8, with 13 instead of 16 gathers per plane.
+constexpr uint32_t FIN_GROUPS = 13, FIN_ES_BYTES = 4 * FIN_GROUPS * 32 * 4;
 __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_finish(const uint8_t *__restrict__ g_tables, const FinArgs A) {
 	extern __shared__ __align__(128) uint8_t smem[];
 	FieldTables T = load_field_tables(smem, g_tables);
-	uint32_t *ESw = reinterpret_cast<uint32_t *>(smem + FIELD_TABLE_BYTES);  // [word][sub-cube][32]
-	uint32_t *ptsS = ESw + 4 * SUBS * 32;                                     // [range]
-	uint8_t *buf = smem + FIELD_TABLE_BYTES + 16 * SUBS * 32 + 4 * MAX_COMP;
+	uint32_t *ESw = reinterpret_cast<uint32_t *>(smem + FIELD_TABLE_BYTES);  // [word][group][32]
+	uint32_t *ptsS = ESw + FIN_ES_BYTES / 4;                                  // [range]
+	uint8_t *buf = smem + FIELD_TABLE_BYTES + FIN_ES_BYTES + 4 * MAX_COMP;
 	const uint32_t tid = threadIdx.x, c0 = blockIdx.y * A.range, nc = min(A.range, A.n_comp - c0), total = nc * A.n_pts;
 	for (uint32_t idx = tid; idx < nc; idx += B8_THREADS) ptsS[idx] = A.comp_pts[c0 + idx];
 	uint4 accL[FIN_ACC];
@@ -475,37 +479,50 @@ __global__ void __launch_bounds__(B8_THREADS, 1) k_uni_finish(const uint8_t *__r
 	for (uint64_t bt = blockIdx.x; bt < n_batches; bt += gridDim.x, it++) {
 		const bool more = bt + gridDim.x < n_batches;
 		if (more) fetch(bt + gridDim.x, (it + 1) & 1);
-		if (tid < SUBS * 32) {
-			const uint32_t sb = tid >> 5, e = tid & 31;
-			const uint64_t s = bt * SUBS + sb;
-			const uint4 eqv = s < A.n_sub ? __ldg(A.eq + s) : u4_zero();
-			const uint4 v = f_mul128_sub(T, eqv, make_uint4(e < 16 ? e : (e - 16) << 4, 0, 0, 0), 3);
-			ESw[tid] = v.x, ESw[SUBS * 32 + tid] = v.y, ESw[2 * SUBS * 32 + tid] = v.z, ESw[3 * SUBS * 32 + tid] = v.w;
+		if (tid < FIN_GROUPS * 32) {
+			// entry e of group g = sum of eq[sub-cube of bit 5g+k] * 2^((5g+k) mod 8) over the set bits k of e: the group's bits lie
+			// in at most two sub-cubes, so it is two B128 x B8 products
+			const uint32_t g = tid >> 5, e = tid & 31, b0 = 5 * g, sb0 = b0 >> 3, o0 = b0 & 7;
+			const uint32_t in0 = min(8u - o0, 5u);  // bits of the group that belong to the first sub-cube
+			const uint64_t s0 = bt * SUBS + sb0;
+			const uint4 eq0 = s0 < A.n_sub ? __ldg(A.eq + s0) : u4_zero();
+			uint4 v = f_mul128_b8_uniform(T, eq0, (e & ((1u << in0) - 1)) << o0);  // (eq is uniform in the warp, the entry varies)
+			if (in0 < 5 && sb0 + 1 < SUBS) {
+				const uint4 eq1 = s0 + 1 < A.n_sub ? __ldg(A.eq + s0 + 1) : u4_zero();
+				v ^= f_mul128_b8_uniform(T, eq1, e >> in0);
+			}
+			ESw[tid] = v.x, ESw[FIN_GROUPS * 32 + tid] = v.y, ESw[2 * FIN_GROUPS * 32 + tid] = v.z, ESw[3 * FIN_GROUPS * 32 + tid] = v.w;
 		}
 		if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
 		else asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncthreads();
 		const uint2 *rb = reinterpret_cast<const uint2 *>(buf + (it & 1) * A.buf_bytes);
-#pragma unroll 1
-		for (uint32_t p = tid, k = 0; p < total; p += B8_THREADS, k++) {
+#pragma unroll
+		for (uint32_t k = 0; k < FIN_ACC; k++) {  // fully unrolled: accL stays in registers
+			const uint32_t p = tid + k * B8_THREADS;
+			if (p >= total) break;
 			const uint32_t c = p / A.n_pts, i = p - c * A.n_pts;
 			if (i >= ptsS[c]) continue;
 			const uint2 w = rb[p];
 			uint4 acc = u4_zero();
 #pragma unroll
-			for (uint32_t sb = 0; sb < SUBS; sb++) {
-				const uint32_t v = ((sb < 4 ? w.x : w.y) >> (8 * (sb & 3))) & 0xffu;
-				const uint32_t *lo = ESw + sb * 32 + (v & 15u), *hi = ESw + sb * 32 + 16 + (v >> 4);
-				acc.x ^= lo[0] ^ hi[0];
-				acc.y ^= lo[SUBS * 32] ^ hi[SUBS * 32];
-				acc.z ^= lo[2 * SUBS * 32] ^ hi[2 * SUBS * 32];
-				acc.w ^= lo[3 * SUBS * 32] ^ hi[3 * SUBS * 32];
+			for (uint32_t g = 0; g < FIN_GROUPS; g++) {
+				const uint32_t b0 = 5 * g;
+				const uint32_t ix = (b0 + 5 <= 32 ? w.x >> b0 : b0 >= 32 ? w.y >> (b0 - 32) : __funnelshift_r(w.x, w.y, b0)) & 31u;
+				const uint32_t *e = ESw + g * 32 + ix;
+				acc.x ^= e[0];
+				acc.y ^= e[FIN_GROUPS * 32];
+				acc.z ^= e[2 * FIN_GROUPS * 32];
+				acc.w ^= e[3 * FIN_GROUPS * 32];
 			}
 			accL[k] ^= acc;
 		}
 		__syncthreads();
 	}
-	for (uint32_t p = tid, k = 0; p < total; p += B8_THREADS, k++) {
+#pragma unroll
+	for (uint32_t k = 0; k < FIN_ACC; k++) {
+		const uint32_t p = tid + k * B8_THREADS;
+		if (p >= total) break;
 		const uint32_t c = p / A.n_pts, i = p - c * A.n_pts;
 		if (i < ptsS[c]) atomic_xor_u4(A.out + (uint64_t)(c0 + c) * A.n_out + i, accL[k]);
 	}
@@ -540,7 +557,7 @@ __global__ void __launch_bounds__(128) k_uni_linear(const uint8_t *__restrict__ 
 	for (uint32_t i = t; i < n_in; i += 128) {
 		const uint8_t *row = A.lag + (uint64_t)i * 128;
 		uint4 acc = u4_zero();
-		for (uint32_t u = 0; u < 128; u++) acc ^= f_mul128_sub(T, Ec[u], make_uint4(row[u], 0, 0, 0), 3);
+		for (uint32_t u = 0; u < 128; u++) acc ^= f_mul128_b8_uniform(T, Ec[u], row[u]);  // (Ec[u] is uniform in the warp, the coefficient varies)
 		A.out[(uint64_t)c * A.n_out + i] ^= acc;  // the only writer of this element in this launch; stream-ordered after k_uni_b8
 	}
 }
@@ -565,7 +582,7 @@ __global__ void __launch_bounds__(256) k_uni_extend(const uint8_t *__restrict__ 
 	const uint8_t *E = A.ext + A.ext_off[c];
 	for (uint32_t i = n_in + threadIdx.x; i < A.n_out; i += blockDim.x) {
 		uint4 acc = u4_zero();
-		for (uint32_t t = 0; t < n_in; t++) acc ^= f_mul128_sub(T, row[t], make_uint4(E[(uint64_t)(i - n_in) * n_in + t], 0, 0, 0), 3);
+		for (uint32_t t = 0; t < n_in; t++) acc ^= f_mul128_b8_uniform(T, row[t], E[(uint64_t)(i - n_in) * n_in + t]);  // (row[t] is uniform in the warp)
 		row[i] = acc;
 	}
 }
