@@ -247,24 +247,37 @@ static int32_t eq_ind_monomial_plan(b200_ctx *ctx, const b200_dev_ptr *mls, uint
 		if (pts.empty()) continue;
 		auto poly = [&](uint32_t c) -> const plan::Poly & { return code == 1 ? comps[c]->poly : leads[c]->poly; };
 		// greedy vertex cover of the degree-2 monomial graph; covering variables get scaled by E
-		std::set<std::pair<uint32_t, uint32_t>> left;
+		std::vector<std::pair<uint32_t, uint32_t>> left;
+		uint32_t n_var = 0;
 		for (uint32_t c = 0; c < n_comp; c++)
 			for (auto &t : poly(c))
-				if (t.first.size() == 2) left.insert({t.first[0], t.first[1]});
+				if (t.first.size() == 2) {
+					left.push_back({t.first[0], t.first[1]});
+					n_var = std::max(n_var, std::max(t.first[0], t.first[1]) + 1);
+				}
+		std::sort(left.begin(), left.end());
+		left.erase(std::unique(left.begin(), left.end()), left.end());
 		std::map<uint32_t, int32_t> cover;
+		std::vector<uint32_t> cnt(n_var, 0);
+		for (auto &e : left) {
+			cnt[e.first]++;
+			if (e.second != e.first) cnt[e.second]++;
+		}
 		while (!left.empty()) {
-			std::map<uint32_t, uint32_t> cnt;
-			for (auto &e : left) {
-				cnt[e.first]++;
-				if (e.second != e.first) cnt[e.second]++;
-			}
-			uint32_t best = cnt.begin()->first;
-			for (auto &kv : cnt)
-				if (kv.second > cnt[best]) best = kv.first;
+			uint32_t best = 0;
+			for (uint32_t v = 1; v < n_var; v++)
+				if (cnt[v] > cnt[best]) best = v;  // the lowest index among the most frequent variables
 			cover[best] = (int32_t)scales.size();
 			scales.push_back(AScale{code, best});
-			for (auto it = left.begin(); it != left.end();)
-				it = (it->first == best || it->second == best) ? left.erase(it) : std::next(it);
+			size_t keep = 0;
+			for (auto &e : left) {
+				if (e.first == best || e.second == best) {
+					cnt[e.first]--;
+					if (e.second != e.first) cnt[e.second]--;
+				} else
+					left[keep++] = e;
+			}
+			left.resize(keep);
 		}
 		auto job = [&](int32_t scaled, int32_t y) {
 			auto key = std::make_tuple(code, scaled, y);
