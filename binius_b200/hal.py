@@ -210,11 +210,12 @@ class PreparedUnivariateRound:
     max_domain_size: int
     store: Optional[DevSlice]
     prepared: bool
+    owns_store: bool = True
 
     def release(self, backend: "B200Backend"):
-        if self.store is not None:
+        if self.store is not None and self.owns_store:
             backend._l.dev_free(self.store)
-            self.store = None
+        self.store = None
 
 
 def _uni_call_args(backend, multilinears, compositions):
@@ -228,7 +229,7 @@ def _uni_call_args(backend, multilinears, compositions):
 
 def zerocheck_univariate_prepare(backend: "B200Backend", multilinears: Sequence[TransparentMultilinear], compositions: Sequence[ArithCircuit],
                                  skip_rounds: int, max_domain_size: int, host_columns: Optional[Sequence[np.ndarray]] = None,
-                                 log_chunks: int = 3) -> PreparedUnivariateRound:
+                                 log_chunks: int = 3, arena_store: Optional[DevSlice] = None) -> PreparedUnivariateRound:
     """The challenge-independent half of `zerocheck_univariate_evals` (b200_zerocheck_univariate_prepare): sub-cube
     extrapolations and composition values on the extrapolation domain (univariate.rs:380-470 need the witness only), run
     BEFORE the zerocheck challenges exist -- in the reference's order (commit, then zerocheck) that is during the witness
@@ -256,17 +257,24 @@ def zerocheck_univariate_prepare(backend: "B200Backend", multilinears: Sequence[
     ptrs, lvls, comps, degs = _uni_call_args(backend, multilinears, compositions)
     m, nc = len(multilinears), len(compositions)
     n_store = int(L._lib.b200_zerocheck_univariate_store_elems(n_vars, skip_rounds, degs, nc))
-    store = L.dev_alloc(n_store) if n_store else None
+    # the value store: a slice of the caller's device arena when given, else an allocation this object owns
+    if arena_store is not None:
+        if arena_store.len() < n_store:
+            raise InputValidation("the store slice is smaller than b200_zerocheck_univariate_store_elems")
+        store = arena_store.slice(0, n_store) if n_store else None
+    else:
+        store = L.dev_alloc(n_store) if n_store else None
+    owns = arena_store is None
     hosts = (C.c_void_p * m)(*[h.ctypes.data for h in host_columns]) if host_columns is not None else None
     done = C.c_uint32()
     try:
         L._check(L._lib.b200_zerocheck_univariate_prepare(L._ctx, hosts, ptrs, lvls, m, n_vars, skip_rounds, comps, degs, nc, max_domain_size,
                                                           max(0, log_chunks), store.ptr if store else None, C.c_uint64(n_store), C.byref(done)))
     except Exception:
-        if store is not None:
+        if store is not None and owns:
             L.dev_free(store)
         raise
-    prep = PreparedUnivariateRound(list(multilinears), list(compositions), skip_rounds, max_domain_size, store, bool(done.value))
+    prep = PreparedUnivariateRound(list(multilinears), list(compositions), skip_rounds, max_domain_size, store, bool(done.value), owns)
     if not prep.prepared:
         prep.release(backend)
     return prep

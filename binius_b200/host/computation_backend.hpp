@@ -391,9 +391,9 @@ struct PreparedUnivariateRound {
 	std::vector<uint32_t> composition_degrees;
 	uint32_t skip_rounds = 0, max_domain_size = 0;
 	DevSlice store{};
-	bool prepared = false;
+	bool prepared = false, owns_store = true;
 	void release(B200Backend &backend) {
-		if (store.ptr) backend.layer().dev_free(store);
+		if (store.ptr && owns_store) backend.layer().dev_free(store);
 		store = DevSlice{};
 	}
 };
@@ -402,7 +402,7 @@ inline PreparedUnivariateRound zerocheck_univariate_prepare(B200Backend &backend
 															const std::vector<SumcheckMultilinear> &multilinears,
 															const std::vector<const ExprEval *> &compositions,
 															const std::vector<uint32_t> &composition_degrees, uint32_t skip_rounds,
-															uint32_t max_domain_size, uint32_t log_chunks = 3) {
+															uint32_t max_domain_size, uint32_t log_chunks = 3, const DevSlice *arena_store = nullptr) {
 	if (multilinears.empty() || (!host_columns.empty() && host_columns.size() != multilinears.size()))
 		throw InputValidation(1, "NumberOfVariablesMismatch: one host column per multilinear");
 	const uint32_t n_vars = multilinears[0].n_vars;
@@ -424,7 +424,13 @@ inline PreparedUnivariateRound zerocheck_univariate_prepare(B200Backend &backend
 	for (auto *c : compositions) exprs.push_back(c->raw());
 	B200Layer &l = backend.layer();
 	const uint64_t n_store = b200_zerocheck_univariate_store_elems(n_vars, skip_rounds, composition_degrees.data(), (uint32_t)composition_degrees.size());
-	if (n_store) p.store = l.dev_alloc(n_store);
+	// the value store comes from the caller's device arena when given (ComputeHolder's bump allocator, compute/src/alloc.rs),
+	// else from a device allocation this object owns
+	if (arena_store) {
+		if (arena_store->n < n_store) throw InputValidation(1, "the store slice is smaller than b200_zerocheck_univariate_store_elems");
+		p.store = arena_store->slice(0, n_store), p.owns_store = false;
+	} else if (n_store)
+		p.store = l.dev_alloc(n_store);
 	uint32_t done = 0;
 	try {
 		l.check(b200_zerocheck_univariate_prepare(l.ctx(), host_columns.empty() ? nullptr : host_columns.data(), ptrs.data(), levels.data(), (uint32_t)ptrs.size(),

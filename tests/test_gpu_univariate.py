@@ -281,7 +281,9 @@ def _two_halves(hal, oracle, cols, levels, n_vars, skip, comps, max_domain, chal
             assert np.array_equal(hal.to_host(ml.evals), p), "columns resident after the streamed prepare"
     else:
         mls = [TransparentMultilinear(hal.to_device(p), l, n_vars) for p, l in zip(packed, levels)]
-        prep = zerocheck_univariate_prepare(be, mls, comps, skip, max_domain)
+        arena = hal.dev_alloc(1 << 16)  # the store as a slice of caller-owned memory (4 x what the largest case here needs)
+        prep = zerocheck_univariate_prepare(be, mls, comps, skip, max_domain, arena_store=arena)
+        assert not prep.owns_store
     prepared = prep.prepared
     out = zerocheck_univariate_finish(be, prep, challenges)
     prep.release(be)

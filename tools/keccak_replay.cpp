@@ -127,6 +127,8 @@ int main(int argc, char **argv) {
 		for (uint64_t i = 0; i < n_cols * col_words * 2; i++) w[i] = splitmix();
 	}
 	DevSlice d_wit = hal.dev_alloc(n_cols * col_words);
+	// the value store of the prepared univariate round: arena memory like the witness and the codeword (allocated once, outside the passes)
+	DevSlice uni_store = hal.dev_alloc(b200_zerocheck_univariate_store_elems(uni_vars, uni_skip, std::vector<uint32_t>(75, 2).data(), 75));
 	// pass 0 warms the context; of the measured passes the one with the smallest total is reported (wall-clock phases
 	// on a shared host: single samples of the streamed round varied 59..65 ms between identical runs)
 	const int n_pass = getenv("REPLAY_PASSES") ? std::max(1, atoi(getenv("REPLAY_PASSES"))) : 3;
@@ -183,7 +185,7 @@ int main(int argc, char **argv) {
 			// challenge-independent half of the round (sub-cube extrapolations + composition values, 8 bytes per 8 sub-cubes,
 			// composition and point) prepared chunk by chunk behind it ...
 			auto w2 = std::chrono::steady_clock::now();
-			prep = zerocheck_univariate_prepare(be, h_cols, cols, cp, deg, uni_skip, 256, getenv("REPLAY_LOG_CHUNKS") ? atoi(getenv("REPLAY_LOG_CHUNKS")) : 5);
+			prep = zerocheck_univariate_prepare(be, h_cols, cols, cp, deg, uni_skip, 256, getenv("REPLAY_LOG_CHUNKS") ? atoi(getenv("REPLAY_LOG_CHUNKS")) : 5, &uni_store);
 			hal.check(b200_sync(hal.ctx()));
 			uni_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w2).count();
 			if (!prep.prepared) {
