@@ -387,9 +387,12 @@ static void ctx_free(b200_ctx *ctx, void *p) {
 struct CtxGuard {
 	b200_ctx *c;
 	int prev = -1;
-	explicit CtxGuard(b200_ctx *ctx) : c(ctx) {
+	// recording = true: an entry point that only RECORDS while a kernel scope is open (decl_value / sum / add / local: ~600
+	// calls per round of the PIOP sumcheck) -- it touches no device state then, so the device switch is skipped
+	explicit CtxGuard(b200_ctx *ctx, bool recording = false) : c(ctx) {
 		if (!c) return;
 		c->mu.lock();
+		if (recording && c->tracing && c->pending.empty() && c->pending_fr.empty()) return;  // (a queued fold would be launched by the call)
 		if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
 		if (prev != c->device) cudaSetDevice(c->device);
 		else prev = -1;
@@ -402,6 +405,7 @@ struct CtxGuard {
 	CtxGuard(const CtxGuard &) = delete;
 };
 #define B200_LOCK(ctx) CtxGuard guard__(ctx)
+#define B200_LOCK_REC(ctx) CtxGuard guard__(ctx, true)
 #define B200_FLUSH(ctx)                                  \
 	do {                                                  \
 		if ((ctx) && (ctx)->tail_active)                  \
@@ -1592,7 +1596,7 @@ static int32_t run_trace(b200_ctx *ctx) {
 				it = job_ix.emplace(key, (uint32_t)jobs.size()).first;
 				jobs.push_back(tc::TcJob{(const uint4 *)o[0], (const uint4 *)o[1], (const uint4 *)o[2], (const uint4 *)o[3]});
 			}
-			const hostf::u128 wgt = hostf::mul128(cf, t.second);
+			const hostf::u128 wgt = t.second == 1 ? cf : hostf::mul128(cf, t.second);  // (a host-side tower product is ~0.3 us)
 			uint64_t w[2] = {(uint64_t)wgt, (uint64_t)(wgt >> 64)};
 			if (wgt) targets.push_back(tc::TcTarget{it->second, op.slot, to_u4(w)});
 		}
@@ -1629,7 +1633,7 @@ int32_t b200_kernel_scope_begin(b200_ctx *ctx) {
 	return B200_OK;
 }
 int32_t b200_kernel_local(b200_ctx *ctx, uint32_t log_size, b200_dev_ptr *out) {
-	B200_LOCK(ctx);
+	B200_LOCK_REC(ctx);
 	if (!ctx || !out) return B200_ERR_INPUT_VALIDATION;
 	if (!ctx->tracing) return fail(ctx, B200_ERR_INPUT_VALIDATION, "b200_kernel_local outside a kernel scope");
 	if (log_size > 40) return fail(ctx, B200_ERR_INPUT_VALIDATION, "Local buffer too large");
@@ -1643,6 +1647,7 @@ int32_t b200_kernel_local(b200_ctx *ctx, uint32_t log_size, b200_dev_ptr *out) {
 		}
 	// chunks are never moved or freed before the context dies: pointers handed out earlier stay valid
 	const uint64_t want = std::max<uint64_t>(bytes, 64ull << 20);
+	CtxGuard device_now(ctx);  // (the pool grows: this path does need the context's device)
 	void *p = nullptr;
 	if (cudaMalloc(&p, want) != cudaSuccess) {
 		cudaGetLastError();
@@ -1670,7 +1675,7 @@ int32_t b200_kernel_scope_end(b200_ctx *ctx) {
 }
 
 int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *slot) {
-	B200_LOCK(ctx);
+	B200_LOCK_REC(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !slot) return B200_ERR_INPUT_VALIDATION;
 	int32_t rc = new_slot(ctx, slot);
@@ -1684,7 +1689,7 @@ int32_t b200_kernel_decl_value(b200_ctx *ctx, const uint64_t init[2], uint32_t *
 	return kernel_decl_now(ctx, init, *slot);
 }
 int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inputs, uint32_t n_inputs, uint64_t row_len, const b200_expr *expr, const uint64_t coeff[2], uint32_t slot) {
-	B200_LOCK(ctx);
+	B200_LOCK_REC(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || !expr) return B200_ERR_INPUT_VALIDATION;
 	if (slot >= ctx->n_results) return fail(ctx, B200_ERR_INPUT_VALIDATION, "value slot %u not declared", slot);
@@ -1700,7 +1705,7 @@ int32_t b200_kernel_sum_composition_evals(b200_ctx *ctx, const b200_dev_ptr *inp
 	return kernel_sum_now(ctx, inputs, n_inputs, row_len, expr, coeff, slot);
 }
 int32_t b200_kernel_add(b200_ctx *ctx, uint32_t log_len, b200_dev_ptr a, b200_dev_ptr b, b200_dev_ptr dst) {
-	B200_LOCK(ctx);
+	B200_LOCK_REC(ctx);
 	B200_FLUSH(ctx);
 	if (!ctx || log_len > 60) return B200_ERR_INPUT_VALIDATION;
 	if (ctx->tracing) {

@@ -314,6 +314,7 @@ int main(int argc, char **argv) {
 				// the literal accumulate_kernels closure of v3::calculate_round_evals (bivariate_product.rs:343-405) through a kernel
 				// scope: sums over the high halves, add(lo, hi) into the Locals, sums over the Locals
 				const uint64_t half = 1ull << (v - 1);
+				auto h0 = std::chrono::steady_clock::now();
 				hal.check(b200_kernel_scope_begin(hal.ctx()));
 				std::vector<b200_dev_ptr> his(m), infs(m);
 				for (uint32_t i = 0; i < m; i++) {
@@ -331,10 +332,16 @@ int main(int argc, char **argv) {
 				for (uint32_t i = 0; i < m; i++) hal.check(b200_kernel_add(hal.ctx(), v - 1, ptrs[i], his[i], infs[i]));
 				hal.check(b200_kernel_decl_value(hal.ctx(), &zero.lo, &s2));
 				for (uint32_t c = 0; c < 100; c++) hal.check(b200_kernel_sum_composition_evals(hal.ctx(), infs.data(), m, half, pair_exprs[c].raw(), &pws[c].lo, s2));
+				auto h1 = std::chrono::steady_clock::now();
 				hal.check(b200_kernel_scope_end(hal.ctx()));
+				auto h2 = std::chrono::steady_clock::now();
 				uint32_t slots[2] = {s1, s2};
 				F128 out[2];
 				hal.check(b200_results_fetch(hal.ctx(), slots, 2, &out[0].lo));
+				if (getenv("REPLAY_PIOP_TRACE") && pass == 1)
+					fprintf(stderr, "PIOP round %2u: recording %.3f ms, scope_end (match + launch) %.3f ms, fetch (device time left) %.3f ms\n", rnd_i,
+							std::chrono::duration<double, std::milli>(h1 - h0).count(), std::chrono::duration<double, std::milli>(h2 - h1).count(),
+							std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h2).count());
 				pi_ev += t.stop(&launches);
 				t.start();
 				be.sumcheck_fold_multilinears(EvaluationOrder::HighToLow, v, mls, rnd(), nullptr);
