@@ -19,6 +19,11 @@ gadget m3/src/gadgets/hash/keccak/stacked.rs):
               in one launch; the reference's skip for this constraint degree is 7)
 What is NOT replayed (out of scope, stays on the host in the reference): witness generation,
 GKR grand product / exponentiation, evalcheck, Merkle hashing, transcript.
+
+NOTE: the figures the bench line and the documents report come from the COMPILED replay, tools/keccak_replay.cpp, which
+has since grown the phases this Python version lacks -- witness upload with the univariate-skip round prepared behind it
+(skip 7), Merkle commit, univariate finish, the projection onto the remaining rounds -- and runs them in the reference's
+order.  This file remains as the Python-mirror view of the sumcheck / NTT / FRI phases (host overhead of the mirror).
 """
 import argparse
 import json
