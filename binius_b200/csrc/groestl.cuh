@@ -83,6 +83,23 @@ __device__ __forceinline__ void compress(uint32_t (&hh)[8], uint32_t (&hl)[8], c
 	}
 }
 
+// the same with Q(m) given: a block that consists of padding only is identical for every leaf, so is its Q
+__device__ __forceinline__ void compress_q_known(uint32_t (&hh)[8], uint32_t (&hl)[8], const uint32_t (&m)[16], const uint32_t (&qh)[8],
+												 const uint32_t (&ql)[8], const uint8_t *tbl) {
+	uint32_t ph[8], pl[8];
+#pragma unroll
+	for (int c = 0; c < 8; c++) {
+		ph[c] = hh[c] ^ bswap(m[2 * c]);
+		pl[c] = hl[c] ^ bswap(m[2 * c + 1]);
+	}
+	permutation<false>(ph, pl, tbl);
+#pragma unroll
+	for (int c = 0; c < 8; c++) {
+		hh[c] ^= ph[c] ^ qh[c];
+		hl[c] ^= pl[c] ^ ql[c];
+	}
+}
+
 // T_0 (256 x 8 bytes, {lo, hi}) from global memory -> 4 rotated tables x 16 replicas in shared memory;
 // returns the lane's replica (byte offset lane % 16 * 8)
 __device__ __forceinline__ const uint8_t *load_tables(uint8_t *smem, const uint2 *__restrict__ t0) {
@@ -103,6 +120,19 @@ __global__ void __launch_bounds__(THREADS) k_groestl_leaves(const uint2 *__restr
 	const uint8_t *tbl = load_tables(smem, t0);
 	const uint32_t n_full = leaf_bytes / 64, rem = leaf_bytes % 64;
 	const uint64_t n_blocks = (uint64_t)n_full + (rem <= 55 ? 1 : 2);
+	// The last block is padding only when the leaf ends on a block boundary (0x80, zeros, block count) or when the padding
+	// spills into a block of its own (zeros, block count): the same block for every leaf, so Q of it is computed once per
+	// thread instead of once per leaf -- one of the 11 permutations of a 256-byte leaf (codeword cosets of 16 elements).
+	const bool pad_only = rem == 0 || rem > 55;
+	uint32_t mpad[16], cqh[8], cql[8];
+#pragma unroll
+	for (int q = 0; q < 14; q++) mpad[q] = 0;
+	if (rem == 0) mpad[0] = 0x80u;
+	mpad[14] = bswap((uint32_t)(n_blocks >> 32));
+	mpad[15] = bswap((uint32_t)n_blocks);
+#pragma unroll
+	for (int c = 0; c < 8; c++) cqh[c] = bswap(mpad[2 * c]), cql[c] = bswap(mpad[2 * c + 1]);
+	if (pad_only) permutation<true>(cqh, cql, tbl);
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_leaves; i += (uint64_t)gridDim.x * blockDim.x) {
 		const uint4 *src = data + i * (leaf_bytes / 16);
 		uint32_t hh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, hl[8] = {0, 0, 0, 0, 0, 0, 0, 0x100};  // IV: 256 as a big-endian u64 in the last column
@@ -126,17 +156,15 @@ __global__ void __launch_bounds__(THREADS) k_groestl_leaves(const uint2 *__restr
 			const uint32_t w = rem / 4;  // rem is a multiple of 16: the 0x80 byte starts word w
 			if (w < 16) m[w] = 0x80u;
 		}
-		if (rem <= 55) {
+		if (rem == 0) {
+			compress_q_known(hh, hl, mpad, cqh, cql, tbl);
+		} else if (rem <= 55) {
 			m[14] = bswap((uint32_t)(n_blocks >> 32));
 			m[15] = bswap((uint32_t)n_blocks);
 			compress(hh, hl, m, tbl);
 		} else {
 			compress(hh, hl, m, tbl);
-#pragma unroll
-			for (int q = 0; q < 14; q++) m[q] = 0;
-			m[14] = bswap((uint32_t)(n_blocks >> 32));
-			m[15] = bswap((uint32_t)n_blocks);
-			compress(hh, hl, m, tbl);
+			compress_q_known(hh, hl, mpad, cqh, cql, tbl);
 		}
 		// output transformation: last 32 bytes of P(h) ^ h
 		uint32_t ph[8], pl[8];
