@@ -292,10 +292,11 @@ def _two_halves(hal, oracle, cols, levels, n_vars, skip, comps, max_domain, chal
     return out.round_evals, ref.round_evals, prepared, packed
 
 
-@pytest.mark.parametrize("skip,n_vars,streamed", [(2, 9, False), (4, 11, True), (6, 12, False), (7, 13, True), (5, 5, False)])
+@pytest.mark.parametrize("skip,n_vars,streamed", [(2, 9, False), (4, 11, True), (6, 12, False), (7, 13, True), (5, 5, False), (4, 8, True)])
 def test_prepare_finish_equals_the_one_call_round(hal, oracle, skip, n_vars, streamed):
     """B1/B8 columns, degree-2 monomials with constants, a composition of lower degree (extended the reference's way) and a
-    linear one; a ragged last batch (n_vars - skip < 3) at skip 5; vs the one-call round AND vs the oracle."""
+    linear one; a ragged last batch (n_vars - skip < 3) at skip 5; at (4, 8) the requested chunking (4 chunks of 4 sub-cubes)
+    is coarsened to whole batches of the store; vs the one-call round AND vs the oracle."""
     from binius_b200 import ArithCircuit as A
     from binius_b200.hal import _degree
 
@@ -319,7 +320,8 @@ def test_prepare_declines_shapes_outside_the_fast_path(hal, oracle):
 
     rng = random.Random(9)
     n_vars, skip = 8, 3
-    for levels, comps in (((0, 5, 0), [A.var(0) * A.var(1) + A.var(2)]), ((0, 0, 0), [A.var(0) * A.var(1) * A.var(2)])):
+    for levels, comps in (((0, 5, 0), [A.var(0) * A.var(1) + A.var(2)]), ((0, 0, 0), [A.var(0) * A.var(1) * A.var(2)]),
+                          ((0, 3, 0), [A.var(0) + A.var(1) + A.var(2)])):  # (linear only: nothing to extrapolate)
         cols = [[rng.getrandbits(1 << l) for _ in range(1 << n_vars)] for l in levels]
         ch = [rng.getrandbits(128) for _ in range(n_vars - skip)]
         got, ref, prepared, _ = _two_halves(hal, oracle, cols, levels, n_vars, skip, comps, 3 << skip, ch, False)
